@@ -1,0 +1,284 @@
+/*
+ * bsched.h — C ABI of the B200 gang-scheduling feasibility engine.
+ *
+ * This is the drop-in boundary for the PreFilter / Permit / Less hot path of
+ * tenstack/batch-scheduler.  Every entry point names the reference interface it
+ * replaces (paths are relative to the reference repository root).  The Go side
+ * binds these through cgo; Python binds them through ctypes
+ * (batch-scheduler_b200/capi.py); nothing but plain pointers and sizes crosses.
+ *
+ * Conventions
+ *   - every function returns 0 (BS_OK) or a negative bs_err; nothing aborts;
+ *   - the caller owns every input array for the duration of the call only
+ *     (cgo rule: no Go pointer is retained); the engine owns device memory;
+ *   - outputs are written into caller-provided buffers;
+ *   - a handle is thread-safe: calls on one bs_engine serialise on an internal
+ *     mutex (the reference calls Less/Permit from several goroutines,
+ *     pkg/scheduler/batch/batchscheduler.go:165,214);
+ *   - there is NO CPU fallback: without a CUDA device bs_create fails with
+ *     BS_E_NODEVICE.
+ *
+ * Resource lanes (SoA, int64): lane 0 MilliCPU, 1 Memory, 2 EphemeralStorage,
+ * 3 AllowedPodNumber (the four fixed nodeinfo.Resource fields used at
+ * pkg/scheduler/core/core.go:656-659,673-685), lanes 4.. are the scalar /
+ * extended resources (`ScalarResources`, core.go:662-668,686-697).  Map-key
+ * presence of a scalar resource is a bit in a uint32 mask (bit d = lane d).
+ * Tables are lane-major: value of lane d for row i is a[d * n_rows + i].
+ */
+#ifndef BSCHED_H
+#define BSCHED_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BS_ABI_VERSION 1
+#define BS_FIXED_LANES 4
+#define BS_MAX_LANES 16
+/* |value| bound accepted for every int64 table entry (validated at upload):
+ * keeps left-req differences and the float32->int64 conversion in range. */
+#define BS_VALUE_LIMIT ((int64_t)1 << 60)
+
+typedef struct bs_engine bs_engine; /* opaque */
+
+typedef enum {
+  BS_OK = 0,
+  BS_E_INVAL = -1,       /* bad argument / table shape */
+  BS_E_NODEVICE = -2,    /* no CUDA device: there is no CPU path */
+  BS_E_CUDA = -3,        /* CUDA runtime error (bs_last_error has the text) */
+  BS_E_NOMEM = -4,
+  BS_E_RANGE = -5,       /* table value outside +-BS_VALUE_LIMIT */
+  BS_E_STATE = -6,       /* call out of order (e.g. evaluate before upload) */
+  BS_E_REF_PANIC = -7,   /* the reference would panic on this input:
+                            findMaxPG divides by MinMember==0 (core.go:716-717) */
+  BS_E_INDEX = -8        /* pod / node / group index out of range */
+} bs_err;
+
+/* ---- framework.Status codes (k8s.io/kubernetes v1.17.5
+ *      pkg/scheduler/framework/v1alpha1; the adapter maps onto them at
+ *      batchscheduler.go:104-107,183-201) ---- */
+typedef enum {
+  BS_CODE_SUCCESS = 0,
+  BS_CODE_ERROR = 1,
+  BS_CODE_UNSCHEDULABLE = 2,
+  BS_CODE_UNSCHEDULABLE_AND_UNRESOLVABLE = 3,
+  BS_CODE_WAIT = 4,
+  BS_CODE_SKIP = 5
+} bs_code;
+
+/* ---- PreFilter verdict per pod (reason enum -> message, core.go:88-167) ---- */
+typedef enum {
+  BS_PF_PASS = 0,
+  BS_PF_ERR_NOT_FOUND = 1,   /* "can not found pod group: %v"          core.go:102 */
+  BS_PF_ERR_DENIED = 2,      /* "pod with pgName: %v last failed in 20s, deny" :107 */
+  BS_PF_ERR_OCCUPIED_NOREFS = 3, /* "pod group %s has been occupied by %v"   :505 */
+  BS_PF_ERR_OCCUPIED = 4,    /* "pod group has been occupied by %v"          :509 */
+  BS_PF_ERR_NOT_ENOUGH = 5   /* "cluster resource not enough"           :143,:164 */
+} bs_prefilter_code;
+
+/* ---- gang decision per group (Permit, core.go:268-309) ---- */
+typedef enum {
+  BS_ADMIT = 0,         /* ready: matched >= MinMember - Status.Scheduled (uint32) */
+  BS_WAIT = 1,          /* not ready yet -> framework.Wait                         */
+  BS_UNSCHEDULABLE = 2  /* pods in the round, none passed PreFilter with a node    */
+} bs_admit_code;
+
+/* ---- node flags: the guards of core.go:606-617 and :639 ---- */
+#define BS_NODE_NIL 0x01u           /* info == nil                   core.go:606 */
+#define BS_NODE_NO_NODE 0x02u       /* info.Node() == nil            core.go:610 */
+#define BS_NODE_UNSCHEDULABLE 0x04u /* Spec.Unschedulable            core.go:615 */
+#define BS_NODE_TAINTS_ERR 0x08u    /* info.Taints() returned error  core.go:639 */
+
+/* ---- pod flags ---- */
+#define BS_POD_PERMITTED_RECENTLY 0x01u /* uid in lastPermittedPod   core.go:95-98 */
+#define BS_POD_OCC_NOREFS 0x02u   /* group occupied, pod has no ownerRefs  :504-506 */
+#define BS_POD_OCC_MISMATCH 0x04u /* group occupied by other owner refs    :507-510 */
+#define BS_POD_LISTER_MISS 0x08u  /* pgLister.Get fails for this pod       :395-399 */
+
+/* ---- group flags (cache.PodGroupMatchStatus, pkg/scheduler/cache/cache.go:52-67) ---- */
+#define BS_GROUP_SCHEDULED 0x01u   /* pgs.Scheduled                cache.go:66 */
+#define BS_GROUP_HAS_POD 0x02u     /* pgs.Pod != nil               cache.go:64 */
+#define BS_GROUP_HAS_MINRES 0x04u  /* Spec.MinResources != nil     types.go:97 */
+#define BS_GROUP_DENIED 0x08u      /* ns/name in lastDeniedPG      core.go:105 */
+
+/* gid values for pods that carry no usable group */
+#define BS_GID_NONE (-1)    /* no group label: VerifyPodLabelSatisfied false (k8s.go:62) */
+#define BS_GID_MISSING (-2) /* labelled, but podGroupStatusCache.Get == nil (core.go:100) */
+
+/* Node table: the scheduler snapshot, in snapshot LIST ORDER (core.go:597,604). */
+typedef struct {
+  uint32_t n_nodes;
+  uint32_t n_lanes;              /* 4..BS_MAX_LANES, same for all three tables */
+  const int64_t* alloc;          /* [n_lanes][n_nodes] info.AllocatableResource() */
+  const int64_t* requested;      /* [n_lanes][n_nodes] info.RequestedResource()   */
+  const int32_t* pod_count;      /* [n_nodes] len(info.Pods())        core.go:650-653 */
+  const uint32_t* alloc_present; /* [n_nodes] scalar keys in allocatable          */
+  const uint32_t* req_present;   /* [n_nodes] scalar keys in requested            */
+  const uint64_t* label_mask;    /* [n_nodes] pre-encoded node labels (checkFit, core.go:741) */
+  const uint64_t* taint_mask;    /* [n_nodes] pre-encoded NoSchedule/NoExecute taints */
+  const uint8_t* flags;          /* [n_nodes] BS_NODE_* */
+} bs_node_table;
+
+/* Pod table: the queue candidates of one round. */
+typedef struct {
+  uint32_t n_pods;
+  uint32_t n_lanes;
+  const int64_t* req;          /* [n_lanes][n_pods] getPodResourceRequire  core.go:761-772 */
+  const uint32_t* req_present; /* [n_pods] scalar keys present in the request            */
+  const int32_t* gid;          /* [n_pods] group index, BS_GID_NONE or BS_GID_MISSING    */
+  const uint64_t* sel_mask;    /* [n_pods] required node-label bits                      */
+  const uint64_t* tol_mask;    /* [n_pods] tolerated taint bits                          */
+  const int32_t* priority;     /* [n_pods] podutil.GetPodPriority         core.go:372    */
+  const int64_t* ts_ns;        /* [n_pods] PodInfo.Timestamp              core.go:385    */
+  const uint8_t* flags;        /* [n_pods] BS_POD_*                                      */
+} bs_pod_table;
+
+/* Group table: PGStatusCache.PGStatusMap flattened (cache.go:45-67); canonical
+ * iteration order = table index (the reference iterates a Go map, core.go:703). */
+typedef struct {
+  uint32_t n_groups;
+  uint32_t n_lanes;
+  const uint32_t* min_member;      /* Spec.MinMember                  types.go:83  */
+  const uint32_t* scheduled;       /* Status.Scheduled                types.go:114 */
+  const uint32_t* matched;         /* len(MatchedPodNodes.Items()) carried in      */
+  const uint8_t* flags;            /* BS_GROUP_*                                   */
+  const int64_t* min_res;          /* [n_lanes][n_groups] Spec.MinResources as a Resource */
+  const uint32_t* min_res_present; /* scalar keys present in MinResources          */
+  const uint64_t* rep_sel;         /* selector mask of pgs.Pod (first-seen pod)    */
+  const uint64_t* rep_tol;         /* toleration mask of pgs.Pod                   */
+  const int64_t* creation_ns;      /* PodGroup CreationTimestamp      core.go:400  */
+  const uint32_t* name_rank;       /* rank of the bare pgName, byte-wise ascending; equal names share a rank (core.go:404) */
+} bs_group_table;
+
+/* What one evaluation materialises in HBM besides the decision vectors. */
+#define BS_OUT_FIT_BITMAP 0x1u /* P x ceil(N/32) u32 words, bit n%32 of word n/32 */
+#define BS_OUT_SCORE 0x2u      /* P x N int64 residual-capacity scores            */
+
+typedef struct {
+  int32_t device;      /* CUDA device ordinal */
+  uint32_t n_lanes;    /* lanes of every table uploaded to this engine */
+  uint32_t out_flags;  /* BS_OUT_* */
+  uint32_t reserved;
+} bs_config;
+
+/* Host result buffers; any pointer may be NULL (that output is not copied back). */
+typedef struct {
+  uint8_t* prefilter;       /* [P] bs_prefilter_code                            */
+  uint32_t* feasible_count; /* [P] number of nodes the pod fits on              */
+  int32_t* best_node;       /* [P] argmax residual score (lowest index on ties), -1 if none */
+  int64_t* best_score;      /* [P] its score, INT64_MIN if none                 */
+  uint8_t* admit;           /* [G] bs_admit_code                                */
+  uint32_t* admit_bitmap;   /* [ceil(G/32)] bit g set <=> admit[g]==BS_ADMIT    */
+  uint8_t* new_denied;      /* [G] 1 if a pod of g hit "cluster resource not enough" (core.go:142,163) */
+  uint32_t* order;          /* [P] queue order: pod indices sorted by Less      */
+  uint32_t* rank;           /* [P] dense rank of each pod under Less (equal keys share a rank) */
+  int32_t max_group;        /* out: findMaxPG winner, -1 if none (core.go:701)  */
+  uint32_t max_finished;    /* out: its progress value                          */
+} bs_results;
+
+typedef struct {
+  int32_t code;         /* bs_code */
+  int32_t reason;       /* bs_prefilter_code */
+  int32_t group;        /* group index the message refers to, or -1 */
+} bs_status;
+
+typedef struct {
+  int32_t ready;        /* core.Permit's first return value (core.go:303-307) */
+  int32_t code;         /* bs_code after the adapter mapping (batchscheduler.go:183-201) */
+  int64_t wait_ns;      /* waitTime+1s, 0 for Success, DefaultWaitTime for Unschedulable */
+  int32_t start_signal; /* 1 when the adapter would fire sendStartScheduleSignal (:197-199) */
+  int32_t group;
+} bs_permit_result;
+
+/* ---- lifecycle.  Replaces batch.New / core.NewScheduleOperation
+ *      (batchscheduler.go:377, core.go:64-77). ---- */
+int bs_abi_version(void);
+int bs_create(const bs_config* cfg, bs_engine** out);
+void bs_destroy(bs_engine* e);
+const char* bs_strerror(int err);
+const char* bs_last_error(const bs_engine* e);
+
+/* ---- snapshot upload.  Replaces the reads of
+ *      frameworkHandler.SnapshotSharedLister().NodeInfos().List() (core.go:597),
+ *      PGStatusCache.PGStatusMap (cache.go:45-49) and the per-pod inputs of
+ *      PreFilter/Permit/Compare (core.go:88,268,368).  Host arrays are copied;
+ *      nothing is retained. ---- */
+int bs_upload_nodes(bs_engine* e, const bs_node_table* t);
+int bs_upload_groups(bs_engine* e, const bs_group_table* t);
+int bs_upload_pods(bs_engine* e, const bs_pod_table* t);
+/* max_schedule_time: plugin arg (batchscheduler.go:71-75, util.GetWaitTimeDuration
+ * k8s.go:82-91).  per_group_ns may be NULL; entries < 0 mean "unset". */
+int bs_set_wait_time(bs_engine* e, int64_t default_ns, const int64_t* per_group_ns,
+                     uint32_t n_groups);
+
+/* ---- one round over the uploaded snapshot.  Replaces, batched over every pod
+ *      of the round: ScheduleOperation.PreFilter (core.go:88-167) incl. findMaxPG
+ *      (:701-739), getPreAllocatedResource (:774-793), compareClusterResourceAndRequire
+ *      (:595-632), singleNodeResource (:634-670), compareResourceAndRequire
+ *      (:672-699); the Permit readiness count (core.go:303); Compare (core.go:368-411).
+ *      bs_evaluate = bs_evaluate_async + bs_fetch. ---- */
+int bs_evaluate(bs_engine* e, bs_results* out);
+int bs_evaluate_async(bs_engine* e);       /* enqueue the kernels, no host sync */
+int bs_sync(bs_engine* e);                 /* wait for the engine stream        */
+int bs_fetch(bs_engine* e, bs_results* out);
+
+/* ---- per-call mirrors answering from the last evaluation ---- */
+/* batchSchedulingPlugin.PreFilter  (batchscheduler.go:102-108) */
+int bs_prefilter(bs_engine* e, uint32_t pod, bs_status* st);
+/* batchSchedulingPlugin.Permit     (batchscheduler.go:165-202) */
+int bs_permit(bs_engine* e, uint32_t pod, uint32_t node, bs_permit_result* r);
+/* batchSchedulingPlugin.Less       (batchscheduler.go:214-216); returns 1/0 or <0 */
+int bs_less(bs_engine* e, uint32_t pod_a, uint32_t pod_b);
+/* Formats the reference's error string for a status (core.go:102,107,143,505,509).
+ * ns_name is the "namespace/name" of the group, occupied_by the OccupiedBy text. */
+int bs_format_message(const bs_status* st, const char* ns_name, const char* occupied_by,
+                      char* buf, size_t buf_len);
+
+/* ---- standalone table kernels (unit-level parity with the reference helpers) ---- */
+/* singleNodeResource over every node for one (sel,tol) pod class and percent
+ * (core.go:634-670).  left: [n_lanes][n_nodes], present: [n_nodes]. */
+int bs_node_left(bs_engine* e, uint64_t sel, uint64_t tol, float percent,
+                 int64_t* left, uint32_t* present);
+/* compareClusterResourceAndRequire for explicit needs (core.go:595-632):
+ * n_needs need vectors [n_lanes][n_needs] + presence masks -> ok[n_needs]. */
+int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent,
+                     const int64_t* need, const uint32_t* need_present, uint32_t n_needs,
+                     uint8_t* ok);
+
+/* ---- device-side access for callers that keep results in HBM (bench, NCCL) ---- */
+typedef enum {
+  BS_BUF_FIT_BITMAP = 0,
+  BS_BUF_SCORE = 1,
+  BS_BUF_ADMIT_BITMAP = 2,
+  BS_BUF_PREFILTER = 3,
+  BS_BUF_ADMIT = 4,
+  BS_BUF_ORDER = 5
+} bs_buffer;
+int bs_device_buffer(bs_engine* e, int which, void** dev_ptr, size_t* bytes);
+void* bs_stream(bs_engine* e); /* the cudaStream_t every kernel is launched on */
+/* copy rows [pod0, pod0+n) of the fit bitmap / score matrix to the host */
+int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words);
+int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores);
+
+/* ---- measurement hooks ---- */
+typedef enum {
+  BS_K_NODE_LEFT = 0,
+  BS_K_FIND_MAX = 1,
+  BS_K_CLASS_PREFIX = 2,
+  BS_K_PREFILTER = 3,
+  BS_K_GANG_FIT = 4,   /* the dominant kernel: fit predicate + score + gang admit */
+  BS_K_SORT = 5,
+  BS_K_COUNT = 6
+} bs_kernel_id;
+int bs_set_profiling(bs_engine* e, int on); /* record CUDA events around each stage */
+/* milliseconds of stage k in the last evaluation, and launches it took */
+int bs_kernel_ms(bs_engine* e, int k, float* ms, uint32_t* launches);
+uint64_t bs_launch_count(const bs_engine* e); /* kernels launched since bs_create */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSCHED_H */
