@@ -6,6 +6,7 @@ include/bsched.h.  The directory name carries a hyphen (it mirrors the reference
 repository's name), so import it with
     importlib.import_module("batch-scheduler_b200")
 """
-from . import snapshot  # noqa: F401
+from . import snapshot, capi  # noqa: F401
+from .engine import Engine  # noqa: F401
 
-__all__ = ["snapshot"]
+__all__ = ["snapshot", "capi", "Engine"]

@@ -1,0 +1,138 @@
+"""ctypes binding of include/bsched.h (libbsched.so) — the same C ABI the Go cgo shim binds.
+
+No torch types cross this boundary; numpy arrays (or any object exposing a raw pointer)
+are passed as plain pointers + sizes.  The library is CUDA-only: loading works on a CPU
+box (symbols resolve), bs_create fails with BS_E_NODEVICE.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+BS_OK, BS_E_INVAL, BS_E_NODEVICE, BS_E_CUDA, BS_E_NOMEM, BS_E_RANGE, BS_E_STATE, BS_E_REF_PANIC, BS_E_INDEX = \
+    0, -1, -2, -3, -4, -5, -6, -7, -8
+CODE_SUCCESS, CODE_ERROR, CODE_UNSCHEDULABLE, CODE_UNSCHEDULABLE_AND_UNRESOLVABLE, CODE_WAIT, CODE_SKIP = range(6)
+OUT_FIT_BITMAP, OUT_SCORE = 0x1, 0x2
+BUF_FIT_BITMAP, BUF_SCORE, BUF_ADMIT_BITMAP, BUF_PREFILTER, BUF_ADMIT, BUF_ORDER = range(6)
+K_NODE_LEFT, K_FIND_MAX, K_CLASS_PREFIX, K_PREFILTER, K_GANG_FIT, K_SORT, K_COUNT = range(7)
+KERNEL_NAMES = ["node_left", "find_max", "class_prefix", "prefilter", "gang_fit", "sort"]
+
+
+def _p(t):
+    return C.POINTER(t)
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_lanes", C.c_uint32), ("out_flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class NodeTableC(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("n_lanes", C.c_uint32), ("alloc", C.c_void_p), ("requested", C.c_void_p),
+                ("pod_count", C.c_void_p), ("alloc_present", C.c_void_p), ("req_present", C.c_void_p),
+                ("label_mask", C.c_void_p), ("taint_mask", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class PodTableC(C.Structure):
+    _fields_ = [("n_pods", C.c_uint32), ("n_lanes", C.c_uint32), ("req", C.c_void_p), ("req_present", C.c_void_p),
+                ("gid", C.c_void_p), ("sel_mask", C.c_void_p), ("tol_mask", C.c_void_p), ("priority", C.c_void_p),
+                ("ts_ns", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class GroupTableC(C.Structure):
+    _fields_ = [("n_groups", C.c_uint32), ("n_lanes", C.c_uint32), ("min_member", C.c_void_p),
+                ("scheduled", C.c_void_p), ("matched", C.c_void_p), ("flags", C.c_void_p), ("min_res", C.c_void_p),
+                ("min_res_present", C.c_void_p), ("rep_sel", C.c_void_p), ("rep_tol", C.c_void_p),
+                ("creation_ns", C.c_void_p), ("name_rank", C.c_void_p)]
+
+
+class ResultsC(C.Structure):
+    _fields_ = [("prefilter", C.c_void_p), ("feasible_count", C.c_void_p), ("best_node", C.c_void_p),
+                ("best_score", C.c_void_p), ("admit", C.c_void_p), ("admit_bitmap", C.c_void_p),
+                ("new_denied", C.c_void_p), ("order", C.c_void_p), ("rank", C.c_void_p),
+                ("max_group", C.c_int32), ("max_finished", C.c_uint32)]
+
+
+class StatusC(C.Structure):
+    _fields_ = [("code", C.c_int32), ("reason", C.c_int32), ("group", C.c_int32)]
+
+
+class PermitResultC(C.Structure):
+    _fields_ = [("ready", C.c_int32), ("code", C.c_int32), ("wait_ns", C.c_int64), ("start_signal", C.c_int32),
+                ("group", C.c_int32)]
+
+
+# every symbol include/bsched.h declares: (restype, argtypes)
+SYMBOLS = {
+    "bs_abi_version": (C.c_int, []),
+    "bs_create": (C.c_int, [_p(Config), _p(C.c_void_p)]),
+    "bs_destroy": (None, [C.c_void_p]),
+    "bs_strerror": (C.c_char_p, [C.c_int]),
+    "bs_last_error": (C.c_char_p, [C.c_void_p]),
+    "bs_upload_nodes": (C.c_int, [C.c_void_p, _p(NodeTableC)]),
+    "bs_upload_groups": (C.c_int, [C.c_void_p, _p(GroupTableC)]),
+    "bs_upload_pods": (C.c_int, [C.c_void_p, _p(PodTableC)]),
+    "bs_set_wait_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32]),
+    "bs_evaluate": (C.c_int, [C.c_void_p, _p(ResultsC)]),
+    "bs_evaluate_async": (C.c_int, [C.c_void_p]),
+    "bs_sync": (C.c_int, [C.c_void_p]),
+    "bs_fetch": (C.c_int, [C.c_void_p, _p(ResultsC)]),
+    "bs_prefilter": (C.c_int, [C.c_void_p, C.c_uint32, _p(StatusC)]),
+    "bs_permit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(PermitResultC)]),
+    "bs_less": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "bs_format_message": (C.c_int, [_p(StatusC), C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    "bs_node_left": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
+    "bs_cluster_check": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_uint32, C.c_void_p]),
+    "bs_device_buffer": (C.c_int, [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_size_t)]),
+    "bs_stream": (C.c_void_p, [C.c_void_p]),
+    "bs_fetch_fit_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "bs_fetch_score_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "bs_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "bs_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, _p(C.c_float), _p(C.c_uint32)]),
+    "bs_launch_count": (C.c_uint64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Loads libbsched.so (building it with nvcc first if it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and not os.path.exists(_build.LIB):
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError(f"{_build.LIB} is missing: the CUDA extension must be built (no CPU fallback exists)")
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(a) -> int:
+    """Raw address of a numpy array / torch tensor / int."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return int(a)
+
+
+class BsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bsched error {code}: {msg}")
+        self.code = code

@@ -1,0 +1,1112 @@
+// engine.cu — C ABI (include/bsched.h) of the B200 gang-scheduling feasibility engine.
+//
+// Host side: table validation + upload, class de-duplication of the pre-encoded
+// selector/toleration masks, kernel sequencing on one CUDA stream (the queue sort
+// runs concurrently on a second stream), result fetch, and the per-call mirrors of
+// batchSchedulingPlugin.PreFilter / Permit / Less (batchscheduler.go:102,165,214).
+// There is no CPU implementation of the path here: no device -> BS_E_NODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+#include "sort.cuh"
+
+using namespace bsk;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Key2 {
+  uint64_t a, b;
+  bool operator==(const Key2& o) const { return a == o.a && b == o.b; }
+};
+struct Key3 {
+  uint64_t a, b;
+  uint32_t c;
+  bool operator==(const Key3& o) const { return a == o.a && b == o.b && c == o.c; }
+};
+struct H2 {
+  size_t operator()(const Key2& k) const {
+    uint64_t h = k.a * 0x9E3779B97F4A7C15ull ^ (k.b + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+struct H3 {
+  size_t operator()(const Key3& k) const {
+    uint64_t h = k.a * 0x9E3779B97F4A7C15ull ^ (k.b + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull ^
+                 (uint64_t)k.c * 0x94D049BB133111EBull;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+
+}  // namespace
+
+struct bs_engine {
+  std::mutex mu;
+  int device = 0;
+  uint32_t L = 0, out_flags = 0;
+  cudaStream_t s = nullptr, s2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+
+  // shapes
+  uint32_t N = 0, Npad = 0, W = 0, P = 0, G = 0;
+  bool have_nodes = false, have_pods = false, have_groups = false;
+  bool nodes_dirty = true, classes_dirty = true, evaluated = false;
+
+  // node table (device, padded to Npad) + derived
+  DevBuf d_alloc, d_requested, d_pod_count, d_apres, d_rpres, d_label, d_taint, d_nflags;
+  DevBuf d_left_eff, d_left_present, d_classfit;
+  // pod table
+  DevBuf d_req, d_ppres, d_gid, d_prio, d_ts, d_pflags, d_pod_fit_class, d_pod_rep_class;
+  // group table
+  DevBuf d_min_member, d_scheduled, d_matched, d_gflags, d_min_res, d_mrpres, d_creation, d_name_rank,
+      d_group_rep_class;
+  // class tables
+  DevBuf d_fsel, d_ftol, d_fnz, d_rsel, d_rtol;
+  uint32_t n_fit_classes = 0, n_rep_classes = 0;
+  // effective group state + round scratch
+  DevBuf d_eflags, d_emin_res, d_emrpres, d_erep_class, d_first_pod, d_in_round, d_contrib, d_done, d_okA;
+  DevBuf d_state, d_pre, d_pre_present, d_pre_stats;
+  uint32_t prefix_slots = 0;
+  // outputs
+  DevBuf d_prefilter, d_feasible, d_best_node, d_best_score, d_admit, d_admit_bitmap, d_new_denied,
+      d_fit_bitmap, d_score, d_order, d_rank;
+  // sort scratch
+  DevBuf d_gk0, d_gk1, d_pk0, d_pk1, d_idx_a, d_idx_b, d_ghist, d_skip, d_group_rank, d_gorder;
+
+  // host copies for the per-call mirrors and class building
+  std::vector<int32_t> h_gid, h_prio;
+  std::vector<uint8_t> h_pflags;
+  std::vector<uint64_t> h_psel, h_ptol, h_gsel, h_gtol;
+  std::vector<uint32_t> h_pnz;
+  std::vector<int64_t> h_wait_ns;
+  int64_t default_wait_ns = 0;
+  // pinned result cache
+  PinBuf h_prefilter, h_feasible, h_best_node, h_best_score, h_admit, h_admit_bitmap, h_new_denied,
+      h_order, h_rank, h_state;
+  bool fetched = false;
+
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev_a[BS_K_COUNT] = {}, ev_b[BS_K_COUNT] = {};
+  uint32_t k_launches[BS_K_COUNT] = {};
+  bool k_valid[BS_K_COUNT] = {};
+};
+
+namespace {
+
+#define CK(call)                                                                     \
+  do {                                                                               \
+    cudaError_t _e = (call);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
+      return BS_E_CUDA;                                                              \
+    }                                                                                \
+  } while (0)
+
+int fail(bs_engine* e, int code, const char* msg) {
+  e->err = msg;
+  return code;
+}
+
+bool in_range(const int64_t* a, size_t n) {
+  const int64_t lim = BS_VALUE_LIMIT;
+  int64_t lo = 0, hi = 0;
+  for (size_t i = 0; i < n; ++i) {
+    lo = std::min(lo, a[i]);
+    hi = std::max(hi, a[i]);
+  }
+  return lo >= -lim && hi <= lim;
+}
+
+inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// upload a [L][n] lane-major host table into a [L][npad] device table
+int upload_lanes(bs_engine* e, DevBuf& dst, const int64_t* src, uint32_t L, uint32_t n, uint32_t npad) {
+  CK(dst.ensure((size_t)L * npad * 8));
+  if (npad != n) CK(cudaMemsetAsync(dst.p, 0, (size_t)L * npad * 8, e->s));
+  if (n)
+    CK(cudaMemcpy2DAsync(dst.p, (size_t)npad * 8, src, (size_t)n * 8, (size_t)n * 8, L,
+                         cudaMemcpyHostToDevice, e->s));
+  return BS_OK;
+}
+
+template <class T>
+int upload_vec(bs_engine* e, DevBuf& dst, const T* src, uint32_t n, uint32_t npad) {
+  CK(dst.ensure((size_t)npad * sizeof(T)));
+  if (npad != n) CK(cudaMemsetAsync(dst.p, 0, (size_t)npad * sizeof(T), e->s));
+  if (n) CK(cudaMemcpyAsync(dst.p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, e->s));
+  return BS_OK;
+}
+
+NodeTab node_tab(const bs_engine* e) {
+  NodeTab t;
+  t.alloc = e->d_alloc.as<int64_t>();
+  t.requested = e->d_requested.as<int64_t>();
+  t.pod_count = e->d_pod_count.as<int32_t>();
+  t.alloc_present = e->d_apres.as<uint32_t>();
+  t.req_present = e->d_rpres.as<uint32_t>();
+  t.label = e->d_label.as<uint64_t>();
+  t.taint = e->d_taint.as<uint64_t>();
+  t.flags = e->d_nflags.as<uint8_t>();
+  t.N = e->N;
+  t.Npad = e->Npad;
+  t.L = e->L;
+  return t;
+}
+PodTab pod_tab(const bs_engine* e) {
+  PodTab p;
+  p.req = e->d_req.as<int64_t>();
+  p.req_present = e->d_ppres.as<uint32_t>();
+  p.gid = e->d_gid.as<int32_t>();
+  p.flags = e->d_pflags.as<uint8_t>();
+  p.fit_class = e->d_pod_fit_class.as<uint32_t>();
+  p.rep_class = e->d_pod_rep_class.as<uint32_t>();
+  p.P = e->P;
+  p.L = e->L;
+  return p;
+}
+GroupTab group_tab(const bs_engine* e) {
+  GroupTab g;
+  g.min_member = e->d_min_member.as<uint32_t>();
+  g.scheduled = e->d_scheduled.as<uint32_t>();
+  g.matched = e->d_matched.as<uint32_t>();
+  g.flags = e->d_gflags.as<uint8_t>();
+  g.min_res = e->d_min_res.as<int64_t>();
+  g.min_res_present = e->d_mrpres.as<uint32_t>();
+  g.rep_class = e->d_group_rep_class.as<uint32_t>();
+  g.G = e->G;
+  g.L = e->L;
+  return g;
+}
+GroupEff group_eff(const bs_engine* e) {
+  GroupEff x;
+  x.flags = e->d_eflags.as<uint8_t>();
+  x.min_res = e->d_emin_res.as<int64_t>();
+  x.min_res_present = e->d_emrpres.as<uint32_t>();
+  x.rep_class = e->d_erep_class.as<uint32_t>();
+  x.first_pod = e->d_first_pod.as<uint32_t>();
+  x.in_round = e->d_in_round.as<uint32_t>();
+  x.contrib = e->d_contrib.as<uint32_t>();
+  x.done = e->d_done.as<uint32_t>();
+  return x;
+}
+PrefixOut prefix_out(const bs_engine* e) {
+  PrefixOut o;
+  o.pre = e->d_pre.as<int64_t>();
+  o.present = e->d_pre_present.as<uint32_t>();
+  o.stats = e->d_pre_stats.as<ClassStats>();
+  return o;
+}
+
+struct StageTimer {
+  bs_engine* e;
+  int k;
+  cudaStream_t st;
+  StageTimer(bs_engine* e_, int k_, cudaStream_t st_) : e(e_), k(k_), st(st_) {
+    e->k_launches[k] = 0;
+    if (e->profiling) cudaEventRecord(e->ev_a[k], st);
+  }
+  ~StageTimer() {
+    if (e->profiling) {
+      cudaEventRecord(e->ev_b[k], st);
+      e->k_valid[k] = true;
+    }
+  }
+  void launched(uint32_t n = 1) {
+    e->k_launches[k] += n;
+    e->launches += n;
+  }
+};
+
+template <int MAXL>
+void launch_prefix_t(NodeTab t, const uint64_t* rsel, const uint64_t* rtol, uint32_t c0, int mode,
+                     uint64_t xsel, uint64_t xtol, float xpct, const RoundState* st, PrefixOut po,
+                     uint32_t grid, cudaStream_t s) {
+  class_prefix_kernel<MAXL><<<grid, PREFIX_THREADS, 0, s>>>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po);
+}
+void launch_prefix(uint32_t L, NodeTab t, const uint64_t* rsel, const uint64_t* rtol, uint32_t c0, int mode,
+                   uint64_t xsel, uint64_t xtol, float xpct, const RoundState* st, PrefixOut po,
+                   uint32_t grid, cudaStream_t s) {
+  if (L <= 4) launch_prefix_t<4>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+  else if (L <= 5) launch_prefix_t<5>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+  else if (L <= 6) launch_prefix_t<6>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+  else if (L <= 8) launch_prefix_t<8>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+  else if (L <= 9) launch_prefix_t<9>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+  else if (L <= 12) launch_prefix_t<12>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+  else launch_prefix_t<16>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+}
+
+template <int L>
+cudaError_t launch_fit_t(const FitArgs& a, uint32_t grid, cudaStream_t s) {
+  const size_t smem = gang_fit_smem_bytes(L);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem);
+    if (er != cudaSuccess) return er;
+    attr_set = true;
+  }
+  gang_fit_kernel<L><<<grid, FIT_THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_fit(uint32_t L, const FitArgs& a, uint32_t grid, cudaStream_t s) {
+  switch (L) {
+    case 4: return launch_fit_t<4>(a, grid, s);
+    case 5: return launch_fit_t<5>(a, grid, s);
+    case 6: return launch_fit_t<6>(a, grid, s);
+    case 7: return launch_fit_t<7>(a, grid, s);
+    case 8: return launch_fit_t<8>(a, grid, s);
+    case 9: return launch_fit_t<9>(a, grid, s);
+    case 10: return launch_fit_t<10>(a, grid, s);
+    case 11: return launch_fit_t<11>(a, grid, s);
+    case 12: return launch_fit_t<12>(a, grid, s);
+    case 13: return launch_fit_t<13>(a, grid, s);
+    case 14: return launch_fit_t<14>(a, grid, s);
+    case 15: return launch_fit_t<15>(a, grid, s);
+    case 16: return launch_fit_t<16>(a, grid, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// one LSD pass over `n` indices
+void radix_pass(bs_engine* e, StageTimer& tm, const uint32_t* in, uint32_t* out, const uint64_t* key,
+                int shift, uint32_t n, cudaStream_t st) {
+  const uint32_t nblk = cdiv(n, SORT_TILE);
+  radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(in, key, shift, n, nblk, e->d_ghist.as<uint32_t>());
+  radix_scan_kernel<<<1, 256, 0, st>>>(e->d_ghist.as<uint32_t>(), nblk, n, e->d_skip.as<uint32_t>());
+  radix_scatter_kernel<<<nblk, SORT_THREADS, 0, st>>>(in, out, key, shift, n, nblk,
+                                                      e->d_ghist.as<uint32_t>(), e->d_skip.as<uint32_t>());
+  tm.launched(3);
+}
+
+// sorts indices 0..n-1 by (k1, k0[low k0_bits]) ascending, stable; result in `result`
+// (ping-pongs between a and b; returns the buffer holding the final order)
+uint32_t* radix_sort(bs_engine* e, StageTimer& tm, uint32_t n, const uint64_t* k0, int k0_bits,
+                     const uint64_t* k1, int k1_bits, uint32_t* a, uint32_t* b, cudaStream_t st) {
+  iota_kernel<<<cdiv(std::max(n, 1u), 256), 256, 0, st>>>(a, n);
+  tm.launched();
+  uint32_t* cur = a;
+  uint32_t* nxt = b;
+  for (int sh = 0; sh < k0_bits; sh += 8) {
+    radix_pass(e, tm, cur, nxt, k0, sh, n, st);
+    std::swap(cur, nxt);
+  }
+  for (int sh = 0; sh < k1_bits; sh += 8) {
+    radix_pass(e, tm, cur, nxt, k1, sh, n, st);
+    std::swap(cur, nxt);
+  }
+  return cur;
+}
+
+int rebuild_classes(bs_engine* e) {
+  // fit classes: distinct (sel, tol, non-zero scalar request mask) over the pods;
+  // rep classes: distinct (sel, tol) over pods and carried-in group representatives.
+  const uint32_t P = e->P, G = e->G;
+  std::unordered_map<Key3, uint32_t, H3> fmap;
+  std::unordered_map<Key2, uint32_t, H2> rmap;
+  std::vector<uint64_t> fsel, ftol, rsel, rtol;
+  std::vector<uint32_t> fnz;
+  std::vector<uint32_t> pfc(P), prc(P), grc(G);
+  fmap.reserve(256);
+  rmap.reserve(256);
+  for (uint32_t p = 0; p < P; ++p) {
+    const Key3 k3{e->h_psel[p], e->h_ptol[p], e->h_pnz[p]};
+    auto it = fmap.find(k3);
+    if (it == fmap.end()) {
+      it = fmap.emplace(k3, (uint32_t)fsel.size()).first;
+      fsel.push_back(k3.a); ftol.push_back(k3.b); fnz.push_back(k3.c);
+    }
+    pfc[p] = it->second;
+    const Key2 k2{e->h_psel[p], e->h_ptol[p]};
+    auto jt = rmap.find(k2);
+    if (jt == rmap.end()) {
+      jt = rmap.emplace(k2, (uint32_t)rsel.size()).first;
+      rsel.push_back(k2.a); rtol.push_back(k2.b);
+    }
+    prc[p] = jt->second;
+  }
+  for (uint32_t g = 0; g < G; ++g) {
+    const Key2 k2{e->h_gsel[g], e->h_gtol[g]};
+    auto jt = rmap.find(k2);
+    if (jt == rmap.end()) {
+      jt = rmap.emplace(k2, (uint32_t)rsel.size()).first;
+      rsel.push_back(k2.a); rtol.push_back(k2.b);
+    }
+    grc[g] = jt->second;
+  }
+  if (fsel.empty()) { fsel.push_back(0); ftol.push_back(0); fnz.push_back(0); }
+  if (rsel.empty()) { rsel.push_back(0); rtol.push_back(0); }
+  e->n_fit_classes = (uint32_t)fsel.size();
+  e->n_rep_classes = (uint32_t)rsel.size();
+  int rc;
+  // cudaMemcpyAsync from pageable memory returns once the data is staged, so the vectors may die.
+  if ((rc = upload_vec(e, e->d_fsel, fsel.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
+  if ((rc = upload_vec(e, e->d_ftol, ftol.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
+  if ((rc = upload_vec(e, e->d_fnz, fnz.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
+  if ((rc = upload_vec(e, e->d_rsel, rsel.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
+  if ((rc = upload_vec(e, e->d_rtol, rtol.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
+  if ((rc = upload_vec(e, e->d_pod_fit_class, pfc.data(), P, std::max(P, 1u)))) return rc;
+  if ((rc = upload_vec(e, e->d_pod_rep_class, prc.data(), P, std::max(P, 1u)))) return rc;
+  if ((rc = upload_vec(e, e->d_group_rep_class, grc.data(), G, std::max(G, 1u)))) return rc;
+  CK(cudaStreamSynchronize(e->s));
+  e->classes_dirty = false;
+  return BS_OK;
+}
+
+int ensure_round_buffers(bs_engine* e) {
+  const uint32_t P = std::max(e->P, 1u), G = std::max(e->G, 1u), L = e->L, N = std::max(e->N, 1u);
+  CK(e->d_eflags.ensure(G));
+  CK(e->d_emin_res.ensure((size_t)L * G * 8));
+  CK(e->d_emrpres.ensure((size_t)G * 4));
+  CK(e->d_erep_class.ensure((size_t)G * 4));
+  CK(e->d_first_pod.ensure((size_t)G * 4));
+  CK(e->d_in_round.ensure((size_t)G * 4));
+  CK(e->d_contrib.ensure((size_t)G * 4));
+  CK(e->d_done.ensure((size_t)G * 4));
+  CK(e->d_okA.ensure(G));
+  CK(e->d_state.ensure(sizeof(RoundState)));
+  CK(e->d_prefilter.ensure(P));
+  CK(e->d_feasible.ensure((size_t)P * 4));
+  CK(e->d_best_node.ensure((size_t)P * 4));
+  CK(e->d_best_score.ensure((size_t)P * 8));
+  CK(e->d_admit.ensure(G));
+  CK(e->d_admit_bitmap.ensure((size_t)cdiv(G, 32) * 4));
+  CK(e->d_new_denied.ensure(G));
+  CK(e->d_order.ensure((size_t)P * 4));
+  CK(e->d_rank.ensure((size_t)P * 4));
+  if (e->out_flags & BS_OUT_FIT_BITMAP) CK(e->d_fit_bitmap.ensure((size_t)e->P * std::max(e->W, 1u) * 4));
+  if (e->out_flags & BS_OUT_SCORE) CK(e->d_score.ensure((size_t)e->P * N * 8));
+  // prefix scratch: as many rep-class slots as fit a 1 GiB budget
+  const size_t per_class = (size_t)N * (8 * L + 4);
+  uint32_t slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(e->n_rep_classes, ((size_t)1 << 30) / per_class));
+  e->prefix_slots = slots;
+  CK(e->d_pre.ensure((size_t)slots * L * N * 8));
+  CK(e->d_pre_present.ensure((size_t)slots * N * 4));
+  CK(e->d_pre_stats.ensure((size_t)slots * sizeof(ClassStats)));
+  // sort scratch
+  const uint32_t M = std::max(P, G);
+  CK(e->d_gk0.ensure((size_t)G * 8));
+  CK(e->d_gk1.ensure((size_t)G * 8));
+  CK(e->d_pk0.ensure((size_t)P * 8));
+  CK(e->d_pk1.ensure((size_t)P * 8));
+  CK(e->d_idx_a.ensure((size_t)M * 4));
+  CK(e->d_idx_b.ensure((size_t)M * 4));
+  CK(e->d_ghist.ensure((size_t)256 * cdiv(M, SORT_TILE) * 4));
+  CK(e->d_skip.ensure(4));
+  CK(e->d_group_rank.ensure((size_t)G * 4));
+  // pinned result cache
+  CK(e->h_prefilter.ensure(P));
+  CK(e->h_feasible.ensure((size_t)P * 4));
+  CK(e->h_best_node.ensure((size_t)P * 4));
+  CK(e->h_best_score.ensure((size_t)P * 8));
+  CK(e->h_admit.ensure(G));
+  CK(e->h_admit_bitmap.ensure((size_t)cdiv(G, 32) * 4));
+  CK(e->h_new_denied.ensure(G));
+  CK(e->h_order.ensure((size_t)P * 4));
+  CK(e->h_rank.ensure((size_t)P * 4));
+  CK(e->h_state.ensure(sizeof(RoundState)));
+  return BS_OK;
+}
+
+int prepare_nodes(bs_engine* e) {
+  // node_left + class fit bitmap (only when nodes or classes changed)
+  NodeTab t = node_tab(e);
+  StageTimer tm(e, BS_K_NODE_LEFT, e->s);
+  CK(e->d_left_eff.ensure((size_t)e->L * e->Npad * 8));
+  CK(e->d_left_present.ensure((size_t)e->Npad * 4));
+  CK(e->d_classfit.ensure((size_t)e->n_fit_classes * std::max(e->W, 1u) * 4));
+  node_left_kernel<<<cdiv(e->Npad, 256), 256, 0, e->s>>>(t, e->d_left_eff.as<int64_t>(),
+                                                         e->d_left_present.as<uint32_t>());
+  tm.launched();
+  if (e->W) {
+    dim3 grid(cdiv(e->W * 32, 256), e->n_fit_classes);
+    class_fit_kernel<<<grid, 256, 0, e->s>>>(t, e->d_left_present.as<uint32_t>(), e->d_fsel.as<uint64_t>(),
+                                             e->d_ftol.as<uint64_t>(), e->d_fnz.as<uint32_t>(),
+                                             e->n_fit_classes, e->W, e->d_classfit.as<uint32_t>());
+    tm.launched();
+  }
+  CK(cudaGetLastError());
+  e->nodes_dirty = false;
+  return BS_OK;
+}
+
+int evaluate_async_locked(bs_engine* e) {
+  if (!e->have_nodes || !e->have_pods || !e->have_groups)
+    return fail(e, BS_E_STATE, "bs_evaluate: upload nodes, groups and pods first");
+  CK(cudaSetDevice(e->device));
+  int rc;
+  bool reprepare = e->nodes_dirty;
+  if (e->classes_dirty) {
+    if ((rc = rebuild_classes(e))) return rc;
+    reprepare = true;
+  }
+  if ((rc = ensure_round_buffers(e))) return rc;
+  for (int k = 0; k < BS_K_COUNT; ++k) e->k_valid[k] = false;
+  if (reprepare && (rc = prepare_nodes(e))) return rc;
+
+  const uint32_t P = e->P, G = e->G, L = e->L;
+  NodeTab t = node_tab(e);
+  PodTab pt = pod_tab(e);
+  GroupTab gt = group_tab(e);
+  GroupEff ge = group_eff(e);
+  PrefixOut po = prefix_out(e);
+  RoundState* st = e->d_state.as<RoundState>();
+
+  // fork the sort stream
+  CK(cudaEventRecord(e->ev_fork, e->s));
+  CK(cudaStreamWaitEvent(e->s2, e->ev_fork, 0));
+  {
+    StageTimer tm(e, BS_K_SORT, e->s2);
+    // groups: (creation asc, name desc) -> dense group rank
+    if (G) {
+      group_keys_kernel<<<cdiv(G, 256), 256, 0, e->s2>>>(e->d_creation.as<int64_t>(), e->d_name_rank.as<uint32_t>(),
+                                                         G, e->d_gk0.as<uint64_t>(), e->d_gk1.as<uint64_t>());
+      tm.launched();
+      uint32_t* gord = radix_sort(e, tm, G, e->d_gk0.as<uint64_t>(), 32, e->d_gk1.as<uint64_t>(), 64,
+                                  e->d_idx_a.as<uint32_t>(), e->d_idx_b.as<uint32_t>(), e->s2);
+      dense_rank_kernel<<<1, 1024, 0, e->s2>>>(gord, e->d_gk0.as<uint64_t>(), e->d_gk1.as<uint64_t>(), G,
+                                               e->d_group_rank.as<uint32_t>());
+      tm.launched();
+    }
+    if (P) {
+      pod_keys_kernel<<<cdiv(P, 256), 256, 0, e->s2>>>(e->d_prio.as<int32_t>(), e->d_gid.as<int32_t>(),
+                                                       e->d_ts.as<int64_t>(), e->d_pflags.as<uint8_t>(),
+                                                       e->d_group_rank.as<uint32_t>(), P, G,
+                                                       e->d_pk0.as<uint64_t>(), e->d_pk1.as<uint64_t>());
+      tm.launched();
+      uint32_t* pord = radix_sort(e, tm, P, e->d_pk0.as<uint64_t>(), 64, e->d_pk1.as<uint64_t>(), 64,
+                                  e->d_idx_a.as<uint32_t>(), e->d_idx_b.as<uint32_t>(), e->s2);
+      CK(cudaMemcpyAsync(e->d_order.p, pord, (size_t)P * 4, cudaMemcpyDeviceToDevice, e->s2));
+      dense_rank_kernel<<<1, 1024, 0, e->s2>>>(e->d_order.as<uint32_t>(), e->d_pk0.as<uint64_t>(),
+                                               e->d_pk1.as<uint64_t>(), P, e->d_rank.as<uint32_t>());
+      tm.launched();
+    }
+  }
+  CK(cudaEventRecord(e->ev_join, e->s2));
+
+  // main stream: group preparation + findMaxPG
+  {
+    StageTimer tm(e, BS_K_FIND_MAX, e->s);
+    const uint32_t gb = cdiv(std::max(G, 1u), 256);
+    group_reset_kernel<<<gb, 256, 0, e->s>>>(gt, ge, e->d_new_denied.as<uint8_t>(),
+                                             e->d_admit_bitmap.as<uint32_t>(), e->d_okA.as<uint8_t>());
+    tm.launched();
+    if (P) {
+      group_first_pod_kernel<<<cdiv(P, 256), 256, 0, e->s>>>(pt, gt, ge);
+      tm.launched();
+    }
+    if (G) {
+      group_effective_kernel<<<gb, 256, 0, e->s>>>(pt, gt, ge);
+      tm.launched();
+    }
+    find_max_pg_kernel<<<1, 1024, 0, e->s>>>(gt, ge, st);
+    tm.launched();
+  }
+  // ordered cluster scans (compareClusterResourceAndRequire) per rep class
+  {
+    StageTimer tm(e, BS_K_CLASS_PREFIX, e->s);
+    if (e->N && G && P) {
+      for (uint32_t c0 = 0; c0 < e->n_rep_classes; c0 += e->prefix_slots) {
+        const uint32_t nc = std::min(e->prefix_slots, e->n_rep_classes - c0);
+        launch_prefix(L, t, e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), c0, 0, 0, 0, 0.f, st, po, nc, e->s);
+        group_check_kernel<<<cdiv(G * 32, 256), 256, 0, e->s>>>(t, gt, ge, po, c0, nc, st, e->d_okA.as<uint8_t>());
+        tm.launched(2);
+      }
+      launch_prefix(L, t, e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), 0, 1, 0, 0, 0.f, st, po, 1, e->s);
+      tm.launched();
+    }
+  }
+  {
+    StageTimer tm(e, BS_K_PREFILTER, e->s);
+    if (P) {
+      const uint64_t threads = (uint64_t)P * 32;
+      prefilter_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, e->s>>>(
+          t, pt, gt, ge, po, st, e->d_okA.as<uint8_t>(), e->d_prefilter.as<uint8_t>(),
+          e->d_new_denied.as<uint8_t>());
+      tm.launched();
+    }
+    if (G) {
+      group_idle_admit_kernel<<<cdiv(G, 256), 256, 0, e->s>>>(gt, ge, e->d_admit.as<uint8_t>(),
+                                                              e->d_admit_bitmap.as<uint32_t>());
+      tm.launched();
+    }
+  }
+  {
+    StageTimer tm(e, BS_K_GANG_FIT, e->s);
+    if (P) {
+      FitArgs a;
+      a.left_eff = e->d_left_eff.as<int64_t>();
+      a.classfit = e->d_classfit.as<uint32_t>();
+      a.req = e->d_req.as<int64_t>();
+      a.req_present = e->d_ppres.as<uint32_t>();
+      a.fit_class = e->d_pod_fit_class.as<uint32_t>();
+      a.gid = e->d_gid.as<int32_t>();
+      a.prefilter = e->d_prefilter.as<uint8_t>();
+      a.min_member = gt.min_member;
+      a.scheduled = gt.scheduled;
+      a.matched = gt.matched;
+      a.in_round = ge.in_round;
+      a.contrib = ge.contrib;
+      a.done = ge.done;
+      a.admit = e->d_admit.as<uint8_t>();
+      a.admit_bitmap = e->d_admit_bitmap.as<uint32_t>();
+      a.feasible_count = e->d_feasible.as<uint32_t>();
+      a.best_node = e->d_best_node.as<int32_t>();
+      a.best_score = e->d_best_score.as<int64_t>();
+      a.fit_bitmap = (e->out_flags & BS_OUT_FIT_BITMAP) ? e->d_fit_bitmap.as<uint32_t>() : nullptr;
+      a.score = (e->out_flags & BS_OUT_SCORE) ? e->d_score.as<int64_t>() : nullptr;
+      a.P = P; a.N = e->N; a.Npad = e->Npad; a.W = e->W; a.G = G;
+      CK(launch_fit(L, a, cdiv(P, PODS_PER_CTA), e->s));
+      tm.launched();
+    }
+  }
+  CK(cudaStreamWaitEvent(e->s, e->ev_join, 0));
+  CK(cudaGetLastError());
+  e->evaluated = true;
+  e->fetched = false;
+  return BS_OK;
+}
+
+int fetch_locked(bs_engine* e, bs_results* out) {
+  if (!e->evaluated) return fail(e, BS_E_STATE, "bs_fetch: nothing evaluated");
+  const uint32_t P = e->P, G = e->G;
+  if (!e->fetched) {
+    auto d2h = [&](PinBuf& h, const DevBuf& d, size_t bytes) -> cudaError_t {
+      return bytes ? cudaMemcpyAsync(h.p, d.p, bytes, cudaMemcpyDeviceToHost, e->s) : cudaSuccess;
+    };
+    CK(d2h(e->h_prefilter, e->d_prefilter, P));
+    CK(d2h(e->h_feasible, e->d_feasible, (size_t)P * 4));
+    CK(d2h(e->h_best_node, e->d_best_node, (size_t)P * 4));
+    CK(d2h(e->h_best_score, e->d_best_score, (size_t)P * 8));
+    CK(d2h(e->h_admit, e->d_admit, G));
+    CK(d2h(e->h_admit_bitmap, e->d_admit_bitmap, (size_t)cdiv(G, 32) * 4));
+    CK(d2h(e->h_new_denied, e->d_new_denied, G));
+    CK(d2h(e->h_order, e->d_order, (size_t)P * 4));
+    CK(d2h(e->h_rank, e->d_rank, (size_t)P * 4));
+    CK(d2h(e->h_state, e->d_state, sizeof(RoundState)));
+    CK(cudaStreamSynchronize(e->s));
+    e->fetched = true;
+  }
+  const RoundState* st = e->h_state.as<RoundState>();
+  if (out) {
+    auto cp = [](void* dst, const PinBuf& src, size_t bytes) {
+      if (dst && bytes) memcpy(dst, src.p, bytes);
+    };
+    cp(out->prefilter, e->h_prefilter, P);
+    cp(out->feasible_count, e->h_feasible, (size_t)P * 4);
+    cp(out->best_node, e->h_best_node, (size_t)P * 4);
+    cp(out->best_score, e->h_best_score, (size_t)P * 8);
+    cp(out->admit, e->h_admit, G);
+    cp(out->admit_bitmap, e->h_admit_bitmap, (size_t)cdiv(G, 32) * 4);
+    cp(out->new_denied, e->h_new_denied, G);
+    cp(out->order, e->h_order, (size_t)P * 4);
+    cp(out->rank, e->h_rank, (size_t)P * 4);
+    out->max_group = st->max_group;
+    out->max_finished = st->max_finished;
+  }
+  if (st->ref_panic)
+    return fail(e, BS_E_REF_PANIC, "findMaxPG: MinMember == 0 with Status.Scheduled != 0 (core.go:716-717 divides by zero)");
+  return BS_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+extern "C" {
+
+int bs_abi_version(void) { return BS_ABI_VERSION; }
+
+const char* bs_strerror(int err) {
+  switch (err) {
+    case BS_OK: return "ok";
+    case BS_E_INVAL: return "invalid argument";
+    case BS_E_NODEVICE: return "no CUDA device (this engine has no CPU path)";
+    case BS_E_CUDA: return "CUDA runtime error";
+    case BS_E_NOMEM: return "out of memory";
+    case BS_E_RANGE: return "table value outside +-2^56";
+    case BS_E_STATE: return "call out of order";
+    case BS_E_REF_PANIC: return "reference would panic (findMaxPG divide by zero)";
+    case BS_E_INDEX: return "index out of range";
+  }
+  return "unknown error";
+}
+
+const char* bs_last_error(const bs_engine* e) { return e ? e->err.c_str() : ""; }
+
+int bs_create(const bs_config* cfg, bs_engine** out) {
+  if (!cfg || !out) return BS_E_INVAL;
+  *out = nullptr;
+  if (cfg->n_lanes < BS_FIXED_LANES || cfg->n_lanes > BS_MAX_LANES) return BS_E_INVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return BS_E_NODEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return BS_E_INVAL;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return BS_E_CUDA;
+  bs_engine* e = new (std::nothrow) bs_engine();
+  if (!e) return BS_E_NOMEM;
+  e->device = cfg->device;
+  e->L = cfg->n_lanes;
+  e->out_flags = cfg->out_flags;
+  bool ok = cudaStreamCreateWithFlags(&e->s, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; ok && k < BS_K_COUNT; ++k)
+    ok = cudaEventCreate(&e->ev_a[k]) == cudaSuccess && cudaEventCreate(&e->ev_b[k]) == cudaSuccess;
+  if (!ok) {
+    bs_destroy(e);
+    return BS_E_CUDA;
+  }
+  *out = e;
+  return BS_OK;
+}
+
+void bs_destroy(bs_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->s) cudaStreamSynchronize(e->s);
+  if (e->s2) cudaStreamSynchronize(e->s2);
+  DevBuf* bufs[] = {&e->d_alloc, &e->d_requested, &e->d_pod_count, &e->d_apres, &e->d_rpres, &e->d_label,
+                    &e->d_taint, &e->d_nflags, &e->d_left_eff, &e->d_left_present, &e->d_classfit, &e->d_req,
+                    &e->d_ppres, &e->d_gid, &e->d_prio, &e->d_ts, &e->d_pflags, &e->d_pod_fit_class,
+                    &e->d_pod_rep_class, &e->d_min_member, &e->d_scheduled, &e->d_matched, &e->d_gflags,
+                    &e->d_min_res, &e->d_mrpres, &e->d_creation, &e->d_name_rank, &e->d_group_rep_class,
+                    &e->d_fsel, &e->d_ftol, &e->d_fnz, &e->d_rsel, &e->d_rtol, &e->d_eflags, &e->d_emin_res,
+                    &e->d_emrpres, &e->d_erep_class, &e->d_first_pod, &e->d_in_round, &e->d_contrib,
+                    &e->d_done, &e->d_okA, &e->d_state, &e->d_pre, &e->d_pre_present, &e->d_pre_stats,
+                    &e->d_prefilter, &e->d_feasible, &e->d_best_node, &e->d_best_score, &e->d_admit,
+                    &e->d_admit_bitmap, &e->d_new_denied, &e->d_fit_bitmap, &e->d_score, &e->d_order,
+                    &e->d_rank, &e->d_gk0, &e->d_gk1, &e->d_pk0, &e->d_pk1, &e->d_idx_a, &e->d_idx_b,
+                    &e->d_ghist, &e->d_skip, &e->d_group_rank, &e->d_gorder};
+  for (DevBuf* b : bufs) b->release();
+  PinBuf* pins[] = {&e->h_prefilter, &e->h_feasible, &e->h_best_node, &e->h_best_score, &e->h_admit,
+                    &e->h_admit_bitmap, &e->h_new_denied, &e->h_order, &e->h_rank, &e->h_state};
+  for (PinBuf* b : pins) b->release();
+  for (int k = 0; k < BS_K_COUNT; ++k) {
+    if (e->ev_a[k]) cudaEventDestroy(e->ev_a[k]);
+    if (e->ev_b[k]) cudaEventDestroy(e->ev_b[k]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->s) cudaStreamDestroy(e->s);
+  if (e->s2) cudaStreamDestroy(e->s2);
+  delete e;
+}
+
+int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
+  if (!e || !t) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (t->n_lanes != e->L) return fail(e, BS_E_INVAL, "bs_upload_nodes: n_lanes differs from the engine's");
+  const uint32_t N = t->n_nodes, L = e->L;
+  if (N && (!t->alloc || !t->requested || !t->pod_count || !t->alloc_present || !t->req_present ||
+            !t->label_mask || !t->taint_mask || !t->flags))
+    return fail(e, BS_E_INVAL, "bs_upload_nodes: null column");
+  if (!in_range(t->alloc, (size_t)L * N) || !in_range(t->requested, (size_t)L * N))
+    return fail(e, BS_E_RANGE, "bs_upload_nodes: value outside +-2^56");
+  CK(cudaSetDevice(e->device));
+  const uint32_t Npad = std::max(1u, cdiv(N, NODE_TILE)) * NODE_TILE;
+  int rc;
+  if ((rc = upload_lanes(e, e->d_alloc, t->alloc, L, N, Npad))) return rc;
+  if ((rc = upload_lanes(e, e->d_requested, t->requested, L, N, Npad))) return rc;
+  if ((rc = upload_vec(e, e->d_pod_count, t->pod_count, N, Npad))) return rc;
+  if ((rc = upload_vec(e, e->d_apres, t->alloc_present, N, Npad))) return rc;
+  if ((rc = upload_vec(e, e->d_rpres, t->req_present, N, Npad))) return rc;
+  if ((rc = upload_vec(e, e->d_label, t->label_mask, N, Npad))) return rc;
+  if ((rc = upload_vec(e, e->d_taint, t->taint_mask, N, Npad))) return rc;
+  if ((rc = upload_vec(e, e->d_nflags, t->flags, N, Npad))) return rc;
+  CK(cudaStreamSynchronize(e->s));
+  e->N = N;
+  e->Npad = Npad;
+  e->W = cdiv(N, 32);
+  e->have_nodes = true;
+  e->nodes_dirty = true;
+  e->evaluated = false;
+  return BS_OK;
+}
+
+int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
+  if (!e || !t) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (t->n_lanes != e->L) return fail(e, BS_E_INVAL, "bs_upload_groups: n_lanes differs from the engine's");
+  const uint32_t G = t->n_groups, L = e->L;
+  if (G && (!t->min_member || !t->scheduled || !t->matched || !t->flags || !t->min_res ||
+            !t->min_res_present || !t->rep_sel || !t->rep_tol || !t->creation_ns || !t->name_rank))
+    return fail(e, BS_E_INVAL, "bs_upload_groups: null column");
+  if (!in_range(t->min_res, (size_t)L * G)) return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
+  for (uint32_t g = 0; g < G; ++g)
+    if (t->creation_ns[g] == INT64_MAX) return fail(e, BS_E_RANGE, "bs_upload_groups: creation_ns == INT64_MAX");
+  CK(cudaSetDevice(e->device));
+  const uint32_t Gp = std::max(G, 1u);
+  int rc;
+  if ((rc = upload_vec(e, e->d_min_member, t->min_member, G, Gp))) return rc;
+  if ((rc = upload_vec(e, e->d_scheduled, t->scheduled, G, Gp))) return rc;
+  if ((rc = upload_vec(e, e->d_matched, t->matched, G, Gp))) return rc;
+  if ((rc = upload_vec(e, e->d_gflags, t->flags, G, Gp))) return rc;
+  if ((rc = upload_lanes(e, e->d_min_res, t->min_res, L, G, Gp))) return rc;
+  if ((rc = upload_vec(e, e->d_mrpres, t->min_res_present, G, Gp))) return rc;
+  if ((rc = upload_vec(e, e->d_creation, t->creation_ns, G, Gp))) return rc;
+  if ((rc = upload_vec(e, e->d_name_rank, t->name_rank, G, Gp))) return rc;
+  CK(cudaStreamSynchronize(e->s));
+  e->h_gsel.assign(t->rep_sel, t->rep_sel + G);
+  e->h_gtol.assign(t->rep_tol, t->rep_tol + G);
+  if (e->h_wait_ns.size() != G) e->h_wait_ns.assign(G, -1);
+  e->G = G;
+  e->have_groups = true;
+  e->classes_dirty = true;
+  e->evaluated = false;
+  return BS_OK;
+}
+
+int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
+  if (!e || !t) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (t->n_lanes != e->L) return fail(e, BS_E_INVAL, "bs_upload_pods: n_lanes differs from the engine's");
+  const uint32_t P = t->n_pods, L = e->L;
+  if (P && (!t->req || !t->req_present || !t->gid || !t->sel_mask || !t->tol_mask || !t->priority ||
+            !t->ts_ns || !t->flags))
+    return fail(e, BS_E_INVAL, "bs_upload_pods: null column");
+  if (!in_range(t->req, (size_t)L * P)) return fail(e, BS_E_RANGE, "bs_upload_pods: value outside +-2^56");
+  CK(cudaSetDevice(e->device));
+  const uint32_t Pp = std::max(P, 1u);
+  int rc;
+  if ((rc = upload_lanes(e, e->d_req, t->req, L, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_ppres, t->req_present, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_gid, t->gid, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
+  // host copies: mirrors + class keys (non-zero scalar request mask, core.go:688-690)
+  e->h_gid.assign(t->gid, t->gid + P);
+  e->h_prio.assign(t->priority, t->priority + P);
+  e->h_pflags.assign(t->flags, t->flags + P);
+  e->h_psel.assign(t->sel_mask, t->sel_mask + P);
+  e->h_ptol.assign(t->tol_mask, t->tol_mask + P);
+  e->h_pnz.assign(P, 0);
+  for (uint32_t d = 4; d < L; ++d) {
+    const int64_t* row = t->req + (size_t)d * P;
+    for (uint32_t p = 0; p < P; ++p)
+      if (((t->req_present[p] >> d) & 1u) && row[p] != 0) e->h_pnz[p] |= 1u << d;
+  }
+  CK(cudaStreamSynchronize(e->s));
+  e->P = P;
+  e->have_pods = true;
+  e->classes_dirty = true;
+  e->evaluated = false;
+  return BS_OK;
+}
+
+int bs_set_wait_time(bs_engine* e, int64_t default_ns, const int64_t* per_group_ns, uint32_t n_groups) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->default_wait_ns = default_ns;
+  if (per_group_ns) e->h_wait_ns.assign(per_group_ns, per_group_ns + n_groups);
+  return BS_OK;
+}
+
+int bs_evaluate_async(bs_engine* e) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return evaluate_async_locked(e);
+}
+
+int bs_sync(bs_engine* e) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->s));
+  return BS_OK;
+}
+
+int bs_fetch(bs_engine* e, bs_results* out) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  return fetch_locked(e, out);
+}
+
+int bs_evaluate(bs_engine* e, bs_results* out) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  int rc = evaluate_async_locked(e);
+  if (rc) return rc;
+  return fetch_locked(e, out);
+}
+
+int bs_prefilter(bs_engine* e, uint32_t pod, bs_status* st) {
+  if (!e || !st) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->evaluated) return fail(e, BS_E_STATE, "bs_prefilter: evaluate first");
+  if (pod >= e->P) return BS_E_INDEX;
+  if (!e->fetched) {
+    int rc = fetch_locked(e, nullptr);
+    if (rc) return rc;
+  }
+  const uint8_t reason = e->h_prefilter.as<uint8_t>()[pod];
+  st->reason = reason;
+  // batchscheduler.go:104-107: nil -> Success, any error -> Unschedulable
+  st->code = reason == BS_PF_PASS ? BS_CODE_SUCCESS : BS_CODE_UNSCHEDULABLE;
+  const int32_t g = e->h_gid[pod];
+  st->group = (g >= 0 && (uint32_t)g < e->G) ? g : -1;
+  return BS_OK;
+}
+
+int bs_permit(bs_engine* e, uint32_t pod, uint32_t node, bs_permit_result* r) {
+  if (!e || !r) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->evaluated) return fail(e, BS_E_STATE, "bs_permit: evaluate first");
+  if (pod >= e->P || node >= e->N) return BS_E_INDEX;
+  if (!e->fetched) {
+    int rc = fetch_locked(e, nullptr);
+    if (rc) return rc;
+  }
+  const int64_t kSecond = 1000000000ll, kDefaultWait = 60 * kSecond;  // util.DefaultWaitTime k8s.go:31
+  const int32_t g = e->h_gid[pod];
+  memset(r, 0, sizeof(*r));
+  r->group = -1;
+  if (g == BS_GID_NONE) {  // core.go:270-272 + batchscheduler.go:190-193
+    r->ready = 1;
+    r->code = BS_CODE_SUCCESS;
+    r->wait_ns = 0;
+    return BS_OK;
+  }
+  if (g < 0 || (uint32_t)g >= e->G) {  // core.go:275-277 + batchscheduler.go:194-195
+    r->ready = 0;
+    r->code = BS_CODE_UNSCHEDULABLE;
+    r->wait_ns = kDefaultWait;
+    return BS_OK;
+  }
+  r->group = g;
+  // util.GetWaitTimeDuration (k8s.go:82-91) + 1s (batchscheduler.go:180-182)
+  int64_t wait = e->default_wait_ns;
+  if ((size_t)g < e->h_wait_ns.size() && e->h_wait_ns[g] >= 0) wait = e->h_wait_ns[g];
+  r->wait_ns = wait + kSecond;
+  const uint8_t a = e->h_admit.as<uint8_t>()[g];
+  r->ready = a == BS_ADMIT;              // core.go:303-307
+  r->start_signal = r->ready;            // batchscheduler.go:197-199
+  r->code = BS_CODE_WAIT;                // :184-187 and :201
+  return BS_OK;
+}
+
+int bs_less(bs_engine* e, uint32_t a, uint32_t b) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->evaluated) return fail(e, BS_E_STATE, "bs_less: evaluate first");
+  if (a >= e->P || b >= e->P) return BS_E_INDEX;
+  if (!e->fetched) {
+    int rc = fetch_locked(e, nullptr);
+    if (rc) return rc;
+  }
+  // core.go:395-399: at equal priority, two grouped pods where a lister lookup fails
+  // compare false both ways; everything else is the rank order of the device sort.
+  auto miss = [&](uint32_t p) {
+    const int32_t g = e->h_gid[p];
+    return g != BS_GID_NONE && (g < 0 || (uint32_t)g >= e->G || (e->h_pflags[p] & BS_POD_LISTER_MISS));
+  };
+  if (e->h_prio[a] == e->h_prio[b] && e->h_gid[a] != BS_GID_NONE && e->h_gid[b] != BS_GID_NONE &&
+      (miss(a) || miss(b)))
+    return 0;
+  const uint32_t* rank = e->h_rank.as<uint32_t>();
+  return rank[a] < rank[b] ? 1 : 0;
+}
+
+int bs_format_message(const bs_status* st, const char* ns_name, const char* occupied_by, char* buf,
+                      size_t buf_len) {
+  if (!st || !buf || !buf_len) return BS_E_INVAL;
+  const char* n = ns_name ? ns_name : "";
+  const char* o = occupied_by ? occupied_by : "";
+  switch (st->reason) {
+    case BS_PF_PASS: snprintf(buf, buf_len, "%s", ""); break;
+    case BS_PF_ERR_NOT_FOUND: snprintf(buf, buf_len, "can not found pod group: %s", n); break;           // core.go:102
+    case BS_PF_ERR_DENIED: snprintf(buf, buf_len, "pod with pgName: %s last failed in 20s, deny", n); break;  // :107
+    case BS_PF_ERR_OCCUPIED_NOREFS: snprintf(buf, buf_len, "pod group %s has been occupied by %s", n, o); break;  // :505
+    case BS_PF_ERR_OCCUPIED: snprintf(buf, buf_len, "pod group has been occupied by %s", o); break;      // :509
+    case BS_PF_ERR_NOT_ENOUGH: snprintf(buf, buf_len, "cluster resource not enough"); break;             // :143,:164
+    default: return BS_E_INVAL;
+  }
+  return BS_OK;
+}
+
+int bs_node_left(bs_engine* e, uint64_t sel, uint64_t tol, float percent, int64_t* left, uint32_t* present) {
+  if (!e || !left || !present) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_nodes) return fail(e, BS_E_STATE, "bs_node_left: upload nodes first");
+  CK(cudaSetDevice(e->device));
+  const uint32_t N = e->N, L = e->L;
+  if (!N) return BS_OK;
+  DevBuf dl, dp;
+  CK(dl.ensure((size_t)L * N * 8));
+  CK(dp.ensure((size_t)N * 4));
+  node_left_class_kernel<<<cdiv(N, 256), 256, 0, e->s>>>(node_tab(e), sel, tol, percent, dl.as<int64_t>(),
+                                                         dp.as<uint32_t>());
+  e->launches++;
+  cudaError_t er = cudaMemcpyAsync(left, dl.p, (size_t)L * N * 8, cudaMemcpyDeviceToHost, e->s);
+  if (er == cudaSuccess) er = cudaMemcpyAsync(present, dp.p, (size_t)N * 4, cudaMemcpyDeviceToHost, e->s);
+  if (er == cudaSuccess) er = cudaStreamSynchronize(e->s);
+  dl.release();
+  dp.release();
+  CK(er);
+  return BS_OK;
+}
+
+int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent, const int64_t* need,
+                     const uint32_t* need_present, uint32_t n_needs, uint8_t* ok) {
+  if (!e || (n_needs && (!need || !need_present || !ok))) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_nodes) return fail(e, BS_E_STATE, "bs_cluster_check: upload nodes first");
+  CK(cudaSetDevice(e->device));
+  const uint32_t N = e->N, L = e->L;
+  if (!n_needs) return BS_OK;
+  if (!N) {
+    memset(ok, 0, n_needs);  // empty snapshot list: the loop never runs (core.go:604,631)
+    return BS_OK;
+  }
+  DevBuf pre, pp, stats, dn, dnp, dok;
+  cudaError_t er = pre.ensure((size_t)L * N * 8);
+  if (er == cudaSuccess) er = pp.ensure((size_t)N * 4);
+  if (er == cudaSuccess) er = stats.ensure(sizeof(ClassStats));
+  if (er == cudaSuccess) er = dn.ensure((size_t)L * n_needs * 8);
+  if (er == cudaSuccess) er = dnp.ensure((size_t)n_needs * 4);
+  if (er == cudaSuccess) er = dok.ensure(n_needs);
+  if (er == cudaSuccess) er = cudaMemcpyAsync(dn.p, need, (size_t)L * n_needs * 8, cudaMemcpyHostToDevice, e->s);
+  if (er == cudaSuccess) er = cudaMemcpyAsync(dnp.p, need_present, (size_t)n_needs * 4, cudaMemcpyHostToDevice, e->s);
+  if (er == cudaSuccess) {
+    PrefixOut po{pre.as<int64_t>(), pp.as<uint32_t>(), stats.as<ClassStats>()};
+    NodeTab t = node_tab(e);
+    launch_prefix(L, t, nullptr, nullptr, 0, 2, sel, tol, percent, nullptr, po, 1, e->s);
+    const uint64_t threads = (uint64_t)n_needs * 32;
+    needs_check_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, e->s>>>(
+        t, po, dn.as<int64_t>(), dnp.as<uint32_t>(), n_needs, dok.as<uint8_t>());
+    e->launches += 2;
+    er = cudaMemcpyAsync(ok, dok.p, n_needs, cudaMemcpyDeviceToHost, e->s);
+  }
+  if (er == cudaSuccess) er = cudaStreamSynchronize(e->s);
+  if (er == cudaSuccess) er = cudaGetLastError();
+  pre.release(); pp.release(); stats.release(); dn.release(); dnp.release(); dok.release();
+  CK(er);
+  return BS_OK;
+}
+
+int bs_device_buffer(bs_engine* e, int which, void** dev_ptr, size_t* bytes) {
+  if (!e || !dev_ptr || !bytes) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const uint32_t P = e->P, G = e->G;
+  switch (which) {
+    case BS_BUF_FIT_BITMAP: *dev_ptr = e->d_fit_bitmap.p; *bytes = (size_t)P * e->W * 4; break;
+    case BS_BUF_SCORE: *dev_ptr = e->d_score.p; *bytes = (size_t)P * e->N * 8; break;
+    case BS_BUF_ADMIT_BITMAP: *dev_ptr = e->d_admit_bitmap.p; *bytes = (size_t)cdiv(G, 32) * 4; break;
+    case BS_BUF_PREFILTER: *dev_ptr = e->d_prefilter.p; *bytes = P; break;
+    case BS_BUF_ADMIT: *dev_ptr = e->d_admit.p; *bytes = G; break;
+    case BS_BUF_ORDER: *dev_ptr = e->d_order.p; *bytes = (size_t)P * 4; break;
+    default: return BS_E_INVAL;
+  }
+  return BS_OK;
+}
+
+void* bs_stream(bs_engine* e) { return e ? (void*)e->s : nullptr; }
+
+int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words) {
+  if (!e || !words) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->evaluated || !(e->out_flags & BS_OUT_FIT_BITMAP)) return fail(e, BS_E_STATE, "no fit bitmap materialised");
+  if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
+  CK(cudaSetDevice(e->device));
+  if (n && e->W)
+    CK(cudaMemcpyAsync(words, e->d_fit_bitmap.as<uint32_t>() + (size_t)pod0 * e->W, (size_t)n * e->W * 4,
+                       cudaMemcpyDeviceToHost, e->s));
+  CK(cudaStreamSynchronize(e->s));
+  return BS_OK;
+}
+
+int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores) {
+  if (!e || !scores) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->evaluated || !(e->out_flags & BS_OUT_SCORE)) return fail(e, BS_E_STATE, "no score matrix materialised");
+  if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
+  CK(cudaSetDevice(e->device));
+  if (n && e->N)
+    CK(cudaMemcpyAsync(scores, e->d_score.as<int64_t>() + (size_t)pod0 * e->N, (size_t)n * e->N * 8,
+                       cudaMemcpyDeviceToHost, e->s));
+  CK(cudaStreamSynchronize(e->s));
+  return BS_OK;
+}
+
+int bs_set_profiling(bs_engine* e, int on) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->profiling = on != 0;
+  return BS_OK;
+}
+
+int bs_kernel_ms(bs_engine* e, int k, float* ms, uint32_t* launches) {
+  if (!e || k < 0 || k >= BS_K_COUNT) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (launches) *launches = e->k_launches[k];
+  if (ms) {
+    *ms = 0.f;
+    if (e->profiling && e->k_valid[k]) {
+      CK(cudaSetDevice(e->device));
+      CK(cudaEventSynchronize(e->ev_b[k]));
+      CK(cudaEventElapsedTime(ms, e->ev_a[k], e->ev_b[k]));
+    }
+  }
+  return BS_OK;
+}
+
+uint64_t bs_launch_count(const bs_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

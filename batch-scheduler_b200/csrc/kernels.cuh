@@ -1,0 +1,914 @@
+// kernels.cuh — sm_100a kernels of the gang-scheduling feasibility engine.
+//
+// Every kernel cites the reference lines it restates (tenstack/batch-scheduler,
+// pkg/scheduler/core/core.go).  All arithmetic is int64 / uint32 / one float32
+// multiply per node lane; there is no dense contraction, so no tensor cores.
+// Tables are lane-major SoA in HBM (see include/bsched.h); the node table is
+// padded to a multiple of NODE_TILE so tiles can be moved with 1-D TMA bulk
+// copies (cp.async.bulk, 16-byte granules).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bsched.h"
+
+namespace bsk {
+
+constexpr int LANE_CPU = 0, LANE_MEM = 1, LANE_EPH = 2, LANE_PODS = 3;
+// Sentinels for lanes without a map key.  With |table values| <= BS_VALUE_LIMIT = 2^56,
+// |left| <= 2^57 and every real left-req difference is below 2^58 in magnitude, while any
+// difference involving a sentinel is >= 2^61 - 2^57 and < 2^63: it never overflows, never
+// fails the >= 0 test, and never wins the min -> score = min over lanes present on BOTH sides.
+constexpr int64_t ABSENT_LEFT = (int64_t)1 << 61;      // left lane without a map key: never limits
+constexpr int64_t UNCHECKED_REQ = -((int64_t)1 << 61); // request lane without a map key: never checked
+constexpr int NODE_TILE = 512;                          // nodes per shared-memory tile
+constexpr int FIT_THREADS = 256;
+constexpr int FIT_WARPS = FIT_THREADS / 32;
+constexpr int PODS_PER_WARP = 8;
+constexpr int POD_BLOCK = 4;                            // pods evaluated together per node (ILP)
+constexpr int PODS_PER_CTA = FIT_WARPS * PODS_PER_WARP; // 64
+
+// round-global scalars living in device memory (no host sync inside a round)
+struct RoundState {
+  int32_t max_group;      // findMaxPG winner or -1
+  uint32_t max_finished;
+  uint32_t max_matched;   // matched[max_group]
+  int32_t case_a;         // 1: matched==0 branch (core.go:136), pct 1.0, need of the pod's own group
+  int32_t ref_panic;      // findMaxPG would divide by zero
+  int32_t max_class;      // rep class of max_group (case B)
+  int32_t pad0, pad1;
+  int64_t base_need[BS_MAX_LANES]; // getPreAllocatedResource(max, matched) (case B, core.go:157)
+  uint32_t base_present;
+};
+
+// per rep-class statistics of the ordered prefix scan (compareClusterResourceAndRequire)
+struct ClassStats {
+  int64_t maxv[BS_MAX_LANES];    // max prefix value per lane over visited prefixes (present ones for scalars)
+  int32_t argmax[BS_MAX_LANES];  // a prefix index attaining it (-1 none)
+  uint32_t any_absent;           // scalar lanes absent at some visited prefix
+  int32_t last_visited;          // last visited node index, -1 if none
+};
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int64_t scale_f32(int64_t alloc, float pct) {
+  // core.go:656-659,667: int64(float32(alloc) * percent) — RN convert, RN multiply
+  // (no FMA contraction possible on a lone multiply), truncating convert back.
+  return __float2ll_rz(__fmul_rn(__ll2float_rn(alloc), pct));
+}
+
+__device__ __forceinline__ bool node_skipped(uint8_t f) {
+  // core.go:606-617
+  return (f & (BS_NODE_NIL | BS_NODE_NO_NODE | BS_NODE_UNSCHEDULABLE)) != 0;
+}
+
+__device__ __forceinline__ bool check_fit(uint64_t label, uint64_t taint, uint64_t sel, uint64_t tol) {
+  // core.go:741-759 with both predicates pre-encoded as bit sets
+  return ((label & sel) == sel) && ((taint & ~tol) == 0);
+}
+
+struct NodeTab {
+  const int64_t* alloc;      // [L][Npad]
+  const int64_t* requested;  // [L][Npad]
+  const int32_t* pod_count;
+  const uint32_t* alloc_present;
+  const uint32_t* req_present;
+  const uint64_t* label;
+  const uint64_t* taint;
+  const uint8_t* flags;
+  uint32_t N, Npad, L;
+};
+
+// singleNodeResource (core.go:634-670) for node i and class (sel,tol) at pct;
+// returns the scalar presence mask; v[] gets every lane (zeros when unfit).
+template <int MAXL>
+__device__ __forceinline__ uint32_t single_node_resource(const NodeTab& t, uint32_t i, uint64_t sel,
+                                                         uint64_t tol, float pct, int64_t* v) {
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) v[d] = 0;
+  const uint8_t f = t.flags[i];
+  if (f & BS_NODE_TAINTS_ERR) return 0;                                  // :639-641
+  if (!check_fit(t.label[i], t.taint[i], sel, tol)) return 0;           // :642-645
+  int64_t pc = t.requested[(size_t)LANE_PODS * t.Npad + i];              // :650-653
+  if (pc == 0) pc = t.pod_count[i];
+  v[LANE_PODS] = scale_f32(t.alloc[(size_t)LANE_PODS * t.Npad + i], pct) - pc;  // :656
+#pragma unroll
+  for (int d = 0; d < 3; ++d)                                            // :657-659
+    v[d] = scale_f32(t.alloc[(size_t)d * t.Npad + i], pct) - t.requested[(size_t)d * t.Npad + i];
+  const uint32_t both = t.alloc_present[i] & t.req_present[i] & ~0xFu;   // :662-666
+  uint32_t present = 0;
+#pragma unroll
+  for (int d = 4; d < MAXL; ++d) {
+    if (d < (int)t.L && (both >> d) & 1u) {
+      v[d] = scale_f32(t.alloc[(size_t)d * t.Npad + i], pct) - t.requested[(size_t)d * t.Npad + i]; // :667
+      present |= 1u << d;
+    }
+  }
+  return present;
+}
+
+// compareResourceAndRequire (core.go:672-699) on lane arrays + presence masks
+__device__ __forceinline__ bool compare_res(const int64_t* left, uint32_t lpres, const int64_t* req,
+                                            uint32_t rpres, int L) {
+  bool ok = (left[LANE_MEM] >= req[LANE_MEM]) & (left[LANE_CPU] >= req[LANE_CPU]) &
+            (left[LANE_EPH] >= req[LANE_EPH]) & (left[LANE_PODS] >= req[LANE_PODS]);
+  for (int d = 4; d < L; ++d) {
+    const uint32_t bit = 1u << d;
+    if (!(rpres & bit)) continue;                 // :686 only keys of req
+    if (!(lpres & bit)) ok &= (req[d] == 0);      // :688-692
+    else ok &= (req[d] <= left[d]);               // :694
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------------------
+// K1  node_left_kernel — per node: residual capacity at percent 1.0 in the
+// sentinel form the fit kernel consumes (absent scalar lane -> ABSENT_LEFT),
+// class-independent (checkFit is applied per pod class by class_fit_kernel).
+// Restates singleNodeResource core.go:647-668.  Padding nodes (>= N) get zeros.
+__global__ void node_left_kernel(NodeTab t, int64_t* __restrict__ left_eff /*[L][Npad]*/,
+                                 uint32_t* __restrict__ left_present /*[Npad]*/) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.Npad) return;
+  if (i >= t.N) {
+    for (uint32_t d = 0; d < t.L; ++d) left_eff[(size_t)d * t.Npad + i] = 0;
+    left_present[i] = 0;
+    return;
+  }
+  int64_t pc = t.requested[(size_t)LANE_PODS * t.Npad + i];
+  if (pc == 0) pc = t.pod_count[i];
+  left_eff[(size_t)LANE_PODS * t.Npad + i] = scale_f32(t.alloc[(size_t)LANE_PODS * t.Npad + i], 1.0f) - pc;
+  for (int d = 0; d < 3; ++d)
+    left_eff[(size_t)d * t.Npad + i] =
+        scale_f32(t.alloc[(size_t)d * t.Npad + i], 1.0f) - t.requested[(size_t)d * t.Npad + i];
+  const uint32_t both = t.alloc_present[i] & t.req_present[i] & ~0xFu;
+  for (uint32_t d = 4; d < t.L; ++d) {
+    int64_t v = ABSENT_LEFT;
+    if ((both >> d) & 1u)
+      v = scale_f32(t.alloc[(size_t)d * t.Npad + i], 1.0f) - t.requested[(size_t)d * t.Npad + i];
+    left_eff[(size_t)d * t.Npad + i] = v;
+  }
+  left_present[i] = both;
+}
+
+// generic singleNodeResource table for one class (bs_node_left): left[L][N], present[N]
+__global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, float pct,
+                                       int64_t* __restrict__ left, uint32_t* __restrict__ present) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.N) return;
+  int64_t v[BS_MAX_LANES];
+  const uint32_t pres = single_node_resource<BS_MAX_LANES>(t, i, sel, tol, pct, v);
+  for (uint32_t d = 0; d < t.L; ++d) left[(size_t)d * t.N + i] = v[d];
+  present[i] = pres;
+}
+
+// K1b  class_fit_kernel — one bit per (pod class, node): node not skipped
+// (core.go:606-617), Taints() ok (:639), checkFit (:741-759), and every scalar
+// key the class requests with a non-zero amount exists in `left`
+// (compareResourceAndRequire :688-690).  Word w of class c: classfit[c*W + w].
+__global__ void class_fit_kernel(NodeTab t, const uint32_t* __restrict__ left_present,
+                                 const uint64_t* __restrict__ csel, const uint64_t* __restrict__ ctol,
+                                 const uint32_t* __restrict__ cnz, uint32_t n_classes, uint32_t W,
+                                 uint32_t* __restrict__ classfit) {
+  const uint32_t c = blockIdx.y;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // node (may be >= N inside the last word)
+  bool ok = false;
+  if (i < t.N) {
+    const uint8_t f = t.flags[i];
+    ok = !node_skipped(f) && !(f & BS_NODE_TAINTS_ERR) &&
+         check_fit(t.label[i], t.taint[i], csel[c], ctol[c]) && ((cnz[c] & ~left_present[i]) == 0);
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && (i >> 5) < W) classfit[(size_t)c * W + (i >> 5)] = word;
+}
+
+// ---------------------------------------------------------------------------
+// K2  group preparation: what fillOccupiedObj (core.go:477-512) leaves behind
+// once the first pod of each group (table order) has reached it.
+struct GroupTab {
+  const uint32_t* min_member;
+  const uint32_t* scheduled;
+  const uint32_t* matched;
+  const uint8_t* flags;
+  const int64_t* min_res;  // [L][G]
+  const uint32_t* min_res_present;
+  const uint32_t* rep_class;  // rep-class id of the carried-in pgs.Pod
+  uint32_t G, L;
+};
+struct PodTab {
+  const int64_t* req;  // [L][P]
+  const uint32_t* req_present;
+  const int32_t* gid;
+  const uint8_t* flags;
+  const uint32_t* fit_class;  // (sel,tol,nzmask) class
+  const uint32_t* rep_class;  // (sel,tol) class
+  uint32_t P, L;
+};
+struct GroupEff {
+  uint8_t* flags;
+  int64_t* min_res;  // [L][G]
+  uint32_t* min_res_present;
+  uint32_t* rep_class;
+  uint32_t* first_pod;  // lowest pod index reaching fillOccupiedObj, 0xffffffff none
+  uint32_t* in_round;   // pods of the group in this round
+  uint32_t* contrib;    // pods that passed PreFilter and fit somewhere
+  uint32_t* done;       // pods whose fit row is finished (ticket)
+};
+
+__global__ void group_reset_kernel(GroupTab g, GroupEff e, uint8_t* __restrict__ new_denied,
+                                   uint32_t* __restrict__ admit_bitmap, uint8_t* __restrict__ okA) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.G) {
+    e.first_pod[i] = 0xffffffffu;
+    e.in_round[i] = 0;
+    e.contrib[i] = 0;
+    e.done[i] = 0;
+    new_denied[i] = 0;
+    okA[i] = 0;
+  }
+  if (i < (g.G + 31) / 32) admit_bitmap[i] = 0;
+}
+
+__global__ void group_first_pod_kernel(PodTab p, GroupTab g, GroupEff e) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.P) return;
+  const int32_t gi = p.gid[i];
+  if (gi < 0 || (uint32_t)gi >= g.G) return;
+  atomicAdd(&e.in_round[gi], 1u);
+  // reaches fillOccupiedObj: not recently permitted (core.go:95-98), group not frozen (:105-110)
+  if (p.flags[i] & BS_POD_PERMITTED_RECENTLY) return;
+  if (g.flags[gi] & BS_GROUP_DENIED) return;
+  atomicMin(&e.first_pod[gi], i);
+}
+
+__global__ void group_effective_kernel(PodTab p, GroupTab g, GroupEff e) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.G) return;
+  uint8_t f = g.flags[i];
+  const uint32_t fp = e.first_pod[i];
+  uint32_t rc = g.rep_class[i];
+  const bool take_pod = fp != 0xffffffffu && !(f & BS_GROUP_HAS_POD);        // core.go:486-488
+  const bool take_res = fp != 0xffffffffu && !(f & BS_GROUP_HAS_MINRES);     // core.go:489-493
+  if (take_pod) { f |= BS_GROUP_HAS_POD; rc = p.rep_class[fp]; }
+  uint32_t mrp = g.min_res_present[i];
+  if (take_res) {
+    f |= BS_GROUP_HAS_MINRES;
+    mrp = p.req_present[fp] & ~0xFu;
+    for (uint32_t d = 0; d < g.L; ++d) {
+      const bool pres = d < 4 || ((mrp >> d) & 1u);
+      e.min_res[(size_t)d * g.G + i] = pres ? p.req[(size_t)d * p.P + fp] : 0;
+    }
+  } else {
+    for (uint32_t d = 0; d < g.L; ++d) e.min_res[(size_t)d * g.G + i] = g.min_res[(size_t)d * g.G + i];
+  }
+  e.flags[i] = f;
+  e.min_res_present[i] = mrp;
+  e.rep_class[i] = rc;
+}
+
+// getPreAllocatedResource (core.go:774-793) from the effective columns
+__device__ __forceinline__ uint32_t pre_allocated(const GroupTab& g, const GroupEff& e, uint32_t gi,
+                                                  int64_t matched, int64_t* need) {
+  for (uint32_t d = 0; d < BS_MAX_LANES; ++d) need[d] = 0;
+  const int64_t mm = (int64_t)g.min_member[gi];
+  const int64_t not_finished = matched != 0 ? mm - matched : mm - (int64_t)g.scheduled[gi];  // :778-783
+  uint32_t present = 0;
+  if (not_finished > 0 && (e.flags[gi] & BS_GROUP_HAS_MINRES)) {                              // :784-788
+    present = e.min_res_present[gi];
+    for (uint32_t d = 0; d < g.L; ++d) {
+      if (d >= 4 && !((present >> d) & 1u)) continue;
+      need[d] = (int64_t)((uint64_t)e.min_res[(size_t)d * g.G + gi] * (uint64_t)not_finished);
+    }
+  }
+  if (need[LANE_PODS] == 0) need[LANE_PODS] = mm + 1;                                         // :789-791
+  return present;
+}
+
+// K3  find_max_pg_kernel — findMaxPG (core.go:701-739) as a parallel reduction
+// that reproduces the sequential table-order scan exactly (tie rule :725-735):
+//   F  = max finished over eligible groups; c0 = first index attaining F;
+//   if c0 is not "finished" (scheduled < minMember) it wins; otherwise the scan
+//   hands over to later F-candidates with Status.Scheduled==0 while the current
+//   holder is finished: the first of them with minMember!=0 wins, else the last.
+// One CTA of 1024 threads; G <= ~10^5 so three strided passes are a few us.
+__global__ void __launch_bounds__(1024) find_max_pg_kernel(GroupTab g, GroupEff e, RoundState* st) {
+  __shared__ uint32_t s_u32[32];
+  __shared__ uint32_t s_val;
+  __shared__ int s_panic;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  auto block_reduce = [&](uint32_t v, bool is_max) -> uint32_t {
+    for (int o = 16; o; o >>= 1) {
+      const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? max(v, w) : min(v, w);
+    }
+    __syncthreads();
+    if (lane == 0) s_u32[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      v = s_u32[lane];
+      for (int o = 16; o; o >>= 1) {
+        const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? max(v, w) : min(v, w);
+      }
+      if (lane == 0) s_val = v;
+    }
+    __syncthreads();
+    return s_val;
+  };
+  auto eligible = [&](uint32_t i) -> bool {
+    const uint8_t f = e.flags[i];
+    return !(f & BS_GROUP_SCHEDULED) && (f & BS_GROUP_HAS_POD);  // :706-711
+  };
+  auto finished = [&](uint32_t i, bool& panic) -> uint32_t {
+    const uint32_t mm = g.min_member[i], sc = g.scheduled[i];
+    if ((uint32_t)(mm - sc) == 0u) return 0u;                    // :712-714 (uint32: <=0 means ==0)
+    if (mm == 0u) { panic = true; return 0u; }                   // :716-717 integer divide by zero
+    return (uint32_t)((g.matched[i] + sc) * 1000u) / mm;         // :716-717 uint32 wrap-around
+  };
+  if (tid == 0) s_panic = 0;
+  __syncthreads();
+  // pass 1: any eligible? F = max finished (encode "none" as 0, track any separately)
+  uint32_t fmax = 0, any = 0;
+  bool panic = false;
+  for (uint32_t i = tid; i < g.G; i += blockDim.x)
+    if (eligible(i)) { any = 1; fmax = max(fmax, finished(i, panic)); }
+  if (panic) s_panic = 1;
+  any = block_reduce(any, true);
+  const uint32_t F = block_reduce(fmax, true);
+  // pass 2: c0 = first eligible index with finished == F
+  uint32_t c0 = 0xffffffffu;
+  for (uint32_t i = tid; i < g.G; i += blockDim.x)
+    if (eligible(i)) { bool pn = false; if (finished(i, pn) == F) { c0 = i; break; } }
+  c0 = block_reduce(c0, false);
+  uint32_t winner = c0;
+  if (any && c0 != 0xffffffffu && g.scheduled[c0] >= g.min_member[c0]) {   // holder is "finished" (:730)
+    // pass 3: later F-candidates with Status.Scheduled == 0 (:731)
+    uint32_t zgood = 0xffffffffu, zlast = 0;  // zlast stores index+1
+    for (uint32_t i = c0 + 1 + tid; i < g.G; i += blockDim.x) {
+      if (!eligible(i)) continue;
+      bool pn = false;
+      if (finished(i, pn) != F || g.scheduled[i] != 0) continue;
+      if (g.min_member[i] != 0) zgood = min(zgood, i);
+      zlast = max(zlast, i + 1);
+    }
+    zgood = block_reduce(zgood, false);
+    zlast = block_reduce(zlast, true);
+    if (zgood != 0xffffffffu) {
+      // every earlier Z element has minMember==0 only if none of them stops the chain first:
+      // an earlier Z element with minMember!=0 would itself be zgood, so zgood is the stop.
+      winner = zgood;
+    } else if (zlast != 0) {
+      winner = zlast - 1;
+    }
+  }
+  if (tid == 0) {
+    const bool none = !any || c0 == 0xffffffffu;
+    st->ref_panic = s_panic;
+    st->max_group = none ? -1 : (int32_t)winner;
+    st->max_finished = none ? 0u : F;
+    st->max_matched = none ? 0u : g.matched[winner];
+    st->case_a = (!none && g.matched[winner] == 0) ? 1 : 0;              // core.go:135-136
+    st->max_class = none ? -1 : (int32_t)e.rep_class[winner];
+    st->base_present = 0;
+    for (int d = 0; d < BS_MAX_LANES; ++d) st->base_need[d] = 0;
+    if (!none && g.matched[winner] != 0) {
+      int64_t need[BS_MAX_LANES];
+      st->base_present = pre_allocated(g, e, winner, (int64_t)g.matched[winner], need);  // core.go:157
+      for (int d = 0; d < BS_MAX_LANES; ++d) st->base_need[d] = need[d];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4  class_prefix_kernel — the ordered scan of compareClusterResourceAndRequire
+// (core.go:595-632) for one rep class: running[i] = sum over visited nodes j<=i
+// of singleNodeResource(node_j, class, pct) with scalar keys accumulating as a
+// union (Resource.Add, :621).  One CTA per class; thread t owns a contiguous
+// run of nodes, block-wide exclusive scan of the per-thread totals in between.
+// mode 0: every class c in [c0, c0+gridDim.x) at pct 1.0, only when case A;
+// mode 1: the class of the max group at pct 0.7, only when case B (blockIdx 0);
+// mode 2: unconditional, explicit (sel,tol,pct) — bs_cluster_check.
+constexpr int PREFIX_THREADS = 256;
+struct PrefixOut {
+  int64_t* pre;       // [classes][L][N]
+  uint32_t* present;  // [classes][N]
+  ClassStats* stats;  // [classes]
+};
+
+template <int MAXL>
+__global__ void __launch_bounds__(PREFIX_THREADS)
+class_prefix_kernel(NodeTab t, const uint64_t* __restrict__ rsel, const uint64_t* __restrict__ rtol,
+                    uint32_t c0, int mode, uint64_t xsel, uint64_t xtol, float xpct,
+                    const RoundState* __restrict__ st, PrefixOut out) {
+  uint32_t c_out = blockIdx.x;
+  uint64_t sel, tol;
+  float pct;
+  if (mode == 0) {
+    if (!st->case_a || st->max_group < 0) return;
+    sel = rsel[c0 + blockIdx.x]; tol = rtol[c0 + blockIdx.x]; pct = 1.0f;
+  } else if (mode == 1) {
+    if (st->case_a || st->max_group < 0) return;
+    sel = rsel[st->max_class]; tol = rtol[st->max_class]; pct = 0.7f;
+  } else {
+    sel = xsel; tol = xtol; pct = xpct;
+  }
+  const uint32_t N = t.N, L = t.L;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t per = (N + PREFIX_THREADS - 1) / PREFIX_THREADS;
+  const uint32_t n0 = min(tid * per, N), n1 = min(n0 + per, N);
+  __shared__ int64_t s_warp[32][MAXL];
+  __shared__ uint32_t s_wpres[32];
+  __shared__ int s_last[32];
+
+  // pass A: per-thread totals
+  int64_t tot[MAXL];
+  int64_t v[MAXL];
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) tot[d] = 0;
+  uint32_t tpres = 0;
+  for (uint32_t i = n0; i < n1; ++i) {
+    if (node_skipped(t.flags[i])) continue;
+    tpres |= single_node_resource<MAXL>(t, i, sel, tol, pct, v);
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) tot[d] += v[d];
+  }
+  // block exclusive scan of (tot, tpres): warp inclusive scan, then warp offsets
+  int64_t inc[MAXL];
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) inc[d] = tot[d];
+  uint32_t ipres = tpres;
+  for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) {
+      const int64_t w = __shfl_up_sync(0xffffffffu, inc[d], o);
+      if ((int)lane >= o) inc[d] += w;
+    }
+    const uint32_t wp = __shfl_up_sync(0xffffffffu, ipres, o);
+    if ((int)lane >= o) ipres |= wp;
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) s_warp[wid][d] = inc[d];
+    s_wpres[wid] = ipres;
+  }
+  __syncthreads();
+  int64_t run[MAXL];
+  uint32_t rpres = 0;
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) run[d] = inc[d] - tot[d];  // exclusive within the warp
+  {
+    uint32_t ex = __shfl_up_sync(0xffffffffu, ipres, 1);
+    rpres = lane ? ex : 0u;
+  }
+  for (uint32_t w = 0; w < wid; ++w) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) run[d] += s_warp[w][d];
+    rpres |= s_wpres[w];
+  }
+  // pass B: write prefixes, gather stats
+  int64_t* pre = out.pre + (size_t)c_out * L * N;
+  uint32_t* pp = out.present + (size_t)c_out * N;
+  int64_t mx[MAXL];
+  int amx[MAXL];
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) { mx[d] = INT64_MIN; amx[d] = -1; }
+  uint32_t absent = 0;
+  int last = -1;
+  for (uint32_t i = n0; i < n1; ++i) {
+    const bool vis = !node_skipped(t.flags[i]);
+    if (vis) {
+      rpres |= single_node_resource<MAXL>(t, i, sel, tol, pct, v);
+#pragma unroll
+      for (int d = 0; d < MAXL; ++d) run[d] += v[d];
+      last = (int)i;
+      absent |= ~rpres;
+#pragma unroll
+      for (int d = 0; d < MAXL; ++d) {
+        const bool pres = d < 4 || ((rpres >> d) & 1u);
+        if (pres && (amx[d] < 0 || run[d] > mx[d])) { mx[d] = run[d]; amx[d] = (int)i; }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d)
+      if (d < (int)L) pre[(size_t)d * N + i] = run[d];
+    pp[i] = rpres;
+  }
+  // block reduce stats
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) {
+      const int64_t om = __shfl_xor_sync(0xffffffffu, mx[d], o);
+      const int oa = __shfl_xor_sync(0xffffffffu, amx[d], o);
+      if (oa >= 0 && (amx[d] < 0 || om > mx[d])) { mx[d] = om; amx[d] = oa; }
+    }
+    absent |= __shfl_xor_sync(0xffffffffu, absent, o);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  __syncthreads();  // s_warp reuse
+  __shared__ int s_amx[32][MAXL];
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) { s_warp[wid][d] = mx[d]; s_amx[wid][d] = amx[d]; }
+    s_wpres[wid] = absent;
+    s_last[wid] = last;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ClassStats cs;
+    for (int d = 0; d < BS_MAX_LANES; ++d) { cs.maxv[d] = INT64_MIN; cs.argmax[d] = -1; }
+    cs.any_absent = 0;
+    cs.last_visited = -1;
+    for (int w = 0; w < PREFIX_THREADS / 32; ++w) {
+      for (int d = 0; d < MAXL; ++d)
+        if (s_amx[w][d] >= 0 && (cs.argmax[d] < 0 || s_warp[w][d] > cs.maxv[d])) {
+          cs.maxv[d] = s_warp[w][d]; cs.argmax[d] = s_amx[w][d];
+        }
+      cs.any_absent |= s_wpres[w];
+      cs.last_visited = max(cs.last_visited, s_last[w]);
+    }
+    out.stats[c_out] = cs;
+  }
+}
+
+// Does any visited prefix of class slot `c` satisfy `need`?  Exact:
+//   1. per-lane bound: lane d can pass somewhere only if need<=max prefix, or the
+//      key is absent somewhere and need==0 (compareResourceAndRequire :686-697);
+//   2. candidates: the last visited prefix and each lane's argmax prefix;
+//   3. otherwise scan every visited prefix (strided over `nthreads` callers).
+// Called by a full warp; returns the warp-uniform answer.
+__device__ __forceinline__ bool prefix_satisfies_at(const int64_t* pre, const uint32_t* pp, uint32_t N,
+                                                    int L, uint32_t i, const int64_t* need,
+                                                    uint32_t npres) {
+  int64_t lv[BS_MAX_LANES];
+  for (int d = 0; d < L; ++d) lv[d] = pre[(size_t)d * N + i];
+  return compare_res(lv, pp[i], need, npres, L);
+}
+
+__device__ bool warp_cluster_check(const NodeTab& t, const PrefixOut& po, uint32_t c,
+                                   const int64_t* need, uint32_t npres) {
+  const uint32_t N = t.N;
+  const int L = (int)t.L;
+  const ClassStats& cs = po.stats[c];
+  const int64_t* pre = po.pre + (size_t)c * L * N;
+  const uint32_t* pp = po.present + (size_t)c * N;
+  const uint32_t lane = threadIdx.x & 31;
+  if (cs.last_visited < 0) return false;  // no node visited: loop body never compares (core.go:631)
+  // 1. bounds
+  for (int d = 0; d < L; ++d) {
+    const bool checked = d < 4 || ((npres >> d) & 1u);
+    if (!checked) continue;
+    const bool via_present = cs.argmax[d] >= 0 && need[d] <= cs.maxv[d];
+    const bool via_absent = d >= 4 && ((cs.any_absent >> d) & 1u) && need[d] == 0;
+    if (!via_present && !via_absent) return false;
+  }
+  // 2. candidates (lane k tests candidate k)
+  bool hit = false;
+  if ((int)lane <= L) {
+    const int idx = lane == 0 ? cs.last_visited : cs.argmax[lane - 1];
+    if (idx >= 0) hit = prefix_satisfies_at(pre, pp, N, L, (uint32_t)idx, need, npres);
+  }
+  if (__any_sync(0xffffffffu, hit)) return true;
+  // 3. full ordered scan (any visited prefix)
+  for (uint32_t base = 0; base < N; base += 32) {
+    const uint32_t i = base + lane;
+    bool ok = false;
+    if (i < N && !node_skipped(t.flags[i])) ok = prefix_satisfies_at(pre, pp, N, L, i, need, npres);
+    if (__any_sync(0xffffffffu, ok)) return true;
+  }
+  return false;
+}
+
+// K5a group_check_kernel — case A (core.go:136-147): per group, need =
+// getPreAllocatedResource(own group, 0) against its own rep class at pct 1.0.
+// One warp per group; classes [c0, c0+nc) are resident in `po`.
+__global__ void group_check_kernel(NodeTab t, GroupTab g, GroupEff e, PrefixOut po, uint32_t c0,
+                                   uint32_t nc, const RoundState* __restrict__ st,
+                                   uint8_t* __restrict__ okA) {
+  if (!st->case_a || st->max_group < 0) return;
+  const uint32_t gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gi >= g.G) return;
+  if (e.in_round[gi] == 0 || !(e.flags[gi] & BS_GROUP_HAS_POD)) return;
+  const uint32_t c = e.rep_class[gi];
+  if (c < c0 || c >= c0 + nc) return;
+  int64_t need[BS_MAX_LANES];
+  const uint32_t npres = pre_allocated(g, e, gi, 0, need);
+  const bool ok = warp_cluster_check(t, po, c - c0, need, npres);
+  if ((threadIdx.x & 31) == 0) okA[gi] = ok ? 1 : 2;
+}
+
+// K5b prefilter_kernel — ScheduleOperation.PreFilter per pod (core.go:88-167)
+// against the frozen round state.  One warp per pod (the case-B cluster check
+// is a warp-wide prefix search).
+__global__ void prefilter_kernel(NodeTab t, PodTab p, GroupTab g, GroupEff e, PrefixOut po,
+                                 const RoundState* __restrict__ st, const uint8_t* __restrict__ okA,
+                                 uint8_t* __restrict__ prefilter, uint8_t* __restrict__ new_denied) {
+  const uint32_t pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pi >= p.P) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const int32_t gi = p.gid[pi];
+  const uint8_t pf = p.flags[pi];
+  uint8_t code = BS_PF_PASS;
+  bool deny = false;
+  if (gi == BS_GID_NONE) code = BS_PF_PASS;                                   // :89-92
+  else if (pf & BS_POD_PERMITTED_RECENTLY) code = BS_PF_PASS;                 // :95-98
+  else if (gi < 0 || (uint32_t)gi >= g.G) code = BS_PF_ERR_NOT_FOUND;         // :100-103
+  else if (g.flags[gi] & BS_GROUP_DENIED) code = BS_PF_ERR_DENIED;            // :105-110
+  else if (pf & BS_POD_OCC_NOREFS) code = BS_PF_ERR_OCCUPIED_NOREFS;          // :504-506
+  else if (pf & BS_POD_OCC_MISMATCH) code = BS_PF_ERR_OCCUPIED;               // :507-510
+  else if (st->max_group < 0) code = BS_PF_PASS;                              // :127-130
+  else if (st->case_a) {                                                      // :136-147
+    if (okA[gi] == 2) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
+  } else if (st->max_group == gi) code = BS_PF_PASS;                          // :150-155
+  else {                                                                      // :157-165
+    int64_t need[BS_MAX_LANES];
+    uint32_t npres = st->base_present;
+    const uint32_t rp = p.req_present[pi] & ~0xFu;
+    for (uint32_t d = 0; d < BS_MAX_LANES; ++d) need[d] = st->base_need[d];
+    for (uint32_t d = 0; d < p.L; ++d)                                        // :159 Add(pod require)
+      if (d < 4 || ((rp >> d) & 1u)) need[d] += p.req[(size_t)d * p.P + pi];
+    npres |= rp;
+    if (!warp_cluster_check(t, po, 0, need, npres)) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
+  }
+  if (lane == 0) {
+    prefilter[pi] = code;
+    if (deny) new_denied[gi] = 1;                                             // :142,:163
+  }
+}
+
+// explicit needs against class slot 0 (bs_cluster_check); one warp per need
+__global__ void needs_check_kernel(NodeTab t, PrefixOut po, const int64_t* __restrict__ need /*[L][n]*/,
+                                   const uint32_t* __restrict__ need_present, uint32_t n_needs,
+                                   uint8_t* __restrict__ ok) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_needs) return;
+  int64_t nd[BS_MAX_LANES];
+  for (uint32_t d = 0; d < BS_MAX_LANES; ++d) nd[d] = d < t.L ? need[(size_t)d * n_needs + i] : 0;
+  const bool r = warp_cluster_check(t, po, 0, nd, need_present[i] & ~0xFu);
+  if ((threadIdx.x & 31) == 0) ok[i] = r ? 1 : 0;
+}
+
+// groups with no pod in the round are decided up front (core.go:303 on carried-in state)
+__global__ void group_idle_admit_kernel(GroupTab g, GroupEff e, uint8_t* __restrict__ admit,
+                                        uint32_t* __restrict__ admit_bitmap) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.G || e.in_round[i] != 0) return;
+  const bool ready = g.matched[i] >= (uint32_t)(g.min_member[i] - g.scheduled[i]);
+  admit[i] = ready ? BS_ADMIT : BS_WAIT;
+  if (ready) atomicOr(&admit_bitmap[i >> 5], 1u << (i & 31));
+}
+
+// ---------------------------------------------------------------------------
+// K6  gang_fit_kernel — THE hot kernel.  For every (pod, node) pair:
+//   fit   = classfit bit  AND  min_d(left_d - req_d) >= 0
+//           (compareResourceAndRequire(singleNodeResource(node,pod,1), require(pod)),
+//            core.go:634-699, as asserted by core_test.go:108-110)
+//   score = fit ? min_d(left_d - req_d) : INT64_MIN      (residual capacity)
+// then, in the same launch, per pod: feasible count + best node (warp shuffles),
+// and per group: the Permit readiness count (core.go:303) by a warp-segmented
+// reduction + one atomic per run, the last pod of a group (ticket) writing the
+// admit / Wait / Unschedulable verdict.
+//
+// Mapping: a CTA owns PODS_PER_CTA pods (each warp PODS_PER_WARP of them) and
+// sweeps the whole node table in tiles of NODE_TILE nodes, staged into shared
+// memory by 1-D TMA bulk copies (one per lane row) on a 2-stage mbarrier ring.
+// A lane owns nodes lane, lane+32, ... of the tile, keeps their `left` in
+// registers and evaluates POD_BLOCK pods against them at a time.  Score rows are
+// written with 8-byte streaming stores, 256 contiguous bytes per warp store.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+struct FitArgs {
+  const int64_t* left_eff;   // [L][Npad]
+  const uint32_t* classfit;  // [classes][W]
+  const int64_t* req;        // [L][P]
+  const uint32_t* req_present;
+  const uint32_t* fit_class;
+  const int32_t* gid;
+  const uint8_t* prefilter;
+  // group side
+  const uint32_t* min_member;
+  const uint32_t* scheduled;
+  const uint32_t* matched;
+  uint32_t* in_round;
+  uint32_t* contrib;
+  uint32_t* done;
+  uint8_t* admit;
+  uint32_t* admit_bitmap;
+  // outputs
+  uint32_t* feasible_count;
+  int32_t* best_node;
+  int64_t* best_score;
+  uint32_t* fit_bitmap;  // [P][W] or null
+  int64_t* score;        // [P][N] or null
+  uint32_t P, N, Npad, W, G;
+};
+
+template <int L>
+__global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? 2 : 1)) gang_fit_kernel(FitArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [2 stages][L][NODE_TILE] int64 | [PODS_PER_CTA][L] int64 | mbarriers
+  int64_t* s_tile = reinterpret_cast<int64_t*>(smem_raw);
+  int64_t* s_req = s_tile + 2 * L * NODE_TILE;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_req + PODS_PER_CTA * L);
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t pod0 = blockIdx.x * PODS_PER_CTA;
+  const uint32_t n_tiles = a.Npad / NODE_TILE;
+  constexpr uint32_t ROW_BYTES = NODE_TILE * sizeof(int64_t);
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // stage the CTA's pod requests (sentinel for lanes without a map key)
+  for (uint32_t i = tid; i < PODS_PER_CTA * L; i += FIT_THREADS) {
+    const uint32_t pl = i / L, d = i % L;
+    const uint32_t p = pod0 + pl;
+    int64_t v = UNCHECKED_REQ;
+    if (p < a.P) {
+      const bool present = d < 4 || ((a.req_present[p] >> d) & 1u);
+      if (present) v = a.req[(size_t)d * a.P + p];
+    } else {
+      v = 0;
+    }
+    s_req[pl * L + d] = v;
+  }
+  __syncthreads();
+  auto issue = [&](uint32_t tile, uint32_t stage) {
+    mbar_expect_tx(&s_bar[stage], L * ROW_BYTES);
+#pragma unroll
+    for (int d = 0; d < L; ++d)
+      tma_bulk_g2s(s_tile + (stage * L + d) * NODE_TILE,
+                   a.left_eff + (size_t)d * a.Npad + (size_t)tile * NODE_TILE, ROW_BYTES, &s_bar[stage]);
+  };
+  if (tid == 0) {
+    issue(0, 0);
+    if (n_tiles > 1) issue(1, 1);
+  }
+
+  // per-pod state of this warp
+  uint32_t cnt[PODS_PER_WARP];
+  int64_t best_s[PODS_PER_WARP];
+  int32_t best_n[PODS_PER_WARP];
+  uint32_t cls[PODS_PER_WARP];
+#pragma unroll
+  for (int k = 0; k < PODS_PER_WARP; ++k) {
+    cnt[k] = 0; best_s[k] = INT64_MIN; best_n[k] = -1;
+    const uint32_t p = pod0 + wid * PODS_PER_WARP + k;
+    cls[k] = p < a.P ? a.fit_class[p] : 0u;
+  }
+  const bool want_score = a.score != nullptr;
+  const bool want_bitmap = a.fit_bitmap != nullptr;
+
+  for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+    const uint32_t stage = tile & 1;
+    mbar_wait(&s_bar[stage], (tile >> 1) & 1);
+    const int64_t* tl = s_tile + stage * L * NODE_TILE;
+    const uint32_t node_base = tile * NODE_TILE;
+    const uint32_t word_base = node_base >> 5;
+#pragma unroll
+    for (int kb = 0; kb < PODS_PER_WARP; kb += POD_BLOCK) {
+      // requests of POD_BLOCK pods (warp-uniform values)
+      int64_t rq[POD_BLOCK][L];
+#pragma unroll
+      for (int r = 0; r < POD_BLOCK; ++r)
+#pragma unroll
+        for (int d = 0; d < L; ++d) rq[r][d] = s_req[(wid * PODS_PER_WARP + kb + r) * L + d];
+      uint32_t words[POD_BLOCK];  // lane j keeps ballot word j of the tile
+#pragma unroll
+      for (int r = 0; r < POD_BLOCK; ++r) words[r] = 0;
+#pragma unroll 2
+      for (uint32_t j = 0; j < NODE_TILE / 32; ++j) {
+        const uint32_t nl = j * 32 + lane;
+        const uint32_t node = node_base + nl;
+        int64_t lf[L];
+#pragma unroll
+        for (int d = 0; d < L; ++d) lf[d] = tl[d * NODE_TILE + nl];
+#pragma unroll
+        for (int r = 0; r < POD_BLOCK; ++r) {
+          const uint32_t k = kb + r;
+          const uint32_t p = pod0 + wid * PODS_PER_WARP + k;
+          int64_t m = lf[0] - rq[r][0];
+#pragma unroll
+          for (int d = 1; d < L; ++d) m = min64(m, lf[d] - rq[r][d]);
+          const uint32_t cw = (word_base + j) < a.W ? __ldg(&a.classfit[(size_t)cls[k] * a.W + word_base + j]) : 0u;
+          const bool fit = (m >= 0) && ((cw >> lane) & 1u);
+          const uint32_t bal = __ballot_sync(0xffffffffu, fit);
+          cnt[k] += __popc(bal);
+          if (lane == j) words[r] = bal;
+          const int64_t sc = fit ? m : INT64_MIN;
+          if (fit && m > best_s[k]) { best_s[k] = m; best_n[k] = (int32_t)node; }
+          if (want_score && p < a.P && node < a.N) __stcs(reinterpret_cast<long long*>(&a.score[(size_t)p * a.N + node]), (long long)sc);
+        }
+      }
+      if (want_bitmap) {
+#pragma unroll
+        for (int r = 0; r < POD_BLOCK; ++r) {
+          const uint32_t p = pod0 + wid * PODS_PER_WARP + kb + r;
+          if (p < a.P && lane < NODE_TILE / 32 && word_base + lane < a.W)
+            a.fit_bitmap[(size_t)p * a.W + word_base + lane] = words[r];
+        }
+      }
+    }
+    __syncthreads();  // everyone is done reading this stage
+    if (tid == 0 && tile + 2 < n_tiles) issue(tile + 2, stage);
+  }
+
+  // per-pod reductions across the warp: best = max score, lowest node on ties
+  uint32_t my_gid = 0xffffffffu, my_pass = 0;
+#pragma unroll
+  for (int k = 0; k < PODS_PER_WARP; ++k) {
+    int64_t s = best_s[k];
+    int32_t n = best_n[k];
+    for (int o = 16; o; o >>= 1) {
+      const int64_t os = __shfl_xor_sync(0xffffffffu, s, o);
+      const int32_t on = __shfl_xor_sync(0xffffffffu, n, o);
+      if (on >= 0 && (n < 0 || os > s || (os == s && on < n))) { s = os; n = on; }
+    }
+    const uint32_t p = pod0 + wid * PODS_PER_WARP + k;
+    if (p < a.P) {
+      if (lane == 0) {
+        a.feasible_count[p] = cnt[k];
+        a.best_node[p] = n;
+        a.best_score[p] = s;
+      }
+      if (lane == (uint32_t)k) {
+        const int32_t g = a.gid[p];
+        if (g >= 0 && (uint32_t)g < a.G) {
+          my_gid = (uint32_t)g;
+          my_pass = (a.prefilter[p] == BS_PF_PASS && cnt[k] > 0) ? 1u : 0u;
+        }
+      }
+    }
+  }
+  // warp-segmented reduction over lanes 0..PODS_PER_WARP-1: runs of equal gid
+  {
+    const uint32_t prev_gid = __shfl_up_sync(0xffffffffu, my_gid, 1);
+    const bool active = lane < PODS_PER_WARP && my_gid != 0xffffffffu;
+    const bool head = active && (lane == 0 || prev_gid != my_gid);
+    uint32_t run_pass = my_pass, run_len = active ? 1u : 0u;
+#pragma unroll
+    for (int o = 1; o < PODS_PER_WARP; ++o) {
+      const uint32_t og = __shfl_down_sync(0xffffffffu, my_gid, o);
+      const uint32_t op = __shfl_down_sync(0xffffffffu, my_pass, o);
+      // run_len == o  <=>  every lane in between carried the same gid (contiguous run)
+      if (head && run_len == (uint32_t)o && lane + o < PODS_PER_WARP && og == my_gid) {
+        run_pass += op;
+        run_len += 1;
+      }
+    }
+    if (head) {
+      if (run_pass) atomicAdd(&a.contrib[my_gid], run_pass);
+      __threadfence();
+      const uint32_t ticket = atomicAdd(&a.done[my_gid], run_len) + run_len;
+      if (ticket == a.in_round[my_gid]) {
+        // last pod of the group: Permit readiness (core.go:303) on the full count
+        __threadfence();
+        const uint32_t c = atomicAdd(&a.contrib[my_gid], 0u);
+        const uint32_t total = a.matched[my_gid] + c;
+        uint8_t verdict;
+        if (c == 0) verdict = BS_UNSCHEDULABLE;
+        else verdict = (total >= (uint32_t)(a.min_member[my_gid] - a.scheduled[my_gid])) ? BS_ADMIT : BS_WAIT;
+        a.admit[my_gid] = verdict;
+        if (verdict == BS_ADMIT) atomicOr(&a.admit_bitmap[my_gid >> 5], 1u << (my_gid & 31));
+      }
+    }
+  }
+}
+
+inline size_t gang_fit_smem_bytes(int L) {
+  return (size_t)(2 * L * NODE_TILE + PODS_PER_CTA * L) * sizeof(int64_t) + 2 * sizeof(uint64_t);
+}
+
+}  // namespace bsk

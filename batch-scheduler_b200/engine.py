@@ -1,0 +1,197 @@
+"""Python host wrapper over the C ABI: one Engine = one bs_engine handle on one GPU."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .snapshot import NodeTable, PodTable, GroupTable, Snapshot
+
+
+@dataclass
+class RoundResult:
+    prefilter: np.ndarray
+    feasible_count: np.ndarray
+    best_node: np.ndarray
+    best_score: np.ndarray
+    admit: np.ndarray
+    admit_bitmap: np.ndarray
+    new_denied: np.ndarray
+    order: np.ndarray
+    rank: np.ndarray
+    max_group: int
+    max_finished: int
+
+
+class Engine:
+    def __init__(self, n_lanes: int, device: int = 0, fit_bitmap: bool = True, score: bool = False):
+        self.lib = capi.load()
+        self.n_lanes = n_lanes
+        self.out_flags = (capi.OUT_FIT_BITMAP if fit_bitmap else 0) | (capi.OUT_SCORE if score else 0)
+        cfg = capi.Config(device, n_lanes, self.out_flags, 0)
+        h = C.c_void_p()
+        rc = self.lib.bs_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise capi.BsError(rc, self.lib.bs_strerror(rc).decode())
+        self.h = h
+        self.P = self.N = self.G = 0
+        self._res = None
+
+    # -- lifecycle -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.bs_last_error(self.h).decode() or self.lib.bs_strerror(rc).decode()
+            raise capi.BsError(rc, msg)
+
+    # -- uploads ---------------------------------------------------------------------------
+    def upload_nodes(self, nt: NodeTable):
+        t = capi.NodeTableC(nt.n, nt.lanes, capi.ptr(nt.alloc), capi.ptr(nt.requested), capi.ptr(nt.pod_count),
+                            capi.ptr(nt.alloc_present), capi.ptr(nt.req_present), capi.ptr(nt.label_mask),
+                            capi.ptr(nt.taint_mask), capi.ptr(nt.flags))
+        self._check(self.lib.bs_upload_nodes(self.h, C.byref(t)))
+        self.N = nt.n
+
+    def upload_groups(self, gt: GroupTable):
+        t = capi.GroupTableC(gt.n, gt.lanes, capi.ptr(gt.min_member), capi.ptr(gt.scheduled), capi.ptr(gt.matched),
+                             capi.ptr(gt.flags), capi.ptr(gt.min_res), capi.ptr(gt.min_res_present),
+                             capi.ptr(gt.rep_sel), capi.ptr(gt.rep_tol), capi.ptr(gt.creation_ns),
+                             capi.ptr(gt.name_rank))
+        self._check(self.lib.bs_upload_groups(self.h, C.byref(t)))
+        self.G = gt.n
+
+    def upload_pods(self, pt: PodTable):
+        t = capi.PodTableC(pt.n, pt.lanes, capi.ptr(pt.req), capi.ptr(pt.req_present), capi.ptr(pt.gid),
+                           capi.ptr(pt.sel_mask), capi.ptr(pt.tol_mask), capi.ptr(pt.priority),
+                           capi.ptr(pt.ts_ns), capi.ptr(pt.flags))
+        self._check(self.lib.bs_upload_pods(self.h, C.byref(t)))
+        self.P = pt.n
+
+    def upload(self, snap: Snapshot):
+        self.upload_nodes(snap.nodes)
+        self.upload_groups(snap.groups)
+        self.upload_pods(snap.pods)
+
+    def set_wait_time(self, default_ns: int, per_group_ns=None):
+        if per_group_ns is None:
+            self._check(self.lib.bs_set_wait_time(self.h, default_ns, None, 0))
+        else:
+            a = np.ascontiguousarray(per_group_ns, dtype=np.int64)
+            self._check(self.lib.bs_set_wait_time(self.h, default_ns, capi.ptr(a), len(a)))
+
+    # -- evaluation ------------------------------------------------------------------------
+    def _alloc_results(self):
+        P, G = self.P, self.G
+        r = RoundResult(np.zeros(P, np.uint8), np.zeros(P, np.uint32), np.zeros(P, np.int32), np.zeros(P, np.int64),
+                        np.zeros(G, np.uint8), np.zeros((G + 31) // 32, np.uint32), np.zeros(G, np.uint8),
+                        np.zeros(P, np.uint32), np.zeros(P, np.uint32), -1, 0)
+        c = capi.ResultsC(capi.ptr(r.prefilter), capi.ptr(r.feasible_count), capi.ptr(r.best_node),
+                          capi.ptr(r.best_score), capi.ptr(r.admit), capi.ptr(r.admit_bitmap),
+                          capi.ptr(r.new_denied), capi.ptr(r.order), capi.ptr(r.rank), -1, 0)
+        return r, c
+
+    def evaluate(self) -> RoundResult:
+        r, c = self._alloc_results()
+        self._check(self.lib.bs_evaluate(self.h, C.byref(c)))
+        r.max_group, r.max_finished = int(c.max_group), int(c.max_finished)
+        return r
+
+    def evaluate_async(self):
+        self._check(self.lib.bs_evaluate_async(self.h))
+
+    def sync(self):
+        self._check(self.lib.bs_sync(self.h))
+
+    def fetch(self) -> RoundResult:
+        r, c = self._alloc_results()
+        self._check(self.lib.bs_fetch(self.h, C.byref(c)))
+        r.max_group, r.max_finished = int(c.max_group), int(c.max_finished)
+        return r
+
+    def fit_rows(self, pod0=0, n=None) -> np.ndarray:
+        n = self.P - pod0 if n is None else n
+        W = (self.N + 31) // 32
+        out = np.zeros((n, W), np.uint32)
+        self._check(self.lib.bs_fetch_fit_rows(self.h, pod0, n, capi.ptr(out)))
+        return out
+
+    def score_rows(self, pod0=0, n=None) -> np.ndarray:
+        n = self.P - pod0 if n is None else n
+        out = np.zeros((n, self.N), np.int64)
+        self._check(self.lib.bs_fetch_score_rows(self.h, pod0, n, capi.ptr(out)))
+        return out
+
+    # -- standalone kernels ------------------------------------------------------------------
+    def node_left(self, sel: int, tol: int, percent: float):
+        left = np.zeros((self.n_lanes, self.N), np.int64)
+        pres = np.zeros(self.N, np.uint32)
+        self._check(self.lib.bs_node_left(self.h, sel, tol, C.c_float(percent), capi.ptr(left), capi.ptr(pres)))
+        return left, pres
+
+    def cluster_check(self, sel: int, tol: int, percent: float, need: np.ndarray, need_present: np.ndarray):
+        need = np.ascontiguousarray(need, dtype=np.int64)  # [L, n]
+        need_present = np.ascontiguousarray(need_present, dtype=np.uint32)
+        n = need.shape[1]
+        ok = np.zeros(n, np.uint8)
+        self._check(self.lib.bs_cluster_check(self.h, sel, tol, C.c_float(percent), capi.ptr(need),
+                                              capi.ptr(need_present), n, capi.ptr(ok)))
+        return ok.astype(bool)
+
+    # -- per-call mirrors ------------------------------------------------------------------
+    def prefilter(self, pod: int):
+        st = capi.StatusC()
+        self._check(self.lib.bs_prefilter(self.h, pod, C.byref(st)))
+        return st.code, st.reason, st.group
+
+    def permit(self, pod: int, node: int):
+        r = capi.PermitResultC()
+        self._check(self.lib.bs_permit(self.h, pod, node, C.byref(r)))
+        return dict(ready=bool(r.ready), code=r.code, wait_ns=r.wait_ns, start_signal=bool(r.start_signal),
+                    group=r.group)
+
+    def less(self, a: int, b: int) -> bool:
+        rc = self.lib.bs_less(self.h, a, b)
+        if rc < 0:
+            self._check(rc)
+        return bool(rc)
+
+    def message(self, reason: int, ns_name: str = "", occupied_by: str = "") -> str:
+        st = capi.StatusC(0, reason, -1)
+        buf = C.create_string_buffer(512)
+        self._check(self.lib.bs_format_message(C.byref(st), ns_name.encode(), occupied_by.encode(), buf, 512))
+        return buf.value.decode()
+
+    # -- device access / measurement ---------------------------------------------------------
+    def device_buffer(self, which: int):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.bs_device_buffer(self.h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def stream(self) -> int:
+        return self.lib.bs_stream(self.h)
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.bs_set_profiling(self.h, int(on)))
+
+    def kernel_ms(self):
+        out = {}
+        for k, name in enumerate(capi.KERNEL_NAMES):
+            ms, n = C.c_float(), C.c_uint32()
+            self._check(self.lib.bs_kernel_ms(self.h, k, C.byref(ms), C.byref(n)))
+            out[name] = (float(ms.value), int(n.value))
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.bs_launch_count(self.h))

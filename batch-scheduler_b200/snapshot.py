@@ -243,8 +243,10 @@ class SplitMix64:
 
 
 def _synth(seed: int, G: int, group_sizes: np.ndarray, min_member: np.ndarray, N: int, S: int,
-           name: str, shuffle_pods: bool = False) -> Snapshot:
-    """Synthetic snapshot per SURVEY.md §8(d)."""
+           name: str, shuffle_pods: bool = False, shard: int = 0) -> Snapshot:
+    """Synthetic snapshot per SURVEY.md §8(d).  Nodes come from their own stream (seed), groups
+    and pods from a second stream that also depends on `shard`: rank r of a weak-scaling run
+    gets the same (replicated) node table and its own groups/pods."""
     rng = SplitMix64(seed)
     L = FIXED_LANES + S
     # ---- nodes ----
@@ -279,6 +281,7 @@ def _synth(seed: int, G: int, group_sizes: np.ndarray, min_member: np.ndarray, N
     nt.taint_mask = rng.bernoulli_bits(N, 4, 0.05)
 
     # ---- groups (pods homogeneous within a group) ----
+    rng = SplitMix64((seed ^ 0x6A09E667F3BCC908) + 0x1000 * shard)
     gt = GroupTable.empty(G, L)
     g_cpu = rng.choice(G, [250, 500, 1000, 2000, 4000, 8000]).astype(np.int64)
     g_mem = (rng.choice(G, [0.25, 1, 4, 16, 32]) * GiB).astype(np.int64)
@@ -328,18 +331,21 @@ def _synth(seed: int, G: int, group_sizes: np.ndarray, min_member: np.ndarray, N
     return snap
 
 
-def config(cfg: int, scale: float = 1.0) -> Snapshot:
-    """BASELINE.json configs #2..#5; `scale` shrinks P, N, G together for tests."""
+def config(cfg: int, scale: float = 1.0, shard: int = 0) -> Snapshot:
+    """BASELINE.json configs #2..#5; `scale` shrinks P, N, G together for tests;
+    `shard` selects the rank-local groups/pods of a weak-scaling run (nodes are replicated)."""
     seed = 0xB2000000 + cfg
     sc = lambda x: max(1, int(round(x * scale)))
     if cfg == 2:
         G, N = sc(1000), sc(1000)
-        return _synth(seed, G, np.full(G, 8), np.full(G, 8), N, 1, "cfg2: 1k groups x 8 pods, 1k nodes, 5 lanes")
+        return _synth(seed, G, np.full(G, 8), np.full(G, 8), N, 1, "cfg2: 1k groups x 8 pods, 1k nodes, 5 lanes",
+                      shard=shard)
     if cfg == 3:
         G, N = sc(10000), sc(10000)
         rng = SplitMix64(seed ^ 0x5555)
         mm = 1 + rng.below(G, 16)
-        return _synth(seed, G, np.full(G, 16), mm, N, 1, "cfg3: 10k groups x 16 pods, 10k nodes, minMember 1-16")
+        return _synth(seed, G, np.full(G, 16), mm, N, 1, "cfg3: 10k groups x 16 pods, 10k nodes, minMember 1-16",
+                      shard=shard)
     if cfg == 4:
         G, N = sc(50000), sc(10000)
         rng = SplitMix64(seed ^ 0x5555)
@@ -356,11 +362,12 @@ def config(cfg: int, scale: float = 1.0) -> Snapshot:
                 sizes[j] += 1; diff += 1
             i += 1
         return _synth(seed, G, sizes, sizes.copy(), N, 1,
-                      "cfg4: 100k pods / 10k nodes, 50k groups, priority-sorted queue", shuffle_pods=True)
+                      "cfg4: 100k pods / 10k nodes, 50k groups, priority-sorted queue", shuffle_pods=True,
+                      shard=shard)
     if cfg == 5:
         G, N = sc(62500), sc(50000)
         return _synth(seed, G, np.full(G, 16), np.full(G, 16), N, 5,
-                      "cfg5: 1M pods / 50k nodes, 62.5k groups, 9 lanes")
+                      "cfg5: 1M pods / 50k nodes, 62.5k groups, 9 lanes", shard=shard)
     raise ValueError(f"unknown config {cfg}")
 
 

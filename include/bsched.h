@@ -40,7 +40,7 @@ extern "C" {
 #define BS_MAX_LANES 16
 /* |value| bound accepted for every int64 table entry (validated at upload):
  * keeps left-req differences and the float32->int64 conversion in range. */
-#define BS_VALUE_LIMIT ((int64_t)1 << 60)
+#define BS_VALUE_LIMIT ((int64_t)1 << 56)
 
 typedef struct bs_engine bs_engine; /* opaque */
 

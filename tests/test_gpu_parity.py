@@ -1,0 +1,196 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from parity import run_and_compare, assert_round_equal
+from randsnap import random_snapshot
+
+pytestmark = pytest.mark.gpu
+
+
+def test_core_test_go_cases(pkg, oracle, snapshot_mod):
+    # pkg/scheduler/core/core_test.go:82-112 through the engine: fit bits true,false,false
+    snap, expected, left_exp = snapshot_mod.core_test_cases()
+    res, orc = run_and_compare(pkg, oracle, snap)
+    assert list(res.feasible_count) == [1, 0, 0]
+    eng = pkg.Engine(snap.lanes)
+    eng.upload_nodes(snap.nodes)
+    left, pres = eng.node_left(0, 0, 1.0)
+    eng.close()
+    assert list(left[:, 0]) == [9000, 0, 0, 99, 9, 19] and pres[0] == 0x30
+
+
+def test_readme_snapshot(pkg, oracle, snapshot_mod):
+    snap = snapshot_mod.readme_scenario()
+    res, _ = run_and_compare(pkg, oracle, snap)
+    assert (res.feasible_count == 1).all()
+    # first pods of both groups in one frozen round: group1 is max (nil rule), matched==0 ->
+    # pct 1.0 check of each pod's own group: 7100 >= 5000 for both -> every pod passes
+    assert (res.prefilter == 0).all()
+    assert list(res.admit) == [snapshot_mod.ADMIT, snapshot_mod.ADMIT]
+
+
+def test_readme_second_round_denies_group2(pkg, oracle, snapshot_mod):
+    # after group1's first pod is permitted (matched=1, requested 1900m): Appendix C step 2
+    S = snapshot_mod
+    snap = S.readme_scenario()
+    snap.groups.matched[0] = 1
+    snap.groups.flags[:] = S.GROUP_HAS_POD | S.GROUP_HAS_MINRES
+    snap.groups.min_res[0, :] = 1000
+    snap.nodes.requested[0, 0] = 1900
+    snap.nodes.pod_count[0] = 5
+    res, _ = run_and_compare(pkg, oracle, snap)
+    assert (res.prefilter[:5] == S.PF_PASS).all()          # max group passes (core.go:150-155)
+    assert (res.prefilter[5:] == S.PF_NOT_ENOUGH).all()    # 5600-1900=3700 < 4000+1000
+    assert list(res.new_denied) == [0, 1]
+    assert res.admit[1] == S.UNSCHEDULABLE
+
+
+@pytest.mark.parametrize("cfg,scale", [(2, 1.0), (3, 0.06), (4, 0.05), (5, 0.012)])
+def test_baseline_configs(pkg, oracle, snapshot_mod, cfg, scale):
+    snap = snapshot_mod.config(cfg, scale)
+    run_and_compare(pkg, oracle, snap)
+
+
+@pytest.mark.parametrize("cfg,scale", [(2, 0.5), (3, 0.04)])
+def test_baseline_configs_case_a(pkg, oracle, snapshot_mod, cfg, scale):
+    # no carried-in matched pods: every group is checked against its own need at pct 1.0
+    snap = snapshot_mod.config(cfg, scale)
+    snap.groups.matched[:] = 0
+    res, orc = run_and_compare(pkg, oracle, snap)
+    assert orc.max_group >= 0
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_snapshots(pkg, oracle, seed):
+    case = ["mixed", "A", "B"][seed % 3]
+    L = [4, 5, 6, 9, 16][seed % 5]
+    snap = random_snapshot(seed, P=150 + 37 * seed, N=33 + 29 * seed, G=5 + 3 * seed, L=L, case=case,
+                           value_scale="big" if seed % 7 == 3 else "normal")
+    run_and_compare(pkg, oracle, snap)
+
+
+def test_ragged_and_empty(pkg, oracle, snapshot_mod):
+    S = snapshot_mod
+    # no pods
+    snap = random_snapshot(100, P=0, N=10, G=4, L=5)
+    run_and_compare(pkg, oracle, snap)
+    # no groups: every pod ungrouped or missing
+    snap = random_snapshot(101, P=50, N=10, G=0, L=5)
+    run_and_compare(pkg, oracle, snap)
+    # single node, node count not a multiple of 32, > one tile
+    for n in (1, 31, 32, 33, 511, 512, 513, 1100):
+        snap = random_snapshot(200 + n, P=70, N=n, G=6, L=5)
+        run_and_compare(pkg, oracle, snap, score=(n < 600))
+    # every node skipped: the cluster loop never compares (core.go:606-631)
+    snap = random_snapshot(102, P=40, N=20, G=5, L=5, case="A")
+    snap.nodes.flags[:] = S.NODE_UNSCHEDULABLE
+    res, _ = run_and_compare(pkg, oracle, snap)
+    assert (res.feasible_count == 0).all()
+
+
+def test_uint32_wraparound_permit(pkg, oracle, snapshot_mod):
+    # Status.Scheduled > MinMember: MinMember - Scheduled wraps (core.go:303, quirk Q6)
+    S = snapshot_mod
+    snap = S.readme_scenario()
+    snap.groups.min_member[:] = [2, 5]
+    snap.groups.scheduled[:] = [3, 0]
+    res, orc = run_and_compare(pkg, oracle, snap)
+    assert res.admit[0] == S.WAIT  # 5 pods < 2^32-1
+
+
+def test_ref_panic_reported(pkg, snapshot_mod):
+    S = snapshot_mod
+    snap = S.readme_scenario()
+    snap.groups.min_member[0] = 0
+    snap.groups.scheduled[0] = 1
+    eng = pkg.Engine(snap.lanes)
+    eng.upload(snap)
+    with pytest.raises(pkg.capi.BsError) as ei:
+        eng.evaluate()
+    assert ei.value.code == pkg.capi.BS_E_REF_PANIC
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_node_left_and_cluster_check(pkg, oracle, seed):
+    snap = random_snapshot(300 + seed, P=10, N=150 + 100 * seed, G=3, L=[5, 6, 9][seed % 3])
+    nt = snap.nodes
+    rng = np.random.default_rng(seed)
+    eng = pkg.Engine(snap.lanes)
+    eng.upload_nodes(nt)
+    for sel, tol, pct in [(0, 0, 1.0), (1, 3, 0.7), (2, 0, 0.7), (5, 1, 1.0)]:
+        left, pres = eng.node_left(sel, tol, pct)
+        oleft, opres = oracle.node_left(nt, sel, tol, pct)
+        np.testing.assert_array_equal(left, oleft)
+        np.testing.assert_array_equal(pres, opres)
+        total, tp = oracle.compute_cluster(nt, sel, tol)
+        n_needs = 64
+        need = np.zeros((snap.lanes, n_needs), np.int64)
+        for d in range(snap.lanes):
+            hi = max(2, int(abs(total[d])) * 2)
+            need[d] = rng.integers(-hi // 4, hi, n_needs)
+        need[:, :8] = 0
+        need[3, :] = rng.integers(0, 50, n_needs)
+        npres = rng.integers(0, 1 << snap.lanes, n_needs).astype(np.uint32) & ~np.uint32(0xF)
+        ok = eng.cluster_check(sel, tol, pct, need, npres)
+        exp = np.array([oracle.compare_cluster(nt, sel, tol, need[:, i], int(npres[i]), pct)
+                        for i in range(n_needs)])
+        np.testing.assert_array_equal(ok, exp)
+    eng.close()
+
+
+def test_mirrors_prefilter_permit_less(pkg, oracle, snapshot_mod):
+    S = snapshot_mod
+    snap = random_snapshot(77, P=120, N=40, G=12, L=5)
+    snap.pods.flags[:10] |= S.POD_LISTER_MISS
+    eng = pkg.Engine(snap.lanes)
+    eng.upload(snap)
+    eng.set_wait_time(0, None)
+    res = eng.evaluate()
+    orc = oracle.round(snap)
+    capi = pkg.capi
+    for p in range(snap.pods.n):
+        code, reason, g = eng.prefilter(p)
+        assert reason == orc.prefilter[p]
+        assert code == (capi.CODE_SUCCESS if reason == 0 else capi.CODE_UNSCHEDULABLE)  # batchscheduler.go:104-107
+        pr = eng.permit(p, 0)
+        gid = snap.pods.gid[p]
+        if gid == S.GID_NONE:
+            assert pr["code"] == capi.CODE_SUCCESS and pr["wait_ns"] == 0
+        elif gid < 0:
+            assert pr["code"] == capi.CODE_UNSCHEDULABLE and pr["wait_ns"] == 60 * 10**9
+        else:
+            assert pr["code"] == capi.CODE_WAIT and pr["wait_ns"] == 10**9
+            assert pr["ready"] == (orc.admit[gid] == S.ADMIT) and pr["start_signal"] == pr["ready"]
+    rng = np.random.default_rng(5)
+    for _ in range(3000):
+        a, b = rng.integers(0, snap.pods.n, 2)
+        assert eng.less(int(a), int(b)) == oracle.compare(snap.pods, snap.groups, int(a), int(b)), (a, b)
+    assert eng.message(S.PF_NOT_ENOUGH) == "cluster resource not enough"
+    assert eng.message(S.PF_NOT_FOUND, "default/g1") == "can not found pod group: default/g1"
+    assert eng.message(S.PF_DENIED, "default/g1") == "pod with pgName: default/g1 last failed in 20s, deny"
+    eng.close()
+
+
+def test_value_range_rejected(pkg, snapshot_mod):
+    snap = snapshot_mod.readme_scenario()
+    snap.nodes.alloc[1, 0] = (1 << 56) + 1
+    eng = pkg.Engine(snap.lanes)
+    with pytest.raises(pkg.capi.BsError) as ei:
+        eng.upload_nodes(snap.nodes)
+    assert ei.value.code == pkg.capi.BS_E_RANGE
+    eng.close()
+
+
+def test_reupload_and_reevaluate(pkg, oracle, snapshot_mod):
+    # one engine, several rounds: state from a previous round must not leak
+    eng = pkg.Engine(5, 0, fit_bitmap=True, score=True)
+    for seed in (1, 2, 3):
+        snap = random_snapshot(400 + seed, P=90 + 40 * seed, N=50 + 300 * seed, G=9 + seed, L=5)
+        eng.upload(snap)
+        for _ in range(2):
+            res = eng.evaluate()
+            orc = oracle.round(snap, want_bitmap=True, want_score=True)
+            assert_round_equal(res, eng.fit_rows(), eng.score_rows(), orc)
+    eng.close()
