@@ -133,6 +133,10 @@ struct bs_engine {
   std::vector<uint32_t> h_pnz;
   std::vector<int64_t> h_wait_ns;
   int64_t default_wait_ns = 0;
+  // bits that differ between rows of each sort key word (a constant byte needs no radix pass)
+  bool any_lister_miss = true;
+  int32_t max_gid = -1;
+  uint64_t vary_ts = ~0ull, vary_prio = ~0ull, vary_creation = ~0ull, vary_name = ~0ull;
   // pinned result cache
   PinBuf h_prefilter, h_feasible, h_best_node, h_best_score, h_admit, h_admit_bitmap, h_new_denied,
       h_order, h_rank, h_state;
@@ -332,23 +336,32 @@ void radix_pass(bs_engine* e, StageTimer& tm, const uint32_t* in, uint32_t* out,
   tm.launched(3);
 }
 
-// sorts indices 0..n-1 by (k1, k0[low k0_bits]) ascending, stable; result in `result`
-// (ping-pongs between a and b; returns the buffer holding the final order)
-uint32_t* radix_sort(bs_engine* e, StageTimer& tm, uint32_t n, const uint64_t* k0, int k0_bits,
-                     const uint64_t* k1, int k1_bits, uint32_t* a, uint32_t* b, cudaStream_t st) {
+// sorts indices 0..n-1 by (k1, k0) ascending, stable.  vary0/vary1: bits that differ between
+// rows of k0/k1 (host-computed at upload); byte digits with no varying bit need no pass.
+// Ping-pongs between a and b; returns the buffer holding the final order.
+uint32_t* radix_sort(bs_engine* e, StageTimer& tm, uint32_t n, const uint64_t* k0, uint64_t vary0,
+                     const uint64_t* k1, uint64_t vary1, uint32_t* a, uint32_t* b, cudaStream_t st) {
   iota_kernel<<<cdiv(std::max(n, 1u), 256), 256, 0, st>>>(a, n);
   tm.launched();
   uint32_t* cur = a;
   uint32_t* nxt = b;
-  for (int sh = 0; sh < k0_bits; sh += 8) {
+  for (int sh = 0; sh < 64; sh += 8) {
+    if (!((vary0 >> sh) & 0xffull)) continue;
     radix_pass(e, tm, cur, nxt, k0, sh, n, st);
     std::swap(cur, nxt);
   }
-  for (int sh = 0; sh < k1_bits; sh += 8) {
+  for (int sh = 0; sh < 64; sh += 8) {
+    if (!((vary1 >> sh) & 0xffull)) continue;
     radix_pass(e, tm, cur, nxt, k1, sh, n, st);
     std::swap(cur, nxt);
   }
   return cur;
+}
+
+inline uint64_t low_bits_mask(uint32_t n) {  // mask covering every value in [0, n]
+  uint64_t m = 0;
+  while (m < n) m = (m << 1) | 1ull;
+  return m;
 }
 
 int rebuild_classes(bs_engine* e) {
@@ -427,8 +440,10 @@ int ensure_round_buffers(bs_engine* e) {
   CK(e->d_new_denied.ensure(G));
   CK(e->d_order.ensure((size_t)P * 4));
   CK(e->d_rank.ensure((size_t)P * 4));
-  if (e->out_flags & BS_OUT_FIT_BITMAP) CK(e->d_fit_bitmap.ensure((size_t)e->P * std::max(e->W, 1u) * 4));
-  if (e->out_flags & BS_OUT_SCORE) CK(e->d_score.ensure((size_t)e->P * N * 8));
+  // rows padded to a whole CTA of pods: the fit kernel writes pods >= P without a guard
+  const size_t Prows = (size_t)cdiv(std::max(e->P, 1u), PODS_PER_CTA) * PODS_PER_CTA;
+  if (e->out_flags & BS_OUT_FIT_BITMAP) CK(e->d_fit_bitmap.ensure(Prows * std::max(e->W, 1u) * 4));
+  if (e->out_flags & BS_OUT_SCORE) CK(e->d_score.ensure(Prows * N * 8));
   // prefix scratch: as many rep-class slots as fit a 1 GiB budget
   const size_t per_class = (size_t)N * (8 * L + 4);
   uint32_t slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(e->n_rep_classes, ((size_t)1 << 30) / per_class));
@@ -467,15 +482,16 @@ int prepare_nodes(bs_engine* e) {
   StageTimer tm(e, BS_K_NODE_LEFT, e->s);
   CK(e->d_left_eff.ensure((size_t)e->L * e->Npad * 8));
   CK(e->d_left_present.ensure((size_t)e->Npad * 4));
-  CK(e->d_classfit.ensure((size_t)e->n_fit_classes * std::max(e->W, 1u) * 4));
+  const uint32_t n_tiles = e->Npad / NODE_TILE;
+  CK(e->d_classfit.ensure((size_t)e->n_fit_classes * n_tiles * 32 * 4));
   node_left_kernel<<<cdiv(e->Npad, 256), 256, 0, e->s>>>(t, e->d_left_eff.as<int64_t>(),
                                                          e->d_left_present.as<uint32_t>());
   tm.launched();
-  if (e->W) {
-    dim3 grid(cdiv(e->W * 32, 256), e->n_fit_classes);
+  {
+    dim3 grid(cdiv(n_tiles * 32, 256), e->n_fit_classes);
     class_fit_kernel<<<grid, 256, 0, e->s>>>(t, e->d_left_present.as<uint32_t>(), e->d_fsel.as<uint64_t>(),
                                              e->d_ftol.as<uint64_t>(), e->d_fnz.as<uint32_t>(),
-                                             e->n_fit_classes, e->W, e->d_classfit.as<uint32_t>());
+                                             e->n_fit_classes, n_tiles, e->d_classfit.as<uint32_t>());
     tm.launched();
   }
   CK(cudaGetLastError());
@@ -515,8 +531,8 @@ int evaluate_async_locked(bs_engine* e) {
       group_keys_kernel<<<cdiv(G, 256), 256, 0, e->s2>>>(e->d_creation.as<int64_t>(), e->d_name_rank.as<uint32_t>(),
                                                          G, e->d_gk0.as<uint64_t>(), e->d_gk1.as<uint64_t>());
       tm.launched();
-      uint32_t* gord = radix_sort(e, tm, G, e->d_gk0.as<uint64_t>(), 32, e->d_gk1.as<uint64_t>(), 64,
-                                  e->d_idx_a.as<uint32_t>(), e->d_idx_b.as<uint32_t>(), e->s2);
+      uint32_t* gord = radix_sort(e, tm, G, e->d_gk0.as<uint64_t>(), e->vary_name, e->d_gk1.as<uint64_t>(),
+                                  e->vary_creation, e->d_idx_a.as<uint32_t>(), e->d_idx_b.as<uint32_t>(), e->s2);
       dense_rank_kernel<<<1, 1024, 0, e->s2>>>(gord, e->d_gk0.as<uint64_t>(), e->d_gk1.as<uint64_t>(), G,
                                                e->d_group_rank.as<uint32_t>());
       tm.launched();
@@ -527,7 +543,10 @@ int evaluate_async_locked(bs_engine* e) {
                                                        e->d_group_rank.as<uint32_t>(), P, G,
                                                        e->d_pk0.as<uint64_t>(), e->d_pk1.as<uint64_t>());
       tm.launched();
-      uint32_t* pord = radix_sort(e, tm, P, e->d_pk0.as<uint64_t>(), 64, e->d_pk1.as<uint64_t>(), 64,
+      // word1 = [~biased prio : 32][grouped : 1][group rank or 0x7fffffff : 31]
+      const uint64_t vary1 = (e->vary_prio << 32) | 0x80000000ull |
+                             ((e->any_lister_miss || e->max_gid >= (int64_t)G) ? 0x7fffffffull : low_bits_mask(G));
+      uint32_t* pord = radix_sort(e, tm, P, e->d_pk0.as<uint64_t>(), e->vary_ts, e->d_pk1.as<uint64_t>(), vary1,
                                   e->d_idx_a.as<uint32_t>(), e->d_idx_b.as<uint32_t>(), e->s2);
       CK(cudaMemcpyAsync(e->d_order.p, pord, (size_t)P * 4, cudaMemcpyDeviceToDevice, e->s2));
       dense_rank_kernel<<<1, 1024, 0, e->s2>>>(e->d_order.as<uint32_t>(), e->d_pk0.as<uint64_t>(),
@@ -802,6 +821,15 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if ((rc = upload_vec(e, e->d_creation, t->creation_ns, G, Gp))) return rc;
   if ((rc = upload_vec(e, e->d_name_rank, t->name_rank, G, Gp))) return rc;
   CK(cudaStreamSynchronize(e->s));
+  {
+    uint64_t o1 = 0, a1 = ~0ull, o0 = 0, a0 = ~0ull;
+    for (uint32_t g = 0; g < G; ++g) {
+      const uint64_t c = (uint64_t)t->creation_ns[g], nm = (uint64_t)(~t->name_rank[g]);
+      o1 |= c; a1 &= c; o0 |= nm; a0 &= nm;
+    }
+    e->vary_creation = G ? (o1 ^ a1) : 0;
+    e->vary_name = G ? (o0 ^ a0) : 0;
+  }
   e->h_gsel.assign(t->rep_sel, t->rep_sel + G);
   e->h_gtol.assign(t->rep_tol, t->rep_tol + G);
   if (e->h_wait_ns.size() != G) e->h_wait_ns.assign(G, -1);
@@ -837,6 +865,23 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   e->h_psel.assign(t->sel_mask, t->sel_mask + P);
   e->h_ptol.assign(t->tol_mask, t->tol_mask + P);
   e->h_pnz.assign(P, 0);
+  {
+    uint64_t ot = 0, at = ~0ull;
+    uint32_t op = 0, apr = ~0u;
+    bool miss = false;
+    int32_t mg = -1;
+    for (uint32_t p = 0; p < P; ++p) {
+      const uint64_t ts = (uint64_t)t->ts_ns[p];
+      const uint32_t pr = (uint32_t)t->priority[p];
+      ot |= ts; at &= ts; op |= pr; apr &= pr;
+      miss |= (t->gid[p] < BS_GID_NONE) || (t->flags[p] & BS_POD_LISTER_MISS);
+      mg = std::max(mg, t->gid[p]);
+    }
+    e->vary_ts = P ? (ot ^ at) : 0;
+    e->vary_prio = P ? (uint64_t)(op ^ apr) : 0;
+    e->any_lister_miss = miss;
+    e->max_gid = mg;
+  }
   for (uint32_t d = 4; d < L; ++d) {
     const int64_t* row = t->req + (size_t)d * P;
     for (uint32_t p = 0; p < P; ++p)

@@ -24,9 +24,12 @@ constexpr int64_t UNCHECKED_REQ = -((int64_t)1 << 61); // request lane without a
 constexpr int NODE_TILE = 512;                          // nodes per shared-memory tile
 constexpr int FIT_THREADS = 256;
 constexpr int FIT_WARPS = FIT_THREADS / 32;
-constexpr int PODS_PER_WARP = 8;
-constexpr int POD_BLOCK = 4;                            // pods evaluated together per node (ILP)
-constexpr int PODS_PER_CTA = FIT_WARPS * PODS_PER_WARP; // 64
+constexpr int PODS_PER_WARP = 4;                        // pods evaluated together per node (ILP)
+constexpr int PODS_PER_CTA = FIT_WARPS * PODS_PER_WARP; // 32
+constexpr int TILE_WORDS = NODE_TILE / 32;              // 16 ballot words per tile and pod
+#ifndef BS_FIT_MINB
+#define BS_FIT_MINB 2
+#endif
 
 // round-global scalars living in device memory (no host sync inside a round)
 struct RoundState {
@@ -164,21 +167,33 @@ __global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, fl
 // K1b  class_fit_kernel — one bit per (pod class, node): node not skipped
 // (core.go:606-617), Taints() ok (:639), checkFit (:741-759), and every scalar
 // key the class requests with a non-zero amount exists in `left`
-// (compareResourceAndRequire :688-690).  Word w of class c: classfit[c*W + w].
+// (compareResourceAndRequire :688-690).  Layout is TRANSPOSED for the fit kernel:
+// classfit[(c * n_tiles + tile) * 32 + lane] holds, in bit j, the verdict for node
+// tile*NODE_TILE + j*32 + lane — exactly the TILE_WORDS nodes lane `lane` owns in
+// that tile, so the hot loop needs one coalesced 4-byte load per (pod, tile).
 __global__ void class_fit_kernel(NodeTab t, const uint32_t* __restrict__ left_present,
                                  const uint64_t* __restrict__ csel, const uint64_t* __restrict__ ctol,
-                                 const uint32_t* __restrict__ cnz, uint32_t n_classes, uint32_t W,
+                                 const uint32_t* __restrict__ cnz, uint32_t n_classes, uint32_t n_tiles,
                                  uint32_t* __restrict__ classfit) {
   const uint32_t c = blockIdx.y;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // node (may be >= N inside the last word)
-  bool ok = false;
-  if (i < t.N) {
-    const uint8_t f = t.flags[i];
-    ok = !node_skipped(f) && !(f & BS_NODE_TAINTS_ERR) &&
-         check_fit(t.label[i], t.taint[i], csel[c], ctol[c]) && ((cnz[c] & ~left_present[i]) == 0);
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;  // tile * 32 + lane
+  if (slot >= n_tiles * 32 || c >= n_classes) return;
+  const uint32_t tile = slot >> 5, lane = slot & 31;
+  const uint64_t sel = csel[c], tol = ctol[c];
+  const uint32_t nz = cnz[c];
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < TILE_WORDS; ++j) {
+    const uint32_t i = tile * NODE_TILE + j * 32 + lane;
+    bool ok = false;
+    if (i < t.N) {
+      const uint8_t f = t.flags[i];
+      ok = !node_skipped(f) && !(f & BS_NODE_TAINTS_ERR) && check_fit(t.label[i], t.taint[i], sel, tol) &&
+           ((nz & ~left_present[i]) == 0);
+    }
+    bits |= (ok ? 1u : 0u) << j;
   }
-  const uint32_t word = __ballot_sync(0xffffffffu, ok);
-  if ((threadIdx.x & 31) == 0 && (i >> 5) < W) classfit[(size_t)c * W + (i >> 5)] = word;
+  classfit[(size_t)c * n_tiles * 32 + slot] = bits;
 }
 
 // ---------------------------------------------------------------------------
@@ -709,7 +724,7 @@ __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? 
 
 struct FitArgs {
   const int64_t* left_eff;   // [L][Npad]
-  const uint32_t* classfit;  // [classes][W]
+  const uint32_t* classfit;  // [classes][n_tiles][32] transposed class bits
   const int64_t* req;        // [L][P]
   const uint32_t* req_present;
   const uint32_t* fit_class;
@@ -728,21 +743,71 @@ struct FitArgs {
   uint32_t* feasible_count;
   int32_t* best_node;
   int64_t* best_score;
-  uint32_t* fit_bitmap;  // [P][W] or null
-  int64_t* score;        // [P][N] or null
+  uint32_t* fit_bitmap;   // [Ppad][W] or null   (Ppad = P rounded up to PODS_PER_CTA: no pod guard)
+  int64_t* score;         // [Ppad][N] or null
   uint32_t P, N, Npad, W, G;
 };
 
+// One node tile for the PODS_PER_WARP pods of a warp.  TAIL: the tile holds padding
+// nodes (>= N): score stores are guarded; full tiles carry no per-pair guard at all.
+// Ballot words go to a per-warp shared-memory slab (one STS per pair, every lane writes the
+// same word: no predicate, no ALU); after the tile lane j < TILE_WORDS pops word j back for
+// the fit-bitmap store (64 B per pod, coalesced) and the feasible count (popcount, reduced
+// across the warp once at the very end).
+template <int L, bool TAIL>
+__device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __restrict__ tl,
+                                         const int64_t (&rq)[PODS_PER_WARP][L],
+                                         const uint32_t (&colbits)[PODS_PER_WARP], int64_t* sp0,
+                                         size_t row_stride, uint32_t* s_words, uint32_t node_base,
+                                         uint32_t lane, bool want_score,
+                                         int64_t (&best_s)[PODS_PER_WARP], int32_t (&best_n)[PODS_PER_WARP]) {
+  int64_t* sp[PODS_PER_WARP];
+#pragma unroll
+  for (int r = 0; r < PODS_PER_WARP; ++r) sp[r] = sp0 + r * row_stride;
+  const int64_t* tp = tl + lane;
+  int32_t node = (int32_t)(node_base + lane);
+  uint32_t* wp = s_words;
+#pragma unroll 1
+  for (int jb = 0; jb < TILE_WORDS; jb += 4) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      int64_t lf[L];
+#pragma unroll
+      for (int d = 0; d < L; ++d) lf[d] = tp[d * NODE_TILE + jj * 32];
+      const bool in_range = !TAIL || ((uint32_t)node + jj * 32 < a.N);
+#pragma unroll
+      for (int r = 0; r < PODS_PER_WARP; ++r) {
+        int64_t m = lf[0] - rq[r][0];
+#pragma unroll
+        for (int d = 1; d < L; ++d) m = min64(m, lf[d] - rq[r][d]);
+        const bool fit = (m >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
+        wp[r * TILE_WORDS + jj] = __ballot_sync(0xffffffffu, fit);
+        if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
+        if (want_score && in_range)
+          __stcs(reinterpret_cast<long long*>(sp[r] + jj * 32), fit ? (long long)m : (long long)INT64_MIN);
+      }
+    }
+    tp += 128;
+    node += 128;
+    wp += 4;
+#pragma unroll
+    for (int r = 0; r < PODS_PER_WARP; ++r) sp[r] += 128;
+  }
+}
+
 template <int L>
-__global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? 2 : 1)) gang_fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ? 2 : 1))) gang_fit_kernel(FitArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [2 stages][L][NODE_TILE] int64 | [PODS_PER_CTA][L] int64 | mbarriers
+  // layout: [2 stages][L][NODE_TILE] int64 | [PODS_PER_CTA][L] int64 | mbarriers | ballot words
   int64_t* s_tile = reinterpret_cast<int64_t*>(smem_raw);
   int64_t* s_req = s_tile + 2 * L * NODE_TILE;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_req + PODS_PER_CTA * L);
+  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(s_bar + 2);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t* s_words = s_words_all + wid * PODS_PER_WARP * TILE_WORDS;
   const uint32_t pod0 = blockIdx.x * PODS_PER_CTA;
+  const uint32_t wpod0 = pod0 + wid * PODS_PER_WARP;  // first pod of this warp
   const uint32_t n_tiles = a.Npad / NODE_TILE;
   constexpr uint32_t ROW_BYTES = NODE_TILE * sizeof(int64_t);
 
@@ -755,12 +820,10 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? 2 : 1)) gang_fit_kernel
   for (uint32_t i = tid; i < PODS_PER_CTA * L; i += FIT_THREADS) {
     const uint32_t pl = i / L, d = i % L;
     const uint32_t p = pod0 + pl;
-    int64_t v = UNCHECKED_REQ;
+    int64_t v = 0;
     if (p < a.P) {
       const bool present = d < 4 || ((a.req_present[p] >> d) & 1u);
-      if (present) v = a.req[(size_t)d * a.P + p];
-    } else {
-      v = 0;
+      v = present ? a.req[(size_t)d * a.P + p] : UNCHECKED_REQ;
     }
     s_req[pl * L + d] = v;
   }
@@ -777,71 +840,48 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? 2 : 1)) gang_fit_kernel
     if (n_tiles > 1) issue(1, 1);
   }
 
-  // per-pod state of this warp
+  // per-pod state of this warp (requests are warp-uniform, in registers for the whole sweep).
+  // The score / bitmap buffers hold PODS_PER_CTA-padded rows, so pods >= P need no guard.
+  const bool want_score = a.score != nullptr;
+  const bool want_bitmap = a.fit_bitmap != nullptr;
   uint32_t cnt[PODS_PER_WARP];
   int64_t best_s[PODS_PER_WARP];
   int32_t best_n[PODS_PER_WARP];
-  uint32_t cls[PODS_PER_WARP];
+  int64_t rq[PODS_PER_WARP][L];
+  uint32_t coff[PODS_PER_WARP];
 #pragma unroll
-  for (int k = 0; k < PODS_PER_WARP; ++k) {
-    cnt[k] = 0; best_s[k] = INT64_MIN; best_n[k] = -1;
-    const uint32_t p = pod0 + wid * PODS_PER_WARP + k;
-    cls[k] = p < a.P ? a.fit_class[p] : 0u;
+  for (int r = 0; r < PODS_PER_WARP; ++r) {
+    cnt[r] = 0; best_s[r] = INT64_MIN; best_n[r] = -1;
+    const uint32_t p = wpod0 + r;
+    coff[r] = (p < a.P ? a.fit_class[p] : 0u) * n_tiles * 32 + lane;
+#pragma unroll
+    for (int d = 0; d < L; ++d) rq[r][d] = s_req[(wid * PODS_PER_WARP + r) * L + d];
   }
-  const bool want_score = a.score != nullptr;
-  const bool want_bitmap = a.fit_bitmap != nullptr;
 
   for (uint32_t tile = 0; tile < n_tiles; ++tile) {
     const uint32_t stage = tile & 1;
+    uint32_t colbits[PODS_PER_WARP];
+#pragma unroll
+    for (int r = 0; r < PODS_PER_WARP; ++r) colbits[r] = __ldg(a.classfit + coff[r] + tile * 32);
     mbar_wait(&s_bar[stage], (tile >> 1) & 1);
     const int64_t* tl = s_tile + stage * L * NODE_TILE;
     const uint32_t node_base = tile * NODE_TILE;
-    const uint32_t word_base = node_base >> 5;
+    int64_t* sp0 = want_score ? a.score + (size_t)wpod0 * a.N + node_base + lane : nullptr;
+    if (node_base + NODE_TILE <= a.N)
+      fit_tile<L, false>(a, tl, rq, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
+    else
+      fit_tile<L, true>(a, tl, rq, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
+    __syncwarp();
+    if (lane < TILE_WORDS) {
+      const uint32_t word = (node_base >> 5) + lane;
 #pragma unroll
-    for (int kb = 0; kb < PODS_PER_WARP; kb += POD_BLOCK) {
-      // requests of POD_BLOCK pods (warp-uniform values)
-      int64_t rq[POD_BLOCK][L];
-#pragma unroll
-      for (int r = 0; r < POD_BLOCK; ++r)
-#pragma unroll
-        for (int d = 0; d < L; ++d) rq[r][d] = s_req[(wid * PODS_PER_WARP + kb + r) * L + d];
-      uint32_t words[POD_BLOCK];  // lane j keeps ballot word j of the tile
-#pragma unroll
-      for (int r = 0; r < POD_BLOCK; ++r) words[r] = 0;
-#pragma unroll 2
-      for (uint32_t j = 0; j < NODE_TILE / 32; ++j) {
-        const uint32_t nl = j * 32 + lane;
-        const uint32_t node = node_base + nl;
-        int64_t lf[L];
-#pragma unroll
-        for (int d = 0; d < L; ++d) lf[d] = tl[d * NODE_TILE + nl];
-#pragma unroll
-        for (int r = 0; r < POD_BLOCK; ++r) {
-          const uint32_t k = kb + r;
-          const uint32_t p = pod0 + wid * PODS_PER_WARP + k;
-          int64_t m = lf[0] - rq[r][0];
-#pragma unroll
-          for (int d = 1; d < L; ++d) m = min64(m, lf[d] - rq[r][d]);
-          const uint32_t cw = (word_base + j) < a.W ? __ldg(&a.classfit[(size_t)cls[k] * a.W + word_base + j]) : 0u;
-          const bool fit = (m >= 0) && ((cw >> lane) & 1u);
-          const uint32_t bal = __ballot_sync(0xffffffffu, fit);
-          cnt[k] += __popc(bal);
-          if (lane == j) words[r] = bal;
-          const int64_t sc = fit ? m : INT64_MIN;
-          if (fit && m > best_s[k]) { best_s[k] = m; best_n[k] = (int32_t)node; }
-          if (want_score && p < a.P && node < a.N) __stcs(reinterpret_cast<long long*>(&a.score[(size_t)p * a.N + node]), (long long)sc);
-        }
-      }
-      if (want_bitmap) {
-#pragma unroll
-        for (int r = 0; r < POD_BLOCK; ++r) {
-          const uint32_t p = pod0 + wid * PODS_PER_WARP + kb + r;
-          if (p < a.P && lane < NODE_TILE / 32 && word_base + lane < a.W)
-            a.fit_bitmap[(size_t)p * a.W + word_base + lane] = words[r];
-        }
+      for (int r = 0; r < PODS_PER_WARP; ++r) {
+        const uint32_t w = s_words[r * TILE_WORDS + lane];
+        cnt[r] += __popc(w);
+        if (want_bitmap && word < a.W) a.fit_bitmap[(size_t)(wpod0 + r) * a.W + word] = w;
       }
     }
-    __syncthreads();  // everyone is done reading this stage
+    __syncthreads();  // everyone is done reading this stage (and the warp's ballot slab)
     if (tid == 0 && tile + 2 < n_tiles) issue(tile + 2, stage);
   }
 
@@ -851,15 +891,17 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? 2 : 1)) gang_fit_kernel
   for (int k = 0; k < PODS_PER_WARP; ++k) {
     int64_t s = best_s[k];
     int32_t n = best_n[k];
+    uint32_t c = cnt[k];
     for (int o = 16; o; o >>= 1) {
       const int64_t os = __shfl_xor_sync(0xffffffffu, s, o);
       const int32_t on = __shfl_xor_sync(0xffffffffu, n, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
       if (on >= 0 && (n < 0 || os > s || (os == s && on < n))) { s = os; n = on; }
     }
-    const uint32_t p = pod0 + wid * PODS_PER_WARP + k;
+    const uint32_t p = wpod0 + k;
     if (p < a.P) {
       if (lane == 0) {
-        a.feasible_count[p] = cnt[k];
+        a.feasible_count[p] = c;
         a.best_node[p] = n;
         a.best_score[p] = s;
       }
@@ -867,7 +909,7 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? 2 : 1)) gang_fit_kernel
         const int32_t g = a.gid[p];
         if (g >= 0 && (uint32_t)g < a.G) {
           my_gid = (uint32_t)g;
-          my_pass = (a.prefilter[p] == BS_PF_PASS && cnt[k] > 0) ? 1u : 0u;
+          my_pass = (a.prefilter[p] == BS_PF_PASS && c > 0) ? 1u : 0u;
         }
       }
     }
@@ -908,7 +950,8 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? 2 : 1)) gang_fit_kernel
 }
 
 inline size_t gang_fit_smem_bytes(int L) {
-  return (size_t)(2 * L * NODE_TILE + PODS_PER_CTA * L) * sizeof(int64_t) + 2 * sizeof(uint64_t);
+  return (size_t)(2 * L * NODE_TILE + PODS_PER_CTA * L) * sizeof(int64_t) + 2 * sizeof(uint64_t) +
+         (size_t)PODS_PER_CTA * TILE_WORDS * sizeof(uint32_t);
 }
 
 }  // namespace bsk

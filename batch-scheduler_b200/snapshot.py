@@ -184,11 +184,44 @@ class Snapshot:
         return Snapshot(self.nodes.copy(), self.pods.copy(), self.groups.copy(), self.name,
                         dict(self.meta))
 
+    def resolve_groups(self) -> "Snapshot":
+        """Applies fillOccupiedObj's first-pod capture (core.go:486-493) on the host, over the WHOLE
+        pod table: for every group the first pod (table order) that reaches fillOccupiedObj becomes
+        pgs.Pod (HAS_POD + rep masks) and, if Spec.MinResources is nil, supplies it (HAS_MINRES).
+        The engine does the same on device for the pods it sees; sharding must resolve first, because
+        findMaxPG (core.go:701) reads this state for groups whose pods live on another rank."""
+        s = self.copy()
+        pt, gt = s.pods, s.groups
+        G = gt.n
+        if G == 0 or pt.n == 0:
+            return s
+        gid = pt.gid
+        ok = (gid >= 0) & (gid < G) & ((pt.flags & POD_PERMITTED_RECENTLY) == 0)
+        ok &= (gt.flags[np.clip(gid, 0, G - 1)] & GROUP_DENIED) == 0
+        first = np.full(G, pt.n, np.int64)
+        idx = np.nonzero(ok)[0]
+        np.minimum.at(first, gid[idx], idx)
+        has = first < pt.n
+        fp = np.where(has, first, 0)
+        take_pod = has & ((gt.flags & GROUP_HAS_POD) == 0)
+        take_res = has & ((gt.flags & GROUP_HAS_MINRES) == 0)
+        gt.rep_sel = np.where(take_pod, pt.sel_mask[fp], gt.rep_sel)
+        gt.rep_tol = np.where(take_pod, pt.tol_mask[fp], gt.rep_tol)
+        pres = pt.req_present[fp] & ~np.uint32(0xF)
+        for d in range(gt.lanes):
+            lane_present = np.ones(G, bool) if d < 4 else ((pres >> np.uint32(d)) & 1).astype(bool)
+            gt.min_res[d] = np.where(take_res, np.where(lane_present, pt.req[d][fp], 0), gt.min_res[d])
+        gt.min_res_present = np.where(take_res, pres, gt.min_res_present).astype(np.uint32)
+        gt.flags = (gt.flags | np.where(take_pod, GROUP_HAS_POD, 0).astype(np.uint8)
+                    | np.where(take_res, GROUP_HAS_MINRES, 0).astype(np.uint8))
+        return s
+
     def shard_groups(self, rank: int, world: int) -> "Snapshot":
         """Rank-local snapshot: contiguous group range balanced by pod count.
 
         The node table and the group table are replicated; only the pods of the
-        rank's groups (and the ungrouped pods with index % world == rank) stay."""
+        rank's groups (and the ungrouped pods with index % world == rank) stay.
+        Call on a snapshot that went through resolve_groups()."""
         P, G = self.pods.n, self.groups.n
         per_group = np.bincount(self.pods.gid[self.pods.gid >= 0], minlength=G)
         cum = np.concatenate([[0], np.cumsum(per_group)])
