@@ -107,7 +107,12 @@ struct bs_engine {
 
   // node table (device, padded to Npad) + derived
   DevBuf d_alloc, d_requested, d_pod_count, d_apres, d_rpres, d_label, d_taint, d_nflags;
-  DevBuf d_left_eff, d_left_present, d_classfit;
+  DevBuf d_left_w, d_left_n, d_left_present, d_classfit;
+  LaneMap lane_map{};
+  bool lane_map_valid = false;
+  // per-lane maxima of |value| (lane classification wide / narrow)
+  int64_t max_alloc[BS_MAX_LANES] = {}, max_requested[BS_MAX_LANES] = {}, max_req[BS_MAX_LANES] = {};
+  int64_t max_pod_count = 0;
   // pod table
   DevBuf d_req, d_ppres, d_gid, d_prio, d_ts, d_pflags, d_pod_fit_class, d_pod_rep_class;
   // group table
@@ -118,7 +123,7 @@ struct bs_engine {
   uint32_t n_fit_classes = 0, n_rep_classes = 0;
   // effective group state + round scratch
   DevBuf d_eflags, d_emin_res, d_emrpres, d_erep_class, d_first_pod, d_in_round, d_contrib, d_done, d_okA;
-  DevBuf d_state, d_pre, d_pre_present, d_pre_stats;
+  DevBuf d_state, d_pre, d_pre_present, d_pre_stats, d_max_partial, d_pre_part, d_pre_part_pres, d_pre_cstats, d_pre_done;
   uint32_t prefix_slots = 0;
   // outputs
   DevBuf d_prefilter, d_feasible, d_best_node, d_best_score, d_admit, d_admit_bitmap, d_new_denied,
@@ -174,6 +179,28 @@ bool in_range(const int64_t* a, size_t n) {
   }
   return lo >= -lim && hi <= lim;
 }
+
+// per-lane max |value| of a [L][n] table; false if any value is outside +-BS_VALUE_LIMIT
+bool lane_maxima(const int64_t* a, uint32_t L, size_t n, int64_t* out) {
+  bool ok = true;
+  for (uint32_t d = 0; d < L; ++d) {
+    const int64_t* row = a + (size_t)d * n;
+    int64_t lo = 0, hi = 0;
+    for (size_t i = 0; i < n; ++i) {
+      lo = std::min(lo, row[i]);
+      hi = std::max(hi, row[i]);
+    }
+    ok = ok && lo >= -BS_VALUE_LIMIT && hi <= BS_VALUE_LIMIT;
+    out[d] = std::max(hi, lo == INT64_MIN ? INT64_MAX : -lo);
+  }
+  return ok;
+}
+
+// Lane classification for the fit kernel (kernels.cuh "Narrow lanes"): lane d is narrow when every
+// residual |left[d]| and every request |req[d]| of the round is <= 2^27.  The narrow set must
+// contain a fixed lane (always a real value) and the (LW, LN) pair must be one the dispatch
+// table instantiates; otherwise every lane is wide.
+LaneMap classify_lanes(const bs_engine* e);
 
 inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
@@ -255,6 +282,15 @@ PrefixOut prefix_out(const bs_engine* e) {
   return o;
 }
 
+PrefixScratch prefix_scratch(const bs_engine* e) {
+  PrefixScratch sc;
+  sc.part = e->d_pre_part.as<int64_t>();
+  sc.part_pres = e->d_pre_part_pres.as<uint32_t>();
+  sc.cstats = e->d_pre_cstats.as<ClassStats>();
+  sc.done = e->d_pre_done.as<uint32_t>();
+  return sc;
+}
+
 struct StageTimer {
   bs_engine* e;
   int k;
@@ -275,54 +311,122 @@ struct StageTimer {
   }
 };
 
-template <int MAXL>
-void launch_prefix_t(NodeTab t, const uint64_t* rsel, const uint64_t* rtol, uint32_t c0, int mode,
-                     uint64_t xsel, uint64_t xtol, float xpct, const RoundState* st, PrefixOut po,
-                     uint32_t grid, cudaStream_t s) {
-  class_prefix_kernel<MAXL><<<grid, PREFIX_THREADS, 0, s>>>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po);
+inline int prefix_maxl(uint32_t L) {
+  return L <= 4 ? 4 : L <= 5 ? 5 : L <= 6 ? 6 : L <= 8 ? 8 : L <= 9 ? 9 : L <= 12 ? 12 : 16;
 }
-void launch_prefix(uint32_t L, NodeTab t, const uint64_t* rsel, const uint64_t* rtol, uint32_t c0, int mode,
-                   uint64_t xsel, uint64_t xtol, float xpct, const RoundState* st, PrefixOut po,
-                   uint32_t grid, cudaStream_t s) {
-  if (L <= 4) launch_prefix_t<4>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
-  else if (L <= 5) launch_prefix_t<5>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
-  else if (L <= 6) launch_prefix_t<6>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
-  else if (L <= 8) launch_prefix_t<8>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
-  else if (L <= 9) launch_prefix_t<9>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
-  else if (L <= 12) launch_prefix_t<12>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
-  else launch_prefix_t<16>(t, rsel, rtol, c0, mode, xsel, xtol, xpct, st, po, grid, s);
+template <int MAXL>
+void launch_prefix_t(NodeTab t, PrefixSel ps, PrefixScratch sc, PrefixOut po, uint32_t n_classes, cudaStream_t s) {
+  const uint32_t n_chunks = cdiv(t.N, PREFIX_CHUNK);
+  dim3 grid(n_chunks, n_classes);
+  prefix_partial_kernel<MAXL><<<grid, PREFIX_CHUNK, 0, s>>>(t, ps, sc, n_chunks);
+  prefix_scan_kernel<MAXL><<<grid, PREFIX_CHUNK, 0, s>>>(t, ps, sc, n_chunks, po);
+}
+// two launches: chunk totals, then offsets + in-chunk scan + statistics
+void launch_prefix(uint32_t L, NodeTab t, PrefixSel ps, PrefixScratch sc, PrefixOut po, uint32_t n_classes,
+                   cudaStream_t s) {
+  switch (prefix_maxl(L)) {
+    case 4: launch_prefix_t<4>(t, ps, sc, po, n_classes, s); break;
+    case 5: launch_prefix_t<5>(t, ps, sc, po, n_classes, s); break;
+    case 6: launch_prefix_t<6>(t, ps, sc, po, n_classes, s); break;
+    case 8: launch_prefix_t<8>(t, ps, sc, po, n_classes, s); break;
+    case 9: launch_prefix_t<9>(t, ps, sc, po, n_classes, s); break;
+    case 12: launch_prefix_t<12>(t, ps, sc, po, n_classes, s); break;
+    default: launch_prefix_t<16>(t, ps, sc, po, n_classes, s); break;
+  }
 }
 
-template <int L>
+template <int LW, int LN>
 cudaError_t launch_fit_t(const FitArgs& a, uint32_t grid, cudaStream_t s) {
-  const size_t smem = gang_fit_smem_bytes(L);
+  const size_t smem = gang_fit_smem_bytes(LW, LN);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<LW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem);
     if (er != cudaSuccess) return er;
     attr_set = true;
   }
-  gang_fit_kernel<L><<<grid, FIT_THREADS, smem, s>>>(a);
+  gang_fit_kernel<LW, LN><<<grid, FIT_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
-cudaError_t launch_fit(uint32_t L, const FitArgs& a, uint32_t grid, cudaStream_t s) {
-  switch (L) {
-    case 4: return launch_fit_t<4>(a, grid, s);
-    case 5: return launch_fit_t<5>(a, grid, s);
-    case 6: return launch_fit_t<6>(a, grid, s);
-    case 7: return launch_fit_t<7>(a, grid, s);
-    case 8: return launch_fit_t<8>(a, grid, s);
-    case 9: return launch_fit_t<9>(a, grid, s);
-    case 10: return launch_fit_t<10>(a, grid, s);
-    case 11: return launch_fit_t<11>(a, grid, s);
-    case 12: return launch_fit_t<12>(a, grid, s);
-    case 13: return launch_fit_t<13>(a, grid, s);
-    case 14: return launch_fit_t<14>(a, grid, s);
-    case 15: return launch_fit_t<15>(a, grid, s);
-    case 16: return launch_fit_t<16>(a, grid, s);
+
+constexpr int FIT_MAX_LW = 4, FIT_MAX_LN = 8;  // mixed wide/narrow instantiations: LW 0..4 x LN 1..8
+bool fit_variant_exists(uint32_t LW, uint32_t LN) {
+  if (LN == 0) return LW >= 4 && LW <= BS_MAX_LANES;
+  return LW <= FIT_MAX_LW && LN <= FIT_MAX_LN && LW + LN >= 4 && LW + LN <= BS_MAX_LANES;
+}
+
+template <int LW>
+cudaError_t launch_fit_ln(uint32_t LN, const FitArgs& a, uint32_t grid, cudaStream_t s) {
+  switch (LN) {
+#define BS_CASE(n) \
+  case n:          \
+    if constexpr (LW + n >= 4) return launch_fit_t<LW, n>(a, grid, s); else break;
+    BS_CASE(1) BS_CASE(2) BS_CASE(3) BS_CASE(4) BS_CASE(5) BS_CASE(6) BS_CASE(7) BS_CASE(8)
+#undef BS_CASE
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fit(const FitArgs& a, uint32_t grid, cudaStream_t s) {
+  const uint32_t LW = a.lm.LW, LN = a.lm.LN;
+  if (LN == 0) {
+    switch (LW) {
+      case 4: return launch_fit_t<4, 0>(a, grid, s);
+      case 5: return launch_fit_t<5, 0>(a, grid, s);
+      case 6: return launch_fit_t<6, 0>(a, grid, s);
+      case 7: return launch_fit_t<7, 0>(a, grid, s);
+      case 8: return launch_fit_t<8, 0>(a, grid, s);
+      case 9: return launch_fit_t<9, 0>(a, grid, s);
+      case 10: return launch_fit_t<10, 0>(a, grid, s);
+      case 11: return launch_fit_t<11, 0>(a, grid, s);
+      case 12: return launch_fit_t<12, 0>(a, grid, s);
+      case 13: return launch_fit_t<13, 0>(a, grid, s);
+      case 14: return launch_fit_t<14, 0>(a, grid, s);
+      case 15: return launch_fit_t<15, 0>(a, grid, s);
+      case 16: return launch_fit_t<16, 0>(a, grid, s);
+    }
+    return cudaErrorInvalidValue;
+  }
+  switch (LW) {
+    case 0: return launch_fit_ln<0>(LN, a, grid, s);
+    case 1: return launch_fit_ln<1>(LN, a, grid, s);
+    case 2: return launch_fit_ln<2>(LN, a, grid, s);
+    case 3: return launch_fit_ln<3>(LN, a, grid, s);
+    case 4: return launch_fit_ln<4>(LN, a, grid, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+LaneMap classify_lanes(const bs_engine* e) {
+  LaneMap lm{};
+  const uint32_t L = e->L;
+  bool narrow[BS_MAX_LANES];
+  bool fixed_narrow = false;
+  uint32_t ln = 0;
+  for (uint32_t d = 0; d < L; ++d) {
+    // |left| <= |scale(alloc)| + |requested| (pods lane: + len(Pods())); float32 rounding of a
+    // value <= 2^26 is exact, so the bound 2^26 + 2^26 = 2^27 holds.
+    int64_t used = e->max_requested[d];
+    if (d == LANE_PODS) used = std::max(used, e->max_pod_count);
+    narrow[d] = e->max_alloc[d] <= (NARROW_LIMIT >> 1) && used <= (NARROW_LIMIT >> 1) && e->max_req[d] <= NARROW_LIMIT;
+    if (narrow[d]) {
+      ++ln;
+      if (d < 4) fixed_narrow = true;
+    }
+  }
+  // keep at most FIT_MAX_LN narrow lanes (prefer the fixed ones) and at most FIT_MAX_LW wide ones
+  if (fixed_narrow && ln > (uint32_t)FIT_MAX_LN)
+    for (int d = (int)L - 1; d >= 4 && ln > (uint32_t)FIT_MAX_LN; --d)
+      if (narrow[d]) { narrow[d] = false; --ln; }
+  if (!fixed_narrow || !fit_variant_exists(L - ln, ln)) {
+    for (uint32_t d = 0; d < L; ++d) narrow[d] = false;
+    ln = 0;
+  }
+  for (uint32_t d = 0; d < L; ++d) {
+    if (narrow[d]) lm.narrow[lm.LN++] = (uint8_t)d;
+    else lm.wide[lm.LW++] = (uint8_t)d;
+  }
+  return lm;
 }
 
 // one LSD pass over `n` indices
@@ -451,6 +555,16 @@ int ensure_round_buffers(bs_engine* e) {
   CK(e->d_pre.ensure((size_t)slots * L * N * 8));
   CK(e->d_pre_present.ensure((size_t)slots * N * 4));
   CK(e->d_pre_stats.ensure((size_t)slots * sizeof(ClassStats)));
+  {
+    const size_t n_chunks = cdiv(N, PREFIX_CHUNK);
+    const bool fresh = e->d_pre_done.cap < (size_t)slots * 4;
+    CK(e->d_pre_part.ensure((size_t)slots * n_chunks * BS_MAX_LANES * 8));
+    CK(e->d_pre_part_pres.ensure((size_t)slots * n_chunks * 4));
+    CK(e->d_pre_cstats.ensure((size_t)slots * n_chunks * sizeof(ClassStats)));
+    CK(e->d_pre_done.ensure((size_t)slots * 4));
+    if (fresh) CK(cudaMemsetAsync(e->d_pre_done.p, 0, e->d_pre_done.cap, e->s));
+    CK(e->d_max_partial.ensure((size_t)cdiv(G, FINDMAX_THREADS * FINDMAX_PER_THREAD) * sizeof(MaxState)));
+  }
   // sort scratch
   const uint32_t M = std::max(P, G);
   CK(e->d_gk0.ensure((size_t)G * 8));
@@ -480,11 +594,13 @@ int prepare_nodes(bs_engine* e) {
   // node_left + class fit bitmap (only when nodes or classes changed)
   NodeTab t = node_tab(e);
   StageTimer tm(e, BS_K_NODE_LEFT, e->s);
-  CK(e->d_left_eff.ensure((size_t)e->L * e->Npad * 8));
+  CK(e->d_left_w.ensure((size_t)std::max(e->lane_map.LW, 1u) * e->Npad * 8));
+  CK(e->d_left_n.ensure((size_t)std::max(e->lane_map.LN, 1u) * e->Npad * 4));
   CK(e->d_left_present.ensure((size_t)e->Npad * 4));
   const uint32_t n_tiles = e->Npad / NODE_TILE;
   CK(e->d_classfit.ensure((size_t)e->n_fit_classes * n_tiles * 32 * 4));
-  node_left_kernel<<<cdiv(e->Npad, 256), 256, 0, e->s>>>(t, e->d_left_eff.as<int64_t>(),
+  node_left_kernel<<<cdiv(e->Npad, 256), 256, 0, e->s>>>(t, e->lane_map, e->d_left_w.as<int64_t>(),
+                                                         e->d_left_n.as<int32_t>(),
                                                          e->d_left_present.as<uint32_t>());
   tm.launched();
   {
@@ -508,6 +624,14 @@ int evaluate_async_locked(bs_engine* e) {
   if (e->classes_dirty) {
     if ((rc = rebuild_classes(e))) return rc;
     reprepare = true;
+  }
+  {
+    const LaneMap lm = classify_lanes(e);
+    if (!e->lane_map_valid || memcmp(&lm, &e->lane_map, sizeof(lm)) != 0) {
+      e->lane_map = lm;
+      e->lane_map_valid = true;
+      reprepare = true;
+    }
   }
   if ((rc = ensure_round_buffers(e))) return rc;
   for (int k = 0; k < BS_K_COUNT; ++k) e->k_valid[k] = false;
@@ -571,28 +695,35 @@ int evaluate_async_locked(bs_engine* e) {
       group_effective_kernel<<<gb, 256, 0, e->s>>>(pt, gt, ge);
       tm.launched();
     }
-    find_max_pg_kernel<<<1, 1024, 0, e->s>>>(gt, ge, st);
-    tm.launched();
+    const uint32_t nmp = cdiv(std::max(G, 1u), FINDMAX_THREADS * FINDMAX_PER_THREAD);
+    find_max_partial_kernel<<<nmp, FINDMAX_THREADS, 0, e->s>>>(gt, ge, e->d_max_partial.as<MaxState>());
+    find_max_final_kernel<<<1, 1024, 0, e->s>>>(gt, ge, e->d_max_partial.as<MaxState>(), nmp, st);
+    tm.launched(2);
   }
   // ordered cluster scans (compareClusterResourceAndRequire) per rep class
   {
     StageTimer tm(e, BS_K_CLASS_PREFIX, e->s);
     if (e->N && G && P) {
+      PrefixScratch psc = prefix_scratch(e);
+      PrefixSel ps{e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), 0, 0, 0, 0, 0.f, st};
       for (uint32_t c0 = 0; c0 < e->n_rep_classes; c0 += e->prefix_slots) {
         const uint32_t nc = std::min(e->prefix_slots, e->n_rep_classes - c0);
-        launch_prefix(L, t, e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), c0, 0, 0, 0, 0.f, st, po, nc, e->s);
+        ps.c0 = c0;
+        ps.mode = 0;
+        launch_prefix(L, t, ps, psc, po, nc, e->s);
         group_check_kernel<<<cdiv(G * 32, 256), 256, 0, e->s>>>(t, gt, ge, po, c0, nc, st, e->d_okA.as<uint8_t>());
-        tm.launched(2);
+        tm.launched(3);
       }
-      launch_prefix(L, t, e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), 0, 1, 0, 0, 0.f, st, po, 1, e->s);
-      tm.launched();
+      ps.c0 = 0;
+      ps.mode = 1;
+      launch_prefix(L, t, ps, psc, po, 1, e->s);
+      tm.launched(2);
     }
   }
   {
     StageTimer tm(e, BS_K_PREFILTER, e->s);
     if (P) {
-      const uint64_t threads = (uint64_t)P * 32;
-      prefilter_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, e->s>>>(
+      prefilter_kernel<<<cdiv(P, PREFILTER_THREADS), PREFILTER_THREADS, 0, e->s>>>(
           t, pt, gt, ge, po, st, e->d_okA.as<uint8_t>(), e->d_prefilter.as<uint8_t>(),
           e->d_new_denied.as<uint8_t>());
       tm.launched();
@@ -607,7 +738,11 @@ int evaluate_async_locked(bs_engine* e) {
     StageTimer tm(e, BS_K_GANG_FIT, e->s);
     if (P) {
       FitArgs a;
-      a.left_eff = e->d_left_eff.as<int64_t>();
+      a.left_w = e->d_left_w.as<int64_t>();
+      a.left_n = e->d_left_n.as<int32_t>();
+      a.lm = e->lane_map;
+      a.left_w_pitch = (uint64_t)e->Npad * 8;
+      a.left_n_pitch = (uint64_t)e->Npad * 4;
       a.classfit = e->d_classfit.as<uint32_t>();
       a.req = e->d_req.as<int64_t>();
       a.req_present = e->d_ppres.as<uint32_t>();
@@ -628,7 +763,7 @@ int evaluate_async_locked(bs_engine* e) {
       a.fit_bitmap = (e->out_flags & BS_OUT_FIT_BITMAP) ? e->d_fit_bitmap.as<uint32_t>() : nullptr;
       a.score = (e->out_flags & BS_OUT_SCORE) ? e->d_score.as<int64_t>() : nullptr;
       a.P = P; a.N = e->N; a.Npad = e->Npad; a.W = e->W; a.G = G;
-      CK(launch_fit(L, a, cdiv(P, PODS_PER_CTA), e->s));
+      CK(launch_fit(a, cdiv(P, PODS_PER_CTA), e->s));
       tm.launched();
     }
   }
@@ -741,13 +876,14 @@ void bs_destroy(bs_engine* e) {
   if (e->s) cudaStreamSynchronize(e->s);
   if (e->s2) cudaStreamSynchronize(e->s2);
   DevBuf* bufs[] = {&e->d_alloc, &e->d_requested, &e->d_pod_count, &e->d_apres, &e->d_rpres, &e->d_label,
-                    &e->d_taint, &e->d_nflags, &e->d_left_eff, &e->d_left_present, &e->d_classfit, &e->d_req,
+                    &e->d_taint, &e->d_nflags, &e->d_left_w, &e->d_left_n, &e->d_left_present, &e->d_classfit, &e->d_req,
                     &e->d_ppres, &e->d_gid, &e->d_prio, &e->d_ts, &e->d_pflags, &e->d_pod_fit_class,
                     &e->d_pod_rep_class, &e->d_min_member, &e->d_scheduled, &e->d_matched, &e->d_gflags,
                     &e->d_min_res, &e->d_mrpres, &e->d_creation, &e->d_name_rank, &e->d_group_rep_class,
                     &e->d_fsel, &e->d_ftol, &e->d_fnz, &e->d_rsel, &e->d_rtol, &e->d_eflags, &e->d_emin_res,
                     &e->d_emrpres, &e->d_erep_class, &e->d_first_pod, &e->d_in_round, &e->d_contrib,
-                    &e->d_done, &e->d_okA, &e->d_state, &e->d_pre, &e->d_pre_present, &e->d_pre_stats,
+                    &e->d_done, &e->d_okA, &e->d_state, &e->d_pre, &e->d_pre_present, &e->d_pre_stats, &e->d_max_partial, &e->d_pre_part,
+                    &e->d_pre_part_pres, &e->d_pre_cstats, &e->d_pre_done,
                     &e->d_prefilter, &e->d_feasible, &e->d_best_node, &e->d_best_score, &e->d_admit,
                     &e->d_admit_bitmap, &e->d_new_denied, &e->d_fit_bitmap, &e->d_score, &e->d_order,
                     &e->d_rank, &e->d_gk0, &e->d_gk1, &e->d_pk0, &e->d_pk1, &e->d_idx_a, &e->d_idx_b,
@@ -775,8 +911,11 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   if (N && (!t->alloc || !t->requested || !t->pod_count || !t->alloc_present || !t->req_present ||
             !t->label_mask || !t->taint_mask || !t->flags))
     return fail(e, BS_E_INVAL, "bs_upload_nodes: null column");
-  if (!in_range(t->alloc, (size_t)L * N) || !in_range(t->requested, (size_t)L * N))
+  int64_t mx_a[BS_MAX_LANES] = {}, mx_r[BS_MAX_LANES] = {};
+  if (!lane_maxima(t->alloc, L, N, mx_a) || !lane_maxima(t->requested, L, N, mx_r))
     return fail(e, BS_E_RANGE, "bs_upload_nodes: value outside +-2^56");
+  int64_t mx_pc = 0;
+  for (uint32_t i = 0; i < N; ++i) mx_pc = std::max<int64_t>(mx_pc, std::abs((int64_t)t->pod_count[i]));
   CK(cudaSetDevice(e->device));
   const uint32_t Npad = std::max(1u, cdiv(N, NODE_TILE)) * NODE_TILE;
   int rc;
@@ -789,6 +928,9 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   if ((rc = upload_vec(e, e->d_taint, t->taint_mask, N, Npad))) return rc;
   if ((rc = upload_vec(e, e->d_nflags, t->flags, N, Npad))) return rc;
   CK(cudaStreamSynchronize(e->s));
+  memcpy(e->max_alloc, mx_a, sizeof(mx_a));
+  memcpy(e->max_requested, mx_r, sizeof(mx_r));
+  e->max_pod_count = mx_pc;
   e->N = N;
   e->Npad = Npad;
   e->W = cdiv(N, 32);
@@ -848,7 +990,8 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   if (P && (!t->req || !t->req_present || !t->gid || !t->sel_mask || !t->tol_mask || !t->priority ||
             !t->ts_ns || !t->flags))
     return fail(e, BS_E_INVAL, "bs_upload_pods: null column");
-  if (!in_range(t->req, (size_t)L * P)) return fail(e, BS_E_RANGE, "bs_upload_pods: value outside +-2^56");
+  int64_t mx_q[BS_MAX_LANES] = {};
+  if (!lane_maxima(t->req, L, P, mx_q)) return fail(e, BS_E_RANGE, "bs_upload_pods: value outside +-2^56");
   CK(cudaSetDevice(e->device));
   const uint32_t Pp = std::max(P, 1u);
   int rc;
@@ -888,6 +1031,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       if (((t->req_present[p] >> d) & 1u) && row[p] != 0) e->h_pnz[p] |= 1u << d;
   }
   CK(cudaStreamSynchronize(e->s));
+  memcpy(e->max_req, mx_q, sizeof(mx_q));
   e->P = P;
   e->have_pods = true;
   e->classes_dirty = true;
@@ -1060,8 +1204,14 @@ int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent, co
     memset(ok, 0, n_needs);  // empty snapshot list: the loop never runs (core.go:604,631)
     return BS_OK;
   }
-  DevBuf pre, pp, stats, dn, dnp, dok;
+  DevBuf pre, pp, stats, dn, dnp, dok, spart, spres, scst, sdone;
+  const size_t n_chunks = cdiv(N, PREFIX_CHUNK);
   cudaError_t er = pre.ensure((size_t)L * N * 8);
+  if (er == cudaSuccess) er = spart.ensure(n_chunks * BS_MAX_LANES * 8);
+  if (er == cudaSuccess) er = spres.ensure(n_chunks * 4);
+  if (er == cudaSuccess) er = scst.ensure(n_chunks * sizeof(ClassStats));
+  if (er == cudaSuccess) er = sdone.ensure(4);
+  if (er == cudaSuccess) er = cudaMemsetAsync(sdone.p, 0, 4, e->s);
   if (er == cudaSuccess) er = pp.ensure((size_t)N * 4);
   if (er == cudaSuccess) er = stats.ensure(sizeof(ClassStats));
   if (er == cudaSuccess) er = dn.ensure((size_t)L * n_needs * 8);
@@ -1072,16 +1222,19 @@ int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent, co
   if (er == cudaSuccess) {
     PrefixOut po{pre.as<int64_t>(), pp.as<uint32_t>(), stats.as<ClassStats>()};
     NodeTab t = node_tab(e);
-    launch_prefix(L, t, nullptr, nullptr, 0, 2, sel, tol, percent, nullptr, po, 1, e->s);
+    PrefixSel ps{nullptr, nullptr, 0, 2, sel, tol, percent, nullptr};
+    PrefixScratch psc{spart.as<int64_t>(), spres.as<uint32_t>(), scst.as<ClassStats>(), sdone.as<uint32_t>()};
+    launch_prefix(L, t, ps, psc, po, 1, e->s);
     const uint64_t threads = (uint64_t)n_needs * 32;
     needs_check_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, e->s>>>(
         t, po, dn.as<int64_t>(), dnp.as<uint32_t>(), n_needs, dok.as<uint8_t>());
-    e->launches += 2;
+    e->launches += 3;
     er = cudaMemcpyAsync(ok, dok.p, n_needs, cudaMemcpyDeviceToHost, e->s);
   }
   if (er == cudaSuccess) er = cudaStreamSynchronize(e->s);
   if (er == cudaSuccess) er = cudaGetLastError();
   pre.release(); pp.release(); stats.release(); dn.release(); dnp.release(); dok.release();
+  spart.release(); spres.release(); scst.release(); sdone.release();
   CK(er);
   return BS_OK;
 }

@@ -21,6 +21,18 @@ constexpr int LANE_CPU = 0, LANE_MEM = 1, LANE_EPH = 2, LANE_PODS = 3;
 // fails the >= 0 test, and never wins the min -> score = min over lanes present on BOTH sides.
 constexpr int64_t ABSENT_LEFT = (int64_t)1 << 61;      // left lane without a map key: never limits
 constexpr int64_t UNCHECKED_REQ = -((int64_t)1 << 61); // request lane without a map key: never checked
+// Narrow lanes: a lane whose every |left| and |req| is <= 2^27 (millicores, pod counts, GPUs ...)
+// is evaluated in int32: |real diff| <= 2^28 < any diff involving a 32-bit sentinel (>= 2^29-2^27),
+// and 2^29 - (-2^29) does not overflow.  The narrow set always contains a fixed lane (always a
+// real value), so the 32-bit min is always a real difference and widens by sign extension.
+constexpr int32_t ABSENT_LEFT32 = 1 << 29;
+constexpr int32_t UNCHECKED_REQ32 = -(1 << 29);
+constexpr int64_t NARROW_LIMIT = (int64_t)1 << 27;
+struct LaneMap {
+  uint8_t wide[BS_MAX_LANES];    // original lane index of wide slot k   (k < LW)
+  uint8_t narrow[BS_MAX_LANES];  // original lane index of narrow slot k (k < LN)
+  uint32_t LW, LN;
+};
 constexpr int NODE_TILE = 512;                          // nodes per shared-memory tile
 constexpr int FIT_THREADS = 256;
 constexpr int FIT_WARPS = FIT_THREADS / 32;
@@ -125,30 +137,41 @@ __device__ __forceinline__ bool compare_res(const int64_t* left, uint32_t lpres,
 
 // ---------------------------------------------------------------------------
 // K1  node_left_kernel — per node: residual capacity at percent 1.0 in the
-// sentinel form the fit kernel consumes (absent scalar lane -> ABSENT_LEFT),
-// class-independent (checkFit is applied per pod class by class_fit_kernel).
+// sentinel form the fit kernel consumes (absent scalar lane -> ABSENT_LEFT / ABSENT_LEFT32),
+// class-independent (checkFit is applied per pod class by class_fit_kernel), split into the
+// wide (int64) and narrow (int32) lane tables of the round's LaneMap.
 // Restates singleNodeResource core.go:647-668.  Padding nodes (>= N) get zeros.
-__global__ void node_left_kernel(NodeTab t, int64_t* __restrict__ left_eff /*[L][Npad]*/,
+__global__ void node_left_kernel(NodeTab t, LaneMap lm, int64_t* __restrict__ left_w /*[LW][Npad]*/,
+                                 int32_t* __restrict__ left_n /*[LN][Npad]*/,
                                  uint32_t* __restrict__ left_present /*[Npad]*/) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.Npad) return;
   if (i >= t.N) {
-    for (uint32_t d = 0; d < t.L; ++d) left_eff[(size_t)d * t.Npad + i] = 0;
+    for (uint32_t k = 0; k < lm.LW; ++k) left_w[(size_t)k * t.Npad + i] = 0;
+    for (uint32_t k = 0; k < lm.LN; ++k) left_n[(size_t)k * t.Npad + i] = 0;
     left_present[i] = 0;
     return;
   }
-  int64_t pc = t.requested[(size_t)LANE_PODS * t.Npad + i];
-  if (pc == 0) pc = t.pod_count[i];
-  left_eff[(size_t)LANE_PODS * t.Npad + i] = scale_f32(t.alloc[(size_t)LANE_PODS * t.Npad + i], 1.0f) - pc;
-  for (int d = 0; d < 3; ++d)
-    left_eff[(size_t)d * t.Npad + i] =
-        scale_f32(t.alloc[(size_t)d * t.Npad + i], 1.0f) - t.requested[(size_t)d * t.Npad + i];
   const uint32_t both = t.alloc_present[i] & t.req_present[i] & ~0xFu;
-  for (uint32_t d = 4; d < t.L; ++d) {
-    int64_t v = ABSENT_LEFT;
-    if ((both >> d) & 1u)
-      v = scale_f32(t.alloc[(size_t)d * t.Npad + i], 1.0f) - t.requested[(size_t)d * t.Npad + i];
-    left_eff[(size_t)d * t.Npad + i] = v;
+  auto lane_left = [&](uint32_t d, bool& present) -> int64_t {
+    present = true;
+    if (d == LANE_PODS) {
+      int64_t pc = t.requested[(size_t)LANE_PODS * t.Npad + i];
+      if (pc == 0) pc = t.pod_count[i];
+      return scale_f32(t.alloc[(size_t)LANE_PODS * t.Npad + i], 1.0f) - pc;
+    }
+    if (d >= 4 && !((both >> d) & 1u)) { present = false; return 0; }
+    return scale_f32(t.alloc[(size_t)d * t.Npad + i], 1.0f) - t.requested[(size_t)d * t.Npad + i];
+  };
+  for (uint32_t k = 0; k < lm.LW; ++k) {
+    bool pres;
+    const int64_t v = lane_left(lm.wide[k], pres);
+    left_w[(size_t)k * t.Npad + i] = pres ? v : ABSENT_LEFT;
+  }
+  for (uint32_t k = 0; k < lm.LN; ++k) {
+    bool pres;
+    const int64_t v = lane_left(lm.narrow[k], pres);
+    left_n[(size_t)k * t.Npad + i] = pres ? (int32_t)v : ABSENT_LEFT32;
   }
   left_present[i] = both;
 }
@@ -298,88 +321,110 @@ __device__ __forceinline__ uint32_t pre_allocated(const GroupTab& g, const Group
   return present;
 }
 
-// K3  find_max_pg_kernel — findMaxPG (core.go:701-739) as a parallel reduction
+// K3  findMaxPG (core.go:701-739) as ONE pass with an associative, order-insensitive merge
 // that reproduces the sequential table-order scan exactly (tie rule :725-735):
-//   F  = max finished over eligible groups; c0 = first index attaining F;
-//   if c0 is not "finished" (scheduled < minMember) it wins; otherwise the scan
-//   hands over to later F-candidates with Status.Scheduled==0 while the current
-//   holder is finished: the first of them with minMember!=0 wins, else the last.
-// One CTA of 1024 threads; G <= ~10^5 so three strided passes are a few us.
-__global__ void __launch_bounds__(1024) find_max_pg_kernel(GroupTab g, GroupEff e, RoundState* st) {
-  __shared__ uint32_t s_u32[32];
-  __shared__ uint32_t s_val;
-  __shared__ int s_panic;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  auto block_reduce = [&](uint32_t v, bool is_max) -> uint32_t {
-    for (int o = 16; o; o >>= 1) {
-      const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o);
-      v = is_max ? max(v, w) : min(v, w);
-    }
-    __syncthreads();
-    if (lane == 0) s_u32[wid] = v;
-    __syncthreads();
-    if (wid == 0) {
-      v = s_u32[lane];
-      for (int o = 16; o; o >>= 1) {
-        const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = is_max ? max(v, w) : min(v, w);
-      }
-      if (lane == 0) s_val = v;
-    }
-    __syncthreads();
-    return s_val;
-  };
-  auto eligible = [&](uint32_t i) -> bool {
-    const uint8_t f = e.flags[i];
-    return !(f & BS_GROUP_SCHEDULED) && (f & BS_GROUP_HAS_POD);  // :706-711
-  };
-  auto finished = [&](uint32_t i, bool& panic) -> uint32_t {
-    const uint32_t mm = g.min_member[i], sc = g.scheduled[i];
-    if ((uint32_t)(mm - sc) == 0u) return 0u;                    // :712-714 (uint32: <=0 means ==0)
-    if (mm == 0u) { panic = true; return 0u; }                   // :716-717 integer divide by zero
-    return (uint32_t)((g.matched[i] + sc) * 1000u) / mm;         // :716-717 uint32 wrap-around
-  };
-  if (tid == 0) s_panic = 0;
-  __syncthreads();
-  // pass 1: any eligible? F = max finished (encode "none" as 0, track any separately)
-  uint32_t fmax = 0, any = 0;
-  bool panic = false;
-  for (uint32_t i = tid; i < g.G; i += blockDim.x)
-    if (eligible(i)) { any = 1; fmax = max(fmax, finished(i, panic)); }
-  if (panic) s_panic = 1;
-  any = block_reduce(any, true);
-  const uint32_t F = block_reduce(fmax, true);
-  // pass 2: c0 = first eligible index with finished == F
-  uint32_t c0 = 0xffffffffu;
-  for (uint32_t i = tid; i < g.G; i += blockDim.x)
-    if (eligible(i)) { bool pn = false; if (finished(i, pn) == F) { c0 = i; break; } }
-  c0 = block_reduce(c0, false);
-  uint32_t winner = c0;
-  if (any && c0 != 0xffffffffu && g.scheduled[c0] >= g.min_member[c0]) {   // holder is "finished" (:730)
-    // pass 3: later F-candidates with Status.Scheduled == 0 (:731)
-    uint32_t zgood = 0xffffffffu, zlast = 0;  // zlast stores index+1
-    for (uint32_t i = c0 + 1 + tid; i < g.G; i += blockDim.x) {
-      if (!eligible(i)) continue;
-      bool pn = false;
-      if (finished(i, pn) != F || g.scheduled[i] != 0) continue;
-      if (g.min_member[i] != 0) zgood = min(zgood, i);
-      zlast = max(zlast, i + 1);
-    }
-    zgood = block_reduce(zgood, false);
-    zlast = block_reduce(zlast, true);
-    if (zgood != 0xffffffffu) {
-      // every earlier Z element has minMember==0 only if none of them stops the chain first:
-      // an earlier Z element with minMember!=0 would itself be zgood, so zgood is the stop.
-      winner = zgood;
-    } else if (zlast != 0) {
-      winner = zlast - 1;
-    }
+//   F  = max finished over eligible groups;  c0 = lowest index attaining F;
+//   Z  = later F-candidates with Status.Scheduled == 0 (the only ones that can take over, :731);
+//   winner = c0 unless c0 is "finished" (scheduled >= minMember, :730); then the scan hands over
+//   through Z while the holder is finished: the first Z element with minMember != 0 stops it
+//   (zgood), otherwise the last Z element holds (zlast).
+// Merging two partial states keeps the lower c0; the other side's c0 joins Z if it qualifies.
+struct MaxState {
+  uint32_t any;      // some eligible group seen
+  uint32_t F;        // max finished
+  uint32_t c0;       // lowest index with finished == F
+  uint32_t c0_flags; // bit0: scheduled >= minMember (holder is finished); bit1: scheduled == 0; bit2: minMember != 0
+  uint32_t zgood;    // lowest Z index with minMember != 0, 0xffffffff none
+  uint32_t zlast;    // highest Z index + 1, 0 none
+  uint32_t panic;
+};
+__device__ __forceinline__ MaxState max_state_empty() { return MaxState{0u, 0u, 0xffffffffu, 0u, 0xffffffffu, 0u, 0u}; }
+__device__ __forceinline__ MaxState max_state_merge(const MaxState& x, const MaxState& y) {
+  MaxState r;
+  if (!y.any || (x.any && x.F > y.F)) { r = x; r.panic = x.panic | y.panic; return r; }
+  if (!x.any || y.F > x.F) { r = y; r.panic = x.panic | y.panic; return r; }
+  const MaxState& lo = x.c0 < y.c0 ? x : y;
+  const MaxState& hi = x.c0 < y.c0 ? y : x;
+  r = lo;
+  r.zgood = min(lo.zgood, hi.zgood);
+  r.zlast = max(lo.zlast, hi.zlast);
+  if (hi.c0_flags & 2u) {            // the displaced c0 has Status.Scheduled == 0: it is a Z element
+    if (hi.c0_flags & 4u) r.zgood = min(r.zgood, hi.c0);
+    r.zlast = max(r.zlast, hi.c0 + 1);
   }
-  if (tid == 0) {
-    const bool none = !any || c0 == 0xffffffffu;
-    st->ref_panic = s_panic;
+  r.panic = x.panic | y.panic;
+  return r;
+}
+__device__ __forceinline__ MaxState max_state_shfl_xor(const MaxState& v, int o) {
+  MaxState r;
+  r.any = __shfl_xor_sync(0xffffffffu, v.any, o);
+  r.F = __shfl_xor_sync(0xffffffffu, v.F, o);
+  r.c0 = __shfl_xor_sync(0xffffffffu, v.c0, o);
+  r.c0_flags = __shfl_xor_sync(0xffffffffu, v.c0_flags, o);
+  r.zgood = __shfl_xor_sync(0xffffffffu, v.zgood, o);
+  r.zlast = __shfl_xor_sync(0xffffffffu, v.zlast, o);
+  r.panic = __shfl_xor_sync(0xffffffffu, v.panic, o);
+  return r;
+}
+__device__ __forceinline__ MaxState max_state_of(const GroupTab& g, const GroupEff& e, uint32_t i) {
+  MaxState st = max_state_empty();
+  const uint8_t f = e.flags[i];
+  if ((f & BS_GROUP_SCHEDULED) || !(f & BS_GROUP_HAS_POD)) return st;   // :706-711
+  const uint32_t mm = g.min_member[i], sc = g.scheduled[i];
+  uint32_t fin = 0;
+  if ((uint32_t)(mm - sc) != 0u) {                                       // :712-714 (uint32: <=0 means ==0)
+    if (mm == 0u) st.panic = 1;                                          // :716-717 integer divide by zero
+    else fin = (uint32_t)((g.matched[i] + sc) * 1000u) / mm;             // uint32 wrap-around
+  }
+  st.any = 1; st.F = fin; st.c0 = i;
+  st.c0_flags = (sc >= mm ? 1u : 0u) | (sc == 0u ? 2u : 0u) | (mm != 0u ? 4u : 0u);
+  return st;
+}
+__device__ __forceinline__ MaxState max_state_block_reduce(MaxState v, MaxState* s_part /*[32]*/) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int o = 16; o; o >>= 1) v = max_state_merge(v, max_state_shfl_xor(v, o));
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = lane < nw ? s_part[lane] : max_state_empty();
+    for (int o = 16; o; o >>= 1) v = max_state_merge(v, max_state_shfl_xor(v, o));
+  }
+  return v;  // valid in warp 0
+}
+
+constexpr int FINDMAX_THREADS = 256;
+constexpr int FINDMAX_PER_THREAD = 4;
+__global__ void __launch_bounds__(FINDMAX_THREADS)
+find_max_partial_kernel(GroupTab g, GroupEff e, MaxState* __restrict__ partial) {
+  __shared__ MaxState s_part[32];
+  MaxState v = max_state_empty();
+  const uint32_t base = blockIdx.x * (FINDMAX_THREADS * FINDMAX_PER_THREAD);
+#pragma unroll
+  for (int k = 0; k < FINDMAX_PER_THREAD; ++k) {
+    const uint32_t i = base + k * FINDMAX_THREADS + threadIdx.x;
+    if (i < g.G) v = max_state_merge(v, max_state_of(g, e, i));
+  }
+  v = max_state_block_reduce(v, s_part);
+  if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(1024)
+find_max_final_kernel(GroupTab g, GroupEff e, const MaxState* __restrict__ partial, uint32_t n_partial,
+                      RoundState* st) {
+  __shared__ MaxState s_part[32];
+  MaxState v = max_state_empty();
+  for (uint32_t i = threadIdx.x; i < n_partial; i += blockDim.x) v = max_state_merge(v, partial[i]);
+  v = max_state_block_reduce(v, s_part);
+  if (threadIdx.x == 0) {
+    const bool none = !v.any;
+    uint32_t winner = v.c0;
+    if (!none && (v.c0_flags & 1u)) {
+      if (v.zgood != 0xffffffffu) winner = v.zgood;
+      else if (v.zlast != 0) winner = v.zlast - 1;
+    }
+    st->ref_panic = (int32_t)v.panic;
     st->max_group = none ? -1 : (int32_t)winner;
-    st->max_finished = none ? 0u : F;
+    st->max_finished = none ? 0u : v.F;
     st->max_matched = none ? 0u : g.matched[winner];
     st->case_a = (!none && g.matched[winner] == 0) ? 1 : 0;              // core.go:135-136
     st->max_class = none ? -1 : (int32_t)e.rep_class[winner];
@@ -394,136 +439,209 @@ __global__ void __launch_bounds__(1024) find_max_pg_kernel(GroupTab g, GroupEff 
 }
 
 // ---------------------------------------------------------------------------
-// K4  class_prefix_kernel — the ordered scan of compareClusterResourceAndRequire
-// (core.go:595-632) for one rep class: running[i] = sum over visited nodes j<=i
-// of singleNodeResource(node_j, class, pct) with scalar keys accumulating as a
-// union (Resource.Add, :621).  One CTA per class; thread t owns a contiguous
-// run of nodes, block-wide exclusive scan of the per-thread totals in between.
-// mode 0: every class c in [c0, c0+gridDim.x) at pct 1.0, only when case A;
-// mode 1: the class of the max group at pct 0.7, only when case B (blockIdx 0);
+// K4  ordered cluster scan — compareClusterResourceAndRequire (core.go:595-632) for a
+// representative class: running[i] = sum over visited nodes j<=i of
+// singleNodeResource(node_j, class, pct), scalar keys accumulating as a union
+// (Resource.Add, :621).  Chunk-parallel: PREFIX_CHUNK nodes per CTA, coalesced loads.
+//   prefix_partial_kernel : per (chunk, class) totals of the chunk;
+//   prefix_scan_kernel    : offset = sum of the preceding chunks' totals, warp-shuffle scan
+//                           inside the chunk, prefixes written, chunk statistics; the last
+//                           chunk of a class to finish folds them into ClassStats.
+// mode 0: every class c in [c0, c0+gridDim.y) at pct 1.0, only when case A;
+// mode 1: the class of the max group at pct 0.7, only when case B (gridDim.y == 1);
 // mode 2: unconditional, explicit (sel,tol,pct) — bs_cluster_check.
-constexpr int PREFIX_THREADS = 256;
+constexpr int PREFIX_CHUNK = 256;
 struct PrefixOut {
   int64_t* pre;       // [classes][L][N]
   uint32_t* present;  // [classes][N]
   ClassStats* stats;  // [classes]
 };
+struct PrefixScratch {
+  int64_t* part;        // [classes][chunks][MAXL] chunk totals
+  uint32_t* part_pres;  // [classes][chunks]
+  ClassStats* cstats;   // [classes][chunks]
+  uint32_t* done;       // [classes] chunks finished (reset by the last one)
+};
+struct PrefixSel {
+  const uint64_t* rsel;
+  const uint64_t* rtol;
+  uint32_t c0;
+  int mode;
+  uint64_t xsel, xtol;
+  float xpct;
+  const RoundState* st;
+};
+__device__ __forceinline__ bool prefix_select(const PrefixSel& ps, uint32_t slot, uint64_t& sel, uint64_t& tol,
+                                              float& pct) {
+  if (ps.mode == 0) {
+    if (!ps.st->case_a || ps.st->max_group < 0) return false;
+    sel = ps.rsel[ps.c0 + slot]; tol = ps.rtol[ps.c0 + slot]; pct = 1.0f;
+  } else if (ps.mode == 1) {
+    if (ps.st->case_a || ps.st->max_group < 0) return false;
+    sel = ps.rsel[ps.st->max_class]; tol = ps.rtol[ps.st->max_class]; pct = 0.7f;
+  } else {
+    sel = ps.xsel; tol = ps.xtol; pct = ps.xpct;
+  }
+  return true;
+}
 
 template <int MAXL>
-__global__ void __launch_bounds__(PREFIX_THREADS)
-class_prefix_kernel(NodeTab t, const uint64_t* __restrict__ rsel, const uint64_t* __restrict__ rtol,
-                    uint32_t c0, int mode, uint64_t xsel, uint64_t xtol, float xpct,
-                    const RoundState* __restrict__ st, PrefixOut out) {
-  uint32_t c_out = blockIdx.x;
+__global__ void __launch_bounds__(PREFIX_CHUNK)
+prefix_partial_kernel(NodeTab t, PrefixSel ps, PrefixScratch sc, uint32_t n_chunks) {
   uint64_t sel, tol;
   float pct;
-  if (mode == 0) {
-    if (!st->case_a || st->max_group < 0) return;
-    sel = rsel[c0 + blockIdx.x]; tol = rtol[c0 + blockIdx.x]; pct = 1.0f;
-  } else if (mode == 1) {
-    if (st->case_a || st->max_group < 0) return;
-    sel = rsel[st->max_class]; tol = rtol[st->max_class]; pct = 0.7f;
-  } else {
-    sel = xsel; tol = xtol; pct = xpct;
-  }
-  const uint32_t N = t.N, L = t.L;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t per = (N + PREFIX_THREADS - 1) / PREFIX_THREADS;
-  const uint32_t n0 = min(tid * per, N), n1 = min(n0 + per, N);
-  __shared__ int64_t s_warp[32][MAXL];
-  __shared__ uint32_t s_wpres[32];
-  __shared__ int s_last[32];
-
-  // pass A: per-thread totals
-  int64_t tot[MAXL];
+  const uint32_t slot = blockIdx.y, chunk = blockIdx.x;
+  if (!prefix_select(ps, slot, sel, tol, pct)) return;
+  __shared__ int64_t s_tot[PREFIX_CHUNK / 32][MAXL];
+  __shared__ uint32_t s_pres[PREFIX_CHUNK / 32];
+  const uint32_t i = chunk * PREFIX_CHUNK + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t v[MAXL];
 #pragma unroll
-  for (int d = 0; d < MAXL; ++d) tot[d] = 0;
-  uint32_t tpres = 0;
-  for (uint32_t i = n0; i < n1; ++i) {
-    if (node_skipped(t.flags[i])) continue;
-    tpres |= single_node_resource<MAXL>(t, i, sel, tol, pct, v);
+  for (int d = 0; d < MAXL; ++d) v[d] = 0;
+  uint32_t pres = 0;
+  if (i < t.N && !node_skipped(t.flags[i])) pres = single_node_resource<MAXL>(t, i, sel, tol, pct, v);
+  for (int o = 16; o; o >>= 1) {
 #pragma unroll
-    for (int d = 0; d < MAXL; ++d) tot[d] += v[d];
+    for (int d = 0; d < MAXL; ++d) v[d] += __shfl_xor_sync(0xffffffffu, v[d], o);
+    pres |= __shfl_xor_sync(0xffffffffu, pres, o);
   }
-  // block exclusive scan of (tot, tpres): warp inclusive scan, then warp offsets
-  int64_t inc[MAXL];
+  if (lane == 0) {
 #pragma unroll
-  for (int d = 0; d < MAXL; ++d) inc[d] = tot[d];
-  uint32_t ipres = tpres;
+    for (int d = 0; d < MAXL; ++d) s_tot[wid][d] = v[d];
+    s_pres[wid] = pres;
+  }
+  __syncthreads();
+  if (threadIdx.x < MAXL) {
+    int64_t tsum = 0;
+    for (int w = 0; w < PREFIX_CHUNK / 32; ++w) tsum += s_tot[w][threadIdx.x];
+    sc.part[((size_t)slot * n_chunks + chunk) * MAXL + threadIdx.x] = tsum;
+  }
+  if (threadIdx.x == 0) {
+    uint32_t p = 0;
+    for (int w = 0; w < PREFIX_CHUNK / 32; ++w) p |= s_pres[w];
+    sc.part_pres[(size_t)slot * n_chunks + chunk] = p;
+  }
+}
+
+template <int MAXL>
+__global__ void __launch_bounds__(PREFIX_CHUNK)
+prefix_scan_kernel(NodeTab t, PrefixSel ps, PrefixScratch sc, uint32_t n_chunks, PrefixOut out) {
+  uint64_t sel, tol;
+  float pct;
+  const uint32_t slot = blockIdx.y, chunk = blockIdx.x;
+  if (!prefix_select(ps, slot, sel, tol, pct)) return;
+  const uint32_t N = t.N, L = t.L;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = PREFIX_CHUNK / 32;
+  __shared__ int64_t s_w[NW][MAXL];
+  __shared__ uint32_t s_wp[NW];
+  __shared__ int64_t s_off[MAXL];
+  __shared__ uint32_t s_offp;
+  __shared__ int s_amx[NW][MAXL];
+  __shared__ int s_last[NW];
+  __shared__ uint32_t s_abs[NW];
+  __shared__ bool s_is_last;
+
+  // offset of this chunk: totals of every preceding chunk (strided over the CTA, block-reduced)
+  int64_t off[MAXL];
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) off[d] = 0;
+  uint32_t offp = 0;
+  for (uint32_t c = tid; c < chunk; c += PREFIX_CHUNK) {
+    const int64_t* pp = sc.part + ((size_t)slot * n_chunks + c) * MAXL;
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) off[d] += pp[d];
+    offp |= sc.part_pres[(size_t)slot * n_chunks + c];
+  }
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) off[d] += __shfl_xor_sync(0xffffffffu, off[d], o);
+    offp |= __shfl_xor_sync(0xffffffffu, offp, o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) s_w[wid][d] = off[d];
+    s_wp[wid] = offp;
+  }
+  __syncthreads();
+  if (tid < MAXL) {
+    int64_t a = 0;
+    for (int w = 0; w < NW; ++w) a += s_w[w][tid];
+    s_off[tid] = a;
+  }
+  if (tid == 0) {
+    uint32_t p = 0;
+    for (int w = 0; w < NW; ++w) p |= s_wp[w];
+    s_offp = p;
+  }
+  __syncthreads();
+
+  // in-chunk inclusive scan
+  const uint32_t i = chunk * PREFIX_CHUNK + tid;
+  const bool inb = i < N;
+  const bool vis = inb && !node_skipped(t.flags[i]);
+  int64_t v[MAXL];
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) v[d] = 0;
+  uint32_t pres = 0;
+  if (vis) pres = single_node_resource<MAXL>(t, i, sel, tol, pct, v);
   for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
     for (int d = 0; d < MAXL; ++d) {
-      const int64_t w = __shfl_up_sync(0xffffffffu, inc[d], o);
-      if ((int)lane >= o) inc[d] += w;
+      const int64_t w = __shfl_up_sync(0xffffffffu, v[d], o);
+      if ((int)lane >= o) v[d] += w;
     }
-    const uint32_t wp = __shfl_up_sync(0xffffffffu, ipres, o);
-    if ((int)lane >= o) ipres |= wp;
+    const uint32_t wp = __shfl_up_sync(0xffffffffu, pres, o);
+    if ((int)lane >= o) pres |= wp;
   }
+  __syncthreads();  // s_w reuse
   if (lane == 31) {
 #pragma unroll
-    for (int d = 0; d < MAXL; ++d) s_warp[wid][d] = inc[d];
-    s_wpres[wid] = ipres;
+    for (int d = 0; d < MAXL; ++d) s_w[wid][d] = v[d];
+    s_wp[wid] = pres;
   }
   __syncthreads();
-  int64_t run[MAXL];
-  uint32_t rpres = 0;
 #pragma unroll
-  for (int d = 0; d < MAXL; ++d) run[d] = inc[d] - tot[d];  // exclusive within the warp
-  {
-    uint32_t ex = __shfl_up_sync(0xffffffffu, ipres, 1);
-    rpres = lane ? ex : 0u;
-  }
+  for (int d = 0; d < MAXL; ++d) v[d] += s_off[d];
+  pres |= s_offp;
   for (uint32_t w = 0; w < wid; ++w) {
 #pragma unroll
-    for (int d = 0; d < MAXL; ++d) run[d] += s_warp[w][d];
-    rpres |= s_wpres[w];
+    for (int d = 0; d < MAXL; ++d) v[d] += s_w[w][d];
+    pres |= s_wp[w];
   }
-  // pass B: write prefixes, gather stats
-  int64_t* pre = out.pre + (size_t)c_out * L * N;
-  uint32_t* pp = out.present + (size_t)c_out * N;
+  if (inb) {
+    int64_t* pre = out.pre + (size_t)slot * L * N;
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d)
+      if (d < (int)L) pre[(size_t)d * N + i] = v[d];
+    out.present[(size_t)slot * N + i] = pres;
+  }
+  // chunk statistics over visited prefixes
   int64_t mx[MAXL];
   int amx[MAXL];
 #pragma unroll
-  for (int d = 0; d < MAXL; ++d) { mx[d] = INT64_MIN; amx[d] = -1; }
-  uint32_t absent = 0;
-  int last = -1;
-  for (uint32_t i = n0; i < n1; ++i) {
-    const bool vis = !node_skipped(t.flags[i]);
-    if (vis) {
-      rpres |= single_node_resource<MAXL>(t, i, sel, tol, pct, v);
-#pragma unroll
-      for (int d = 0; d < MAXL; ++d) run[d] += v[d];
-      last = (int)i;
-      absent |= ~rpres;
-#pragma unroll
-      for (int d = 0; d < MAXL; ++d) {
-        const bool pres = d < 4 || ((rpres >> d) & 1u);
-        if (pres && (amx[d] < 0 || run[d] > mx[d])) { mx[d] = run[d]; amx[d] = (int)i; }
-      }
-    }
-#pragma unroll
-    for (int d = 0; d < MAXL; ++d)
-      if (d < (int)L) pre[(size_t)d * N + i] = run[d];
-    pp[i] = rpres;
+  for (int d = 0; d < MAXL; ++d) {
+    const bool has = vis && (d < 4 || ((pres >> d) & 1u));
+    mx[d] = has ? v[d] : INT64_MIN;
+    amx[d] = has ? (int)i : -1;
   }
-  // block reduce stats
+  uint32_t absent = vis ? ~pres : 0u;
+  int last = vis ? (int)i : -1;
   for (int o = 16; o; o >>= 1) {
 #pragma unroll
     for (int d = 0; d < MAXL; ++d) {
       const int64_t om = __shfl_xor_sync(0xffffffffu, mx[d], o);
       const int oa = __shfl_xor_sync(0xffffffffu, amx[d], o);
-      if (oa >= 0 && (amx[d] < 0 || om > mx[d])) { mx[d] = om; amx[d] = oa; }
+      if (oa >= 0 && (amx[d] < 0 || om > mx[d] || (om == mx[d] && oa < amx[d]))) { mx[d] = om; amx[d] = oa; }
     }
     absent |= __shfl_xor_sync(0xffffffffu, absent, o);
     last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
   }
-  __syncthreads();  // s_warp reuse
-  __shared__ int s_amx[32][MAXL];
+  __syncthreads();  // s_w reuse
   if (lane == 0) {
 #pragma unroll
-    for (int d = 0; d < MAXL; ++d) { s_warp[wid][d] = mx[d]; s_amx[wid][d] = amx[d]; }
-    s_wpres[wid] = absent;
+    for (int d = 0; d < MAXL; ++d) { s_w[wid][d] = mx[d]; s_amx[wid][d] = amx[d]; }
+    s_abs[wid] = absent;
     s_last[wid] = last;
   }
   __syncthreads();
@@ -532,15 +650,48 @@ class_prefix_kernel(NodeTab t, const uint64_t* __restrict__ rsel, const uint64_t
     for (int d = 0; d < BS_MAX_LANES; ++d) { cs.maxv[d] = INT64_MIN; cs.argmax[d] = -1; }
     cs.any_absent = 0;
     cs.last_visited = -1;
-    for (int w = 0; w < PREFIX_THREADS / 32; ++w) {
+    for (int w = 0; w < NW; ++w) {
       for (int d = 0; d < MAXL; ++d)
-        if (s_amx[w][d] >= 0 && (cs.argmax[d] < 0 || s_warp[w][d] > cs.maxv[d])) {
-          cs.maxv[d] = s_warp[w][d]; cs.argmax[d] = s_amx[w][d];
+        if (s_amx[w][d] >= 0 && (cs.argmax[d] < 0 || s_w[w][d] > cs.maxv[d])) {
+          cs.maxv[d] = s_w[w][d]; cs.argmax[d] = s_amx[w][d];
         }
-      cs.any_absent |= s_wpres[w];
+      cs.any_absent |= s_abs[w];
       cs.last_visited = max(cs.last_visited, s_last[w]);
     }
-    out.stats[c_out] = cs;
+    sc.cstats[(size_t)slot * n_chunks + chunk] = cs;
+    __threadfence();
+    const uint32_t ticket = atomicAdd(&sc.done[slot], 1u);
+    s_is_last = (ticket == n_chunks - 1);
+  }
+  __syncthreads();
+  if (s_is_last) {
+    // last chunk of this class: fold the chunk statistics (lane d of warp 0 owns lane d)
+    __threadfence();
+    if (tid < MAXL) {
+      int64_t bm = INT64_MIN;
+      int ba = -1;
+      for (uint32_t c = 0; c < n_chunks; ++c) {
+        const ClassStats& cs = sc.cstats[(size_t)slot * n_chunks + c];
+        if (cs.argmax[tid] >= 0 && (ba < 0 || cs.maxv[tid] > bm)) { bm = cs.maxv[tid]; ba = cs.argmax[tid]; }
+      }
+      out.stats[slot].maxv[tid] = bm;
+      out.stats[slot].argmax[tid] = ba;
+    } else if (tid >= 32 && tid < 32 + BS_MAX_LANES - MAXL) {
+      out.stats[slot].maxv[MAXL + tid - 32] = INT64_MIN;
+      out.stats[slot].argmax[MAXL + tid - 32] = -1;
+    }
+    if (tid == 64) {
+      uint32_t ab = 0;
+      int lv = -1;
+      for (uint32_t c = 0; c < n_chunks; ++c) {
+        const ClassStats& cs = sc.cstats[(size_t)slot * n_chunks + c];
+        ab |= cs.any_absent;
+        lv = max(lv, cs.last_visited);
+      }
+      out.stats[slot].any_absent = ab;
+      out.stats[slot].last_visited = lv;
+      sc.done[slot] = 0;  // ready for the next launch
+    }
   }
 }
 
@@ -610,42 +761,104 @@ __global__ void group_check_kernel(NodeTab t, GroupTab g, GroupEff e, PrefixOut 
   if ((threadIdx.x & 31) == 0) okA[gi] = ok ? 1 : 2;
 }
 
-// K5b prefilter_kernel — ScheduleOperation.PreFilter per pod (core.go:88-167)
-// against the frozen round state.  One warp per pod (the case-B cluster check
-// is a warp-wide prefix search).
-__global__ void prefilter_kernel(NodeTab t, PodTab p, GroupTab g, GroupEff e, PrefixOut po,
-                                 const RoundState* __restrict__ st, const uint8_t* __restrict__ okA,
-                                 uint8_t* __restrict__ prefilter, uint8_t* __restrict__ new_denied) {
-  const uint32_t pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (pi >= p.P) return;
-  const uint32_t lane = threadIdx.x & 31;
-  const int32_t gi = p.gid[pi];
-  const uint8_t pf = p.flags[pi];
-  uint8_t code = BS_PF_PASS;
-  bool deny = false;
-  if (gi == BS_GID_NONE) code = BS_PF_PASS;                                   // :89-92
-  else if (pf & BS_POD_PERMITTED_RECENTLY) code = BS_PF_PASS;                 // :95-98
-  else if (gi < 0 || (uint32_t)gi >= g.G) code = BS_PF_ERR_NOT_FOUND;         // :100-103
-  else if (g.flags[gi] & BS_GROUP_DENIED) code = BS_PF_ERR_DENIED;            // :105-110
-  else if (pf & BS_POD_OCC_NOREFS) code = BS_PF_ERR_OCCUPIED_NOREFS;          // :504-506
-  else if (pf & BS_POD_OCC_MISMATCH) code = BS_PF_ERR_OCCUPIED;               // :507-510
-  else if (st->max_group < 0) code = BS_PF_PASS;                              // :127-130
-  else if (st->case_a) {                                                      // :136-147
-    if (okA[gi] == 2) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
-  } else if (st->max_group == gi) code = BS_PF_PASS;                          // :150-155
-  else {                                                                      // :157-165
-    int64_t need[BS_MAX_LANES];
-    uint32_t npres = st->base_present;
-    const uint32_t rp = p.req_present[pi] & ~0xFu;
-    for (uint32_t d = 0; d < BS_MAX_LANES; ++d) need[d] = st->base_need[d];
-    for (uint32_t d = 0; d < p.L; ++d)                                        // :159 Add(pod require)
-      if (d < 4 || ((rp >> d) & 1u)) need[d] += p.req[(size_t)d * p.P + pi];
-    npres |= rp;
-    if (!warp_cluster_check(t, po, 0, need, npres)) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
+// K5b prefilter_kernel — ScheduleOperation.PreFilter per pod (core.go:88-167) against the
+// frozen round state.  Thread per pod.  Case B (core.go:157-165) needs a cluster check per pod
+// against the ONE prefix array of the max group's class: the class statistics and the L+1
+// candidate prefixes are staged in shared memory once per CTA, so almost every pod is decided
+// by <= (L+1)*L compares; a pod the bounds and candidates leave undecided is handed to its warp
+// for a cooperative scan over every visited prefix (exactness is never traded).
+constexpr int PREFILTER_THREADS = 256;
+__global__ void __launch_bounds__(PREFILTER_THREADS)
+prefilter_kernel(NodeTab t, PodTab p, GroupTab g, GroupEff e, PrefixOut po,
+                 const RoundState* __restrict__ st, const uint8_t* __restrict__ okA,
+                 uint8_t* __restrict__ prefilter, uint8_t* __restrict__ new_denied) {
+  __shared__ ClassStats s_cs;
+  __shared__ int64_t s_cand[BS_MAX_LANES + 1][BS_MAX_LANES];
+  __shared__ uint32_t s_cand_pres[BS_MAX_LANES + 1];
+  __shared__ int s_cand_idx[BS_MAX_LANES + 1];
+  const int L = (int)t.L;
+  const uint32_t N = t.N;
+  const bool case_b = st->max_group >= 0 && !st->case_a;
+  if (case_b) {
+    if (threadIdx.x == 0) s_cs = po.stats[0];
+    __syncthreads();
+    if (threadIdx.x <= (uint32_t)L) {
+      const int idx = threadIdx.x == 0 ? s_cs.last_visited : s_cs.argmax[threadIdx.x - 1];
+      s_cand_idx[threadIdx.x] = idx;
+      if (idx >= 0) {
+        for (int d = 0; d < L; ++d) s_cand[threadIdx.x][d] = po.pre[(size_t)d * N + idx];
+        s_cand_pres[threadIdx.x] = po.present[idx];
+      }
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
+  const uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const bool valid = pi < p.P;
+  int32_t gi = BS_GID_NONE;
+  uint8_t code = BS_PF_PASS;
+  bool deny = false, undecided = false;
+  int64_t need[BS_MAX_LANES];
+  uint32_t npres = 0;
+  if (valid) {
+    gi = p.gid[pi];
+    const uint8_t pf = p.flags[pi];
+    if (gi == BS_GID_NONE) code = BS_PF_PASS;                                   // :89-92
+    else if (pf & BS_POD_PERMITTED_RECENTLY) code = BS_PF_PASS;                 // :95-98
+    else if (gi < 0 || (uint32_t)gi >= g.G) code = BS_PF_ERR_NOT_FOUND;         // :100-103
+    else if (g.flags[gi] & BS_GROUP_DENIED) code = BS_PF_ERR_DENIED;            // :105-110
+    else if (pf & BS_POD_OCC_NOREFS) code = BS_PF_ERR_OCCUPIED_NOREFS;          // :504-506
+    else if (pf & BS_POD_OCC_MISMATCH) code = BS_PF_ERR_OCCUPIED;               // :507-510
+    else if (st->max_group < 0) code = BS_PF_PASS;                              // :127-130
+    else if (st->case_a) {                                                      // :136-147
+      if (okA[gi] == 2) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
+    } else if (st->max_group == gi) code = BS_PF_PASS;                          // :150-155
+    else {                                                                      // :157-165
+      npres = st->base_present;
+      const uint32_t rp = p.req_present[pi] & ~0xFu;
+      for (int d = 0; d < L; ++d) {                                             // :159 Add(pod require)
+        need[d] = st->base_need[d];
+        if (d < 4 || ((rp >> d) & 1u)) need[d] += p.req[(size_t)d * p.P + pi];
+      }
+      npres |= rp;
+      // 1. bounds  2. candidates (see warp_cluster_check)  3. cooperative scan if undecided
+      bool reject = s_cs.last_visited < 0;
+      for (int d = 0; d < L && !reject; ++d) {
+        const bool checked = d < 4 || ((npres >> d) & 1u);
+        if (!checked) continue;
+        const bool via_present = s_cs.argmax[d] >= 0 && need[d] <= s_cs.maxv[d];
+        const bool via_absent = d >= 4 && ((s_cs.any_absent >> d) & 1u) && need[d] == 0;
+        if (!via_present && !via_absent) reject = true;
+      }
+      if (reject) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
+      else {
+        bool hit = false;
+        for (int c = 0; c <= L && !hit; ++c)
+          if (s_cand_idx[c] >= 0) hit = compare_res(s_cand[c], s_cand_pres[c], need, npres, L);
+        undecided = !hit;
+      }
+    }
+  }
+  // cooperative fallback: one undecided pod at a time, the whole warp scans the prefixes
+  uint32_t pending = __ballot_sync(0xffffffffu, undecided);
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    int64_t nd[BS_MAX_LANES];
+    for (int d = 0; d < L; ++d) nd[d] = __shfl_sync(0xffffffffu, need[d], src);
+    const uint32_t np = __shfl_sync(0xffffffffu, npres, src);
+    bool found = false;
+    for (uint32_t base = 0; base < N && !found; base += 32) {
+      const uint32_t i = base + lane;
+      bool ok = false;
+      if (i < N && !node_skipped(t.flags[i])) ok = prefix_satisfies_at(po.pre, po.present, N, L, i, nd, np);
+      found = __any_sync(0xffffffffu, ok);
+    }
+    if ((int)lane == src && !found) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
+  }
+  if (valid) {
     prefilter[pi] = code;
-    if (deny) new_denied[gi] = 1;                                             // :142,:163
+    if (deny) new_denied[gi] = 1;                                               // :142,:163
   }
 }
 
@@ -723,13 +936,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 struct FitArgs {
-  const int64_t* left_eff;   // [L][Npad]
+  const int64_t* left_w;     // [LW][Npad] wide lanes
+  const int32_t* left_n;     // [LN][Npad] narrow lanes
   const uint32_t* classfit;  // [classes][n_tiles][32] transposed class bits
   const int64_t* req;        // [L][P]
   const uint32_t* req_present;
   const uint32_t* fit_class;
   const int32_t* gid;
   const uint8_t* prefilter;
+  LaneMap lm;
   // group side
   const uint32_t* min_member;
   const uint32_t* scheduled;
@@ -745,18 +960,25 @@ struct FitArgs {
   int64_t* best_score;
   uint32_t* fit_bitmap;   // [Ppad][W] or null   (Ppad = P rounded up to PODS_PER_CTA: no pod guard)
   int64_t* score;         // [Ppad][N] or null
+  // Row pitches in BYTES as 64-bit kernel parameters: ptxas 12.9 miscompiles the uniform-datapath
+  // form of `int32 base + (uint32 Npad << 2)` (a lone ULEA with the high word zeroed) when the
+  // TMA source address of a narrow row is derived from a 32-bit Npad; 64-bit pitches avoid it.
+  uint64_t left_w_pitch, left_n_pitch;
   uint32_t P, N, Npad, W, G;
 };
 
 // One node tile for the PODS_PER_WARP pods of a warp.  TAIL: the tile holds padding
 // nodes (>= N): score stores are guarded; full tiles carry no per-pair guard at all.
-// Ballot words go to a per-warp shared-memory slab (one STS per pair, every lane writes the
-// same word: no predicate, no ALU); after the tile lane j < TILE_WORDS pops word j back for
-// the fit-bitmap store (64 B per pod, coalesced) and the feasible count (popcount, reduced
-// across the warp once at the very end).
-template <int L, bool TAIL>
-__device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __restrict__ tl,
-                                         const int64_t (&rq)[PODS_PER_WARP][L],
+// Wide lanes: 64-bit subtract + compare/select min.  Narrow lanes: one 32-bit VIADDMNMX
+// (fused subtract+min) each.  Ballot words go to a per-warp shared-memory slab (one STS per
+// pair, every lane writes the same word: no predicate, no ALU); after the tile lane
+// j < TILE_WORDS pops word j back for the fit-bitmap store (64 B per pod, coalesced) and the
+// feasible count (popcount, reduced across the warp once at the very end).
+template <int LW, int LN, bool TAIL>
+__device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __restrict__ tlw,
+                                         const int32_t* __restrict__ tln,
+                                         const int64_t (&rqw)[PODS_PER_WARP][LW > 0 ? LW : 1],
+                                         const int32_t (&rqn)[PODS_PER_WARP][LN > 0 ? LN : 1],
                                          const uint32_t (&colbits)[PODS_PER_WARP], int64_t* sp0,
                                          size_t row_stride, uint32_t* s_words, uint32_t node_base,
                                          uint32_t lane, bool want_score,
@@ -764,22 +986,36 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
   int64_t* sp[PODS_PER_WARP];
 #pragma unroll
   for (int r = 0; r < PODS_PER_WARP; ++r) sp[r] = sp0 + r * row_stride;
-  const int64_t* tp = tl + lane;
+  const int64_t* tpw = tlw + lane;
+  const int32_t* tpn = tln + lane;
   int32_t node = (int32_t)(node_base + lane);
   uint32_t* wp = s_words;
 #pragma unroll 1
   for (int jb = 0; jb < TILE_WORDS; jb += 4) {
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      int64_t lf[L];
+      int64_t lfw[LW > 0 ? LW : 1];
+      int32_t lfn[LN > 0 ? LN : 1];
 #pragma unroll
-      for (int d = 0; d < L; ++d) lf[d] = tp[d * NODE_TILE + jj * 32];
+      for (int d = 0; d < LW; ++d) lfw[d] = tpw[d * NODE_TILE + jj * 32];
+#pragma unroll
+      for (int d = 0; d < LN; ++d) lfn[d] = tpn[d * NODE_TILE + jj * 32];
       const bool in_range = !TAIL || ((uint32_t)node + jj * 32 < a.N);
 #pragma unroll
       for (int r = 0; r < PODS_PER_WARP; ++r) {
-        int64_t m = lf[0] - rq[r][0];
+        int64_t m;
+        if (LN > 0) {
+          int32_t t = lfn[0] - rqn[r][0];
 #pragma unroll
-        for (int d = 1; d < L; ++d) m = min64(m, lf[d] - rq[r][d]);
+          for (int d = 1; d < LN; ++d) t = min(t, lfn[d] - rqn[r][d]);
+          m = (int64_t)t;
+#pragma unroll
+          for (int d = 0; d < LW; ++d) m = min64(m, lfw[d] - rqw[r][d]);
+        } else {
+          m = lfw[0] - rqw[r][0];
+#pragma unroll
+          for (int d = 1; d < LW; ++d) m = min64(m, lfw[d] - rqw[r][d]);
+        }
         const bool fit = (m >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
         wp[r * TILE_WORDS + jj] = __ballot_sync(0xffffffffu, fit);
         if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
@@ -787,7 +1023,8 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
           __stcs(reinterpret_cast<long long*>(sp[r] + jj * 32), fit ? (long long)m : (long long)INT64_MIN);
       }
     }
-    tp += 128;
+    tpw += 128;
+    tpn += 128;
     node += 128;
     wp += 4;
 #pragma unroll
@@ -795,13 +1032,23 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
   }
 }
 
-template <int L>
-__global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ? 2 : 1))) gang_fit_kernel(FitArgs a) {
+__host__ __device__ constexpr size_t fit_tile_bytes(int LW, int LN) {
+  return (size_t)NODE_TILE * (8 * LW + 4 * LN);
+}
+__host__ __device__ constexpr int fit_min_blocks(int LW, int LN) {
+  return (2 * LW + LN) <= 10 ? BS_FIT_MINB : ((2 * LW + LN) <= 18 ? 2 : 1);
+}
+
+template <int LW, int LN>
+__global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_kernel(FitArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [2 stages][L][NODE_TILE] int64 | [PODS_PER_CTA][L] int64 | mbarriers | ballot words
-  int64_t* s_tile = reinterpret_cast<int64_t*>(smem_raw);
-  int64_t* s_req = s_tile + 2 * L * NODE_TILE;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_req + PODS_PER_CTA * L);
+  // layout: [2 stages]{[LW][NODE_TILE] i64, [LN][NODE_TILE] i32} | req_w | req_n | mbarriers | ballot words
+  constexpr size_t STAGE_BYTES = fit_tile_bytes(LW, LN);
+  unsigned char* s_tile = smem_raw;
+  int64_t* s_req_w = reinterpret_cast<int64_t*>(smem_raw + 2 * STAGE_BYTES);
+  int32_t* s_req_n = reinterpret_cast<int32_t*>(s_req_w + PODS_PER_CTA * LW);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(s_req_n + PODS_PER_CTA * LN) + 7) & ~(uintptr_t)7);
   uint32_t* s_words_all = reinterpret_cast<uint32_t*>(s_bar + 2);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -809,7 +1056,6 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ?
   const uint32_t pod0 = blockIdx.x * PODS_PER_CTA;
   const uint32_t wpod0 = pod0 + wid * PODS_PER_WARP;  // first pod of this warp
   const uint32_t n_tiles = a.Npad / NODE_TILE;
-  constexpr uint32_t ROW_BYTES = NODE_TILE * sizeof(int64_t);
 
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
@@ -817,23 +1063,34 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ?
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // stage the CTA's pod requests (sentinel for lanes without a map key)
-  for (uint32_t i = tid; i < PODS_PER_CTA * L; i += FIT_THREADS) {
-    const uint32_t pl = i / L, d = i % L;
+  for (uint32_t i = tid; i < PODS_PER_CTA * (LW + LN); i += FIT_THREADS) {
+    const uint32_t pl = i / (LW + LN), k = i % (LW + LN);
     const uint32_t p = pod0 + pl;
+    const bool is_w = k < (uint32_t)LW;
+    const uint32_t d = is_w ? a.lm.wide[k] : a.lm.narrow[k - LW];
     int64_t v = 0;
+    bool present = true;
     if (p < a.P) {
-      const bool present = d < 4 || ((a.req_present[p] >> d) & 1u);
-      v = present ? a.req[(size_t)d * a.P + p] : UNCHECKED_REQ;
+      present = d < 4 || ((a.req_present[p] >> d) & 1u);
+      v = present ? a.req[(size_t)d * a.P + p] : 0;
     }
-    s_req[pl * L + d] = v;
+    if (is_w) s_req_w[pl * LW + k] = present ? v : UNCHECKED_REQ;
+    else s_req_n[pl * LN + (k - LW)] = present ? (int32_t)v : UNCHECKED_REQ32;
   }
   __syncthreads();
   auto issue = [&](uint32_t tile, uint32_t stage) {
-    mbar_expect_tx(&s_bar[stage], L * ROW_BYTES);
+    mbar_expect_tx(&s_bar[stage], (uint32_t)STAGE_BYTES);
+    unsigned char* dst = s_tile + stage * STAGE_BYTES;
+    const unsigned char* src_w = reinterpret_cast<const unsigned char*>(a.left_w) + (uint64_t)tile * (NODE_TILE * 8);
+    const unsigned char* src_n = reinterpret_cast<const unsigned char*>(a.left_n) + (uint64_t)tile * (NODE_TILE * 4);
 #pragma unroll
-    for (int d = 0; d < L; ++d)
-      tma_bulk_g2s(s_tile + (stage * L + d) * NODE_TILE,
-                   a.left_eff + (size_t)d * a.Npad + (size_t)tile * NODE_TILE, ROW_BYTES, &s_bar[stage]);
+    for (int d = 0; d < LW; ++d)
+      tma_bulk_g2s(dst + (size_t)d * NODE_TILE * 8, src_w + (uint64_t)d * a.left_w_pitch, NODE_TILE * 8,
+                   &s_bar[stage]);
+#pragma unroll
+    for (int d = 0; d < LN; ++d)
+      tma_bulk_g2s(dst + (size_t)LW * NODE_TILE * 8 + (size_t)d * NODE_TILE * 4,
+                   src_n + (uint64_t)d * a.left_n_pitch, NODE_TILE * 4, &s_bar[stage]);
   };
   if (tid == 0) {
     issue(0, 0);
@@ -847,7 +1104,8 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ?
   uint32_t cnt[PODS_PER_WARP];
   int64_t best_s[PODS_PER_WARP];
   int32_t best_n[PODS_PER_WARP];
-  int64_t rq[PODS_PER_WARP][L];
+  int64_t rqw[PODS_PER_WARP][LW > 0 ? LW : 1];
+  int32_t rqn[PODS_PER_WARP][LN > 0 ? LN : 1];
   uint32_t coff[PODS_PER_WARP];
 #pragma unroll
   for (int r = 0; r < PODS_PER_WARP; ++r) {
@@ -855,7 +1113,9 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ?
     const uint32_t p = wpod0 + r;
     coff[r] = (p < a.P ? a.fit_class[p] : 0u) * n_tiles * 32 + lane;
 #pragma unroll
-    for (int d = 0; d < L; ++d) rq[r][d] = s_req[(wid * PODS_PER_WARP + r) * L + d];
+    for (int d = 0; d < LW; ++d) rqw[r][d] = s_req_w[(wid * PODS_PER_WARP + r) * LW + d];
+#pragma unroll
+    for (int d = 0; d < LN; ++d) rqn[r][d] = s_req_n[(wid * PODS_PER_WARP + r) * LN + d];
   }
 
   for (uint32_t tile = 0; tile < n_tiles; ++tile) {
@@ -864,13 +1124,14 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ?
 #pragma unroll
     for (int r = 0; r < PODS_PER_WARP; ++r) colbits[r] = __ldg(a.classfit + coff[r] + tile * 32);
     mbar_wait(&s_bar[stage], (tile >> 1) & 1);
-    const int64_t* tl = s_tile + stage * L * NODE_TILE;
+    const int64_t* tlw = reinterpret_cast<const int64_t*>(s_tile + stage * STAGE_BYTES);
+    const int32_t* tln = reinterpret_cast<const int32_t*>(s_tile + stage * STAGE_BYTES + (size_t)LW * NODE_TILE * 8);
     const uint32_t node_base = tile * NODE_TILE;
     int64_t* sp0 = want_score ? a.score + (size_t)wpod0 * a.N + node_base + lane : nullptr;
     if (node_base + NODE_TILE <= a.N)
-      fit_tile<L, false>(a, tl, rq, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
+      fit_tile<LW, LN, false>(a, tlw, tln, rqw, rqn, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
     else
-      fit_tile<L, true>(a, tl, rq, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
+      fit_tile<LW, LN, true>(a, tlw, tln, rqw, rqn, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
     __syncwarp();
     if (lane < TILE_WORDS) {
       const uint32_t word = (node_base >> 5) + lane;
@@ -949,9 +1210,10 @@ __global__ void __launch_bounds__(FIT_THREADS, (L <= 6 ? BS_FIT_MINB : (L <= 9 ?
   }
 }
 
-inline size_t gang_fit_smem_bytes(int L) {
-  return (size_t)(2 * L * NODE_TILE + PODS_PER_CTA * L) * sizeof(int64_t) + 2 * sizeof(uint64_t) +
-         (size_t)PODS_PER_CTA * TILE_WORDS * sizeof(uint32_t);
+inline size_t gang_fit_smem_bytes(int LW, int LN) {
+  size_t b = 2 * fit_tile_bytes(LW, LN) + (size_t)PODS_PER_CTA * (8 * LW + 4 * LN);
+  b = (b + 7) & ~(size_t)7;
+  return b + 2 * sizeof(uint64_t) + (size_t)PODS_PER_CTA * TILE_WORDS * sizeof(uint32_t);
 }
 
 }  // namespace bsk

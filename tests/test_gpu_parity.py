@@ -194,3 +194,48 @@ def test_reupload_and_reevaluate(pkg, oracle, snapshot_mod):
             orc = oracle.round(snap, want_bitmap=True, want_score=True)
             assert_round_equal(res, eng.fit_rows(), eng.score_rows(), orc)
     eng.close()
+
+
+@pytest.mark.parametrize("variant", ["all_narrow", "boundary", "cpu_wide", "many_scalars", "all_wide", "sentinel_mix"])
+def test_lane_classification_variants(pkg, oracle, snapshot_mod, variant):
+    """The fit kernel evaluates lanes whose values fit in 28 bits with 32-bit arithmetic and the
+    rest in 64-bit; every wide/narrow split must give the same bits as the oracle."""
+    S = snapshot_mod
+    L = {"many_scalars": 13, "sentinel_mix": 9}.get(variant, 6)
+    snap = random_snapshot(900 + len(variant), P=257, N=700, G=20, L=L)
+    nt, pt = snap.nodes, snap.pods
+    rng = np.random.default_rng(len(variant))
+    N, P = nt.n, pt.n
+    if variant in ("all_narrow", "boundary", "many_scalars", "sentinel_mix"):
+        for d in range(L):
+            hi = (1 << 26) if variant == "boundary" else 100000
+            nt.alloc[d] = rng.integers(0, hi, N)
+            nt.requested[d] = rng.integers(0, hi, N)
+            pt.req[d] = rng.integers(0, 1 << 27 if variant == "boundary" else 50000, P)
+            snap.groups.min_res[d] = rng.integers(0, 1000, snap.groups.n)
+        if variant == "boundary":
+            nt.alloc[0, 0] = 1 << 26           # still narrow
+            nt.alloc[1, 0] = (1 << 26) + 1     # lane 1 becomes wide
+            pt.req[2, 0] = 1 << 27             # still narrow
+        nt.pod_count = rng.integers(0, 100, N).astype(np.int32)
+        nt.requested[3] = 0
+    if variant == "cpu_wide":
+        nt.alloc[0] = rng.integers(1 << 30, 1 << 40, N)
+        for d in (1, 2):
+            nt.alloc[d] = rng.integers(0, 1 << 20, N)
+            nt.requested[d] = rng.integers(0, 1 << 20, N)
+            pt.req[d] = rng.integers(0, 1 << 19, P)
+    if variant == "all_wide":
+        for d in range(L):
+            nt.alloc[d] = rng.integers(1 << 30, 1 << 45, N)
+            pt.req[d] = rng.integers(0, 1 << 44, P)
+    if variant == "sentinel_mix":
+        # scalar lanes with absent keys on both sides: exercises the 32-bit sentinels
+        nt.alloc_present = rng.integers(0, 1 << L, N).astype(np.uint32) & ~np.uint32(0xF)
+        nt.req_present = rng.integers(0, 1 << L, N).astype(np.uint32) & ~np.uint32(0xF)
+        pt.req_present = rng.integers(0, 1 << L, P).astype(np.uint32) & ~np.uint32(0xF)
+        pt.req[4:] = rng.integers(0, 3, (L - 4, P))
+        nt.flags[:] = 0
+        nt.label_mask[:] = 0xF
+        nt.taint_mask[:] = 0
+    run_and_compare(pkg, oracle, snap)
