@@ -129,7 +129,9 @@ struct bs_engine {
   DevBuf d_prefilter, d_feasible, d_best_node, d_best_score, d_admit, d_admit_bitmap, d_new_denied,
       d_fit_bitmap, d_score, d_order, d_rank;
   // sort scratch
-  DevBuf d_gk0, d_gk1, d_pk0, d_pk1, d_idx_a, d_idx_b, d_ghist, d_skip, d_group_rank, d_gorder;
+  DevBuf d_gk0, d_gk1, d_pk0, d_pk1, d_idx_a, d_idx_b, d_ghist, d_skip, d_group_rank, d_gorder, d_tilecnt,
+      d_sort_barrier;
+  uint32_t sort_max_grid = 1;
 
   // host copies for the per-call mirrors and class building
   std::vector<int32_t> h_gid, h_prio;
@@ -429,37 +431,14 @@ LaneMap classify_lanes(const bs_engine* e) {
   return lm;
 }
 
-// one LSD pass over `n` indices
-void radix_pass(bs_engine* e, StageTimer& tm, const uint32_t* in, uint32_t* out, const uint64_t* key,
-                int shift, uint32_t n, cudaStream_t st) {
-  const uint32_t nblk = cdiv(n, SORT_TILE);
-  radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(in, key, shift, n, nblk, e->d_ghist.as<uint32_t>());
-  radix_scan_kernel<<<1, 256, 0, st>>>(e->d_ghist.as<uint32_t>(), nblk, n, e->d_skip.as<uint32_t>());
-  radix_scatter_kernel<<<nblk, SORT_THREADS, 0, st>>>(in, out, key, shift, n, nblk,
-                                                      e->d_ghist.as<uint32_t>(), e->d_skip.as<uint32_t>());
-  tm.launched(3);
-}
-
-// sorts indices 0..n-1 by (k1, k0) ascending, stable.  vary0/vary1: bits that differ between
-// rows of k0/k1 (host-computed at upload); byte digits with no varying bit need no pass.
-// Ping-pongs between a and b; returns the buffer holding the final order.
-uint32_t* radix_sort(bs_engine* e, StageTimer& tm, uint32_t n, const uint64_t* k0, uint64_t vary0,
-                     const uint64_t* k1, uint64_t vary1, uint32_t* a, uint32_t* b, cudaStream_t st) {
-  iota_kernel<<<cdiv(std::max(n, 1u), 256), 256, 0, st>>>(a, n);
-  tm.launched();
-  uint32_t* cur = a;
-  uint32_t* nxt = b;
-  for (int sh = 0; sh < 64; sh += 8) {
-    if (!((vary0 >> sh) & 0xffull)) continue;
-    radix_pass(e, tm, cur, nxt, k0, sh, n, st);
-    std::swap(cur, nxt);
-  }
-  for (int sh = 0; sh < 64; sh += 8) {
-    if (!((vary1 >> sh) & 0xffull)) continue;
-    radix_pass(e, tm, cur, nxt, k1, sh, n, st);
-    std::swap(cur, nxt);
-  }
-  return cur;
+// radix passes for the byte digits of (k0, k1) that actually vary (LSD order: k0 low..high, k1 low..high)
+uint32_t build_passes(uint64_t vary0, uint64_t vary1, SortPass* out) {
+  uint32_t n = 0;
+  for (int sh = 0; sh < 64; sh += 8)
+    if ((vary0 >> sh) & 0xffull) out[n++] = SortPass{0, (uint8_t)sh};
+  for (int sh = 0; sh < 64; sh += 8)
+    if ((vary1 >> sh) & 0xffull) out[n++] = SortPass{1, (uint8_t)sh};
+  return n;
 }
 
 inline uint64_t low_bits_mask(uint32_t n) {  // mask covering every value in [0, n]
@@ -573,8 +552,9 @@ int ensure_round_buffers(bs_engine* e) {
   CK(e->d_pk1.ensure((size_t)P * 8));
   CK(e->d_idx_a.ensure((size_t)M * 4));
   CK(e->d_idx_b.ensure((size_t)M * 4));
-  CK(e->d_ghist.ensure((size_t)256 * cdiv(M, SORT_TILE) * 4));
-  CK(e->d_skip.ensure(4));
+  CK(e->d_ghist.ensure((size_t)3 * 256 * cdiv(M, SORT_TILE) * 4));
+  CK(e->d_tilecnt.ensure((size_t)cdiv(M, SORT_TILE) * 4));
+  CK(e->d_sort_barrier.ensure(sizeof(unsigned int)));
   CK(e->d_group_rank.ensure((size_t)G * 4));
   // pinned result cache
   CK(e->h_prefilter.ensure(P));
@@ -650,31 +630,39 @@ int evaluate_async_locked(bs_engine* e) {
   CK(cudaStreamWaitEvent(e->s2, e->ev_fork, 0));
   {
     StageTimer tm(e, BS_K_SORT, e->s2);
-    // groups: (creation asc, name desc) -> dense group rank
-    if (G) {
-      group_keys_kernel<<<cdiv(G, 256), 256, 0, e->s2>>>(e->d_creation.as<int64_t>(), e->d_name_rank.as<uint32_t>(),
-                                                         G, e->d_gk0.as<uint64_t>(), e->d_gk1.as<uint64_t>());
-      tm.launched();
-      uint32_t* gord = radix_sort(e, tm, G, e->d_gk0.as<uint64_t>(), e->vary_name, e->d_gk1.as<uint64_t>(),
-                                  e->vary_creation, e->d_idx_a.as<uint32_t>(), e->d_idx_b.as<uint32_t>(), e->s2);
-      dense_rank_kernel<<<1, 1024, 0, e->s2>>>(gord, e->d_gk0.as<uint64_t>(), e->d_gk1.as<uint64_t>(), G,
-                                               e->d_group_rank.as<uint32_t>());
-      tm.launched();
-    }
-    if (P) {
-      pod_keys_kernel<<<cdiv(P, 256), 256, 0, e->s2>>>(e->d_prio.as<int32_t>(), e->d_gid.as<int32_t>(),
-                                                       e->d_ts.as<int64_t>(), e->d_pflags.as<uint8_t>(),
-                                                       e->d_group_rank.as<uint32_t>(), P, G,
-                                                       e->d_pk0.as<uint64_t>(), e->d_pk1.as<uint64_t>());
-      tm.launched();
+    // one persistent kernel: group keys -> sort -> dense group rank -> pod keys -> sort -> order + rank
+    if (P || G) {
+      SortArgs sa{};
+      sa.creation = e->d_creation.as<int64_t>();
+      sa.name_rank = e->d_name_rank.as<uint32_t>();
+      sa.G = G;
+      sa.gk0 = e->d_gk0.as<uint64_t>();
+      sa.gk1 = e->d_gk1.as<uint64_t>();
+      sa.group_rank = e->d_group_rank.as<uint32_t>();
+      sa.prio = e->d_prio.as<int32_t>();
+      sa.gid = e->d_gid.as<int32_t>();
+      sa.ts = e->d_ts.as<int64_t>();
+      sa.pflags = e->d_pflags.as<uint8_t>();
+      sa.P = P;
+      sa.pk0 = e->d_pk0.as<uint64_t>();
+      sa.pk1 = e->d_pk1.as<uint64_t>();
+      sa.order = e->d_order.as<uint32_t>();
+      sa.rank = e->d_rank.as<uint32_t>();
+      sa.idx_a = e->d_idx_a.as<uint32_t>();
+      sa.idx_b = e->d_idx_b.as<uint32_t>();
+      sa.hist = e->d_ghist.as<uint32_t>();
+      sa.tilecnt = e->d_tilecnt.as<uint32_t>();
+      sa.barrier = e->d_sort_barrier.as<unsigned int>();
+      sa.ntiles_max = cdiv(std::max(std::max(P, G), 1u), SORT_TILE);
+      sa.n_gpass = build_passes(e->vary_name, e->vary_creation, sa.gpass);
       // word1 = [~biased prio : 32][grouped : 1][group rank or 0x7fffffff : 31]
       const uint64_t vary1 = (e->vary_prio << 32) | 0x80000000ull |
                              ((e->any_lister_miss || e->max_gid >= (int64_t)G) ? 0x7fffffffull : low_bits_mask(G));
-      uint32_t* pord = radix_sort(e, tm, P, e->d_pk0.as<uint64_t>(), e->vary_ts, e->d_pk1.as<uint64_t>(), vary1,
-                                  e->d_idx_a.as<uint32_t>(), e->d_idx_b.as<uint32_t>(), e->s2);
-      CK(cudaMemcpyAsync(e->d_order.p, pord, (size_t)P * 4, cudaMemcpyDeviceToDevice, e->s2));
-      dense_rank_kernel<<<1, 1024, 0, e->s2>>>(e->d_order.as<uint32_t>(), e->d_pk0.as<uint64_t>(),
-                                               e->d_pk1.as<uint64_t>(), P, e->d_rank.as<uint32_t>());
+      sa.n_ppass = build_passes(e->vary_ts, vary1, sa.ppass);
+      CK(cudaMemsetAsync(sa.barrier, 0, sizeof(unsigned int), e->s2));
+      const uint32_t grid = std::max(1u, std::min(sa.ntiles_max, e->sort_max_grid));
+      void* params[] = {&sa};
+      CK(cudaLaunchCooperativeKernel((const void*)queue_sort_kernel, dim3(grid), dim3(SORT_THREADS), params, 0, e->s2));
       tm.launched();
     }
   }
@@ -862,6 +850,13 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
             cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; ok && k < BS_K_COUNT; ++k)
     ok = cudaEventCreate(&e->ev_a[k]) == cudaSuccess && cudaEventCreate(&e->ev_b[k]) == cudaSuccess;
+  if (ok) {
+    int per_sm = 0, sms = 0;
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, queue_sort_kernel, SORT_THREADS, 0) == cudaSuccess &&
+         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess;
+    // the sort shares the GPU with the fit kernel on the other stream: one CTA per SM is plenty
+    e->sort_max_grid = (uint32_t)std::max(1, std::min(per_sm * sms, sms));
+  }
   if (!ok) {
     bs_destroy(e);
     return BS_E_CUDA;
@@ -887,7 +882,7 @@ void bs_destroy(bs_engine* e) {
                     &e->d_prefilter, &e->d_feasible, &e->d_best_node, &e->d_best_score, &e->d_admit,
                     &e->d_admit_bitmap, &e->d_new_denied, &e->d_fit_bitmap, &e->d_score, &e->d_order,
                     &e->d_rank, &e->d_gk0, &e->d_gk1, &e->d_pk0, &e->d_pk1, &e->d_idx_a, &e->d_idx_b,
-                    &e->d_ghist, &e->d_skip, &e->d_group_rank, &e->d_gorder};
+                    &e->d_ghist, &e->d_skip, &e->d_group_rank, &e->d_gorder, &e->d_tilecnt, &e->d_sort_barrier};
   for (DevBuf* b : bufs) b->release();
   PinBuf* pins[] = {&e->h_prefilter, &e->h_feasible, &e->h_best_node, &e->h_best_score, &e->h_admit,
                     &e->h_admit_bitmap, &e->h_new_denied, &e->h_order, &e->h_rank, &e->h_state};

@@ -1,11 +1,19 @@
-// sort.cuh — queue ordering (ScheduleOperation.Compare, core.go:368-411) as a stable
-// LSD radix sort over composite integer keys, plus dense ranking.
+// sort.cuh — queue ordering (ScheduleOperation.Compare, core.go:368-411) as ONE persistent
+// kernel: stable LSD radix sort over composite integer keys + dense ranking, for the groups
+// first (their rank feeds the pod keys) and then for the pods.
 //
 // Compare is lexicographic: priority desc (:379) | group-less before grouped (:384-393)
 // | PodGroup creation asc (:400) | pgName DESC (:404) | pod queue timestamp asc (:385,:407).
-// Groups are ranked first (creation asc, name desc -> dense group rank), then pods sort on
-//   word1 = [~biased priority : 32][grouped : 1][group rank : 31]   word0 = biased timestamp.
-// Sorting moves 4-byte indices only; digits are gathered from the (L2-resident) key words.
+//   group key : k1 = biased creation, k0 = ~name_rank          -> dense group rank
+//   pod key   : k1 = [~biased priority : 32][grouped : 1][group rank : 31], k0 = biased timestamp
+// Only 4-byte indices move; digits are gathered from the (L2-resident) key words.  Byte digits
+// that are constant over the table (host-computed masks) are not sorted on at all.
+//
+// One launch, `grid` co-resident CTAs, phases separated by a software grid barrier.  A radix
+// pass is a single phase: each CTA ranks its 4096-key tiles (warp multi-split keeps equal
+// digits in order), derives its global bases from the tile histograms of THIS digit, scatters,
+// and already accumulates the tile histograms of the NEXT digit at the destinations
+// (three rotating histogram buffers: read / accumulate / clear).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,183 +24,298 @@ namespace bsk {
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_MAX_PASSES = 16;
+
+struct SortPass {
+  uint8_t word;   // 0: k0, 1: k1
+  uint8_t shift;  // bit offset of the 8-bit digit
+};
+
+struct SortArgs {
+  // groups
+  const int64_t* creation;
+  const uint32_t* name_rank;
+  uint32_t G;
+  uint64_t* gk0;
+  uint64_t* gk1;
+  uint32_t* group_rank;  // out [G]
+  // pods
+  const int32_t* prio;
+  const int32_t* gid;
+  const int64_t* ts;
+  const uint8_t* pflags;
+  uint32_t P;
+  uint64_t* pk0;
+  uint64_t* pk1;
+  uint32_t* order;  // out [P]
+  uint32_t* rank;   // out [P]
+  // scratch
+  uint32_t* idx_a;    // [max(P,G)]
+  uint32_t* idx_b;    // [max(P,G)]
+  uint32_t* hist;     // [3][256][ntiles_max]
+  uint32_t* tilecnt;  // [ntiles_max]
+  unsigned int* barrier;  // zeroed before the launch
+  uint32_t ntiles_max;
+  SortPass gpass[SORT_MAX_PASSES];
+  uint32_t n_gpass;
+  SortPass ppass[SORT_MAX_PASSES];
+  uint32_t n_ppass;
+};
 
 __device__ __forceinline__ uint64_t bias64(int64_t v) { return (uint64_t)v ^ 0x8000000000000000ull; }
 
-__global__ void iota_kernel(uint32_t* __restrict__ idx, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) idx[i] = i;
-}
-
-// group keys: k1 = creation (biased, ascending), k0 = ~name_rank (descending name)
-__global__ void group_keys_kernel(const int64_t* __restrict__ creation, const uint32_t* __restrict__ name_rank,
-                                  uint32_t G, uint64_t* __restrict__ k0, uint64_t* __restrict__ k1) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G) return;
-  k0[i] = (uint64_t)(~name_rank[i]);
-  k1[i] = bias64(creation[i]);
-}
-
-// pod keys from the dense group rank
-__global__ void pod_keys_kernel(const int32_t* __restrict__ prio, const int32_t* __restrict__ gid,
-                                const int64_t* __restrict__ ts, const uint8_t* __restrict__ flags,
-                                const uint32_t* __restrict__ group_rank, uint32_t P, uint32_t G,
-                                uint64_t* __restrict__ k0, uint64_t* __restrict__ k1) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const int32_t g = gid[i];
-  const uint32_t pbits = ~((uint32_t)prio[i] ^ 0x80000000u);  // higher priority first
-  uint32_t low;
-  if (g == BS_GID_NONE) low = 0u;                             // group-less first at equal priority
-  else {
-    const bool miss = g < 0 || (uint32_t)g >= G || (flags[i] & BS_POD_LISTER_MISS);
-    low = 0x80000000u | (miss ? 0x7fffffffu : group_rank[g]);
+// software grid barrier: every CTA of a co-resident grid arrives once per call
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int target = (epoch + 1) * gridDim.x;
+    atomicAdd(counter, 1u);
+    while (*((volatile unsigned int*)counter) < target) __nanosleep(64);
+    __threadfence();
   }
-  k1[i] = ((uint64_t)pbits << 32) | low;
-  k0[i] = bias64(ts[i]);
+  epoch += 1;
+  __syncthreads();
 }
 
-__device__ __forceinline__ uint32_t digit_of(const uint64_t* __restrict__ key, uint32_t idx, int shift) {
-  return (uint32_t)(key[idx] >> shift) & 0xffu;
+__device__ __forceinline__ uint32_t digit_of(const uint64_t* __restrict__ k0, const uint64_t* __restrict__ k1,
+                                             SortPass ps, uint32_t idx) {
+  const uint64_t* k = ps.word ? k1 : k0;
+  return (uint32_t)(k[idx] >> ps.shift) & 0xffu;
 }
 
-// pass kernel 1: per-CTA digit histogram -> ghist[digit * nblk + blk]
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint32_t* __restrict__ idx_in, const uint64_t* __restrict__ key, int shift,
-                  uint32_t n, uint32_t nblk, uint32_t* __restrict__ ghist) {
-  __shared__ uint32_t sh[256];
-  sh[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t base = blockIdx.x * SORT_TILE;
-  for (int k = 0; k < SORT_ITEMS; ++k) {
-    const uint32_t i = base + k * SORT_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&sh[digit_of(key, idx_in[i], shift)], 1u);
-  }
-  __syncthreads();
-  ghist[threadIdx.x * nblk + blockIdx.x] = sh[threadIdx.x];
-}
-
-// pass kernel 2: exclusive scan over (digit-major) histogram; flags a pass whose
-// keys all share one digit (scatter then degenerates to a copy).
-__global__ void __launch_bounds__(256)
-radix_scan_kernel(uint32_t* __restrict__ ghist, uint32_t nblk, uint32_t n, uint32_t* __restrict__ skip) {
-  __shared__ uint32_t s_tot[256];
-  __shared__ uint32_t s_skip;
-  const uint32_t d = threadIdx.x;
-  uint32_t tot = 0;
-  for (uint32_t b = 0; b < nblk; ++b) tot += ghist[d * nblk + b];
-  s_tot[d] = tot;
-  if (d == 0) s_skip = 0;
-  __syncthreads();
-  if (tot == n && n > 0) s_skip = 1;
-  // exclusive scan of 256 totals (Hillis-Steele in shared memory)
-  uint32_t v = tot;
-  for (int o = 1; o < 256; o <<= 1) {
-    const uint32_t w = d >= (uint32_t)o ? s_tot[d - o] : 0u;
+// first-pass tile histograms for identity order, and zeroing of the other two buffers,
+// restricted to the tiles this CTA owns (no cross-CTA write races)
+__device__ void sort_init_tiles(const uint64_t* k0, const uint64_t* k1, const SortPass* passes, uint32_t npass,
+                                uint32_t n, uint32_t* idx, uint32_t* hist, uint32_t ntiles, uint32_t hstride,
+                                uint32_t* s_hist) {
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    s_hist[threadIdx.x] = 0;
     __syncthreads();
-    v += w;
-    s_tot[d] = v;
-    __syncthreads();
-  }
-  uint32_t run = v - tot;
-  for (uint32_t b = 0; b < nblk; ++b) {
-    const uint32_t c = ghist[d * nblk + b];
-    ghist[d * nblk + b] = run;
-    run += c;
-  }
-  if (d == 0) *skip = s_skip;
-}
-
-// pass kernel 3: stable scatter.  Each warp owns a contiguous 512-key slice of the
-// tile; warp-level multi-split with __match_any_sync keeps equal digits in order.
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_scatter_kernel(const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ idx_out,
-                     const uint64_t* __restrict__ key, int shift, uint32_t n, uint32_t nblk,
-                     const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ skip) {
-  const uint32_t base = blockIdx.x * SORT_TILE;
-  if (*skip) {
+    const uint32_t base = t * SORT_TILE;
     for (int k = 0; k < SORT_ITEMS; ++k) {
       const uint32_t i = base + k * SORT_THREADS + threadIdx.x;
-      if (i < n) idx_out[i] = idx_in[i];
+      if (i < n) {
+        idx[i] = i;
+        if (npass) atomicAdd(&s_hist[digit_of(k0, k1, passes[0], i)], 1u);
+      }
     }
-    return;
-  }
-  __shared__ uint32_t wcount[SORT_WARPS][256];
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int w = 0; w < SORT_WARPS; ++w) wcount[w][threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t wbase = base + wid * (SORT_TILE / SORT_WARPS);
-  constexpr int ITER = SORT_TILE / SORT_WARPS / 32;
-  uint32_t my_idx[ITER];
-  uint32_t my_dig[ITER];
-  // (a) warp digit counts
-#pragma unroll
-  for (int k = 0; k < ITER; ++k) {
-    const uint32_t i = wbase + k * 32 + lane;
-    const bool act = i < n;
-    my_idx[k] = act ? idx_in[i] : 0u;
-    my_dig[k] = act ? digit_of(key, my_idx[k], shift) : 0x100u;
-    const uint32_t mask = __match_any_sync(0xffffffffu, my_dig[k]);
-    if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][my_dig[k]] += __popc(mask);
-    __syncwarp();
-  }
-  __syncthreads();
-  // (b) per digit: global base of this CTA + exclusive prefix over the warps
-  {
-    const uint32_t d = threadIdx.x;
-    uint32_t run = ghist[d * nblk + blockIdx.x];
-    for (int w = 0; w < SORT_WARPS; ++w) {
-      const uint32_t c = wcount[w][d];
-      wcount[w][d] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  // (c) ranks in original order
-#pragma unroll
-  for (int k = 0; k < ITER; ++k) {
-    const uint32_t i = wbase + k * 32 + lane;
-    const bool act = i < n;
-    const uint32_t mask = __match_any_sync(0xffffffffu, my_dig[k]);
-    uint32_t pos = 0;
-    if (act) pos = wcount[wid][my_dig[k]] + __popc(mask & ((1u << lane) - 1u));
-    __syncwarp();
-    if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][my_dig[k]] += __popc(mask);
-    __syncwarp();
-    if (act) idx_out[pos] = my_idx[k];
+    __syncthreads();
+    hist[0 * hstride + threadIdx.x * ntiles + t] = s_hist[threadIdx.x];
+    hist[1 * hstride + threadIdx.x * ntiles + t] = 0;
+    hist[2 * hstride + threadIdx.x * ntiles + t] = 0;
+    __syncthreads();
   }
 }
 
-// dense rank over a sorted order: rank[order[i]] = number of key changes before i.
-// Single CTA; thread t owns a contiguous run.
-__global__ void __launch_bounds__(1024)
-dense_rank_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__ k0,
-                  const uint64_t* __restrict__ k1, uint32_t n, uint32_t* __restrict__ rank) {
-  __shared__ uint32_t s_w[32];
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
-  const uint32_t a = min(tid * per, n), b = min(a + per, n);
-  auto differs = [&](uint32_t i) -> uint32_t {
-    if (i == 0) return 0u;
-    const uint32_t x = order[i], y = order[i - 1];
-    return (k0[x] != k0[y] || k1[x] != k1[y]) ? 1u : 0u;
-  };
-  uint32_t cnt = 0;
-  for (uint32_t i = a; i < b; ++i) cnt += differs(i);
-  uint32_t inc = cnt;
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t w = __shfl_up_sync(0xffffffffu, inc, o);
-    if ((int)lane >= o) inc += w;
+// One radix pass (one phase).  cur: histograms of this digit; nxt: accumulates the next digit's
+// tile histograms at the scatter destinations; clr: cleared for the pass after next.
+__device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, bool has_next, SortPass ps_next,
+                          uint32_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                          const uint32_t* cur, uint32_t* nxt, uint32_t* clr, uint32_t ntiles,
+                          uint32_t (*wcount)[256], uint32_t* s_base) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int w = 0; w < SORT_WARPS; ++w) wcount[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t wbase = t * SORT_TILE + wid * (SORT_TILE / SORT_WARPS);
+    constexpr int ITER = SORT_TILE / SORT_WARPS / 32;
+    uint32_t my_idx[ITER];
+    uint32_t my_dig[ITER];
+    // (a) warp digit counts
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      const uint32_t i = wbase + k * 32 + lane;
+      const bool act = i < n;
+      my_idx[k] = act ? in[i] : 0u;
+      my_dig[k] = act ? digit_of(k0, k1, ps, my_idx[k]) : 0x100u;
+      const uint32_t mask = __match_any_sync(0xffffffffu, my_dig[k]);
+      if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][my_dig[k]] += __popc(mask);
+      __syncwarp();
+    }
+    // (b) thread d: tiles before this one with digit d, and the digit total
+    {
+      const uint32_t d = threadIdx.x;
+      const uint32_t* row = cur + d * ntiles;
+      uint32_t before = 0, total = 0;
+      for (uint32_t tt = 0; tt < ntiles; ++tt) {
+        const uint32_t c = row[tt];
+        total += c;
+        if (tt < t) before += c;
+      }
+      // exclusive scan of the 256 digit totals (warp scans + warp offsets)
+      uint32_t inc = total;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += v;
+      }
+      __shared__ uint32_t s_wtot[SORT_WARPS];
+      if (lane == 31) s_wtot[wid] = inc;
+      __syncthreads();
+      uint32_t digit_base = inc - total;
+      for (uint32_t w = 0; w < wid; ++w) digit_base += s_wtot[w];
+      uint32_t run = digit_base + before;
+      for (int w = 0; w < SORT_WARPS; ++w) {
+        const uint32_t c = wcount[w][d];
+        wcount[w][d] = run;
+        run += c;
+      }
+      clr[d * ntiles + t] = 0;
+    }
+    __syncthreads();
+    // (c) ranks in original order, scatter, next-digit histogram at the destination tile
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      const uint32_t i = wbase + k * 32 + lane;
+      const bool act = i < n;
+      const uint32_t mask = __match_any_sync(0xffffffffu, my_dig[k]);
+      uint32_t pos = 0;
+      if (act) pos = wcount[wid][my_dig[k]] + __popc(mask & ((1u << lane) - 1u));
+      __syncwarp();
+      if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][my_dig[k]] += __popc(mask);
+      __syncwarp();
+      if (act) {
+        out[pos] = my_idx[k];
+        if (has_next) atomicAdd(&nxt[digit_of(k0, k1, ps_next, my_idx[k]) * ntiles + pos / SORT_TILE], 1u);
+      }
+    }
+    __syncthreads();
   }
-  if (lane == 31) s_w[wid] = inc;
+  (void)s_base;
+}
+
+// dense rank over a sorted order (two phases): rank[order[i]] = number of key changes before i
+__device__ __forceinline__ uint32_t rank_flag(const uint32_t* order, const uint64_t* k0, const uint64_t* k1,
+                                              uint32_t i) {
+  if (i == 0) return 0u;
+  const uint32_t x = order[i], y = order[i - 1];
+  return (k0[x] != k0[y] || k1[x] != k1[y]) ? 1u : 0u;
+}
+
+__device__ uint32_t block_sum(uint32_t v, uint32_t* s_w) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
-  uint32_t run = inc - cnt;
-  for (uint32_t w = 0; w < wid; ++w) run += s_w[w];
-  for (uint32_t i = a; i < b; ++i) {
-    run += differs(i);
-    rank[order[i]] = run;
+  if (lane == 0) s_w[wid] = v;
+  __syncthreads();
+  uint32_t t = 0;
+  for (int w = 0; w < SORT_WARPS; ++w) t += s_w[w];
+  return t;
+}
+
+__device__ void rank_count_tiles(const uint32_t* order, const uint64_t* k0, const uint64_t* k1, uint32_t n,
+                                 uint32_t ntiles, uint32_t* tilecnt, uint32_t* s_w) {
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
+    uint32_t c = 0;
+    for (int k = 0; k < SORT_ITEMS; ++k)
+      if (base + k < n) c += rank_flag(order, k0, k1, base + k);
+    c = block_sum(c, s_w);
+    if (threadIdx.x == 0) tilecnt[t] = c;
+  }
+}
+
+__device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, const uint64_t* k1, uint32_t n,
+                                 uint32_t ntiles, const uint32_t* tilecnt, uint32_t* rank, uint32_t* order_out,
+                                 uint32_t* s_w) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    uint32_t off = 0;
+    for (uint32_t tt = threadIdx.x; tt < t; tt += SORT_THREADS) off += tilecnt[tt];
+    off = block_sum(off, s_w);
+    const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
+    uint32_t c = 0;
+    for (int k = 0; k < SORT_ITEMS; ++k)
+      if (base + k < n) c += rank_flag(order, k0, k1, base + k);
+    uint32_t inc = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)lane >= o) inc += v;
+    }
+    __syncthreads();
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    uint32_t run = off + inc - c;
+    for (uint32_t w = 0; w < wid; ++w) run += s_w[w];
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+      const uint32_t i = base + k;
+      if (i < n) {
+        run += rank_flag(order, k0, k1, i);
+        const uint32_t o = order[i];
+        rank[o] = run;
+        if (order_out) order_out[i] = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// sorts 0..n-1 by the pass list; returns the buffer holding the final order (uniform over the grid)
+__device__ uint32_t* sort_table(const uint64_t* k0, const uint64_t* k1, const SortPass* passes, uint32_t npass,
+                                uint32_t n, uint32_t* a, uint32_t* b, uint32_t* hist, uint32_t ntiles_max,
+                                unsigned int* barrier, unsigned int& epoch, uint32_t (*wcount)[256],
+                                uint32_t* s_misc) {
+  const uint32_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+  const uint32_t hstride = 256 * ntiles_max;
+  sort_init_tiles(k0, k1, passes, npass, n, a, hist, ntiles, hstride, s_misc);
+  grid_barrier(barrier, epoch);
+  uint32_t* cur = a;
+  uint32_t* nxt = b;
+  for (uint32_t k = 0; k < npass; ++k) {
+    const bool has_next = k + 1 < npass;
+    sort_pass(k0, k1, passes[k], has_next, passes[has_next ? k + 1 : k], n, cur, nxt,
+              hist + (k % 3) * hstride, hist + ((k + 1) % 3) * hstride, hist + ((k + 2) % 3) * hstride, ntiles,
+              wcount, s_misc);
+    grid_barrier(barrier, epoch);
+    uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  return cur;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) queue_sort_kernel(SortArgs a) {
+  __shared__ uint32_t wcount[SORT_WARPS][256];
+  __shared__ uint32_t s_misc[256];
+  unsigned int epoch = 0;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+
+  // ---- groups: keys -> sort -> dense rank
+  if (a.G) {
+    for (uint32_t i = gtid; i < a.G; i += gsz) {
+      a.gk0[i] = (uint64_t)(~a.name_rank[i]);   // descending name
+      a.gk1[i] = bias64(a.creation[i]);         // ascending creation
+    }
+    grid_barrier(a.barrier, epoch);
+    uint32_t* gord = sort_table(a.gk0, a.gk1, a.gpass, a.n_gpass, a.G, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
+                                a.barrier, epoch, wcount, s_misc);
+    const uint32_t gt = (a.G + SORT_TILE - 1) / SORT_TILE;
+    rank_count_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, s_misc);
+    grid_barrier(a.barrier, epoch);
+    rank_write_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, a.group_rank, nullptr, s_misc);
+    grid_barrier(a.barrier, epoch);
+  }
+  // ---- pods
+  if (a.P) {
+    for (uint32_t i = gtid; i < a.P; i += gsz) {
+      const int32_t g = a.gid[i];
+      const uint32_t pbits = ~((uint32_t)a.prio[i] ^ 0x80000000u);  // higher priority first
+      uint32_t low;
+      if (g == BS_GID_NONE) low = 0u;                               // group-less first at equal priority
+      else {
+        const bool miss = g < 0 || (uint32_t)g >= a.G || (a.pflags[i] & BS_POD_LISTER_MISS);
+        low = 0x80000000u | (miss ? 0x7fffffffu : a.group_rank[g]);
+      }
+      a.pk1[i] = ((uint64_t)pbits << 32) | low;
+      a.pk0[i] = bias64(a.ts[i]);
+    }
+    grid_barrier(a.barrier, epoch);
+    uint32_t* pord = sort_table(a.pk0, a.pk1, a.ppass, a.n_ppass, a.P, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
+                                a.barrier, epoch, wcount, s_misc);
+    const uint32_t pt = (a.P + SORT_TILE - 1) / SORT_TILE;
+    rank_count_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, s_misc);
+    grid_barrier(a.barrier, epoch);
+    rank_write_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, a.rank, a.order, s_misc);
   }
 }
 
