@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists(plugin):
         srcs.append(plugin)
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-shared", "-Xcompiler", "-fPIC,-Wall", "-fmad=false", "-o", LIB] + srcs
+           "-shared", "-Xcompiler", "-fPIC,-Wall,-fopenmp", "-fmad=false", "-o", LIB] + srcs + ["-lgomp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd, cwd=CSRC)

@@ -7,6 +7,8 @@
 // There is no CPU implementation of the path here: no device -> BS_E_NODEVICE.
 #include <cuda_runtime.h>
 
+#include <omp.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -66,28 +68,96 @@ struct PinBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct Key2 {
-  uint64_t a, b;
-  bool operator==(const Key2& o) const { return a == o.a && b == o.b; }
+// (sel, tol, non-zero scalar request mask): the pre-encoded predicates a pod class shares
+struct ClassKey {
+  uint64_t sel, tol;
+  uint32_t nz;
+  bool operator==(const ClassKey& o) const { return sel == o.sel && tol == o.tol && nz == o.nz; }
 };
-struct Key3 {
-  uint64_t a, b;
-  uint32_t c;
-  bool operator==(const Key3& o) const { return a == o.a && b == o.b && c == o.c; }
-};
-struct H2 {
-  size_t operator()(const Key2& k) const {
-    uint64_t h = k.a * 0x9E3779B97F4A7C15ull ^ (k.b + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
-    return (size_t)(h ^ (h >> 29));
+
+// flat open-addressing index ClassKey -> dense id (insertion order)
+struct ClassIndex {
+  std::vector<ClassKey> keys;
+  std::vector<uint32_t> slots;  // id + 1, 0 = empty
+  uint32_t mask = 0;
+  ClassKey last_key{0, 0, 0xffffffffu};
+  uint32_t last_id = 0;
+  static uint64_t hash(const ClassKey& k) {
+    uint64_t h = k.sel * 0x9E3779B97F4A7C15ull ^ (k.tol + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull ^
+                 (uint64_t)k.nz * 0x94D049BB133111EBull;
+    return h ^ (h >> 29);
   }
-};
-struct H3 {
-  size_t operator()(const Key3& k) const {
-    uint64_t h = k.a * 0x9E3779B97F4A7C15ull ^ (k.b + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull ^
-                 (uint64_t)k.c * 0x94D049BB133111EBull;
-    return (size_t)(h ^ (h >> 29));
+  void clear() {
+    keys.clear();
+    slots.assign(256, 0);
+    mask = 255;
+    last_key = ClassKey{0, 0, 0xffffffffu};
   }
+  void grow() {
+    std::vector<uint32_t> ns((size_t)(mask + 1) * 2, 0);
+    const uint32_t nm = (uint32_t)ns.size() - 1;
+    for (uint32_t id = 0; id < keys.size(); ++id) {
+      uint32_t s = (uint32_t)hash(keys[id]) & nm;
+      while (ns[s]) s = (s + 1) & nm;
+      ns[s] = id + 1;
+    }
+    slots.swap(ns);
+    mask = nm;
+  }
+  uint32_t get_or_add(const ClassKey& k) {
+    if (k == last_key) return last_id;
+    if (slots.empty()) clear();
+    uint32_t s = (uint32_t)hash(k) & mask;
+    while (slots[s]) {
+      if (keys[slots[s] - 1] == k) {
+        last_key = k;
+        last_id = slots[s] - 1;
+        return last_id;
+      }
+      s = (s + 1) & mask;
+    }
+    const uint32_t id = (uint32_t)keys.size();
+    keys.push_back(k);
+    slots[s] = id + 1;
+    if (keys.size() * 2 > slots.size()) grow();
+    last_key = k;
+    last_id = id;
+    return id;
+  }
+  size_t size() const { return keys.size(); }
 };
+
+inline int host_threads() { return std::max(1, std::min(omp_get_max_threads(), 16)); }
+
+// out[i] = id of key_of(i) in `global` (ids stable across calls: the index only grows).
+// Two parallel passes: thread-local indices, a small sequential merge, then a remap.
+template <class KeyFn>
+void assign_classes(ClassIndex& global, uint32_t n, KeyFn key_of, uint32_t* out) {
+  if (global.slots.empty()) global.clear();
+  const int T = n < 8192 ? 1 : host_threads();
+  std::vector<ClassIndex> local(T);
+  std::vector<std::vector<uint32_t>> remap(T);
+  const uint32_t chunk = (n + T - 1) / T;
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    ClassIndex& li = local[t];
+    li.clear();
+    const uint32_t a = std::min(n, (uint32_t)t * chunk), b = std::min(n, a + chunk);
+    for (uint32_t i = a; i < b; ++i) out[i] = li.get_or_add(key_of(i));
+  }
+  for (int t = 0; t < T; ++t) {
+    remap[t].resize(local[t].size());
+    for (size_t j = 0; j < local[t].size(); ++j) remap[t][j] = global.get_or_add(local[t].keys[j]);
+  }
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    const uint32_t a = std::min(n, (uint32_t)t * chunk), b = std::min(n, a + chunk);
+    const uint32_t* rm = remap[t].data();
+    for (uint32_t i = a; i < b; ++i) out[i] = rm[out[i]];
+  }
+}
 
 }  // namespace
 
@@ -136,8 +206,12 @@ struct bs_engine {
   // host copies for the per-call mirrors and class building
   std::vector<int32_t> h_gid, h_prio;
   std::vector<uint8_t> h_pflags;
-  std::vector<uint64_t> h_psel, h_ptol, h_gsel, h_gtol;
-  std::vector<uint32_t> h_pnz;
+  std::vector<uint64_t> h_gsel, h_gtol;
+  // class indices (host packing): fit classes (sel, tol, nz) of the pods; representative classes
+  // (sel, tol) of pods and carried-in group representatives
+  ClassIndex fit_index, rep_index;
+  std::vector<uint32_t> h_pfc, h_prc, h_grc;
+  bool group_classes_dirty = true;
   std::vector<int64_t> h_wait_ns;
   int64_t default_wait_ns = 0;
   // bits that differ between rows of each sort key word (a constant byte needs no radix pass)
@@ -188,6 +262,7 @@ bool lane_maxima(const int64_t* a, uint32_t L, size_t n, int64_t* out) {
   for (uint32_t d = 0; d < L; ++d) {
     const int64_t* row = a + (size_t)d * n;
     int64_t lo = 0, hi = 0;
+#pragma omp parallel for reduction(min : lo) reduction(max : hi) if (n > 65536) num_threads(host_threads())
     for (size_t i = 0; i < n; ++i) {
       lo = std::min(lo, row[i]);
       hi = std::max(hi, row[i]);
@@ -448,45 +523,29 @@ inline uint64_t low_bits_mask(uint32_t n) {  // mask covering every value in [0,
 }
 
 int rebuild_classes(bs_engine* e) {
-  // fit classes: distinct (sel, tol, non-zero scalar request mask) over the pods;
-  // rep classes: distinct (sel, tol) over pods and carried-in group representatives.
+  // Pod classes were indexed while the pod table was uploaded; group representative classes are
+  // looked up here (the representative index must already hold the pods' (sel, tol) pairs so that
+  // the ids agree).  Then the class tables go to the device.
   const uint32_t P = e->P, G = e->G;
-  std::unordered_map<Key3, uint32_t, H3> fmap;
-  std::unordered_map<Key2, uint32_t, H2> rmap;
-  std::vector<uint64_t> fsel, ftol, rsel, rtol;
-  std::vector<uint32_t> fnz;
-  std::vector<uint32_t> pfc(P), prc(P), grc(G);
-  fmap.reserve(256);
-  rmap.reserve(256);
-  for (uint32_t p = 0; p < P; ++p) {
-    const Key3 k3{e->h_psel[p], e->h_ptol[p], e->h_pnz[p]};
-    auto it = fmap.find(k3);
-    if (it == fmap.end()) {
-      it = fmap.emplace(k3, (uint32_t)fsel.size()).first;
-      fsel.push_back(k3.a); ftol.push_back(k3.b); fnz.push_back(k3.c);
-    }
-    pfc[p] = it->second;
-    const Key2 k2{e->h_psel[p], e->h_ptol[p]};
-    auto jt = rmap.find(k2);
-    if (jt == rmap.end()) {
-      jt = rmap.emplace(k2, (uint32_t)rsel.size()).first;
-      rsel.push_back(k2.a); rtol.push_back(k2.b);
-    }
-    prc[p] = jt->second;
+  if (e->group_classes_dirty) {
+    e->h_grc.resize(G);
+    const uint64_t* gs = e->h_gsel.data();
+    const uint64_t* gt = e->h_gtol.data();
+    assign_classes(e->rep_index, G, [=](uint32_t g) { return ClassKey{gs[g], gt[g], 0u}; }, e->h_grc.data());
+    e->group_classes_dirty = false;
   }
-  for (uint32_t g = 0; g < G; ++g) {
-    const Key2 k2{e->h_gsel[g], e->h_gtol[g]};
-    auto jt = rmap.find(k2);
-    if (jt == rmap.end()) {
-      jt = rmap.emplace(k2, (uint32_t)rsel.size()).first;
-      rsel.push_back(k2.a); rtol.push_back(k2.b);
-    }
-    grc[g] = jt->second;
+  if (e->fit_index.size() == 0) e->fit_index.get_or_add(ClassKey{0, 0, 0});
+  if (e->rep_index.size() == 0) e->rep_index.get_or_add(ClassKey{0, 0, 0});
+  e->n_fit_classes = (uint32_t)e->fit_index.size();
+  e->n_rep_classes = (uint32_t)e->rep_index.size();
+  std::vector<uint64_t> fsel(e->n_fit_classes), ftol(e->n_fit_classes), rsel(e->n_rep_classes), rtol(e->n_rep_classes);
+  std::vector<uint32_t> fnz(e->n_fit_classes);
+  for (uint32_t c = 0; c < e->n_fit_classes; ++c) {
+    fsel[c] = e->fit_index.keys[c].sel; ftol[c] = e->fit_index.keys[c].tol; fnz[c] = e->fit_index.keys[c].nz;
   }
-  if (fsel.empty()) { fsel.push_back(0); ftol.push_back(0); fnz.push_back(0); }
-  if (rsel.empty()) { rsel.push_back(0); rtol.push_back(0); }
-  e->n_fit_classes = (uint32_t)fsel.size();
-  e->n_rep_classes = (uint32_t)rsel.size();
+  for (uint32_t c = 0; c < e->n_rep_classes; ++c) {
+    rsel[c] = e->rep_index.keys[c].sel; rtol[c] = e->rep_index.keys[c].tol;
+  }
   int rc;
   // cudaMemcpyAsync from pageable memory returns once the data is staged, so the vectors may die.
   if ((rc = upload_vec(e, e->d_fsel, fsel.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
@@ -494,9 +553,9 @@ int rebuild_classes(bs_engine* e) {
   if ((rc = upload_vec(e, e->d_fnz, fnz.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
   if ((rc = upload_vec(e, e->d_rsel, rsel.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
   if ((rc = upload_vec(e, e->d_rtol, rtol.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
-  if ((rc = upload_vec(e, e->d_pod_fit_class, pfc.data(), P, std::max(P, 1u)))) return rc;
-  if ((rc = upload_vec(e, e->d_pod_rep_class, prc.data(), P, std::max(P, 1u)))) return rc;
-  if ((rc = upload_vec(e, e->d_group_rep_class, grc.data(), G, std::max(G, 1u)))) return rc;
+  if ((rc = upload_vec(e, e->d_pod_fit_class, e->h_pfc.data(), P, std::max(P, 1u)))) return rc;
+  if ((rc = upload_vec(e, e->d_pod_rep_class, e->h_prc.data(), P, std::max(P, 1u)))) return rc;
+  if ((rc = upload_vec(e, e->d_group_rep_class, e->h_grc.data(), G, std::max(G, 1u)))) return rc;
   CK(cudaStreamSynchronize(e->s));
   e->classes_dirty = false;
   return BS_OK;
@@ -973,6 +1032,7 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   e->G = G;
   e->have_groups = true;
   e->classes_dirty = true;
+  e->group_classes_dirty = true;
   e->evaluated = false;
   return BS_OK;
 }
@@ -996,35 +1056,49 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
-  // host copies: mirrors + class keys (non-zero scalar request mask, core.go:688-690)
+  // host copies for the per-call mirrors
   e->h_gid.assign(t->gid, t->gid + P);
   e->h_prio.assign(t->priority, t->priority + P);
   e->h_pflags.assign(t->flags, t->flags + P);
-  e->h_psel.assign(t->sel_mask, t->sel_mask + P);
-  e->h_ptol.assign(t->tol_mask, t->tol_mask + P);
-  e->h_pnz.assign(P, 0);
   {
     uint64_t ot = 0, at = ~0ull;
     uint32_t op = 0, apr = ~0u;
-    bool miss = false;
+    int miss = 0;
     int32_t mg = -1;
+#pragma omp parallel for reduction(| : ot, op, miss) reduction(& : at, apr) reduction(max : mg) \
+    if (P > 65536) num_threads(host_threads())
     for (uint32_t p = 0; p < P; ++p) {
       const uint64_t ts = (uint64_t)t->ts_ns[p];
       const uint32_t pr = (uint32_t)t->priority[p];
       ot |= ts; at &= ts; op |= pr; apr &= pr;
-      miss |= (t->gid[p] < BS_GID_NONE) || (t->flags[p] & BS_POD_LISTER_MISS);
+      miss |= ((t->gid[p] < BS_GID_NONE) || (t->flags[p] & BS_POD_LISTER_MISS)) ? 1 : 0;
       mg = std::max(mg, t->gid[p]);
     }
     e->vary_ts = P ? (ot ^ at) : 0;
     e->vary_prio = P ? (uint64_t)(op ^ apr) : 0;
-    e->any_lister_miss = miss;
+    e->any_lister_miss = miss != 0;
     e->max_gid = mg;
   }
-  for (uint32_t d = 4; d < L; ++d) {
-    const int64_t* row = t->req + (size_t)d * P;
-    for (uint32_t p = 0; p < P; ++p)
-      if (((t->req_present[p] >> d) & 1u) && row[p] != 0) e->h_pnz[p] |= 1u << d;
+  // class indices: fit class = (sel, tol, scalar keys requested with a non-zero amount,
+  // core.go:688-690); representative class = (sel, tol).  Both indices restart with the pod table.
+  e->fit_index.clear();
+  e->rep_index.clear();
+  e->h_pfc.resize(P);
+  e->h_prc.resize(P);
+  {
+    const bs_pod_table tt = *t;
+    const uint32_t LL = L, PP = P;
+    assign_classes(e->fit_index, P, [=](uint32_t p) {
+      uint32_t nz = 0;
+      const uint32_t rp = tt.req_present[p];
+      for (uint32_t d = 4; d < LL; ++d)
+        if (((rp >> d) & 1u) && tt.req[(size_t)d * PP + p] != 0) nz |= 1u << d;
+      return ClassKey{tt.sel_mask[p], tt.tol_mask[p], nz};
+    }, e->h_pfc.data());
+    assign_classes(e->rep_index, P, [=](uint32_t p) { return ClassKey{tt.sel_mask[p], tt.tol_mask[p], 0u}; },
+                   e->h_prc.data());
   }
+  e->group_classes_dirty = true;
   CK(cudaStreamSynchronize(e->s));
   memcpy(e->max_req, mx_q, sizeof(mx_q));
   e->P = P;

@@ -934,6 +934,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+// high word of an int64, opaque to the optimiser (it otherwise re-forms a 2-instruction 64-bit compare)
+__device__ __forceinline__ int32_t hi32(int64_t v) {
+  int32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  (void)lo;
+  return hi;
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 
 struct FitArgs {
   const int64_t* left_w;     // [LW][Npad] wide lanes
@@ -989,7 +999,7 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
   const int64_t* tpw = tlw + lane;
   const int32_t* tpn = tln + lane;
   int32_t node = (int32_t)(node_base + lane);
-  uint32_t* wp = s_words;
+  uint32_t wp = smem_u32(s_words);
 #pragma unroll 1
   for (int jb = 0; jb < TILE_WORDS; jb += 4) {
 #pragma unroll
@@ -1016,8 +1026,9 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
 #pragma unroll
           for (int d = 1; d < LW; ++d) m = min64(m, lfw[d] - rqw[r][d]);
         }
-        const bool fit = (m >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
-        wp[r * TILE_WORDS + jj] = __ballot_sync(0xffffffffu, fit);
+        // m >= 0 needs only the sign of the high word (one ISETP instead of a 64-bit compare)
+        const bool fit = (hi32(m) >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
+        sts_u32(wp + (r * TILE_WORDS + jj) * 4, __ballot_sync(0xffffffffu, fit));
         if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
         if (want_score && in_range)
           __stcs(reinterpret_cast<long long*>(sp[r] + jj * 32), fit ? (long long)m : (long long)INT64_MIN);
@@ -1026,7 +1037,7 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
     tpw += 128;
     tpn += 128;
     node += 128;
-    wp += 4;
+    wp += 16;
 #pragma unroll
     for (int r = 0; r < PODS_PER_WARP; ++r) sp[r] += 128;
   }

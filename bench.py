@@ -316,9 +316,15 @@ def main():
     full_sync()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
+    br = {"upload_nodes": 0.0, "upload_groups": 0.0, "upload_pods": 0.0, "evaluate_fetch": 0.0}
     for _ in range(e2e_steps):
-        eng.upload(snap)
-        res = eng.evaluate()
+        ta = time.perf_counter(); eng.upload_nodes(snap.nodes)
+        tb = time.perf_counter(); eng.upload_groups(snap.groups)
+        tc = time.perf_counter(); eng.upload_pods(snap.pods)
+        td = time.perf_counter(); res = eng.evaluate()
+        te_ = time.perf_counter()
+        br["upload_nodes"] += tb - ta; br["upload_groups"] += tc - tb; br["upload_pods"] += td - tc
+        br["evaluate_fetch"] += te_ - td
         if world > 1:
             with torch.cuda.stream(ext):
                 dist.all_gather_into_tensor(gathered, bitmap_t)
@@ -360,6 +366,7 @@ def main():
             "admit_decisions_per_s": admit_rate,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
+                    "breakdown_ms": {k: v / e2e_steps * 1e3 for k, v in br.items()},
                     "what": "bs_upload_nodes/groups/pods from pinned host tables + bs_evaluate (D2H of all decision "
                             "vectors) per step, wall clock"},
             "gpu_launches": int(launches),
