@@ -1,0 +1,87 @@
+"""GPU, BASELINE.json's full sizes: bit-exact decisions against the (multi-threaded) oracle where the
+oracle finishes in seconds, and size-independent properties of the materialised matrices elsewhere."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _popcount_rows(words):
+    return np.unpackbits(words.view(np.uint8), axis=1).sum(axis=1).astype(np.uint32)
+
+
+def _properties(snap, res, eng, S, sample_rows=64):
+    P, N, G = snap.pods.n, snap.nodes.n, snap.groups.n
+    # order is a permutation, rank is monotone along it and dense
+    assert np.array_equal(np.sort(res.order), np.arange(P, dtype=np.uint32))
+    r_along = res.rank[res.order]
+    assert (np.diff(r_along.astype(np.int64)) >= 0).all() and (np.diff(r_along.astype(np.int64)) <= 1).all()
+    assert r_along[0] == 0
+    # Compare's leading key: priority never increases along the order
+    assert (np.diff(snap.pods.priority[res.order].astype(np.int64)) <= 0).all()
+    # admit bitmap <-> admit codes
+    bits = np.unpackbits(res.admit_bitmap.view(np.uint8), bitorder="little")[:G]
+    assert np.array_equal(bits.astype(bool), res.admit == S.ADMIT)
+    # new_denied only for groups with a NOT_ENOUGH pod, and every such group is flagged
+    ne = res.prefilter == S.PF_NOT_ENOUGH
+    flagged = np.zeros(G, bool)
+    flagged[snap.pods.gid[ne]] = True
+    assert np.array_equal(flagged, res.new_denied.astype(bool))
+    # Permit readiness recomputed from the per-pod outputs (core.go:303, uint32)
+    ok = (res.prefilter == S.PF_PASS) & (res.feasible_count > 0) & (snap.pods.gid >= 0)
+    contrib = np.bincount(snap.pods.gid[ok], minlength=G).astype(np.uint32)
+    in_round = np.bincount(snap.pods.gid[snap.pods.gid >= 0], minlength=G)
+    need = (snap.groups.min_member - snap.groups.scheduled).astype(np.uint32)
+    ready = (snap.groups.matched + contrib).astype(np.uint32) >= need
+    exp = np.where((in_round > 0) & (contrib == 0), S.UNSCHEDULABLE, np.where(ready, S.ADMIT, S.WAIT))
+    assert np.array_equal(exp.astype(np.uint8), res.admit)
+    # sampled rows of the matrices: bitmap popcount, score sign, best node
+    rows = np.linspace(0, P - 1, sample_rows).astype(int)
+    for p in rows:
+        w = eng.fit_rows(int(p), 1)
+        sc = eng.score_rows(int(p), 1)[0]
+        fit = np.unpackbits(w.view(np.uint8), bitorder="little")[:N].astype(bool)
+        assert fit.sum() == res.feasible_count[p]
+        assert ((sc >= 0) == fit).all() and (sc[~fit] == np.iinfo(np.int64).min).all()
+        if fit.any():
+            assert res.best_score[p] == sc.max() and res.best_node[p] == int(np.argmax(sc))
+        else:
+            assert res.best_node[p] == -1
+
+
+@pytest.mark.parametrize("cfg", [3, 4])
+def test_full_size_decisions_and_properties(pkg, oracle, snapshot_mod, cfg):
+    S = snapshot_mod
+    snap = S.config(cfg)
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=True, score=True)
+    eng.upload(snap)
+    res = eng.evaluate()
+    _properties(snap, res, eng, S)
+    orc = oracle.round(snap, want_bitmap=False, want_score=False, threads=0)
+    for f in ("prefilter", "feasible_count", "best_node", "best_score", "admit", "admit_bitmap", "new_denied",
+              "order", "rank"):
+        np.testing.assert_array_equal(getattr(res, f), getattr(orc, f), err_msg=f)
+    assert res.max_group == orc.max_group
+    # a slice of the matrices against the oracle
+    sub = S.Snapshot(snap.nodes, snap.pods.take(np.arange(2000, 2300)), snap.groups)
+    o2 = oracle.round(sub, want_bitmap=True, want_score=True, want_sort=False)
+    np.testing.assert_array_equal(eng.fit_rows(2000, 300), o2.fit_bitmap)
+    np.testing.assert_array_equal(eng.score_rows(2000, 300), o2.score)
+    eng.close()
+
+
+def test_cfg5_shard_properties(pkg, oracle, snapshot_mod):
+    # config #5 is 1M pods / 50k nodes over 8 GPUs: one rank's shard (125k pods, 9 lanes) on one GPU
+    S = snapshot_mod
+    snap = S.config(5, 0.125)
+    snap.nodes = S.config(5, 0.25).nodes      # 12.5k nodes keep the score matrix at 12.5 GB
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=True, score=True)
+    eng.upload(snap)
+    res = eng.evaluate()
+    _properties(snap, res, eng, S, sample_rows=24)
+    sub = S.Snapshot(snap.nodes, snap.pods.take(np.arange(500, 700)), snap.groups)
+    o2 = oracle.round(sub, want_bitmap=True, want_score=True, want_sort=False)
+    np.testing.assert_array_equal(eng.fit_rows(500, 200), o2.fit_bitmap)
+    np.testing.assert_array_equal(eng.score_rows(500, 200), o2.score)
+    np.testing.assert_array_equal(res.feasible_count[500:700], o2.feasible_count)
+    eng.close()
