@@ -11,9 +11,11 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -127,7 +129,18 @@ struct ClassIndex {
   size_t size() const { return keys.size(); }
 };
 
-inline int host_threads() { return std::max(1, std::min(omp_get_max_threads(), 16)); }
+// Threads for the host packing passes.  Not taken from OMP_NUM_THREADS (launchers such as torchrun
+// pin it to 1): BS_HOST_THREADS if set, else the cores divided by the GPUs of the box, at most 8.
+inline int host_threads() {
+  static int n = [] {
+    if (const char* s = getenv("BS_HOST_THREADS")) return std::max(1, atoi(s));
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    const int hw = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(8, hw / ndev));
+  }();
+  return n;
+}
 
 // out[i] = id of key_of(i) in `global` (ids stable across calls: the index only grows).
 // Two parallel passes: thread-local indices, a small sequential merge, then a remap.
