@@ -1,0 +1,552 @@
+// plugin.cpp — snapshot packer + BatchSchedulingPlugin mirror (see plugin.hpp).
+#include "plugin.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <set>
+
+namespace bsched {
+
+namespace {
+
+constexpr int64_t kSecond = 1000000000ll;
+constexpr int kLaneCpu = 0, kLaneMem = 1, kLaneEph = 2, kLanePods = 3;
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+bool has_prefix(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
+
+__int128 ipow(__int128 b, int e) {
+  __int128 r = 1;
+  while (e-- > 0) r *= b;
+  return r;
+}
+
+}  // namespace
+
+// resource.Quantity textual form: [sign]digits[.digits][suffix]; suffix in
+//   binarySI   Ki Mi Gi Ti Pi Ei
+//   decimalSI  n u m "" k M G T P E
+//   exponent   e<int> | E<int>
+// (k8s.io/apimachinery v0.17.5 pkg/api/resource/quantity.go, restated: source absent).
+bool ParseQuantityMilli(const std::string& s, __int128* milli) {
+  size_t i = 0;
+  bool neg = false;
+  if (i < s.size() && (s[i] == '+' || s[i] == '-')) neg = s[i++] == '-';
+  __int128 mant = 0;
+  int frac_digits = 0, digits = 0;
+  while (i < s.size() && s[i] >= '0' && s[i] <= '9') { mant = mant * 10 + (s[i++] - '0'); if (++digits > 30) return false; }
+  if (i < s.size() && s[i] == '.') {
+    ++i;
+    while (i < s.size() && s[i] >= '0' && s[i] <= '9') {
+      mant = mant * 10 + (s[i++] - '0');
+      ++frac_digits;
+      if (++digits > 30) return false;
+    }
+  }
+  if (digits == 0) return false;
+  const std::string suf = s.substr(i);
+  __int128 num = 1, den = 1;
+  if (suf.empty()) {
+  } else if (suf == "Ki") num = (__int128)1 << 10;
+  else if (suf == "Mi") num = (__int128)1 << 20;
+  else if (suf == "Gi") num = (__int128)1 << 30;
+  else if (suf == "Ti") num = (__int128)1 << 40;
+  else if (suf == "Pi") num = (__int128)1 << 50;
+  else if (suf == "Ei") num = (__int128)1 << 60;
+  else if (suf == "n") den = 1000000000;
+  else if (suf == "u") den = 1000000;
+  else if (suf == "m") den = 1000;
+  else if (suf == "k") num = 1000;
+  else if (suf == "M") num = 1000000;
+  else if (suf == "G") num = 1000000000;
+  else if (suf == "T") num = ipow(10, 12);
+  else if (suf == "P") num = ipow(10, 15);
+  else if (suf == "E") num = ipow(10, 18);
+  else if ((suf[0] == 'e' || suf[0] == 'E') && suf.size() > 1) {
+    size_t j = 1;
+    bool eneg = false;
+    if (suf[j] == '+' || suf[j] == '-') eneg = suf[j++] == '-';
+    if (j >= suf.size()) return false;
+    int ex = 0;
+    for (; j < suf.size(); ++j) {
+      if (suf[j] < '0' || suf[j] > '9') return false;
+      ex = ex * 10 + (suf[j] - '0');
+      if (ex > 24) return false;
+    }
+    if (eneg) den = ipow(10, ex); else num = ipow(10, ex);
+  } else {
+    return false;
+  }
+  den *= ipow(10, frac_digits);
+  const __int128 n = mant * num * 1000;
+  __int128 q = n / den;
+  if (n % den != 0) q += 1;  // Quantity rounds up (away from zero)
+  *milli = neg ? -q : q;
+  return true;
+}
+
+bool QuantityMilliValue(const std::string& s, int64_t* out) {
+  __int128 m;
+  if (!ParseQuantityMilli(s, &m)) return false;
+  if (m > (__int128)INT64_MAX || m < (__int128)INT64_MIN) return false;
+  *out = (int64_t)m;
+  return true;
+}
+
+bool QuantityValue(const std::string& s, int64_t* out) {
+  __int128 m;
+  if (!ParseQuantityMilli(s, &m)) return false;
+  const bool neg = m < 0;
+  __int128 a = neg ? -m : m;
+  __int128 v = a / 1000 + (a % 1000 != 0 ? 1 : 0);
+  if (v > (__int128)INT64_MAX) return false;
+  *out = neg ? -(int64_t)v : (int64_t)v;
+  return true;
+}
+
+// v1helper.IsScalarResourceName (k8s v1.17.5, restated): extended || hugepages- || prefixed native
+// ("kubernetes.io/") || attachable-volumes-.  Extended: not native (has a '/', no "kubernetes.io/")
+// and not prefixed "requests.".
+bool IsScalarResourceName(const std::string& name) {
+  if (has_prefix(name, "hugepages-") || has_prefix(name, "attachable-volumes-")) return true;
+  if (name.find("kubernetes.io/") != std::string::npos) return true;
+  const bool native = name.find('/') == std::string::npos;
+  if (!native && !has_prefix(name, "requests.")) return true;
+  return false;
+}
+
+bs_node_table PackedSnapshot::node_table() const {
+  bs_node_table t{};
+  t.n_nodes = n_nodes; t.n_lanes = lanes;
+  t.alloc = alloc.data(); t.requested = requested.data(); t.pod_count = pod_count.data();
+  t.alloc_present = alloc_present.data(); t.req_present = req_present.data();
+  t.label_mask = label_mask.data(); t.taint_mask = taint_mask.data(); t.flags = node_flags.data();
+  return t;
+}
+bs_pod_table PackedSnapshot::pod_table() const {
+  bs_pod_table t{};
+  t.n_pods = n_pods; t.n_lanes = lanes;
+  t.req = req.data(); t.req_present = pod_req_present.data(); t.gid = gid.data();
+  t.sel_mask = sel_mask.data(); t.tol_mask = tol_mask.data(); t.priority = priority.data();
+  t.ts_ns = ts_ns.data(); t.flags = pod_flags.data();
+  return t;
+}
+bs_group_table PackedSnapshot::group_table() const {
+  bs_group_table t{};
+  t.n_groups = n_groups; t.n_lanes = lanes;
+  t.min_member = min_member.data(); t.scheduled = scheduled.data(); t.matched = matched.data();
+  t.flags = group_flags.data(); t.min_res = min_res.data(); t.min_res_present = min_res_present.data();
+  t.rep_sel = rep_sel.data(); t.rep_tol = rep_tol.data(); t.creation_ns = creation_ns.data();
+  t.name_rank = name_rank.data();
+  return t;
+}
+
+namespace {
+
+struct LaneTable {
+  std::vector<std::string> scalars;
+  std::unordered_map<std::string, uint32_t> lane_of;
+  bool overflow = false;
+  int lane(const std::string& name, bool create) {
+    if (name == "cpu") return kLaneCpu;
+    if (name == "memory") return kLaneMem;
+    if (name == "ephemeral-storage") return kLaneEph;
+    if (name == "pods") return kLanePods;
+    if (!IsScalarResourceName(name)) return -1;  // Resource.Add ignores it
+    auto it = lane_of.find(name);
+    if (it != lane_of.end()) return (int)it->second;
+    if (!create) return -1;
+    if (BS_FIXED_LANES + scalars.size() >= BS_MAX_LANES) { overflow = true; return -1; }
+    const uint32_t l = BS_FIXED_LANES + (uint32_t)scalars.size();
+    scalars.push_back(name);
+    lane_of.emplace(name, l);
+    return (int)l;
+  }
+  void scan(const ResourceList& rl) { for (auto& kv : rl) lane(kv.first, true); }
+};
+
+// nodeinfo.Resource.Add(rl): v[lane] += quantity (cpu in milli), scalar keys become present
+bool add_list(LaneTable& lt, const ResourceList& rl, int64_t* v, uint32_t* present) {
+  for (auto& kv : rl) {
+    const int l = lt.lane(kv.first, false);
+    if (l < 0) continue;
+    int64_t q;
+    if (l == kLaneCpu ? !QuantityMilliValue(kv.second, &q) : !QuantityValue(kv.second, &q)) return false;
+    v[l] += q;
+    if (l >= (int)BS_FIXED_LANES) *present |= 1u << l;
+  }
+  return true;
+}
+
+const ResourceList& container_demand(const Container& c) { return c.has_limits ? c.limits : c.requests; }  // core.go:765-769
+
+// toleration.ToleratesTaint (k8s v1.17.5 api/core/v1/toleration.go, restated)
+bool tolerates(const Toleration& t, const Taint& taint) {
+  if (!t.effect.empty() && t.effect != taint.effect) return false;
+  if (!t.key.empty() && t.key != taint.key) return false;
+  if (t.op.empty() || t.op == "Equal") return t.value == taint.value;
+  if (t.op == "Exists") return true;
+  return false;
+}
+
+std::string joined_sorted(std::vector<std::string> v) {
+  std::sort(v.begin(), v.end());  // sortkeys.Strings (core.go:498,507)
+  std::string s;
+  for (size_t i = 0; i < v.size(); ++i) { if (i) s += ","; s += v[i]; }
+  return s;
+}
+
+struct PackGroupIn {
+  const PodGroup* pg;
+  uint32_t matched;
+  uint8_t flags;        // BS_GROUP_SCHEDULED | BS_GROUP_HAS_POD | BS_GROUP_DENIED (HAS_MINRES derived)
+  const Pod* rep_pod;   // pgs.Pod or nullptr
+};
+
+Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector<const Pod*>& pending,
+                 const std::vector<PackGroupIn>& groups, const std::vector<uint8_t>& pod_flags_in,
+                 int64_t default_wait_ns, PackedSnapshot* out) {
+  Status bad{BS_CODE_ERROR, ""};
+  PackedSnapshot& ps = *out;
+  ps = PackedSnapshot();
+  const uint32_t N = (uint32_t)snapshot.size(), P = (uint32_t)pending.size(), G = (uint32_t)groups.size();
+  // ---- lanes: scalar resources in first-seen order (nodes, groups, pods)
+  LaneTable lt;
+  for (auto* ni : snapshot) {
+    if (!ni) continue;
+    if (ni->node) lt.scan(ni->node->allocatable);
+    lt.scan(ni->requested);
+  }
+  for (auto& g : groups) if (g.pg->has_min_resources) lt.scan(g.pg->min_resources);
+  for (auto* p : pending) for (auto& c : p->containers) lt.scan(container_demand(c));
+  for (auto& g : groups) if (g.rep_pod) for (auto& c : g.rep_pod->containers) lt.scan(container_demand(c));
+  if (lt.overflow) { bad.message = "more than 12 scalar resources"; return bad; }
+  const uint32_t L = BS_FIXED_LANES + (uint32_t)lt.scalars.size();
+  ps.lanes = L;
+  ps.scalar_names = lt.scalars;
+  ps.n_nodes = N; ps.n_pods = P; ps.n_groups = G;
+
+  // ---- selector pairs and taints -> bits
+  std::map<std::pair<std::string, std::string>, int> sel_bit;
+  auto scan_sel = [&](const Pod* p) { for (auto& kv : p->node_selector) sel_bit.emplace(kv, 0); };
+  for (auto* p : pending) scan_sel(p);
+  for (auto& g : groups) if (g.rep_pod) scan_sel(g.rep_pod);
+  if (sel_bit.size() > 64) { bad.message = "more than 64 distinct nodeSelector pairs in one round"; return bad; }
+  { int b = 0; for (auto& kv : sel_bit) kv.second = b++; }
+  std::vector<Taint> taints;
+  auto taint_bit = [&](const Taint& t) -> int {
+    for (size_t i = 0; i < taints.size(); ++i)
+      if (taints[i].key == t.key && taints[i].value == t.value && taints[i].effect == t.effect) return (int)i;
+    taints.push_back(t);
+    return (int)taints.size() - 1;
+  };
+  // ---- nodes
+  ps.alloc.assign((size_t)L * N, 0); ps.requested.assign((size_t)L * N, 0);
+  ps.pod_count.assign(N, 0); ps.alloc_present.assign(N, 0); ps.req_present.assign(N, 0);
+  ps.label_mask.assign(N, 0); ps.taint_mask.assign(N, 0); ps.node_flags.assign(N, 0);
+  std::vector<int64_t> tmp(L);
+  for (uint32_t i = 0; i < N; ++i) {
+    const NodeInfo* ni = snapshot[i];
+    if (!ni) { ps.node_flags[i] = BS_NODE_NIL; continue; }              // core.go:606
+    if (!ni->node) ps.node_flags[i] |= BS_NODE_NO_NODE;                 // core.go:610
+    if (ni->taints_error) ps.node_flags[i] |= BS_NODE_TAINTS_ERR;       // core.go:639
+    ps.pod_count[i] = ni->num_pods;
+    uint32_t pres = 0;
+    std::fill(tmp.begin(), tmp.end(), 0);
+    if (!add_list(lt, ni->requested, tmp.data(), &pres)) { bad.message = "bad quantity in requested"; return bad; }
+    for (uint32_t d = 0; d < L; ++d) ps.requested[(size_t)d * N + i] = tmp[d];
+    ps.req_present[i] = pres;
+    if (!ni->node) continue;
+    const Node& nd = *ni->node;
+    if (nd.unschedulable) ps.node_flags[i] |= BS_NODE_UNSCHEDULABLE;    // core.go:615
+    pres = 0;
+    std::fill(tmp.begin(), tmp.end(), 0);
+    if (!add_list(lt, nd.allocatable, tmp.data(), &pres)) { bad.message = "bad quantity in allocatable"; return bad; }
+    for (uint32_t d = 0; d < L; ++d) ps.alloc[(size_t)d * N + i] = tmp[d];
+    ps.alloc_present[i] = pres;
+    for (auto& kv : sel_bit) {
+      auto it = nd.labels.find(kv.first.first);
+      if (it != nd.labels.end() && it->second == kv.first.second) ps.label_mask[i] |= 1ull << kv.second;
+    }
+    for (auto& t : nd.taints) {
+      if (t.effect != "NoSchedule" && t.effect != "NoExecute") continue;  // PodToleratesNodeTaints filter
+      const int b = taint_bit(t);
+      if (b >= 64) { bad.message = "more than 64 distinct taints in one round"; return bad; }
+      ps.taint_mask[i] |= 1ull << b;
+    }
+  }
+  auto pod_masks = [&](const Pod& p, uint64_t* sel, uint64_t* tol) {
+    *sel = 0; *tol = 0;
+    for (auto& kv : p.node_selector) *sel |= 1ull << sel_bit[kv];
+    for (size_t b = 0; b < taints.size(); ++b)
+      for (auto& t : p.tolerations)
+        if (tolerates(t, taints[b])) { *tol |= 1ull << b; break; }
+  };
+  auto pod_demand = [&](const Pod& p, int64_t* v, uint32_t* pres) -> bool {  // getPodResourceRequire core.go:761-772
+    for (auto& c : p.containers)
+      if (!add_list(lt, container_demand(c), v, pres)) return false;
+    return true;
+  };
+  // ---- groups
+  std::unordered_map<std::string, uint32_t> gindex;
+  ps.min_member.assign(G, 0); ps.scheduled.assign(G, 0); ps.matched.assign(G, 0); ps.group_flags.assign(G, 0);
+  ps.min_res.assign((size_t)L * G, 0); ps.min_res_present.assign(G, 0); ps.rep_sel.assign(G, 0);
+  ps.rep_tol.assign(G, 0); ps.creation_ns.assign(G, 0); ps.name_rank.assign(G, 0); ps.wait_ns.assign(G, 0);
+  std::set<std::string> names;
+  for (auto& g : groups) names.insert(g.pg->name);
+  std::unordered_map<std::string, uint32_t> rank_of;
+  { uint32_t r = 0; for (auto& n : names) rank_of[n] = r++; }  // byte-wise ascending (Go string compare)
+  for (uint32_t g = 0; g < G; ++g) {
+    const PodGroup& pg = *groups[g].pg;
+    gindex[pg.ns + "/" + pg.name] = g;
+    ps.min_member[g] = pg.min_member;
+    ps.scheduled[g] = pg.scheduled;
+    ps.matched[g] = groups[g].matched;
+    ps.group_flags[g] = groups[g].flags & (BS_GROUP_SCHEDULED | BS_GROUP_HAS_POD | BS_GROUP_DENIED);
+    ps.creation_ns[g] = pg.creation_ns;
+    ps.name_rank[g] = rank_of[pg.name];
+    // util.GetWaitTimeDuration (k8s.go:82-91): Spec.MaxScheduleTime wins, else the plugin default
+    ps.wait_ns[g] = pg.max_schedule_time_ns >= 0 ? pg.max_schedule_time_ns : default_wait_ns;
+    if (pg.has_min_resources) {
+      ps.group_flags[g] |= BS_GROUP_HAS_MINRES;
+      uint32_t pres = 0;
+      std::fill(tmp.begin(), tmp.end(), 0);
+      if (!add_list(lt, pg.min_resources, tmp.data(), &pres)) { bad.message = "bad quantity in MinResources"; return bad; }
+      for (uint32_t d = 0; d < L; ++d) ps.min_res[(size_t)d * G + g] = tmp[d];
+      ps.min_res_present[g] = pres;
+    }
+    if (groups[g].rep_pod) {
+      ps.group_flags[g] |= BS_GROUP_HAS_POD;
+      pod_masks(*groups[g].rep_pod, &ps.rep_sel[g], &ps.rep_tol[g]);
+    }
+  }
+  // ---- pods (arrival order); occupancy follows fillOccupiedObj sequentially (core.go:494-511)
+  ps.req.assign((size_t)L * P, 0); ps.pod_req_present.assign(P, 0); ps.gid.assign(P, BS_GID_NONE);
+  ps.sel_mask.assign(P, 0); ps.tol_mask.assign(P, 0); ps.priority.assign(P, 0); ps.ts_ns.assign(P, 0);
+  ps.pod_flags.assign(P, 0);
+  std::vector<std::string> occupied(G);
+  for (uint32_t g = 0; g < G; ++g) occupied[g] = groups[g].pg->occupied_by;
+  for (uint32_t i = 0; i < P; ++i) {
+    const Pod& p = *pending[i];
+    uint32_t pres = 0;
+    std::fill(tmp.begin(), tmp.end(), 0);
+    if (!pod_demand(p, tmp.data(), &pres)) { bad.message = "bad quantity in pod " + p.name; return bad; }
+    for (uint32_t d = 0; d < L; ++d) ps.req[(size_t)d * P + i] = tmp[d];
+    ps.pod_req_present[i] = pres;
+    pod_masks(p, &ps.sel_mask[i], &ps.tol_mask[i]);
+    ps.priority[i] = p.priority;
+    ps.ts_ns[i] = p.queue_ts_ns;
+    uint8_t fl = i < pod_flags_in.size() ? pod_flags_in[i] : 0;
+    auto lab = p.labels.find(kPodGroupLabel);                          // util.VerifyPodLabelSatisfied k8s.go:62-70
+    if (lab == p.labels.end() || lab->second.empty()) { ps.pod_flags[i] = fl; continue; }
+    auto gi = gindex.find(p.ns + "/" + lab->second);
+    if (gi == gindex.end()) { ps.gid[i] = BS_GID_MISSING; ps.pod_flags[i] = fl | BS_POD_LISTER_MISS; continue; }
+    const uint32_t g = gi->second;
+    ps.gid[i] = (int32_t)g;
+    const bool reaches = !(fl & BS_POD_PERMITTED_RECENTLY) && !(ps.group_flags[g] & BS_GROUP_DENIED);
+    if (reaches) {
+      const std::string refs = joined_sorted(p.owner_uids);
+      if (occupied[g].empty()) {
+        if (!p.owner_uids.empty()) occupied[g] = refs;                 // core.go:496-500
+      } else if (p.owner_uids.empty()) fl |= BS_POD_OCC_NOREFS;        // core.go:504-506
+      else if (refs != occupied[g]) fl |= BS_POD_OCC_MISMATCH;         // core.go:507-510
+    }
+    ps.pod_flags[i] = fl;
+  }
+  return Status{};
+}
+
+}  // namespace
+
+Status BatchSchedulingPlugin::Pack(const std::vector<const NodeInfo*>& snapshot, const std::vector<const Pod*>& pending,
+                                   const std::vector<PodGroup>& groups, const std::vector<uint32_t>& matched,
+                                   const std::vector<uint8_t>& extra_group_flags,
+                                   const std::vector<uint8_t>& extra_pod_flags, int64_t default_wait_ns,
+                                   PackedSnapshot* out) {
+  std::vector<PackGroupIn> gi(groups.size());
+  for (size_t g = 0; g < groups.size(); ++g)
+    gi[g] = PackGroupIn{&groups[g], g < matched.size() ? matched[g] : 0u,
+                        g < extra_group_flags.size() ? extra_group_flags[g] : (uint8_t)0, nullptr};
+  return pack_impl(snapshot, pending, gi, extra_pod_flags, default_wait_ns, out);
+}
+
+BatchSchedulingPlugin::BatchSchedulingPlugin(int device, int64_t max_schedule_time_ns, uint32_t out_flags)
+    : max_schedule_time_ns_(max_schedule_time_ns) {
+  (void)device;
+  (void)out_flags;
+  device_ = device;
+  out_flags_ = out_flags;
+}
+
+BatchSchedulingPlugin::~BatchSchedulingPlugin() {
+  if (eng_) bs_destroy(eng_);
+}
+
+void BatchSchedulingPlugin::SetPodGroup(const PodGroup& pg) {
+  GroupState& gs = groups_[pg.ns + "/" + pg.name];
+  gs.pg = pg;
+}
+
+void BatchSchedulingPlugin::DeletePodGroup(const std::string& ns_name) { groups_.erase(ns_name); }
+
+void BatchSchedulingPlugin::AddToDenyCache(const std::string& ns_name, int64_t now_ns) {
+  auto it = deny_expiry_.find(ns_name);
+  if (it != deny_expiry_.end() && it->second > now_ns) return;  // go-cache Add: no-op while present (Q11)
+  deny_expiry_[ns_name] = now_ns + 20 * kSecond;                 // core.go:424
+}
+
+void BatchSchedulingPlugin::AddPermitted(const std::string& uid, int64_t now_ns) {
+  auto it = permitted_expiry_.find(uid);
+  if (it != permitted_expiry_.end() && it->second > now_ns) return;
+  permitted_expiry_[uid] = now_ns + 2 * kSecond;                 // core.go:188
+}
+
+int BatchSchedulingPlugin::group_index(const std::string& ns_name) const {
+  for (size_t i = 0; i < group_names_.size(); ++i)
+    if (group_names_[i] == ns_name) return (int)i;
+  return -1;
+}
+
+Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& snapshot,
+                                         const std::vector<const Pod*>& pending, int64_t now_ns) {
+  const double t0 = now_ms();
+  now_ns_ = now_ns;
+  // TTL expiry (go-cache semantics: an entry is gone once now >= expiry)
+  for (auto it = deny_expiry_.begin(); it != deny_expiry_.end();) it = it->second <= now_ns ? deny_expiry_.erase(it) : std::next(it);
+  for (auto it = permitted_expiry_.begin(); it != permitted_expiry_.end();) it = it->second <= now_ns ? permitted_expiry_.erase(it) : std::next(it);
+  std::vector<PackGroupIn> gin;
+  group_names_.clear();
+  for (auto& kv : groups_) {
+    GroupState& gs = kv.second;
+    for (auto it = gs.matched_uid_expiry.begin(); it != gs.matched_uid_expiry.end();)
+      it = it->second <= now_ns ? gs.matched_uid_expiry.erase(it) : std::next(it);
+    uint8_t fl = 0;
+    if (gs.scheduled_flag) fl |= BS_GROUP_SCHEDULED;
+    if (deny_expiry_.count(kv.first)) fl |= BS_GROUP_DENIED;
+    gin.push_back(PackGroupIn{&gs.pg, (uint32_t)gs.matched_uid_expiry.size(), fl, gs.has_pod ? &gs.rep_pod : nullptr});
+    group_names_.push_back(kv.first);
+  }
+  std::vector<uint8_t> pflags(pending.size(), 0);
+  pod_row_.clear();
+  for (size_t i = 0; i < pending.size(); ++i) {
+    pod_row_[pending[i]->uid] = (uint32_t)i;
+    if (permitted_expiry_.count(pending[i]->uid)) pflags[i] |= BS_POD_PERMITTED_RECENTLY;
+  }
+  node_row_.clear();
+  for (size_t i = 0; i < snapshot.size(); ++i)
+    if (snapshot[i] && snapshot[i]->node) node_row_[snapshot[i]->node->name] = (uint32_t)i;
+  Status st = pack_impl(snapshot, pending, gin, pflags, max_schedule_time_ns_, &packed_);
+  if (!st.ok()) return st;
+  last_pack_ms_ = now_ms() - t0;
+
+  const double t1 = now_ms();
+  auto fail = [&](int rc) {
+    Status s{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+    if (eng_) s.message += std::string(" (") + bs_last_error(eng_) + ")";
+    return s;
+  };
+  if (eng_ && eng_lanes_ != packed_.lanes) { bs_destroy(eng_); eng_ = nullptr; }
+  if (!eng_) {
+    bs_config cfg{device_, packed_.lanes, out_flags_, 0};
+    int rc = bs_create(&cfg, &eng_);
+    if (rc) { eng_ = nullptr; return fail(rc); }
+    eng_lanes_ = packed_.lanes;
+  }
+  bs_node_table nt = packed_.node_table();
+  bs_group_table gt = packed_.group_table();
+  bs_pod_table pt = packed_.pod_table();
+  int rc;
+  if ((rc = bs_upload_nodes(eng_, &nt))) return fail(rc);
+  if ((rc = bs_upload_groups(eng_, &gt))) return fail(rc);
+  if ((rc = bs_upload_pods(eng_, &pt))) return fail(rc);
+  if ((rc = bs_set_wait_time(eng_, max_schedule_time_ns_, packed_.wait_ns.data(), packed_.n_groups))) return fail(rc);
+  const uint32_t P = packed_.n_pods, G = packed_.n_groups;
+  prefilter_.assign(P, 0); feasible_.assign(P, 0); best_node_.assign(P, -1); order_.assign(P, 0); rank_.assign(P, 0);
+  admit_.assign(G, 0); new_denied_.assign(G, 0);
+  bs_results r{};
+  r.prefilter = prefilter_.data(); r.feasible_count = feasible_.data(); r.best_node = best_node_.data();
+  r.admit = admit_.data(); r.new_denied = new_denied_.data(); r.order = order_.data(); r.rank = rank_.data();
+  if ((rc = bs_evaluate(eng_, &r))) return fail(rc);
+  last_device_ms_ = now_ms() - t1;
+
+  // side effects the reference performs while it walks the pods:
+  //  * AddToDenyCache for every group refused with "cluster resource not enough" (core.go:142,163)
+  //  * fillOccupiedObj: first reaching pod becomes pgs.Pod, supplies MinResources / OccupiedBy
+  for (uint32_t g = 0; g < G; ++g)
+    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns);
+  for (uint32_t i = 0; i < P; ++i) {
+    const int32_t g = packed_.gid[i];
+    if (g < 0) continue;
+    if (packed_.pod_flags[i] & BS_POD_PERMITTED_RECENTLY) continue;
+    if (packed_.group_flags[g] & BS_GROUP_DENIED) continue;
+    GroupState& gs = groups_[group_names_[g]];
+    const Pod& p = *pending[i];
+    if (!gs.has_pod) { gs.has_pod = true; gs.rep_pod = p; }                    // core.go:486-488
+    if (!gs.pg.has_min_resources) {                                            // core.go:489-493
+      gs.pg.has_min_resources = true;
+      gs.pg.min_resources.clear();
+      for (auto& c : p.containers)
+        for (auto& kv : container_demand(c)) gs.pg.min_resources.push_back(kv);
+    }
+    if (gs.pg.occupied_by.empty() && !p.owner_uids.empty()) gs.pg.occupied_by = joined_sorted(p.owner_uids);  // :496-500
+  }
+  return Status{};
+}
+
+Status BatchSchedulingPlugin::PreFilter(const Pod& pod) {
+  auto it = pod_row_.find(pod.uid);
+  if (it == pod_row_.end()) return Status{BS_CODE_ERROR, "pod is not part of the current round"};
+  bs_status st{};
+  int rc = bs_prefilter(eng_, it->second, &st);
+  if (rc) return Status{BS_CODE_ERROR, bs_strerror(rc)};
+  if (st.reason == BS_PF_PASS) return Status{};                                 // batchscheduler.go:107
+  std::string ns_name, occ;
+  auto lab = pod.labels.find(kPodGroupLabel);
+  if (lab != pod.labels.end()) ns_name = pod.ns + "/" + lab->second;            // fullName core.go:93
+  if (st.group >= 0) occ = groups_[group_names_[st.group]].pg.occupied_by;
+  char buf[512];
+  bs_format_message(&st, ns_name.c_str(), occ.c_str(), buf, sizeof(buf));
+  return Status{BS_CODE_UNSCHEDULABLE, buf};                                    // batchscheduler.go:104-106
+}
+
+std::pair<Status, int64_t> BatchSchedulingPlugin::Permit(const Pod& pod, const std::string& node_name,
+                                                         bool* start_signal) {
+  if (start_signal) *start_signal = false;
+  auto it = pod_row_.find(pod.uid);
+  auto nt = node_row_.find(node_name);
+  if (it == pod_row_.end() || nt == node_row_.end())
+    return {Status{BS_CODE_ERROR, "pod or node is not part of the current round"}, 0};
+  bs_permit_result r{};
+  int rc = bs_permit(eng_, it->second, nt->second, &r);
+  if (rc) return {Status{BS_CODE_ERROR, bs_strerror(rc)}, 0};
+  if (r.code == BS_CODE_UNSCHEDULABLE) {
+    auto lab = pod.labels.find(kPodGroupLabel);
+    return {Status{BS_CODE_UNSCHEDULABLE, "can not found pod group: " + (lab != pod.labels.end() ? lab->second : std::string())},
+            r.wait_ns};                                                          // core.go:276, batchscheduler.go:194-195
+  }
+  if (r.group >= 0) {
+    // bookkeeping of core.go:284-300 for the NEXT round's carried-in matched count
+    GroupState& gs = groups_[group_names_[r.group]];
+    const std::string pod_name = pod.ns + "/" + pod.name;
+    const int64_t ttl = r.wait_ns - kSecond;                                     // waitTime (without the +1 s)
+    gs.matched_uid_expiry[pod.uid] = now_ns_ + (ttl > 0 ? ttl : 60 * kSecond);   // go-cache default 1 min (Q12, controller.go:317)
+    auto old = gs.pod_name_uid.find(pod_name);
+    if (old != gs.pod_name_uid.end()) gs.matched_uid_expiry.erase(old->second);  // core.go:293-296 (quirk Q7)
+    gs.pod_name_uid[pod_name] = pod.uid;                                         // core.go:300
+    if (r.ready) gs.scheduled_flag = true;                                       // core.go:305
+  }
+  if (start_signal) *start_signal = r.start_signal != 0;                         // batchscheduler.go:197-199
+  return {Status{r.code, ""}, r.wait_ns};
+}
+
+bool BatchSchedulingPlugin::Less(const Pod& a, const Pod& b) {
+  auto ia = pod_row_.find(a.uid), ib = pod_row_.find(b.uid);
+  if (ia == pod_row_.end() || ib == pod_row_.end()) return false;
+  return bs_less(eng_, ia->second, ib->second) == 1;
+}
+
+}  // namespace bsched

@@ -1,0 +1,196 @@
+// plugin.hpp — C++ host mirror of the reference's plugin surface for the hot path.
+//
+// The reference is Go; this image has no Go toolchain, so (per the tier rules) the host side above
+// the C ABI is C++ for a compiled reference: the same names, argument meaning and status / error
+// behaviour as
+//   batchSchedulingPlugin.PreFilter / Permit / Less   pkg/scheduler/batch/batchscheduler.go:102,165,214
+//   ScheduleOperation.AddToDenyCache                  pkg/scheduler/core/core.go:423
+//   PGStatusCache.Set / Delete                        pkg/scheduler/cache/cache.go:94-120
+// plus the SNAPSHOT PACKER: NodeInfo / Pod / PodGroup objects -> the SoA
+// tables of include/bsched.h (resource.Quantity -> int64 lanes, labels / taints / selectors /
+// tolerations -> bit sets, label -> group index, bare-name rank).
+//
+// Everything here is packing and bookkeeping; every decision comes from the CUDA engine through
+// the C ABI (bs_evaluate, bs_prefilter, bs_permit, bs_less).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/bsched.h"
+
+namespace bsched {
+
+// v1.ResourceList with quantities in their textual form ("1", "900m", "140Mi", "1e3")
+using ResourceList = std::vector<std::pair<std::string, std::string>>;
+
+constexpr const char* kPodGroupLabel = "group.batch.scheduler.tencent.com";  // pkg/util/types.go:25
+
+struct Container {
+  bool has_limits = false;  // Resources.Limits != nil  (core.go:765)
+  ResourceList limits;
+  ResourceList requests;
+};
+struct Toleration {
+  std::string key, op /* "", "Equal", "Exists" */, value, effect;
+};
+struct Taint {
+  std::string key, value, effect;  // effect: NoSchedule | PreferNoSchedule | NoExecute
+};
+struct Pod {
+  std::string ns, name, uid;
+  std::map<std::string, std::string> labels;
+  std::map<std::string, std::string> node_selector;
+  std::vector<Toleration> tolerations;
+  std::vector<Container> containers;
+  std::vector<std::string> owner_uids;  // OwnerReferences[].UID (core.go:483-485)
+  int32_t priority = 0;                 // podutil.GetPodPriority
+  int64_t queue_ts_ns = 0;              // framework.PodInfo.Timestamp
+};
+struct Node {
+  std::string name;
+  std::map<std::string, std::string> labels;
+  std::vector<Taint> taints;
+  ResourceList allocatable;
+  bool unschedulable = false;
+};
+struct NodeInfo {          // k8s.io/kubernetes/pkg/scheduler/nodeinfo.NodeInfo, the fields core.go reads
+  const Node* node = nullptr;  // nullptr: info.Node() == nil (core.go:610)
+  ResourceList requested;      // info.RequestedResource()
+  int32_t num_pods = 0;        // len(info.Pods())
+  bool taints_error = false;   // info.Taints() returned an error (core.go:639)
+};
+struct PodGroup {          // pkg/apis/podgroup/v1/types.go:62-130 (fields on the path)
+  std::string ns, name;
+  uint32_t min_member = 0;
+  bool has_min_resources = false;
+  ResourceList min_resources;
+  int64_t max_schedule_time_ns = -1;  // Spec.MaxScheduleTime, <0 unset
+  uint32_t scheduled = 0;             // Status.Scheduled
+  std::string occupied_by;            // Status.OccupiedBy
+  int64_t creation_ns = 0;
+};
+
+struct Status {  // framework.Status
+  int code = BS_CODE_SUCCESS;
+  std::string message;
+  bool ok() const { return code == BS_CODE_SUCCESS; }
+};
+
+// resource.Quantity: exact parse of the textual form; value in units of 10^-3 (milli), rounded up
+// like Quantity.MilliValue(); Value() = ceil(milli / 1000).  Returns false on a malformed string.
+bool ParseQuantityMilli(const std::string& s, __int128* milli);
+bool QuantityValue(const std::string& s, int64_t* out);       // Quantity.Value()
+bool QuantityMilliValue(const std::string& s, int64_t* out);  // Quantity.MilliValue()
+bool IsScalarResourceName(const std::string& name);           // v1helper.IsScalarResourceName
+
+// The packed tables of one round (owning storage + the C-ABI views over it).
+struct PackedSnapshot {
+  uint32_t lanes = BS_FIXED_LANES;
+  std::vector<std::string> scalar_names;  // lane 4+k
+  // nodes
+  std::vector<int64_t> alloc, requested;
+  std::vector<int32_t> pod_count;
+  std::vector<uint32_t> alloc_present, req_present;
+  std::vector<uint64_t> label_mask, taint_mask;
+  std::vector<uint8_t> node_flags;
+  // pods
+  std::vector<int64_t> req;
+  std::vector<uint32_t> pod_req_present;
+  std::vector<int32_t> gid, priority;
+  std::vector<uint64_t> sel_mask, tol_mask;
+  std::vector<int64_t> ts_ns;
+  std::vector<uint8_t> pod_flags;
+  // groups
+  std::vector<uint32_t> min_member, scheduled, matched, min_res_present, name_rank;
+  std::vector<uint8_t> group_flags;
+  std::vector<int64_t> min_res, creation_ns, wait_ns;
+  std::vector<uint64_t> rep_sel, rep_tol;
+  uint32_t n_nodes = 0, n_pods = 0, n_groups = 0;
+
+  bs_node_table node_table() const;
+  bs_pod_table pod_table() const;
+  bs_group_table group_table() const;
+};
+
+class BatchSchedulingPlugin {
+ public:
+  // batch.New (batchscheduler.go:377): max_schedule_time from the plugin args (Configuration, :71-75)
+  BatchSchedulingPlugin(int device, int64_t max_schedule_time_ns, uint32_t out_flags = BS_OUT_FIT_BITMAP);
+  ~BatchSchedulingPlugin();
+  BatchSchedulingPlugin(const BatchSchedulingPlugin&) = delete;
+  BatchSchedulingPlugin& operator=(const BatchSchedulingPlugin&) = delete;
+  const std::string& init_error() const { return init_error_; }
+
+  // PGStatusCache.Set / Delete (cache.go:104-120), keyed by "namespace/name"
+  void SetPodGroup(const PodGroup& pg);
+  void DeletePodGroup(const std::string& ns_name);
+
+  // One scheduling round: pack the snapshot (list order preserved, core.go:597,604) and the pending
+  // pods (queue arrival order), upload, evaluate on the GPU, fetch.  now_ns drives TTL expiry.
+  Status BeginRound(const std::vector<const NodeInfo*>& snapshot, const std::vector<const Pod*>& pending,
+                    int64_t now_ns);
+
+  // batchSchedulingPlugin.PreFilter (batchscheduler.go:102-108)
+  Status PreFilter(const Pod& pod);
+  // batchSchedulingPlugin.Permit (batchscheduler.go:165-202): status + wait duration (ns)
+  std::pair<Status, int64_t> Permit(const Pod& pod, const std::string& node_name, bool* start_signal = nullptr);
+  // batchSchedulingPlugin.Less (batchscheduler.go:214-216)
+  bool Less(const Pod& a, const Pod& b);
+  // ScheduleOperation.AddToDenyCache (core.go:423-425): 20 s, Add semantics (no-op if present)
+  void AddToDenyCache(const std::string& ns_name, int64_t now_ns);
+  // lastPermittedPod.Add(uid, 2s) (core.go:188)
+  void AddPermitted(const std::string& uid, int64_t now_ns);
+
+  // results of the last round, by pending index
+  const PackedSnapshot& packed() const { return packed_; }
+  const std::vector<uint8_t>& prefilter_codes() const { return prefilter_; }
+  const std::vector<uint8_t>& admit_codes() const { return admit_; }
+  const std::vector<uint32_t>& queue_order() const { return order_; }
+  const std::vector<uint32_t>& feasible_counts() const { return feasible_; }
+  const std::vector<int32_t>& best_nodes() const { return best_node_; }
+  int group_index(const std::string& ns_name) const;
+  double last_pack_ms() const { return last_pack_ms_; }
+  double last_device_ms() const { return last_device_ms_; }
+  bs_engine* engine() const { return eng_; }
+
+  // the packer alone (no GPU): objects -> tables
+  static Status Pack(const std::vector<const NodeInfo*>& snapshot, const std::vector<const Pod*>& pending,
+                     const std::vector<PodGroup>& groups, const std::vector<uint32_t>& matched,
+                     const std::vector<uint8_t>& extra_group_flags, const std::vector<uint8_t>& extra_pod_flags,
+                     int64_t default_wait_ns, PackedSnapshot* out);
+
+ private:
+  struct GroupState {
+    PodGroup pg;
+    std::unordered_map<std::string, int64_t> matched_uid_expiry;   // MatchedPodNodes (TTL)
+    std::unordered_map<std::string, std::string> pod_name_uid;     // PodNameUIDs (name -> uid)
+    bool scheduled_flag = false;                                    // pgs.Scheduled (cache.go:66)
+    bool has_pod = false;                                           // pgs.Pod != nil
+    uint64_t rep_sel_pairs_hash = 0;
+    Pod rep_pod;                                                    // pgs.Pod
+  };
+  bs_engine* eng_ = nullptr;
+  int device_ = 0;
+  uint32_t out_flags_ = 0, eng_lanes_ = 0;
+  std::string init_error_;
+  int64_t max_schedule_time_ns_;
+  std::map<std::string, GroupState> groups_;                        // ordered: canonical table order
+  std::unordered_map<std::string, int64_t> deny_expiry_;            // lastDeniedPG
+  std::unordered_map<std::string, int64_t> permitted_expiry_;       // lastPermittedPod
+  // last round
+  PackedSnapshot packed_;
+  std::unordered_map<std::string, uint32_t> pod_row_;               // uid -> pending index
+  std::unordered_map<std::string, uint32_t> node_row_;              // node name -> snapshot index
+  std::vector<std::string> group_names_;                            // table index -> "ns/name"
+  std::vector<uint8_t> prefilter_, admit_, new_denied_;
+  std::vector<uint32_t> order_, rank_, feasible_;
+  std::vector<int32_t> best_node_;
+  int64_t now_ns_ = 0;
+  double last_pack_ms_ = 0, last_device_ms_ = 0;
+};
+
+}  // namespace bsched

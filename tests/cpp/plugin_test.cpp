@@ -1,0 +1,189 @@
+// plugin_test.cpp — drives the C++ host mirror (plugin.hpp) the way the reference's own test and
+// README drive the Go plugin; prints JSON for tests/test_plugin_cpp.py.
+//   quantity <s>...   : Quantity.Value / MilliValue of each argument             (CPU)
+//   pack_core_test    : core_test.go:27-115 objects -> packed tables             (CPU)
+//   readme            : README.md:76-188 resource race, pod by pod, on the GPU
+//   bench_pack N P G  : packer throughput on synthetic objects                   (CPU)
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../batch-scheduler_b200/csrc/plugin.hpp"
+
+using namespace bsched;
+
+template <class T>
+static void print_arr(const char* name, const std::vector<T>& v, bool last = false) {
+  printf("\"%s\": [", name);
+  for (size_t i = 0; i < v.size(); ++i) printf("%s%lld", i ? ", " : "", (long long)v[i]);
+  printf("]%s\n", last ? "" : ",");
+}
+
+static int cmd_quantity(int argc, char** argv) {
+  printf("{");
+  for (int i = 2; i < argc; ++i) {
+    int64_t v = 0, m = 0;
+    const bool ok = QuantityValue(argv[i], &v) && QuantityMilliValue(argv[i], &m);
+    printf("%s\"%s\": [%d, %lld, %lld]", i > 2 ? ", " : "", argv[i], ok ? 1 : 0, (long long)v, (long long)m);
+  }
+  printf("}\n");
+  return 0;
+}
+
+// core_test.go:28-80
+static void core_test_objects(Node* node, NodeInfo* info, Pod pods[3]) {
+  Pod pod;
+  pod.ns = "default"; pod.name = "p"; pod.uid = "u0";
+  Container c;
+  c.has_limits = true;
+  c.limits = {{"cpu", "1"}, {"alpha.kubernetes.io/nvidia-gpu", "1"}, {"tencent.cr/tencentip", "1"}};
+  c.requests = c.limits;
+  pod.containers = {c};
+  node->name = "n0";
+  node->allocatable = {{"cpu", "10"}, {"alpha.kubernetes.io/nvidia-gpu", "10"}, {"pods", "100"}, {"tencent.cr/tencentip", "20"}};
+  info->node = node;
+  // nodeIf.AddPod(&pod): requested = the pod's Requests, one pod on the node
+  info->requested = {{"cpu", "1"}, {"alpha.kubernetes.io/nvidia-gpu", "1"}, {"tencent.cr/tencentip", "1"}};
+  info->num_pods = 1;
+  pods[0] = pod;
+  pods[1] = pod; pods[1].uid = "u1";
+  pods[1].containers[0].limits[1].second = "101"; pods[1].containers[0].requests[1].second = "101";
+  pods[2] = pod; pods[2].uid = "u2";
+  pods[2].containers[0].limits[2].second = "101"; pods[2].containers[0].requests[2].second = "101";
+}
+
+static int cmd_pack_core_test() {
+  Node node; NodeInfo info; Pod pods[3];
+  core_test_objects(&node, &info, pods);
+  PackedSnapshot ps;
+  Status st = BatchSchedulingPlugin::Pack({&info}, {&pods[0], &pods[1], &pods[2]}, {}, {}, {}, {}, 0, &ps);
+  if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+  printf("{\"lanes\": %u,\n", ps.lanes);
+  printf("\"scalars\": [");
+  for (size_t i = 0; i < ps.scalar_names.size(); ++i) printf("%s\"%s\"", i ? ", " : "", ps.scalar_names[i].c_str());
+  printf("],\n");
+  print_arr("alloc", ps.alloc); print_arr("requested", ps.requested); print_arr("pod_count", ps.pod_count);
+  print_arr("alloc_present", ps.alloc_present); print_arr("req_present", ps.req_present);
+  print_arr("req", ps.req); print_arr("pod_req_present", ps.pod_req_present); print_arr("gid", ps.gid, true);
+  printf("}\n");
+  return 0;
+}
+
+static Pod readme_pod(int group, int i) {
+  Pod p;
+  p.ns = "default";
+  p.name = "web-group-race" + std::to_string(group) + "-" + std::to_string(i);
+  p.uid = "uid-" + p.name;
+  p.labels[kPodGroupLabel] = "group" + std::to_string(group);
+  Container c;
+  c.has_limits = true;
+  c.limits = {{"cpu", "1"}};
+  c.requests = {{"cpu", "1"}};
+  p.containers = {c};
+  p.owner_uids = {"sts-" + std::to_string(group)};
+  p.queue_ts_ns = 1000 + i * 10 + group;
+  return p;
+}
+
+static int cmd_readme() {
+  // README.md:78-88: 8 cpu, 900m / 140Mi requested
+  Node node; node.name = "node1";
+  node.allocatable = {{"cpu", "8"}, {"memory", "16Gi"}, {"ephemeral-storage", "100Gi"}, {"pods", "110"}};
+  NodeInfo info; info.node = &node; info.num_pods = 4;
+  int64_t req_cpu_m = 900;
+  info.requested = {{"cpu", "900m"}, {"memory", "140Mi"}};
+  BatchSchedulingPlugin plugin(0, 0);
+  for (int g = 1; g <= 2; ++g) {
+    PodGroup pg; pg.ns = "default"; pg.name = "group" + std::to_string(g); pg.min_member = 5;
+    pg.creation_ns = 1600000000ll * 1000000000ll;
+    plugin.SetPodGroup(pg);
+  }
+  std::vector<Pod> queue;
+  for (int i = 0; i < 5; ++i) { queue.push_back(readme_pod(1, i)); queue.push_back(readme_pod(2, i)); }
+  int64_t now = 1000000000ll;
+  printf("[\n");
+  for (size_t qi = 0; qi < queue.size(); ++qi) {
+    const Pod& p = queue[qi];
+    now += 100000000ll;  // 0.1 s per cycle: the 20 s freeze cache stays warm
+    Status st = plugin.BeginRound({&info}, {&p}, now);
+    if (!st.ok()) { fprintf(stderr, "round failed: %s\n", st.message.c_str()); return 1; }
+    Status pf = plugin.PreFilter(p);
+    int permit_code = -1; long long wait = 0; bool start = false; int node_idx = -1;
+    if (pf.ok()) {
+      node_idx = plugin.best_nodes()[0];
+      if (node_idx >= 0) {
+        // assume: upstream adds the pod to the node (NodeInfo.AddPod)
+        req_cpu_m += 1000; info.num_pods += 1;
+        info.requested[0].second = std::to_string(req_cpu_m) + "m";
+        auto r = plugin.Permit(p, node.name, &start);
+        permit_code = r.first.code; wait = r.second;
+      }
+    }
+    printf("%s{\"pod\": \"%s\", \"prefilter_code\": %d, \"message\": \"%s\", \"node\": %d, \"permit_code\": %d, "
+           "\"wait_ns\": %lld, \"start_signal\": %d}\n",
+           qi ? "," : "", p.name.c_str(), pf.code, pf.message.c_str(), node_idx, permit_code, wait, start ? 1 : 0);
+  }
+  printf("]\n");
+  return 0;
+}
+
+static int cmd_bench_pack(int N, int P, int G) {
+  std::vector<Node> nodes(N);
+  std::vector<NodeInfo> infos(N);
+  for (int i = 0; i < N; ++i) {
+    nodes[i].name = "node-" + std::to_string(i);
+    nodes[i].allocatable = {{"cpu", std::to_string(16 + i % 5 * 16)}, {"memory", std::to_string(64 + i % 7) + "Gi"},
+                            {"ephemeral-storage", "500Gi"}, {"pods", "110"}, {"nvidia.com/gpu", std::to_string(i % 3 * 4)}};
+    nodes[i].labels = {{"zone", "z" + std::to_string(i % 4)}, {"disk", i % 2 ? "ssd" : "hdd"}};
+    if (i % 20 == 0) nodes[i].taints = {{"dedicated", "batch", "NoSchedule"}};
+    infos[i].node = &nodes[i];
+    infos[i].requested = {{"cpu", std::to_string(100 * (i % 90)) + "m"}, {"memory", std::to_string(i % 50) + "Gi"},
+                          {"nvidia.com/gpu", std::to_string(i % 3)}};
+    infos[i].num_pods = i % 60;
+  }
+  std::vector<PodGroup> groups(G);
+  for (int g = 0; g < G; ++g) {
+    groups[g].ns = "default"; groups[g].name = "pg-" + std::to_string(g); groups[g].min_member = 1 + g % 8;
+    groups[g].creation_ns = 1600000000ll * 1000000000ll + g % 3600 * 1000000000ll;
+  }
+  std::vector<Pod> pods(P);
+  for (int i = 0; i < P; ++i) {
+    Pod& p = pods[i];
+    p.ns = "default"; p.name = "pod-" + std::to_string(i); p.uid = "uid-" + std::to_string(i);
+    p.labels[kPodGroupLabel] = "pg-" + std::to_string(i % G);
+    Container c; c.has_limits = true;
+    c.limits = {{"cpu", std::to_string(250 * (1 + i % 8)) + "m"}, {"memory", std::to_string(1 + i % 16) + "Gi"}};
+    if (i % 5 == 0) c.limits.push_back({"nvidia.com/gpu", "1"});
+    p.containers = {c};
+    if (i % 10 == 0) p.node_selector = {{"disk", "ssd"}};
+    if (i % 7 == 0) p.tolerations = {{"dedicated", "Equal", "batch", "NoSchedule"}};
+    p.priority = i % 10; p.queue_ts_ns = i;
+  }
+  std::vector<const NodeInfo*> snap(N);
+  std::vector<const Pod*> pend(P);
+  for (int i = 0; i < N; ++i) snap[i] = &infos[i];
+  for (int i = 0; i < P; ++i) pend[i] = &pods[i];
+  PackedSnapshot ps;
+  double best = 1e30;
+  for (int it = 0; it < 3; ++it) {
+    auto t0 = std::chrono::steady_clock::now();
+    Status st = BatchSchedulingPlugin::Pack(snap, pend, groups, {}, {}, {}, 0, &ps);
+    auto t1 = std::chrono::steady_clock::now();
+    if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+    best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+  }
+  printf("{\"nodes\": %d, \"pods\": %d, \"groups\": %d, \"lanes\": %u, \"pack_ms\": %.3f, \"objects_per_s\": %.0f}\n", N, P, G,
+         ps.lanes, best, (N + P + G) / (best * 1e-3));
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  if (!strcmp(argv[1], "quantity")) return cmd_quantity(argc, argv);
+  if (!strcmp(argv[1], "pack_core_test")) return cmd_pack_core_test();
+  if (!strcmp(argv[1], "readme")) return cmd_readme();
+  if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
+  return 2;
+}

@@ -1,0 +1,80 @@
+"""The C++ host mirror (batch-scheduler_b200/csrc/plugin.{hpp,cpp}): resource.Quantity parsing and the
+snapshot packer on CPU; the README scenario pod-by-pod through BatchSchedulingPlugin on the GPU."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "plugin_test")
+
+
+@pytest.fixture(scope="module")
+def plugin_bin(pkg):
+    pkg.capi.load()  # makes sure libbsched.so exists
+    src = os.path.join(ROOT, "tests", "cpp", "plugin_test.cpp")
+    libdir = os.path.join(ROOT, "batch-scheduler_b200")
+    lib = os.path.join(libdir, "libbsched.so")
+    if (not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(lib))):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", BIN, src, "-L" + libdir, "-lbsched",
+                               "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return BIN
+
+
+def _run(binary, *args):
+    return json.loads(subprocess.check_output([binary, *args], text=True))
+
+
+def test_quantity_parsing(plugin_bin):
+    # (Value, MilliValue) as k8s resource.Quantity computes them (both round up)
+    cases = {"1": (1, 1000), "900m": (1, 900), "140Mi": (140 << 20, (140 << 20) * 1000), "1.5": (2, 1500),
+             "100": (100, 100000), "0": (0, 0), "1e3": (1000, 1000000), "2Gi": (2 << 30, (2 << 30) * 1000),
+             "1k": (1000, 1000000), "0.5Gi": (1 << 29, (1 << 29) * 1000), "250u": (1, 1), "12E-1": None,
+             "5G": (5 * 10**9, 5 * 10**12), "1Ki": (1024, 1024000), "-1": (-1, -1000), "1500m": (2, 1500)}
+    out = _run(plugin_bin, "quantity", *cases)
+    for s, exp in cases.items():
+        ok, v, m = out[s]
+        if exp is None:
+            continue
+        assert ok == 1 and (v, m) == exp, (s, out[s])
+    bad = _run(plugin_bin, "quantity", "abc", "1Zi", "")
+    assert all(v[0] == 0 for v in bad.values())
+
+
+def test_packer_core_test_go(plugin_bin, snapshot_mod):
+    # the objects of core_test.go:28-80 packed by the C++ packer == the hand-built tables
+    snap, _, _ = snapshot_mod.core_test_cases()
+    out = _run(plugin_bin, "pack_core_test")
+    assert out["lanes"] == 6
+    assert out["scalars"] == ["alpha.kubernetes.io/nvidia-gpu", "tencent.cr/tencentip"]
+    assert out["alloc"] == snap.nodes.alloc.reshape(-1).tolist()
+    assert out["requested"] == snap.nodes.requested.reshape(-1).tolist()
+    assert out["pod_count"] == snap.nodes.pod_count.tolist()
+    assert out["alloc_present"] == snap.nodes.alloc_present.tolist()
+    assert out["req_present"] == snap.nodes.req_present.tolist()
+    assert out["req"] == snap.pods.req.reshape(-1).tolist()
+    assert out["pod_req_present"] == snap.pods.req_present.tolist()
+    assert out["gid"] == [-1, -1, -1]
+
+
+def test_packer_throughput_smoke(plugin_bin):
+    out = _run(plugin_bin, "bench_pack", "500", "4000", "500")
+    assert out["lanes"] == 5 and out["pack_ms"] > 0
+
+
+@pytest.mark.gpu
+def test_readme_race_through_cpp_plugin(plugin_bin, snapshot_mod):
+    # README.md:76-188 — "only one and at least one group" runs; messages as core.go:107,143 print them
+    S = snapshot_mod
+    rows = _run(plugin_bin, "readme")
+    g1 = [r for r in rows if "race1" in r["pod"]]
+    g2 = [r for r in rows if "race2" in r["pod"]]
+    assert all(r["prefilter_code"] == 0 and r["node"] == 0 and r["permit_code"] == 4 for r in g1)   # Wait
+    assert [r["start_signal"] for r in g1] == [0, 0, 0, 0, 1]
+    assert all(r["wait_ns"] == 10**9 for r in g1)                                                    # 0 + 1 s (Q12)
+    assert g2[0]["prefilter_code"] == 2 and g2[0]["message"] == "cluster resource not enough"
+    for r in g2[1:]:
+        assert r["prefilter_code"] == 2
+        assert r["message"] == "pod with pgName: default/group2 last failed in 20s, deny"
