@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -150,9 +150,10 @@ def run_reference(args, rank, world):
     S = importlib.import_module("batch-scheduler_b200.snapshot")
     snap = S.config(WORKLOAD_CFG)
     threads = oracle.max_threads()
-    # size one step to ~4 s so steps+warmup stay within minutes
+    # bounded sample per step: the whole --steps K --warmup W run is sized to ~90 s of CPU work
     v, n_pods, _ = cpu_sample(oracle, snap, seconds=2.0, threads=threads)
-    n_step = int(min(snap.pods.n, max(64, v * 4.0 / snap.nodes.n)))
+    per_step_s = min(4.0, max(0.05, 90.0 / max(1, args.steps + args.warmup)))
+    n_step = int(min(snap.pods.n, max(64, v * per_step_s / snap.nodes.n)))
     sub = S.Snapshot(snap.nodes, snap.pods.take(np.arange(n_step)), snap.groups)
     for _ in range(args.warmup):
         oracle.round(sub, want_bitmap=True, want_score=False, faithful=True, threads=threads)
@@ -182,7 +183,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; marks the line)")
@@ -288,7 +289,7 @@ def main():
     # ---- per-kernel CUDA-event times (same process, same data, per-step sync) -------------
     eng.set_profiling(True)
     kms = {k: [] for k in capi.KERNEL_NAMES}
-    for _ in range(max(5, min(args.steps, 20))):
+    for _ in range(max(5, min(args.steps, 30))):
         eng.evaluate_async()
         eng.sync()
         for k, (ms, n) in eng.kernel_ms().items():
