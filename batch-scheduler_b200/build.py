@@ -40,6 +40,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         srcs.append(plugin)
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-shared", "-Xcompiler", "-fPIC,-Wall,-fopenmp", "-fmad=false", "-o", LIB] + srcs + ["-lgomp"]
+    extra = os.environ.get("BS_NVCC_EXTRA", "").split()
+    if extra:
+        cmd[1:1] = extra
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd, cwd=CSRC)

@@ -34,11 +34,18 @@ struct LaneMap {
   uint32_t LW, LN;
 };
 constexpr int NODE_TILE = 512;                          // nodes per shared-memory tile
-constexpr int FIT_THREADS = 256;
-constexpr int FIT_WARPS = FIT_THREADS / 32;
-constexpr int PODS_PER_WARP = 4;                        // pods evaluated together per node (ILP)
+#ifndef BS_FIT_WARPS
+#define BS_FIT_WARPS 8
+#endif
+#ifndef BS_FIT_PPW
+#define BS_FIT_PPW 4
+#endif
+constexpr int FIT_WARPS = BS_FIT_WARPS;                 // consumer warps (each sweeps PODS_PER_WARP pods)
+constexpr int FIT_THREADS = (FIT_WARPS + 1) * 32;       // + one producer warp that only drives the TMA ring
+constexpr int PODS_PER_WARP = BS_FIT_PPW;               // pods evaluated together per node (ILP)
 constexpr int PODS_PER_CTA = FIT_WARPS * PODS_PER_WARP; // 32
 constexpr int TILE_WORDS = NODE_TILE / 32;              // 16 ballot words per tile and pod
+constexpr int FIT_STAGES = 3;                           // TMA ring depth (full/empty mbarrier pairs)
 #ifndef BS_FIT_MINB
 #define BS_FIT_MINB 2
 #endif
@@ -911,6 +918,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -940,6 +950,32 @@ __device__ __forceinline__ int32_t hi32(int64_t v) {
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
   (void)lo;
   return hi;
+}
+__device__ __forceinline__ uint32_t lo32(int64_t v) {
+  int32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  (void)hi;
+  return (uint32_t)lo;
+}
+__device__ __forceinline__ long long pack64(uint32_t lo, uint32_t hi) {
+  long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+  return v;
+}
+#ifndef BS_FIT_STORE
+#define BS_FIT_STORE 0
+#endif
+// score store: cache-policy variants for experiments (0 = .cs streaming / evict-first)
+__device__ __forceinline__ void score_store(int64_t* p, long long v) {
+#if BS_FIT_STORE == 0
+  __stcs(reinterpret_cast<long long*>(p), v);
+#elif BS_FIT_STORE == 1
+  *reinterpret_cast<long long*>(p) = v;
+#elif BS_FIT_STORE == 2
+  __stwt(reinterpret_cast<long long*>(p), v);
+#else
+  __stcg(reinterpret_cast<long long*>(p), v);
+#endif
 }
 __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
@@ -984,6 +1020,11 @@ struct FitArgs {
 // pair, every lane writes the same word: no predicate, no ALU); after the tile lane
 // j < TILE_WORDS pops word j back for the fit-bitmap store (64 B per pod, coalesced) and the
 // feasible count (popcount, reduced across the warp once at the very end).
+// running best score of a lane: int32 on the narrow fast path (scores of fitting pairs are < 2^28,
+// "none" = -1), int64 otherwise ("none" = INT64_MIN)
+template <bool NARROW> struct BestT { using type = int64_t; };
+template <> struct BestT<true> { using type = int32_t; };
+
 template <int LW, int LN, bool TAIL>
 __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __restrict__ tlw,
                                          const int32_t* __restrict__ tln,
@@ -992,7 +1033,8 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
                                          const uint32_t (&colbits)[PODS_PER_WARP], int64_t* sp0,
                                          size_t row_stride, uint32_t* s_words, uint32_t node_base,
                                          uint32_t lane, bool want_score,
-                                         int64_t (&best_s)[PODS_PER_WARP], int32_t (&best_n)[PODS_PER_WARP]) {
+                                         typename BestT<(LN > 0)>::type (&best_s)[PODS_PER_WARP],
+                                         int32_t (&best_n)[PODS_PER_WARP]) {
   int64_t* sp[PODS_PER_WARP];
 #pragma unroll
   for (int r = 0; r < PODS_PER_WARP; ++r) sp[r] = sp0 + r * row_stride;
@@ -1013,25 +1055,46 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
       const bool in_range = !TAIL || ((uint32_t)node + jj * 32 < a.N);
 #pragma unroll
       for (int r = 0; r < PODS_PER_WARP; ++r) {
-        int64_t m;
         if (LN > 0) {
+          // Narrow fast path.  t = min over the narrow lanes is a REAL difference (the narrow set
+          // holds a fixed lane) with |t| <= 2^28, and the pair's score m = min over all lanes <= t.
+          // So when the pair fits (every difference >= 0) m is a 32-bit value: wide differences
+          // only matter through (a) their sign and (b) their low word when the high word is 0.
           int32_t t = lfn[0] - rqn[r][0];
+#ifndef BS_FIT_NOCOMPUTE   // (experiment switch: store pattern without the arithmetic)
 #pragma unroll
           for (int d = 1; d < LN; ++d) t = min(t, lfn[d] - rqn[r][d]);
-          m = (int64_t)t;
+#endif
+          uint32_t m32 = (uint32_t)t;
+          int32_t sgn = t;
+#ifndef BS_FIT_NOCOMPUTE
 #pragma unroll
-          for (int d = 0; d < LW; ++d) m = min64(m, lfw[d] - rqw[r][d]);
+#endif
+          for (int d = 0; d < (LW
+#ifdef BS_FIT_NOCOMPUTE
+                                  * 0
+#endif
+                              ); ++d) {
+            const int64_t w = lfw[d] - rqw[r][d];
+            const int32_t whi = hi32(w);
+            sgn |= whi;                                               // any negative difference -> sign bit
+            m32 = min(m32, whi != 0 ? 0xffffffffu : lo32(w));         // unsigned: valid when all are >= 0
+          }
+          const bool fit = (sgn >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
+          sts_u32(wp + (r * TILE_WORDS + jj) * 4, __ballot_sync(0xffffffffu, fit));
+          if (fit && (int32_t)m32 > best_s[r]) { best_s[r] = (int32_t)m32; best_n[r] = node + jj * 32; }
+          if (want_score && in_range)
+            score_store(sp[r] + jj * 32, pack64(fit ? m32 : 0u, fit ? 0u : 0x80000000u));
         } else {
-          m = lfw[0] - rqw[r][0];
+          int64_t m = lfw[0] - rqw[r][0];
 #pragma unroll
           for (int d = 1; d < LW; ++d) m = min64(m, lfw[d] - rqw[r][d]);
+          const bool fit = (hi32(m) >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
+          sts_u32(wp + (r * TILE_WORDS + jj) * 4, __ballot_sync(0xffffffffu, fit));
+          if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
+          if (want_score && in_range)
+            score_store(sp[r] + jj * 32, fit ? (long long)m : (long long)INT64_MIN);
         }
-        // m >= 0 needs only the sign of the high word (one ISETP instead of a 64-bit compare)
-        const bool fit = (hi32(m) >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
-        sts_u32(wp + (r * TILE_WORDS + jj) * 4, __ballot_sync(0xffffffffu, fit));
-        if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
-        if (want_score && in_range)
-          __stcs(reinterpret_cast<long long*>(sp[r] + jj * 32), fit ? (long long)m : (long long)INT64_MIN);
       }
     }
     tpw += 128;
@@ -1053,14 +1116,16 @@ __host__ __device__ constexpr int fit_min_blocks(int LW, int LN) {
 template <int LW, int LN>
 __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_kernel(FitArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [2 stages]{[LW][NODE_TILE] i64, [LN][NODE_TILE] i32} | req_w | req_n | mbarriers | ballot words
+  // layout: [FIT_STAGES]{[LW][NODE_TILE] i64, [LN][NODE_TILE] i32} | req_w | req_n | mbarriers | ballot words
   constexpr size_t STAGE_BYTES = fit_tile_bytes(LW, LN);
   unsigned char* s_tile = smem_raw;
-  int64_t* s_req_w = reinterpret_cast<int64_t*>(smem_raw + 2 * STAGE_BYTES);
+  int64_t* s_req_w = reinterpret_cast<int64_t*>(smem_raw + FIT_STAGES * STAGE_BYTES);
   int32_t* s_req_n = reinterpret_cast<int32_t*>(s_req_w + PODS_PER_CTA * LW);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(s_req_n + PODS_PER_CTA * LN) + 7) & ~(uintptr_t)7);
-  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(s_bar + 2);
+  uint64_t* s_full = s_bar;                 // [FIT_STAGES] TMA bytes landed
+  uint64_t* s_empty = s_bar + FIT_STAGES;   // [FIT_STAGES] every warp is done with the stage
+  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(s_bar + 2 * FIT_STAGES);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   uint32_t* s_words = s_words_all + wid * PODS_PER_WARP * TILE_WORDS;
@@ -1069,8 +1134,10 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
   const uint32_t n_tiles = a.Npad / NODE_TILE;
 
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    for (int st = 0; st < FIT_STAGES; ++st) {
+      mbar_init(&s_full[st], 1);
+      mbar_init(&s_empty[st], FIT_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // stage the CTA's pod requests (sentinel for lanes without a map key)
@@ -1090,22 +1157,31 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
   }
   __syncthreads();
   auto issue = [&](uint32_t tile, uint32_t stage) {
-    mbar_expect_tx(&s_bar[stage], (uint32_t)STAGE_BYTES);
+    mbar_expect_tx(&s_full[stage], (uint32_t)STAGE_BYTES);
     unsigned char* dst = s_tile + stage * STAGE_BYTES;
     const unsigned char* src_w = reinterpret_cast<const unsigned char*>(a.left_w) + (uint64_t)tile * (NODE_TILE * 8);
     const unsigned char* src_n = reinterpret_cast<const unsigned char*>(a.left_n) + (uint64_t)tile * (NODE_TILE * 4);
 #pragma unroll
     for (int d = 0; d < LW; ++d)
       tma_bulk_g2s(dst + (size_t)d * NODE_TILE * 8, src_w + (uint64_t)d * a.left_w_pitch, NODE_TILE * 8,
-                   &s_bar[stage]);
+                   &s_full[stage]);
 #pragma unroll
     for (int d = 0; d < LN; ++d)
       tma_bulk_g2s(dst + (size_t)LW * NODE_TILE * 8 + (size_t)d * NODE_TILE * 4,
-                   src_n + (uint64_t)d * a.left_n_pitch, NODE_TILE * 4, &s_bar[stage]);
+                   src_n + (uint64_t)d * a.left_n_pitch, NODE_TILE * 4, &s_full[stage]);
   };
-  if (tid == 0) {
-    issue(0, 0);
-    if (n_tiles > 1) issue(1, 1);
+  // Warp specialisation: warp FIT_WARPS is the producer.  Its lane 0 walks the tiles, waits until
+  // every consumer warp has released the stage (`empty`), and issues the TMA bulk copies that
+  // complete on `full`.  Consumers never meet at a CTA-wide barrier during the sweep.
+  if (wid == FIT_WARPS) {
+    if (lane == 0) {
+      for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        const uint32_t st = tile % FIT_STAGES, use = tile / FIT_STAGES;
+        if (use > 0) mbar_wait(&s_empty[st], (use - 1) & 1);
+        issue(tile, st);
+      }
+    }
+    return;
   }
 
   // per-pod state of this warp (requests are warp-uniform, in registers for the whole sweep).
@@ -1113,14 +1189,15 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
   const bool want_score = a.score != nullptr;
   const bool want_bitmap = a.fit_bitmap != nullptr;
   uint32_t cnt[PODS_PER_WARP];
-  int64_t best_s[PODS_PER_WARP];
+  typename BestT<(LN > 0)>::type best_s[PODS_PER_WARP];
   int32_t best_n[PODS_PER_WARP];
   int64_t rqw[PODS_PER_WARP][LW > 0 ? LW : 1];
   int32_t rqn[PODS_PER_WARP][LN > 0 ? LN : 1];
   uint32_t coff[PODS_PER_WARP];
 #pragma unroll
   for (int r = 0; r < PODS_PER_WARP; ++r) {
-    cnt[r] = 0; best_s[r] = INT64_MIN; best_n[r] = -1;
+    cnt[r] = 0; best_n[r] = -1;
+    best_s[r] = LN > 0 ? (typename BestT<(LN > 0)>::type)(-1) : (typename BestT<(LN > 0)>::type)INT64_MIN;
     const uint32_t p = wpod0 + r;
     coff[r] = (p < a.P ? a.fit_class[p] : 0u) * n_tiles * 32 + lane;
 #pragma unroll
@@ -1129,12 +1206,14 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
     for (int d = 0; d < LN; ++d) rqn[r][d] = s_req_n[(wid * PODS_PER_WARP + r) * LN + d];
   }
 
+  // Consumers: a warp releases a stage by arriving on its `empty` mbarrier and may run up to
+  // FIT_STAGES-1 tiles ahead of the slowest warp.
+  uint32_t stage = 0, phase = 0;
   for (uint32_t tile = 0; tile < n_tiles; ++tile) {
-    const uint32_t stage = tile & 1;
     uint32_t colbits[PODS_PER_WARP];
 #pragma unroll
     for (int r = 0; r < PODS_PER_WARP; ++r) colbits[r] = __ldg(a.classfit + coff[r] + tile * 32);
-    mbar_wait(&s_bar[stage], (tile >> 1) & 1);
+    mbar_wait(&s_full[stage], phase);
     const int64_t* tlw = reinterpret_cast<const int64_t*>(s_tile + stage * STAGE_BYTES);
     const int32_t* tln = reinterpret_cast<const int32_t*>(s_tile + stage * STAGE_BYTES + (size_t)LW * NODE_TILE * 8);
     const uint32_t node_base = tile * NODE_TILE;
@@ -1144,6 +1223,7 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
     else
       fit_tile<LW, LN, true>(a, tlw, tln, rqw, rqn, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
     __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the stage
     if (lane < TILE_WORDS) {
       const uint32_t word = (node_base >> 5) + lane;
 #pragma unroll
@@ -1153,16 +1233,16 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
         if (want_bitmap && word < a.W) a.fit_bitmap[(size_t)(wpod0 + r) * a.W + word] = w;
       }
     }
-    __syncthreads();  // everyone is done reading this stage (and the warp's ballot slab)
-    if (tid == 0 && tile + 2 < n_tiles) issue(tile + 2, stage);
+    __syncwarp();                                   // the ballot slab is rewritten by the next tile
+    if (++stage == FIT_STAGES) { stage = 0; phase ^= 1; }
   }
 
   // per-pod reductions across the warp: best = max score, lowest node on ties
   uint32_t my_gid = 0xffffffffu, my_pass = 0;
 #pragma unroll
   for (int k = 0; k < PODS_PER_WARP; ++k) {
-    int64_t s = best_s[k];
     int32_t n = best_n[k];
+    int64_t s = n < 0 ? INT64_MIN : (int64_t)best_s[k];
     uint32_t c = cnt[k];
     for (int o = 16; o; o >>= 1) {
       const int64_t os = __shfl_xor_sync(0xffffffffu, s, o);
@@ -1222,9 +1302,9 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
 }
 
 inline size_t gang_fit_smem_bytes(int LW, int LN) {
-  size_t b = 2 * fit_tile_bytes(LW, LN) + (size_t)PODS_PER_CTA * (8 * LW + 4 * LN);
+  size_t b = FIT_STAGES * fit_tile_bytes(LW, LN) + (size_t)PODS_PER_CTA * (8 * LW + 4 * LN);
   b = (b + 7) & ~(size_t)7;
-  return b + 2 * sizeof(uint64_t) + (size_t)PODS_PER_CTA * TILE_WORDS * sizeof(uint32_t);
+  return b + 2 * FIT_STAGES * sizeof(uint64_t) + (size_t)PODS_PER_CTA * TILE_WORDS * sizeof(uint32_t);
 }
 
 }  // namespace bsk
