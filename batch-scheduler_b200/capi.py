@@ -16,10 +16,11 @@ from . import build as _build
 BS_OK, BS_E_INVAL, BS_E_NODEVICE, BS_E_CUDA, BS_E_NOMEM, BS_E_RANGE, BS_E_STATE, BS_E_REF_PANIC, BS_E_INDEX = \
     0, -1, -2, -3, -4, -5, -6, -7, -8
 CODE_SUCCESS, CODE_ERROR, CODE_UNSCHEDULABLE, CODE_UNSCHEDULABLE_AND_UNRESOLVABLE, CODE_WAIT, CODE_SKIP = range(6)
-OUT_FIT_BITMAP, OUT_SCORE = 0x1, 0x2
+OUT_FIT_BITMAP, OUT_SCORE, OUT_FILTER = 0x1, 0x2, 0x4
+FILTER_PASS, FILTER_NOT_FOUND, FILTER_NOT_ENOUGH, FILTER_NO_SNAPSHOT, FILTER_REF_PANIC = range(5)
 BUF_FIT_BITMAP, BUF_SCORE, BUF_ADMIT_BITMAP, BUF_PREFILTER, BUF_ADMIT, BUF_ORDER = range(6)
-K_NODE_LEFT, K_FIND_MAX, K_CLASS_PREFIX, K_PREFILTER, K_GANG_FIT, K_SORT, K_COUNT = range(7)
-KERNEL_NAMES = ["node_left", "find_max", "class_prefix", "prefilter", "gang_fit", "sort"]
+K_NODE_LEFT, K_FIND_MAX, K_CLASS_PREFIX, K_PREFILTER, K_GANG_FIT, K_SORT, K_FILTER, K_COUNT = range(8)
+KERNEL_NAMES = ["node_left", "find_max", "class_prefix", "prefilter", "gang_fit", "sort", "filter"]
 
 
 def _p(t):
@@ -53,7 +54,7 @@ class ResultsC(C.Structure):
     _fields_ = [("prefilter", C.c_void_p), ("feasible_count", C.c_void_p), ("best_node", C.c_void_p),
                 ("best_score", C.c_void_p), ("admit", C.c_void_p), ("admit_bitmap", C.c_void_p),
                 ("new_denied", C.c_void_p), ("order", C.c_void_p), ("rank", C.c_void_p),
-                ("max_group", C.c_int32), ("max_finished", C.c_uint32)]
+                ("max_group", C.c_int32), ("max_finished", C.c_uint32), ("filter_code", C.c_void_p)]
 
 
 class StatusC(C.Structure):
@@ -83,6 +84,7 @@ SYMBOLS = {
     "bs_prefilter": (C.c_int, [C.c_void_p, C.c_uint32, _p(StatusC)]),
     "bs_permit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(PermitResultC)]),
     "bs_less": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "bs_filter": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(StatusC)]),
     "bs_format_message": (C.c_int, [_p(StatusC), C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "bs_node_left": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
     "bs_cluster_check": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p,
@@ -91,6 +93,7 @@ SYMBOLS = {
     "bs_stream": (C.c_void_p, [C.c_void_p]),
     "bs_fetch_fit_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bs_fetch_score_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "bs_fetch_filter_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bs_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "bs_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, _p(C.c_float), _p(C.c_uint32)]),
     "bs_launch_count": (C.c_uint64, [C.c_void_p]),

@@ -190,7 +190,7 @@ struct bs_engine {
 
   // node table (device, padded to Npad) + derived
   DevBuf d_alloc, d_requested, d_pod_count, d_apres, d_rpres, d_label, d_taint, d_nflags;
-  DevBuf d_left_w, d_left_n, d_left_present, d_classfit;
+  DevBuf d_left_w, d_left_n, d_left_present, d_classfit, d_left_plain, d_filter_bitmap, d_filter_code;
   LaneMap lane_map{};
   bool lane_map_valid = false;
   // per-lane maxima of |value| (lane classification wide / narrow)
@@ -233,7 +233,7 @@ struct bs_engine {
   uint64_t vary_ts = ~0ull, vary_prio = ~0ull, vary_creation = ~0ull, vary_name = ~0ull;
   // pinned result cache
   PinBuf h_prefilter, h_feasible, h_best_node, h_best_score, h_admit, h_admit_bitmap, h_new_denied,
-      h_order, h_rank, h_state;
+      h_order, h_rank, h_state, h_filter_code;
   bool fetched = false;
 
   // profiling
@@ -599,6 +599,11 @@ int ensure_round_buffers(bs_engine* e) {
   const size_t Prows = (size_t)cdiv(std::max(e->P, 1u), PODS_PER_CTA) * PODS_PER_CTA;
   if (e->out_flags & BS_OUT_FIT_BITMAP) CK(e->d_fit_bitmap.ensure(Prows * std::max(e->W, 1u) * 4));
   if (e->out_flags & BS_OUT_SCORE) CK(e->d_score.ensure(Prows * N * 8));
+  if (e->out_flags & BS_OUT_FILTER) {
+    CK(e->d_filter_bitmap.ensure(Prows * std::max(e->W, 1u) * 4));
+    CK(e->d_filter_code.ensure(P));
+    CK(e->h_filter_code.ensure(P));
+  }
   // prefix scratch: as many rep-class slots as fit a 1 GiB budget
   const size_t per_class = (size_t)N * (8 * L + 4);
   uint32_t slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(e->n_rep_classes, ((size_t)1 << 30) / per_class));
@@ -649,11 +654,13 @@ int prepare_nodes(bs_engine* e) {
   CK(e->d_left_w.ensure((size_t)std::max(e->lane_map.LW, 1u) * e->Npad * 8));
   CK(e->d_left_n.ensure((size_t)std::max(e->lane_map.LN, 1u) * e->Npad * 4));
   CK(e->d_left_present.ensure((size_t)e->Npad * 4));
+  if (e->out_flags & BS_OUT_FILTER) CK(e->d_left_plain.ensure((size_t)4 * e->Npad * 8));
   const uint32_t n_tiles = e->Npad / NODE_TILE;
   CK(e->d_classfit.ensure((size_t)e->n_fit_classes * n_tiles * 32 * 4));
   node_left_kernel<<<cdiv(e->Npad, 256), 256, 0, e->s>>>(t, e->lane_map, e->d_left_w.as<int64_t>(),
                                                          e->d_left_n.as<int32_t>(),
-                                                         e->d_left_present.as<uint32_t>());
+                                                         e->d_left_present.as<uint32_t>(),
+                                                         (e->out_flags & BS_OUT_FILTER) ? e->d_left_plain.as<int64_t>() : nullptr);
   tm.launched();
   {
     dim3 grid(cdiv(n_tiles * 32, 256), e->n_fit_classes);
@@ -827,6 +834,27 @@ int evaluate_async_locked(bs_engine* e) {
       tm.launched();
     }
   }
+  {
+    StageTimer tm(e, BS_K_FILTER, e->s);
+    if (P && (e->out_flags & BS_OUT_FILTER)) {
+      FilterArgs fa;
+      fa.left_plain = e->d_left_plain.as<int64_t>();
+      fa.node_flags = e->d_nflags.as<uint8_t>();
+      fa.req = e->d_req.as<int64_t>();
+      fa.req_present = e->d_ppres.as<uint32_t>();
+      fa.gid = e->d_gid.as<int32_t>();
+      fa.emin_res = ge.min_res;
+      fa.emin_res_present = ge.min_res_present;
+      fa.eflags = ge.flags;
+      fa.st = st;
+      fa.filter_bitmap = e->d_filter_bitmap.as<uint32_t>();
+      fa.filter_code = e->d_filter_code.as<uint8_t>();
+      fa.P = P; fa.N = e->N; fa.Npad = e->Npad; fa.W = e->W; fa.G = G; fa.L = L;
+      const uint32_t warps = cdiv(P, FILTER_PPW);
+      filter_kernel<<<cdiv(warps * 32, 256), 256, 0, e->s>>>(fa);
+      tm.launched();
+    }
+  }
   CK(cudaStreamWaitEvent(e->s, e->ev_join, 0));
   CK(cudaGetLastError());
   e->evaluated = true;
@@ -851,6 +879,7 @@ int fetch_locked(bs_engine* e, bs_results* out) {
     CK(d2h(e->h_order, e->d_order, (size_t)P * 4));
     CK(d2h(e->h_rank, e->d_rank, (size_t)P * 4));
     CK(d2h(e->h_state, e->d_state, sizeof(RoundState)));
+    if (e->out_flags & BS_OUT_FILTER) CK(d2h(e->h_filter_code, e->d_filter_code, P));
     CK(cudaStreamSynchronize(e->s));
     e->fetched = true;
   }
@@ -870,6 +899,7 @@ int fetch_locked(bs_engine* e, bs_results* out) {
     cp(out->rank, e->h_rank, (size_t)P * 4);
     out->max_group = st->max_group;
     out->max_finished = st->max_finished;
+    if (e->out_flags & BS_OUT_FILTER) cp(out->filter_code, e->h_filter_code, P);
   }
   if (st->ref_panic)
     return fail(e, BS_E_REF_PANIC, "findMaxPG: MinMember == 0 with Status.Scheduled != 0 (core.go:716-717 divides by zero)");
@@ -943,7 +973,7 @@ void bs_destroy(bs_engine* e) {
   if (e->s) cudaStreamSynchronize(e->s);
   if (e->s2) cudaStreamSynchronize(e->s2);
   DevBuf* bufs[] = {&e->d_alloc, &e->d_requested, &e->d_pod_count, &e->d_apres, &e->d_rpres, &e->d_label,
-                    &e->d_taint, &e->d_nflags, &e->d_left_w, &e->d_left_n, &e->d_left_present, &e->d_classfit, &e->d_req,
+                    &e->d_taint, &e->d_nflags, &e->d_left_w, &e->d_left_n, &e->d_left_present, &e->d_left_plain, &e->d_filter_bitmap, &e->d_filter_code, &e->d_classfit, &e->d_req,
                     &e->d_ppres, &e->d_gid, &e->d_prio, &e->d_ts, &e->d_pflags, &e->d_pod_fit_class,
                     &e->d_pod_rep_class, &e->d_min_member, &e->d_scheduled, &e->d_matched, &e->d_gflags,
                     &e->d_min_res, &e->d_mrpres, &e->d_creation, &e->d_name_rank, &e->d_group_rep_class,
@@ -957,7 +987,7 @@ void bs_destroy(bs_engine* e) {
                     &e->d_ghist, &e->d_skip, &e->d_group_rank, &e->d_gorder, &e->d_tilecnt, &e->d_sort_barrier};
   for (DevBuf* b : bufs) b->release();
   PinBuf* pins[] = {&e->h_prefilter, &e->h_feasible, &e->h_best_node, &e->h_best_score, &e->h_admit,
-                    &e->h_admit_bitmap, &e->h_new_denied, &e->h_order, &e->h_rank, &e->h_state};
+                    &e->h_admit_bitmap, &e->h_new_denied, &e->h_order, &e->h_rank, &e->h_state, &e->h_filter_code};
   for (PinBuf* b : pins) b->release();
   for (int k = 0; k < BS_K_COUNT; ++k) {
     if (e->ev_a[k]) cudaEventDestroy(e->ev_a[k]);
@@ -1349,6 +1379,45 @@ int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words) 
     CK(cudaMemcpyAsync(words, e->d_fit_bitmap.as<uint32_t>() + (size_t)pod0 * e->W, (size_t)n * e->W * 4,
                        cudaMemcpyDeviceToHost, e->s));
   CK(cudaStreamSynchronize(e->s));
+  return BS_OK;
+}
+
+int bs_fetch_filter_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words) {
+  if (!e || !words) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->evaluated || !(e->out_flags & BS_OUT_FILTER)) return fail(e, BS_E_STATE, "no filter matrix materialised");
+  if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
+  CK(cudaSetDevice(e->device));
+  if (n && e->W)
+    CK(cudaMemcpyAsync(words, e->d_filter_bitmap.as<uint32_t>() + (size_t)pod0 * e->W, (size_t)n * e->W * 4,
+                       cudaMemcpyDeviceToHost, e->s));
+  CK(cudaStreamSynchronize(e->s));
+  return BS_OK;
+}
+
+int bs_filter(bs_engine* e, uint32_t pod, uint32_t node, bs_status* st) {
+  if (!e || !st) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->evaluated || !(e->out_flags & BS_OUT_FILTER)) return fail(e, BS_E_STATE, "bs_filter: evaluate with BS_OUT_FILTER first");
+  if (pod >= e->P || node >= e->N) return BS_E_INDEX;
+  if (!e->fetched) {
+    int rc = fetch_locked(e, nullptr);
+    if (rc) return rc;
+  }
+  CK(cudaSetDevice(e->device));
+  uint32_t word = 0;
+  uint8_t nflag = 0;
+  CK(cudaMemcpyAsync(&word, e->d_filter_bitmap.as<uint32_t>() + (size_t)pod * e->W + (node >> 5), 4,
+                     cudaMemcpyDeviceToHost, e->s));
+  CK(cudaMemcpyAsync(&nflag, e->d_nflags.as<uint8_t>() + node, 1, cudaMemcpyDeviceToHost, e->s));
+  CK(cudaStreamSynchronize(e->s));
+  const int32_t g = e->h_gid[pod];
+  st->group = (g >= 0 && (uint32_t)g < e->G) ? g : -1;
+  const uint8_t pcode = e->h_filter_code.as<uint8_t>()[pod];
+  if ((word >> (node & 31)) & 1u) st->reason = BS_FILTER_PASS;
+  else if (pcode != BS_FILTER_PASS) st->reason = pcode;
+  else st->reason = (nflag & BS_NODE_NIL) ? BS_FILTER_ERR_NO_SNAPSHOT : BS_FILTER_ERR_NOT_ENOUGH;
+  st->code = st->reason == BS_FILTER_PASS ? BS_CODE_SUCCESS : BS_CODE_UNSCHEDULABLE;   // batchscheduler.go:153-156
   return BS_OK;
 }
 

@@ -150,9 +150,22 @@ __device__ __forceinline__ bool compare_res(const int64_t* left, uint32_t lpres,
 // Restates singleNodeResource core.go:647-668.  Padding nodes (>= N) get zeros.
 __global__ void node_left_kernel(NodeTab t, LaneMap lm, int64_t* __restrict__ left_w /*[LW][Npad]*/,
                                  int32_t* __restrict__ left_n /*[LN][Npad]*/,
-                                 uint32_t* __restrict__ left_present /*[Npad]*/) {
+                                 uint32_t* __restrict__ left_present /*[Npad]*/,
+                                 int64_t* __restrict__ left_plain /*[4][Npad] getLeftResource, or null*/) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.Npad) return;
+  if (left_plain) {
+    // getLeftResource (core.go:436-475): plain alloc - requested on the four fixed lanes, no float32
+    // factor, no checkFit, never a scalar key (the cloned zero Resource has a nil map, :465-472)
+    int64_t v[4] = {0, 0, 0, 0};
+    if (i < t.N) {
+      int64_t pc = t.requested[(size_t)LANE_PODS * t.Npad + i];
+      if (pc == 0) pc = t.pod_count[i];
+      for (int d = 0; d < 3; ++d) v[d] = t.alloc[(size_t)d * t.Npad + i] - t.requested[(size_t)d * t.Npad + i];
+      v[LANE_PODS] = t.alloc[(size_t)LANE_PODS * t.Npad + i] - pc;
+    }
+    for (int d = 0; d < 4; ++d) left_plain[(size_t)d * t.Npad + i] = v[d];
+  }
   if (i >= t.N) {
     for (uint32_t k = 0; k < lm.LW; ++k) left_w[(size_t)k * t.Npad + i] = 0;
     for (uint32_t k = 0; k < lm.LN; ++k) left_n[(size_t)k * t.Npad + i] = 0;
@@ -1296,6 +1309,111 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
         else verdict = (total >= (uint32_t)(a.min_member[my_gid] - a.scheduled[my_gid])) ? BS_ADMIT : BS_WAIT;
         a.admit[my_gid] = verdict;
         if (verdict == BS_ADMIT) atomicOr(&a.admit_bitmap[my_gid >> 5], 1u << (my_gid & 31));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K7  filter_kernel — ScheduleOperation.Filter / computeResourceSatisfied (core.go:170-191,
+// 514-564) for every (pod,node) against the round's max group m (optional, BS_OUT_FILTER):
+//   unlabelled -> pass; group missing -> "can not found pod group"; m == own group -> pass (case 1);
+//   max group without MinResources -> pass; info == nil -> "SnapShot not initialized";
+//   case 2: left >= require(pod) + MinResources(max) -> pass;
+//   case 3: !(left >= MinResources(max)) -> pass; else "resource not enough".
+// `left` = getLeftResource has NO scalar keys, so a request key passes only with amount 0.
+// Warp per FILTER_PPW pods; a lane owns one node of each 32-node step; ballots become bitmap words.
+constexpr int FILTER_PPW = 4;
+struct FilterArgs {
+  const int64_t* left_plain;  // [4][Npad]
+  const uint8_t* node_flags;
+  const int64_t* req;         // [L][P]
+  const uint32_t* req_present;
+  const int32_t* gid;
+  const int64_t* emin_res;    // [L][G] effective MinResources
+  const uint32_t* emin_res_present;
+  const uint8_t* eflags;
+  const RoundState* st;
+  uint32_t* filter_bitmap;    // [Ppad][W]
+  uint8_t* filter_code;       // [P]
+  uint32_t P, N, Npad, W, G, L;
+};
+__global__ void __launch_bounds__(256) filter_kernel(FilterArgs a) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t wpod0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * FILTER_PPW;
+  if (wpod0 >= a.P) return;
+  const int32_t m = a.st->max_group;
+  // MinResources of the max group as a Resource (core.go:525-528)
+  int64_t mmr[4] = {0, 0, 0, 0};
+  bool has_mr = false, mmr_scalars_zero = true;
+  uint32_t mmr_present = 0;
+  if (m >= 0 && (a.eflags[m] & BS_GROUP_HAS_MINRES)) {
+    has_mr = true;
+    mmr_present = a.emin_res_present[m] & ~0xFu;
+    for (int d = 0; d < 4; ++d) mmr[d] = a.emin_res[(size_t)d * a.G + m];
+    for (uint32_t d = 4; d < a.L; ++d)
+      if (((mmr_present >> d) & 1u) && a.emin_res[(size_t)d * a.G + m] != 0) mmr_scalars_zero = false;
+  }
+  int64_t rq[FILTER_PPW][4];
+  uint8_t mode[FILTER_PPW];   // 0 all pass, 1 none pass, 2 general
+  bool sc_ok[FILTER_PPW];
+#pragma unroll
+  for (int r = 0; r < FILTER_PPW; ++r) {
+    const uint32_t p = wpod0 + r;
+    mode[r] = 1; sc_ok[r] = false;
+    for (int d = 0; d < 4; ++d) rq[r][d] = 0;
+    if (p >= a.P) continue;
+    const int32_t g = a.gid[p];
+    uint8_t code = BS_FILTER_PASS;
+    if (g == BS_GID_NONE) mode[r] = 0;                                        // core.go:171-174
+    else if (g < 0 || (uint32_t)g >= a.G) { mode[r] = 1; code = BS_FILTER_ERR_NOT_FOUND; }  // :177-180
+    else if (m < 0) { mode[r] = 1; code = BS_FILTER_REF_PANIC; }              // :525
+    else if (m == g || !has_mr) mode[r] = 0;                                  // :531-535, :542-544
+    else {
+      mode[r] = 2;
+      const uint32_t rp = a.req_present[p] & ~0xFu;
+      for (int d = 0; d < 4; ++d) rq[r][d] = a.req[(size_t)d * a.P + p] + mmr[d];   // :551-552
+      bool ok = true;   // every scalar key of (pod require + MinResources) must sum to 0 (:686-693)
+      for (uint32_t d = 4; d < a.L; ++d) {
+        const bool in_p = (rp >> d) & 1u, in_m = (mmr_present >> d) & 1u;
+        if (!in_p && !in_m) continue;
+        const int64_t v = (in_p ? a.req[(size_t)d * a.P + p] : 0) + (in_m ? a.emin_res[(size_t)d * a.G + m] : 0);
+        if (v != 0) ok = false;
+      }
+      sc_ok[r] = ok;
+    }
+    if (lane == 0) a.filter_code[p] = code;
+  }
+  uint32_t words[FILTER_PPW];
+#pragma unroll
+  for (int r = 0; r < FILTER_PPW; ++r) words[r] = 0;
+  for (uint32_t base = 0; base < a.Npad; base += 32) {
+    const uint32_t n = base + lane;
+    int64_t lf[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) lf[d] = a.left_plain[(size_t)d * a.Npad + n];
+    const bool in_n = n < a.N;
+    const bool nil = in_n && (a.node_flags[n] & BS_NODE_NIL);
+    // case 3 (:558): node cannot hold the max group's MinResources
+    const bool c3 = !(mmr_scalars_zero && lf[0] >= mmr[0] && lf[1] >= mmr[1] && lf[2] >= mmr[2] && lf[3] >= mmr[3]);
+#pragma unroll
+    for (int r = 0; r < FILTER_PPW; ++r) {
+      bool pass;
+      if (mode[r] == 0) pass = in_n;
+      else if (mode[r] == 1) pass = false;
+      else {
+        const bool c2 = sc_ok[r] && lf[0] >= rq[r][0] && lf[1] >= rq[r][1] && lf[2] >= rq[r][2] && lf[3] >= rq[r][3];
+        pass = in_n && !nil && (c2 || c3);                                    // :545-563
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+      if (lane == ((base >> 5) & 31)) words[r] = bal;
+    }
+    if (((base >> 5) & 31) == 31 || base + 32 >= a.Npad) {
+      const uint32_t w = (base >> 5) - ((base >> 5) & 31) + lane;
+#pragma unroll
+      for (int r = 0; r < FILTER_PPW; ++r) {
+        if (w < a.W) a.filter_bitmap[(size_t)(wpod0 + r) * a.W + w] = words[r];
+        words[r] = 0;
       }
     }
   }

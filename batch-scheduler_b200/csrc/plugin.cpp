@@ -543,6 +543,33 @@ std::pair<Status, int64_t> BatchSchedulingPlugin::Permit(const Pod& pod, const s
   return {Status{r.code, ""}, r.wait_ns};
 }
 
+Status BatchSchedulingPlugin::Filter(const Pod& pod, const std::string& node_name) {
+  auto it = pod_row_.find(pod.uid);
+  auto nt = node_row_.find(node_name);
+  if (it == pod_row_.end() || nt == node_row_.end())
+    return Status{BS_CODE_ERROR, "pod or node is not part of the current round"};
+  bs_status st{};
+  int rc = bs_filter(eng_, it->second, nt->second, &st);
+  if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+  auto lab = pod.labels.find(kPodGroupLabel);
+  const std::string pg_name = lab != pod.labels.end() ? lab->second : std::string();
+  switch (st.reason) {
+    case BS_FILTER_PASS:
+      if (!pg_name.empty()) AddPermitted(pod.uid, now_ns_);                       // core.go:188
+      return Status{};
+    case BS_FILTER_ERR_NOT_FOUND:
+      return Status{BS_CODE_UNSCHEDULABLE, "can not found pod group: " + pg_name};  // core.go:179 (bare name)
+    case BS_FILTER_ERR_NO_SNAPSHOT:
+      AddToDenyCache(pod.ns + "/" + pg_name, now_ns_);                            // core.go:184
+      return Status{BS_CODE_UNSCHEDULABLE, "SnapShot not initialized"};           // core.go:547
+    case BS_FILTER_ERR_NOT_ENOUGH:
+      AddToDenyCache(pod.ns + "/" + pg_name, now_ns_);
+      return Status{BS_CODE_UNSCHEDULABLE, "resource not enough"};                // util.ErrorResourceNotEnough
+    default:
+      return Status{BS_CODE_ERROR, "reference would dereference a nil maxPGStatus (core.go:525)"};
+  }
+}
+
 bool BatchSchedulingPlugin::Less(const Pod& a, const Pod& b) {
   auto ia = pod_row_.find(a.uid), ib = pod_row_.find(b.uid);
   if (ia == pod_row_.end() || ib == pod_row_.end()) return false;

@@ -140,6 +140,10 @@ class BatchSchedulingPlugin {
   std::pair<Status, int64_t> Permit(const Pod& pod, const std::string& node_name, bool* start_signal = nullptr);
   // batchSchedulingPlugin.Less (batchscheduler.go:214-216)
   bool Less(const Pod& a, const Pod& b);
+  // batchSchedulingPlugin.Filter (batchscheduler.go:151-157) -> core.Filter (core.go:170-191); the
+  // plugin must have been created with BS_OUT_FILTER in out_flags.  On failure the group is
+  // deny-listed (core.go:184), on success the pod is remembered as permitted for 2 s (:188).
+  Status Filter(const Pod& pod, const std::string& node_name);
   // ScheduleOperation.AddToDenyCache (core.go:423-425): 20 s, Add semantics (no-op if present)
   void AddToDenyCache(const std::string& ns_name, int64_t now_ns);
   // lastPermittedPod.Add(uid, 2s) (core.go:188)

@@ -23,13 +23,16 @@ class RoundResult:
     rank: np.ndarray
     max_group: int
     max_finished: int
+    filter_code: np.ndarray = None
 
 
 class Engine:
-    def __init__(self, n_lanes: int, device: int = 0, fit_bitmap: bool = True, score: bool = False):
+    def __init__(self, n_lanes: int, device: int = 0, fit_bitmap: bool = True, score: bool = False,
+                 filter: bool = False):
         self.lib = capi.load()
         self.n_lanes = n_lanes
-        self.out_flags = (capi.OUT_FIT_BITMAP if fit_bitmap else 0) | (capi.OUT_SCORE if score else 0)
+        self.out_flags = ((capi.OUT_FIT_BITMAP if fit_bitmap else 0) | (capi.OUT_SCORE if score else 0) |
+                          (capi.OUT_FILTER if filter else 0))
         cfg = capi.Config(device, n_lanes, self.out_flags, 0)
         h = C.c_void_p()
         rc = self.lib.bs_create(C.byref(cfg), C.byref(h))
@@ -96,10 +99,12 @@ class Engine:
         P, G = self.P, self.G
         r = RoundResult(np.zeros(P, np.uint8), np.zeros(P, np.uint32), np.zeros(P, np.int32), np.zeros(P, np.int64),
                         np.zeros(G, np.uint8), np.zeros((G + 31) // 32, np.uint32), np.zeros(G, np.uint8),
-                        np.zeros(P, np.uint32), np.zeros(P, np.uint32), -1, 0)
+                        np.zeros(P, np.uint32), np.zeros(P, np.uint32), -1, 0,
+                        np.zeros(P, np.uint8) if (self.out_flags & capi.OUT_FILTER) else None)
         c = capi.ResultsC(capi.ptr(r.prefilter), capi.ptr(r.feasible_count), capi.ptr(r.best_node),
                           capi.ptr(r.best_score), capi.ptr(r.admit), capi.ptr(r.admit_bitmap),
-                          capi.ptr(r.new_denied), capi.ptr(r.order), capi.ptr(r.rank), -1, 0)
+                          capi.ptr(r.new_denied), capi.ptr(r.order), capi.ptr(r.rank), -1, 0,
+                          capi.ptr(r.filter_code) if r.filter_code is not None else None)
         return r, c
 
     def evaluate(self) -> RoundResult:
@@ -126,6 +131,18 @@ class Engine:
         out = np.zeros((n, W), np.uint32)
         self._check(self.lib.bs_fetch_fit_rows(self.h, pod0, n, capi.ptr(out)))
         return out
+
+    def filter_rows(self, pod0=0, n=None) -> np.ndarray:
+        n = self.P - pod0 if n is None else n
+        W = (self.N + 31) // 32
+        out = np.zeros((n, W), np.uint32)
+        self._check(self.lib.bs_fetch_filter_rows(self.h, pod0, n, capi.ptr(out)))
+        return out
+
+    def filter(self, pod: int, node: int):
+        st = capi.StatusC()
+        self._check(self.lib.bs_filter(self.h, pod, node, C.byref(st)))
+        return st.code, st.reason, st.group
 
     def score_rows(self, pod0=0, n=None) -> np.ndarray:
         n = self.P - pod0 if n is None else n

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 1
+#define BS_ABI_VERSION 2
 #define BS_FIXED_LANES 4
 #define BS_MAX_LANES 16
 /* |value| bound accepted for every int64 table entry (validated at upload):
@@ -78,6 +78,15 @@ typedef enum {
   BS_PF_ERR_OCCUPIED = 4,    /* "pod group has been occupied by %v"          :509 */
   BS_PF_ERR_NOT_ENOUGH = 5   /* "cluster resource not enough"           :143,:164 */
 } bs_prefilter_code;
+
+/* ---- Filter verdict (core.go:170-191 + computeResourceSatisfied :514-564) ---- */
+typedef enum {
+  BS_FILTER_PASS = 0,
+  BS_FILTER_ERR_NOT_FOUND = 1,   /* "can not found pod group: %v" (bare pgName)   core.go:179 */
+  BS_FILTER_ERR_NOT_ENOUGH = 2,  /* util.ErrorResourceNotEnough "resource not enough"    :563 */
+  BS_FILTER_ERR_NO_SNAPSHOT = 3, /* "SnapShot not initialized"                           :547 */
+  BS_FILTER_REF_PANIC = 4        /* sop.maxPGStatus == nil is dereferenced at            :525 */
+} bs_filter_code;
 
 /* ---- gang decision per group (Permit, core.go:268-309) ---- */
 typedef enum {
@@ -156,6 +165,8 @@ typedef struct {
 /* What one evaluation materialises in HBM besides the decision vectors. */
 #define BS_OUT_FIT_BITMAP 0x1u /* P x ceil(N/32) u32 words, bit n%32 of word n/32 */
 #define BS_OUT_SCORE 0x2u      /* P x N int64 residual-capacity scores            */
+#define BS_OUT_FILTER 0x4u     /* P x ceil(N/32) u32: Filter verdict bit per (pod,node) — ScheduleOperation.Filter /
+                                  computeResourceSatisfied (core.go:170-191, 514-564) against the round's max group */
 
 typedef struct {
   int32_t device;      /* CUDA device ordinal */
@@ -177,6 +188,7 @@ typedef struct {
   uint32_t* rank;           /* [P] dense rank of each pod under Less (equal keys share a rank) */
   int32_t max_group;        /* out: findMaxPG winner, -1 if none (core.go:701)  */
   uint32_t max_finished;    /* out: its progress value                          */
+  uint8_t* filter_code;     /* [P] bs_filter_code when it does not depend on the node (BS_OUT_FILTER) */
 } bs_results;
 
 typedef struct {
@@ -232,6 +244,9 @@ int bs_prefilter(bs_engine* e, uint32_t pod, bs_status* st);
 int bs_permit(bs_engine* e, uint32_t pod, uint32_t node, bs_permit_result* r);
 /* batchSchedulingPlugin.Less       (batchscheduler.go:214-216); returns 1/0 or <0 */
 int bs_less(bs_engine* e, uint32_t pod_a, uint32_t pod_b);
+/* batchSchedulingPlugin.Filter (batchscheduler.go:151-157) -> core.Filter (core.go:170-191).  Needs
+ * BS_OUT_FILTER.  st->reason is a bs_filter_code; code Success / Unschedulable. */
+int bs_filter(bs_engine* e, uint32_t pod, uint32_t node, bs_status* st);
 /* Formats the reference's error string for a status (core.go:102,107,143,505,509).
  * ns_name is the "namespace/name" of the group, occupied_by the OccupiedBy text. */
 int bs_format_message(const bs_status* st, const char* ns_name, const char* occupied_by,
@@ -262,6 +277,7 @@ void* bs_stream(bs_engine* e); /* the cudaStream_t every kernel is launched on *
 /* copy rows [pod0, pod0+n) of the fit bitmap / score matrix to the host */
 int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words);
 int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores);
+int bs_fetch_filter_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words);
 
 /* ---- measurement hooks ---- */
 typedef enum {
@@ -271,7 +287,8 @@ typedef enum {
   BS_K_PREFILTER = 3,
   BS_K_GANG_FIT = 4,   /* the dominant kernel: fit predicate + score + gang admit */
   BS_K_SORT = 5,
-  BS_K_COUNT = 6
+  BS_K_FILTER = 6,     /* optional Filter matrix (BS_OUT_FILTER) */
+  BS_K_COUNT = 7
 } bs_kernel_id;
 int bs_set_profiling(bs_engine* e, int on); /* record CUDA events around each stage */
 /* milliseconds of stage k in the last evaluation, and launches it took */

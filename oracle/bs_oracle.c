@@ -310,6 +310,39 @@ int bso_fit_eval(const bso_nodes* nd, const bso_pods* pd, uint32_t p, uint32_t n
   return 1;
 }
 
+/* core.go:436-475 getLeftResource */
+int bso_get_left_resource(const bso_nodes* nd, uint32_t n, bso_resource* out) {
+  const uint32_t N = nd->n;
+  memset(out, 0, sizeof(*out));
+  if (nd->flags[n] & BSO_NODE_NIL) return 0;                           /* :447-449 info == nil */
+  int64_t pod_count = nd->requested[(size_t)LANE_PODS * N + n];        /* :455-458 */
+  if (pod_count == 0) pod_count = nd->pod_count[n];
+  out->v[LANE_CPU] = wrap_sub(nd->alloc[(size_t)LANE_CPU * N + n], nd->requested[(size_t)LANE_CPU * N + n]);   /* :460 */
+  out->v[LANE_PODS] = wrap_sub(nd->alloc[(size_t)LANE_PODS * N + n], pod_count);                               /* :461 */
+  out->v[LANE_MEM] = wrap_sub(nd->alloc[(size_t)LANE_MEM * N + n], nd->requested[(size_t)LANE_MEM * N + n]);   /* :462 */
+  out->v[LANE_EPH] = wrap_sub(nd->alloc[(size_t)LANE_EPH * N + n], nd->requested[(size_t)LANE_EPH * N + n]);   /* :463 */
+  /* :465-472: leftResourceCopy.ScalarResources is a nil map -> the loop never runs: no scalar keys */
+  return 1;
+}
+
+/* core.go:514-564 computeResourceSatisfied (Filter, :170-191, maps its error) */
+int bso_filter_eval(const bso_nodes* nd, const bso_pods* pd, uint32_t p, uint32_t n, int m, int max_has_minres,
+                    const bso_resource* max_min_res) {
+  const int g = pd->gid[p];
+  if (g == BSO_GID_NONE) return BSO_FILTER_PASS;                       /* :171-174 */
+  if (g < 0) return BSO_FILTER_NOT_FOUND;                              /* :177-180 */
+  if (m < 0) return BSO_FILTER_REF_PANIC;                              /* :525 sop.maxPGStatus == nil */
+  if (m == g) return BSO_FILTER_PASS;                                  /* :531-535 case 1 */
+  if (!max_has_minres) return BSO_FILTER_PASS;                         /* :542-544 */
+  bso_resource left, req;
+  if (!bso_get_left_resource(nd, n, &left)) return BSO_FILTER_NO_SNAPSHOT;   /* :545-548 */
+  bso_pod_require(pd, p, &req);                                        /* :551 */
+  bso_resource_add(&req, max_min_res, nd->lanes);                      /* :552 */
+  if (bso_compare_resource_and_require(&left, &req, nd->lanes)) return BSO_FILTER_PASS;          /* :553 case 2 */
+  if (!bso_compare_resource_and_require(&left, max_min_res, nd->lanes)) return BSO_FILTER_PASS;  /* :558 case 3 */
+  return BSO_FILTER_NOT_ENOUGH;                                        /* :563 */
+}
+
 /* ------------------------------------------------------------------------ */
 /* Effective group state of a round: what fillOccupiedObj (core.go:477-512)
  * leaves behind once the first pod of each group (table order) has reached it:
@@ -517,6 +550,41 @@ int bso_round(const bso_nodes* nd, const bso_pods* pd, const bso_groups* gr, bso
     if (out->best_node) out->best_node[p] = best;
     if (out->best_score) out->best_score[p] = best_s;
     any_fit[p] = cnt > 0;
+  }
+
+  /* Filter: computeResourceSatisfied per (pod,node) against the round's max group */
+  if (out->filter_bitmap || out->filter_code) {
+    bso_resource mmr;
+    memset(&mmr, 0, sizeof(mmr));
+    int has_mr = 0;
+    if (m >= 0 && (eg.flags[m] & BSO_GROUP_HAS_MINRES)) {
+      has_mr = 1;   /* :525-528: Resource{}.Add(*MinResources) */
+      for (uint32_t d = 0; d < gr->lanes; ++d) {
+        if (d >= 4 && !(eg.min_res_present[m] & (1u << d))) continue;
+        mmr.v[d] = eg.min_res[(size_t)d * G + m];
+      }
+      mmr.present = eg.min_res_present[m];
+    }
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
+    for (uint32_t p = 0; p < P; ++p) {
+      uint32_t* row = out->filter_bitmap ? out->filter_bitmap + (size_t)p * words : NULL;
+      if (row) memset(row, 0, (size_t)words * 4);
+      const int g = pd->gid[p];
+      uint8_t pcode = BSO_FILTER_PASS;
+      if (g != BSO_GID_NONE && (g < 0 || (uint32_t)g >= G)) pcode = BSO_FILTER_NOT_FOUND;
+      else if (g != BSO_GID_NONE && m < 0) pcode = BSO_FILTER_REF_PANIC;
+      if (out->filter_code) out->filter_code[p] = pcode;
+      if (!row) continue;
+      for (uint32_t n = 0; n < N; ++n) {
+        const int gg = (g >= 0 && (uint32_t)g >= G) ? BSO_GID_MISSING : g;
+        bso_pods pd2 = *pd;
+        (void)pd2;
+        int c;
+        if (gg == BSO_GID_MISSING) c = BSO_FILTER_NOT_FOUND;
+        else c = bso_filter_eval(nd, pd, p, n, m, has_mr, &mmr);
+        if (c == BSO_FILTER_PASS) row[n >> 5] |= 1u << (n & 31);
+      }
+    }
   }
 
   /* D.4: Permit readiness per group (core.go:303) */

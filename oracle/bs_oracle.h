@@ -46,6 +46,9 @@
 enum { BSO_PF_PASS = 0, BSO_PF_NOT_FOUND = 1, BSO_PF_DENIED = 2, BSO_PF_OCC_NOREFS = 3,
        BSO_PF_OCCUPIED = 4, BSO_PF_NOT_ENOUGH = 5 };
 enum { BSO_ADMIT = 0, BSO_WAIT = 1, BSO_UNSCHEDULABLE = 2 };
+/* Filter verdict per (pod,node), core.go:170-191 + computeResourceSatisfied :514-564 */
+enum { BSO_FILTER_PASS = 0, BSO_FILTER_NOT_FOUND = 1, BSO_FILTER_NOT_ENOUGH = 2, BSO_FILTER_NO_SNAPSHOT = 3,
+       BSO_FILTER_REF_PANIC = 4 };
 
 /* nodeinfo.Resource: 4 fixed fields + ScalarResources map (key presence = bit) */
 typedef struct {
@@ -101,6 +104,8 @@ typedef struct {
   uint8_t* new_denied;       /* [G] */
   uint32_t* order;           /* [P] */
   uint32_t* rank;            /* [P] */
+  uint32_t* filter_bitmap;   /* [P][ceil(N/32)] bit = Filter passes, or NULL */
+  uint8_t* filter_code;      /* [P] pod-level Filter outcome when it does not depend on the node */
   uint32_t* fit_bitmap;      /* [P][ceil(N/32)] or NULL */
   int64_t* score;            /* [P][N] or NULL */
   int32_t max_group;
@@ -125,6 +130,14 @@ void bso_pod_require(const bso_pods* pd, uint32_t p, bso_resource* out);      /*
 int bso_permit_ready(uint32_t matched_count, uint32_t min_member, uint32_t scheduled); /* core.go:303 */
 int bso_compare(const bso_pods* pd, const bso_groups* gr, uint32_t a, uint32_t b); /* core.go:368-411 */
 int bso_fit_eval(const bso_nodes* nd, const bso_pods* pd, uint32_t p, uint32_t n, int64_t* score);
+/* getLeftResource (core.go:436-475): plain alloc - requested, no float32 factor, no checkFit, and
+ * never any scalar key (the Clone of a zero Resource has a nil map, :465-472).  Returns 0 when the
+ * reference returns nil (info == nil). */
+int bso_get_left_resource(const bso_nodes* nd, uint32_t n, bso_resource* out);
+/* computeResourceSatisfied (core.go:514-564) for one (pod,node) given the round's max group m and its
+ * effective MinResources; returns a BSO_FILTER_* code. */
+int bso_filter_eval(const bso_nodes* nd, const bso_pods* pd, uint32_t p, uint32_t n, int m, int max_has_minres,
+                    const bso_resource* max_min_res);
 
 /* ---- one snapshot round (DESIGN.md "Round semantics") ----
  * faithful != 0: PreFilter is evaluated the way the reference does it, per pod:

@@ -60,7 +60,8 @@ class _Results(C.Structure):
     _fields_ = [("prefilter", _p(C.c_uint8)), ("feasible_count", _p(C.c_uint32)),
                 ("best_node", _p(C.c_int32)), ("best_score", _p(C.c_int64)), ("admit", _p(C.c_uint8)),
                 ("admit_bitmap", _p(C.c_uint32)), ("new_denied", _p(C.c_uint8)), ("order", _p(C.c_uint32)),
-                ("rank", _p(C.c_uint32)), ("fit_bitmap", _p(C.c_uint32)), ("score", _p(C.c_int64)),
+                ("rank", _p(C.c_uint32)), ("filter_bitmap", _p(C.c_uint32)), ("filter_code", _p(C.c_uint8)),
+                ("fit_bitmap", _p(C.c_uint32)), ("score", _p(C.c_int64)),
                 ("max_group", C.c_int32), ("max_finished", C.c_uint32), ("ref_panic", C.c_int32)]
 
 
@@ -201,12 +202,15 @@ class RoundResult:
     rank: np.ndarray
     fit_bitmap: np.ndarray | None
     score: np.ndarray | None
+    filter_bitmap: np.ndarray | None
+    filter_code: np.ndarray | None
     max_group: int
     max_finished: int
     ref_panic: bool
 
 
-def round(snap, want_bitmap=True, want_score=False, faithful=False, threads=0, want_sort=True) -> RoundResult:
+def round(snap, want_bitmap=True, want_score=False, faithful=False, threads=0, want_sort=True,
+          want_filter=False) -> RoundResult:
     """One snapshot round (DESIGN.md 'Round semantics') on the CPU oracle."""
     nt, pt, gt = snap.nodes, snap.pods, snap.groups
     P, N, G = pt.n, nt.n, gt.n
@@ -215,12 +219,16 @@ def round(snap, want_bitmap=True, want_score=False, faithful=False, threads=0, w
                     np.zeros(P, np.int64), np.zeros(G, np.uint8), np.zeros((G + 31) // 32, np.uint32),
                     np.zeros(G, np.uint8), np.zeros(P, np.uint32), np.zeros(P, np.uint32),
                     np.zeros((P, words), np.uint32) if want_bitmap else None,
-                    np.zeros((P, N), np.int64) if want_score else None, -1, 0, False)
+                    np.zeros((P, N), np.int64) if want_score else None,
+                    np.zeros((P, words), np.uint32) if want_filter else None,
+                    np.zeros(P, np.uint8) if want_filter else None, -1, 0, False)
     res = _Results(_ptr(r.prefilter, C.c_uint8), _ptr(r.feasible_count, C.c_uint32),
                    _ptr(r.best_node, C.c_int32), _ptr(r.best_score, C.c_int64), _ptr(r.admit, C.c_uint8),
                    _ptr(r.admit_bitmap, C.c_uint32), _ptr(r.new_denied, C.c_uint8),
                    _ptr(r.order, C.c_uint32) if want_sort else None,
                    _ptr(r.rank, C.c_uint32) if want_sort else None,
+                   _ptr(r.filter_bitmap, C.c_uint32) if want_filter else None,
+                   _ptr(r.filter_code, C.c_uint8) if want_filter else None,
                    _ptr(r.fit_bitmap, C.c_uint32) if want_bitmap else None,
                    _ptr(r.score, C.c_int64) if want_score else None, -1, 0, 0)
     nd, pd, gr = _nodes(nt), _pods(pt), _groups(gt)

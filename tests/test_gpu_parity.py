@@ -239,3 +239,33 @@ def test_lane_classification_variants(pkg, oracle, snapshot_mod, variant):
         nt.label_mask[:] = 0xF
         nt.taint_mask[:] = 0
     run_and_compare(pkg, oracle, snap)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_filter_matrix(pkg, oracle, snapshot_mod, seed):
+    """ScheduleOperation.Filter / computeResourceSatisfied (core.go:170-191, 514-564) per (pod,node)."""
+    S = snapshot_mod
+    snap = random_snapshot(700 + seed, P=130 + 60 * seed, N=40 + 150 * seed, G=8 + 2 * seed, L=[5, 6, 9][seed % 3],
+                           case=["mixed", "B", "A"][seed % 3])
+    if seed == 5:
+        snap.groups.flags[:] |= S.GROUP_SCHEDULED      # no eligible group: maxPGStatus == nil (core.go:525)
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=False, score=False, filter=True)
+    eng.upload(snap)
+    res = eng.evaluate()
+    rows = eng.filter_rows()
+    orc = oracle.round(snap, want_bitmap=False, want_filter=True)
+    np.testing.assert_array_equal(rows, orc.filter_bitmap)
+    np.testing.assert_array_equal(res.filter_code, orc.filter_code)
+    np.testing.assert_array_equal(res.prefilter, orc.prefilter)
+    # per-call mirror on a sample of pairs
+    rng = np.random.default_rng(seed)
+    capi = pkg.capi
+    for _ in range(40):
+        p, n = int(rng.integers(0, snap.pods.n)), int(rng.integers(0, snap.nodes.n))
+        code, reason, _ = eng.filter(p, n)
+        bit = (orc.filter_bitmap[p, n >> 5] >> (n & 31)) & 1
+        assert (reason == capi.FILTER_PASS) == bool(bit)
+        assert code == (capi.CODE_SUCCESS if bit else capi.CODE_UNSCHEDULABLE)
+        if not bit and orc.filter_code[p] == capi.FILTER_PASS:
+            assert reason == (capi.FILTER_NO_SNAPSHOT if snap.nodes.flags[n] & S.NODE_NIL else capi.FILTER_NOT_ENOUGH)
+    eng.close()
