@@ -250,7 +250,8 @@ namespace {
     cudaError_t _e = (call);                                                         \
     if (_e != cudaSuccess) {                                                         \
       e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
-      return BS_E_CUDA;                                                              \
+      cudaGetLastError();                                                            \
+      return _e == cudaErrorMemoryAllocation ? BS_E_NOMEM : BS_E_CUDA;               \
     }                                                                                \
   } while (0)
 

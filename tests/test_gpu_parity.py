@@ -269,3 +269,22 @@ def test_filter_matrix(pkg, oracle, snapshot_mod, seed):
         if not bit and orc.filter_code[p] == capi.FILTER_PASS:
             assert reason == (capi.FILTER_NO_SNAPSHOT if snap.nodes.flags[n] & S.NODE_NIL else capi.FILTER_NOT_ENOUGH)
     eng.close()
+
+
+def test_out_of_memory_is_reported_not_fatal(pkg, snapshot_mod):
+    # a score matrix that cannot fit (2M pods x 50k nodes x 8 B = 800 GB) must come back as BS_E_NOMEM,
+    # and the engine must stay usable
+    S = snapshot_mod
+    big = S.config(5, 0.002)
+    P = 2_000_000
+    idx = np.arange(P) % big.pods.n
+    snap = S.Snapshot(S.config(5, 1.0).nodes, big.pods.take(idx), big.groups)
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=False, score=True)
+    eng.upload(snap)
+    with pytest.raises(pkg.capi.BsError) as ei:
+        eng.evaluate()
+    assert ei.value.code == pkg.capi.BS_E_NOMEM
+    small = random_snapshot(5, P=60, N=40, G=6, L=9)
+    eng.upload(small)
+    eng.evaluate()
+    eng.close()
