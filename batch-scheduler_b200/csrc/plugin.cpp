@@ -1,8 +1,14 @@
 // plugin.cpp — snapshot packer + BatchSchedulingPlugin mirror (see plugin.hpp).
 #include "plugin.hpp"
 
+#include <omp.h>
+
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -193,6 +199,13 @@ bool tolerates(const Toleration& t, const Taint& taint) {
   return false;
 }
 
+// threads for the packer: BS_HOST_THREADS, else up to 8 (small inputs stay single-threaded)
+int pack_threads(size_t objects) {
+  if (objects < 4096) return 1;
+  if (const char* s = getenv("BS_HOST_THREADS")) return std::max(1, atoi(s));
+  return std::max(1, std::min(8, (int)std::thread::hardware_concurrency()));
+}
+
 std::string joined_sorted(std::vector<std::string> v) {
   std::sort(v.begin(), v.end());  // sortkeys.Strings (core.go:498,507)
   std::string s;
@@ -214,17 +227,60 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   PackedSnapshot& ps = *out;
   ps = PackedSnapshot();
   const uint32_t N = (uint32_t)snapshot.size(), P = (uint32_t)pending.size(), G = (uint32_t)groups.size();
+  const bool prof = getenv("BS_PACK_PROFILE") != nullptr;
+  double tp = now_ms();
+  auto phase = [&](const char* name) {
+    if (!prof) return;
+    const double t = now_ms();
+    fprintf(stderr, "[pack] %-12s %.2f ms\n", name, t - tp);
+    tp = t;
+  };
   // ---- lanes: scalar resources in first-seen order (nodes, groups, pods)
+  // Objects are scanned in parallel; each thread records the scalar names it meets with the position
+  // (object class, index) of their first appearance, and the merge keeps the global first-seen order.
   LaneTable lt;
-  for (auto* ni : snapshot) {
-    if (!ni) continue;
-    if (ni->node) lt.scan(ni->node->allocatable);
-    lt.scan(ni->requested);
+  const int T = pack_threads((size_t)N + P + G);
+  {
+    struct Seen { uint64_t pos; std::string name; };
+    std::vector<std::vector<Seen>> seen(T);
+    auto note = [&](std::vector<Seen>& mine, uint64_t pos, const ResourceList& rl) {
+      for (auto& kv : rl) {
+        const std::string& nm = kv.first;
+        if (nm == "cpu" || nm == "memory" || nm == "ephemeral-storage" || nm == "pods") continue;
+        if (!IsScalarResourceName(nm)) continue;
+        bool dup = false;
+        for (auto& s2 : mine) if (s2.name == nm) { dup = true; break; }
+        if (!dup) mine.push_back(Seen{pos, nm});
+      }
+    };
+#pragma omp parallel num_threads(T)
+    {
+      std::vector<Seen>& mine = seen[omp_get_thread_num()];
+#pragma omp for schedule(static) nowait
+      for (uint32_t i = 0; i < N; ++i) {
+        const NodeInfo* ni = snapshot[i];
+        if (!ni) continue;
+        if (ni->node) note(mine, ((uint64_t)0 << 40) | ((uint64_t)i << 1), ni->node->allocatable);
+        note(mine, ((uint64_t)0 << 40) | ((uint64_t)i << 1) | 1, ni->requested);
+      }
+#pragma omp for schedule(static) nowait
+      for (uint32_t g = 0; g < G; ++g)
+        if (groups[g].pg->has_min_resources) note(mine, ((uint64_t)1 << 40) | g, groups[g].pg->min_resources);
+#pragma omp for schedule(static) nowait
+      for (uint32_t i = 0; i < P; ++i)
+        for (auto& c : pending[i]->containers) note(mine, ((uint64_t)2 << 40) | i, container_demand(c));
+#pragma omp for schedule(static) nowait
+      for (uint32_t g = 0; g < G; ++g)
+        if (groups[g].rep_pod)
+          for (auto& c : groups[g].rep_pod->containers) note(mine, ((uint64_t)3 << 40) | g, container_demand(c));
+    }
+    std::vector<Seen> all;
+    for (auto& v : seen) all.insert(all.end(), v.begin(), v.end());
+    std::stable_sort(all.begin(), all.end(), [](const Seen& a, const Seen& b) { return a.pos < b.pos; });
+    for (auto& s2 : all) lt.lane(s2.name, true);
   }
-  for (auto& g : groups) if (g.pg->has_min_resources) lt.scan(g.pg->min_resources);
-  for (auto* p : pending) for (auto& c : p->containers) lt.scan(container_demand(c));
-  for (auto& g : groups) if (g.rep_pod) for (auto& c : g.rep_pod->containers) lt.scan(container_demand(c));
   if (lt.overflow) { bad.message = "more than 12 scalar resources"; return bad; }
+  phase("lane scan");
   const uint32_t L = BS_FIXED_LANES + (uint32_t)lt.scalars.size();
   ps.lanes = L;
   ps.scalar_names = lt.scalars;
@@ -248,24 +304,34 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   ps.alloc.assign((size_t)L * N, 0); ps.requested.assign((size_t)L * N, 0);
   ps.pod_count.assign(N, 0); ps.alloc_present.assign(N, 0); ps.req_present.assign(N, 0);
   ps.label_mask.assign(N, 0); ps.taint_mask.assign(N, 0); ps.node_flags.assign(N, 0);
-  std::vector<int64_t> tmp(L);
+  phase("selectors");
+  // taints: sequential pre-pass (first-seen order defines the bit), then the nodes in parallel
+  for (uint32_t i = 0; i < N; ++i) {
+    const NodeInfo* ni = snapshot[i];
+    if (!ni || !ni->node) continue;
+    for (auto& t : ni->node->taints)
+      if (t.effect == "NoSchedule" || t.effect == "NoExecute") taint_bit(t);   // PodToleratesNodeTaints filter
+  }
+  if (taints.size() > 64) { bad.message = "more than 64 distinct taints in one round"; return bad; }
+  std::atomic<int> err{0};
+#pragma omp parallel for num_threads(T) schedule(static)
   for (uint32_t i = 0; i < N; ++i) {
     const NodeInfo* ni = snapshot[i];
     if (!ni) { ps.node_flags[i] = BS_NODE_NIL; continue; }              // core.go:606
+    int64_t tmp[BS_MAX_LANES] = {};
     if (!ni->node) ps.node_flags[i] |= BS_NODE_NO_NODE;                 // core.go:610
     if (ni->taints_error) ps.node_flags[i] |= BS_NODE_TAINTS_ERR;       // core.go:639
     ps.pod_count[i] = ni->num_pods;
     uint32_t pres = 0;
-    std::fill(tmp.begin(), tmp.end(), 0);
-    if (!add_list(lt, ni->requested, tmp.data(), &pres)) { bad.message = "bad quantity in requested"; return bad; }
+    if (!add_list(lt, ni->requested, tmp, &pres)) { err = 1; continue; }
     for (uint32_t d = 0; d < L; ++d) ps.requested[(size_t)d * N + i] = tmp[d];
     ps.req_present[i] = pres;
     if (!ni->node) continue;
     const Node& nd = *ni->node;
     if (nd.unschedulable) ps.node_flags[i] |= BS_NODE_UNSCHEDULABLE;    // core.go:615
     pres = 0;
-    std::fill(tmp.begin(), tmp.end(), 0);
-    if (!add_list(lt, nd.allocatable, tmp.data(), &pres)) { bad.message = "bad quantity in allocatable"; return bad; }
+    std::fill(tmp, tmp + BS_MAX_LANES, 0);
+    if (!add_list(lt, nd.allocatable, tmp, &pres)) { err = 2; continue; }
     for (uint32_t d = 0; d < L; ++d) ps.alloc[(size_t)d * N + i] = tmp[d];
     ps.alloc_present[i] = pres;
     for (auto& kv : sel_bit) {
@@ -273,15 +339,19 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
       if (it != nd.labels.end() && it->second == kv.first.second) ps.label_mask[i] |= 1ull << kv.second;
     }
     for (auto& t : nd.taints) {
-      if (t.effect != "NoSchedule" && t.effect != "NoExecute") continue;  // PodToleratesNodeTaints filter
-      const int b = taint_bit(t);
-      if (b >= 64) { bad.message = "more than 64 distinct taints in one round"; return bad; }
-      ps.taint_mask[i] |= 1ull << b;
+      if (t.effect != "NoSchedule" && t.effect != "NoExecute") continue;
+      for (size_t b = 0; b < taints.size(); ++b)
+        if (taints[b].key == t.key && taints[b].value == t.value && taints[b].effect == t.effect) {
+          ps.taint_mask[i] |= 1ull << b;
+          break;
+        }
     }
   }
+  if (err) { bad.message = err == 1 ? "bad quantity in requested" : "bad quantity in allocatable"; return bad; }
+  phase("nodes");
   auto pod_masks = [&](const Pod& p, uint64_t* sel, uint64_t* tol) {
     *sel = 0; *tol = 0;
-    for (auto& kv : p.node_selector) *sel |= 1ull << sel_bit[kv];
+    for (auto& kv : p.node_selector) *sel |= 1ull << sel_bit.at(kv);
     for (size_t b = 0; b < taints.size(); ++b)
       for (auto& t : p.tolerations)
         if (tolerates(t, taints[b])) { *tol |= 1ull << b; break; }
@@ -296,26 +366,37 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   ps.min_member.assign(G, 0); ps.scheduled.assign(G, 0); ps.matched.assign(G, 0); ps.group_flags.assign(G, 0);
   ps.min_res.assign((size_t)L * G, 0); ps.min_res_present.assign(G, 0); ps.rep_sel.assign(G, 0);
   ps.rep_tol.assign(G, 0); ps.creation_ns.assign(G, 0); ps.name_rank.assign(G, 0); ps.wait_ns.assign(G, 0);
-  std::set<std::string> names;
-  for (auto& g : groups) names.insert(g.pg->name);
-  std::unordered_map<std::string, uint32_t> rank_of;
-  { uint32_t r = 0; for (auto& n : names) rank_of[n] = r++; }  // byte-wise ascending (Go string compare)
+  // bare-name ranks, byte-wise ascending (Go string compare); equal names share a rank (core.go:404)
+  std::vector<uint32_t> by_name(G);
+  for (uint32_t g = 0; g < G; ++g) by_name[g] = g;
+  std::sort(by_name.begin(), by_name.end(),
+            [&](uint32_t a, uint32_t b) { return groups[a].pg->name < groups[b].pg->name; });
+  std::vector<uint32_t> rank_of_group(G);
+  {
+    uint32_t r = 0;
+    for (uint32_t k = 0; k < G; ++k) {
+      if (k > 0 && groups[by_name[k]].pg->name != groups[by_name[k - 1]].pg->name) ++r;
+      rank_of_group[by_name[k]] = r;
+    }
+  }
+  gindex.reserve((size_t)G * 2);
+  for (uint32_t g = 0; g < G; ++g) gindex.emplace(groups[g].pg->ns + "/" + groups[g].pg->name, g);
+#pragma omp parallel for num_threads(T) schedule(static)
   for (uint32_t g = 0; g < G; ++g) {
     const PodGroup& pg = *groups[g].pg;
-    gindex[pg.ns + "/" + pg.name] = g;
+    int64_t tmp[BS_MAX_LANES] = {};
     ps.min_member[g] = pg.min_member;
     ps.scheduled[g] = pg.scheduled;
     ps.matched[g] = groups[g].matched;
     ps.group_flags[g] = groups[g].flags & (BS_GROUP_SCHEDULED | BS_GROUP_HAS_POD | BS_GROUP_DENIED);
     ps.creation_ns[g] = pg.creation_ns;
-    ps.name_rank[g] = rank_of[pg.name];
+    ps.name_rank[g] = rank_of_group[g];
     // util.GetWaitTimeDuration (k8s.go:82-91): Spec.MaxScheduleTime wins, else the plugin default
     ps.wait_ns[g] = pg.max_schedule_time_ns >= 0 ? pg.max_schedule_time_ns : default_wait_ns;
     if (pg.has_min_resources) {
       ps.group_flags[g] |= BS_GROUP_HAS_MINRES;
       uint32_t pres = 0;
-      std::fill(tmp.begin(), tmp.end(), 0);
-      if (!add_list(lt, pg.min_resources, tmp.data(), &pres)) { bad.message = "bad quantity in MinResources"; return bad; }
+      if (!add_list(lt, pg.min_resources, tmp, &pres)) { err = 3; continue; }
       for (uint32_t d = 0; d < L; ++d) ps.min_res[(size_t)d * G + g] = tmp[d];
       ps.min_res_present[g] = pres;
     }
@@ -324,17 +405,21 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
       pod_masks(*groups[g].rep_pod, &ps.rep_sel[g], &ps.rep_tol[g]);
     }
   }
-  // ---- pods (arrival order); occupancy follows fillOccupiedObj sequentially (core.go:494-511)
+  if (err) { bad.message = "bad quantity in MinResources"; return bad; }
+  phase("groups");
+  // ---- pods (arrival order): demand / masks / group lookup in parallel, then the occupancy
+  // rule sequentially, as fillOccupiedObj is order dependent (core.go:494-511)
   ps.req.assign((size_t)L * P, 0); ps.pod_req_present.assign(P, 0); ps.gid.assign(P, BS_GID_NONE);
   ps.sel_mask.assign(P, 0); ps.tol_mask.assign(P, 0); ps.priority.assign(P, 0); ps.ts_ns.assign(P, 0);
   ps.pod_flags.assign(P, 0);
   std::vector<std::string> occupied(G);
   for (uint32_t g = 0; g < G; ++g) occupied[g] = groups[g].pg->occupied_by;
+#pragma omp parallel for num_threads(T) schedule(static)
   for (uint32_t i = 0; i < P; ++i) {
     const Pod& p = *pending[i];
     uint32_t pres = 0;
-    std::fill(tmp.begin(), tmp.end(), 0);
-    if (!pod_demand(p, tmp.data(), &pres)) { bad.message = "bad quantity in pod " + p.name; return bad; }
+    int64_t tmp[BS_MAX_LANES] = {};
+    if (!pod_demand(p, tmp, &pres)) { err = 4; continue; }
     for (uint32_t d = 0; d < L; ++d) ps.req[(size_t)d * P + i] = tmp[d];
     ps.pod_req_present[i] = pres;
     pod_masks(p, &ps.sel_mask[i], &ps.tol_mask[i]);
@@ -342,21 +427,31 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
     ps.ts_ns[i] = p.queue_ts_ns;
     uint8_t fl = i < pod_flags_in.size() ? pod_flags_in[i] : 0;
     auto lab = p.labels.find(kPodGroupLabel);                          // util.VerifyPodLabelSatisfied k8s.go:62-70
-    if (lab == p.labels.end() || lab->second.empty()) { ps.pod_flags[i] = fl; continue; }
-    auto gi = gindex.find(p.ns + "/" + lab->second);
-    if (gi == gindex.end()) { ps.gid[i] = BS_GID_MISSING; ps.pod_flags[i] = fl | BS_POD_LISTER_MISS; continue; }
-    const uint32_t g = gi->second;
-    ps.gid[i] = (int32_t)g;
-    const bool reaches = !(fl & BS_POD_PERMITTED_RECENTLY) && !(ps.group_flags[g] & BS_GROUP_DENIED);
-    if (reaches) {
-      const std::string refs = joined_sorted(p.owner_uids);
-      if (occupied[g].empty()) {
-        if (!p.owner_uids.empty()) occupied[g] = refs;                 // core.go:496-500
-      } else if (p.owner_uids.empty()) fl |= BS_POD_OCC_NOREFS;        // core.go:504-506
-      else if (refs != occupied[g]) fl |= BS_POD_OCC_MISMATCH;         // core.go:507-510
+    if (lab != p.labels.end() && !lab->second.empty()) {
+      auto gi = gindex.find(p.ns + "/" + lab->second);
+      if (gi == gindex.end()) { ps.gid[i] = BS_GID_MISSING; fl |= BS_POD_LISTER_MISS; }
+      else ps.gid[i] = (int32_t)gi->second;
     }
     ps.pod_flags[i] = fl;
   }
+  if (err) { bad.message = "bad quantity in a pod's containers"; return bad; }
+  phase("pods par");
+  for (uint32_t i = 0; i < P; ++i) {
+    const int32_t gidx = ps.gid[i];
+    if (gidx < 0) continue;
+    const uint32_t g = (uint32_t)gidx;
+    const Pod& p = *pending[i];
+    uint8_t fl = ps.pod_flags[i];
+    const bool reaches = !(fl & BS_POD_PERMITTED_RECENTLY) && !(ps.group_flags[g] & BS_GROUP_DENIED);
+    if (reaches) {
+      if (occupied[g].empty()) {
+        if (!p.owner_uids.empty()) occupied[g] = joined_sorted(p.owner_uids);   // core.go:496-500
+      } else if (p.owner_uids.empty()) fl |= BS_POD_OCC_NOREFS;                 // core.go:504-506
+      else if (joined_sorted(p.owner_uids) != occupied[g]) fl |= BS_POD_OCC_MISMATCH;  // core.go:507-510
+    }
+    ps.pod_flags[i] = fl;
+  }
+  phase("occupancy");
   return Status{};
 }
 
