@@ -1089,8 +1089,77 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   if (P && (!t->req || !t->req_present || !t->gid || !t->sel_mask || !t->tol_mask || !t->priority ||
             !t->ts_ns || !t->flags))
     return fail(e, BS_E_INVAL, "bs_upload_pods: null column");
+  // ONE parallel pass over the table before anything is committed: per-lane maxima (range check and
+  // wide/narrow lane classification), the varying bits of the sort keys, thread-local class indices
+  // (fit class = (sel, tol, scalar keys requested with a non-zero amount, core.go:688-690);
+  // representative class = (sel, tol)), and the host copies the per-call mirrors read.
+  const int T = P < 8192 ? 1 : host_threads();
+  struct Part {
+    int64_t lo[BS_MAX_LANES], hi[BS_MAX_LANES];
+    uint64_t ot = 0, at = ~0ull;
+    uint32_t op = 0, apr = ~0u;
+    int miss = 0;
+    int32_t mg = -1;
+    ClassIndex fit, rep;
+  };
+  std::vector<Part> part(T);
+  e->h_gid.resize(P); e->h_prio.resize(P); e->h_pflags.resize(P); e->h_pfc.resize(P); e->h_prc.resize(P);
+  const uint32_t chunk = (P + T - 1) / std::max(T, 1);
+#pragma omp parallel num_threads(T)
+  {
+    Part& pt = part[omp_get_thread_num()];
+    for (uint32_t d = 0; d < BS_MAX_LANES; ++d) { pt.lo[d] = 0; pt.hi[d] = 0; }
+    pt.fit.clear();
+    pt.rep.clear();
+    const uint32_t a0 = std::min(P, (uint32_t)omp_get_thread_num() * chunk), a1 = std::min(P, a0 + chunk);
+    for (uint32_t d = 0; d < L; ++d) {
+      const int64_t* row = t->req + (size_t)d * P;
+      int64_t lo = 0, hi = 0;
+      for (uint32_t p = a0; p < a1; ++p) { lo = std::min(lo, row[p]); hi = std::max(hi, row[p]); }
+      pt.lo[d] = lo; pt.hi[d] = hi;
+    }
+    for (uint32_t p = a0; p < a1; ++p) {
+      const uint64_t ts = (uint64_t)t->ts_ns[p];
+      const uint32_t pr = (uint32_t)t->priority[p];
+      const int32_t g = t->gid[p];
+      const uint8_t fl = t->flags[p];
+      pt.ot |= ts; pt.at &= ts; pt.op |= pr; pt.apr &= pr;
+      pt.miss |= ((g < BS_GID_NONE) || (fl & BS_POD_LISTER_MISS)) ? 1 : 0;
+      pt.mg = std::max(pt.mg, g);
+      e->h_gid[p] = g; e->h_prio[p] = (int32_t)pr; e->h_pflags[p] = fl;
+      uint32_t nz = 0;
+      const uint32_t rp = t->req_present[p];
+      for (uint32_t d = 4; d < L; ++d)
+        if (((rp >> d) & 1u) && t->req[(size_t)d * P + p] != 0) nz |= 1u << d;
+      e->h_pfc[p] = pt.fit.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], nz});
+      e->h_prc[p] = pt.rep.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], 0u});
+    }
+  }
   int64_t mx_q[BS_MAX_LANES] = {};
-  if (!lane_maxima(t->req, L, P, mx_q)) return fail(e, BS_E_RANGE, "bs_upload_pods: value outside +-2^56");
+  {
+    uint64_t ot = 0, at = ~0ull;
+    uint32_t op = 0, apr = ~0u;
+    int miss = 0;
+    int32_t mg = -1;
+    bool ok = true;
+    for (int k = 0; k < T; ++k) {
+      const Part& pt = part[k];
+      for (uint32_t d = 0; d < L; ++d) {
+        ok = ok && pt.lo[d] >= -BS_VALUE_LIMIT && pt.hi[d] <= BS_VALUE_LIMIT;
+        mx_q[d] = std::max(mx_q[d], std::max(pt.hi[d], pt.lo[d] == INT64_MIN ? INT64_MAX : -pt.lo[d]));
+      }
+      ot |= pt.ot; at &= pt.at; op |= pt.op; apr &= pt.apr; miss |= pt.miss; mg = std::max(mg, pt.mg);
+    }
+    if (!ok) {
+      e->have_pods = false;   // the host-side columns were already overwritten: drop the table
+      e->evaluated = false;
+      return fail(e, BS_E_RANGE, "bs_upload_pods: value outside +-2^56");
+    }
+    e->vary_ts = P ? (ot ^ at) : 0;
+    e->vary_prio = P ? (uint64_t)(op ^ apr) : 0;
+    e->any_lister_miss = miss != 0;
+    e->max_gid = mg;
+  }
   CK(cudaSetDevice(e->device));
   const uint32_t Pp = std::max(P, 1u);
   int rc;
@@ -1100,47 +1169,27 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
-  // host copies for the per-call mirrors
-  e->h_gid.assign(t->gid, t->gid + P);
-  e->h_prio.assign(t->priority, t->priority + P);
-  e->h_pflags.assign(t->flags, t->flags + P);
-  {
-    uint64_t ot = 0, at = ~0ull;
-    uint32_t op = 0, apr = ~0u;
-    int miss = 0;
-    int32_t mg = -1;
-#pragma omp parallel for reduction(| : ot, op, miss) reduction(& : at, apr) reduction(max : mg) \
-    if (P > 65536) num_threads(host_threads())
-    for (uint32_t p = 0; p < P; ++p) {
-      const uint64_t ts = (uint64_t)t->ts_ns[p];
-      const uint32_t pr = (uint32_t)t->priority[p];
-      ot |= ts; at &= ts; op |= pr; apr &= pr;
-      miss |= ((t->gid[p] < BS_GID_NONE) || (t->flags[p] & BS_POD_LISTER_MISS)) ? 1 : 0;
-      mg = std::max(mg, t->gid[p]);
-    }
-    e->vary_ts = P ? (ot ^ at) : 0;
-    e->vary_prio = P ? (uint64_t)(op ^ apr) : 0;
-    e->any_lister_miss = miss != 0;
-    e->max_gid = mg;
-  }
-  // class indices: fit class = (sel, tol, scalar keys requested with a non-zero amount,
-  // core.go:688-690); representative class = (sel, tol).  Both indices restart with the pod table.
+  // merge the thread-local class indices (both restart with the pod table) and remap the ids while
+  // the DMA is in flight
   e->fit_index.clear();
   e->rep_index.clear();
-  e->h_pfc.resize(P);
-  e->h_prc.resize(P);
   {
-    const bs_pod_table tt = *t;
-    const uint32_t LL = L, PP = P;
-    assign_classes(e->fit_index, P, [=](uint32_t p) {
-      uint32_t nz = 0;
-      const uint32_t rp = tt.req_present[p];
-      for (uint32_t d = 4; d < LL; ++d)
-        if (((rp >> d) & 1u) && tt.req[(size_t)d * PP + p] != 0) nz |= 1u << d;
-      return ClassKey{tt.sel_mask[p], tt.tol_mask[p], nz};
-    }, e->h_pfc.data());
-    assign_classes(e->rep_index, P, [=](uint32_t p) { return ClassKey{tt.sel_mask[p], tt.tol_mask[p], 0u}; },
-                   e->h_prc.data());
+    std::vector<std::vector<uint32_t>> rf(T), rr(T);
+    for (int k = 0; k < T; ++k) {
+      rf[k].resize(part[k].fit.size());
+      rr[k].resize(part[k].rep.size());
+      for (size_t j = 0; j < part[k].fit.size(); ++j) rf[k][j] = e->fit_index.get_or_add(part[k].fit.keys[j]);
+      for (size_t j = 0; j < part[k].rep.size(); ++j) rr[k][j] = e->rep_index.get_or_add(part[k].rep.keys[j]);
+    }
+#pragma omp parallel num_threads(T)
+    {
+      const int k = omp_get_thread_num();
+      const uint32_t a0 = std::min(P, (uint32_t)k * chunk), a1 = std::min(P, a0 + chunk);
+      for (uint32_t p = a0; p < a1; ++p) {
+        e->h_pfc[p] = rf[k][e->h_pfc[p]];
+        e->h_prc[p] = rr[k][e->h_prc[p]];
+      }
+    }
   }
   e->group_classes_dirty = true;
   CK(cudaStreamSynchronize(e->s));
