@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists(plugin):
         srcs.append(plugin)
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-shared", "-Xcompiler", "-fPIC,-Wall,-fopenmp", "-fmad=false", "-o", LIB] + srcs + ["-lgomp"]
+           "-shared", "-Xcompiler", "-fPIC,-Wall,-fopenmp", "-fmad=false", "-diag-suppress=186,550", "-o", LIB] + srcs + ["-lgomp"]
     extra = os.environ.get("BS_NVCC_EXTRA", "").split()
     if extra:
         cmd[1:1] = extra

@@ -509,9 +509,10 @@ int bso_round(const bso_nodes* nd, const bso_pods* pd, const bso_groups* gr, bso
         if (m >= 0 && gr->matched[m] == 0 && g >= 0 && (uint32_t)g < G &&
             (code == BSO_PF_PASS || code == BSO_PF_NOT_ENOUGH) && reaches_fill(pd, gr, p) &&
             !(pd->flags[p] & (BSO_POD_OCC_NOREFS | BSO_POD_OCC_MISMATCH))) {
-          const uint8_t c = (code == BSO_PF_PASS) ? 1 : 2;
+          uint8_t c = (code == BSO_PF_PASS) ? 1 : 2;
 #pragma omp atomic write
           gcache[g] = c;
+          (void)c;
         }
       }
     }
