@@ -607,7 +607,10 @@ int ensure_round_buffers(bs_engine* e) {
   }
   // prefix scratch: as many rep-class slots as fit a 1 GiB budget
   const size_t per_class = (size_t)N * (8 * L + 4);
-  uint32_t slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(e->n_rep_classes, ((size_t)1 << 30) / per_class));
+  // BS_PREFIX_BUDGET_BYTES (default 1 GiB) bounds the scratch; classes beyond it are processed in chunks
+  size_t budget = (size_t)1 << 30;
+  if (const char* bs = getenv("BS_PREFIX_BUDGET_BYTES")) budget = std::max<size_t>(1, strtoull(bs, nullptr, 10));
+  uint32_t slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(e->n_rep_classes, budget / per_class));
   e->prefix_slots = slots;
   CK(e->d_pre.ensure((size_t)slots * L * N * 8));
   CK(e->d_pre_present.ensure((size_t)slots * N * 4));

@@ -288,3 +288,53 @@ def test_out_of_memory_is_reported_not_fatal(pkg, snapshot_mod):
     eng.upload(small)
     eng.evaluate()
     eng.close()
+
+
+def test_find_max_tie_rule_on_gpu(pkg, oracle, snapshot_mod):
+    """findMaxPG's order-dependent tie rule (core.go:725-735) through the parallel merge: many groups
+    with equal progress, finished holders, Status.Scheduled==0 challengers, MinMember==0 chains."""
+    S = snapshot_mod
+    rng = np.random.default_rng(123)
+    for trial in range(40):
+        G = int(rng.integers(1, 3000))
+        snap = random_snapshot(1000 + trial, P=64, N=20, G=G, L=4)
+        gt = snap.groups
+        gt.flags[:] = S.GROUP_HAS_POD | S.GROUP_HAS_MINRES
+        gt.flags[rng.random(G) < 0.1] |= S.GROUP_SCHEDULED
+        mode = trial % 4
+        if mode == 0:      # everything at progress 0, mixed finished / unfinished holders
+            gt.matched[:] = 0
+            gt.min_member[:] = rng.choice([0, 1, 2, 5], G)
+            gt.scheduled[:] = np.where(rng.random(G) < 0.5, gt.min_member, 0)
+        elif mode == 1:    # equal non-zero progress everywhere
+            gt.min_member[:] = 4
+            gt.scheduled[:] = rng.choice([0, 0, 1], G)
+            gt.matched[:] = 2 - gt.scheduled
+        elif mode == 2:    # holder finished (scheduled > minMember wraps), challengers with Scheduled == 0
+            gt.min_member[:] = rng.choice([1, 2, 3], G)
+            gt.scheduled[:] = np.where(rng.random(G) < 0.3, gt.min_member, 0)
+            gt.matched[:] = 0
+        else:              # MinMember == 0 with Scheduled == 0 chains (0 >= 0 is "finished")
+            gt.min_member[:] = rng.choice([0, 0, 3], G)
+            gt.scheduled[:] = 0
+            gt.matched[:] = 0
+        gt.scheduled[(gt.min_member == 0) & (gt.scheduled != 0)] = 0   # avoid the divide-by-zero panic
+        m, fin, panic = oracle.find_max_pg(snap.resolve_groups().groups)
+        assert not panic
+        eng = pkg.Engine(snap.lanes, 0, fit_bitmap=False, score=False)
+        eng.upload(snap)
+        res = eng.evaluate()
+        eng.close()
+        assert (res.max_group, res.max_finished) == (m, fin), (trial, mode, G)
+
+
+def test_prefix_scratch_chunking(pkg, oracle, monkeypatch):
+    """Case A with more representative classes than scratch slots: the class loop runs in chunks."""
+    snap = random_snapshot(4242, P=400, N=300, G=60, L=6, case="A")
+    rng = np.random.default_rng(1)
+    snap.groups.rep_sel = rng.integers(0, 16, snap.groups.n).astype(np.uint64)    # many distinct classes
+    snap.groups.rep_tol = rng.integers(0, 4, snap.groups.n).astype(np.uint64)
+    snap.pods.sel_mask = rng.integers(0, 16, snap.pods.n).astype(np.uint64)
+    snap.pods.tol_mask = rng.integers(0, 4, snap.pods.n).astype(np.uint64)
+    monkeypatch.setenv("BS_PREFIX_BUDGET_BYTES", str(3 * 300 * (8 * 6 + 4)))       # 3 class slots
+    run_and_compare(pkg, oracle, snap)
