@@ -660,7 +660,7 @@ int prepare_nodes(bs_engine* e) {
   CK(e->d_left_present.ensure((size_t)e->Npad * 4));
   if (e->out_flags & BS_OUT_FILTER) CK(e->d_left_plain.ensure((size_t)4 * e->Npad * 8));
   const uint32_t n_tiles = e->Npad / NODE_TILE;
-  CK(e->d_classfit.ensure((size_t)e->n_fit_classes * n_tiles * 32 * 4));
+  CK(e->d_classfit.ensure((size_t)e->n_fit_classes * n_tiles * 32 * sizeof(ColBits)));
   node_left_kernel<<<cdiv(e->Npad, 256), 256, 0, e->s>>>(t, e->lane_map, e->d_left_w.as<int64_t>(),
                                                          e->d_left_n.as<int32_t>(),
                                                          e->d_left_present.as<uint32_t>(),
@@ -670,7 +670,7 @@ int prepare_nodes(bs_engine* e) {
     dim3 grid(cdiv(n_tiles * 32, 256), e->n_fit_classes);
     class_fit_kernel<<<grid, 256, 0, e->s>>>(t, e->d_left_present.as<uint32_t>(), e->d_fsel.as<uint64_t>(),
                                              e->d_ftol.as<uint64_t>(), e->d_fnz.as<uint32_t>(),
-                                             e->n_fit_classes, n_tiles, e->d_classfit.as<uint32_t>());
+                                             e->n_fit_classes, n_tiles, e->d_classfit.as<ColBits>());
     tm.launched();
   }
   CK(cudaGetLastError());
@@ -814,7 +814,7 @@ int evaluate_async_locked(bs_engine* e) {
       a.lm = e->lane_map;
       a.left_w_pitch = (uint64_t)e->Npad * 8;
       a.left_n_pitch = (uint64_t)e->Npad * 4;
-      a.classfit = e->d_classfit.as<uint32_t>();
+      a.classfit = e->d_classfit.as<ColBits>();
       a.req = e->d_req.as<int64_t>();
       a.req_present = e->d_ppres.as<uint32_t>();
       a.fit_class = e->d_pod_fit_class.as<uint32_t>();

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/bsched.h"
 
 namespace bsk {
@@ -33,7 +35,10 @@ struct LaneMap {
   uint8_t narrow[BS_MAX_LANES];  // original lane index of narrow slot k (k < LN)
   uint32_t LW, LN;
 };
-constexpr int NODE_TILE = 512;                          // nodes per shared-memory tile
+#ifndef BS_FIT_TILE
+#define BS_FIT_TILE 512
+#endif
+constexpr int NODE_TILE = BS_FIT_TILE;                  // nodes per shared-memory tile (512 / 1024 / 2048)
 #ifndef BS_FIT_WARPS
 #define BS_FIT_WARPS 8
 #endif
@@ -44,8 +49,13 @@ constexpr int FIT_WARPS = BS_FIT_WARPS;                 // consumer warps (each 
 constexpr int FIT_THREADS = (FIT_WARPS + 1) * 32;       // + one producer warp that only drives the TMA ring
 constexpr int PODS_PER_WARP = BS_FIT_PPW;               // pods evaluated together per node (ILP)
 constexpr int PODS_PER_CTA = FIT_WARPS * PODS_PER_WARP; // 32
-constexpr int TILE_WORDS = NODE_TILE / 32;              // 16 ballot words per tile and pod
-constexpr int FIT_STAGES = 3;                           // TMA ring depth (full/empty mbarrier pairs)
+constexpr int TILE_WORDS = NODE_TILE / 32;              // ballot words per tile and pod
+#ifndef BS_FIT_STAGES
+#define BS_FIT_STAGES 3
+#endif
+constexpr int FIT_STAGES = BS_FIT_STAGES;               // TMA ring depth (full/empty mbarrier pairs)
+// class bits of the TILE_WORDS nodes a lane owns in one tile
+using ColBits = std::conditional<(TILE_WORDS > 32), uint64_t, uint32_t>::type;
 #ifndef BS_FIT_MINB
 #define BS_FIT_MINB 2
 #endif
@@ -217,14 +227,14 @@ __global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, fl
 __global__ void class_fit_kernel(NodeTab t, const uint32_t* __restrict__ left_present,
                                  const uint64_t* __restrict__ csel, const uint64_t* __restrict__ ctol,
                                  const uint32_t* __restrict__ cnz, uint32_t n_classes, uint32_t n_tiles,
-                                 uint32_t* __restrict__ classfit) {
+                                 ColBits* __restrict__ classfit) {
   const uint32_t c = blockIdx.y;
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;  // tile * 32 + lane
   if (slot >= n_tiles * 32 || c >= n_classes) return;
   const uint32_t tile = slot >> 5, lane = slot & 31;
   const uint64_t sel = csel[c], tol = ctol[c];
   const uint32_t nz = cnz[c];
-  uint32_t bits = 0;
+  ColBits bits = 0;
 #pragma unroll
   for (int j = 0; j < TILE_WORDS; ++j) {
     const uint32_t i = tile * NODE_TILE + j * 32 + lane;
@@ -234,7 +244,7 @@ __global__ void class_fit_kernel(NodeTab t, const uint32_t* __restrict__ left_pr
       ok = !node_skipped(f) && !(f & BS_NODE_TAINTS_ERR) && check_fit(t.label[i], t.taint[i], sel, tol) &&
            ((nz & ~left_present[i]) == 0);
     }
-    bits |= (ok ? 1u : 0u) << j;
+    bits |= (ColBits)(ok ? 1u : 0u) << j;
   }
   classfit[(size_t)c * n_tiles * 32 + slot] = bits;
 }
@@ -997,7 +1007,7 @@ __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
 struct FitArgs {
   const int64_t* left_w;     // [LW][Npad] wide lanes
   const int32_t* left_n;     // [LN][Npad] narrow lanes
-  const uint32_t* classfit;  // [classes][n_tiles][32] transposed class bits
+  const ColBits* classfit;   // [classes][n_tiles][32] transposed class bits
   const int64_t* req;        // [L][P]
   const uint32_t* req_present;
   const uint32_t* fit_class;
@@ -1043,7 +1053,7 @@ __device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __rest
                                          const int32_t* __restrict__ tln,
                                          const int64_t (&rqw)[PODS_PER_WARP][LW > 0 ? LW : 1],
                                          const int32_t (&rqn)[PODS_PER_WARP][LN > 0 ? LN : 1],
-                                         const uint32_t (&colbits)[PODS_PER_WARP], int64_t* sp0,
+                                         const ColBits (&colbits)[PODS_PER_WARP], int64_t* sp0,
                                          size_t row_stride, uint32_t* s_words, uint32_t node_base,
                                          uint32_t lane, bool want_score,
                                          typename BestT<(LN > 0)>::type (&best_s)[PODS_PER_WARP],
@@ -1223,7 +1233,7 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
   // FIT_STAGES-1 tiles ahead of the slowest warp.
   uint32_t stage = 0, phase = 0;
   for (uint32_t tile = 0; tile < n_tiles; ++tile) {
-    uint32_t colbits[PODS_PER_WARP];
+    ColBits colbits[PODS_PER_WARP];
 #pragma unroll
     for (int r = 0; r < PODS_PER_WARP; ++r) colbits[r] = __ldg(a.classfit + coff[r] + tile * 32);
     mbar_wait(&s_full[stage], phase);
@@ -1237,13 +1247,16 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
       fit_tile<LW, LN, true>(a, tlw, tln, rqw, rqn, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the stage
-    if (lane < TILE_WORDS) {
-      const uint32_t word = (node_base >> 5) + lane;
 #pragma unroll
-      for (int r = 0; r < PODS_PER_WARP; ++r) {
-        const uint32_t w = s_words[r * TILE_WORDS + lane];
-        cnt[r] += __popc(w);
-        if (want_bitmap && word < a.W) a.fit_bitmap[(size_t)(wpod0 + r) * a.W + word] = w;
+    for (int w0 = 0; w0 < TILE_WORDS; w0 += 32) {
+      if (w0 + lane < TILE_WORDS) {
+        const uint32_t word = (node_base >> 5) + w0 + lane;
+#pragma unroll
+        for (int r = 0; r < PODS_PER_WARP; ++r) {
+          const uint32_t w = s_words[r * TILE_WORDS + w0 + lane];
+          cnt[r] += __popc(w);
+          if (want_bitmap && word < a.W) a.fit_bitmap[(size_t)(wpod0 + r) * a.W + word] = w;
+        }
       }
     }
     __syncwarp();                                   // the ballot slab is rewritten by the next tile

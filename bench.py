@@ -309,6 +309,29 @@ def main():
         except Exception:
             traffic = None
 
+    # ---- decisions-only regime: same round, no P x N matrix leaves the SMs ------
+    fused = None
+    if world == 1:
+        eng2 = pkg.Engine(L, local_rank, fit_bitmap=False, score=False)
+        eng2.upload(snap)
+        for _ in range(3):
+            eng2.evaluate_async()
+        eng2.sync()
+        ext2 = torch.cuda.ExternalStream(eng2.stream(), device=local_rank)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext2)
+        nf = max(10, min(args.steps, 50))
+        for _ in range(nf):
+            eng2.evaluate_async()
+        f1.record(ext2)
+        eng2.sync()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / nf
+        fused = {"ms_per_step": fms, "value": float(P) * N / (fms * 1e-3), "unit": UNIT,
+                 "what": "same round with out_flags=0: prefilter/admit/order/feasible-count/best-node only; "
+                         "ALU-bound, no HBM roofline applies (tables are L2-resident)"}
+        eng2.close()
+
     # ---- e2e leg: host tables -> C ABI -> host decisions, every step ------------------------
     res = None
     for _ in range(2):
@@ -372,7 +395,8 @@ def main():
                             "vectors) per step, wall clock"},
             "gpu_launches": int(launches),
             "kernel_ms": kavg,
-            "roofline": {"bound": "hbm", "kernel": "gang_fit_kernel<5>", "achieved": achieved, "peak": peak,
+            "decisions_only": fused,
+            "roofline": {"bound": "hbm", "kernel": "gang_fit_kernel<LW=2,LN=3> (2 int64 + 3 int32 lanes)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": peak_src, "alg_bytes_per_launch": int(alg), "kernel_ms": fit_ms},
             "cpu_baseline": cpu,
