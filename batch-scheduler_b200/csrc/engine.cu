@@ -220,6 +220,7 @@ struct bs_engine {
   std::vector<int32_t> h_gid, h_prio;
   std::vector<uint8_t> h_pflags;
   std::vector<uint64_t> h_gsel, h_gtol;
+  std::vector<uint8_t> h_nflags;
   // class indices (host packing): fit classes (sel, tol, nz) of the pods; representative classes
   // (sel, tol) of pods and carried-in group representatives
   ClassIndex fit_index, rep_index;
@@ -382,6 +383,24 @@ PrefixScratch prefix_scratch(const bs_engine* e) {
   return sc;
 }
 
+// Makes the engine's device current for the scope and restores the caller's device afterwards
+// (the library must not leave the calling thread on a different device).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+#define BS_DEVICE_GUARD(e)        \
+  DeviceGuard _guard((e)->device); \
+  CK(_guard.err)
+
 struct StageTimer {
   bs_engine* e;
   int k;
@@ -429,13 +448,10 @@ void launch_prefix(uint32_t L, NodeTab t, PrefixSel ps, PrefixScratch sc, Prefix
 template <int LW, int LN>
 cudaError_t launch_fit_t(const FitArgs& a, uint32_t grid, cudaStream_t s) {
   const size_t smem = gang_fit_smem_bytes(LW, LN);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<LW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem);
-    if (er != cudaSuccess) return er;
-    attr_set = true;
-  }
+  // per launch, not cached: the attribute is per device and one process may drive several GPUs
+  cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<LW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem);
+  if (er != cudaSuccess) return er;
   gang_fit_kernel<LW, LN><<<grid, FIT_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -681,7 +697,7 @@ int prepare_nodes(bs_engine* e) {
 int evaluate_async_locked(bs_engine* e) {
   if (!e->have_nodes || !e->have_pods || !e->have_groups)
     return fail(e, BS_E_STATE, "bs_evaluate: upload nodes, groups and pods first");
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   int rc;
   bool reprepare = e->nodes_dirty;
   if (e->classes_dirty) {
@@ -944,7 +960,8 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
     return BS_E_NODEVICE;
   }
   if (cfg->device < 0 || cfg->device >= ndev) return BS_E_INVAL;
-  if (cudaSetDevice(cfg->device) != cudaSuccess) return BS_E_CUDA;
+  DeviceGuard guard(cfg->device);
+  if (guard.err != cudaSuccess) return BS_E_CUDA;
   bs_engine* e = new (std::nothrow) bs_engine();
   if (!e) return BS_E_NOMEM;
   e->device = cfg->device;
@@ -973,7 +990,7 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
 
 void bs_destroy(bs_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  DeviceGuard guard(e->device);
   if (e->s) cudaStreamSynchronize(e->s);
   if (e->s2) cudaStreamSynchronize(e->s2);
   DevBuf* bufs[] = {&e->d_alloc, &e->d_requested, &e->d_pod_count, &e->d_apres, &e->d_rpres, &e->d_label,
@@ -1017,7 +1034,7 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
     return fail(e, BS_E_RANGE, "bs_upload_nodes: value outside +-2^56");
   int64_t mx_pc = 0;
   for (uint32_t i = 0; i < N; ++i) mx_pc = std::max<int64_t>(mx_pc, std::abs((int64_t)t->pod_count[i]));
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   const uint32_t Npad = std::max(1u, cdiv(N, NODE_TILE)) * NODE_TILE;
   int rc;
   if ((rc = upload_lanes(e, e->d_alloc, t->alloc, L, N, Npad))) return rc;
@@ -1029,6 +1046,7 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   if ((rc = upload_vec(e, e->d_taint, t->taint_mask, N, Npad))) return rc;
   if ((rc = upload_vec(e, e->d_nflags, t->flags, N, Npad))) return rc;
   CK(cudaStreamSynchronize(e->s));
+  e->h_nflags.assign(t->flags, t->flags + N);
   memcpy(e->max_alloc, mx_a, sizeof(mx_a));
   memcpy(e->max_requested, mx_r, sizeof(mx_r));
   e->max_pod_count = mx_pc;
@@ -1052,7 +1070,7 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if (!in_range(t->min_res, (size_t)L * G)) return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
   for (uint32_t g = 0; g < G; ++g)
     if (t->creation_ns[g] == INT64_MAX) return fail(e, BS_E_RANGE, "bs_upload_groups: creation_ns == INT64_MAX");
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   const uint32_t Gp = std::max(G, 1u);
   int rc;
   if ((rc = upload_vec(e, e->d_min_member, t->min_member, G, Gp))) return rc;
@@ -1163,7 +1181,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
     e->any_lister_miss = miss != 0;
     e->max_gid = mg;
   }
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   const uint32_t Pp = std::max(P, 1u);
   int rc;
   if ((rc = upload_lanes(e, e->d_req, t->req, L, P, Pp))) return rc;
@@ -1221,7 +1239,7 @@ int bs_evaluate_async(bs_engine* e) {
 int bs_sync(bs_engine* e) {
   if (!e) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   CK(cudaStreamSynchronize(e->s));
   return BS_OK;
 }
@@ -1229,7 +1247,7 @@ int bs_sync(bs_engine* e) {
 int bs_fetch(bs_engine* e, bs_results* out) {
   if (!e) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   return fetch_locked(e, out);
 }
 
@@ -1339,7 +1357,7 @@ int bs_node_left(bs_engine* e, uint64_t sel, uint64_t tol, float percent, int64_
   if (!e || !left || !present) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_nodes) return fail(e, BS_E_STATE, "bs_node_left: upload nodes first");
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   const uint32_t N = e->N, L = e->L;
   if (!N) return BS_OK;
   DevBuf dl, dp;
@@ -1362,7 +1380,7 @@ int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent, co
   if (!e || (n_needs && (!need || !need_present || !ok))) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->have_nodes) return fail(e, BS_E_STATE, "bs_cluster_check: upload nodes first");
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   const uint32_t N = e->N, L = e->L;
   if (!n_needs) return BS_OK;
   if (!N) {
@@ -1427,7 +1445,7 @@ int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words) 
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->evaluated || !(e->out_flags & BS_OUT_FIT_BITMAP)) return fail(e, BS_E_STATE, "no fit bitmap materialised");
   if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   if (n && e->W)
     CK(cudaMemcpyAsync(words, e->d_fit_bitmap.as<uint32_t>() + (size_t)pod0 * e->W, (size_t)n * e->W * 4,
                        cudaMemcpyDeviceToHost, e->s));
@@ -1440,7 +1458,7 @@ int bs_fetch_filter_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* word
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->evaluated || !(e->out_flags & BS_OUT_FILTER)) return fail(e, BS_E_STATE, "no filter matrix materialised");
   if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   if (n && e->W)
     CK(cudaMemcpyAsync(words, e->d_filter_bitmap.as<uint32_t>() + (size_t)pod0 * e->W, (size_t)n * e->W * 4,
                        cudaMemcpyDeviceToHost, e->s));
@@ -1457,12 +1475,11 @@ int bs_filter(bs_engine* e, uint32_t pod, uint32_t node, bs_status* st) {
     int rc = fetch_locked(e, nullptr);
     if (rc) return rc;
   }
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   uint32_t word = 0;
-  uint8_t nflag = 0;
+  const uint8_t nflag = e->h_nflags[node];
   CK(cudaMemcpyAsync(&word, e->d_filter_bitmap.as<uint32_t>() + (size_t)pod * e->W + (node >> 5), 4,
                      cudaMemcpyDeviceToHost, e->s));
-  CK(cudaMemcpyAsync(&nflag, e->d_nflags.as<uint8_t>() + node, 1, cudaMemcpyDeviceToHost, e->s));
   CK(cudaStreamSynchronize(e->s));
   const int32_t g = e->h_gid[pod];
   st->group = (g >= 0 && (uint32_t)g < e->G) ? g : -1;
@@ -1479,7 +1496,7 @@ int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->evaluated || !(e->out_flags & BS_OUT_SCORE)) return fail(e, BS_E_STATE, "no score matrix materialised");
   if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
-  CK(cudaSetDevice(e->device));
+  BS_DEVICE_GUARD(e);
   if (n && e->N)
     CK(cudaMemcpyAsync(scores, e->d_score.as<int64_t>() + (size_t)pod0 * e->N, (size_t)n * e->N * 8,
                        cudaMemcpyDeviceToHost, e->s));
@@ -1501,7 +1518,7 @@ int bs_kernel_ms(bs_engine* e, int k, float* ms, uint32_t* launches) {
   if (ms) {
     *ms = 0.f;
     if (e->profiling && e->k_valid[k]) {
-      CK(cudaSetDevice(e->device));
+      BS_DEVICE_GUARD(e);
       CK(cudaEventSynchronize(e->ev_b[k]));
       CK(cudaEventElapsedTime(ms, e->ev_a[k], e->ev_b[k]));
     }

@@ -1,0 +1,238 @@
+"""A SECOND, independent restatement of the reference's hot path — pure Python over Go-like objects
+(dict-based ScalarResources, explicit loops), written from pkg/scheduler/core/core.go without looking
+at oracle/bs_oracle.c.  Used only to cross-check the C oracle on small cases (tests/test_oracle_crosscheck.py):
+two independent restatements agreeing is the strongest pin available while the Go reference cannot run.
+
+Go semantics reproduced explicitly: int == int64 (Python ints are masked where Go would wrap),
+uint32 arithmetic wraps, float32 via numpy.float32, float->int truncates.
+"""
+import numpy as np
+
+M64 = (1 << 64) - 1
+M32 = (1 << 32) - 1
+
+
+def i64(x):
+    x &= M64
+    return x - (1 << 64) if x >> 63 else x
+
+
+class Resource:  # nodeinfo.Resource
+    def __init__(self):
+        self.MilliCPU = 0
+        self.Memory = 0
+        self.EphemeralStorage = 0
+        self.AllowedPodNumber = 0
+        self.ScalarResources = {}
+
+    def Add(self, other):  # Resource.Add(other.ResourceList())
+        self.MilliCPU = i64(self.MilliCPU + other.MilliCPU)
+        self.Memory = i64(self.Memory + other.Memory)
+        self.EphemeralStorage = i64(self.EphemeralStorage + other.EphemeralStorage)
+        self.AllowedPodNumber = i64(self.AllowedPodNumber + other.AllowedPodNumber)
+        for k, v in other.ScalarResources.items():
+            self.ScalarResources[k] = i64(self.ScalarResources.get(k, 0) + v)
+
+
+def scale(alloc, percent):  # int64(float32(alloc) * percent)
+    return int(np.float32(alloc) * np.float32(percent))
+
+
+class Node:
+    def __init__(self, nt, i):
+        L = nt.lanes
+        self.flags = int(nt.flags[i])
+        self.alloc = Resource()
+        self.req = Resource()
+        a, r = nt.alloc[:, i], nt.requested[:, i]
+        self.alloc.MilliCPU, self.alloc.Memory, self.alloc.EphemeralStorage, self.alloc.AllowedPodNumber = (int(x) for x in a[:4])
+        self.req.MilliCPU, self.req.Memory, self.req.EphemeralStorage, self.req.AllowedPodNumber = (int(x) for x in r[:4])
+        for d in range(4, L):
+            if (int(nt.alloc_present[i]) >> d) & 1:
+                self.alloc.ScalarResources[d] = int(a[d])
+            if (int(nt.req_present[i]) >> d) & 1:
+                self.req.ScalarResources[d] = int(r[d])
+        self.n_pods = int(nt.pod_count[i])
+        self.labels = int(nt.label_mask[i])
+        self.taints = int(nt.taint_mask[i])
+
+
+def check_fit(sel, tol, node):  # core.go:741-759
+    return (node.labels & sel) == sel and (node.taints & ~tol & M64) == 0
+
+
+def single_node_resource(node, sel, tol, percent):  # core.go:634-670
+    left = Resource()
+    if node.flags & 0x08:  # Taints() error
+        return left
+    if not check_fit(sel, tol, node):
+        return left
+    pod_count = node.req.AllowedPodNumber
+    if pod_count == 0:
+        pod_count = node.n_pods
+    left.AllowedPodNumber = i64(scale(node.alloc.AllowedPodNumber, percent) - pod_count)
+    left.MilliCPU = i64(scale(node.alloc.MilliCPU, percent) - node.req.MilliCPU)
+    left.Memory = i64(scale(node.alloc.Memory, percent) - node.req.Memory)
+    left.EphemeralStorage = i64(scale(node.alloc.EphemeralStorage, percent) - node.req.EphemeralStorage)
+    for k, a in node.alloc.ScalarResources.items():
+        if k not in node.req.ScalarResources:
+            continue
+        left.ScalarResources[k] = i64(scale(a, percent) - node.req.ScalarResources[k])
+    return left
+
+
+def compare_resource_and_require(left, req):  # core.go:672-699
+    if left.Memory < req.Memory:
+        return False
+    if left.MilliCPU < req.MilliCPU:
+        return False
+    if left.EphemeralStorage < req.EphemeralStorage:
+        return False
+    if left.AllowedPodNumber < req.AllowedPodNumber:
+        return False
+    for k, v1 in req.ScalarResources.items():
+        if k not in left.ScalarResources:
+            if v1 != 0:
+                return False
+            continue
+        if v1 > left.ScalarResources[k]:
+            return False
+    return True
+
+
+def compare_cluster(nodes, sel, tol, need, percent):  # core.go:595-632
+    running = Resource()
+    for node in nodes:
+        if node.flags & 0x07:  # nil info / nil Node() / unschedulable
+            continue
+        running.Add(single_node_resource(node, sel, tol, percent))
+        if compare_resource_and_require(running, need):
+            return True
+    return False
+
+
+def resource_from(vals, present, lanes):
+    r = Resource()
+    r.MilliCPU, r.Memory, r.EphemeralStorage, r.AllowedPodNumber = (int(x) for x in vals[:4])
+    for d in range(4, lanes):
+        if (int(present) >> d) & 1:
+            r.ScalarResources[d] = int(vals[d])
+    return r
+
+
+def find_max_pg(gt, flags=None):  # core.go:701-739, table order
+    flags = gt.flags if flags is None else flags
+    max_idx, max_fin = -1, 0
+    for g in range(gt.n):
+        if flags[g] & 0x01:
+            continue
+        if not (flags[g] & 0x02):
+            continue
+        mm, sc = int(gt.min_member[g]), int(gt.scheduled[g])
+        if ((mm - sc) & M32) <= 0:
+            fin = 0
+        else:
+            if mm == 0:
+                raise ZeroDivisionError("findMaxPG")
+            fin = ((((int(gt.matched[g]) + sc) & M32) * 1000) & M32) // mm
+        if fin > max_fin:
+            max_fin, max_idx = fin, g
+        elif fin == max_fin:
+            if max_idx < 0 or (int(gt.scheduled[max_idx]) >= int(gt.min_member[max_idx]) and sc == 0):
+                max_fin, max_idx = fin, g
+    return max_idx, max_fin
+
+
+def pre_allocated(gt, g, matched, min_res, min_res_present, has_minres):  # core.go:774-793
+    out = Resource()
+    mm = int(gt.min_member[g])
+    not_finished = mm - matched if matched != 0 else mm - int(gt.scheduled[g])
+    for _ in range(max(0, not_finished)):
+        if has_minres:
+            out.Add(resource_from(min_res, min_res_present, gt.lanes))
+    if out.AllowedPodNumber == 0:
+        out.AllowedPodNumber = mm + 1
+    return out
+
+
+def compare_pods(pt, gt, a, b):  # core.go:368-411
+    p1, p2 = int(pt.priority[a]), int(pt.priority[b])
+    g1, g2 = int(pt.gid[a]), int(pt.gid[b])
+    n1, n2 = g1 == -1, g2 == -1
+    if p1 > p2:
+        return True
+    if p1 == p2:
+        if n1 and n2:
+            return int(pt.ts_ns[a]) < int(pt.ts_ns[b])
+        if n1:
+            return True
+        if n2:
+            return False
+    miss1 = n1 or g1 == -2 or bool(pt.flags[a] & 0x08)
+    miss2 = n2 or g2 == -2 or bool(pt.flags[b] & 0x08)
+    if miss1 or miss2:
+        return False
+    c1, c2 = int(gt.creation_ns[g1]), int(gt.creation_ns[g2])
+    r1, r2 = int(gt.name_rank[g1]), int(gt.name_rank[g2])
+    if p1 == p2 and c1 < c2:
+        return True
+    if p1 == p2 and c1 == c2 and r1 > r2:
+        return True
+    return p1 == p2 and c1 == c2 and r1 == r2 and int(pt.ts_ns[a]) < int(pt.ts_ns[b])
+
+
+def prefilter_round(snap):
+    """Round semantics of DESIGN.md §2 written straight from core.go:88-167 (+ :477-512)."""
+    nt, pt, gt = snap.nodes, snap.pods, snap.groups
+    L = nt.lanes
+    nodes = [Node(nt, i) for i in range(nt.n)]
+    flags = gt.flags.copy()
+    rep_sel, rep_tol = gt.rep_sel.copy(), gt.rep_tol.copy()
+    min_res, min_res_present = gt.min_res.copy(), gt.min_res_present.copy()
+    for p in range(pt.n):  # fillOccupiedObj first-pod capture
+        g = int(pt.gid[p])
+        if g < 0 or g >= gt.n or (pt.flags[p] & 0x01) or (gt.flags[g] & 0x08):
+            continue
+        if not (flags[g] & 0x02):
+            flags[g] |= 0x02
+            rep_sel[g], rep_tol[g] = pt.sel_mask[p], pt.tol_mask[p]
+        if not (flags[g] & 0x04):
+            flags[g] |= 0x04
+            for d in range(L):
+                pres = d < 4 or ((int(pt.req_present[p]) >> d) & 1)
+                min_res[d, g] = pt.req[d, p] if pres else 0
+            min_res_present[g] = int(pt.req_present[p]) & ~0xF
+    m, _ = find_max_pg(gt, flags)
+    codes, denied = np.zeros(pt.n, np.uint8), np.zeros(gt.n, np.uint8)
+    for p in range(pt.n):
+        g = int(pt.gid[p])
+        f = int(pt.flags[p])
+        if g == -1 or (f & 0x01):
+            continue
+        if g < 0 or g >= gt.n:
+            codes[p] = 1
+            continue
+        if gt.flags[g] & 0x08:
+            codes[p] = 2
+            continue
+        if f & 0x02:
+            codes[p] = 3
+            continue
+        if f & 0x04:
+            codes[p] = 4
+            continue
+        if m < 0:
+            continue
+        matched = int(gt.matched[m])
+        if matched == 0:
+            need = pre_allocated(gt, g, 0, min_res[:, g], min_res_present[g], bool(flags[g] & 0x04))
+            if not compare_cluster(nodes, int(rep_sel[g]), int(rep_tol[g]), need, 1.0):
+                codes[p], denied[g] = 5, 1
+            continue
+        if m == g:
+            continue
+        need = pre_allocated(gt, m, matched, min_res[:, m], min_res_present[m], bool(flags[m] & 0x04))
+        need.Add(resource_from(pt.req[:, p], int(pt.req_present[p]) & ~0xF, L))
+        if not compare_cluster(nodes, int(rep_sel[m]), int(rep_tol[m]), need, 0.7):
+            codes[p], denied[g] = 5, 1
+    return codes, denied, m

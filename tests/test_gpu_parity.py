@@ -338,3 +338,33 @@ def test_prefix_scratch_chunking(pkg, oracle, monkeypatch):
     snap.pods.tol_mask = rng.integers(0, 4, snap.pods.n).astype(np.uint64)
     monkeypatch.setenv("BS_PREFIX_BUDGET_BYTES", str(3 * 300 * (8 * 6 + 4)))       # 3 class slots
     run_and_compare(pkg, oracle, snap)
+
+
+def test_concurrent_mirror_calls_are_safe(pkg, oracle, snapshot_mod):
+    """Less / Permit / PreFilter are called from several goroutines in the reference
+    (batchscheduler.go:165,214); one handle must serve concurrent callers."""
+    import threading
+    snap = random_snapshot(808, P=300, N=50, G=20, L=5)
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=True, score=False)
+    eng.upload(snap)
+    eng.evaluate()
+    orc = oracle.round(snap)
+    errors = []
+
+    def worker(seed):
+        rng = np.random.default_rng(seed)
+        try:
+            for _ in range(400):
+                a, b = (int(x) for x in rng.integers(0, snap.pods.n, 2))
+                assert eng.less(a, b) == oracle.compare(snap.pods, snap.groups, a, b)
+                assert eng.prefilter(a)[1] == orc.prefilter[a]
+                eng.permit(b, 0)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:1]
+    eng.close()
