@@ -1067,9 +1067,19 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if (G && (!t->min_member || !t->scheduled || !t->matched || !t->flags || !t->min_res ||
             !t->min_res_present || !t->rep_sel || !t->rep_tol || !t->creation_ns || !t->name_rank))
     return fail(e, BS_E_INVAL, "bs_upload_groups: null column");
-  if (!in_range(t->min_res, (size_t)L * G)) return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
-  for (uint32_t g = 0; g < G; ++g)
-    if (t->creation_ns[g] == INT64_MAX) return fail(e, BS_E_RANGE, "bs_upload_groups: creation_ns == INT64_MAX");
+  {
+    int64_t mx[BS_MAX_LANES] = {};
+    if (!lane_maxima(t->min_res, L, G, mx)) return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
+  }
+  uint64_t o1 = 0, a1 = ~0ull, o0 = 0, a0 = ~0ull;
+  int bad_creation = 0;
+#pragma omp parallel for reduction(| : o1, o0, bad_creation) reduction(& : a1, a0) if (G > 65536) num_threads(host_threads())
+  for (uint32_t g = 0; g < G; ++g) {
+    const uint64_t c = (uint64_t)t->creation_ns[g], nm = (uint64_t)(~t->name_rank[g]);
+    o1 |= c; a1 &= c; o0 |= nm; a0 &= nm;
+    bad_creation |= t->creation_ns[g] == INT64_MAX ? 1 : 0;
+  }
+  if (bad_creation) return fail(e, BS_E_RANGE, "bs_upload_groups: creation_ns == INT64_MAX");
   BS_DEVICE_GUARD(e);
   const uint32_t Gp = std::max(G, 1u);
   int rc;
@@ -1081,19 +1091,12 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if ((rc = upload_vec(e, e->d_mrpres, t->min_res_present, G, Gp))) return rc;
   if ((rc = upload_vec(e, e->d_creation, t->creation_ns, G, Gp))) return rc;
   if ((rc = upload_vec(e, e->d_name_rank, t->name_rank, G, Gp))) return rc;
-  CK(cudaStreamSynchronize(e->s));
-  {
-    uint64_t o1 = 0, a1 = ~0ull, o0 = 0, a0 = ~0ull;
-    for (uint32_t g = 0; g < G; ++g) {
-      const uint64_t c = (uint64_t)t->creation_ns[g], nm = (uint64_t)(~t->name_rank[g]);
-      o1 |= c; a1 &= c; o0 |= nm; a0 &= nm;
-    }
-    e->vary_creation = G ? (o1 ^ a1) : 0;
-    e->vary_name = G ? (o0 ^ a0) : 0;
-  }
+  e->vary_creation = G ? (o1 ^ a1) : 0;
+  e->vary_name = G ? (o0 ^ a0) : 0;
   e->h_gsel.assign(t->rep_sel, t->rep_sel + G);
   e->h_gtol.assign(t->rep_tol, t->rep_tol + G);
   if (e->h_wait_ns.size() != G) e->h_wait_ns.assign(G, -1);
+  CK(cudaStreamSynchronize(e->s));   // the caller's arrays are free again once we return
   e->G = G;
   e->have_groups = true;
   e->classes_dirty = true;

@@ -149,7 +149,8 @@ def run_reference(args, rank, world):
     from oracle import oracle
     S = importlib.import_module("batch-scheduler_b200.snapshot")
     snap = S.config(WORKLOAD_CFG)
-    threads = oracle.max_threads()
+    # every host thread of the box (torchrun pins OMP_NUM_THREADS=1; the oracle takes an explicit count)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # bounded sample per step: the whole --steps K --warmup W run is sized to ~90 s of CPU work
     v, n_pods, _ = cpu_sample(oracle, snap, seconds=2.0, threads=threads)
     per_step_s = min(4.0, max(0.05, 90.0 / max(1, args.steps + args.warmup)))
@@ -368,7 +369,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
-        threads = oracle.max_threads()
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         v, n_pods, dt = cpu_sample(oracle, snap, seconds=12.0, threads=threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {n_pods} pods x all {N} nodes / {G} groups of the same snapshot, {dt:.1f} s, "
