@@ -13,14 +13,14 @@ import numpy as np
 
 from . import build as _build
 
-BS_OK, BS_E_INVAL, BS_E_NODEVICE, BS_E_CUDA, BS_E_NOMEM, BS_E_RANGE, BS_E_STATE, BS_E_REF_PANIC, BS_E_INDEX = \
-    0, -1, -2, -3, -4, -5, -6, -7, -8
+BS_OK, BS_E_INVAL, BS_E_NODEVICE, BS_E_CUDA, BS_E_NOMEM, BS_E_RANGE, BS_E_STATE, BS_E_REF_PANIC, BS_E_INDEX, BS_E_PEER = \
+    0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 CODE_SUCCESS, CODE_ERROR, CODE_UNSCHEDULABLE, CODE_UNSCHEDULABLE_AND_UNRESOLVABLE, CODE_WAIT, CODE_SKIP = range(6)
 OUT_FIT_BITMAP, OUT_SCORE, OUT_FILTER = 0x1, 0x2, 0x4
 FILTER_PASS, FILTER_NOT_FOUND, FILTER_NOT_ENOUGH, FILTER_NO_SNAPSHOT, FILTER_REF_PANIC = range(5)
-BUF_FIT_BITMAP, BUF_SCORE, BUF_ADMIT_BITMAP, BUF_PREFILTER, BUF_ADMIT, BUF_ORDER = range(6)
-K_NODE_LEFT, K_FIND_MAX, K_CLASS_PREFIX, K_PREFILTER, K_GANG_FIT, K_SORT, K_FILTER, K_COUNT = range(8)
-KERNEL_NAMES = ["node_left", "find_max", "class_prefix", "prefilter", "gang_fit", "sort", "filter"]
+BUF_FIT_BITMAP, BUF_SCORE, BUF_ADMIT_BITMAP, BUF_PREFILTER, BUF_ADMIT, BUF_ORDER, BUF_GATHERED_ADMIT = range(7)
+K_NODE_LEFT, K_FIND_MAX, K_CLASS_PREFIX, K_PREFILTER, K_GANG_FIT, K_SORT, K_FILTER, K_PEER, K_COUNT = range(9)
+KERNEL_NAMES = ["node_left", "find_max", "class_prefix", "prefilter", "gang_fit", "sort", "filter", "peer"]
 
 
 def _p(t):
@@ -94,6 +94,10 @@ SYMBOLS = {
     "bs_fetch_fit_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bs_fetch_score_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bs_fetch_filter_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "bs_peer_init": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "bs_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bs_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bs_peer_detach": (C.c_int, [C.c_void_p]),
     "bs_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "bs_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, _p(C.c_float), _p(C.c_uint32)]),
     "bs_launch_count": (C.c_uint64, [C.c_void_p]),

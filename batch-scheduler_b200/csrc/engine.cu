@@ -237,6 +237,12 @@ struct bs_engine {
       h_order, h_rank, h_state, h_filter_code;
   bool fetched = false;
 
+  // peer exchange (admit bitmap all-gather over NVLink peer memory)
+  DevBuf d_gather, d_peer_err;
+  uint32_t peer_rank = 0, peer_world = 0, peer_wpr = 0, peer_seq = 0;
+  bool peer_attached = false;
+  void* peer_ptr[PEER_MAX_WORLD] = {};
+
   // profiling
   bool profiling = false;
   cudaEvent_t ev_a[BS_K_COUNT] = {}, ev_b[BS_K_COUNT] = {};
@@ -875,6 +881,20 @@ int evaluate_async_locked(bs_engine* e) {
       tm.launched();
     }
   }
+  {
+    StageTimer tm(e, BS_K_PEER, e->s);
+    if (e->peer_attached) {
+      PeerArgs pa{};
+      for (uint32_t r = 0; r < e->peer_world; ++r) pa.peer_buf[r] = reinterpret_cast<uint32_t*>(e->peer_ptr[r]);
+      pa.local_bitmap = e->d_admit_bitmap.as<uint32_t>();
+      pa.rank = e->peer_rank; pa.world = e->peer_world; pa.words_per_rank = e->peer_wpr;
+      pa.n_words = std::min(e->peer_wpr, cdiv(std::max(G, 1u), 32));
+      pa.seq = ++e->peer_seq;
+      pa.err = e->d_peer_err.as<int>();
+      peer_exchange_kernel<<<1, 256, 0, e->s>>>(pa);
+      tm.launched();
+    }
+  }
   CK(cudaStreamWaitEvent(e->s, e->ev_join, 0));
   CK(cudaGetLastError());
   e->evaluated = true;
@@ -944,6 +964,7 @@ const char* bs_strerror(int err) {
     case BS_E_STATE: return "call out of order";
     case BS_E_REF_PANIC: return "reference would panic (findMaxPG divide by zero)";
     case BS_E_INDEX: return "index out of range";
+    case BS_E_PEER: return "peer exchange timed out";
   }
   return "unknown error";
 }
@@ -993,6 +1014,10 @@ void bs_destroy(bs_engine* e) {
   DeviceGuard guard(e->device);
   if (e->s) cudaStreamSynchronize(e->s);
   if (e->s2) cudaStreamSynchronize(e->s2);
+  for (uint32_t r = 0; r < e->peer_world; ++r)
+    if (r != e->peer_rank && e->peer_ptr[r]) cudaIpcCloseMemHandle(e->peer_ptr[r]);
+  e->d_gather.release();
+  e->d_peer_err.release();
   DevBuf* bufs[] = {&e->d_alloc, &e->d_requested, &e->d_pod_count, &e->d_apres, &e->d_rpres, &e->d_label,
                     &e->d_taint, &e->d_nflags, &e->d_left_w, &e->d_left_n, &e->d_left_present, &e->d_left_plain, &e->d_filter_bitmap, &e->d_filter_code, &e->d_classfit, &e->d_req,
                     &e->d_ppres, &e->d_gid, &e->d_prio, &e->d_ts, &e->d_pflags, &e->d_pod_fit_class,
@@ -1244,6 +1269,11 @@ int bs_sync(bs_engine* e) {
   std::lock_guard<std::mutex> lk(e->mu);
   BS_DEVICE_GUARD(e);
   CK(cudaStreamSynchronize(e->s));
+  if (e->peer_attached) {
+    int bad = 0;
+    CK(cudaMemcpy(&bad, e->d_peer_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return fail(e, BS_E_PEER, "peer exchange timed out: a rank did not arrive");
+  }
   return BS_OK;
 }
 
@@ -1436,6 +1466,7 @@ int bs_device_buffer(bs_engine* e, int which, void** dev_ptr, size_t* bytes) {
     case BS_BUF_PREFILTER: *dev_ptr = e->d_prefilter.p; *bytes = P; break;
     case BS_BUF_ADMIT: *dev_ptr = e->d_admit.p; *bytes = G; break;
     case BS_BUF_ORDER: *dev_ptr = e->d_order.p; *bytes = (size_t)P * 4; break;
+    case BS_BUF_GATHERED_ADMIT: *dev_ptr = e->d_gather.p; *bytes = (size_t)e->peer_world * e->peer_wpr * 4; break;
     default: return BS_E_INVAL;
   }
   return BS_OK;
@@ -1504,6 +1535,72 @@ int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores
     CK(cudaMemcpyAsync(scores, e->d_score.as<int64_t>() + (size_t)pod0 * e->N, (size_t)n * e->N * 8,
                        cudaMemcpyDeviceToHost, e->s));
   CK(cudaStreamSynchronize(e->s));
+  return BS_OK;
+}
+
+int bs_peer_init(bs_engine* e, uint32_t rank, uint32_t world, uint32_t words_per_rank) {
+  if (!e || world == 0 || world > PEER_MAX_WORLD || rank >= world || words_per_rank == 0) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  BS_DEVICE_GUARD(e);
+  if (e->peer_attached) return fail(e, BS_E_STATE, "bs_peer_init: detach first");
+  const size_t bytes = ((size_t)world * words_per_rank + 2 * PEER_MAX_WORLD) * 4;
+  e->d_gather.release();   // a fresh allocation: the IPC handle names this exact block
+  CK(e->d_gather.ensure(bytes));
+  CK(e->d_peer_err.ensure(sizeof(int)));
+  CK(cudaMemsetAsync(e->d_gather.p, 0, e->d_gather.cap, e->s));
+  CK(cudaMemsetAsync(e->d_peer_err.p, 0, sizeof(int), e->s));
+  CK(cudaStreamSynchronize(e->s));
+  e->peer_rank = rank; e->peer_world = world; e->peer_wpr = words_per_rank; e->peer_seq = 0;
+  return BS_OK;
+}
+
+int bs_peer_handle(bs_engine* e, unsigned char handle[64]) {
+  if (!e || !handle) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  BS_DEVICE_GUARD(e);
+  if (!e->d_gather.p) return fail(e, BS_E_STATE, "bs_peer_handle: bs_peer_init first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->d_gather.p));
+  memcpy(handle, &h, 64);
+  return BS_OK;
+}
+
+int bs_peer_attach(bs_engine* e, const unsigned char* handles) {
+  if (!e || !handles) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  BS_DEVICE_GUARD(e);
+  if (!e->d_gather.p) return fail(e, BS_E_STATE, "bs_peer_attach: bs_peer_init first");
+  if (e->peer_attached) return fail(e, BS_E_STATE, "bs_peer_attach: already attached");
+  for (uint32_t r = 0; r < e->peer_world; ++r) {
+    if (r == e->peer_rank) { e->peer_ptr[r] = e->d_gather.p; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t er = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (er != cudaSuccess) {
+      for (uint32_t q = 0; q < r; ++q)
+        if (q != e->peer_rank && e->peer_ptr[q]) { cudaIpcCloseMemHandle(e->peer_ptr[q]); e->peer_ptr[q] = nullptr; }
+      e->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(er);
+      cudaGetLastError();
+      return BS_E_CUDA;
+    }
+    e->peer_ptr[r] = p;
+  }
+  e->peer_attached = true;
+  return BS_OK;
+}
+
+int bs_peer_detach(bs_engine* e) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  BS_DEVICE_GUARD(e);
+  if (e->s) cudaStreamSynchronize(e->s);
+  for (uint32_t r = 0; r < e->peer_world; ++r) {
+    if (r != e->peer_rank && e->peer_ptr[r]) cudaIpcCloseMemHandle(e->peer_ptr[r]);
+    e->peer_ptr[r] = nullptr;
+  }
+  e->peer_attached = false;
   return BS_OK;
 }
 

@@ -1432,6 +1432,70 @@ __global__ void __launch_bounds__(256) filter_kernel(FilterArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// K8  peer_exchange_kernel — all-gather of the admit bitmap over NVLink peer memory, fused into
+// the round as its last kernel (one CTA).  Protocol per evaluation `seq` (1, 2, ...):
+//   1. wait until every peer has acknowledged seq-1 (their buffers may be overwritten);
+//   2. store this rank's words into slot[rank] of every peer's gather buffer (plain coalesced
+//      stores to mapped peer addresses), __threadfence_system(), publish flag[rank] = seq there;
+//   3. wait until flag[r] == seq for every r in the local buffer (all slots have landed);
+//   4. write ack[rank] = seq to every peer.
+// All spins are bounded (clock64); on a timeout *err is set and the kernel leaves.
+constexpr int PEER_MAX_WORLD = 16;
+struct PeerArgs {
+  uint32_t* peer_buf[PEER_MAX_WORLD];  // mapped base of every rank's gather buffer (own = local)
+  const uint32_t* local_bitmap;        // this rank's admit bitmap words
+  uint32_t rank, world, words_per_rank, n_words;  // n_words <= words_per_rank valid words
+  uint32_t seq;
+  int* err;
+};
+// buffer layout: [world][words_per_rank] data | [PEER_MAX_WORLD] flags | [PEER_MAX_WORLD] acks
+__device__ __forceinline__ uint32_t* peer_flags(uint32_t* base, uint32_t world, uint32_t wpr) { return base + (size_t)world * wpr; }
+__device__ __forceinline__ bool peer_spin(volatile uint32_t* p, uint32_t want) {
+  const long long t0 = clock64();
+  while (*p < want) {
+    __nanosleep(128);
+    if (clock64() - t0 > 6000000000ll) return false;   // ~3 s
+  }
+  return true;
+}
+__global__ void __launch_bounds__(256) peer_exchange_kernel(PeerArgs a) {
+  __shared__ int s_bad;
+  uint32_t* mine = a.peer_buf[a.rank];
+  volatile uint32_t* my_flags = peer_flags(mine, a.world, a.words_per_rank);
+  volatile uint32_t* my_acks = my_flags + PEER_MAX_WORLD;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  // 1. peers are done reading the previous round out of their buffers
+  if (threadIdx.x < a.world && a.seq > 1 && !peer_spin(&my_acks[threadIdx.x], a.seq - 1)) s_bad = 1;
+  __syncthreads();
+  if (!s_bad) {
+    // 2. push
+    for (uint32_t r = 0; r < a.world; ++r) {
+      uint32_t* dst = a.peer_buf[r] + (size_t)a.rank * a.words_per_rank;
+      for (uint32_t w = threadIdx.x; w < a.words_per_rank; w += blockDim.x) dst[w] = w < a.n_words ? a.local_bitmap[w] : 0u;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+      volatile uint32_t* f = peer_flags(a.peer_buf[threadIdx.x], a.world, a.words_per_rank);
+      f[a.rank] = a.seq;
+    }
+    __threadfence_system();
+    // 3. everybody's slot has landed here
+    if (threadIdx.x < a.world && !peer_spin(&my_flags[threadIdx.x], a.seq)) s_bad = 1;
+    __syncthreads();
+    // 4. acknowledge
+    if (threadIdx.x < a.world) {
+      volatile uint32_t* ack = peer_flags(a.peer_buf[threadIdx.x], a.world, a.words_per_rank) + PEER_MAX_WORLD;
+      ack[a.rank] = a.seq;
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_bad) *a.err = 1;
+}
+
 inline size_t gang_fit_smem_bytes(int LW, int LN) {
   size_t b = FIT_STAGES * fit_tile_bytes(LW, LN) + (size_t)PODS_PER_CTA * (8 * LW + 4 * LN);
   b = (b + 7) & ~(size_t)7;

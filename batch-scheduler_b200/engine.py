@@ -190,6 +190,35 @@ class Engine:
         self._check(self.lib.bs_format_message(C.byref(st), ns_name.encode(), occupied_by.encode(), buf, 512))
         return buf.value.decode()
 
+    # -- multi-GPU: admit-bitmap all-gather over peer memory ------------------------------------
+    def peer_setup(self, rank: int, world: int, words_per_rank: int, all_gather_bytes):
+        """Maps every rank's gather buffer into this process.  `all_gather_bytes(b) -> [bytes]*world`
+        exchanges the 64-byte IPC handles (e.g. torch.distributed.all_gather_object)."""
+        self._check(self.lib.bs_peer_init(self.h, rank, world, words_per_rank))
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.bs_peer_handle(self.h, buf))
+        handles = all_gather_bytes(bytes(buf))
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        self._check(self.lib.bs_peer_attach(self.h, blob))
+        self.peer_world, self.peer_wpr = world, words_per_rank
+
+    def peer_detach(self):
+        self._check(self.lib.bs_peer_detach(self.h))
+
+    def gathered_admit(self) -> np.ndarray:
+        """[world, words_per_rank] uint32: every rank's admit bitmap after the last evaluation."""
+        ptr, nbytes = self.device_buffer(capi.BUF_GATHERED_ADMIT)
+        out = np.zeros(nbytes // 4, np.uint32)
+        import torch
+
+        class _H:
+            pass
+        h = _H()
+        h.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(h, device=torch.device("cuda", torch.cuda.current_device()))
+        out[:] = t.cpu().numpy().view(np.uint32)
+        return out.reshape(self.peer_world, self.peer_wpr)
+
     # -- device access / measurement ---------------------------------------------------------
     def device_buffer(self, which: int):
         p, n = C.c_void_p(), C.c_size_t()

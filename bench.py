@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; marks the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: admit-bitmap all-gather by the engine's peer-memory kernel (default) or by NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -237,7 +239,15 @@ def main():
     # admit bitmap as a torch tensor over the engine's device buffer (NCCL all-gather payload)
     gathered = None
     bitmap_t = None
-    if world > 1:
+    use_p2p = world > 1 and args.exchange == "p2p"
+    if use_p2p:
+        def _ag(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        eng.peer_setup(rank, world, (G + 31) // 32, _ag)
+        dist.barrier()
+    if world > 1 and not use_p2p:
         eng.evaluate_async(); eng.sync()
         ptr, nbytes = eng.device_buffer(capi.BUF_ADMIT_BITMAP)
 
@@ -249,8 +259,8 @@ def main():
         gathered = torch.empty(world * bitmap_t.numel(), dtype=torch.int32, device=f"cuda:{local_rank}")
 
     def step():
-        eng.evaluate_async()
-        if world > 1:
+        eng.evaluate_async()   # with --exchange p2p the round's last kernel is the peer-memory all-gather
+        if world > 1 and not use_p2p:
             with torch.cuda.stream(ext):
                 dist.all_gather_into_tensor(gathered, bitmap_t)
 
@@ -350,7 +360,7 @@ def main():
         te_ = time.perf_counter()
         br["upload_nodes"] += tb - ta; br["upload_groups"] += tc - tb; br["upload_pods"] += td - tc
         br["evaluate_fetch"] += te_ - td
-        if world > 1:
+        if world > 1 and not use_p2p:
             with torch.cuda.stream(ext):
                 dist.all_gather_into_tensor(gathered, bitmap_t)
             torch.cuda.synchronize()
@@ -385,8 +395,9 @@ def main():
                        "outputs": "score matrix int64 PxN + fit bitmap + decisions",
                        "l2": "each step streams an %.1f GB score matrix (>> 126 MB L2) — working set larger than L2, "
                              "no explicit flush" % (8.0 * P * N / 1e9),
-                       "sharding": "groups/pods per rank, node table replicated, 1 NCCL all-gather of the admit "
-                                   "bitmap per step" if world > 1 else "single GPU",
+                       "sharding": ("groups/pods per rank, node table replicated, admit bitmap all-gathered every step by "
+                                    + ("one peer-memory kernel over NVLink (CUDA IPC), fused as the round's last launch"
+                                       if use_p2p else "one NCCL all-gather")) if world > 1 else "single GPU",
                        "scale": args.scale},
             "admit_decisions_per_s": admit_rate,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -404,6 +415,9 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if use_p2p:
+        dist.barrier()
+        eng.peer_detach()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -54,7 +54,8 @@ typedef enum {
   BS_E_STATE = -6,       /* call out of order (e.g. evaluate before upload) */
   BS_E_REF_PANIC = -7,   /* the reference would panic on this input:
                             findMaxPG divides by MinMember==0 (core.go:716-717) */
-  BS_E_INDEX = -8        /* pod / node / group index out of range */
+  BS_E_INDEX = -8,       /* pod / node / group index out of range */
+  BS_E_PEER = -9         /* peer exchange timed out (a rank did not arrive) */
 } bs_err;
 
 /* ---- framework.Status codes (k8s.io/kubernetes v1.17.5
@@ -270,7 +271,8 @@ typedef enum {
   BS_BUF_ADMIT_BITMAP = 2,
   BS_BUF_PREFILTER = 3,
   BS_BUF_ADMIT = 4,
-  BS_BUF_ORDER = 5
+  BS_BUF_ORDER = 5,
+  BS_BUF_GATHERED_ADMIT = 6
 } bs_buffer;
 int bs_device_buffer(bs_engine* e, int which, void** dev_ptr, size_t* bytes);
 void* bs_stream(bs_engine* e); /* the cudaStream_t every kernel is launched on */
@@ -278,6 +280,20 @@ void* bs_stream(bs_engine* e); /* the cudaStream_t every kernel is launched on *
 int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words);
 int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores);
 int bs_fetch_filter_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words);
+
+/* ---- multi-GPU exchange of the admit bitmap over peer memory (NVLink / NVSwitch) ----
+ * The path shards over groups (one process per GPU); the only exchange is the all-gather of the
+ * per-rank admit bitmaps.  Instead of a separate NCCL launch, bs_evaluate_async ends with ONE small
+ * kernel that writes this rank's bitmap words straight into every peer's gather buffer (CUDA IPC
+ * mapped peer memory), publishes a sequence number, and waits (bounded spins) for the peers'.
+ *   bs_peer_init    allocate the gather buffer [world][words_per_rank] (+ flags) on this GPU
+ *   bs_peer_handle  64-byte cudaIpcMemHandle of it, to be exchanged out of band (e.g. torch.distributed)
+ *   bs_peer_attach  map every peer's buffer (handles[world][64], own slot ignored)
+ * BS_BUF_GATHERED_ADMIT then holds, after each evaluation, rank r's bitmap at word r*words_per_rank. */
+int bs_peer_init(bs_engine* e, uint32_t rank, uint32_t world, uint32_t words_per_rank);
+int bs_peer_handle(bs_engine* e, unsigned char handle[64]);
+int bs_peer_attach(bs_engine* e, const unsigned char* handles /* [world][64] */);
+int bs_peer_detach(bs_engine* e);
 
 /* ---- measurement hooks ---- */
 typedef enum {
@@ -288,7 +304,8 @@ typedef enum {
   BS_K_GANG_FIT = 4,   /* the dominant kernel: fit predicate + score + gang admit */
   BS_K_SORT = 5,
   BS_K_FILTER = 6,     /* optional Filter matrix (BS_OUT_FILTER) */
-  BS_K_COUNT = 7
+  BS_K_PEER = 7,       /* admit-bitmap exchange over peer memory */
+  BS_K_COUNT = 8
 } bs_kernel_id;
 int bs_set_profiling(bs_engine* e, int on); /* record CUDA events around each stage */
 /* milliseconds of stage k in the last evaluation, and launches it took */

@@ -63,6 +63,20 @@ def _worker(rank, world, port, out_dir):
         a0, a1 = (int(x) for x in allb[r].cpu())
         bits = np.unpackbits(words[r].view(np.uint8), bitorder="little")[:G].astype(bool)
         merged[a0:a1] = bits[a0:a1]
+    # the same all-gather by the engine's own peer-memory kernel (CUDA IPC over NVLink), three rounds
+    def _ag(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+    eng.peer_setup(rank, world, (G + 31) // 32, _ag)
+    dist.barrier()
+    for _ in range(3):
+        eng.evaluate_async()
+        eng.sync()
+    p2p = eng.gathered_admit()
+    np.testing.assert_array_equal(p2p, words[:, :p2p.shape[1]])
+    dist.barrier()
+    eng.peer_detach()
     if rank == 0:
         from oracle import oracle
         ref = oracle.round(full, want_bitmap=False)
