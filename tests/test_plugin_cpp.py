@@ -78,3 +78,36 @@ def test_readme_race_through_cpp_plugin(plugin_bin, snapshot_mod):
     for r in g2[1:]:
         assert r["prefilter_code"] == 2
         assert r["message"] == "pod with pgName: default/group2 last failed in 20s, deny"
+
+
+def test_quantity_parsing_randomised(plugin_bin):
+    """resource.Quantity semantics against an exact rational model: Value() and MilliValue() are the
+    ceilings (away from zero for negatives) of the parsed number and of 1000x it."""
+    import math
+    import random
+    from fractions import Fraction
+    rnd = random.Random(7)
+    sufs = {"": Fraction(1), "m": Fraction(1, 1000), "u": Fraction(1, 10**6), "n": Fraction(1, 10**9), "k": Fraction(10**3),
+            "M": Fraction(10**6), "G": Fraction(10**9), "T": Fraction(10**12), "P": Fraction(10**15),
+            "Ki": Fraction(2**10), "Mi": Fraction(2**20), "Gi": Fraction(2**30), "Ti": Fraction(2**40), "Pi": Fraction(2**50)}
+    cases = {}
+    for _ in range(400):
+        whole = rnd.randint(0, 10**rnd.randint(1, 6))
+        frac = "" if rnd.random() < 0.5 else "." + "".join(rnd.choice("0123456789") for _ in range(rnd.randint(1, 4)))
+        suf = rnd.choice(list(sufs))
+        if rnd.random() < 0.15:
+            ex = rnd.randint(0, 6)
+            s = f"{whole}{frac}e{ex}"
+            val = Fraction(f"{whole}{frac}") * 10**ex
+        else:
+            s = f"{whole}{frac}{suf}"
+            val = Fraction(f"{whole}{frac}") * sufs[suf]
+        if val * 1000 >= 2**62:
+            continue
+        cases[s] = (math.ceil(val), math.ceil(val * 1000))
+    keys = list(cases)
+    for i in range(0, len(keys), 100):
+        out = _run(plugin_bin, "quantity", *keys[i:i + 100])
+        for s in keys[i:i + 100]:
+            ok, v, m = out[s]
+            assert ok == 1 and (v, m) == cases[s], (s, out[s], cases[s])
