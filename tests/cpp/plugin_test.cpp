@@ -125,6 +125,19 @@ static int cmd_readme() {
            "\"wait_ns\": %lld, \"start_signal\": %d}\n",
            qi ? "," : "", p.name.c_str(), pf.code, pf.message.c_str(), node_idx, permit_code, wait, start ? 1 : 0);
   }
+  // README.md:184-188 / SURVEY Appendix C step 4: 21 s later the freeze cache has expired, group1 is
+  // skipped by findMaxPG (pgs.Scheduled), group2 is the max group with nothing matched -> pct 1.0 check:
+  // 8000 - 5900 = 2100 < 5000 -> refused again, and frozen again.
+  now += 21000000000ll;
+  for (int i = 0; i < 2; ++i) {
+    const Pod& p = queue[1 + 2 * i];  // group2's pods
+    now += 100000000ll;
+    Status st = plugin.BeginRound({&info}, {&p}, now);
+    if (!st.ok()) { fprintf(stderr, "round failed: %s\n", st.message.c_str()); return 1; }
+    Status pf = plugin.PreFilter(p);
+    printf(",{\"pod\": \"late-%s\", \"prefilter_code\": %d, \"message\": \"%s\", \"node\": -1, \"permit_code\": -1, "
+           "\"wait_ns\": 0, \"start_signal\": 0}\n", p.name.c_str(), pf.code, pf.message.c_str());
+  }
   printf("]\n");
   return 0;
 }

@@ -69,8 +69,13 @@ def test_readme_race_through_cpp_plugin(plugin_bin, snapshot_mod):
     # README.md:76-188 — "only one and at least one group" runs; messages as core.go:107,143 print them
     S = snapshot_mod
     rows = _run(plugin_bin, "readme")
+    late = [r for r in rows if r["pod"].startswith("late-")]
+    rows = [r for r in rows if not r["pod"].startswith("late-")]
     g1 = [r for r in rows if "race1" in r["pod"]]
     g2 = [r for r in rows if "race2" in r["pod"]]
+    # 21 s later (freeze cache expired): group2 is refused again at pct 1.0 (2100 < 5000), then frozen again
+    assert late[0]["prefilter_code"] == 2 and late[0]["message"] == "cluster resource not enough"
+    assert late[1]["message"] == "pod with pgName: default/group2 last failed in 20s, deny"
     assert all(r["prefilter_code"] == 0 and r["node"] == 0 and r["permit_code"] == 4 for r in g1)   # Wait
     assert [r["start_signal"] for r in g1] == [0, 0, 0, 0, 1]
     assert all(r["wait_ns"] == 10**9 for r in g1)                                                    # 0 + 1 s (Q12)
