@@ -1084,6 +1084,68 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   return BS_OK;
 }
 
+int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t) {
+  if (!e || !t || (t->n_nodes && !idx)) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_nodes) return fail(e, BS_E_STATE, "bs_update_nodes: upload nodes first");
+  if (t->n_lanes != e->L) return fail(e, BS_E_INVAL, "bs_update_nodes: n_lanes differs from the engine's");
+  const uint32_t n = t->n_nodes, L = e->L;
+  if (!n) return BS_OK;
+  if (!t->alloc || !t->requested || !t->pod_count || !t->alloc_present || !t->req_present || !t->label_mask ||
+      !t->taint_mask || !t->flags)
+    return fail(e, BS_E_INVAL, "bs_update_nodes: null column");
+  for (uint32_t k = 0; k < n; ++k)
+    if (idx[k] >= e->N) return BS_E_INDEX;
+  int64_t mx_a[BS_MAX_LANES] = {}, mx_r[BS_MAX_LANES] = {};
+  if (!lane_maxima(t->alloc, L, n, mx_a) || !lane_maxima(t->requested, L, n, mx_r))
+    return fail(e, BS_E_RANGE, "bs_update_nodes: value outside +-2^56");
+  BS_DEVICE_GUARD(e);
+  DevBuf da, dr, dpc, dap, drp, dl, dt, df, di;
+  cudaError_t er = da.ensure((size_t)L * n * 8);
+  if (er == cudaSuccess) er = dr.ensure((size_t)L * n * 8);
+  if (er == cudaSuccess) er = dpc.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = dap.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = drp.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = dl.ensure((size_t)n * 8);
+  if (er == cudaSuccess) er = dt.ensure((size_t)n * 8);
+  if (er == cudaSuccess) er = df.ensure(n);
+  if (er == cudaSuccess) er = di.ensure((size_t)n * 4);
+  auto h2d = [&](DevBuf& d, const void* src, size_t bytes) {
+    if (er == cudaSuccess) er = cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, e->s);
+  };
+  h2d(da, t->alloc, (size_t)L * n * 8); h2d(dr, t->requested, (size_t)L * n * 8);
+  h2d(dpc, t->pod_count, (size_t)n * 4); h2d(dap, t->alloc_present, (size_t)n * 4);
+  h2d(drp, t->req_present, (size_t)n * 4); h2d(dl, t->label_mask, (size_t)n * 8);
+  h2d(dt, t->taint_mask, (size_t)n * 8); h2d(df, t->flags, n); h2d(di, idx, (size_t)n * 4);
+  if (er == cudaSuccess) {
+    NodeTabMut dst{e->d_alloc.as<int64_t>(), e->d_requested.as<int64_t>(), e->d_pod_count.as<int32_t>(),
+                   e->d_apres.as<uint32_t>(), e->d_rpres.as<uint32_t>(), e->d_label.as<uint64_t>(),
+                   e->d_taint.as<uint64_t>(), e->d_nflags.as<uint8_t>()};
+    NodeTab src{};
+    src.alloc = da.as<int64_t>(); src.requested = dr.as<int64_t>(); src.pod_count = dpc.as<int32_t>();
+    src.alloc_present = dap.as<uint32_t>(); src.req_present = drp.as<uint32_t>(); src.label = dl.as<uint64_t>();
+    src.taint = dt.as<uint64_t>(); src.flags = df.as<uint8_t>();
+    node_scatter_kernel<<<cdiv(n, 256), 256, 0, e->s>>>(dst, e->Npad, L, src, di.as<uint32_t>(), n);
+    e->launches++;
+    er = cudaStreamSynchronize(e->s);
+  }
+  da.release(); dr.release(); dpc.release(); dap.release(); drp.release(); dl.release(); dt.release(); df.release();
+  di.release();
+  CK(er);
+  // lane maxima only ever grow here (a conservative bound keeps the wide/narrow split exact)
+  for (uint32_t d = 0; d < L; ++d) {
+    e->max_alloc[d] = std::max(e->max_alloc[d], mx_a[d]);
+    e->max_requested[d] = std::max(e->max_requested[d], mx_r[d]);
+  }
+  for (uint32_t k = 0; k < n; ++k) {
+    e->max_pod_count = std::max<int64_t>(e->max_pod_count, std::abs((int64_t)t->pod_count[k]));
+    e->h_nflags[idx[k]] = t->flags[k];
+  }
+  e->nodes_dirty = true;
+  e->evaluated = false;
+  return BS_OK;
+}
+
 int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if (!e || !t) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);

@@ -206,6 +206,34 @@ __global__ void node_left_kernel(NodeTab t, LaneMap lm, int64_t* __restrict__ le
   left_present[i] = both;
 }
 
+// scatter of changed node rows into the resident node table (bs_update_nodes)
+struct NodeTabMut {
+  int64_t* alloc;
+  int64_t* requested;
+  int32_t* pod_count;
+  uint32_t* alloc_present;
+  uint32_t* req_present;
+  uint64_t* label;
+  uint64_t* taint;
+  uint8_t* flags;
+};
+__global__ void node_scatter_kernel(NodeTabMut dst, uint32_t Npad, uint32_t L, NodeTab src /*compact, Npad = n*/,
+                                    const uint32_t* __restrict__ idx, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = idx[k];
+  for (uint32_t d = 0; d < L; ++d) {
+    dst.alloc[(size_t)d * Npad + i] = src.alloc[(size_t)d * n + k];
+    dst.requested[(size_t)d * Npad + i] = src.requested[(size_t)d * n + k];
+  }
+  dst.pod_count[i] = src.pod_count[k];
+  dst.alloc_present[i] = src.alloc_present[k];
+  dst.req_present[i] = src.req_present[k];
+  dst.label[i] = src.label[k];
+  dst.taint[i] = src.taint[k];
+  dst.flags[i] = src.flags[k];
+}
+
 // generic singleNodeResource table for one class (bs_node_left): left[L][N], present[N]
 __global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, float pct,
                                        int64_t* __restrict__ left, uint32_t* __restrict__ present) {

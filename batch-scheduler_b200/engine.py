@@ -67,6 +67,15 @@ class Engine:
         self._check(self.lib.bs_upload_nodes(self.h, C.byref(t)))
         self.N = nt.n
 
+    def update_nodes(self, idx, rows: NodeTable):
+        """Overwrites rows `idx` of the resident node table with `rows` (a compact NodeTable)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        assert len(idx) == rows.n
+        t = capi.NodeTableC(rows.n, rows.lanes, capi.ptr(rows.alloc), capi.ptr(rows.requested),
+                            capi.ptr(rows.pod_count), capi.ptr(rows.alloc_present), capi.ptr(rows.req_present),
+                            capi.ptr(rows.label_mask), capi.ptr(rows.taint_mask), capi.ptr(rows.flags))
+        self._check(self.lib.bs_update_nodes(self.h, capi.ptr(idx), C.byref(t)))
+
     def upload_groups(self, gt: GroupTable):
         t = capi.GroupTableC(gt.n, gt.lanes, capi.ptr(gt.min_member), capi.ptr(gt.scheduled), capi.ptr(gt.matched),
                              capi.ptr(gt.flags), capi.ptr(gt.min_res), capi.ptr(gt.min_res_present),

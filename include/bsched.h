@@ -220,6 +220,10 @@ const char* bs_last_error(const bs_engine* e);
  *      PreFilter/Permit/Compare (core.go:88,268,368).  Host arrays are copied;
  *      nothing is retained. ---- */
 int bs_upload_nodes(bs_engine* e, const bs_node_table* t);
+/* Incremental snapshot update: overwrite rows idx[0..t->n_nodes) of the uploaded node table with
+ * the rows of `t` (a compact table of the changed nodes, same lane layout).  The snapshot's list
+ * order and size do not change; between scheduling cycles only a few NodeInfos differ. */
+int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t);
 int bs_upload_groups(bs_engine* e, const bs_group_table* t);
 int bs_upload_pods(bs_engine* e, const bs_pod_table* t);
 /* max_schedule_time: plugin arg (batchscheduler.go:71-75, util.GetWaitTimeDuration

@@ -368,3 +368,29 @@ def test_concurrent_mirror_calls_are_safe(pkg, oracle, snapshot_mod):
         t.join()
     assert not errors, errors[:1]
     eng.close()
+
+
+def test_incremental_node_update(pkg, oracle, snapshot_mod):
+    """bs_update_nodes: changing a few NodeInfos between cycles == re-uploading the whole snapshot."""
+    S = snapshot_mod
+    snap = random_snapshot(5150, P=220, N=900, G=14, L=5)
+    other = random_snapshot(5151, P=10, N=900, G=2, L=5).nodes
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=True, score=True)
+    eng.upload(snap)
+    eng.evaluate()
+    rng = np.random.default_rng(3)
+    for round_ in range(3):
+        idx = np.sort(rng.choice(snap.nodes.n, size=37, replace=False)).astype(np.uint32)
+        rows = S.NodeTable(other.alloc[:, idx], other.requested[:, idx], other.pod_count[idx], other.alloc_present[idx],
+                           other.req_present[idx], other.label_mask[idx], other.taint_mask[idx], other.flags[idx])
+        if round_ == 2:   # a huge value flips a lane from narrow to wide
+            rows.alloc[0, 0] = 1 << 40
+        for f in ("alloc", "requested"):
+            getattr(snap.nodes, f)[:, idx] = getattr(rows, f)
+        for f in ("pod_count", "alloc_present", "req_present", "label_mask", "taint_mask", "flags"):
+            getattr(snap.nodes, f)[idx] = getattr(rows, f)
+        eng.update_nodes(idx, rows)
+        res = eng.evaluate()
+        orc = oracle.round(snap, want_bitmap=True, want_score=True)
+        assert_round_equal(res, eng.fit_rows(), eng.score_rows(), orc)
+    eng.close()
