@@ -235,8 +235,9 @@ int bso_compare(const bso_pods* pd, const bso_groups* gr, uint32_t a, uint32_t b
     if (name2_empty) return 0;                                   /* :391 */
   }
   /* :395-399 lister lookups; Get("") or an unknown group is an error */
-  const int miss1 = name1_empty || g1 == BSO_GID_MISSING || (pd->flags[a] & BSO_POD_LISTER_MISS);
-  const int miss2 = name2_empty || g2 == BSO_GID_MISSING || (pd->flags[b] & BSO_POD_LISTER_MISS);
+  /* a group index outside the table is an unknown group as well */
+  const int miss1 = name1_empty || g1 < 0 || (uint32_t)g1 >= gr->n || (pd->flags[a] & BSO_POD_LISTER_MISS);
+  const int miss2 = name2_empty || g2 < 0 || (uint32_t)g2 >= gr->n || (pd->flags[b] & BSO_POD_LISTER_MISS);
   if (miss1 || miss2) return 0;
   const int64_t c1 = gr->creation_ns[g1], c2 = gr->creation_ns[g2];
   const uint32_t r1 = gr->name_rank[g1], r2 = gr->name_rank[g2];
@@ -256,8 +257,8 @@ static int key_less(const bso_pods* pd, const bso_groups* gr, uint32_t a, uint32
   const int grouped1 = g1 != BSO_GID_NONE, grouped2 = g2 != BSO_GID_NONE;
   if (grouped1 != grouped2) return grouped1 < grouped2;
   if (!grouped1) return pd->ts_ns[a] < pd->ts_ns[b];
-  const int miss1 = g1 == BSO_GID_MISSING || (pd->flags[a] & BSO_POD_LISTER_MISS);
-  const int miss2 = g2 == BSO_GID_MISSING || (pd->flags[b] & BSO_POD_LISTER_MISS);
+  const int miss1 = g1 < 0 || (uint32_t)g1 >= gr->n || (pd->flags[a] & BSO_POD_LISTER_MISS);
+  const int miss2 = g2 < 0 || (uint32_t)g2 >= gr->n || (pd->flags[b] & BSO_POD_LISTER_MISS);
   const int64_t c1 = miss1 ? INT64_MAX : gr->creation_ns[g1];
   const int64_t c2 = miss2 ? INT64_MAX : gr->creation_ns[g2];
   if (c1 != c2) return c1 < c2;

@@ -394,3 +394,34 @@ def test_incremental_node_update(pkg, oracle, snapshot_mod):
         orc = oracle.round(snap, want_bitmap=True, want_score=True)
         assert_round_equal(res, eng.fit_rows(), eng.score_rows(), orc)
     eng.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_extreme_values(pkg, oracle, snapshot_mod, seed):
+    """Corners of the value domain: magnitudes at +-2^56, negative capacities / requests, int64-extreme
+    timestamps and creation times, uint32-extreme name ranks and counters, out-of-range group ids."""
+    S = snapshot_mod
+    rng = np.random.default_rng(900 + seed)
+    snap = random_snapshot(9000 + seed, P=180, N=130, G=16, L=[5, 6, 9, 12][seed])
+    nt, pt, gt = snap.nodes, snap.pods, snap.groups
+    LIM = 1 << 56
+    for d in range(snap.lanes):
+        pick = rng.random(nt.n) < 0.3
+        nt.alloc[d] = np.where(pick, rng.choice([LIM, LIM - 1, -LIM, 0, 1, -1, (1 << 26), (1 << 26) + 1], nt.n), nt.alloc[d])
+        pick = rng.random(nt.n) < 0.3
+        nt.requested[d] = np.where(pick, rng.choice([LIM, -LIM, 0, 1, -5, 1 << 55], nt.n), nt.requested[d])
+        pick = rng.random(pt.n) < 0.3
+        pt.req[d] = np.where(pick, rng.choice([LIM, -LIM, 0, -1, 1, (1 << 27), (1 << 27) + 1, 1 << 40], pt.n), pt.req[d])
+        pick = rng.random(gt.n) < 0.3
+        gt.min_res[d] = np.where(pick, rng.choice([LIM, -LIM, 0, 7, -7], gt.n), gt.min_res[d])
+    nt.pod_count = rng.choice([0, 1, 2**31 - 1, -5, 100], nt.n).astype(np.int32)
+    I64 = np.iinfo(np.int64)
+    pt.ts_ns = rng.choice([I64.min, I64.max, 0, -1, 1, 10**18], pt.n)
+    gt.creation_ns = rng.choice([I64.min, I64.max - 1, 0, -1, 1], gt.n)
+    gt.name_rank = rng.choice([0, 1, 2**32 - 1, 2**31], gt.n).astype(np.uint32)
+    gt.min_member = rng.choice([1, 2, 2**32 - 1, 2**31, 7], gt.n).astype(np.uint32)
+    gt.scheduled = rng.choice([0, 1, 2**32 - 1, 7], gt.n).astype(np.uint32)
+    gt.matched = rng.choice([0, 1, 2**32 - 1, 5000000], gt.n).astype(np.uint32)
+    pt.gid = np.where(rng.random(pt.n) < 0.1, gt.n + 5, pt.gid).astype(np.int32)
+    pt.priority = rng.choice([-2**31, 2**31 - 1, 0, -1, 1], pt.n).astype(np.int32)
+    run_and_compare(pkg, oracle, snap)
