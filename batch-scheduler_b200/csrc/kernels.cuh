@@ -953,12 +953,13 @@ __global__ void group_idle_admit_kernel(GroupTab g, GroupEff e, uint8_t* __restr
 // reduction + one atomic per run, the last pod of a group (ticket) writing the
 // admit / Wait / Unschedulable verdict.
 //
-// Mapping: a CTA owns PODS_PER_CTA pods (each warp PODS_PER_WARP of them) and
-// sweeps the whole node table in tiles of NODE_TILE nodes, staged into shared
-// memory by 1-D TMA bulk copies (one per lane row) on a 2-stage mbarrier ring.
-// A lane owns nodes lane, lane+32, ... of the tile, keeps their `left` in
-// registers and evaluates POD_BLOCK pods against them at a time.  Score rows are
-// written with 8-byte streaming stores, 256 contiguous bytes per warp store.
+// Mapping: a CTA = FIT_WARPS consumer warps + one producer warp.  It owns PODS_PER_CTA
+// pods (each consumer warp PODS_PER_WARP of them, requests in registers) and sweeps the
+// whole node table in tiles of NODE_TILE nodes; the producer lane streams the tiles into a
+// FIT_STAGES-deep shared-memory ring with 1-D TMA bulk copies (one per lane row), guarded
+// by full/empty mbarrier pairs.  A lane owns nodes lane, lane+32, ... of the tile, keeps
+// their `left` in registers and evaluates PODS_PER_WARP pods against them at a time.  Score
+// rows are written with 8-byte streaming stores, 256 contiguous bytes per warp store.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
