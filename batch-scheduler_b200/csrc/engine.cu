@@ -633,6 +633,7 @@ int ensure_round_buffers(bs_engine* e) {
   size_t budget = (size_t)1 << 30;
   if (const char* bs = getenv("BS_PREFIX_BUDGET_BYTES")) budget = std::max<size_t>(1, strtoull(bs, nullptr, 10));
   uint32_t slots = (uint32_t)std::max<size_t>(1, std::min<size_t>(e->n_rep_classes, budget / per_class));
+  slots = std::min(slots, 32768u);   // one grid row (gridDim.y <= 65535) per resident class
   e->prefix_slots = slots;
   CK(e->d_pre.ensure((size_t)slots * L * N * 8));
   CK(e->d_pre_present.ensure((size_t)slots * N * 4));
@@ -689,11 +690,13 @@ int prepare_nodes(bs_engine* e) {
                                                          (e->out_flags & BS_OUT_FILTER) ? e->d_left_plain.as<int64_t>() : nullptr);
   tm.launched();
   {
-    dim3 grid(cdiv(n_tiles * 32, 256), e->n_fit_classes);
-    class_fit_kernel<<<grid, 256, 0, e->s>>>(t, e->d_left_present.as<uint32_t>(), e->d_fsel.as<uint64_t>(),
-                                             e->d_ftol.as<uint64_t>(), e->d_fnz.as<uint32_t>(),
-                                             e->n_fit_classes, n_tiles, e->d_classfit.as<ColBits>());
-    tm.launched();
+    for (uint32_t c0 = 0; c0 < e->n_fit_classes; c0 += 32768) {
+      dim3 grid(cdiv(n_tiles * 32, 256), std::min(32768u, e->n_fit_classes - c0));
+      class_fit_kernel<<<grid, 256, 0, e->s>>>(t, e->d_left_present.as<uint32_t>(), e->d_fsel.as<uint64_t>(),
+                                               e->d_ftol.as<uint64_t>(), e->d_fnz.as<uint32_t>(),
+                                               e->n_fit_classes, n_tiles, e->d_classfit.as<ColBits>(), c0);
+      tm.launched();
+    }
   }
   CK(cudaGetLastError());
   e->nodes_dirty = false;

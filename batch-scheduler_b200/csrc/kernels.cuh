@@ -255,8 +255,8 @@ __global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, fl
 __global__ void class_fit_kernel(NodeTab t, const uint32_t* __restrict__ left_present,
                                  const uint64_t* __restrict__ csel, const uint64_t* __restrict__ ctol,
                                  const uint32_t* __restrict__ cnz, uint32_t n_classes, uint32_t n_tiles,
-                                 ColBits* __restrict__ classfit) {
-  const uint32_t c = blockIdx.y;
+                                 ColBits* __restrict__ classfit, uint32_t class0) {
+  const uint32_t c = class0 + blockIdx.y;   // gridDim.y is capped at 65535: classes go in chunks
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;  // tile * 32 + lane
   if (slot >= n_tiles * 32 || c >= n_classes) return;
   const uint32_t tile = slot >> 5, lane = slot & 31;

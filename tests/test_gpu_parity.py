@@ -425,3 +425,17 @@ def test_extreme_values(pkg, oracle, snapshot_mod, seed):
     pt.gid = np.where(rng.random(pt.n) < 0.1, gt.n + 5, pt.gid).astype(np.int32)
     pt.priority = rng.choice([-2**31, 2**31 - 1, 0, -1, 1], pt.n).astype(np.int32)
     run_and_compare(pkg, oracle, snap)
+
+
+@pytest.mark.parametrize("case", ["A", "B"])
+def test_more_than_65535_classes(pkg, oracle, snapshot_mod, case):
+    """Every pod its own selector/toleration class: class tables beyond one grid dimension
+    (gridDim.y <= 65535) and beyond one prefix-scratch chunk."""
+    rng = np.random.default_rng(77)
+    snap = random_snapshot(6500, P=70000, N=64, G=300, L=5, case=case)
+    snap.pods.sel_mask = rng.integers(0, 1 << 62, snap.pods.n).astype(np.uint64) & np.uint64(0xFFFFFFFFFFFFFFF0)
+    snap.pods.sel_mask |= rng.integers(0, 16, snap.pods.n).astype(np.uint64)
+    snap.pods.sel_mask[::7] = 0                      # some pods still fit somewhere
+    snap.pods.tol_mask = rng.integers(0, 1 << 40, snap.pods.n).astype(np.uint64)
+    snap.groups.flags &= ~np.uint8(snapshot_mod.GROUP_HAS_POD)   # representatives come from the pods
+    run_and_compare(pkg, oracle, snap, score=False)
