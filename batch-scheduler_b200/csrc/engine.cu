@@ -793,7 +793,7 @@ int evaluate_async_locked(bs_engine* e) {
     }
     const uint32_t nmp = cdiv(std::max(G, 1u), FINDMAX_THREADS * FINDMAX_PER_THREAD);
     find_max_partial_kernel<<<nmp, FINDMAX_THREADS, 0, e->s>>>(gt, ge, e->d_max_partial.as<MaxState>());
-    find_max_final_kernel<<<1, 1024, 0, e->s>>>(gt, ge, e->d_max_partial.as<MaxState>(), nmp, st);
+    find_max_final_kernel<<<1, 1024, 0, e->s>>>(gt, ge, e->d_max_partial.as<MaxState>(), nmp, st, e->N);
     tm.launched(2);
   }
   // ordered cluster scans (compareClusterResourceAndRequire) per rep class

@@ -68,7 +68,8 @@ struct RoundState {
   int32_t case_a;         // 1: matched==0 branch (core.go:136), pct 1.0, need of the pod's own group
   int32_t ref_panic;      // findMaxPG would divide by zero
   int32_t max_class;      // rep class of max_group (case B)
-  int32_t pad0, pad1;
+  int32_t no_nodes;       // empty snapshot list: every cluster check is false (core.go:604,631)
+  int32_t pad1;
   int64_t base_need[BS_MAX_LANES]; // getPreAllocatedResource(max, matched) (case B, core.go:157)
   uint32_t base_present;
 };
@@ -468,7 +469,7 @@ find_max_partial_kernel(GroupTab g, GroupEff e, MaxState* __restrict__ partial) 
 
 __global__ void __launch_bounds__(1024)
 find_max_final_kernel(GroupTab g, GroupEff e, const MaxState* __restrict__ partial, uint32_t n_partial,
-                      RoundState* st) {
+                      RoundState* st, uint32_t n_nodes) {
   __shared__ MaxState s_part[32];
   MaxState v = max_state_empty();
   for (uint32_t i = threadIdx.x; i < n_partial; i += blockDim.x) v = max_state_merge(v, partial[i]);
@@ -481,6 +482,7 @@ find_max_final_kernel(GroupTab g, GroupEff e, const MaxState* __restrict__ parti
       else if (v.zlast != 0) winner = v.zlast - 1;
     }
     st->ref_panic = (int32_t)v.panic;
+    st->no_nodes = n_nodes == 0 ? 1 : 0;
     st->max_group = none ? -1 : (int32_t)winner;
     st->max_finished = none ? 0u : v.F;
     st->max_matched = none ? 0u : g.matched[winner];
@@ -836,7 +838,7 @@ prefilter_kernel(NodeTab t, PodTab p, GroupTab g, GroupEff e, PrefixOut po,
   __shared__ int s_cand_idx[BS_MAX_LANES + 1];
   const int L = (int)t.L;
   const uint32_t N = t.N;
-  const bool case_b = st->max_group >= 0 && !st->case_a;
+  const bool case_b = st->max_group >= 0 && !st->case_a && !st->no_nodes;
   if (case_b) {
     if (threadIdx.x == 0) s_cs = po.stats[0];
     __syncthreads();
@@ -869,7 +871,7 @@ prefilter_kernel(NodeTab t, PodTab p, GroupTab g, GroupEff e, PrefixOut po,
     else if (pf & BS_POD_OCC_MISMATCH) code = BS_PF_ERR_OCCUPIED;               // :507-510
     else if (st->max_group < 0) code = BS_PF_PASS;                              // :127-130
     else if (st->case_a) {                                                      // :136-147
-      if (okA[gi] == 2) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
+      if (okA[gi] == 2 || st->no_nodes) { code = BS_PF_ERR_NOT_ENOUGH; deny = true; }
     } else if (st->max_group == gi) code = BS_PF_PASS;                          // :150-155
     else {                                                                      // :157-165
       npres = st->base_present;
@@ -880,7 +882,7 @@ prefilter_kernel(NodeTab t, PodTab p, GroupTab g, GroupEff e, PrefixOut po,
       }
       npres |= rp;
       // 1. bounds  2. candidates (see warp_cluster_check)  3. cooperative scan if undecided
-      bool reject = s_cs.last_visited < 0;
+      bool reject = st->no_nodes || s_cs.last_visited < 0;
       for (int d = 0; d < L && !reject; ++d) {
         const bool checked = d < 4 || ((npres >> d) & 1u);
         if (!checked) continue;

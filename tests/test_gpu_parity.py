@@ -82,6 +82,11 @@ def test_ragged_and_empty(pkg, oracle, snapshot_mod):
     for n in (1, 31, 32, 33, 511, 512, 513, 1100):
         snap = random_snapshot(200 + n, P=70, N=n, G=6, L=5)
         run_and_compare(pkg, oracle, snap, score=(n < 600))
+    # empty snapshot list: every cluster check is false (core.go:604,631)
+    for case in ("A", "B"):
+        snap = random_snapshot(103, P=40, N=0, G=5, L=5, case=case)
+        res, _ = run_and_compare(pkg, oracle, snap)
+        assert (res.feasible_count == 0).all()
     # every node skipped: the cluster loop never compares (core.go:606-631)
     snap = random_snapshot(102, P=40, N=20, G=5, L=5, case="A")
     snap.nodes.flags[:] = S.NODE_UNSCHEDULABLE
