@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbsched.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["kernels.cuh", "sort.cuh", os.path.join("..", "..", "include", "bsched.h")]
+HEADERS = ["kernels.cuh", "sort.cuh", "replay.cuh", os.path.join("..", "..", "include", "bsched.h")]
 
 
 def nvcc_path() -> str:

@@ -19,8 +19,8 @@ CODE_SUCCESS, CODE_ERROR, CODE_UNSCHEDULABLE, CODE_UNSCHEDULABLE_AND_UNRESOLVABL
 OUT_FIT_BITMAP, OUT_SCORE, OUT_FILTER = 0x1, 0x2, 0x4
 FILTER_PASS, FILTER_NOT_FOUND, FILTER_NOT_ENOUGH, FILTER_NO_SNAPSHOT, FILTER_REF_PANIC = range(5)
 BUF_FIT_BITMAP, BUF_SCORE, BUF_ADMIT_BITMAP, BUF_PREFILTER, BUF_ADMIT, BUF_ORDER, BUF_GATHERED_ADMIT = range(7)
-K_NODE_LEFT, K_FIND_MAX, K_CLASS_PREFIX, K_PREFILTER, K_GANG_FIT, K_SORT, K_FILTER, K_PEER, K_COUNT = range(9)
-KERNEL_NAMES = ["node_left", "find_max", "class_prefix", "prefilter", "gang_fit", "sort", "filter", "peer"]
+K_NODE_LEFT, K_FIND_MAX, K_CLASS_PREFIX, K_PREFILTER, K_GANG_FIT, K_SORT, K_FILTER, K_PEER, K_REPLAY, K_COUNT = range(10)
+KERNEL_NAMES = ["node_left", "find_max", "class_prefix", "prefilter", "gang_fit", "sort", "filter", "peer", "replay"]
 
 
 def _p(t):
@@ -57,6 +57,13 @@ class ResultsC(C.Structure):
                 ("max_group", C.c_int32), ("max_finished", C.c_uint32), ("filter_code", C.c_void_p)]
 
 
+class ReplayResultC(C.Structure):
+    _fields_ = [("prefilter", C.c_void_p), ("node", C.c_void_p), ("ready", C.c_void_p),
+                ("node_requested", C.c_void_p), ("node_pod_count", C.c_void_p), ("node_req_present", C.c_void_p),
+                ("group_matched", C.c_void_p), ("group_flags", C.c_void_p), ("group_min_res", C.c_void_p),
+                ("group_min_res_present", C.c_void_p), ("group_rep_sel", C.c_void_p), ("group_rep_tol", C.c_void_p)]
+
+
 class StatusC(C.Structure):
     _fields_ = [("code", C.c_int32), ("reason", C.c_int32), ("group", C.c_int32)]
 
@@ -88,6 +95,7 @@ SYMBOLS = {
     "bs_filter": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(StatusC)]),
     "bs_format_message": (C.c_int, [_p(StatusC), C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "bs_node_left": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
+    "bs_replay": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, _p(ReplayResultC)]),
     "bs_cluster_check": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_uint32, C.c_void_p]),
     "bs_device_buffer": (C.c_int, [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_size_t)]),

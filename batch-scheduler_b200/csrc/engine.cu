@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "sort.cuh"
+#include "replay.cuh"
 
 using namespace bsk;
 
@@ -196,6 +197,7 @@ struct bs_engine {
   // per-lane maxima of |value| (lane classification wide / narrow)
   int64_t max_alloc[BS_MAX_LANES] = {}, max_requested[BS_MAX_LANES] = {}, max_req[BS_MAX_LANES] = {};
   int64_t max_pod_count = 0;
+  int64_t neg_req[BS_MAX_LANES] = {};   // largest negative request per lane (0 when none)
   // pod table
   DevBuf d_req, d_ppres, d_gid, d_prio, d_ts, d_pflags, d_pod_fit_class, d_pod_rep_class;
   // group table
@@ -448,6 +450,17 @@ void launch_prefix(uint32_t L, NodeTab t, PrefixSel ps, PrefixScratch sc, Prefix
     case 9: launch_prefix_t<9>(t, ps, sc, po, n_classes, s); break;
     case 12: launch_prefix_t<12>(t, ps, sc, po, n_classes, s); break;
     default: launch_prefix_t<16>(t, ps, sc, po, n_classes, s); break;
+  }
+}
+
+template <int MAXL>
+void launch_replay_t(const ReplayArgs& a, cudaStream_t s) { replay_kernel<MAXL><<<1, REPLAY_THREADS, 0, s>>>(a); }
+inline uint32_t replay_maxl(uint32_t L) { return L <= 5 ? 5u : L <= 9 ? 9u : 16u; }
+void launch_replay(uint32_t L, const ReplayArgs& a, cudaStream_t s) {
+  switch (replay_maxl(L)) {
+    case 5: launch_replay_t<5>(a, s); break;
+    case 9: launch_replay_t<9>(a, s); break;
+    default: launch_replay_t<16>(a, s); break;
   }
 }
 
@@ -1249,7 +1262,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       e->h_prc[p] = pt.rep.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], 0u});
     }
   }
-  int64_t mx_q[BS_MAX_LANES] = {};
+  int64_t mx_q[BS_MAX_LANES] = {}, neg_q[BS_MAX_LANES] = {};
   {
     uint64_t ot = 0, at = ~0ull;
     uint32_t op = 0, apr = ~0u;
@@ -1261,6 +1274,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       for (uint32_t d = 0; d < L; ++d) {
         ok = ok && pt.lo[d] >= -BS_VALUE_LIMIT && pt.hi[d] <= BS_VALUE_LIMIT;
         mx_q[d] = std::max(mx_q[d], std::max(pt.hi[d], pt.lo[d] == INT64_MIN ? INT64_MAX : -pt.lo[d]));
+        neg_q[d] = std::max(neg_q[d], pt.lo[d] == INT64_MIN ? INT64_MAX : -pt.lo[d]);
       }
       ot |= pt.ot; at &= pt.at; op |= pt.op; apr &= pt.apr; miss |= pt.miss; mg = std::max(mg, pt.mg);
     }
@@ -1308,6 +1322,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   e->group_classes_dirty = true;
   CK(cudaStreamSynchronize(e->s));
   memcpy(e->max_req, mx_q, sizeof(mx_q));
+  memcpy(e->neg_req, neg_q, sizeof(neg_q));
   e->P = P;
   e->have_pods = true;
   e->classes_dirty = true;
@@ -1517,6 +1532,153 @@ int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent, co
   pre.release(); pp.release(); stats.release(); dn.release(); dnp.release(); dok.release();
   spart.release(); spres.release(); scst.release(); sdone.release();
   CK(er);
+  return BS_OK;
+}
+
+int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_result* out) {
+  if (!e || !out) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_nodes || !e->have_pods || !e->have_groups)
+    return fail(e, BS_E_STATE, "bs_replay: upload nodes, groups and pods first");
+  BS_DEVICE_GUARD(e);
+  const uint32_t N = e->N, Npad = e->Npad, P = e->P, G = e->G, L = e->L;
+  if (!queue) n_queue = P;
+  if (n_queue && (!out->prefilter || !out->node || !out->ready)) return BS_E_INVAL;
+  if (queue)
+    for (uint32_t i = 0; i < n_queue; ++i)
+      if (queue[i] >= P) return fail(e, BS_E_INDEX, "bs_replay: queue entry is not a pod of the table");
+  int rc;
+  if (e->classes_dirty && (rc = rebuild_classes(e))) return rc;
+
+  // scratch copies of everything the cycle mutates
+  DevBuf s_req, s_pc, s_rp, s_matched, s_gflags, s_grc, s_minres, s_mrp, d_queue, d_pf, d_node, d_ready, d_status,
+      c_sum, c_max, c_keys;
+  auto release_all = [&]() {
+    for (DevBuf* b : {&s_req, &s_pc, &s_rp, &s_matched, &s_gflags, &s_grc, &s_minres, &s_mrp, &d_queue, &d_pf, &d_node,
+                      &d_ready, &d_status, &c_sum, &c_max, &c_keys})
+      b->release();
+  };
+  const uint32_t Gp = std::max(G, 1u), Qp = std::max(n_queue, 1u);
+  cudaError_t er = s_req.ensure((size_t)L * Npad * 8);
+  auto dup = [&](DevBuf& dst, const DevBuf& src, size_t bytes) {
+    if (er == cudaSuccess) er = dst.ensure(std::max<size_t>(bytes, 4));
+    if (er == cudaSuccess && bytes) er = cudaMemcpyAsync(dst.p, src.p, bytes, cudaMemcpyDeviceToDevice, e->s);
+  };
+  dup(s_req, e->d_requested, (size_t)L * Npad * 8);
+  dup(s_pc, e->d_pod_count, (size_t)Npad * 4);
+  dup(s_rp, e->d_rpres, (size_t)Npad * 4);
+  dup(s_matched, e->d_matched, (size_t)G * 4);
+  dup(s_gflags, e->d_gflags, (size_t)G);
+  dup(s_grc, e->d_group_rep_class, (size_t)G * 4);
+  dup(s_minres, e->d_min_res, (size_t)L * G * 8);
+  dup(s_mrp, e->d_mrpres, (size_t)G * 4);
+  if (er == cudaSuccess) er = d_queue.ensure((size_t)Qp * 4);
+  if (er == cudaSuccess && queue && n_queue)
+    er = cudaMemcpyAsync(d_queue.p, queue, (size_t)n_queue * 4, cudaMemcpyHostToDevice, e->s);
+  if (er == cudaSuccess) er = d_pf.ensure(Qp);
+  if (er == cudaSuccess) er = d_node.ensure((size_t)Qp * 4);
+  if (er == cudaSuccess) er = d_ready.ensure(Qp);
+  if (er == cudaSuccess) er = d_status.ensure(128);
+  if (er == cudaSuccess) er = cudaMemsetAsync(d_status.p, 0, 128, e->s);
+  int32_t status = 0;
+  if (er == cudaSuccess) {
+    ReplayArgs a{};
+    a.nt = node_tab(e);
+    a.nt.requested = s_req.as<int64_t>();
+    a.nt.pod_count = s_pc.as<int32_t>();
+    a.nt.req_present = s_rp.as<uint32_t>();
+    a.requested = s_req.as<int64_t>();
+    a.pod_count = s_pc.as<int32_t>();
+    a.req_present = s_rp.as<uint32_t>();
+    a.pt = pod_tab(e);
+    a.fsel = e->d_fsel.as<uint64_t>();
+    a.ftol = e->d_ftol.as<uint64_t>();
+    a.rsel = e->d_rsel.as<uint64_t>();
+    a.rtol = e->d_rtol.as<uint64_t>();
+    a.n_rep = e->n_rep_classes;
+    {
+      // block cache of the cluster scan (replay.cuh): every running sum must stay below 2^62.
+      // A pod is only assumed where it fits, so a node's `requested` never passes its capacity by
+      // more than one request; only negative requests accumulate without that limit.
+      long double worst = 0;
+      for (uint32_t d = 0; d < L; ++d)
+        worst = std::max(worst, (long double)e->max_alloc[d] + (long double)e->max_requested[d] + (long double)e->max_req[d] +
+                                    (long double)e->neg_req[d] * (long double)n_queue + (long double)e->max_pod_count + n_queue);
+      const bool safe = worst * (long double)std::max(N, 1u) < 4.0e18L;
+      const uint32_t n_blocks = cdiv(N, REPLAY_THREADS);
+      const uint32_t maxl = replay_maxl(L);
+      a.cache_ok = 0;
+      if (safe && a.n_rep <= (uint32_t)REPLAY_MAX_CLASSES && n_blocks >= 2 && n_blocks <= (uint32_t)REPLAY_THREADS) {
+        const size_t rows = (size_t)2 * a.n_rep * n_blocks;
+        er = c_sum.ensure(rows * maxl * 8);
+        if (er == cudaSuccess) er = c_max.ensure(rows * maxl * 8);
+        if (er == cudaSuccess) er = c_keys.ensure(rows * 4);
+        a.blk_sum = c_sum.as<int64_t>();
+        a.blk_max = c_max.as<int64_t>();
+        a.blk_keys = c_keys.as<uint32_t>();
+        a.cache_ok = 1;
+      }
+    }
+    a.min_member = e->d_min_member.as<uint32_t>();
+    a.scheduled = e->d_scheduled.as<uint32_t>();
+    a.matched = s_matched.as<uint32_t>();
+    a.gflags = s_gflags.as<uint8_t>();
+    a.grc = s_grc.as<uint32_t>();
+    a.min_res = s_minres.as<int64_t>();
+    a.mrpres = s_mrp.as<uint32_t>();
+    a.G = G;
+    a.queue = queue ? d_queue.as<uint32_t>() : nullptr;
+    a.n_queue = n_queue;
+    a.prefilter = d_pf.as<uint8_t>();
+    a.node = d_node.as<int32_t>();
+    a.ready = d_ready.as<uint8_t>();
+    a.status = d_status.as<int32_t>();
+    if (er == cudaSuccess) {
+      StageTimer tm(e, BS_K_REPLAY, e->s);
+      launch_replay(L, a, e->s);
+      tm.launched();
+      er = cudaGetLastError();
+    }
+  }
+  std::vector<uint32_t> grc;
+  auto d2h = [&](void* dst, const DevBuf& src, size_t bytes) {
+    if (er == cudaSuccess && dst && bytes) er = cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, e->s);
+  };
+  d2h(&status, d_status, 4);
+#ifdef BS_REPLAY_PROFILE
+  long long rp[8] = {};
+  d2h(rp, d_status, 0);
+  if (er == cudaSuccess) er = cudaMemcpyAsync(rp, (char*)d_status.p + 8, 64, cudaMemcpyDeviceToHost, e->s);
+#endif
+  d2h(out->prefilter, d_pf, n_queue);
+  d2h(out->node, d_node, (size_t)n_queue * 4);
+  d2h(out->ready, d_ready, n_queue);
+  if (er == cudaSuccess && out->node_requested && N)
+    er = cudaMemcpy2DAsync(out->node_requested, (size_t)N * 8, s_req.p, (size_t)Npad * 8, (size_t)N * 8, L,
+                           cudaMemcpyDeviceToHost, e->s);
+  d2h(out->node_pod_count, s_pc, (size_t)N * 4);
+  d2h(out->node_req_present, s_rp, (size_t)N * 4);
+  d2h(out->group_matched, s_matched, (size_t)G * 4);
+  d2h(out->group_flags, s_gflags, (size_t)G);
+  d2h(out->group_min_res, s_minres, (size_t)L * G * 8);
+  d2h(out->group_min_res_present, s_mrp, (size_t)G * 4);
+  if (out->group_rep_sel || out->group_rep_tol) {
+    grc.resize(Gp);
+    d2h(grc.data(), s_grc, (size_t)G * 4);
+  }
+  if (er == cudaSuccess) er = cudaStreamSynchronize(e->s);
+  release_all();
+  CK(er);
+  (void)Gp;
+#ifdef BS_REPLAY_PROFILE
+  fprintf(stderr, "replay clocks: init %lld pre %lld fill %lld findmax %lld cluster %lld misc %lld firstfit %lld commit %lld\n", rp[7], rp[0], rp[1], rp[2], rp[3], rp[4], rp[5], rp[6]);
+#endif
+  if (status) return fail(e, BS_E_REF_PANIC, "bs_replay: findMaxPG would divide by MinMember == 0 (core.go:716)");
+  for (uint32_t g = 0; g < G && (out->group_rep_sel || out->group_rep_tol); ++g) {
+    const ClassKey& k = e->rep_index.keys[grc[g]];
+    if (out->group_rep_sel) out->group_rep_sel[g] = k.sel;
+    if (out->group_rep_tol) out->group_rep_tol[g] = k.tol;
+  }
   return BS_OK;
 }
 

@@ -175,6 +175,27 @@ class Engine:
                                               capi.ptr(need_present), n, capi.ptr(ok)))
         return ok.astype(bool)
 
+    # -- multi-round admission -------------------------------------------
+    def replay(self, queue=None, after_state=True):
+        """The reference's pod-at-a-time cycle over the uploaded tables, on the device, in queue order.
+        Returns a dict: prefilter / node / ready per queue position and, with after_state, the mutated
+        node and group columns (the uploaded tables themselves are left untouched)."""
+        q = None if queue is None else np.ascontiguousarray(queue, dtype=np.uint32)
+        n = self.P if q is None else len(q)
+        L, N, G = self.n_lanes, self.N, self.G
+        out = dict(prefilter=np.zeros(n, np.uint8), node=np.zeros(n, np.int32), ready=np.zeros(n, np.uint8))
+        r = capi.ReplayResultC()
+        if after_state:
+            out.update(node_requested=np.zeros((L, N), np.int64), node_pod_count=np.zeros(N, np.int32),
+                       node_req_present=np.zeros(N, np.uint32), group_matched=np.zeros(G, np.uint32),
+                       group_flags=np.zeros(G, np.uint8), group_min_res=np.zeros((L, G), np.int64),
+                       group_min_res_present=np.zeros(G, np.uint32), group_rep_sel=np.zeros(G, np.uint64),
+                       group_rep_tol=np.zeros(G, np.uint64))
+        for k, v in out.items():
+            setattr(r, k, capi.ptr(v))
+        self._check(self.lib.bs_replay(self.h, None if q is None else capi.ptr(q), n, C.byref(r)))
+        return out
+
     # -- per-call mirrors ------------------------------------------------------------------
     def prefilter(self, pod: int):
         st = capi.StatusC()

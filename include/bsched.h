@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 2
+#define BS_ABI_VERSION 3
 #define BS_FIXED_LANES 4
 #define BS_MAX_LANES 16
 /* |value| bound accepted for every int64 table entry (validated at upload):
@@ -268,6 +268,34 @@ int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent,
                      const int64_t* need, const uint32_t* need_present, uint32_t n_needs,
                      uint8_t* ok);
 
+/* ---- multi-round admission on the device ----
+ * The reference schedules one pod per cycle against MUTABLE state: PreFilter reads the live group
+ * cache and snapshot (core.go:88-167), the chosen node's `requested` grows when the pod is assumed
+ * (NodeInfo.AddPod), Permit records the match and may mark the group Scheduled (core.go:268-309), a
+ * failed cluster check freezes the group (AddToDenyCache, core.go:423-425).  bs_replay walks `queue`
+ * (pod indices in pop order; NULL = table order, n_queue = number of pods) through exactly that
+ * cycle in ONE kernel, starting from the uploaded tables, which stay untouched.  The node a passing
+ * pod is assumed onto is the first node in list order where it fits (the stand-in for the upstream
+ * Filter/Score/selectHost the repo's oracle uses as well).  Sequential by nature: one GPU, no
+ * sharding ("replicas only").
+ * Outputs per queue position; the optional after-state arrays (NULL = not wanted) return the
+ * mutated copies so that the caller can continue from them (bs_upload_* / bs_update_nodes). */
+typedef struct bs_replay_result {
+  uint8_t* prefilter;          /* [n_queue] bs_prefilter_code */
+  int32_t* node;               /* [n_queue] assumed node, -1 none */
+  uint8_t* ready;              /* [n_queue] Permit returned ready (core.go:303) */
+  int64_t* node_requested;     /* [n_lanes][n_nodes] or NULL */
+  int32_t* node_pod_count;     /* [n_nodes] or NULL */
+  uint32_t* node_req_present;  /* [n_nodes] or NULL */
+  uint32_t* group_matched;     /* [n_groups] or NULL */
+  uint8_t* group_flags;        /* [n_groups] or NULL (BS_GROUP_*) */
+  int64_t* group_min_res;      /* [n_lanes][n_groups] or NULL */
+  uint32_t* group_min_res_present; /* [n_groups] or NULL */
+  uint64_t* group_rep_sel;     /* [n_groups] or NULL */
+  uint64_t* group_rep_tol;     /* [n_groups] or NULL */
+} bs_replay_result;
+int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_result* out);
+
 /* ---- device-side access for callers that keep results in HBM (bench, NCCL) ---- */
 typedef enum {
   BS_BUF_FIT_BITMAP = 0,
@@ -309,7 +337,8 @@ typedef enum {
   BS_K_SORT = 5,
   BS_K_FILTER = 6,     /* optional Filter matrix (BS_OUT_FILTER) */
   BS_K_PEER = 7,       /* admit-bitmap exchange over peer memory */
-  BS_K_COUNT = 8
+  BS_K_REPLAY = 8,     /* bs_replay: the pod-at-a-time cycle in one persistent kernel */
+  BS_K_COUNT = 9
 } bs_kernel_id;
 int bs_set_profiling(bs_engine* e, int on); /* record CUDA events around each stage */
 /* milliseconds of stage k in the last evaluation, and launches it took */
