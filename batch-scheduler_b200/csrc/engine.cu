@@ -1552,10 +1552,10 @@ int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_r
 
   // scratch copies of everything the cycle mutates
   DevBuf s_req, s_pc, s_rp, s_matched, s_gflags, s_grc, s_minres, s_mrp, d_queue, d_pf, d_node, d_ready, d_status,
-      c_sum, c_max, c_keys;
+      c_sum, c_max, c_keys, n_left0, n_left1, n_both, n_fit, n_stat;
   auto release_all = [&]() {
     for (DevBuf* b : {&s_req, &s_pc, &s_rp, &s_matched, &s_gflags, &s_grc, &s_minres, &s_mrp, &d_queue, &d_pf, &d_node,
-                      &d_ready, &d_status, &c_sum, &c_max, &c_keys})
+                      &d_ready, &d_status, &c_sum, &c_max, &c_keys, &n_left0, &n_left1, &n_both, &n_fit, &n_stat})
       b->release();
   };
   const uint32_t Gp = std::max(G, 1u), Qp = std::max(n_queue, 1u);
@@ -1591,8 +1591,17 @@ int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_r
     a.pod_count = s_pc.as<int32_t>();
     a.req_present = s_rp.as<uint32_t>();
     a.pt = pod_tab(e);
-    a.fsel = e->d_fsel.as<uint64_t>();
-    a.ftol = e->d_ftol.as<uint64_t>();
+    // compact node state the kernel builds and maintains (replay.cuh)
+    er = n_left0.ensure((size_t)L * Npad * 8);
+    if (er == cudaSuccess) er = n_left1.ensure((size_t)L * Npad * 8);
+    if (er == cudaSuccess) er = n_both.ensure((size_t)Npad * 4);
+    if (er == cudaSuccess) er = n_stat.ensure((size_t)Npad);
+    if (er == cudaSuccess && e->n_rep_classes <= (uint32_t)REPLAY_MAX_CLASSES) er = n_fit.ensure((size_t)Npad * 4);
+    a.left[0] = n_left0.as<int64_t>();
+    a.left[1] = n_left1.as<int64_t>();
+    a.both = n_both.as<uint32_t>();
+    a.nstat = n_stat.as<uint8_t>();
+    a.fitmask = e->n_rep_classes <= (uint32_t)REPLAY_MAX_CLASSES ? n_fit.as<uint32_t>() : nullptr;
     a.rsel = e->d_rsel.as<uint64_t>();
     a.rtol = e->d_rtol.as<uint64_t>();
     a.n_rep = e->n_rep_classes;
@@ -1605,10 +1614,10 @@ int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_r
         worst = std::max(worst, (long double)e->max_alloc[d] + (long double)e->max_requested[d] + (long double)e->max_req[d] +
                                     (long double)e->neg_req[d] * (long double)n_queue + (long double)e->max_pod_count + n_queue);
       const bool safe = worst * (long double)std::max(N, 1u) < 4.0e18L;
-      const uint32_t n_blocks = cdiv(N, REPLAY_THREADS);
+      const uint32_t n_blocks = cdiv(N, REPLAY_BLOCK);
       const uint32_t maxl = replay_maxl(L);
       a.cache_ok = 0;
-      if (safe && a.n_rep <= (uint32_t)REPLAY_MAX_CLASSES && n_blocks >= 2 && n_blocks <= (uint32_t)REPLAY_THREADS) {
+      if (er == cudaSuccess && safe && a.n_rep <= (uint32_t)REPLAY_MAX_CLASSES && n_blocks >= 1 && n_blocks <= (uint32_t)REPLAY_MAX_BLOCKS) {
         const size_t rows = (size_t)2 * a.n_rep * n_blocks;
         er = c_sum.ensure(rows * maxl * 8);
         if (er == cudaSuccess) er = c_max.ensure(rows * maxl * 8);

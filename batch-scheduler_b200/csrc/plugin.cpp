@@ -592,6 +592,21 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   return Status{};
 }
 
+Status BatchSchedulingPlugin::ReplayQueue(std::vector<ReplayDecision>* out) {
+  if (!out) return Status{BS_CODE_ERROR, "ReplayQueue: null output"};
+  if (!eng_) return Status{BS_CODE_ERROR, "ReplayQueue: no round has been started"};
+  const uint32_t P = packed_.n_pods;
+  std::vector<uint8_t> pf(P), rd(P);
+  std::vector<int32_t> nd(P);
+  bs_replay_result r{};
+  r.prefilter = pf.data(); r.node = nd.data(); r.ready = rd.data();
+  const int rc = bs_replay(eng_, order_.data(), P, &r);
+  if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
+  out->assign(P, ReplayDecision{});
+  for (uint32_t qi = 0; qi < P; ++qi) (*out)[order_[qi]] = ReplayDecision{pf[qi], nd[qi], rd[qi] != 0, qi};
+  return Status{};
+}
+
 Status BatchSchedulingPlugin::PreFilter(const Pod& pod) {
   auto it = pod_row_.find(pod.uid);
   if (it == pod_row_.end()) return Status{BS_CODE_ERROR, "pod is not part of the current round"};

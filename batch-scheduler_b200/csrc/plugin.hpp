@@ -149,6 +149,18 @@ class BatchSchedulingPlugin {
   // lastPermittedPod.Add(uid, 2s) (core.go:188)
   void AddPermitted(const std::string& uid, int64_t now_ns);
 
+  // The whole pending queue of the last BeginRound walked through the reference's pod-at-a-time cycle
+  // (PreFilter against live state -> first fitting node -> assume -> Permit, core.go:88-167,268-309)
+  // on the device, in the order Less defines (bs_replay).  A what-if: neither the
+  // plugin's caches nor the uploaded tables change.  out is indexed like `pending`.
+  struct ReplayDecision {
+    uint8_t prefilter = 0;    // bs_prefilter_code
+    int32_t node = -1;        // snapshot index of the node the pod was assumed onto, -1 none
+    bool ready = false;       // Permit found the gang complete with this pod (core.go:303)
+    uint32_t position = 0;    // place in the walked queue
+  };
+  Status ReplayQueue(std::vector<ReplayDecision>* out);
+
   // results of the last round, by pending index
   const PackedSnapshot& packed() const { return packed_; }
   const std::vector<uint8_t>& prefilter_codes() const { return prefilter_; }

@@ -4,23 +4,31 @@
 // PodGroup state and the live snapshot (core.go:88-167), the pod is assumed onto a node
 // (NodeInfo.AddPod debits `requested`), Permit records the match and may flip the group to
 // Scheduled (core.go:268-309).  Every step depends on the previous one, so the queue is walked by
-// ONE persistent CTA; the parallelism is inside a step:
+// ONE persistent CTA (256 threads: registers to spare, cheap barriers); the parallelism is inside
+// a step:
+//   node state         next to the reference-format columns it returns, the kernel keeps the
+//                      residuals singleNodeResource would compute (percent 1.0 and 0.7, int64,
+//                      zero for absent scalar keys), the key mask and one checkFit bit per
+//                      representative class; a step reads them with 16-byte loads, four consecutive
+//                      nodes per thread, and only the assumed node's row is rewritten;
 //   findMaxPG          the group table is cut into <= 1024 buckets whose merged states (the
 //                      order-insensitive merge of kernels.cuh) sit in shared memory; a changed group
 //                      costs one warp one bucket, the answer is one block reduction, and it is
 //                      recomputed only after some group changed;
-//   cluster check      blocks of 1024 nodes: warp-shuffle scan of singleNodeResource + running
-//                      carry, every prefix tested, block-wide OR (the reference returns true at
-//                      the first satisfying prefix == some prefix satisfies), early exit.  Past
-//                      the first block the scan is not repeated blindly: per (representative class,
+//   cluster check      blocks of 1024 nodes: serial prefix over a thread's four nodes, warp-shuffle
+//                      scan of the thread totals, running carry, every prefix tested, block-wide OR
+//                      (the reference returns true at the first satisfying prefix == some prefix
+//                      satisfies).  Blocks are not rescanned blindly: per (representative class,
 //                      percent, block) the block total, key set and per-lane maximum of the in-block
 //                      prefix are cached (one node changes per step, so one block goes stale); a
 //                      block whose carry + maximum stays below the need on a compared lane cannot
-//                      hold a satisfying prefix and is skipped, the others are scanned exactly;
-//   node choice        first node in list order where the pod fits (ballot + shared min), the
-//                      stand-in for the upstream filter/selectHost the oracle uses too.  Requests
-//                      only grow `requested`, so a leading run of nodes no pod of the table can
-//                      ever fit again (or that is skipped) is remembered and not rescanned;
+//                      hold a satisfying prefix and is skipped, the others are scanned exactly, in
+//                      order.  A stale first block is scanned exactly before anything else: where
+//                      the cluster has room the need is met there;
+//   node choice        first node in list order where the pod fits, the stand-in for the upstream
+//                      filter/selectHost the oracle uses too.  Requests only grow `requested`, so a
+//                      leading run of nodes no pod of the table can ever fit again (or that is
+//                      skipped) is remembered and not rescanned;
 //   assume + Permit    a handful of stores by the first lanes.
 // Mutable state lives in scratch copies (requested, pod_count, req_present, matched, group flags,
 // representative class, MinResources); the uploaded tables are untouched.
@@ -29,27 +37,37 @@
 
 namespace bsk {
 
-constexpr int REPLAY_THREADS = 1024;
+constexpr int REPLAY_THREADS = 256;
 constexpr int REPLAY_WARPS = REPLAY_THREADS / 32;
-constexpr int REPLAY_MAX_CLASSES = 32;   // representative classes covered by the block cache
+constexpr int REPLAY_NPT = 4;                                  // consecutive nodes per thread
+constexpr int REPLAY_BLOCK = REPLAY_THREADS * REPLAY_NPT;      // nodes per scan block
+constexpr int REPLAY_MAX_BUCKETS = 1024;                       // findMaxPG buckets
+constexpr int REPLAY_MAX_BLOCKS = REPLAY_BLOCK;                // blocks the summary cache can index
+constexpr int REPLAY_MAX_CLASSES = 32;                         // representative classes with a checkFit bit
 #ifdef BS_REPLAY_PROFILE
 #define RP_T(k) do { if (threadIdx.x == 0) { const long long _n = clock64(); rp_acc[k] += _n - rp_t; rp_t = _n; } } while (0)
 #else
 #define RP_T(k) do { } while (0)
 #endif
 
+// node status bits of the compact table
+constexpr uint32_t RN_VISITED = 1;    // in the list and not skipped (core.go:606-617)
+constexpr uint32_t RN_TAINTS_OK = 2;  // info.Taints() did not fail (:639)
+
 struct ReplayArgs {
   NodeTab nt;                 // requested / pod_count / req_present point at the SCRATCH copies
   int64_t* requested;         // [L][Npad] scratch (same memory as nt.requested)
   int32_t* pod_count;
   uint32_t* req_present;
+  int64_t* left[2];           // [L][Npad] residual at percent 1.0 / 0.7 (class-free), 0 for absent keys
+  uint32_t* both;             // [Npad] scalar keys present in allocatable AND requested (:662-666)
+  uint32_t* fitmask;          // [Npad] bit c: checkFit(class c); null when n_rep > 32
+  uint8_t* nstat;             // [Npad] RN_*
   PodTab pt;
-  const uint64_t* fsel;       // fit-class tables: the pod's own selector / tolerations
-  const uint64_t* ftol;
-  const uint64_t* rsel;       // representative-class tables
+  const uint64_t* rsel;       // representative-class tables (every pod's (sel, tol) is one of them)
   const uint64_t* rtol;
-  uint32_t n_rep;             // representative classes
-  uint32_t cache_ok;          // block cache usable: sums stay below 2^62 and the scratch exists (host)
+  uint32_t n_rep;
+  uint32_t cache_ok;          // block summaries usable: sums stay below 2^62 and the scratch exists (host)
   int64_t* blk_sum;           // [2*n_rep][n_blocks][MAXL] block totals
   int64_t* blk_max;           // [2*n_rep][n_blocks][MAXL] max in-block prefix per lane
   uint32_t* blk_keys;         // [2*n_rep][n_blocks]       scalar keys seen in the block
@@ -71,21 +89,20 @@ struct ReplayArgs {
 
 template <int MAXL>
 struct ReplaySmem {
-  MaxState bucket[REPLAY_THREADS];    // merged findMaxPG state of each bucket of groups
+  MaxState bucket[REPLAY_MAX_BUCKETS];   // merged findMaxPG state of each bucket of groups
   MaxState part[32];
-  uint32_t valid[2 * REPLAY_MAX_CLASSES][REPLAY_THREADS / 32];   // cached block summaries that are current
-  int64_t woff[REPLAY_WARPS][MAXL];   // carry + exclusive warp offsets of the current block of nodes
+  uint32_t valid[2 * REPLAY_MAX_CLASSES][REPLAY_MAX_BLOCKS / 32];   // block summaries that are current
+  uint8_t cand[REPLAY_MAX_BLOCKS];       // blocks that may hold a satisfying prefix
+  int64_t woff[REPLAY_WARPS][MAXL];      // carry + exclusive warp offsets of the current block of nodes
   int64_t wmax[REPLAY_WARPS][MAXL];
   uint32_t wkeys[REPLAY_WARPS];
-  uint32_t cand[REPLAY_WARPS];
-  int64_t carry[MAXL];                // running total of the blocks already scanned
-  int64_t base[MAXL];
-  uint32_t carry_keys, base_keys;
-  int64_t req[2][MAXL];               // getPodResourceRequire of the current / next pod
+  int64_t carry[MAXL];                   // running total in front of / after the current block
+  uint32_t carry_keys;
+  int64_t req[2][MAXL];                  // getPodResourceRequire of the current / next pod
   int64_t need[MAXL];
-  int64_t min_req[4];                 // smallest request of any pod of the table, fixed lanes
-  int32_t monotone;                   // no pod has a negative fixed-lane request: residuals only shrink
-  int32_t first[2];                   // chosen node, one slot per step parity
+  int64_t min_req[4];                    // smallest request of any pod of the table, fixed lanes
+  int32_t monotone;                      // no pod has a negative fixed-lane request: residuals only shrink
+  int32_t first[2];                      // chosen node, one slot per step parity
   int32_t max_group;
   int32_t panic;
 };
@@ -104,36 +121,46 @@ __device__ __forceinline__ bool compare_lanes(const int64_t (&left)[MAXL], uint3
   return ok;
 }
 
-// Inclusive scan of (v, keys) over the 1024 threads of the CTA (sum / OR).  use_carry adds
-// sm.carry to every result; update_carry leaves the total (carry included) in sm.carry.
-// Two barriers inside; the caller puts one more before the next call (woff is reused).
+// Inclusive scan over the 1024 items of a block, four consecutive items per thread (sum of v,
+// OR of keys).  use_carry adds sm.carry in front; update_carry leaves the total (carry included)
+// in sm.carry.  Two barriers inside; the caller puts one more before the next call.
 template <int MAXL>
-__device__ __forceinline__ void block_scan(ReplaySmem<MAXL>& sm, int64_t (&v)[MAXL], uint32_t& keys,
-                                           bool use_carry, bool update_carry) {
+__device__ __forceinline__ void block_scan(ReplaySmem<MAXL>& sm, int64_t (&v)[REPLAY_NPT][MAXL],
+                                           uint32_t (&keys)[REPLAY_NPT], bool use_carry, bool update_carry) {
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 1; k < REPLAY_NPT; ++k) {
+#pragma unroll
+    for (int d = 0; d < MAXL; ++d) v[k][d] += v[k - 1][d];
+    keys[k] |= keys[k - 1];
+  }
+  int64_t tot[MAXL];
+  uint32_t tk = keys[REPLAY_NPT - 1];
+#pragma unroll
+  for (int d = 0; d < MAXL; ++d) tot[d] = v[REPLAY_NPT - 1][d];
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
     for (int d = 0; d < MAXL; ++d) {
-      const int64_t t = __shfl_up_sync(0xffffffffu, v[d], o);
-      if ((int)lane >= o) v[d] += t;
+      const int64_t t = __shfl_up_sync(0xffffffffu, tot[d], o);
+      if ((int)lane >= o) tot[d] += t;
     }
-    const uint32_t k = __shfl_up_sync(0xffffffffu, keys, o);
-    if ((int)lane >= o) keys |= k;
+    const uint32_t k = __shfl_up_sync(0xffffffffu, tk, o);
+    if ((int)lane >= o) tk |= k;
   }
   if (lane == 31) {
 #pragma unroll
-    for (int d = 0; d < MAXL; ++d) sm.woff[wid][d] = v[d];
-    sm.wkeys[wid] = keys;
+    for (int d = 0; d < MAXL; ++d) sm.woff[wid][d] = tot[d];
+    sm.wkeys[wid] = tk;
   }
   __syncthreads();
   if (wid == 0) {
     int64_t x[MAXL];
 #pragma unroll
-    for (int d = 0; d < MAXL; ++d) x[d] = sm.woff[lane][d];
-    uint32_t xk = sm.wkeys[lane];
+    for (int d = 0; d < MAXL; ++d) x[d] = lane < REPLAY_WARPS ? sm.woff[lane][d] : 0;
+    uint32_t xk = lane < REPLAY_WARPS ? sm.wkeys[lane] : 0u;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < REPLAY_WARPS; o <<= 1) {
 #pragma unroll
       for (int d = 0; d < MAXL; ++d) {
         const int64_t t = __shfl_up_sync(0xffffffffu, x[d], o);
@@ -142,7 +169,7 @@ __device__ __forceinline__ void block_scan(ReplaySmem<MAXL>& sm, int64_t (&v)[MA
       const uint32_t k = __shfl_up_sync(0xffffffffu, xk, o);
       if ((int)lane >= o) xk |= k;
     }
-    // carry + exclusive offset of each warp, in place; lane 31 holds the total
+    // carry + exclusive offset of each warp, in place; the last warp's lane holds the total
     const uint32_t ck = use_carry ? sm.carry_keys : 0u;
     uint32_t exk = __shfl_up_sync(0xffffffffu, xk, 1);
     if (lane == 0) exk = 0;
@@ -151,21 +178,29 @@ __device__ __forceinline__ void block_scan(ReplaySmem<MAXL>& sm, int64_t (&v)[MA
       const int64_t c = use_carry ? sm.carry[d] : 0;
       int64_t ex = __shfl_up_sync(0xffffffffu, x[d], 1);
       if (lane == 0) ex = 0;
-      sm.woff[lane][d] = c + ex;
+      if (lane < REPLAY_WARPS) sm.woff[lane][d] = c + ex;
       x[d] += c;
     }
-    sm.wkeys[lane] = ck | exk;
+    if (lane < REPLAY_WARPS) sm.wkeys[lane] = ck | exk;
     __syncwarp();
-    if (update_carry && lane == 31) {
+    if (update_carry && lane == REPLAY_WARPS - 1) {
 #pragma unroll
       for (int d = 0; d < MAXL; ++d) sm.carry[d] = x[d];
       sm.carry_keys = ck | xk;
     }
   }
   __syncthreads();
+  // what lies in front of this thread: the warp offset + the lanes below
+  uint32_t fk = __shfl_up_sync(0xffffffffu, tk, 1);
+  fk = (lane ? fk : 0u) | sm.wkeys[wid];
 #pragma unroll
-  for (int d = 0; d < MAXL; ++d) v[d] += sm.woff[wid][d];
-  keys |= sm.wkeys[wid];
+  for (int d = 0; d < MAXL; ++d) {
+    const int64_t front = sm.woff[wid][d] + (tot[d] - v[REPLAY_NPT - 1][d]);
+#pragma unroll
+    for (int k = 0; k < REPLAY_NPT; ++k) v[k][d] += front;
+  }
+#pragma unroll
+  for (int k = 0; k < REPLAY_NPT; ++k) keys[k] |= fk;
 }
 
 template <int MAXL>
@@ -175,8 +210,9 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
   const uint32_t N = a.nt.N, Npad = a.nt.Npad, G = a.G, P = a.pt.P;
   const uint32_t L = a.nt.L;
   const uint32_t C = a.n_rep;
-  const uint32_t NBLK = (N + REPLAY_THREADS - 1) / REPLAY_THREADS;
-  const bool use_cache = a.cache_ok && C <= (uint32_t)REPLAY_MAX_CLASSES && NBLK >= 2 && NBLK <= (uint32_t)REPLAY_THREADS;
+  const uint32_t NBLK = (N + REPLAY_BLOCK - 1) / REPLAY_BLOCK;
+  const bool use_mask = a.fitmask != nullptr;
+  const bool use_cache = a.cache_ok && use_mask && NBLK >= 1 && NBLK <= (uint32_t)REPLAY_MAX_BLOCKS;
 
   GroupTab gt{};
   gt.min_member = a.min_member; gt.scheduled = a.scheduled; gt.matched = a.matched;
@@ -189,8 +225,36 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
   long long rp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long rp_t = clock64();
 #endif
+  // ---- compact node state: residuals at both percents (:647-668), key mask, checkFit bits ----
+  for (uint32_t i = tid; i < Npad; i += REPLAY_THREADS) {
+    uint32_t st = 0, both = 0, fm = 0;
+    if (i < N) {
+      const uint8_t f = a.nt.flags[i];
+      if (!node_skipped(f)) st |= RN_VISITED;
+      if (!(f & BS_NODE_TAINTS_ERR)) st |= RN_TAINTS_OK;
+      both = a.nt.alloc_present[i] & a.nt.req_present[i] & ~0xFu;
+      for (uint32_t d = 0; d < L; ++d) {
+        const bool present = d < 4 || ((both >> d) & 1u);
+        int64_t sub = a.nt.requested[(size_t)d * Npad + i];
+        if (d == LANE_PODS && sub == 0) sub = a.nt.pod_count[i];     // :650-653
+        const int64_t cap = a.nt.alloc[(size_t)d * Npad + i];
+        a.left[0][(size_t)d * Npad + i] = present ? scale_f32(cap, 1.0f) - sub : 0;
+        a.left[1][(size_t)d * Npad + i] = present ? scale_f32(cap, 0.7f) - sub : 0;
+      }
+      if (use_mask) {
+        const uint64_t lb = a.nt.label[i], tn = a.nt.taint[i];
+        for (uint32_t c = 0; c < C; ++c)
+          if (check_fit(lb, tn, a.rsel[c], a.rtol[c])) fm |= 1u << c;
+      }
+    } else {
+      for (uint32_t d = 0; d < L; ++d) { a.left[0][(size_t)d * Npad + i] = 0; a.left[1][(size_t)d * Npad + i] = 0; }
+    }
+    a.nstat[i] = (uint8_t)st;
+    a.both[i] = both;
+    if (use_mask) a.fitmask[i] = fm;
+  }
   // ---- findMaxPG buckets: S consecutive groups each, at most 1024 of them ----
-  const uint32_t per = (G + 32u * REPLAY_THREADS - 1) / (32u * REPLAY_THREADS);
+  const uint32_t per = (G + 32u * REPLAY_MAX_BUCKETS - 1) / (32u * REPLAY_MAX_BUCKETS);
   const uint32_t S = 32u * (per ? per : 1u);
   const uint32_t NB = (G + S - 1) / S;
   auto bucket_compute = [&](uint32_t b) {   // by one whole warp
@@ -229,10 +293,10 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
     __syncthreads();
     if (tid == 0) sm.monotone = (sm.min_req[LANE_CPU] >= 0 && sm.min_req[LANE_MEM] >= 0 && sm.min_req[LANE_EPH] >= 0) ? 1 : 0;
   }
-  for (uint32_t k = tid; k < 2u * REPLAY_MAX_CLASSES * (REPLAY_THREADS / 32); k += REPLAY_THREADS) (&sm.valid[0][0])[k] = 0;
+  for (uint32_t k = tid; k < 2u * REPLAY_MAX_CLASSES * (REPLAY_MAX_BLOCKS / 32); k += REPLAY_THREADS) (&sm.valid[0][0])[k] = 0;
 
   // pod columns of the NEXT step are fetched one step ahead (the walk is latency-bound)
-  struct PodRow { uint32_t p; int32_t g; uint8_t pf; uint32_t keys, fc, rc; };
+  struct PodRow { uint32_t p; int32_t g; uint8_t pf; uint32_t keys, rc; };
   auto load_row = [&](uint32_t qi, int slot) {
     PodRow r;
     r.p = a.queue ? a.queue[qi] : qi;
@@ -240,7 +304,6 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
     r.pf = a.pt.flags[r.p];
     const uint32_t ppres = a.pt.req_present[r.p];
     r.keys = ppres & ~0xFu;
-    r.fc = a.pt.fit_class[r.p];
     r.rc = a.pt.rep_class[r.p];
     if (tid < L)   // getPodResourceRequire (core.go:761-772): the packer summed the containers
       sm.req[slot][tid] = (tid < 4 || ((ppres >> tid) & 1u)) ? a.pt.req[(size_t)tid * P + r.p] : 0;
@@ -255,6 +318,50 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
   const bool monotone = sm.monotone != 0;
   uint32_t lo = 0;   // uniform: nodes before `lo` can never host a pod of this table again
   RP_T(7);
+
+  // The four consecutive nodes base + 4*tid .. of a block: residual lanes at percent index pi
+  // (class-free), key masks, and per node (bit k): visited, Taints() ok, checkFit of class rc.
+  auto load_quad = [&](uint32_t base, int pi, uint32_t rc, uint64_t sel, uint64_t tol, int64_t (&v)[REPLAY_NPT][MAXL],
+                       uint32_t (&keys)[REPLAY_NPT], uint32_t& vis, uint32_t& tok, uint32_t& fit) {
+    const uint32_t i0 = base + REPLAY_NPT * tid;
+    vis = 0; tok = 0; fit = 0;
+    if (i0 < Npad) {
+      const uint32_t st4 = *reinterpret_cast<const uint32_t*>(a.nstat + i0);
+      const uint4 k4 = *reinterpret_cast<const uint4*>(a.both + i0);
+      keys[0] = k4.x; keys[1] = k4.y; keys[2] = k4.z; keys[3] = k4.w;
+#pragma unroll
+      for (int d = 0; d < MAXL; ++d) {
+        if ((uint32_t)d < L) {
+          const longlong2* src = reinterpret_cast<const longlong2*>(a.left[pi] + (size_t)d * Npad + i0);
+          const longlong2 x = src[0], y = src[1];
+          v[0][d] = x.x; v[1][d] = x.y; v[2][d] = y.x; v[3][d] = y.y;
+        } else {
+          v[0][d] = 0; v[1][d] = 0; v[2][d] = 0; v[3][d] = 0;
+        }
+      }
+      if (use_mask) {
+        const uint4 f4 = *reinterpret_cast<const uint4*>(a.fitmask + i0);
+        fit = ((f4.x >> rc) & 1u) | (((f4.y >> rc) & 1u) << 1) | (((f4.z >> rc) & 1u) << 2) | (((f4.w >> rc) & 1u) << 3);
+      } else {
+#pragma unroll
+        for (int k = 0; k < REPLAY_NPT; ++k)
+          if (i0 + k < N && check_fit(a.nt.label[i0 + k], a.nt.taint[i0 + k], sel, tol)) fit |= 1u << k;
+      }
+#pragma unroll
+      for (int k = 0; k < REPLAY_NPT; ++k) {
+        const uint32_t s = (st4 >> (8 * k)) & 0xffu;
+        if (s & RN_VISITED) vis |= 1u << k;
+        if (s & RN_TAINTS_OK) tok |= 1u << k;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < REPLAY_NPT; ++k) {
+        keys[k] = 0;
+#pragma unroll
+        for (int d = 0; d < MAXL; ++d) v[k][d] = 0;
+      }
+    }
+  };
 
   for (uint32_t qi = 0; qi < a.n_queue; ++qi) {
     const PodRow cur = nx;
@@ -298,19 +405,21 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
       // findMaxPG :120 (re-reduced only when some group changed)
       if (max_dirty) {
         __syncthreads();   // bucket states written by the updating warp are visible
-        MaxState v = max_state_block_reduce(tid < NB ? sm.bucket[tid] : max_state_empty(), sm.part);
+        MaxState mv = max_state_empty();
+        for (uint32_t b = tid; b < NB; b += REPLAY_THREADS) mv = max_state_merge(mv, sm.bucket[b]);
+        mv = max_state_block_reduce(mv, sm.part);
         if (tid == 0) {
           int32_t w = -1;
-          if (v.any) {
-            uint32_t winner = v.c0;
-            if (v.c0_flags & 1u) {
-              if (v.zgood != 0xffffffffu) winner = v.zgood;
-              else if (v.zlast != 0) winner = v.zlast - 1;
+          if (mv.any) {
+            uint32_t winner = mv.c0;
+            if (mv.c0_flags & 1u) {
+              if (mv.zgood != 0xffffffffu) winner = mv.zgood;
+              else if (mv.zlast != 0) winner = mv.zlast - 1;
             }
             w = (int32_t)winner;
           }
           sm.max_group = w;
-          sm.panic = (int32_t)v.panic;
+          sm.panic = (int32_t)mv.panic;
         }
         __syncthreads();
         max_group = sm.max_group;
@@ -340,54 +449,56 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
         sm.need[tid] = val;
       }
       const uint32_t rc = a.grc[gi];
-      const uint32_t ci = rc * 2u + (case_a ? 0u : 1u);
-      const float pct = case_a ? 1.0f : 0.7f;
+      const int pi = case_a ? 0 : 1;
+      const uint32_t ci = rc * 2u + (uint32_t)pi;
       const uint64_t sel = a.rsel[rc], tol = a.rtol[rc];
       __syncthreads();
 
-      // singleNodeResource of this thread's node of the block (:619), zeros when not visited (:606-617)
-      auto node_terms = [&](uint32_t base, int64_t (&v)[MAXL], uint32_t& keys) -> bool {
-        const uint32_t i = base + tid;
+      // singleNodeResource of this thread's four nodes (:619): zeros when unfit (:639-645) or skipped
+      auto node_terms = [&](uint32_t base, int64_t (&v)[REPLAY_NPT][MAXL], uint32_t (&keys)[REPLAY_NPT]) -> uint32_t {
+        uint32_t vis, tok, fit;
+        load_quad(base, pi, rc, sel, tol, v, keys, vis, tok, fit);
+        const uint32_t act = vis & tok & fit;
 #pragma unroll
-        for (int d = 0; d < MAXL; ++d) v[d] = 0;
-        keys = 0;
-        if (i < N && !node_skipped(a.nt.flags[i])) {
-          keys = single_node_resource<MAXL>(a.nt, i, sel, tol, pct, v);
-          return true;
-        }
-        return false;
+        for (int k = 0; k < REPLAY_NPT; ++k)
+          if (!((act >> k) & 1u)) {
+            keys[k] = 0;
+#pragma unroll
+            for (int d = 0; d < MAXL; ++d) v[k][d] = 0;
+          }
+        return vis;
       };
       // every prefix ending in the block against the need (:621-627); ends with a barrier
       auto exact_block = [&](uint32_t base, bool use_carry, bool update_carry) -> bool {
-        int64_t v[MAXL];
-        uint32_t keys;
-        const bool visited = node_terms(base, v, keys);
+        int64_t v[REPLAY_NPT][MAXL];
+        uint32_t keys[REPLAY_NPT];
+        const uint32_t vis = node_terms(base, v, keys);
         block_scan<MAXL>(sm, v, keys, use_carry, update_carry);
-        const bool ok = visited && compare_lanes<MAXL>(v, keys, sm.need, need_keys);
+        bool ok = false;
+#pragma unroll
+        for (int k = 0; k < REPLAY_NPT; ++k)
+          ok |= ((vis >> k) & 1u) && compare_lanes<MAXL>(v[k], keys[k], sm.need, need_keys);
         return __syncthreads_or(ok ? 1 : 0) != 0;
       };
 
       // compareClusterResourceAndRequire :595-632 — true iff some visited prefix satisfies the need
       bool enough = false;
-      if (N) enough = exact_block(0, false, true);
-      if (!enough && NBLK > 1) {
-        if (!use_cache) {
-          for (uint32_t base = REPLAY_THREADS; base < N && !enough; base += REPLAY_THREADS)
-            enough = exact_block(base, true, true);
-        } else {
-          // the running total after block 0 is the base of everything that follows
-          if (tid < MAXL) sm.base[tid] = sm.carry[tid];
-          if (tid == 0) sm.base_keys = sm.carry_keys;
+      if (!use_cache) {
+        for (uint32_t base = 0; base < N && !enough; base += REPLAY_BLOCK) enough = exact_block(base, base != 0, true);
+      } else {
+        const bool b0_cached = (sm.valid[ci][0] & 1u) != 0;
+        if (!b0_cached) enough = exact_block(0, false, false);
+        if (!enough) {
           // refresh the stale block summaries of this (class, percent)
-          for (uint32_t j = 1; j < NBLK; ++j) {
+          for (uint32_t j = 0; j < NBLK; ++j) {
             if ((sm.valid[ci][j >> 5] >> (j & 31)) & 1u) continue;
-            int64_t v[MAXL];
-            uint32_t keys;
-            node_terms(j * REPLAY_THREADS, v, keys);
+            int64_t v[REPLAY_NPT][MAXL];
+            uint32_t keys[REPLAY_NPT];
+            node_terms(j * REPLAY_BLOCK, v, keys);
             block_scan<MAXL>(sm, v, keys, false, true);   // in-block prefixes; sm.carry = block total
 #pragma unroll
             for (int d = 0; d < MAXL; ++d) {
-              int64_t mx = v[d];
+              int64_t mx = max(max(v[0][d], v[1][d]), max(v[2][d], v[3][d]));
 #pragma unroll
               for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
               if (lane == 0) sm.wmax[wid][d] = mx;
@@ -406,55 +517,69 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
             }
             __syncthreads();
           }
-          __syncthreads();   // sm.base is written; summaries are visible
-          // carry in front of each block: exclusive scan of (base, totals of blocks 1..)
-          int64_t own[MAXL], ex[MAXL];
-          uint32_t own_keys = 0, ex_keys;
-          const bool is_blk = tid >= 1 && tid < NBLK;
+          // carry in front of each block: exclusive scan of the block totals, four blocks per thread
+          int64_t own[REPLAY_NPT][MAXL], ex[REPLAY_NPT][MAXL];
+          uint32_t own_keys[REPLAY_NPT], ex_keys[REPLAY_NPT];
 #pragma unroll
-          for (int d = 0; d < MAXL; ++d)
-            own[d] = tid == 0 ? sm.base[d] : (is_blk ? a.blk_sum[((size_t)ci * NBLK + tid) * MAXL + d] : 0);
-          own_keys = tid == 0 ? sm.base_keys : (is_blk ? a.blk_keys[(size_t)ci * NBLK + tid] : 0u);
+          for (int k = 0; k < REPLAY_NPT; ++k) {
+            const uint32_t j = REPLAY_NPT * tid + k;
+#pragma unroll
+            for (int d = 0; d < MAXL; ++d) own[k][d] = j < NBLK ? a.blk_sum[((size_t)ci * NBLK + j) * MAXL + d] : 0;
+            own_keys[k] = j < NBLK ? a.blk_keys[(size_t)ci * NBLK + j] : 0u;
+          }
           {
-            int64_t v[MAXL];
-            uint32_t keys = own_keys;
+            int64_t v[REPLAY_NPT][MAXL];
+            uint32_t keys[REPLAY_NPT];
 #pragma unroll
-            for (int d = 0; d < MAXL; ++d) v[d] = own[d];
+            for (int k = 0; k < REPLAY_NPT; ++k) {
+              keys[k] = own_keys[k];
+#pragma unroll
+              for (int d = 0; d < MAXL; ++d) v[k][d] = own[k][d];
+            }
             block_scan<MAXL>(sm, v, keys, false, false);
+            // keys in front of item k: inclusive keys of item k-1 (of the lane below for k = 0)
+            const uint32_t up = __shfl_up_sync(0xffffffffu, keys[REPLAY_NPT - 1], 1);
+            const uint32_t front0 = (lane ? up : 0u) | sm.wkeys[wid];
 #pragma unroll
-            for (int d = 0; d < MAXL; ++d) ex[d] = v[d] - own[d];
-            const uint32_t up = __shfl_up_sync(0xffffffffu, keys, 1);
-            ex_keys = sm.wkeys[wid] | (lane ? up : 0u);
-          }
-          // can a prefix inside block `tid` satisfy the need at all?
-          bool possible = is_blk;
-          if (is_blk) {
-            const uint32_t reach = ex_keys | own_keys;
+            for (int k = 0; k < REPLAY_NPT; ++k) {
+              ex_keys[k] = k == 0 ? front0 : keys[k - 1];
 #pragma unroll
-            for (int d = 0; d < MAXL; ++d) {
-              if ((uint32_t)d >= L) continue;
-              const int64_t top = ex[d] + a.blk_max[((size_t)ci * NBLK + tid) * MAXL + d];
-              const int64_t nd = sm.need[d];
-              if (d < 4) possible &= top >= nd;
-              else if (((need_keys >> d) & 1u) && nd > 0) possible &= ((reach >> d) & 1u) && top >= nd;
+              for (int d = 0; d < MAXL; ++d) ex[k][d] = v[k][d] - own[k][d];
             }
           }
-          const uint32_t bal = __ballot_sync(0xffffffffu, possible);
-          if (lane == 0) sm.cand[wid] = bal;
-          __syncthreads();
-          for (uint32_t w = 0; w < (NBLK + 31) / 32 && !enough; ++w) {
-            uint32_t word = sm.cand[w];
-            while (word && !enough) {
-              const uint32_t j = w * 32 + (uint32_t)(__ffs(word) - 1);
-              word &= word - 1;
-              if (tid == j) {
+          // can a prefix inside the block satisfy the need at all?
 #pragma unroll
-                for (int d = 0; d < MAXL; ++d) sm.carry[d] = ex[d];
-                sm.carry_keys = ex_keys;
+          for (int k = 0; k < REPLAY_NPT; ++k) {
+            const uint32_t j = REPLAY_NPT * tid + k;
+            if (j >= NBLK) continue;
+            bool possible = j > 0 || b0_cached;   // a stale block 0 was just scanned exactly
+            if (possible) {
+              const uint32_t reach = ex_keys[k] | own_keys[k];
+#pragma unroll
+              for (int d = 0; d < MAXL; ++d) {
+                if ((uint32_t)d >= L) continue;
+                const int64_t top = ex[k][d] + a.blk_max[((size_t)ci * NBLK + j) * MAXL + d];
+                const int64_t nd = sm.need[d];
+                if (d < 4) possible &= top >= nd;
+                else if (((need_keys >> d) & 1u) && nd > 0) possible &= ((reach >> d) & 1u) && top >= nd;
               }
-              __syncthreads();
-              enough = exact_block(j * REPLAY_THREADS, true, false);
             }
+            sm.cand[j] = possible ? 1 : 0;
+          }
+          __syncthreads();
+          for (uint32_t j = 0; j < NBLK && !enough; ++j) {
+            if (!sm.cand[j]) continue;
+            if (tid == j / REPLAY_NPT) {
+#pragma unroll
+              for (int k = 0; k < REPLAY_NPT; ++k)
+                if ((int)(j % REPLAY_NPT) == k) {
+#pragma unroll
+                  for (int d = 0; d < MAXL; ++d) sm.carry[d] = ex[k][d];
+                  sm.carry_keys = ex_keys[k];
+                }
+            }
+            __syncthreads();
+            enough = exact_block(j * REPLAY_BLOCK, true, false);
           }
         }
       }
@@ -471,41 +596,66 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
     uint8_t rdy = 0;
     if (code == BS_PF_PASS) {
       // ---- node choice: first node (list order) where the pod fits, A5 at percent 1.0 ----
-      const uint64_t sel = a.fsel[cur.fc], tol = a.ftol[cur.fc];
-      for (uint32_t base = lo; base < N; base += REPLAY_THREADS) {
-        const uint32_t i = base + tid;
-        bool fit = false, dead = true;
-        if (i < N) {
-          const uint8_t f = a.nt.flags[i];
-          if (!node_skipped(f) && !(f & BS_NODE_TAINTS_ERR)) {
-            int64_t v[MAXL];
-            const uint32_t keys = single_node_resource<MAXL>(a.nt, i, 0ull, ~0ull, 1.0f, v);   // class-free residual
-            dead = (v[LANE_CPU] < sm.min_req[LANE_CPU]) | (v[LANE_MEM] < sm.min_req[LANE_MEM]) |
-                   (v[LANE_EPH] < sm.min_req[LANE_EPH]) | (v[LANE_PODS] < sm.min_req[LANE_PODS]);
-            fit = check_fit(a.nt.label[i], a.nt.taint[i], sel, tol) && compare_lanes<MAXL>(v, keys, req, req_keys);
-          }
+      const uint32_t rc = cur.rc;   // the pod's own (selector, tolerations) class
+      const uint64_t sel = a.rsel[rc], tol = a.rtol[rc];
+      for (uint32_t base = lo; base < N; base += REPLAY_BLOCK) {
+        int64_t v[REPLAY_NPT][MAXL];
+        uint32_t keys[REPLAY_NPT], vis, tok, cf;
+        load_quad(base, 0, rc, sel, tol, v, keys, vis, tok, cf);
+        const uint32_t usable = vis & tok;
+        uint32_t fit = 0, dead = 0;
+#pragma unroll
+        for (int k = 0; k < REPLAY_NPT; ++k) {
+          const bool d0 = !((usable >> k) & 1u) | (v[k][LANE_CPU] < sm.min_req[LANE_CPU]) | (v[k][LANE_MEM] < sm.min_req[LANE_MEM]) |
+                          (v[k][LANE_EPH] < sm.min_req[LANE_EPH]) | (v[k][LANE_PODS] < sm.min_req[LANE_PODS]);
+          if (d0) dead |= 1u << k;
+          if (((usable & cf) >> k) & 1u)
+            if (compare_lanes<MAXL>(v[k], keys[k], req, req_keys)) fit |= 1u << k;
         }
         if (__syncthreads_or(fit ? 1 : 0)) {
-          const uint32_t b = __ballot_sync(0xffffffffu, fit);
-          if (b && lane == 0) atomicMin(&sm.first[par], (int32_t)(base + wid * 32 + (__ffs(b) - 1)));
+          const uint32_t b = __ballot_sync(0xffffffffu, fit != 0);
+          if (b && lane == (uint32_t)(__ffs(b) - 1))
+            atomicMin(&sm.first[par], (int32_t)(base + REPLAY_NPT * tid + (uint32_t)(__ffs(fit) - 1)));
           __syncthreads();
           chosen = sm.first[par];
           break;
         }
         if (monotone && base == lo) {
-          if (__syncthreads_and(dead ? 1 : 0)) lo = base + REPLAY_THREADS;
+          if (__syncthreads_and(dead == (1u << REPLAY_NPT) - 1u ? 1 : 0)) lo = base + REPLAY_BLOCK;
         }
       }
       RP_T(5);
       if (chosen >= 0) {
-        // assume: NodeInfo.AddPod adds the pod's request to `requested` (pods lane: the pod list grows)
-        if (tid < L && tid != LANE_PODS && (tid < 4 || ((req_keys >> tid) & 1u)))
-          a.requested[(size_t)tid * Npad + chosen] += req[tid];
-        if (tid < 2u * REPLAY_MAX_CLASSES)   // the node's block summaries are stale for every class
-          sm.valid[tid][(uint32_t)chosen / REPLAY_THREADS >> 5] &= ~(1u << (((uint32_t)chosen / REPLAY_THREADS) & 31));
+        // assume: NodeInfo.AddPod adds the pod's request to `requested` (pods lane: the pod list
+        // grows); the node's residual rows follow
+        const uint32_t n = (uint32_t)chosen;
+        if (tid < L) {
+          const uint32_t d = tid;
+          int64_t rq = a.requested[(size_t)d * Npad + n];
+          if (d != LANE_PODS && (d < 4 || ((req_keys >> d) & 1u))) {
+            rq += req[d];
+            a.requested[(size_t)d * Npad + n] = rq;
+          }
+          int64_t sub = rq;
+          if (d == LANE_PODS) {
+            const int32_t pc = a.pod_count[n] + 1;
+            a.pod_count[n] = pc;
+            if (rq == 0) sub = pc;                                   // :650-653
+          }
+          const uint32_t keys_now = a.nt.alloc_present[n] & (a.req_present[n] | req_keys) & ~0xFu;
+          const bool present = d < 4 || ((keys_now >> d) & 1u);
+          const int64_t cap = a.nt.alloc[(size_t)d * Npad + n];
+          a.left[0][(size_t)d * Npad + n] = present ? scale_f32(cap, 1.0f) - sub : 0;
+          a.left[1][(size_t)d * Npad + n] = present ? scale_f32(cap, 0.7f) - sub : 0;
+        }
+        if (tid >= 32 && tid < 32 + 2u * REPLAY_MAX_CLASSES)   // the node's block summaries are stale for every class
+          sm.valid[tid - 32][(n / REPLAY_BLOCK) >> 5] &= ~(1u << ((n / REPLAY_BLOCK) & 31));
+        if (tid == 32) {
+          const uint32_t rp = a.req_present[n] | req_keys;
+          a.req_present[n] = rp;
+          a.both[n] = a.nt.alloc_present[n] & rp & ~0xFu;
+        }
         if (tid == 0) {
-          a.req_present[chosen] |= req_keys;
-          a.pod_count[chosen] += 1;
           // ---- Permit (core.go:268-309) ----
           if (g < 0 || (uint32_t)g >= G) {
             rdy = 1;

@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; marks the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-replay", action="store_true", help="skip the multi-round admission leg")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: admit-bitmap all-gather by the engine's peer-memory kernel (default) or by NCCL")
     args = ap.parse_args()
@@ -343,6 +344,36 @@ def main():
                          "ALU-bound, no HBM roofline applies (tables are L2-resident)"}
         eng2.close()
 
+    # ---- multi-round admission: the whole queue through bs_replay, once ----
+    replay = None
+    if world == 1 and not args.no_replay:
+        order = eng.evaluate().order.copy()
+        eng.replay(order, after_state=False)            # warm-up (allocations, first touch)
+        eng.set_profiling(True)
+        t0 = time.perf_counter()
+        out = eng.replay(order, after_state=False)
+        wall = time.perf_counter() - t0
+        rms = eng.kernel_ms()["replay"][0]
+        eng.set_profiling(False)
+        replay = {"pods": int(P), "ms": wall * 1e3, "kernel_ms": rms, "pods_per_s": P / wall,
+                  "assumed": int((out["node"] >= 0).sum()), "gangs_ready": int(out["ready"].sum()),
+                  "what": "bs_replay: every pod of the queue (device sort order) through PreFilter -> first fitting node "
+                          "-> assume -> Permit against mutable state, one persistent CTA; host queue in, verdicts out"}
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import oracle
+            sub = S.config(WORKLOAD_CFG, scale=min(args.scale, 0.3))
+            engs = pkg.Engine(L, local_rank, fit_bitmap=False, score=False)
+            engs.upload(sub)
+            so = engs.evaluate().order.copy()
+            engs.replay(so, after_state=False)
+            t0 = time.perf_counter(); g = engs.replay(so, after_state=False); tg = time.perf_counter() - t0
+            engs.close()
+            t0 = time.perf_counter(); pf, node, rdy, _ = oracle.replay(sub, so); tc = time.perf_counter() - t0
+            same = bool((pf == g["prefilter"]).all() and (node == g["node"]).all() and (rdy == g["ready"]).all())
+            replay["cpu_port_sample"] = {"pods": int(sub.pods.n), "nodes": int(sub.nodes.n), "cpu_ms": tc * 1e3,
+                                         "gpu_ms": tg * 1e3, "identical": same, "cores": 1,
+                                         "what": "oracle bso_replay (sequential by nature) on the same reduced snapshot"}
+
     # ---- e2e leg: host tables -> C ABI -> host decisions, every step ------------------------
     res = None
     for _ in range(2):
@@ -408,6 +439,7 @@ def main():
             "gpu_launches": int(launches),
             "kernel_ms": kavg,
             "decisions_only": fused,
+            "replay": replay,
             "roofline": {"bound": "hbm", "kernel": "gang_fit_kernel<LW=2,LN=3> (2 int64 + 3 int32 lanes)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": peak_src, "alg_bytes_per_launch": int(alg), "kernel_ms": fit_ms},

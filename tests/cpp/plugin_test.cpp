@@ -3,6 +3,7 @@
 //   quantity <s>...   : Quantity.Value / MilliValue of each argument             (CPU)
 //   pack_core_test    : core_test.go:27-115 objects -> packed tables             (CPU)
 //   readme            : README.md:76-188 resource race, pod by pod, on the GPU
+//   readme_replay     : the same race in one call (all pods pending, the device walks the queue)
 //   bench_pack N P G  : packer throughput on synthetic objects                   (CPU)
 #include <chrono>
 #include <cstdio>
@@ -142,6 +143,35 @@ static int cmd_readme() {
   return 0;
 }
 
+static int cmd_readme_replay() {
+  // the same race in ONE call: all ten pods pending, the device walks the queue (bs_replay)
+  Node node; node.name = "node1";
+  node.allocatable = {{"cpu", "8"}, {"memory", "16Gi"}, {"ephemeral-storage", "100Gi"}, {"pods", "110"}};
+  NodeInfo info; info.node = &node; info.num_pods = 4;
+  info.requested = {{"cpu", "900m"}, {"memory", "140Mi"}};
+  BatchSchedulingPlugin plugin(0, 0);
+  for (int g = 1; g <= 2; ++g) {
+    PodGroup pg; pg.ns = "default"; pg.name = "group" + std::to_string(g); pg.min_member = 5;
+    pg.creation_ns = 1600000000ll * 1000000000ll;
+    plugin.SetPodGroup(pg);
+  }
+  std::vector<Pod> pods;
+  for (int i = 0; i < 5; ++i) { pods.push_back(readme_pod(1, i)); pods.push_back(readme_pod(2, i)); }
+  std::vector<const Pod*> pending;
+  for (auto& p : pods) pending.push_back(&p);
+  Status st = plugin.BeginRound({&info}, pending, 1000000000ll);
+  if (!st.ok()) { fprintf(stderr, "round failed: %s\n", st.message.c_str()); return 1; }
+  std::vector<BatchSchedulingPlugin::ReplayDecision> dec;
+  st = plugin.ReplayQueue(&dec);
+  if (!st.ok()) { fprintf(stderr, "replay failed: %s\n", st.message.c_str()); return 1; }
+  printf("[\n");
+  for (size_t i = 0; i < pods.size(); ++i)
+    printf("%s{\"pod\": \"%s\", \"prefilter_code\": %d, \"node\": %d, \"ready\": %d, \"position\": %u}\n", i ? "," : "",
+           pods[i].name.c_str(), (int)dec[i].prefilter, dec[i].node, dec[i].ready ? 1 : 0, dec[i].position);
+  printf("]\n");
+  return 0;
+}
+
 static int cmd_bench_pack(int N, int P, int G) {
   std::vector<Node> nodes(N);
   std::vector<NodeInfo> infos(N);
@@ -197,6 +227,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "quantity")) return cmd_quantity(argc, argv);
   if (!strcmp(argv[1], "pack_core_test")) return cmd_pack_core_test();
   if (!strcmp(argv[1], "readme")) return cmd_readme();
+  if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
   return 2;
 }

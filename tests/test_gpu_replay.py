@@ -131,6 +131,23 @@ def test_queue_from_the_engine_order(pkg, oracle, snapshot_mod):
     assert (got["ready"] == 1).any()
 
 
+def test_baseline_cfg4_third_scale(pkg, oracle, snapshot_mod):
+    # 30k pods / 3k nodes / 15k groups (three scan blocks, 18 classes): the oracle needs ~3 s
+    snap = snapshot_mod.config(4, scale=0.3)
+    eng = pkg.Engine(snap.lanes, fit_bitmap=False, score=False)
+    eng.upload(snap)
+    order = eng.evaluate().order.copy()
+    eng.close()
+    got, _ = replay_both(pkg, oracle, snap, order)
+    assert (got["prefilter"] == snapshot_mod.PF_NOT_ENOUGH).sum() > 1000 and got["ready"].sum() > 1000
+
+
+def test_nine_lane_config(pkg, oracle, snapshot_mod):
+    # BASELINE configs[4] shape (9 lanes: the MAXL = 9 instantiation) at a size the oracle walks in seconds
+    snap = snapshot_mod.config(5, scale=0.012)
+    replay_both(pkg, oracle, snap)
+
+
 def test_repeated_and_empty_queue(pkg, oracle):
     snap = random_snapshot(5, P=50, N=40, G=8, L=5, case="mixed")
     replay_both(pkg, oracle, snap, np.array([3, 3, 7, 3, 0, 49, 49], np.uint32))

@@ -85,6 +85,21 @@ def test_readme_race_through_cpp_plugin(plugin_bin, snapshot_mod):
         assert r["message"] == "pod with pgName: default/group2 last failed in 20s, deny"
 
 
+@pytest.mark.gpu
+def test_readme_race_in_one_call(plugin_bin, snapshot_mod):
+    # all ten pods pending at once; ReplayQueue walks them in Less order on the device: equal priority
+    # and creation time -> the group with the greater name goes first (core.go:404) and wins the race
+    S = snapshot_mod
+    rows = _run(plugin_bin, "readme_replay")
+    g1 = sorted((r for r in rows if "race1" in r["pod"]), key=lambda r: r["position"])
+    g2 = sorted((r for r in rows if "race2" in r["pod"]), key=lambda r: r["position"])
+    assert max(r["position"] for r in g2) < min(r["position"] for r in g1)
+    assert all(r["prefilter_code"] == S.PF_PASS and r["node"] == 0 for r in g2)
+    assert [r["ready"] for r in g2] == [0, 0, 0, 0, 1]
+    assert g1[0]["prefilter_code"] == S.PF_NOT_ENOUGH and all(r["prefilter_code"] == S.PF_DENIED for r in g1[1:])
+    assert all(r["node"] == -1 and r["ready"] == 0 for r in g1)
+
+
 def test_quantity_parsing_randomised(plugin_bin):
     """resource.Quantity semantics against an exact rational model: Value() and MilliValue() are the
     ceilings (away from zero for negatives) of the parsed number and of 1000x it."""
