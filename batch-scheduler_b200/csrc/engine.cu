@@ -239,6 +239,10 @@ struct bs_engine {
       h_order, h_rank, h_state, h_filter_code;
   bool fetched = false;
 
+  // bs_replay scratch (kept between calls: cudaMalloc/cudaFree per call would dominate small queues)
+  DevBuf r_req, r_pc, r_rp, r_matched, r_gflags, r_grc, r_minres, r_mrp, r_queue, r_pf, r_node, r_ready, r_status,
+      r_sum, r_max, r_keys, r_left0, r_left1, r_both, r_fit, r_stat;
+
   // peer exchange (admit bitmap all-gather over NVLink peer memory)
   DevBuf d_gather, d_peer_err;
   uint32_t peer_rank = 0, peer_world = 0, peer_wpr = 0, peer_seq = 0;
@@ -267,16 +271,6 @@ namespace {
 int fail(bs_engine* e, int code, const char* msg) {
   e->err = msg;
   return code;
-}
-
-bool in_range(const int64_t* a, size_t n) {
-  const int64_t lim = BS_VALUE_LIMIT;
-  int64_t lo = 0, hi = 0;
-  for (size_t i = 0; i < n; ++i) {
-    lo = std::min(lo, a[i]);
-    hi = std::max(hi, a[i]);
-  }
-  return lo >= -lim && hi <= lim;
 }
 
 // per-lane max |value| of a [L][n] table; false if any value is outside +-BS_VALUE_LIMIT
@@ -1046,7 +1040,10 @@ void bs_destroy(bs_engine* e) {
                     &e->d_prefilter, &e->d_feasible, &e->d_best_node, &e->d_best_score, &e->d_admit,
                     &e->d_admit_bitmap, &e->d_new_denied, &e->d_fit_bitmap, &e->d_score, &e->d_order,
                     &e->d_rank, &e->d_gk0, &e->d_gk1, &e->d_pk0, &e->d_pk1, &e->d_idx_a, &e->d_idx_b,
-                    &e->d_ghist, &e->d_skip, &e->d_group_rank, &e->d_gorder, &e->d_tilecnt, &e->d_sort_barrier};
+                    &e->d_ghist, &e->d_skip, &e->d_group_rank, &e->d_gorder, &e->d_tilecnt, &e->d_sort_barrier,
+                    &e->r_req, &e->r_pc, &e->r_rp, &e->r_matched, &e->r_gflags, &e->r_grc, &e->r_minres, &e->r_mrp,
+                    &e->r_queue, &e->r_pf, &e->r_node, &e->r_ready, &e->r_status, &e->r_sum, &e->r_max, &e->r_keys,
+                    &e->r_left0, &e->r_left1, &e->r_both, &e->r_fit, &e->r_stat};
   for (DevBuf* b : bufs) b->release();
   PinBuf* pins[] = {&e->h_prefilter, &e->h_feasible, &e->h_best_node, &e->h_best_score, &e->h_admit,
                     &e->h_admit_bitmap, &e->h_new_denied, &e->h_order, &e->h_rank, &e->h_state, &e->h_filter_code};
@@ -1551,13 +1548,11 @@ int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_r
   if (e->classes_dirty && (rc = rebuild_classes(e))) return rc;
 
   // scratch copies of everything the cycle mutates
-  DevBuf s_req, s_pc, s_rp, s_matched, s_gflags, s_grc, s_minres, s_mrp, d_queue, d_pf, d_node, d_ready, d_status,
-      c_sum, c_max, c_keys, n_left0, n_left1, n_both, n_fit, n_stat;
-  auto release_all = [&]() {
-    for (DevBuf* b : {&s_req, &s_pc, &s_rp, &s_matched, &s_gflags, &s_grc, &s_minres, &s_mrp, &d_queue, &d_pf, &d_node,
-                      &d_ready, &d_status, &c_sum, &c_max, &c_keys, &n_left0, &n_left1, &n_both, &n_fit, &n_stat})
-      b->release();
-  };
+  DevBuf &s_req = e->r_req, &s_pc = e->r_pc, &s_rp = e->r_rp, &s_matched = e->r_matched, &s_gflags = e->r_gflags,
+         &s_grc = e->r_grc, &s_minres = e->r_minres, &s_mrp = e->r_mrp, &d_queue = e->r_queue, &d_pf = e->r_pf,
+         &d_node = e->r_node, &d_ready = e->r_ready, &d_status = e->r_status, &c_sum = e->r_sum, &c_max = e->r_max,
+         &c_keys = e->r_keys, &n_left0 = e->r_left0, &n_left1 = e->r_left1, &n_both = e->r_both, &n_fit = e->r_fit,
+         &n_stat = e->r_stat;
   const uint32_t Gp = std::max(G, 1u), Qp = std::max(n_queue, 1u);
   cudaError_t er = s_req.ensure((size_t)L * Npad * 8);
   auto dup = [&](DevBuf& dst, const DevBuf& src, size_t bytes) {
@@ -1676,7 +1671,6 @@ int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_r
     d2h(grc.data(), s_grc, (size_t)G * 4);
   }
   if (er == cudaSuccess) er = cudaStreamSynchronize(e->s);
-  release_all();
   CK(er);
   (void)Gp;
 #ifdef BS_REPLAY_PROFILE

@@ -85,3 +85,49 @@ def test_cfg5_shard_properties(pkg, oracle, snapshot_mod):
     np.testing.assert_array_equal(eng.score_rows(500, 200), o2.score)
     np.testing.assert_array_equal(res.feasible_count[500:700], o2.feasible_count)
     eng.close()
+
+
+def test_replay_full_size_conservation(pkg, snapshot_mod):
+    """bs_replay on BASELINE configs[3] at full size (100k pods in device-sort order): properties that
+    hold for any correct walk — every debit is accounted for, a pod is only assumed after passing
+    PreFilter, gangs are flagged exactly when Permit's uint32 compare says so, refused groups freeze."""
+    S = snapshot_mod
+    snap = S.config(4)
+    P, N, G, L = snap.pods.n, snap.nodes.n, snap.groups.n, snap.lanes
+    eng = pkg.Engine(L, 0, fit_bitmap=False, score=False)
+    eng.upload(snap)
+    order = eng.evaluate().order.copy()
+    out = eng.replay(order)
+    eng.close()
+    pf, node, ready = out["prefilter"], out["node"], out["ready"]
+    pods = order
+    placed = node >= 0
+    assert (pf[placed] == S.PF_PASS).all() and placed.sum() > 10000
+    # requested grew by exactly the requests of the pods assumed onto each node (pods lane: pod list)
+    for d in range(L):
+        if d == 3:
+            continue
+        add = np.zeros(N, np.int64)
+        use = placed & ((d < 4) | (((snap.pods.req_present[pods] >> np.uint32(d)) & 1) == 1))
+        np.add.at(add, node[use], snap.pods.req[d, pods[use]])
+        np.testing.assert_array_equal(out["node_requested"][d], snap.nodes.requested[d] + add)
+    np.testing.assert_array_equal(out["node_requested"][3], snap.nodes.requested[3])
+    np.testing.assert_array_equal(out["node_pod_count"], snap.nodes.pod_count + np.bincount(node[placed], minlength=N))
+    # matched grew by the pods assumed per group; Scheduled <=> the gang completed during the walk
+    gid = snap.pods.gid[pods]
+    grouped = placed & (gid >= 0)
+    np.testing.assert_array_equal(out["group_matched"], snap.groups.matched + np.bincount(gid[grouped], minlength=G).astype(np.uint32))
+    newly = (out["group_flags"] & S.GROUP_SCHEDULED) & ~(snap.groups.flags & S.GROUP_SCHEDULED)
+    completed = np.zeros(G, bool)
+    completed[gid[(ready == 1) & (gid >= 0)]] = True
+    assert np.array_equal(newly.astype(bool), completed & ~(snap.groups.flags & S.GROUP_SCHEDULED).astype(bool))
+    # a refused group is frozen: after its NOT_ENOUGH pod every later pod of the group is DENIED
+    ne_first = {}
+    for qi in np.flatnonzero(pf == S.PF_NOT_ENOUGH):
+        ne_first.setdefault(int(gid[qi]), int(qi))
+    later = np.array([qi > ne_first.get(int(g), P) for qi, g in enumerate(gid)])
+    assert (pf[later] == S.PF_DENIED).all() and later.sum() > 1000
+    # no node is left over-committed on a lane the walk debited (it only assumes where the pod fits)
+    left_cpu = snap.nodes.alloc[0] - out["node_requested"][0]
+    touched = np.bincount(node[placed], minlength=N) > 0
+    assert (left_cpu[touched] >= 0).all()
