@@ -774,10 +774,18 @@ int evaluate_async_locked(bs_engine* e) {
       const uint64_t vary1 = (e->vary_prio << 32) | 0x80000000ull |
                              ((e->any_lister_miss || e->max_gid >= (int64_t)G) ? 0x7fffffffull : low_bits_mask(G));
       sa.n_ppass = build_passes(e->vary_ts, vary1, sa.ppass);
-      CK(cudaMemsetAsync(sa.barrier, 0, sizeof(unsigned int), e->s2));
-      const uint32_t grid = std::max(1u, std::min(sa.ntiles_max, e->sort_max_grid));
-      void* params[] = {&sa};
-      CK(cudaLaunchCooperativeKernel((const void*)queue_sort_kernel, dim3(grid), dim3(SORT_THREADS), params, 0, e->s2));
+      if (std::max(P, G) <= (uint32_t)SORT_SMALL_MAX) {
+        // small tables: one CTA, the same radix passes with the index arrays in shared memory
+        const size_t smem = sort_small_smem();
+        CK(cudaFuncSetAttribute(queue_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        queue_sort_small_kernel<<<1, SORT_SMALL_THREADS, smem, e->s2>>>(sa);
+        CK(cudaGetLastError());
+      } else {
+        CK(cudaMemsetAsync(sa.barrier, 0, sizeof(unsigned int), e->s2));
+        const uint32_t grid = std::max(1u, std::min(sa.ntiles_max, e->sort_max_grid));
+        void* params[] = {&sa};
+        CK(cudaLaunchCooperativeKernel((const void*)queue_sort_kernel, dim3(grid), dim3(SORT_THREADS), params, 0, e->s2));
+      }
       tm.launched();
     }
   }

@@ -319,4 +319,177 @@ __global__ void __launch_bounds__(SORT_THREADS) queue_sort_kernel(SortArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Small tables (max(P, G) <= SORT_SMALL_MAX): the persistent kernel's cost is the latency of its
+// ~25 phases through global memory, not its work.  One CTA runs the same stable LSD radix passes
+// (same keys, same host-built pass lists) with the index arrays and the warp-digit counters in shared
+// memory and the key words read through L1: no grid barrier, ~10x lower latency.  Same outputs.
+constexpr int SORT_SMALL_THREADS = 1024;
+constexpr int SORT_SMALL_WARPS = SORT_SMALL_THREADS / 32;
+constexpr int SORT_SMALL_MAX = 16384;
+constexpr int SORT_SMALL_ITER = SORT_SMALL_MAX / SORT_SMALL_THREADS;   // entries per lane and pass
+inline size_t sort_small_smem() {
+  return (size_t)SORT_SMALL_MAX * 4 * 2 + (size_t)SORT_SMALL_WARPS * 256 * 4 + 256 * 4 + 64 * 4;
+}
+
+struct SmallSortSmem {
+  uint32_t* ix_a;                 // [SORT_SMALL_MAX]
+  uint32_t* ix_b;                 // [SORT_SMALL_MAX]
+  uint32_t (*wcount)[256];        // [warps][digit]
+  uint32_t* dtot;                 // [256]
+  uint32_t* s_w;                  // [64]
+};
+
+// stable LSD radix sort of 0..n-1 by the pass list; returns the shared array holding the order
+__device__ uint32_t* small_radix(const uint64_t* k0, const uint64_t* k1, const SortPass* passes, uint32_t npass,
+                                 uint32_t n, const SmallSortSmem& sm) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < n; i += SORT_SMALL_THREADS) sm.ix_a[i] = i;
+  __syncthreads();
+  uint32_t* in = sm.ix_a;
+  uint32_t* out = sm.ix_b;
+  // warp w owns the contiguous slice [w * chunk, (w + 1) * chunk): equal digits keep their order
+  const uint32_t chunk = ((n + SORT_SMALL_THREADS - 1) / SORT_SMALL_THREADS) * 32;
+  const uint32_t iters = chunk / 32;
+  for (uint32_t ps = 0; ps < npass; ++ps) {
+    const SortPass pass = passes[ps];
+    for (int d = lane; d < 256; d += 32) sm.wcount[wid][d] = 0;
+    __syncwarp();
+    uint32_t my_idx[SORT_SMALL_ITER], my_dig[SORT_SMALL_ITER];
+    // (a) digit counts of this warp's slice
+#pragma unroll
+    for (int k = 0; k < SORT_SMALL_ITER; ++k) {
+      my_idx[k] = 0; my_dig[k] = 0x100u;
+      if ((uint32_t)k < iters) {
+        const uint32_t i = wid * chunk + k * 32 + lane;
+        const bool act = i < n;
+        if (act) { my_idx[k] = in[i]; my_dig[k] = digit_of(k0, k1, pass, my_idx[k]); }
+        const uint32_t mask = __match_any_sync(0xffffffffu, my_dig[k]);
+        if (act && lane == (uint32_t)(__ffs(mask) - 1)) sm.wcount[wid][my_dig[k]] += __popc(mask);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // (b) thread d: offsets of digit d per warp, digit totals, exclusive scan over the digits
+    if (threadIdx.x < 256) {
+      const uint32_t d = threadIdx.x;
+      uint32_t run = 0;
+      for (int w = 0; w < SORT_SMALL_WARPS; ++w) {
+        const uint32_t c = sm.wcount[w][d];
+        sm.wcount[w][d] = run;
+        run += c;
+      }
+      uint32_t inc = run;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += v;
+      }
+      if (lane == 31) sm.s_w[wid] = inc;
+      sm.dtot[d] = inc - run;   // exclusive within the warp of digits; warp offsets added below
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      uint32_t base = sm.dtot[threadIdx.x];
+      for (uint32_t w = 0; w < wid; ++w) base += sm.s_w[w];
+      sm.dtot[threadIdx.x] = base;
+    }
+    __syncthreads();
+    // (c) ranks in slice order, scatter
+#pragma unroll
+    for (int k = 0; k < SORT_SMALL_ITER; ++k) {
+      if ((uint32_t)k < iters) {
+        const uint32_t i = wid * chunk + k * 32 + lane;
+        const bool act = i < n;
+        const uint32_t mask = __match_any_sync(0xffffffffu, my_dig[k]);
+        uint32_t pos = 0;
+        if (act) pos = sm.dtot[my_dig[k]] + sm.wcount[wid][my_dig[k]] + __popc(mask & ((1u << lane) - 1u));
+        __syncwarp();
+        if (act && lane == (uint32_t)(__ffs(mask) - 1)) sm.wcount[wid][my_dig[k]] += __popc(mask);
+        __syncwarp();
+        if (act) out[pos] = my_idx[k];
+      }
+    }
+    __syncthreads();
+    uint32_t* t = in; in = out; out = t;
+  }
+  return in;
+}
+
+// dense rank over the sorted order: rank_out[ord[i]] = number of key changes before position i (inclusive)
+__device__ void small_rank(const uint32_t* ord, const uint64_t* k0, const uint64_t* k1, uint32_t n,
+                           uint32_t* rank_out, uint32_t* order_out, uint32_t* s_w) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t per = (n + SORT_SMALL_THREADS - 1) / SORT_SMALL_THREADS;   // consecutive positions per thread
+  const uint32_t base = threadIdx.x * per;
+  uint32_t c = 0;
+  for (uint32_t q = 0; q < per; ++q)
+    if (base + q < n) c += rank_flag(ord, k0, k1, base + q);
+  uint32_t inc = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((int)lane >= o) inc += v;
+  }
+  if (lane == 31) s_w[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t x = s_w[lane];
+    const uint32_t own = x;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, x, o);
+      if ((int)lane >= o) x += v;
+    }
+    s_w[32 + lane] = x - own;   // exclusive warp offsets
+  }
+  __syncthreads();
+  uint32_t run = s_w[32 + wid] + inc - c;
+  for (uint32_t q = 0; q < per; ++q) {
+    const uint32_t i = base + q;
+    if (i < n) {
+      run += rank_flag(ord, k0, k1, i);
+      const uint32_t o = ord[i];
+      rank_out[o] = run;
+      if (order_out) order_out[i] = o;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SORT_SMALL_THREADS, 1) queue_sort_small_kernel(SortArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallSortSmem sm;
+  sm.ix_a = reinterpret_cast<uint32_t*>(smem_raw);
+  sm.ix_b = sm.ix_a + SORT_SMALL_MAX;
+  sm.wcount = reinterpret_cast<uint32_t (*)[256]>(sm.ix_b + SORT_SMALL_MAX);
+  sm.dtot = reinterpret_cast<uint32_t*>(sm.wcount + SORT_SMALL_WARPS);
+  sm.s_w = sm.dtot + 256;
+  // ---- groups: keys -> sort -> dense rank
+  if (a.G) {
+    for (uint32_t i = threadIdx.x; i < a.G; i += SORT_SMALL_THREADS) {
+      a.gk0[i] = (uint64_t)(~a.name_rank[i]);   // descending name
+      a.gk1[i] = bias64(a.creation[i]);         // ascending creation
+    }
+    __syncthreads();
+    const uint32_t* gord = small_radix(a.gk0, a.gk1, a.gpass, a.n_gpass, a.G, sm);
+    small_rank(gord, a.gk0, a.gk1, a.G, a.group_rank, nullptr, sm.s_w);
+  }
+  // ---- pods
+  if (a.P) {
+    for (uint32_t i = threadIdx.x; i < a.P; i += SORT_SMALL_THREADS) {
+      const int32_t g = a.gid[i];
+      const uint32_t pbits = ~((uint32_t)a.prio[i] ^ 0x80000000u);  // higher priority first
+      uint32_t low;
+      if (g == BS_GID_NONE) low = 0u;                               // group-less first at equal priority
+      else {
+        const bool miss = g < 0 || (uint32_t)g >= a.G || (a.pflags[i] & BS_POD_LISTER_MISS);
+        low = 0x80000000u | (miss ? 0x7fffffffu : a.group_rank[g]);
+      }
+      a.pk1[i] = ((uint64_t)pbits << 32) | low;
+      a.pk0[i] = bias64(a.ts[i]);
+    }
+    __syncthreads();
+    const uint32_t* pord = small_radix(a.pk0, a.pk1, a.ppass, a.n_ppass, a.P, sm);
+    small_rank(pord, a.pk0, a.pk1, a.P, a.rank, a.order, sm.s_w);
+  }
+}
+
 }  // namespace bsk
