@@ -82,6 +82,7 @@ SYMBOLS = {
     "bs_last_error": (C.c_char_p, [C.c_void_p]),
     "bs_upload_nodes": (C.c_int, [C.c_void_p, _p(NodeTableC)]),
     "bs_update_nodes": (C.c_int, [C.c_void_p, C.c_void_p, _p(NodeTableC)]),
+    "bs_update_groups": (C.c_int, [C.c_void_p, C.c_void_p, _p(GroupTableC)]),
     "bs_upload_groups": (C.c_int, [C.c_void_p, _p(GroupTableC)]),
     "bs_upload_pods": (C.c_int, [C.c_void_p, _p(PodTableC)]),
     "bs_set_wait_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32]),

@@ -17,6 +17,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <chrono>
 #include <vector>
 
 #include "kernels.cuh"
@@ -69,6 +70,23 @@ struct PinBuf {
   }
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// a resizable array in pinned host memory: what is DMA'd every round must not be staged through
+// pageable memory
+template <class T>
+struct PinVec {
+  PinBuf buf;
+  size_t n = 0;
+  bool resize(size_t count) {
+    if (buf.ensure(std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return false;
+    n = count;
+    return true;
+  }
+  T* data() const { return buf.as<T>(); }
+  T& operator[](size_t i) const { return buf.as<T>()[i]; }
+  size_t size() const { return n; }
+  void release() { buf.release(); n = 0; }
 };
 
 // (sel, tol, non-zero scalar request mask): the pre-encoded predicates a pod class shares
@@ -226,7 +244,8 @@ struct bs_engine {
   // class indices (host packing): fit classes (sel, tol, nz) of the pods; representative classes
   // (sel, tol) of pods and carried-in group representatives
   ClassIndex fit_index, rep_index;
-  std::vector<uint32_t> h_pfc, h_prc, h_grc;
+  PinVec<uint32_t> h_pfc, h_prc, h_grc;   // pinned: DMA'd whenever the classes change
+  cudaEvent_t ev_classes = nullptr;       // the last class-table DMA out of them
   bool group_classes_dirty = true;
   std::vector<int64_t> h_wait_ns;
   int64_t default_wait_ns = 0;
@@ -234,6 +253,9 @@ struct bs_engine {
   bool any_lister_miss = true;
   int32_t max_gid = -1;
   uint64_t vary_ts = ~0ull, vary_prio = ~0ull, vary_creation = ~0ull, vary_name = ~0ull;
+  uint64_t g_or1 = 0, g_and1 = ~0ull, g_or0 = 0, g_and0 = ~0ull;   // OR / AND of the group key words seen so far
+  bool pod_classes_dirty = true;
+  double last_classes_us = 0;
   // pinned result cache
   PinBuf h_prefilter, h_feasible, h_best_node, h_best_score, h_admit, h_admit_bitmap, h_new_denied,
       h_order, h_rank, h_state, h_filter_code;
@@ -570,8 +592,10 @@ int rebuild_classes(bs_engine* e) {
   // looked up here (the representative index must already hold the pods' (sel, tol) pairs so that
   // the ids agree).  Then the class tables go to the device.
   const uint32_t P = e->P, G = e->G;
+  CK(cudaEventSynchronize(e->ev_classes));   // a previous DMA out of h_grc has finished
+  const bool groups_assigned = e->group_classes_dirty;
   if (e->group_classes_dirty) {
-    e->h_grc.resize(G);
+    if (!e->h_grc.resize(G)) return fail(e, BS_E_NOMEM, "pinned host memory");
     const uint64_t* gs = e->h_gsel.data();
     const uint64_t* gt = e->h_gtol.data();
     assign_classes(e->rep_index, G, [=](uint32_t g) { return ClassKey{gs[g], gt[g], 0u}; }, e->h_grc.data());
@@ -596,11 +620,14 @@ int rebuild_classes(bs_engine* e) {
   if ((rc = upload_vec(e, e->d_fnz, fnz.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
   if ((rc = upload_vec(e, e->d_rsel, rsel.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
   if ((rc = upload_vec(e, e->d_rtol, rtol.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
-  if ((rc = upload_vec(e, e->d_pod_fit_class, e->h_pfc.data(), P, std::max(P, 1u)))) return rc;
-  if ((rc = upload_vec(e, e->d_pod_rep_class, e->h_prc.data(), P, std::max(P, 1u)))) return rc;
-  if ((rc = upload_vec(e, e->d_group_rep_class, e->h_grc.data(), G, std::max(G, 1u)))) return rc;
-  CK(cudaStreamSynchronize(e->s));
+  if (e->pod_classes_dirty) {   // a group-only change (bs_update_groups) leaves the pods' ids alone
+    if ((rc = upload_vec(e, e->d_pod_fit_class, e->h_pfc.data(), P, std::max(P, 1u)))) return rc;
+    if ((rc = upload_vec(e, e->d_pod_rep_class, e->h_prc.data(), P, std::max(P, 1u)))) return rc;
+  }
+  if (groups_assigned && (rc = upload_vec(e, e->d_group_rep_class, e->h_grc.data(), G, std::max(G, 1u)))) return rc;
+  CK(cudaEventRecord(e->ev_classes, e->s));   // the pinned id arrays are read asynchronously from here on
   e->classes_dirty = false;
+  e->pod_classes_dirty = false;
   return BS_OK;
 }
 
@@ -717,8 +744,11 @@ int evaluate_async_locked(bs_engine* e) {
   int rc;
   bool reprepare = e->nodes_dirty;
   if (e->classes_dirty) {
+    const bool pods_changed = e->pod_classes_dirty;   // the fit classes (class_fit bits) come from the pods only
+    const auto tc0 = std::chrono::steady_clock::now();
     if ((rc = rebuild_classes(e))) return rc;
-    reprepare = true;
+    e->last_classes_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tc0).count();
+    reprepare = reprepare || pods_changed;
   }
   {
     const LaneMap lm = classify_lanes(e);
@@ -1009,7 +1039,8 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
   bool ok = cudaStreamCreateWithFlags(&e->s, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_classes, cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; ok && k < BS_K_COUNT; ++k)
     ok = cudaEventCreate(&e->ev_a[k]) == cudaSuccess && cudaEventCreate(&e->ev_b[k]) == cudaSuccess;
   if (ok) {
@@ -1062,6 +1093,8 @@ void bs_destroy(bs_engine* e) {
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->ev_classes) cudaEventDestroy(e->ev_classes);
+  e->h_pfc.release(); e->h_prc.release(); e->h_grc.release();
   if (e->s) cudaStreamDestroy(e->s);
   if (e->s2) cudaStreamDestroy(e->s2);
   delete e;
@@ -1201,13 +1234,82 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if ((rc = upload_vec(e, e->d_name_rank, t->name_rank, G, Gp))) return rc;
   e->vary_creation = G ? (o1 ^ a1) : 0;
   e->vary_name = G ? (o0 ^ a0) : 0;
-  e->h_gsel.assign(t->rep_sel, t->rep_sel + G);
-  e->h_gtol.assign(t->rep_tol, t->rep_tol + G);
+  e->g_or1 = o1; e->g_and1 = a1; e->g_or0 = o0; e->g_and0 = a0;
+  // representative (sel, tol) columns unchanged since the ids were assigned: nothing to look up again
+  const bool same_reps = e->h_gsel.size() == G && e->h_gtol.size() == G && e->h_grc.size() == G &&
+                         (G == 0 || (memcmp(e->h_gsel.data(), t->rep_sel, (size_t)G * 8) == 0 &&
+                                     memcmp(e->h_gtol.data(), t->rep_tol, (size_t)G * 8) == 0));
+  if (!same_reps) {
+    e->h_gsel.assign(t->rep_sel, t->rep_sel + G);
+    e->h_gtol.assign(t->rep_tol, t->rep_tol + G);
+    e->group_classes_dirty = true;
+    e->classes_dirty = true;
+  }
   if (e->h_wait_ns.size() != G) e->h_wait_ns.assign(G, -1);
   CK(cudaStreamSynchronize(e->s));   // the caller's arrays are free again once we return
   e->G = G;
   e->have_groups = true;
-  e->classes_dirty = true;
+  e->evaluated = false;
+  return BS_OK;
+}
+
+int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t) {
+  if (!e || !t || (t->n_groups && !idx)) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_groups) return fail(e, BS_E_STATE, "bs_update_groups: upload groups first");
+  if (t->n_lanes != e->L) return fail(e, BS_E_INVAL, "bs_update_groups: n_lanes differs from the engine's");
+  const uint32_t n = t->n_groups, L = e->L, G = e->G;
+  if (!n) return BS_OK;
+  if (!t->min_member || !t->scheduled || !t->matched || !t->flags || !t->min_res || !t->min_res_present ||
+      !t->rep_sel || !t->rep_tol || !t->creation_ns || !t->name_rank)
+    return fail(e, BS_E_INVAL, "bs_update_groups: null column");
+  for (uint32_t k = 0; k < n; ++k)
+    if (idx[k] >= G) return BS_E_INDEX;
+  {
+    int64_t mx[BS_MAX_LANES] = {};
+    if (!lane_maxima(t->min_res, L, n, mx)) return fail(e, BS_E_RANGE, "bs_update_groups: value outside +-2^56");
+  }
+  for (uint32_t k = 0; k < n; ++k)
+    if (t->creation_ns[k] == INT64_MAX) return fail(e, BS_E_RANGE, "bs_update_groups: creation_ns == INT64_MAX");
+  BS_DEVICE_GUARD(e);
+  DevBuf dmm, dsc, dma, dfl, dmr, dmp, dcr, dnr, di;
+  cudaError_t er = dmm.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = dsc.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = dma.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = dfl.ensure(n);
+  if (er == cudaSuccess) er = dmr.ensure((size_t)L * n * 8);
+  if (er == cudaSuccess) er = dmp.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = dcr.ensure((size_t)n * 8);
+  if (er == cudaSuccess) er = dnr.ensure((size_t)n * 4);
+  if (er == cudaSuccess) er = di.ensure((size_t)n * 4);
+  auto h2d = [&](DevBuf& d, const void* src, size_t bytes) {
+    if (er == cudaSuccess) er = cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, e->s);
+  };
+  h2d(dmm, t->min_member, (size_t)n * 4); h2d(dsc, t->scheduled, (size_t)n * 4); h2d(dma, t->matched, (size_t)n * 4);
+  h2d(dfl, t->flags, n); h2d(dmr, t->min_res, (size_t)L * n * 8); h2d(dmp, t->min_res_present, (size_t)n * 4);
+  h2d(dcr, t->creation_ns, (size_t)n * 8); h2d(dnr, t->name_rank, (size_t)n * 4); h2d(di, idx, (size_t)n * 4);
+  if (er == cudaSuccess) {
+    GroupCols dst{e->d_min_member.as<uint32_t>(), e->d_scheduled.as<uint32_t>(), e->d_matched.as<uint32_t>(),
+                  e->d_gflags.as<uint8_t>(), e->d_min_res.as<int64_t>(), e->d_mrpres.as<uint32_t>(),
+                  e->d_creation.as<int64_t>(), e->d_name_rank.as<uint32_t>()};
+    GroupCols src{dmm.as<uint32_t>(), dsc.as<uint32_t>(), dma.as<uint32_t>(), dfl.as<uint8_t>(), dmr.as<int64_t>(),
+                  dmp.as<uint32_t>(), dcr.as<int64_t>(), dnr.as<uint32_t>()};
+    group_scatter_kernel<<<cdiv(n, 256), 256, 0, e->s>>>(dst, std::max(G, 1u), L, src, di.as<uint32_t>(), n);
+    e->launches++;
+    er = cudaStreamSynchronize(e->s);
+  }
+  for (DevBuf* b : {&dmm, &dsc, &dma, &dfl, &dmr, &dmp, &dcr, &dnr, &di}) b->release();
+  CK(er);
+  // sort-key digits that vary: the accumulated OR / AND only widen (a superset costs a pass, never an error)
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint64_t c = (uint64_t)t->creation_ns[k], nm = (uint64_t)(~t->name_rank[k]);
+    e->g_or1 |= c; e->g_and1 &= c; e->g_or0 |= nm; e->g_and0 &= nm;
+    e->h_gsel[idx[k]] = t->rep_sel[k];
+    e->h_gtol[idx[k]] = t->rep_tol[k];
+  }
+  e->vary_creation = e->g_or1 ^ e->g_and1;
+  e->vary_name = e->g_or0 ^ e->g_and0;
+  e->classes_dirty = true;         // representative classes are looked up again; the pods' ids stay
   e->group_classes_dirty = true;
   e->evaluated = false;
   return BS_OK;
@@ -1235,7 +1337,12 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
     ClassIndex fit, rep;
   };
   std::vector<Part> part(T);
-  e->h_gid.resize(P); e->h_prio.resize(P); e->h_pflags.resize(P); e->h_pfc.resize(P); e->h_prc.resize(P);
+  e->h_gid.resize(P); e->h_prio.resize(P); e->h_pflags.resize(P);
+  {
+    BS_DEVICE_GUARD(e);
+    CK(cudaEventSynchronize(e->ev_classes));   // the class ids of the previous table are no longer being read
+    if (!e->h_pfc.resize(P) || !e->h_prc.resize(P)) return fail(e, BS_E_NOMEM, "pinned host memory");
+  }
   const uint32_t chunk = (P + T - 1) / std::max(T, 1);
 #pragma omp parallel num_threads(T)
   {
@@ -1302,10 +1409,18 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
-  // merge the thread-local class indices (both restart with the pod table) and remap the ids while
-  // the DMA is in flight
-  e->fit_index.clear();
-  e->rep_index.clear();
+  // Merge the thread-local class indices into the engine's and remap the ids while the DMA is in
+  // flight.  The engine's indices persist across uploads (ids of known classes are stable, so the
+  // groups' representative ids stay valid); they restart only when mostly stale.
+  {
+    size_t lf = 0, lr = 0;
+    for (int k = 0; k < T; ++k) { lf += part[k].fit.size(); lr += part[k].rep.size(); }
+    if (e->fit_index.size() > std::max<size_t>(4096, 4 * lf)) e->fit_index.clear();
+    if (e->rep_index.size() > std::max<size_t>(4096, 4 * lr)) {
+      e->rep_index.clear();
+      e->group_classes_dirty = true;   // the groups' ids referred to the old index
+    }
+  }
   {
     std::vector<std::vector<uint32_t>> rf(T), rr(T);
     for (int k = 0; k < T; ++k) {
@@ -1324,13 +1439,13 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       }
     }
   }
-  e->group_classes_dirty = true;
   CK(cudaStreamSynchronize(e->s));
   memcpy(e->max_req, mx_q, sizeof(mx_q));
   memcpy(e->neg_req, neg_q, sizeof(neg_q));
   e->P = P;
   e->have_pods = true;
   e->classes_dirty = true;
+  e->pod_classes_dirty = true;
   e->evaluated = false;
   return BS_OK;
 }
@@ -1372,9 +1487,25 @@ int bs_fetch(bs_engine* e, bs_results* out) {
 int bs_evaluate(bs_engine* e, bs_results* out) {
   if (!e) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);
+  static const bool prof = getenv("BS_HOST_PROFILE") != nullptr;   // host-side stage times on stderr
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = evaluate_async_locked(e);
   if (rc) return rc;
-  return fetch_locked(e, out);
+  if (!prof) return fetch_locked(e, out);
+  const auto t1 = std::chrono::steady_clock::now();
+  {
+    BS_DEVICE_GUARD(e);
+    CK(cudaStreamSynchronize(e->s));
+  }
+  const auto t2 = std::chrono::steady_clock::now();
+  rc = fetch_locked(e, out);
+  const auto t3 = std::chrono::steady_clock::now();
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  fprintf(stderr, "[bs_evaluate] enqueue %.0f us (classes %.0f us)  device wait %.0f us  fetch %.0f us\n", us(t0, t1),
+          e->last_classes_us, us(t1, t2), us(t2, t3));
+  return rc;
 }
 
 int bs_prefilter(bs_engine* e, uint32_t pod, bs_status* st) {

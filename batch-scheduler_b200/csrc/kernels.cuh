@@ -235,6 +235,32 @@ __global__ void node_scatter_kernel(NodeTabMut dst, uint32_t Npad, uint32_t L, N
   dst.flags[i] = src.flags[k];
 }
 
+// scatter of changed group rows into the resident group table (bs_update_groups)
+struct GroupCols {
+  uint32_t* min_member;
+  uint32_t* scheduled;
+  uint32_t* matched;
+  uint8_t* flags;
+  int64_t* min_res;   // [L][pitch]
+  uint32_t* min_res_present;
+  int64_t* creation;
+  uint32_t* name_rank;
+};
+__global__ void group_scatter_kernel(GroupCols dst, uint32_t G, uint32_t L, GroupCols src /*compact, pitch n*/,
+                                     const uint32_t* __restrict__ idx, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t g = idx[k];
+  dst.min_member[g] = src.min_member[k];
+  dst.scheduled[g] = src.scheduled[k];
+  dst.matched[g] = src.matched[k];
+  dst.flags[g] = src.flags[k];
+  for (uint32_t d = 0; d < L; ++d) dst.min_res[(size_t)d * G + g] = src.min_res[(size_t)d * n + k];
+  dst.min_res_present[g] = src.min_res_present[k];
+  dst.creation[g] = src.creation[k];
+  dst.name_rank[g] = src.name_rank[k];
+}
+
 // generic singleNodeResource table for one class (bs_node_left): left[L][N], present[N]
 __global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, float pct,
                                        int64_t* __restrict__ left, uint32_t* __restrict__ present) {

@@ -481,7 +481,7 @@ __device__ void small_rank(const uint32_t* ord, const uint64_t* k0, const uint64
 }
 
 __global__ void __launch_bounds__(SORT_SMALL_THREADS, 1) queue_sort_small_kernel(SortArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   SmallSortSmem sm;
   sm.ix_a = reinterpret_cast<uint32_t*>(smem_raw);
   sm.ix_b = sm.ix_a + SORT_SMALL_MAX;

@@ -84,6 +84,16 @@ class Engine:
         self._check(self.lib.bs_upload_groups(self.h, C.byref(t)))
         self.G = gt.n
 
+    def update_groups(self, idx, rows: GroupTable):
+        """Overwrites rows `idx` of the resident group table with `rows` (a compact GroupTable)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        assert len(idx) == rows.n
+        t = capi.GroupTableC(rows.n, rows.lanes, capi.ptr(rows.min_member), capi.ptr(rows.scheduled),
+                             capi.ptr(rows.matched), capi.ptr(rows.flags), capi.ptr(rows.min_res),
+                             capi.ptr(rows.min_res_present), capi.ptr(rows.rep_sel), capi.ptr(rows.rep_tol),
+                             capi.ptr(rows.creation_ns), capi.ptr(rows.name_rank))
+        self._check(self.lib.bs_update_groups(self.h, capi.ptr(idx), C.byref(t)))
+
     def upload_pods(self, pt: PodTable):
         t = capi.PodTableC(pt.n, pt.lanes, capi.ptr(pt.req), capi.ptr(pt.req_present), capi.ptr(pt.gid),
                            capi.ptr(pt.sel_mask), capi.ptr(pt.tol_mask), capi.ptr(pt.priority),
@@ -104,20 +114,32 @@ class Engine:
             self._check(self.lib.bs_set_wait_time(self.h, default_ns, capi.ptr(a), len(a)))
 
     # -- evaluation ------------------------------------------------------------------------
-    def _alloc_results(self):
+    def _alloc_results(self, out=None):
         P, G = self.P, self.G
-        r = RoundResult(np.zeros(P, np.uint8), np.zeros(P, np.uint32), np.zeros(P, np.int32), np.zeros(P, np.int64),
-                        np.zeros(G, np.uint8), np.zeros((G + 31) // 32, np.uint32), np.zeros(G, np.uint8),
-                        np.zeros(P, np.uint32), np.zeros(P, np.uint32), -1, 0,
-                        np.zeros(P, np.uint8) if (self.out_flags & capi.OUT_FILTER) else None)
+        if out is not None:
+            # numpy-style out=: refill a RoundResult of the same shape (a caller looping over rounds
+            # avoids ~2.6 MB of fresh, page-faulting result arrays per call)
+            if len(out.prefilter) != P or len(out.admit) != G or \
+                    (out.filter_code is None) != (not (self.out_flags & capi.OUT_FILTER)):
+                raise ValueError("out= does not match the uploaded tables")
+            r = out
+        else:
+            r = self._new_results(P, G)
         c = capi.ResultsC(capi.ptr(r.prefilter), capi.ptr(r.feasible_count), capi.ptr(r.best_node),
                           capi.ptr(r.best_score), capi.ptr(r.admit), capi.ptr(r.admit_bitmap),
                           capi.ptr(r.new_denied), capi.ptr(r.order), capi.ptr(r.rank), -1, 0,
                           capi.ptr(r.filter_code) if r.filter_code is not None else None)
         return r, c
 
-    def evaluate(self) -> RoundResult:
-        r, c = self._alloc_results()
+    def _new_results(self, P, G):
+        r = RoundResult(np.zeros(P, np.uint8), np.zeros(P, np.uint32), np.zeros(P, np.int32), np.zeros(P, np.int64),
+                        np.zeros(G, np.uint8), np.zeros((G + 31) // 32, np.uint32), np.zeros(G, np.uint8),
+                        np.zeros(P, np.uint32), np.zeros(P, np.uint32), -1, 0,
+                        np.zeros(P, np.uint8) if (self.out_flags & capi.OUT_FILTER) else None)
+        return r
+
+    def evaluate(self, out=None) -> RoundResult:
+        r, c = self._alloc_results(out)
         self._check(self.lib.bs_evaluate(self.h, C.byref(c)))
         r.max_group, r.max_finished = int(c.max_group), int(c.max_finished)
         return r
@@ -128,8 +150,8 @@ class Engine:
     def sync(self):
         self._check(self.lib.bs_sync(self.h))
 
-    def fetch(self) -> RoundResult:
-        r, c = self._alloc_results()
+    def fetch(self, out=None) -> RoundResult:
+        r, c = self._alloc_results(out)
         self._check(self.lib.bs_fetch(self.h, C.byref(c)))
         r.max_group, r.max_finished = int(c.max_group), int(c.max_finished)
         return r

@@ -387,7 +387,7 @@ def main():
         ta = time.perf_counter(); eng.upload_nodes(snap.nodes)
         tb = time.perf_counter(); eng.upload_groups(snap.groups)
         tc = time.perf_counter(); eng.upload_pods(snap.pods)
-        td = time.perf_counter(); res = eng.evaluate()
+        td = time.perf_counter(); res = eng.evaluate(out=res)
         te_ = time.perf_counter()
         br["upload_nodes"] += tb - ta; br["upload_groups"] += tc - tb; br["upload_pods"] += td - tc
         br["evaluate_fetch"] += te_ - td

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 3
+#define BS_ABI_VERSION 4
 #define BS_FIXED_LANES 4
 #define BS_MAX_LANES 16
 /* |value| bound accepted for every int64 table entry (validated at upload):
@@ -225,6 +225,11 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t);
  * order and size do not change; between scheduling cycles only a few NodeInfos differ. */
 int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t);
 int bs_upload_groups(bs_engine* e, const bs_group_table* t);
+/* The same for PodGroup state: overwrite rows idx[0..t->n_groups) of the uploaded group table.
+ * Between cycles a few groups change (matched count, Status.Scheduled, the Scheduled / denied flags,
+ * MinResources and the representative pod once the first pod arrived: cache.go:52-67); the table's
+ * size and order stay. */
+int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t);
 int bs_upload_pods(bs_engine* e, const bs_pod_table* t);
 /* max_schedule_time: plugin arg (batchscheduler.go:71-75, util.GetWaitTimeDuration
  * k8s.go:82-91).  per_group_ns may be NULL; entries < 0 mean "unset". */

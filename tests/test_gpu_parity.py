@@ -401,6 +401,47 @@ def test_incremental_node_update(pkg, oracle, snapshot_mod):
     eng.close()
 
 
+def test_incremental_group_update(pkg, oracle, snapshot_mod):
+    """bs_update_groups: a few PodGroups change between cycles (matched, Scheduled, freeze flag, MinResources,
+    representative pod, even creation time) == re-uploading the whole group table."""
+    S = snapshot_mod
+    snap = random_snapshot(6160, P=260, N=300, G=40, L=6)
+    other = random_snapshot(6161, P=10, N=10, G=40, L=6, case="B").groups
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=True, score=True)
+    eng.upload(snap)
+    eng.evaluate()
+    rng = np.random.default_rng(4)
+    cols1 = ("min_member", "scheduled", "matched", "flags", "min_res_present", "rep_sel", "rep_tol", "creation_ns",
+             "name_rank")
+    for round_ in range(4):
+        idx = np.sort(rng.choice(snap.groups.n, size=9, replace=False)).astype(np.uint32)
+        rows = S.GroupTable(other.min_member[idx], other.scheduled[idx], other.matched[idx], other.flags[idx],
+                            other.min_res[:, idx], other.min_res_present[idx], other.rep_sel[idx], other.rep_tol[idx],
+                            other.creation_ns[idx], snap.groups.name_rank[idx])
+        if round_ == 1:   # a representative class no pod of the round has
+            rows.rep_sel[0] = np.uint64(0xF0F0)
+            rows.flags[0] |= S.GROUP_HAS_POD
+        if round_ == 2:   # a creation time with new high bits: more sort digits vary
+            rows.creation_ns[1] = np.int64(1) << 61
+        if round_ == 3:   # the walk continues from here as well
+            rows.matched[:] = 0
+        snap.groups.min_res[:, idx] = rows.min_res
+        for f in cols1:
+            getattr(snap.groups, f)[idx] = getattr(rows, f)
+        eng.update_groups(idx, rows)
+        res = eng.evaluate()
+        orc = oracle.round(snap, want_bitmap=True, want_score=True)
+        assert_round_equal(res, eng.fit_rows(), eng.score_rows(), orc)
+        walk = eng.replay(res.order)
+        pf, node, ready, _ = oracle.replay(snap, res.order)
+        assert np.array_equal(walk["prefilter"], pf) and np.array_equal(walk["node"], node) and np.array_equal(walk["ready"], ready)
+    with pytest.raises(Exception):
+        eng.update_groups(np.array([snap.groups.n], np.uint32), S.GroupTable(*(getattr(rows, f)[..., :1] for f in (
+            "min_member", "scheduled", "matched", "flags", "min_res", "min_res_present", "rep_sel", "rep_tol",
+            "creation_ns", "name_rank"))))
+    eng.close()
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_extreme_values(pkg, oracle, snapshot_mod, seed):
     """Corners of the value domain: magnitudes at +-2^56, negative capacities / requests, int64-extreme
