@@ -1208,20 +1208,11 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if (G && (!t->min_member || !t->scheduled || !t->matched || !t->flags || !t->min_res ||
             !t->min_res_present || !t->rep_sel || !t->rep_tol || !t->creation_ns || !t->name_rank))
     return fail(e, BS_E_INVAL, "bs_upload_groups: null column");
-  {
-    int64_t mx[BS_MAX_LANES] = {};
-    if (!lane_maxima(t->min_res, L, G, mx)) return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
-  }
-  uint64_t o1 = 0, a1 = ~0ull, o0 = 0, a0 = ~0ull;
-  int bad_creation = 0;
-#pragma omp parallel for reduction(| : o1, o0, bad_creation) reduction(& : a1, a0) if (G > 65536) num_threads(host_threads())
-  for (uint32_t g = 0; g < G; ++g) {
-    const uint64_t c = (uint64_t)t->creation_ns[g], nm = (uint64_t)(~t->name_rank[g]);
-    o1 |= c; a1 &= c; o0 |= nm; a0 &= nm;
-    bad_creation |= t->creation_ns[g] == INT64_MAX ? 1 : 0;
-  }
-  if (bad_creation) return fail(e, BS_E_RANGE, "bs_upload_groups: creation_ns == INT64_MAX");
+  // the DMAs go first (asynchronous from pinned tables) and run under the host checks below; a table
+  // that then fails validation is dropped (have_groups = false)
   BS_DEVICE_GUARD(e);
+  e->have_groups = false;
+  e->evaluated = false;
   const uint32_t Gp = std::max(G, 1u);
   int rc;
   if ((rc = upload_vec(e, e->d_min_member, t->min_member, G, Gp))) return rc;
@@ -1232,6 +1223,25 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if ((rc = upload_vec(e, e->d_mrpres, t->min_res_present, G, Gp))) return rc;
   if ((rc = upload_vec(e, e->d_creation, t->creation_ns, G, Gp))) return rc;
   if ((rc = upload_vec(e, e->d_name_rank, t->name_rank, G, Gp))) return rc;
+  {
+    int64_t mx[BS_MAX_LANES] = {};
+    if (!lane_maxima(t->min_res, L, G, mx)) {
+      cudaStreamSynchronize(e->s);
+      return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
+    }
+  }
+  uint64_t o1 = 0, a1 = ~0ull, o0 = 0, a0 = ~0ull;
+  int bad_creation = 0;
+#pragma omp parallel for reduction(| : o1, o0, bad_creation) reduction(& : a1, a0) if (G > 65536) num_threads(host_threads())
+  for (uint32_t g = 0; g < G; ++g) {
+    const uint64_t c = (uint64_t)t->creation_ns[g], nm = (uint64_t)(~t->name_rank[g]);
+    o1 |= c; a1 &= c; o0 |= nm; a0 &= nm;
+    bad_creation |= t->creation_ns[g] == INT64_MAX ? 1 : 0;
+  }
+  if (bad_creation) {
+    cudaStreamSynchronize(e->s);
+    return fail(e, BS_E_RANGE, "bs_upload_groups: creation_ns == INT64_MAX");
+  }
   e->vary_creation = G ? (o1 ^ a1) : 0;
   e->vary_name = G ? (o0 ^ a0) : 0;
   e->g_or1 = o1; e->g_and1 = a1; e->g_or0 = o0; e->g_and0 = a0;
@@ -1338,11 +1348,21 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   };
   std::vector<Part> part(T);
   e->h_gid.resize(P); e->h_prio.resize(P); e->h_pflags.resize(P);
-  {
-    BS_DEVICE_GUARD(e);
-    CK(cudaEventSynchronize(e->ev_classes));   // the class ids of the previous table are no longer being read
-    if (!e->h_pfc.resize(P) || !e->h_prc.resize(P)) return fail(e, BS_E_NOMEM, "pinned host memory");
-  }
+  BS_DEVICE_GUARD(e);
+  CK(cudaEventSynchronize(e->ev_classes));   // the class ids of the previous table are no longer being read
+  if (!e->h_pfc.resize(P) || !e->h_prc.resize(P)) return fail(e, BS_E_NOMEM, "pinned host memory");
+  // the DMAs go first (asynchronous from pinned tables) and run under the host pass below; a table
+  // that then fails validation is dropped (have_pods = false)
+  e->have_pods = false;
+  e->evaluated = false;
+  const uint32_t Pp = std::max(P, 1u);
+  int rc;
+  if ((rc = upload_lanes(e, e->d_req, t->req, L, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_ppres, t->req_present, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_gid, t->gid, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
+  if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
   const uint32_t chunk = (P + T - 1) / std::max(T, 1);
 #pragma omp parallel num_threads(T)
   {
@@ -1390,9 +1410,8 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       }
       ot |= pt.ot; at &= pt.at; op |= pt.op; apr &= pt.apr; miss |= pt.miss; mg = std::max(mg, pt.mg);
     }
-    if (!ok) {
-      e->have_pods = false;   // the host-side columns were already overwritten: drop the table
-      e->evaluated = false;
+    if (!ok) {   // the device and host-side columns were already overwritten: the table stays dropped
+      cudaStreamSynchronize(e->s);
       return fail(e, BS_E_RANGE, "bs_upload_pods: value outside +-2^56");
     }
     e->vary_ts = P ? (ot ^ at) : 0;
@@ -1400,15 +1419,6 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
     e->any_lister_miss = miss != 0;
     e->max_gid = mg;
   }
-  BS_DEVICE_GUARD(e);
-  const uint32_t Pp = std::max(P, 1u);
-  int rc;
-  if ((rc = upload_lanes(e, e->d_req, t->req, L, P, Pp))) return rc;
-  if ((rc = upload_vec(e, e->d_ppres, t->req_present, P, Pp))) return rc;
-  if ((rc = upload_vec(e, e->d_gid, t->gid, P, Pp))) return rc;
-  if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
-  if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
-  if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
   // Merge the thread-local class indices into the engine's and remap the ids while the DMA is in
   // flight.  The engine's indices persist across uploads (ids of known classes are stable, so the
   // groups' representative ids stay valid); they restart only when mostly stale.

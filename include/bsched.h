@@ -218,7 +218,9 @@ const char* bs_last_error(const bs_engine* e);
  *      frameworkHandler.SnapshotSharedLister().NodeInfos().List() (core.go:597),
  *      PGStatusCache.PGStatusMap (cache.go:45-49) and the per-pod inputs of
  *      PreFilter/Permit/Compare (core.go:88,268,368).  Host arrays are copied;
- *      nothing is retained. ---- */
+ *      nothing is retained.  The copy runs under the validation pass: a table
+ *      that fails it (BS_E_RANGE) is dropped, and the engine answers BS_E_STATE
+ *      until a valid table of that kind is uploaded. ---- */
 int bs_upload_nodes(bs_engine* e, const bs_node_table* t);
 /* Incremental snapshot update: overwrite rows idx[0..t->n_nodes) of the uploaded node table with
  * the rows of `t` (a compact table of the changed nodes, same lane layout).  The snapshot's list

@@ -186,6 +186,23 @@ def test_value_range_rejected(pkg, snapshot_mod):
         eng.upload_nodes(snap.nodes)
     assert ei.value.code == pkg.capi.BS_E_RANGE
     eng.close()
+    # a group / pod table that fails validation is dropped: the engine refuses to evaluate until a
+    # valid one arrives (the DMA runs under the validation pass, so the old rows are gone)
+    snap = snapshot_mod.readme_scenario()
+    eng = pkg.Engine(snap.lanes)
+    eng.upload(snap)
+    eng.evaluate()
+    bad = snap.groups.copy() if hasattr(snap.groups, "copy") else snap.copy().groups
+    bad.min_res[0, 0] = -(1 << 57)
+    with pytest.raises(pkg.capi.BsError) as ei:
+        eng.upload_groups(bad)
+    assert ei.value.code == pkg.capi.BS_E_RANGE
+    with pytest.raises(pkg.capi.BsError) as ei:
+        eng.evaluate()
+    assert ei.value.code == pkg.capi.BS_E_STATE
+    eng.upload_groups(snap.groups)
+    assert (eng.evaluate().prefilter == 0).all()
+    eng.close()
 
 
 def test_reupload_and_reevaluate(pkg, oracle, snapshot_mod):
