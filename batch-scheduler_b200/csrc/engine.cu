@@ -197,8 +197,8 @@ struct bs_engine {
   std::mutex mu;
   int device = 0;
   uint32_t L = 0, out_flags = 0;
-  cudaStream_t s = nullptr, s2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t s = nullptr, s2 = nullptr, s3 = nullptr;   // main; queue sort; PreFilter chain (high priority)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pre = nullptr;
   std::string err;
   uint64_t launches = 0;
 
@@ -773,6 +773,7 @@ int evaluate_async_locked(bs_engine* e) {
   // fork the sort stream
   CK(cudaEventRecord(e->ev_fork, e->s));
   CK(cudaStreamWaitEvent(e->s2, e->ev_fork, 0));
+  CK(cudaStreamWaitEvent(e->s3, e->ev_fork, 0));
   {
     StageTimer tm(e, BS_K_SORT, e->s2);
     // one persistent kernel: group keys -> sort -> dense group rank -> pod keys -> sort -> order + rank
@@ -821,29 +822,30 @@ int evaluate_async_locked(bs_engine* e) {
   }
   CK(cudaEventRecord(e->ev_join, e->s2));
 
-  // main stream: group preparation + findMaxPG
+  // side stream (high priority): group preparation + findMaxPG, cluster scans, PreFilter.  The fit
+  // kernel does not need any of it; only the per-group verdicts do, and they come after both.
   {
-    StageTimer tm(e, BS_K_FIND_MAX, e->s);
+    StageTimer tm(e, BS_K_FIND_MAX, e->s3);
     const uint32_t gb = cdiv(std::max(G, 1u), 256);
-    group_reset_kernel<<<gb, 256, 0, e->s>>>(gt, ge, e->d_new_denied.as<uint8_t>(),
+    group_reset_kernel<<<gb, 256, 0, e->s3>>>(gt, ge, e->d_new_denied.as<uint8_t>(),
                                              e->d_admit_bitmap.as<uint32_t>(), e->d_okA.as<uint8_t>());
     tm.launched();
     if (P) {
-      group_first_pod_kernel<<<cdiv(P, 256), 256, 0, e->s>>>(pt, gt, ge);
+      group_first_pod_kernel<<<cdiv(P, 256), 256, 0, e->s3>>>(pt, gt, ge);
       tm.launched();
     }
     if (G) {
-      group_effective_kernel<<<gb, 256, 0, e->s>>>(pt, gt, ge);
+      group_effective_kernel<<<gb, 256, 0, e->s3>>>(pt, gt, ge);
       tm.launched();
     }
     const uint32_t nmp = cdiv(std::max(G, 1u), FINDMAX_THREADS * FINDMAX_PER_THREAD);
-    find_max_partial_kernel<<<nmp, FINDMAX_THREADS, 0, e->s>>>(gt, ge, e->d_max_partial.as<MaxState>());
-    find_max_final_kernel<<<1, 1024, 0, e->s>>>(gt, ge, e->d_max_partial.as<MaxState>(), nmp, st, e->N);
+    find_max_partial_kernel<<<nmp, FINDMAX_THREADS, 0, e->s3>>>(gt, ge, e->d_max_partial.as<MaxState>());
+    find_max_final_kernel<<<1, 1024, 0, e->s3>>>(gt, ge, e->d_max_partial.as<MaxState>(), nmp, st, e->N);
     tm.launched(2);
   }
   // ordered cluster scans (compareClusterResourceAndRequire) per rep class
   {
-    StageTimer tm(e, BS_K_CLASS_PREFIX, e->s);
+    StageTimer tm(e, BS_K_CLASS_PREFIX, e->s3);
     if (e->N && G && P) {
       PrefixScratch psc = prefix_scratch(e);
       PrefixSel ps{e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), 0, 0, 0, 0, 0.f, st};
@@ -851,30 +853,31 @@ int evaluate_async_locked(bs_engine* e) {
         const uint32_t nc = std::min(e->prefix_slots, e->n_rep_classes - c0);
         ps.c0 = c0;
         ps.mode = 0;
-        launch_prefix(L, t, ps, psc, po, nc, e->s);
-        group_check_kernel<<<cdiv(G * 32, 256), 256, 0, e->s>>>(t, gt, ge, po, c0, nc, st, e->d_okA.as<uint8_t>());
+        launch_prefix(L, t, ps, psc, po, nc, e->s3);
+        group_check_kernel<<<cdiv(G * 32, 256), 256, 0, e->s3>>>(t, gt, ge, po, c0, nc, st, e->d_okA.as<uint8_t>());
         tm.launched(3);
       }
       ps.c0 = 0;
       ps.mode = 1;
-      launch_prefix(L, t, ps, psc, po, 1, e->s);
+      launch_prefix(L, t, ps, psc, po, 1, e->s3);
       tm.launched(2);
     }
   }
   {
-    StageTimer tm(e, BS_K_PREFILTER, e->s);
+    StageTimer tm(e, BS_K_PREFILTER, e->s3);
     if (P) {
-      prefilter_kernel<<<cdiv(P, PREFILTER_THREADS), PREFILTER_THREADS, 0, e->s>>>(
+      prefilter_kernel<<<cdiv(P, PREFILTER_THREADS), PREFILTER_THREADS, 0, e->s3>>>(
           t, pt, gt, ge, po, st, e->d_okA.as<uint8_t>(), e->d_prefilter.as<uint8_t>(),
           e->d_new_denied.as<uint8_t>());
       tm.launched();
     }
     if (G) {
-      group_idle_admit_kernel<<<cdiv(G, 256), 256, 0, e->s>>>(gt, ge, e->d_admit.as<uint8_t>(),
+      group_idle_admit_kernel<<<cdiv(G, 256), 256, 0, e->s3>>>(gt, ge, e->d_admit.as<uint8_t>(),
                                                               e->d_admit_bitmap.as<uint32_t>());
       tm.launched();
     }
   }
+  CK(cudaEventRecord(e->ev_pre, e->s3));
   {
     StageTimer tm(e, BS_K_GANG_FIT, e->s);
     if (P) {
@@ -904,9 +907,25 @@ int evaluate_async_locked(bs_engine* e) {
       a.fit_bitmap = (e->out_flags & BS_OUT_FIT_BITMAP) ? e->d_fit_bitmap.as<uint32_t>() : nullptr;
       a.score = (e->out_flags & BS_OUT_SCORE) ? e->d_score.as<int64_t>() : nullptr;
       a.P = P; a.N = e->N; a.Npad = e->Npad; a.W = e->W; a.G = G;
+      a.defer_admit = 1;
       CK(launch_fit(a, cdiv(P, PODS_PER_CTA), e->s));
       tm.launched();
     }
+  }
+  CK(cudaStreamWaitEvent(e->s, e->ev_pre, 0));   // PreFilter verdicts, effective group state, RoundState
+  if (P && G) {
+    AdmitArgs aa{};
+    aa.gid = e->d_gid.as<int32_t>();
+    aa.prefilter = e->d_prefilter.as<uint8_t>();
+    aa.feasible_count = e->d_feasible.as<uint32_t>();
+    aa.min_member = gt.min_member; aa.scheduled = gt.scheduled; aa.matched = gt.matched;
+    aa.in_round = ge.in_round; aa.contrib = ge.contrib; aa.done = ge.done;
+    aa.admit = e->d_admit.as<uint8_t>();
+    aa.admit_bitmap = e->d_admit_bitmap.as<uint32_t>();
+    aa.P = P; aa.G = G;
+    gang_admit_kernel<<<cdiv(P, 256), 256, 0, e->s>>>(aa);
+    e->k_launches[BS_K_GANG_FIT] += 1;
+    e->launches += 1;
   }
   {
     StageTimer tm(e, BS_K_FILTER, e->s);
@@ -1036,8 +1055,13 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
   e->device = cfg->device;
   e->L = cfg->n_lanes;
   e->out_flags = cfg->out_flags;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the small kernels of the PreFilter chain must get the
+                                                          // SM slots the fit kernel's retiring CTAs free
   bool ok = cudaStreamCreateWithFlags(&e->s, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&e->s3, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_pre, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_classes, cudaEventDisableTiming) == cudaSuccess;
@@ -1093,6 +1117,8 @@ void bs_destroy(bs_engine* e) {
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->ev_pre) cudaEventDestroy(e->ev_pre);
+  if (e->s3) cudaStreamDestroy(e->s3);
   if (e->ev_classes) cudaEventDestroy(e->ev_classes);
   e->h_pfc.release(); e->h_prc.release(); e->h_grc.release();
   if (e->s) cudaStreamDestroy(e->s);

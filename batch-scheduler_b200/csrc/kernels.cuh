@@ -1091,6 +1091,7 @@ struct FitArgs {
   // TMA source address of a narrow row is derived from a 32-bit Npad; 64-bit pitches avoid it.
   uint64_t left_w_pitch, left_n_pitch;
   uint32_t P, N, Npad, W, G;
+  uint32_t defer_admit;   // 1: the group verdicts are left to gang_admit_kernel (the PreFilter chain runs beside this kernel)
 };
 
 // One node tile for the PODS_PER_WARP pods of a warp.  TAIL: the tile holds padding
@@ -1340,7 +1341,7 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
         a.best_node[p] = n;
         a.best_score[p] = s;
       }
-      if (lane == (uint32_t)k) {
+      if (!a.defer_admit && lane == (uint32_t)k) {
         const int32_t g = a.gid[p];
         if (g >= 0 && (uint32_t)g < a.G) {
           my_gid = (uint32_t)g;
@@ -1350,7 +1351,7 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
     }
   }
   // warp-segmented reduction over lanes 0..PODS_PER_WARP-1: runs of equal gid
-  {
+  if (!a.defer_admit) {
     const uint32_t prev_gid = __shfl_up_sync(0xffffffffu, my_gid, 1);
     const bool active = lane < PODS_PER_WARP && my_gid != 0xffffffffu;
     const bool head = active && (lane == 0 || prev_gid != my_gid);
@@ -1380,6 +1381,66 @@ __global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_
         a.admit[my_gid] = verdict;
         if (verdict == BS_ADMIT) atomicOr(&a.admit_bitmap[my_gid >> 5], 1u << (my_gid & 31));
       }
+    }
+  }
+}
+
+// K6b  gang_admit_kernel — the per-group half of Permit (core.go:303) as its own launch: one pod per
+// thread, runs of equal gid merged inside the warp, one atomic per run, the run that completes the
+// group's pod count writes the verdict.  Used when the PreFilter chain runs on a side stream beside
+// gang_fit_kernel (its verdicts are needed only here, after both).
+struct AdmitArgs {
+  const int32_t* gid;
+  const uint8_t* prefilter;
+  const uint32_t* feasible_count;
+  const uint32_t* min_member;
+  const uint32_t* scheduled;
+  const uint32_t* matched;
+  const uint32_t* in_round;
+  uint32_t* contrib;
+  uint32_t* done;
+  uint8_t* admit;
+  uint32_t* admit_bitmap;
+  uint32_t P, G;
+};
+__global__ void __launch_bounds__(256) gang_admit_kernel(AdmitArgs a) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  uint32_t my_gid = 0xffffffffu, my_pass = 0;
+  if (p < a.P) {
+    const int32_t g = a.gid[p];
+    if (g >= 0 && (uint32_t)g < a.G) {
+      my_gid = (uint32_t)g;
+      my_pass = (a.prefilter[p] == BS_PF_PASS && a.feasible_count[p] > 0) ? 1u : 0u;
+    }
+  }
+  const uint32_t prev_gid = __shfl_up_sync(0xffffffffu, my_gid, 1);
+  const bool active = my_gid != 0xffffffffu;
+  const bool head = active && (lane == 0 || prev_gid != my_gid);
+  uint32_t run_pass = my_pass, run_len = active ? 1u : 0u;
+#pragma unroll
+  for (int o = 1; o < 32; ++o) {
+    const uint32_t og = __shfl_down_sync(0xffffffffu, my_gid, o);
+    const uint32_t op = __shfl_down_sync(0xffffffffu, my_pass, o);
+    // run_len == o  <=>  every lane in between carried the same gid (contiguous run)
+    if (head && run_len == (uint32_t)o && lane + o < 32 && og == my_gid) {
+      run_pass += op;
+      run_len += 1;
+    }
+  }
+  if (head) {
+    if (run_pass) atomicAdd(&a.contrib[my_gid], run_pass);
+    __threadfence();
+    const uint32_t ticket = atomicAdd(&a.done[my_gid], run_len) + run_len;
+    if (ticket == a.in_round[my_gid]) {
+      // last pod of the group: Permit readiness (core.go:303) on the full count
+      __threadfence();
+      const uint32_t c = atomicAdd(&a.contrib[my_gid], 0u);
+      const uint32_t total = a.matched[my_gid] + c;
+      uint8_t verdict;
+      if (c == 0) verdict = BS_UNSCHEDULABLE;
+      else verdict = (total >= (uint32_t)(a.min_member[my_gid] - a.scheduled[my_gid])) ? BS_ADMIT : BS_WAIT;
+      a.admit[my_gid] = verdict;
+      if (verdict == BS_ADMIT) atomicOr(&a.admit_bitmap[my_gid >> 5], 1u << (my_gid & 31));
     }
   }
 }
