@@ -215,6 +215,20 @@ def test_reupload_and_reevaluate(pkg, oracle, snapshot_mod):
             res = eng.evaluate()
             orc = oracle.round(snap, want_bitmap=True, want_score=True)
             assert_round_equal(res, eng.fit_rows(), eng.score_rows(), orc)
+        # numpy-style out=: the same arrays are refilled (and a stale shape is refused)
+        res.prefilter[:] = 99
+        again = eng.evaluate(out=res)
+        assert again is res
+        assert_round_equal(res, eng.fit_rows(), eng.score_rows(), orc)
+        # back-to-back rounds without a sync in between, then one fetch: the three streams of a round
+        # (fit, PreFilter chain, sort) must not run into the next round's
+        for _ in range(3):
+            eng.evaluate_async()
+        eng.sync()
+        assert_round_equal(eng.fetch(), eng.fit_rows(), eng.score_rows(), orc)
+    with pytest.raises(ValueError):
+        eng.upload(random_snapshot(77, P=33, N=20, G=4, L=5))
+        eng.evaluate(out=res)
     eng.close()
 
 
