@@ -21,3 +21,13 @@ def load(path):
                       os.path.basename(path))
     out = {k[5:]: z[k] for k in z.files if k.startswith("out__")}
     return snap, out
+
+
+def replay_fixtures():
+    return sorted(glob.glob(os.path.join(HERE, "golden", "replay_*.npz")))
+
+
+def load_replay(path):
+    """(snapshot, queue, expected prefilter / node / ready) of a tests/golden/replay_*.npz fixture."""
+    snap, out = load(path)
+    return snap, np.load(path)["queue"], out

@@ -236,3 +236,108 @@ def prefilter_round(snap):
         if not compare_cluster(nodes, int(rep_sel[m]), int(rep_tol[m]), need, 0.7):
             codes[p], denied[g] = 5, 1
     return codes, denied, m
+
+
+def replay(snap, queue=None):
+    """The reference's cycle, pod after pod, with mutable Go-like objects: PreFilter
+    against the live state (core.go:88-167, fillOccupiedObj :477-512, AddToDenyCache :423-425), the
+    pod assumed onto the first node in list order where A5 holds (NodeInfo.AddPod), Permit
+    (core.go:268-309).  Written from core.go, independently of oracle/bs_oracle.c's bso_replay.
+    Returns (prefilter[], node[], ready[]) per queue position."""
+    nt, pt, gt = snap.nodes, snap.pods, snap.groups
+    L = nt.lanes
+    nodes = [Node(nt, i) for i in range(nt.n)]
+    flags = [int(f) for f in gt.flags]
+    matched = [int(m) for m in gt.matched]
+    rep = [(int(s), int(t)) for s, t in zip(gt.rep_sel, gt.rep_tol)]
+    min_res = [resource_from(gt.min_res[:, g], int(gt.min_res_present[g]), L) for g in range(gt.n)]
+
+    class Live:  # what find_max_pg / pre_allocated read, seen through the mutable lists
+        n, lanes = gt.n, L
+        min_member, scheduled = gt.min_member, gt.scheduled
+    Live.matched = matched
+
+    def need_of(g, matched_arg):
+        out = Resource()
+        mm = int(gt.min_member[g])
+        not_finished = mm - matched_arg if matched_arg != 0 else mm - int(gt.scheduled[g])
+        for _ in range(max(0, not_finished)):
+            if flags[g] & 0x04:
+                out.Add(min_res[g])
+        if out.AllowedPodNumber == 0:
+            out.AllowedPodNumber = mm + 1
+        return out
+
+    q = range(pt.n) if queue is None else [int(x) for x in queue]
+    out_pf, out_node, out_ready = [], [], []
+    for p in q:
+        g, f = int(pt.gid[p]), int(pt.flags[p])
+        req = resource_from(pt.req[:, p], int(pt.req_present[p]) & ~0xF, L)
+        code = 0
+        while True:  # PreFilter
+            if g == -1 or (f & 0x01):
+                break
+            if g < 0 or g >= gt.n:
+                code = 1
+                break
+            if flags[g] & 0x08:
+                code = 2
+                break
+            if not (flags[g] & 0x02):
+                flags[g] |= 0x02
+                rep[g] = (int(pt.sel_mask[p]), int(pt.tol_mask[p]))
+            if not (flags[g] & 0x04):
+                flags[g] |= 0x04
+                mr = Resource()
+                mr.Add(req)
+                min_res[g] = mr
+            if f & 0x02:
+                code = 3
+                break
+            if f & 0x04:
+                code = 4
+                break
+            m, _ = find_max_pg(Live, flags)
+            if m < 0:
+                break
+            if matched[m] == 0:
+                if not compare_cluster(nodes, rep[g][0], rep[g][1], need_of(g, 0), 1.0):
+                    flags[g] |= 0x08
+                    code = 5
+                break
+            if m == g:
+                break
+            need = need_of(m, matched[m])
+            need.Add(req)
+            if not compare_cluster(nodes, rep[m][0], rep[m][1], need, 0.7):
+                flags[g] |= 0x08
+                code = 5
+            break
+        out_pf.append(code)
+        chosen, ready = -1, 0
+        if code == 0:
+            sel, tol = int(pt.sel_mask[p]), int(pt.tol_mask[p])
+            for i, node in enumerate(nodes):
+                if (node.flags & 0x0F) or not check_fit(sel, tol, node):
+                    continue
+                if compare_resource_and_require(single_node_resource(node, sel, tol, 1.0), req):
+                    chosen = i
+                    break
+            if chosen >= 0:
+                node = nodes[chosen]  # NodeInfo.AddPod: requested += request, the pod list grows
+                node.req.MilliCPU = i64(node.req.MilliCPU + req.MilliCPU)
+                node.req.Memory = i64(node.req.Memory + req.Memory)
+                node.req.EphemeralStorage = i64(node.req.EphemeralStorage + req.EphemeralStorage)
+                for k, v in req.ScalarResources.items():
+                    node.req.ScalarResources[k] = i64(node.req.ScalarResources.get(k, int(nt.requested[k, chosen])) + v)
+                node.n_pods += 1
+                if g < 0 or g >= gt.n:
+                    ready = 1
+                else:
+                    matched[g] += 1
+                    if (matched[g] & M32) >= ((int(gt.min_member[g]) - int(gt.scheduled[g])) & M32):
+                        flags[g] |= 0x01
+                        ready = 1
+        out_node.append(chosen)
+        out_ready.append(ready)
+    return np.array(out_pf, np.uint8), np.array(out_node, np.int32), np.array(out_ready, np.uint8)

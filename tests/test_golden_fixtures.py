@@ -34,3 +34,29 @@ def test_engine_reproduces_fixture(pkg, path):
     np.testing.assert_array_equal(eng.filter_rows(), exp["filter_bitmap"])
     assert res.max_group == int(exp["max_group"][0])
     eng.close()
+
+
+RFIX = golden_util.replay_fixtures()
+
+
+@pytest.mark.parametrize("path", RFIX, ids=[os.path.basename(p) for p in RFIX])
+def test_oracle_reproduces_replay_fixture(oracle, path):
+    # the walk with mutable state; the arrays were written by tests/pyref.py
+    snap, queue, exp = golden_util.load_replay(path)
+    pf, node, ready, _ = oracle.replay(snap, queue)
+    np.testing.assert_array_equal(pf, exp["prefilter"])
+    np.testing.assert_array_equal(node, exp["node"])
+    np.testing.assert_array_equal(ready, exp["ready"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", RFIX, ids=[os.path.basename(p) for p in RFIX])
+def test_engine_reproduces_replay_fixture(pkg, path):
+    snap, queue, exp = golden_util.load_replay(path)
+    eng = pkg.Engine(snap.lanes, 0, fit_bitmap=False, score=False)
+    eng.upload(snap)
+    got = eng.replay(queue, after_state=False)
+    eng.close()
+    np.testing.assert_array_equal(got["prefilter"], exp["prefilter"])
+    np.testing.assert_array_equal(got["node"], exp["node"])
+    np.testing.assert_array_equal(got["ready"], exp["ready"])

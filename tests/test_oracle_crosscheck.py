@@ -18,6 +18,19 @@ def test_prefilter_round_matches_python_restatement(oracle, seed):
     np.testing.assert_array_equal(r.new_denied, denied)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_replay_matches_python_restatement(oracle, seed):
+    # the pod-at-a-time walk with mutable state (bso_replay) against pyref.replay, written from core.go
+    snap = random_snapshot(3000 + seed, P=70, N=20 + seed, G=9, L=[4, 5, 6, 9][seed % 4],
+                           case=["mixed", "A", "B"][seed % 3])
+    queue = None if seed % 2 == 0 else np.random.default_rng(seed).permutation(snap.pods.n)
+    pf, node, ready, _ = oracle.replay(snap, queue)
+    a, b, c = pyref.replay(snap, queue)
+    np.testing.assert_array_equal(pf, a)
+    np.testing.assert_array_equal(node, b)
+    np.testing.assert_array_equal(ready, c)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_single_node_and_cluster(oracle, seed):
     snap = random_snapshot(2100 + seed, P=5, N=40, G=3, L=6)
