@@ -18,6 +18,7 @@
 #include <thread>
 #include <unordered_map>
 #include <chrono>
+#include <sched.h>
 #include <vector>
 
 #include "kernels.cuh"
@@ -155,7 +156,9 @@ inline int host_threads() {
     if (const char* s = getenv("BS_HOST_THREADS")) return std::max(1, atoi(s));
     int ndev = 1;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
-    const int hw = (int)std::thread::hardware_concurrency();
+    int hw = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;   // cores this process may actually run on (cgroup / taskset), not the box's total
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = std::min(hw > 0 ? hw : 1 << 20, CPU_COUNT(&set));
     return std::max(1, std::min(8, hw / ndev));
   }();
   return n;

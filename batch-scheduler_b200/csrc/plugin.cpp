@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <sched.h>
 #include <thread>
 #include <chrono>
 #include <cstdio>
@@ -203,7 +204,10 @@ bool tolerates(const Toleration& t, const Taint& taint) {
 int pack_threads(size_t objects) {
   if (objects < 4096) return 1;
   if (const char* s = getenv("BS_HOST_THREADS")) return std::max(1, atoi(s));
-  return std::max(1, std::min(8, (int)std::thread::hardware_concurrency()));
+  int hw = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;   // cores this process may run on, not the box's total
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = std::min(hw > 0 ? hw : 1 << 20, CPU_COUNT(&set));
+  return std::max(1, std::min(8, hw));
 }
 
 std::string joined_sorted(std::vector<std::string> v) {
