@@ -238,6 +238,76 @@ def prefilter_round(snap):
     return codes, denied, m
 
 
+def get_left_resource(node):  # core.go:436-475
+    """None when the reference returns nil (info == nil).  The scalar loop at :465-472 ranges over the
+    Clone of a zero Resource, whose map is nil: it never runs, so no scalar key is ever reported."""
+    if node.flags & 0x01:
+        return None
+    left = Resource()
+    pod_count = node.req.AllowedPodNumber
+    if pod_count == 0:
+        pod_count = node.n_pods
+    left.MilliCPU = i64(node.alloc.MilliCPU - node.req.MilliCPU)
+    left.AllowedPodNumber = i64(node.alloc.AllowedPodNumber - pod_count)
+    left.Memory = i64(node.alloc.Memory - node.req.Memory)
+    left.EphemeralStorage = i64(node.alloc.EphemeralStorage - node.req.EphemeralStorage)
+    return left
+
+
+def filter_round(snap):
+    """Filter / computeResourceSatisfied (core.go:170-191, :514-564) for every (pod, node) of a round,
+    against the round's max group and its MinResources after the first-pod capture.
+    Returns (passes[P][N] bool, code[P]) with code 0 pass-able, 1 group not found, 4 maxPGStatus nil."""
+    nt, pt, gt = snap.nodes, snap.pods, snap.groups
+    L = nt.lanes
+    nodes = [Node(nt, i) for i in range(nt.n)]
+    flags = gt.flags.copy()
+    min_res, min_res_present = gt.min_res.copy(), gt.min_res_present.copy()
+    for p in range(pt.n):  # fillOccupiedObj first-pod capture (as in prefilter_round)
+        g = int(pt.gid[p])
+        if g < 0 or g >= gt.n or (pt.flags[p] & 0x01) or (gt.flags[g] & 0x08):
+            continue
+        flags[g] |= 0x02
+        if not (flags[g] & 0x04):
+            flags[g] |= 0x04
+            for d in range(L):
+                pres = d < 4 or ((int(pt.req_present[p]) >> d) & 1)
+                min_res[d, g] = pt.req[d, p] if pres else 0
+            min_res_present[g] = int(pt.req_present[p]) & ~0xF
+    m, _ = find_max_pg(gt, flags)
+    max_single = None
+    if m >= 0 and (flags[m] & 0x04):  # :525-528 maxSingleRequired = Resource{}.Add(*MinResources)
+        max_single = Resource()
+        max_single.Add(resource_from(min_res[:, m], int(min_res_present[m]), L))
+    passes = np.zeros((pt.n, nt.n), bool)
+    codes = np.zeros(pt.n, np.uint8)
+    for p in range(pt.n):
+        g = int(pt.gid[p])
+        if g == -1:  # :171-174
+            passes[p, :] = True
+            continue
+        if g < 0 or g >= gt.n:  # :177-180
+            codes[p] = 1
+            continue
+        if m < 0:  # :525 dereferences sop.maxPGStatus == nil
+            codes[p] = 4
+            continue
+        if m == g or max_single is None:  # :531-535 case 1; :542-544
+            passes[p, :] = True
+            continue
+        for i, node in enumerate(nodes):
+            left = get_left_resource(node)
+            if left is None:  # :545-548
+                continue
+            cur = resource_from(pt.req[:, p], int(pt.req_present[p]) & ~0xF, L)
+            cur.Add(max_single)  # :551-552
+            if compare_resource_and_require(left, cur):  # case 2
+                passes[p, i] = True
+            elif not compare_resource_and_require(left, max_single):  # case 3
+                passes[p, i] = True
+    return passes, codes
+
+
 def replay(snap, queue=None):
     """The reference's cycle, pod after pod, with mutable Go-like objects: PreFilter
     against the live state (core.go:88-167, fillOccupiedObj :477-512, AddToDenyCache :423-425), the

@@ -31,6 +31,18 @@ def test_replay_matches_python_restatement(oracle, seed):
     np.testing.assert_array_equal(ready, c)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_filter_matrix_matches_python_restatement(oracle, seed):
+    # Filter / computeResourceSatisfied / getLeftResource (core.go:170-191, 436-475, 514-564)
+    snap = random_snapshot(3100 + seed, P=50, N=30 + seed, G=8, L=[4, 5, 6, 9][seed % 4],
+                           case=["mixed", "A", "B"][seed % 3])
+    r = oracle.round(snap, want_bitmap=False, want_sort=False, want_filter=True)
+    passes, codes = pyref.filter_round(snap)
+    bits = np.unpackbits(r.filter_bitmap.view(np.uint8), axis=1, bitorder="little")[:, :snap.nodes.n].astype(bool)
+    np.testing.assert_array_equal(r.filter_code, codes)
+    np.testing.assert_array_equal(bits, passes)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_single_node_and_cluster(oracle, seed):
     snap = random_snapshot(2100 + seed, P=5, N=40, G=3, L=6)
