@@ -238,6 +238,75 @@ def prefilter_round(snap):
     return codes, denied, m
 
 
+def round_outputs(snap):
+    """The rest of a snapshot round from the Go-like objects: fit matrix (the composite
+    of core_test.go:108-110 behind the node guards and checkFit), builder-defined score, per-pod
+    reductions, Permit verdict per group (core.go:303, uint32), and the queue order by Compare's key.
+    Returns a dict of arrays shaped like the oracle's."""
+    import functools
+    nt, pt, gt = snap.nodes, snap.pods, snap.groups
+    L, P, N, G = nt.lanes, pt.n, nt.n, gt.n
+    nodes = [Node(nt, i) for i in range(N)]
+    INT64_MIN = -(1 << 63)
+    fit = np.zeros((P, N), bool)
+    score = np.full((P, N), INT64_MIN, np.int64)
+    for p in range(P):
+        sel, tol = int(pt.sel_mask[p]), int(pt.tol_mask[p])
+        req = resource_from(pt.req[:, p], int(pt.req_present[p]) & ~0xF, L)
+        for i, node in enumerate(nodes):
+            if (node.flags & 0x0F) or not check_fit(sel, tol, node):
+                continue
+            left = single_node_resource(node, sel, tol, 1.0)
+            if not compare_resource_and_require(left, req):
+                continue
+            fit[p, i] = True
+            diffs = [left.MilliCPU - req.MilliCPU, left.Memory - req.Memory,
+                     left.EphemeralStorage - req.EphemeralStorage, left.AllowedPodNumber - req.AllowedPodNumber]
+            diffs += [left.ScalarResources[k] - v for k, v in req.ScalarResources.items() if k in left.ScalarResources]
+            score[p, i] = i64(min(diffs))
+    feasible = fit.sum(axis=1).astype(np.uint32)
+    best_node = np.full(P, -1, np.int32)
+    best_score = np.full(P, INT64_MIN, np.int64)
+    for p in range(P):
+        if feasible[p]:
+            best_node[p] = int(np.argmax(score[p]))   # first maximum = lowest index on ties
+            best_score[p] = score[p, best_node[p]]
+    codes, _, _ = prefilter_round(snap)
+    contrib, in_round = np.zeros(G, np.int64), np.zeros(G, np.int64)
+    for p in range(P):
+        g = int(pt.gid[p])
+        if 0 <= g < G:
+            in_round[g] += 1
+            if codes[p] == 0 and feasible[p]:
+                contrib[g] += 1
+    admit = np.zeros(G, np.uint8)
+    for g in range(G):
+        cnt = (int(gt.matched[g]) + int(contrib[g])) & M32
+        if in_round[g] > 0 and contrib[g] == 0:
+            admit[g] = 2
+        else:
+            admit[g] = 0 if cnt >= ((int(gt.min_member[g]) - int(gt.scheduled[g])) & M32) else 1
+
+    def key(p):  # Compare's lexicographic key (core.go:379-408); lister misses after the resolvable groups
+        g = int(pt.gid[p])
+        if g == -1:
+            return (-int(pt.priority[p]), 0, 0, 0, int(pt.ts_ns[p]))
+        miss = g < 0 or g >= G or bool(pt.flags[p] & 0x08)
+        creation = (1 << 63) - 1 if miss else int(gt.creation_ns[g])
+        name = 0 if miss else -int(gt.name_rank[g])
+        return (-int(pt.priority[p]), 1, creation, name, int(pt.ts_ns[p]))
+
+    order = np.array(sorted(range(P), key=key), np.uint32)   # sorted() is stable
+    rank = np.zeros(P, np.uint32)
+    r = 0
+    for i in range(P):
+        if i and key(int(order[i])) != key(int(order[i - 1])):
+            r += 1
+        rank[order[i]] = r
+    return dict(fit=fit, score=score, feasible_count=feasible, best_node=best_node, best_score=best_score,
+                admit=admit, order=order, rank=rank)
+
+
 def get_left_resource(node):  # core.go:436-475
     """None when the reference returns nil (info == nil).  The scalar loop at :465-472 ranges over the
     Clone of a zero Resource, whose map is nil: it never runs, so no scalar key is ever reported."""

@@ -31,6 +31,20 @@ def test_replay_matches_python_restatement(oracle, seed):
     np.testing.assert_array_equal(ready, c)
 
 
+@pytest.mark.parametrize("seed", range(9))
+def test_whole_round_matches_python_restatement(oracle, seed):
+    # fit matrix, score, per-pod reductions, Permit verdicts and the queue order of one snapshot round
+    snap = random_snapshot(3200 + seed, P=60, N=20 + 2 * seed, G=9, L=[4, 5, 6, 9][seed % 4],
+                           case=["mixed", "A", "B"][seed % 3])
+    r = oracle.round(snap, want_bitmap=True, want_score=True)
+    py = pyref.round_outputs(snap)
+    bits = np.unpackbits(r.fit_bitmap.view(np.uint8), axis=1, bitorder="little")[:, :snap.nodes.n].astype(bool)
+    np.testing.assert_array_equal(bits, py["fit"])
+    np.testing.assert_array_equal(r.score, py["score"])
+    for k in ("feasible_count", "best_node", "best_score", "admit", "order", "rank"):
+        np.testing.assert_array_equal(getattr(r, k), py[k], err_msg=k)
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_filter_matrix_matches_python_restatement(oracle, seed):
     # Filter / computeResourceSatisfied / getLeftResource (core.go:170-191, 436-475, 514-564)
