@@ -314,7 +314,10 @@ typedef enum {
   BS_BUF_GATHERED_ADMIT = 6
 } bs_buffer;
 int bs_device_buffer(bs_engine* e, int which, void** dev_ptr, size_t* bytes);
-void* bs_stream(bs_engine* e); /* the cudaStream_t every kernel is launched on */
+void* bs_stream(bs_engine* e); /* the cudaStream_t a round is ordered on: uploads, the fit kernel and the
+                                  verdicts run on it, and the two side streams of a round (PreFilter chain,
+                                  queue sort) join it before the round ends, so work enqueued on it after
+                                  bs_evaluate_async sees every result */
 /* copy rows [pod0, pod0+n) of the fit bitmap / score matrix to the host */
 int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words);
 int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores);
