@@ -143,6 +143,70 @@ static int cmd_readme() {
   return 0;
 }
 
+static int cmd_pack_semantics() {
+  // a hand-built scenario for the packer's encodings: selectors / labels, taints / tolerations
+  // (ToleratesTaint), node guards, Limits-vs-Requests (quirk Q10), group lookup, bare-name ranks,
+  // wait time, and the sequential OccupiedBy rule of fillOccupiedObj (core.go:494-511)
+  Node n0; n0.name = "n0"; n0.labels = {{"zone", "a"}, {"disk", "ssd"}};
+  n0.taints = {{"dedicated", "batch", "NoSchedule"}, {"soft", "x", "PreferNoSchedule"}};
+  n0.allocatable = {{"cpu", "4"}, {"memory", "8Gi"}, {"pods", "110"}, {"nvidia.com/gpu", "2"}, {"hugepages-2Mi", "1Gi"}};
+  NodeInfo i0; i0.node = &n0; i0.requested = {{"cpu", "500m"}, {"nvidia.com/gpu", "1"}}; i0.num_pods = 3;
+  Node n1; n1.name = "n1"; n1.labels = {{"zone", "b"}}; n1.taints = {{"gpu", "", "NoExecute"}}; n1.unschedulable = true;
+  n1.allocatable = {{"cpu", "8"}};
+  NodeInfo i1; i1.node = &n1;
+  NodeInfo i2;                      // info.Node() == nil
+  Node n4; n4.name = "n4"; n4.labels = {{"zone", "a"}}; n4.allocatable = {{"cpu", "1"}};
+  NodeInfo i4; i4.node = &n4; i4.taints_error = true;
+  std::vector<const NodeInfo*> snap = {&i0, &i1, &i2, nullptr, &i4};
+
+  auto mkpod = [](const char* name, const char* group) {
+    Pod p; p.ns = "default"; p.name = name; p.uid = std::string("uid-") + name;
+    if (group) p.labels[kPodGroupLabel] = group;
+    return p;
+  };
+  Pod p0 = mkpod("p0", "pgA");
+  p0.node_selector = {{"zone", "a"}};
+  p0.tolerations = {{"dedicated", "Equal", "batch", "NoSchedule"}};
+  { Container c; c.has_limits = true; c.limits = {{"cpu", "1"}, {"memory", "1Gi"}}; c.requests = {{"cpu", "2"}}; p0.containers = {c}; }
+  Pod p1 = mkpod("p1", "pgA");
+  p1.tolerations = {{"", "Exists", "", ""}};
+  { Container c; c.requests = {{"cpu", "250m"}, {"nvidia.com/gpu", "1"}}; p1.containers = {c, c}; }
+  p1.owner_uids = {"u2", "u1"};
+  p1.priority = 7; p1.queue_ts_ns = 42;
+  Pod p2 = mkpod("p2", "missing");
+  Pod p3 = mkpod("p3", nullptr);
+  { Container c; c.has_limits = true; c.requests = {{"cpu", "3"}}; p3.containers = {c}; }   // Limits non-nil but empty
+  Pod p4 = mkpod("p4", "pgB"); p4.owner_uids = {"u9"};
+  Pod p5 = mkpod("p5", "pgB");
+  Pod p6 = mkpod("p6", "pgA"); p6.owner_uids = {"u1", "u2"};      // matches what p1 left behind
+  std::vector<const Pod*> pending = {&p0, &p1, &p2, &p3, &p4, &p5, &p6};
+
+  std::vector<PodGroup> groups(4);
+  groups[0].ns = "default"; groups[0].name = "pgA"; groups[0].min_member = 2; groups[0].creation_ns = 100;
+  groups[1].ns = "default"; groups[1].name = "pgB"; groups[1].min_member = 3; groups[1].creation_ns = 200;
+  groups[1].has_min_resources = true; groups[1].min_resources = {{"cpu", "2"}, {"nvidia.com/gpu", "1"}};
+  groups[1].occupied_by = "u1,u2"; groups[1].max_schedule_time_ns = 5000000000ll; groups[1].scheduled = 1;
+  groups[2].ns = "other"; groups[2].name = "pgA"; groups[2].min_member = 1; groups[2].creation_ns = 300;
+  groups[3].ns = "default"; groups[3].name = "pgC"; groups[3].min_member = 4; groups[3].creation_ns = 50;
+  PackedSnapshot ps;
+  Status st = BatchSchedulingPlugin::Pack(snap, pending, groups, {1, 0, 0, 0}, {0, 0, 0, BS_GROUP_SCHEDULED}, {}, 7000000000ll, &ps);
+  if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+  printf("{\"lanes\": %u,\n\"scalars\": [", ps.lanes);
+  for (size_t i = 0; i < ps.scalar_names.size(); ++i) printf("%s\"%s\"", i ? ", " : "", ps.scalar_names[i].c_str());
+  printf("],\n");
+  print_arr("alloc", ps.alloc); print_arr("requested", ps.requested); print_arr("pod_count", ps.pod_count);
+  print_arr("alloc_present", ps.alloc_present); print_arr("req_present", ps.req_present);
+  print_arr("label_mask", ps.label_mask); print_arr("taint_mask", ps.taint_mask); print_arr("node_flags", ps.node_flags);
+  print_arr("req", ps.req); print_arr("pod_req_present", ps.pod_req_present); print_arr("gid", ps.gid);
+  print_arr("sel_mask", ps.sel_mask); print_arr("tol_mask", ps.tol_mask); print_arr("priority", ps.priority);
+  print_arr("ts_ns", ps.ts_ns); print_arr("pod_flags", ps.pod_flags);
+  print_arr("min_member", ps.min_member); print_arr("scheduled", ps.scheduled); print_arr("matched", ps.matched);
+  print_arr("group_flags", ps.group_flags); print_arr("min_res", ps.min_res); print_arr("min_res_present", ps.min_res_present);
+  print_arr("creation_ns", ps.creation_ns); print_arr("name_rank", ps.name_rank); print_arr("wait_ns", ps.wait_ns, true);
+  printf("}\n");
+  return 0;
+}
+
 static int cmd_readme_replay() {
   // the same race in ONE call: all ten pods pending, the device walks the queue (bs_replay)
   Node node; node.name = "node1";
@@ -226,6 +290,7 @@ int main(int argc, char** argv) {
   if (argc < 2) return 2;
   if (!strcmp(argv[1], "quantity")) return cmd_quantity(argc, argv);
   if (!strcmp(argv[1], "pack_core_test")) return cmd_pack_core_test();
+  if (!strcmp(argv[1], "pack_semantics")) return cmd_pack_semantics();
   if (!strcmp(argv[1], "readme")) return cmd_readme();
   if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));

@@ -59,6 +59,40 @@ def test_packer_core_test_go(plugin_bin, snapshot_mod):
     assert out["gid"] == [-1, -1, -1]
 
 
+def test_packer_semantics(plugin_bin, snapshot_mod):
+    """Hand-built objects through the C++ packer: every encoding the engine's tables rely on."""
+    S = snapshot_mod
+    o = _run(plugin_bin, "pack_semantics")
+    N, P, G, L = 5, 7, 4, 6
+    assert o["lanes"] == L and o["scalars"] == ["nvidia.com/gpu", "hugepages-2Mi"]   # first-seen order, IsScalarResourceName
+    alloc = np.array(o["alloc"]).reshape(L, N)
+    requested = np.array(o["requested"]).reshape(L, N)
+    assert alloc[:, 0].tolist() == [4000, 8 << 30, 0, 110, 2, 1 << 30] and alloc[0].tolist() == [4000, 8000, 0, 0, 1000]
+    assert requested[:, 0].tolist() == [500, 0, 0, 0, 1, 0] and o["pod_count"] == [3, 0, 0, 0, 0]
+    assert o["alloc_present"] == [0x30, 0, 0, 0, 0] and o["req_present"] == [0x10, 0, 0, 0, 0]
+    # nodeSelector pairs -> label bits; only NoSchedule / NoExecute taints get a bit (PodToleratesNodeTaints)
+    assert o["label_mask"] == [1, 0, 0, 0, 1] and o["taint_mask"] == [1, 2, 0, 0, 0]
+    assert o["node_flags"] == [0, S.NODE_UNSCHEDULABLE, S.NODE_NO_NODE, S.NODE_NIL, S.NODE_TAINTS_ERR]
+    req = np.array(o["req"]).reshape(L, P)
+    assert req[:, 0].tolist() == [1000, 1 << 30, 0, 0, 0, 0]      # Limits win over Requests when non-nil (Q10)
+    assert req[:, 1].tolist() == [500, 0, 0, 0, 2, 0]             # two containers summed, Requests (Limits nil)
+    assert req[:, 3].tolist() == [0] * L                          # Limits non-nil but empty: demand 0
+    assert o["pod_req_present"] == [0, 0x10, 0, 0, 0, 0, 0]
+    assert o["gid"] == [0, 0, S.GID_MISSING, S.GID_NONE, 1, 1, 0]
+    assert o["sel_mask"] == [1, 0, 0, 0, 0, 0, 0]
+    assert o["tol_mask"][:2] == [1, 3]                            # Equal key/value/effect; bare Exists tolerates all
+    assert o["priority"][1] == 7 and o["ts_ns"][1] == 42
+    # fillOccupiedObj order: p1 is the first pod with owner refs -> OccupiedBy "u1,u2" (sorted); p6 matches it;
+    # pgB is occupied by "u1,u2": other owners -> mismatch, no owners -> the "no refs" message
+    assert o["pod_flags"] == [0, 0, S.POD_LISTER_MISS, 0, S.POD_OCC_MISMATCH, S.POD_OCC_NOREFS, 0]
+    assert o["min_member"] == [2, 3, 1, 4] and o["scheduled"] == [0, 1, 0, 0] and o["matched"] == [1, 0, 0, 0]
+    assert o["group_flags"] == [0, S.GROUP_HAS_MINRES, 0, S.GROUP_SCHEDULED]
+    min_res = np.array(o["min_res"]).reshape(L, G)
+    assert min_res[:, 1].tolist() == [2000, 0, 0, 0, 1, 0] and o["min_res_present"] == [0, 0x10, 0, 0]
+    assert o["name_rank"] == [0, 1, 0, 2]                         # bare name, namespace ignored (core.go:404)
+    assert o["wait_ns"] == [7 * 10**9, 5 * 10**9, 7 * 10**9, 7 * 10**9]   # Spec.MaxScheduleTime wins (k8s.go:82-91)
+
+
 def test_packer_throughput_smoke(plugin_bin):
     out = _run(plugin_bin, "bench_pack", "500", "4000", "500")
     assert out["lanes"] == 5 and out["pack_ms"] > 0
