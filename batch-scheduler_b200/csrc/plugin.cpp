@@ -317,6 +317,9 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
       if (t.effect == "NoSchedule" || t.effect == "NoExecute") taint_bit(t);   // PodToleratesNodeTaints filter
   }
   if (taints.size() > 64) { bad.message = "more than 64 distinct taints in one round"; return bad; }
+  ps.sel_pairs.resize(sel_bit.size());
+  for (auto& kv : sel_bit) ps.sel_pairs[kv.second] = kv.first;
+  ps.taint_list = taints;
   std::atomic<int> err{0};
 #pragma omp parallel for num_threads(T) schedule(static)
   for (uint32_t i = 0; i < N; ++i) {
@@ -593,6 +596,107 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
     }
     if (gs.pg.occupied_by.empty() && !p.owner_uids.empty()) gs.pg.occupied_by = joined_sorted(p.owner_uids);  // :496-500
   }
+  return Status{};
+}
+
+Status BatchSchedulingPlugin::PackNodeRows(const PackedSnapshot& ctx, const std::vector<const NodeInfo*>& rows,
+                                           PackedSnapshot* out, bool* needs_full) {
+  if (!out || !needs_full) return Status{BS_CODE_ERROR, "PackNodeRows: null output"};
+  *needs_full = false;
+  PackedSnapshot& ps = *out;
+  ps = PackedSnapshot();
+  const uint32_t n = (uint32_t)rows.size(), L = ctx.lanes;
+  ps.lanes = L; ps.scalar_names = ctx.scalar_names; ps.sel_pairs = ctx.sel_pairs; ps.taint_list = ctx.taint_list;
+  ps.n_nodes = n;
+  LaneTable lt;   // the lanes of the full pack, nothing may be added
+  for (auto& nm : ctx.scalar_names) lt.lane(nm, true);
+  auto known = [&](const ResourceList& rl) {
+    for (auto& kv : rl) {
+      const std::string& nm = kv.first;
+      if (nm == "cpu" || nm == "memory" || nm == "ephemeral-storage" || nm == "pods") continue;
+      if (IsScalarResourceName(nm) && lt.lane(nm, false) < 0) return false;
+    }
+    return true;
+  };
+  ps.alloc.assign((size_t)L * n, 0); ps.requested.assign((size_t)L * n, 0);
+  ps.pod_count.assign(n, 0); ps.alloc_present.assign(n, 0); ps.req_present.assign(n, 0);
+  ps.label_mask.assign(n, 0); ps.taint_mask.assign(n, 0); ps.node_flags.assign(n, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    const NodeInfo* ni = rows[i];
+    if (!ni) { ps.node_flags[i] = BS_NODE_NIL; continue; }              // core.go:606
+    if (!known(ni->requested) || (ni->node && !known(ni->node->allocatable))) { *needs_full = true; return Status{}; }
+    int64_t tmp[BS_MAX_LANES] = {};
+    if (!ni->node) ps.node_flags[i] |= BS_NODE_NO_NODE;                 // core.go:610
+    if (ni->taints_error) ps.node_flags[i] |= BS_NODE_TAINTS_ERR;       // core.go:639
+    ps.pod_count[i] = ni->num_pods;
+    uint32_t pres = 0;
+    if (!add_list(lt, ni->requested, tmp, &pres)) return Status{BS_CODE_ERROR, "bad quantity in requested"};
+    for (uint32_t d = 0; d < L; ++d) ps.requested[(size_t)d * n + i] = tmp[d];
+    ps.req_present[i] = pres;
+    if (!ni->node) continue;
+    const Node& nd = *ni->node;
+    if (nd.unschedulable) ps.node_flags[i] |= BS_NODE_UNSCHEDULABLE;    // core.go:615
+    pres = 0;
+    std::fill(tmp, tmp + BS_MAX_LANES, 0);
+    if (!add_list(lt, nd.allocatable, tmp, &pres)) return Status{BS_CODE_ERROR, "bad quantity in allocatable"};
+    for (uint32_t d = 0; d < L; ++d) ps.alloc[(size_t)d * n + i] = tmp[d];
+    ps.alloc_present[i] = pres;
+    for (size_t b = 0; b < ctx.sel_pairs.size(); ++b) {
+      auto it = nd.labels.find(ctx.sel_pairs[b].first);
+      if (it != nd.labels.end() && it->second == ctx.sel_pairs[b].second) ps.label_mask[i] |= 1ull << b;
+    }
+    for (auto& t : nd.taints) {
+      if (t.effect != "NoSchedule" && t.effect != "NoExecute") continue;   // PodToleratesNodeTaints filter
+      bool found = false;
+      for (size_t b = 0; b < ctx.taint_list.size() && !found; ++b)
+        if (ctx.taint_list[b].key == t.key && ctx.taint_list[b].value == t.value && ctx.taint_list[b].effect == t.effect) {
+          ps.taint_mask[i] |= 1ull << b;
+          found = true;
+        }
+      if (!found) { *needs_full = true; return Status{}; }   // a taint no toleration mask of the round knows
+    }
+  }
+  return Status{};
+}
+
+Status BatchSchedulingPlugin::UpdateNodes(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed) {
+  if (!eng_) return Status{BS_CODE_ERROR, "UpdateNodes: no round has been started"};
+  if (changed.empty()) return Status{};
+  std::vector<const NodeInfo*> rows(changed.size());
+  std::vector<uint32_t> idx(changed.size());
+  for (size_t k = 0; k < changed.size(); ++k) {
+    if (changed[k].first >= packed_.n_nodes) return Status{BS_CODE_ERROR, "UpdateNodes: index outside the snapshot"};
+    idx[k] = changed[k].first;
+    rows[k] = changed[k].second;
+  }
+  PackedSnapshot delta;
+  bool needs_full = false;
+  Status st = PackNodeRows(packed_, rows, &delta, &needs_full);
+  if (!st.ok()) return st;
+  if (needs_full) return Status{BS_CODE_ERROR, "full repack needed"};
+  bs_node_table t = delta.node_table();
+  const int rc = bs_update_nodes(eng_, idx.data(), &t);
+  if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
+  // keep the host copy of the round in step with the device table
+  const uint32_t N = packed_.n_nodes, n = delta.n_nodes, L = packed_.lanes;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t i = idx[k];
+    for (uint32_t d = 0; d < L; ++d) {
+      packed_.alloc[(size_t)d * N + i] = delta.alloc[(size_t)d * n + k];
+      packed_.requested[(size_t)d * N + i] = delta.requested[(size_t)d * n + k];
+    }
+    packed_.pod_count[i] = delta.pod_count[k]; packed_.alloc_present[i] = delta.alloc_present[k];
+    packed_.req_present[i] = delta.req_present[k]; packed_.label_mask[i] = delta.label_mask[k];
+    packed_.taint_mask[i] = delta.taint_mask[k]; packed_.node_flags[i] = delta.node_flags[k];
+  }
+  // the round's decisions follow the new snapshot: same pods, same groups, same result vectors
+  bs_results r{};
+  r.prefilter = prefilter_.data(); r.feasible_count = feasible_.data(); r.best_node = best_node_.data();
+  r.admit = admit_.data(); r.new_denied = new_denied_.data(); r.order = order_.data(); r.rank = rank_.data();
+  const int rc2 = bs_evaluate(eng_, &r);
+  if (rc2) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc2) + " (" + bs_last_error(eng_) + ")"};
+  for (uint32_t g = 0; g < packed_.n_groups; ++g)
+    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns_);   // core.go:142,163
   return Status{};
 }
 

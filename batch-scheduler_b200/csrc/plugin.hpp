@@ -110,6 +110,10 @@ struct PackedSnapshot {
   std::vector<int64_t> min_res, creation_ns, wait_ns;
   std::vector<uint64_t> rep_sel, rep_tol;
   uint32_t n_nodes = 0, n_pods = 0, n_groups = 0;
+  // dictionaries of the round: bit b of the label / selector masks and of the taint / toleration
+  // masks (needed to pack changed rows later with the same encoding, PackNodeRows)
+  std::vector<std::pair<std::string, std::string>> sel_pairs;
+  std::vector<Taint> taint_list;
 
   bs_node_table node_table() const;
   bs_pod_table pod_table() const;
@@ -172,6 +176,16 @@ class BatchSchedulingPlugin {
   double last_pack_ms() const { return last_pack_ms_; }
   double last_device_ms() const { return last_device_ms_; }
   bs_engine* engine() const { return eng_; }
+
+  // Incremental snapshot update: between cycles the informer touches a few
+  // NodeInfos.  PackNodeRows re-packs just those with the encoding of the last full pack (`ctx`) into
+  // a compact node table; *needs_full is set when a row brings a scalar resource or a NoSchedule /
+  // NoExecute taint the dictionaries of `ctx` do not hold (then only a full Pack is correct).
+  // UpdateNodes does that for the current round and scatters the rows into the resident device
+  // table (bs_update_nodes); `changed` pairs the snapshot index with the new NodeInfo.
+  static Status PackNodeRows(const PackedSnapshot& ctx, const std::vector<const NodeInfo*>& rows, PackedSnapshot* out,
+                             bool* needs_full);
+  Status UpdateNodes(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed);
 
   // the packer alone (no GPU): objects -> tables
   static Status Pack(const std::vector<const NodeInfo*>& snapshot, const std::vector<const Pod*>& pending,

@@ -207,6 +207,115 @@ static int cmd_pack_semantics() {
   return 0;
 }
 
+static int cmd_pack_delta() {
+  // PackNodeRows: changed NodeInfos packed with the dictionaries of a full pack == the same rows of a
+  // full re-pack of the modified snapshot; an unknown taint / scalar resource asks for a full pack
+  const int N = 300, P = 400, G = 40;
+  std::vector<Node> nodes(N);
+  std::vector<NodeInfo> infos(N);
+  for (int i = 0; i < N; ++i) {
+    nodes[i].name = "node-" + std::to_string(i);
+    nodes[i].allocatable = {{"cpu", std::to_string(16 + i % 5 * 16)}, {"memory", std::to_string(64 + i % 7) + "Gi"},
+                            {"ephemeral-storage", "500Gi"}, {"pods", "110"}, {"nvidia.com/gpu", std::to_string(i % 3 * 4)}};
+    nodes[i].labels = {{"zone", "z" + std::to_string(i % 4)}, {"disk", i % 2 ? "ssd" : "hdd"}};
+    if (i % 20 == 0) nodes[i].taints = {{"dedicated", "batch", "NoSchedule"}};
+    if (i % 45 == 7) nodes[i].taints.push_back({"maint", "", "NoExecute"});
+    infos[i].node = &nodes[i];
+    infos[i].requested = {{"cpu", std::to_string(100 * (i % 90)) + "m"}, {"memory", std::to_string(i % 50) + "Gi"},
+                          {"nvidia.com/gpu", std::to_string(i % 3)}};
+    infos[i].num_pods = i % 60;
+  }
+  std::vector<PodGroup> groups(G);
+  for (int g = 0; g < G; ++g) { groups[g].ns = "default"; groups[g].name = "pg-" + std::to_string(g); groups[g].min_member = 1 + g % 8; }
+  std::vector<Pod> pods(P);
+  for (int i = 0; i < P; ++i) {
+    Pod& p = pods[i];
+    p.ns = "default"; p.name = "pod-" + std::to_string(i); p.uid = "uid-" + std::to_string(i);
+    p.labels[kPodGroupLabel] = "pg-" + std::to_string(i % G);
+    Container c; c.has_limits = true; c.limits = {{"cpu", "500m"}, {"memory", "1Gi"}};
+    p.containers = {c};
+    if (i % 10 == 0) p.node_selector = {{"disk", "ssd"}};
+    if (i % 13 == 0) p.node_selector = {{"zone", "z2"}};
+    if (i % 7 == 0) p.tolerations = {{"dedicated", "Equal", "batch", "NoSchedule"}};
+  }
+  std::vector<const NodeInfo*> snap(N);
+  std::vector<const Pod*> pend(P);
+  for (int i = 0; i < N; ++i) snap[i] = &infos[i];
+  for (int i = 0; i < P; ++i) pend[i] = &pods[i];
+  PackedSnapshot before;
+  Status st = BatchSchedulingPlugin::Pack(snap, pend, groups, {}, {}, {}, 0, &before);
+  if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+
+  // the informer touched these NodeInfos (first-seen order of the taints is left as it was)
+  std::vector<uint32_t> idx = {3, 5, 20, 21, 64, 100, 101, 150, 199, 250, 299};
+  std::vector<Node> nodes2 = nodes;
+  std::vector<NodeInfo> infos2 = infos;
+  for (int i = 0; i < N; ++i) if (infos2[i].node) infos2[i].node = &nodes2[i];
+  infos2[3].requested = {{"cpu", "7777m"}, {"memory", "3Gi"}};                 // the gpu key disappears from requested
+  infos2[3].num_pods = 61;
+  nodes2[5].taints = {{"dedicated", "batch", "NoSchedule"}};                    // gains a known taint
+  nodes2[20].taints.clear();                                                    // loses it
+  nodes2[21].labels = {{"zone", "z2"}, {"disk", "ssd"}};
+  nodes2[64].unschedulable = true;
+  infos2[100].node = nullptr;                                                   // info.Node() == nil
+  infos2[101].taints_error = true;
+  nodes2[150].allocatable = {{"cpu", "1"}, {"memory", "1Gi"}, {"pods", "1"}};   // no gpu any more
+  nodes2[199].taints = {{"maint", "", "NoExecute"}, {"soft", "x", "PreferNoSchedule"}};
+  nodes2[250].labels.clear();
+  infos2[299].requested.push_back({"nvidia.com/gpu", "3"});
+  std::vector<const NodeInfo*> snap2(N);
+  for (int i = 0; i < N; ++i) snap2[i] = &infos2[i];
+  PackedSnapshot after;
+  st = BatchSchedulingPlugin::Pack(snap2, pend, groups, {}, {}, {}, 0, &after);
+  if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+  std::vector<const NodeInfo*> rows;
+  for (uint32_t i : idx) rows.push_back(snap2[i]);
+  PackedSnapshot delta;
+  bool needs_full = true;
+  st = BatchSchedulingPlugin::PackNodeRows(before, rows, &delta, &needs_full);
+  if (!st.ok()) { fprintf(stderr, "delta failed: %s\n", st.message.c_str()); return 1; }
+  int mismatches = 0;
+  const uint32_t L = after.lanes, n = (uint32_t)idx.size();
+  for (uint32_t k = 0; k < n && !needs_full; ++k) {
+    const uint32_t i = idx[k];
+    for (uint32_t d = 0; d < L; ++d) {
+      mismatches += delta.alloc[(size_t)d * n + k] != after.alloc[(size_t)d * N + i];
+      mismatches += delta.requested[(size_t)d * n + k] != after.requested[(size_t)d * N + i];
+    }
+    mismatches += delta.pod_count[k] != after.pod_count[i];
+    mismatches += delta.alloc_present[k] != after.alloc_present[i];
+    mismatches += delta.req_present[k] != after.req_present[i];
+    mismatches += delta.label_mask[k] != after.label_mask[i];
+    mismatches += delta.taint_mask[k] != after.taint_mask[i];
+    mismatches += delta.node_flags[k] != after.node_flags[i];
+  }
+  // untouched rows of the re-pack equal the first pack (nothing else moved)
+  int untouched_diff = 0;
+  for (int i = 0; i < N; ++i) {
+    bool touched = false;
+    for (uint32_t j : idx) touched |= (int)j == i;
+    if (touched) continue;
+    for (uint32_t d = 0; d < L; ++d)
+      untouched_diff += before.alloc[(size_t)d * N + i] != after.alloc[(size_t)d * N + i] ||
+                        before.requested[(size_t)d * N + i] != after.requested[(size_t)d * N + i];
+    untouched_diff += before.label_mask[i] != after.label_mask[i] || before.taint_mask[i] != after.taint_mask[i];
+  }
+  // a taint / a scalar resource the round has never seen: only a full pack is correct
+  Node odd = nodes[9]; odd.taints = {{"brand", "new", "NoSchedule"}};
+  NodeInfo odd_info = infos[9]; odd_info.node = &odd;
+  bool full_taint = false, full_scalar = false;
+  PackedSnapshot scratch;
+  BatchSchedulingPlugin::PackNodeRows(before, {&odd_info}, &scratch, &full_taint);
+  Node odd2 = nodes[9]; odd2.allocatable.push_back({"example.com/fpga", "2"});
+  NodeInfo odd_info2 = infos[9]; odd_info2.node = &odd2;
+  BatchSchedulingPlugin::PackNodeRows(before, {&odd_info2}, &scratch, &full_scalar);
+  printf("{\"lanes\": %u, \"rows\": %u, \"needs_full\": %d, \"mismatches\": %d, \"untouched_diff\": %d, "
+         "\"sel_pairs\": %zu, \"taints\": %zu, \"full_on_new_taint\": %d, \"full_on_new_scalar\": %d}\n",
+         L, n, needs_full ? 1 : 0, mismatches, untouched_diff, before.sel_pairs.size(), before.taint_list.size(),
+         full_taint ? 1 : 0, full_scalar ? 1 : 0);
+  return 0;
+}
+
 static int cmd_readme_replay() {
   // the same race in ONE call: all ten pods pending, the device walks the queue (bs_replay)
   Node node; node.name = "node1";
@@ -291,6 +400,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "quantity")) return cmd_quantity(argc, argv);
   if (!strcmp(argv[1], "pack_core_test")) return cmd_pack_core_test();
   if (!strcmp(argv[1], "pack_semantics")) return cmd_pack_semantics();
+  if (!strcmp(argv[1], "pack_delta")) return cmd_pack_delta();
   if (!strcmp(argv[1], "readme")) return cmd_readme();
   if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));

@@ -93,6 +93,17 @@ def test_packer_semantics(plugin_bin, snapshot_mod):
     assert o["wait_ns"] == [7 * 10**9, 5 * 10**9, 7 * 10**9, 7 * 10**9]   # Spec.MaxScheduleTime wins (k8s.go:82-91)
 
 
+def test_packer_delta_rows(plugin_bin):
+    """PackNodeRows (incremental snapshot update): the NodeInfos an informer touched, packed with the
+    dictionaries of the last full pack, equal the same rows of a full re-pack; a taint or scalar resource
+    the round has never seen asks for a full pack instead."""
+    o = _run(plugin_bin, "pack_delta")
+    assert o["rows"] == 11 and o["needs_full"] == 0
+    assert o["mismatches"] == 0 and o["untouched_diff"] == 0
+    assert o["sel_pairs"] == 2 and o["taints"] == 2
+    assert o["full_on_new_taint"] == 1 and o["full_on_new_scalar"] == 1
+
+
 def test_packer_throughput_smoke(plugin_bin):
     out = _run(plugin_bin, "bench_pack", "500", "4000", "500")
     assert out["lanes"] == 5 and out["pack_ms"] > 0
