@@ -700,6 +700,116 @@ Status BatchSchedulingPlugin::UpdateNodes(const std::vector<std::pair<uint32_t, 
   return Status{};
 }
 
+Status BatchSchedulingPlugin::PackGroupRows(const PackedSnapshot& ctx, const std::vector<GroupDelta>& rows,
+                                            int64_t default_wait_ns, PackedSnapshot* out, bool* needs_full) {
+  if (!out || !needs_full) return Status{BS_CODE_ERROR, "PackGroupRows: null output"};
+  *needs_full = false;
+  PackedSnapshot& ps = *out;
+  ps = PackedSnapshot();
+  const uint32_t n = (uint32_t)rows.size(), L = ctx.lanes;
+  ps.lanes = L; ps.scalar_names = ctx.scalar_names; ps.sel_pairs = ctx.sel_pairs; ps.taint_list = ctx.taint_list;
+  ps.n_groups = n;
+  LaneTable lt;
+  for (auto& nm : ctx.scalar_names) lt.lane(nm, true);
+  ps.min_member.assign(n, 0); ps.scheduled.assign(n, 0); ps.matched.assign(n, 0); ps.group_flags.assign(n, 0);
+  ps.min_res.assign((size_t)L * n, 0); ps.min_res_present.assign(n, 0); ps.rep_sel.assign(n, 0);
+  ps.rep_tol.assign(n, 0); ps.creation_ns.assign(n, 0); ps.name_rank.assign(n, 0); ps.wait_ns.assign(n, 0);
+  for (uint32_t k = 0; k < n; ++k) {
+    const GroupDelta& gd = rows[k];
+    if (!gd.pg || gd.index >= ctx.n_groups) return Status{BS_CODE_ERROR, "PackGroupRows: bad row"};
+    const PodGroup& pg = *gd.pg;
+    ps.min_member[k] = pg.min_member;
+    ps.scheduled[k] = pg.scheduled;
+    ps.matched[k] = gd.matched;
+    ps.group_flags[k] = gd.flags & (BS_GROUP_SCHEDULED | BS_GROUP_HAS_POD | BS_GROUP_DENIED);
+    ps.creation_ns[k] = pg.creation_ns;
+    ps.name_rank[k] = ctx.name_rank[gd.index];   // the name of an object does not change
+    ps.wait_ns[k] = pg.max_schedule_time_ns >= 0 ? pg.max_schedule_time_ns : default_wait_ns;   // k8s.go:82-91
+    if (pg.has_min_resources) {
+      for (auto& kv : pg.min_resources) {
+        const std::string& nm = kv.first;
+        if (nm == "cpu" || nm == "memory" || nm == "ephemeral-storage" || nm == "pods") continue;
+        if (IsScalarResourceName(nm) && lt.lane(nm, false) < 0) { *needs_full = true; return Status{}; }
+      }
+      ps.group_flags[k] |= BS_GROUP_HAS_MINRES;
+      int64_t tmp[BS_MAX_LANES] = {};
+      uint32_t pres = 0;
+      if (!add_list(lt, pg.min_resources, tmp, &pres)) return Status{BS_CODE_ERROR, "bad quantity in MinResources"};
+      for (uint32_t d = 0; d < L; ++d) ps.min_res[(size_t)d * n + k] = tmp[d];
+      ps.min_res_present[k] = pres;
+    }
+    if (gd.rep_pod) {
+      ps.group_flags[k] |= BS_GROUP_HAS_POD;
+      for (auto& kv : gd.rep_pod->node_selector) {
+        bool found = false;
+        for (size_t b = 0; b < ctx.sel_pairs.size() && !found; ++b)
+          if (ctx.sel_pairs[b] == std::pair<std::string, std::string>(kv.first, kv.second)) {
+            ps.rep_sel[k] |= 1ull << b;
+            found = true;
+          }
+        if (!found) { *needs_full = true; return Status{}; }   // the nodes' label masks have no bit for this pair
+      }
+      for (size_t b = 0; b < ctx.taint_list.size(); ++b)
+        for (auto& t : gd.rep_pod->tolerations)
+          if (tolerates(t, ctx.taint_list[b])) { ps.rep_tol[k] |= 1ull << b; break; }
+    }
+  }
+  return Status{};
+}
+
+Status BatchSchedulingPlugin::UpdateGroups(const std::vector<std::string>& ns_names, int64_t now_ns) {
+  if (!eng_) return Status{BS_CODE_ERROR, "UpdateGroups: no round has been started"};
+  if (ns_names.empty()) return Status{};
+  now_ns_ = now_ns;
+  std::vector<GroupDelta> rows;
+  std::vector<uint32_t> idx;
+  for (auto& name : ns_names) {
+    const int gi = group_index(name);
+    auto it = groups_.find(name);
+    if (gi < 0 || it == groups_.end()) return Status{BS_CODE_ERROR, "UpdateGroups: " + name + " is not part of the round (full repack needed)"};
+    GroupState& gs = it->second;
+    for (auto m = gs.matched_uid_expiry.begin(); m != gs.matched_uid_expiry.end();)
+      m = m->second <= now_ns ? gs.matched_uid_expiry.erase(m) : std::next(m);
+    auto de = deny_expiry_.find(name);
+    uint8_t fl = 0;
+    if (gs.scheduled_flag) fl |= BS_GROUP_SCHEDULED;
+    if (de != deny_expiry_.end() && de->second > now_ns) fl |= BS_GROUP_DENIED;
+    GroupDelta gd;
+    gd.index = (uint32_t)gi; gd.pg = &gs.pg; gd.matched = (uint32_t)gs.matched_uid_expiry.size(); gd.flags = fl;
+    gd.rep_pod = gs.has_pod ? &gs.rep_pod : nullptr;
+    rows.push_back(gd);
+    idx.push_back((uint32_t)gi);
+  }
+  PackedSnapshot delta;
+  bool needs_full = false;
+  Status st = PackGroupRows(packed_, rows, max_schedule_time_ns_, &delta, &needs_full);
+  if (!st.ok()) return st;
+  if (needs_full) return Status{BS_CODE_ERROR, "full repack needed"};
+  bs_group_table t = delta.group_table();
+  int rc = bs_update_groups(eng_, idx.data(), &t);
+  if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
+  const uint32_t G = packed_.n_groups, n = delta.n_groups, L = packed_.lanes;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t g = idx[k];
+    packed_.min_member[g] = delta.min_member[k]; packed_.scheduled[g] = delta.scheduled[k];
+    packed_.matched[g] = delta.matched[k]; packed_.group_flags[g] = delta.group_flags[k];
+    for (uint32_t d = 0; d < L; ++d) packed_.min_res[(size_t)d * G + g] = delta.min_res[(size_t)d * n + k];
+    packed_.min_res_present[g] = delta.min_res_present[k]; packed_.rep_sel[g] = delta.rep_sel[k];
+    packed_.rep_tol[g] = delta.rep_tol[k]; packed_.creation_ns[g] = delta.creation_ns[k];
+    packed_.wait_ns[g] = delta.wait_ns[k];
+  }
+  if ((rc = bs_set_wait_time(eng_, max_schedule_time_ns_, packed_.wait_ns.data(), G)))
+    return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+  bs_results r{};
+  r.prefilter = prefilter_.data(); r.feasible_count = feasible_.data(); r.best_node = best_node_.data();
+  r.admit = admit_.data(); r.new_denied = new_denied_.data(); r.order = order_.data(); r.rank = rank_.data();
+  if ((rc = bs_evaluate(eng_, &r)))
+    return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
+  for (uint32_t g = 0; g < G; ++g)
+    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns_);   // core.go:142,163
+  return Status{};
+}
+
 Status BatchSchedulingPlugin::ReplayQueue(std::vector<ReplayDecision>* out) {
   if (!out) return Status{BS_CODE_ERROR, "ReplayQueue: null output"};
   if (!eng_) return Status{BS_CODE_ERROR, "ReplayQueue: no round has been started"};

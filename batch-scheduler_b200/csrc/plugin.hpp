@@ -186,6 +186,22 @@ class BatchSchedulingPlugin {
   static Status PackNodeRows(const PackedSnapshot& ctx, const std::vector<const NodeInfo*>& rows, PackedSnapshot* out,
                              bool* needs_full);
   Status UpdateNodes(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed);
+  // The same for PodGroup state (cache.go:52-67): one changed group = its table index, the object, the
+  // unexpired matched count, the SCHEDULED / HAS_POD / DENIED flags and the representative pod (or null).
+  // Names are immutable, so the bare-name rank is taken over from `ctx`.  needs_full: MinResources or the
+  // representative pod use a scalar resource / nodeSelector pair the round's dictionaries do not hold.
+  struct GroupDelta {
+    uint32_t index = 0;
+    const PodGroup* pg = nullptr;
+    uint32_t matched = 0;
+    uint8_t flags = 0;
+    const Pod* rep_pod = nullptr;
+  };
+  static Status PackGroupRows(const PackedSnapshot& ctx, const std::vector<GroupDelta>& rows, int64_t default_wait_ns,
+                              PackedSnapshot* out, bool* needs_full);
+  // re-derives the named groups ("namespace/name") from the plugin's caches and scatters their rows
+  // into the resident device table (bs_update_groups), then re-evaluates the round
+  Status UpdateGroups(const std::vector<std::string>& ns_names, int64_t now_ns);
 
   // the packer alone (no GPU): objects -> tables
   static Status Pack(const std::vector<const NodeInfo*>& snapshot, const std::vector<const Pod*>& pending,

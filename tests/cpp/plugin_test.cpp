@@ -316,6 +316,98 @@ static int cmd_pack_delta() {
   return 0;
 }
 
+static int cmd_pack_group_delta() {
+  // PackGroupRows: changed PodGroup rows packed with the dictionaries of a full pack == the same rows
+  // of a full re-pack; representative-pod masks against the round's selector / taint bits
+  Node n0; n0.name = "n0"; n0.labels = {{"disk", "ssd"}, {"zone", "a"}};
+  n0.taints = {{"dedicated", "batch", "NoSchedule"}};
+  n0.allocatable = {{"cpu", "64"}, {"memory", "256Gi"}, {"pods", "110"}, {"nvidia.com/gpu", "8"}};
+  NodeInfo i0; i0.node = &n0; i0.requested = {{"cpu", "1"}};
+  const int G = 30, P = 60;
+  std::vector<PodGroup> groups(G);
+  for (int g = 0; g < G; ++g) {
+    groups[g].ns = g % 2 ? "default" : "batch"; groups[g].name = "pg-" + std::to_string(g % 17);   // shared bare names
+    groups[g].min_member = 1 + g % 5; groups[g].creation_ns = 1000 + g;
+    if (g % 3 == 0) { groups[g].has_min_resources = true; groups[g].min_resources = {{"cpu", "2"}, {"nvidia.com/gpu", "1"}}; }
+  }
+  std::vector<Pod> pods(P);
+  for (int i = 0; i < P; ++i) {
+    pods[i].ns = "default"; pods[i].name = "p" + std::to_string(i); pods[i].uid = "u" + std::to_string(i);
+    Container c; c.requests = {{"cpu", "1"}}; pods[i].containers = {c};
+    if (i % 4 == 0) pods[i].node_selector = {{"disk", "ssd"}};
+    if (i % 6 == 0) pods[i].node_selector = {{"zone", "a"}};
+  }
+  std::vector<const Pod*> pend(P);
+  for (int i = 0; i < P; ++i) pend[i] = &pods[i];
+  std::vector<uint32_t> matched(G, 0);
+  std::vector<uint8_t> flags(G, 0);
+  PackedSnapshot before;
+  Status st = BatchSchedulingPlugin::Pack({&i0}, pend, groups, matched, flags, {}, 9000000000ll, &before);
+  if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+  // what moved between two cycles
+  std::vector<uint32_t> idx = {0, 3, 7, 8, 19, 29};
+  std::vector<PodGroup> groups2 = groups;
+  std::vector<uint32_t> matched2 = matched;
+  std::vector<uint8_t> flags2 = flags;
+  matched2[0] = 2; groups2[0].scheduled = 1;
+  flags2[3] = BS_GROUP_SCHEDULED; matched2[3] = 4;
+  groups2[7].has_min_resources = true; groups2[7].min_resources = {{"cpu", "500m"}, {"memory", "1Gi"}};
+  flags2[8] = BS_GROUP_DENIED;
+  groups2[19].max_schedule_time_ns = 3000000000ll; groups2[19].creation_ns = 77;
+  groups2[29].min_member = 9;
+  PackedSnapshot after;
+  st = BatchSchedulingPlugin::Pack({&i0}, pend, groups2, matched2, flags2, {}, 9000000000ll, &after);
+  if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+  std::vector<BatchSchedulingPlugin::GroupDelta> rows;
+  for (uint32_t g : idx) {
+    BatchSchedulingPlugin::GroupDelta gd;
+    gd.index = g; gd.pg = &groups2[g]; gd.matched = matched2[g]; gd.flags = flags2[g];
+    rows.push_back(gd);
+  }
+  PackedSnapshot delta;
+  bool needs_full = true;
+  st = BatchSchedulingPlugin::PackGroupRows(before, rows, 9000000000ll, &delta, &needs_full);
+  if (!st.ok()) { fprintf(stderr, "delta failed: %s\n", st.message.c_str()); return 1; }
+  int mismatches = 0;
+  const uint32_t L = after.lanes, n = (uint32_t)idx.size();
+  for (uint32_t k = 0; k < n && !needs_full; ++k) {
+    const uint32_t g = idx[k];
+    mismatches += delta.min_member[k] != after.min_member[g];
+    mismatches += delta.scheduled[k] != after.scheduled[g];
+    mismatches += delta.matched[k] != after.matched[g];
+    mismatches += delta.group_flags[k] != after.group_flags[g];
+    for (uint32_t d = 0; d < L; ++d) mismatches += delta.min_res[(size_t)d * n + k] != after.min_res[(size_t)d * G + g];
+    mismatches += delta.min_res_present[k] != after.min_res_present[g];
+    mismatches += delta.rep_sel[k] != after.rep_sel[g];
+    mismatches += delta.rep_tol[k] != after.rep_tol[g];
+    mismatches += delta.creation_ns[k] != after.creation_ns[g];
+    mismatches += delta.name_rank[k] != after.name_rank[g];
+    mismatches += delta.wait_ns[k] != after.wait_ns[g];
+  }
+  // a representative pod: its masks in the round's bit assignment
+  Pod rep = pods[0];                     // selector {zone: a}
+  rep.tolerations = {{"dedicated", "Exists", "", "NoSchedule"}};
+  BatchSchedulingPlugin::GroupDelta gd;
+  gd.index = 5; gd.pg = &groups2[5]; gd.rep_pod = &rep;
+  PackedSnapshot one;
+  bool full_rep = true;
+  BatchSchedulingPlugin::PackGroupRows(before, {gd}, 0, &one, &full_rep);
+  uint64_t want_sel = 0;
+  for (size_t b = 0; b < before.sel_pairs.size(); ++b)
+    if (before.sel_pairs[b].first == "zone" && before.sel_pairs[b].second == "a") want_sel = 1ull << b;
+  const int rep_ok = !full_rep && one.rep_sel[0] == want_sel && one.rep_tol[0] == 1 && (one.group_flags[0] & BS_GROUP_HAS_POD);
+  Pod rep2 = pods[1]; rep2.node_selector = {{"rack", "r9"}};     // a pair no pod of the round selects on
+  gd.rep_pod = &rep2;
+  bool full_sel = false, full_scalar = false;
+  BatchSchedulingPlugin::PackGroupRows(before, {gd}, 0, &one, &full_sel);
+  PodGroup odd = groups2[5]; odd.has_min_resources = true; odd.min_resources = {{"example.com/fpga", "1"}};
+  gd.pg = &odd; gd.rep_pod = nullptr;
+  BatchSchedulingPlugin::PackGroupRows(before, {gd}, 0, &one, &full_scalar);
+  printf("{\"rows\": %u, \"needs_full\": %d, \"mismatches\": %d, \"rep_ok\": %d, \"full_on_new_selector\": %d, "
+         "\"full_on_new_scalar\": %d}\n", n, needs_full ? 1 : 0, mismatches, rep_ok, full_sel ? 1 : 0, full_scalar ? 1 : 0);
+  return 0;
+}
+
 static int cmd_readme_replay() {
   // the same race in ONE call: all ten pods pending, the device walks the queue (bs_replay)
   Node node; node.name = "node1";
@@ -401,6 +493,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "pack_core_test")) return cmd_pack_core_test();
   if (!strcmp(argv[1], "pack_semantics")) return cmd_pack_semantics();
   if (!strcmp(argv[1], "pack_delta")) return cmd_pack_delta();
+  if (!strcmp(argv[1], "pack_group_delta")) return cmd_pack_group_delta();
   if (!strcmp(argv[1], "readme")) return cmd_readme();
   if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));

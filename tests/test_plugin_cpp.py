@@ -104,6 +104,15 @@ def test_packer_delta_rows(plugin_bin):
     assert o["full_on_new_taint"] == 1 and o["full_on_new_scalar"] == 1
 
 
+def test_packer_group_delta_rows(plugin_bin):
+    """PackGroupRows: PodGroups whose state moved between cycles, packed with the round's dictionaries,
+    equal the same rows of a full re-pack (bare-name ranks taken over); representative-pod masks use the
+    round's selector / taint bits; an unknown selector pair or scalar resource asks for a full pack."""
+    o = _run(plugin_bin, "pack_group_delta")
+    assert o["rows"] == 6 and o["needs_full"] == 0 and o["mismatches"] == 0
+    assert o["rep_ok"] == 1 and o["full_on_new_selector"] == 1 and o["full_on_new_scalar"] == 1
+
+
 def test_packer_throughput_smoke(plugin_bin):
     out = _run(plugin_bin, "bench_pack", "500", "4000", "500")
     assert out["lanes"] == 5 and out["pack_ms"] > 0
