@@ -13,6 +13,7 @@ import numpy as np
 
 from . import build as _build
 
+AFF_NONE = 0xffffffff
 BS_OK, BS_E_INVAL, BS_E_NODEVICE, BS_E_CUDA, BS_E_NOMEM, BS_E_RANGE, BS_E_STATE, BS_E_REF_PANIC, BS_E_INDEX, BS_E_PEER = \
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 CODE_SUCCESS, CODE_ERROR, CODE_UNSCHEDULABLE, CODE_UNSCHEDULABLE_AND_UNRESOLVABLE, CODE_WAIT, CODE_SKIP = range(6)
@@ -40,14 +41,14 @@ class NodeTableC(C.Structure):
 class PodTableC(C.Structure):
     _fields_ = [("n_pods", C.c_uint32), ("n_lanes", C.c_uint32), ("req", C.c_void_p), ("req_present", C.c_void_p),
                 ("gid", C.c_void_p), ("sel_mask", C.c_void_p), ("tol_mask", C.c_void_p), ("priority", C.c_void_p),
-                ("ts_ns", C.c_void_p), ("flags", C.c_void_p)]
+                ("ts_ns", C.c_void_p), ("flags", C.c_void_p), ("aff_class", C.c_void_p)]
 
 
 class GroupTableC(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("n_lanes", C.c_uint32), ("min_member", C.c_void_p),
                 ("scheduled", C.c_void_p), ("matched", C.c_void_p), ("flags", C.c_void_p), ("min_res", C.c_void_p),
                 ("min_res_present", C.c_void_p), ("rep_sel", C.c_void_p), ("rep_tol", C.c_void_p),
-                ("creation_ns", C.c_void_p), ("name_rank", C.c_void_p)]
+                ("creation_ns", C.c_void_p), ("name_rank", C.c_void_p), ("rep_aff_class", C.c_void_p)]
 
 
 class ResultsC(C.Structure):
@@ -85,6 +86,7 @@ SYMBOLS = {
     "bs_update_groups": (C.c_int, [C.c_void_p, C.c_void_p, _p(GroupTableC)]),
     "bs_upload_groups": (C.c_int, [C.c_void_p, _p(GroupTableC)]),
     "bs_upload_pods": (C.c_int, [C.c_void_p, _p(PodTableC)]),
+    "bs_upload_affinity": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "bs_set_wait_time": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32]),
     "bs_evaluate": (C.c_int, [C.c_void_p, _p(ResultsC)]),
     "bs_evaluate_async": (C.c_int, [C.c_void_p]),
@@ -101,6 +103,8 @@ SYMBOLS = {
                                    C.c_uint32, C.c_void_p]),
     "bs_device_buffer": (C.c_int, [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_size_t)]),
     "bs_stream": (C.c_void_p, [C.c_void_p]),
+    "bs_score_pitch": (C.c_uint32, [C.c_void_p]),
+    "bs_bitmap_pitch": (C.c_uint32, [C.c_void_p]),
     "bs_fetch_fit_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bs_fetch_score_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bs_fetch_filter_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
@@ -108,16 +112,20 @@ SYMBOLS = {
     "bs_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bs_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bs_peer_detach": (C.c_int, [C.c_void_p]),
+    "bs_peer_join": (C.c_int, [C.c_void_p]),
+    "bs_fetch_gathered_admit": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bs_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "bs_kernel_ms": (C.c_int, [C.c_void_p, C.c_int, _p(C.c_float), _p(C.c_uint32)]),
     "bs_launch_count": (C.c_uint64, [C.c_void_p]),
+    "bs_fit_shape": (C.c_int, [C.c_void_p, _p(C.c_uint32), _p(C.c_uint32), _p(C.c_uint32)]),
 }
 
 _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """libbsched.so next to the package; BS_LIB selects another build of it (kernel experiments)."""
+    return os.environ.get("BS_LIB") or _build.LIB
 
 
 def load(build_if_missing: bool = True):
@@ -125,11 +133,12 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing and not os.path.exists(_build.LIB):
+    path = lib_path()
+    if build_if_missing and path == _build.LIB and not os.path.exists(path):
         _build.build()
-    if not os.path.exists(_build.LIB):
-        raise RuntimeError(f"{_build.LIB} is missing: the CUDA extension must be built (no CPU fallback exists)")
-    lib = C.CDLL(_build.LIB)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: the CUDA extension must be built (no CPU fallback exists)")
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

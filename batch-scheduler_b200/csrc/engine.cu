@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "fit.cuh"
 #include "sort.cuh"
 #include "replay.cuh"
 
@@ -94,7 +95,8 @@ struct PinVec {
 struct ClassKey {
   uint64_t sel, tol;
   uint32_t nz;
-  bool operator==(const ClassKey& o) const { return sel == o.sel && tol == o.tol && nz == o.nz; }
+  uint32_t aff;   // affinity class (row of the bs_upload_affinity table) or BS_AFF_NONE
+  bool operator==(const ClassKey& o) const { return sel == o.sel && tol == o.tol && nz == o.nz && aff == o.aff; }
 };
 
 // flat open-addressing index ClassKey -> dense id (insertion order)
@@ -102,18 +104,18 @@ struct ClassIndex {
   std::vector<ClassKey> keys;
   std::vector<uint32_t> slots;  // id + 1, 0 = empty
   uint32_t mask = 0;
-  ClassKey last_key{0, 0, 0xffffffffu};
+  ClassKey last_key{0, 0, 0xffffffffu, 0};
   uint32_t last_id = 0;
   static uint64_t hash(const ClassKey& k) {
     uint64_t h = k.sel * 0x9E3779B97F4A7C15ull ^ (k.tol + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull ^
-                 (uint64_t)k.nz * 0x94D049BB133111EBull;
+                 ((uint64_t)k.nz | ((uint64_t)k.aff << 32)) * 0x94D049BB133111EBull;
     return h ^ (h >> 29);
   }
   void clear() {
     keys.clear();
     slots.assign(256, 0);
     mask = 255;
-    last_key = ClassKey{0, 0, 0xffffffffu};
+    last_key = ClassKey{0, 0, 0xffffffffu, 0};
   }
   void grow() {
     std::vector<uint32_t> ns((size_t)(mask + 1) * 2, 0);
@@ -170,12 +172,13 @@ template <class KeyFn>
 void assign_classes(ClassIndex& global, uint32_t n, KeyFn key_of, uint32_t* out) {
   if (global.slots.empty()) global.clear();
   const int T = n < 8192 ? 1 : host_threads();
+  // T fixed CHUNKS, not T threads: num_threads(T) is only a request (OMP_THREAD_LIMIT, OMP_DYNAMIC, a failed
+  // thread creation give a smaller team), so the chunks are shared out with an omp for
   std::vector<ClassIndex> local(T);
   std::vector<std::vector<uint32_t>> remap(T);
   const uint32_t chunk = (n + T - 1) / T;
-#pragma omp parallel num_threads(T)
-  {
-    const int t = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+  for (int t = 0; t < T; ++t) {
     ClassIndex& li = local[t];
     li.clear();
     const uint32_t a = std::min(n, (uint32_t)t * chunk), b = std::min(n, a + chunk);
@@ -185,9 +188,8 @@ void assign_classes(ClassIndex& global, uint32_t n, KeyFn key_of, uint32_t* out)
     remap[t].resize(local[t].size());
     for (size_t j = 0; j < local[t].size(); ++j) remap[t][j] = global.get_or_add(local[t].keys[j]);
   }
-#pragma omp parallel num_threads(T)
-  {
-    const int t = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+  for (int t = 0; t < T; ++t) {
     const uint32_t a = std::min(n, (uint32_t)t * chunk), b = std::min(n, a + chunk);
     const uint32_t* rm = remap[t].data();
     for (uint32_t i = a; i < b; ++i) out[i] = rm[out[i]];
@@ -200,8 +202,8 @@ struct bs_engine {
   std::mutex mu;
   int device = 0;
   uint32_t L = 0, out_flags = 0;
-  cudaStream_t s = nullptr, s2 = nullptr, s3 = nullptr;   // main; queue sort; PreFilter chain (high priority)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pre = nullptr;
+  cudaStream_t s = nullptr, s2 = nullptr, s3 = nullptr, s4 = nullptr;   // main; queue sort; PreFilter chain (high priority); peer wait
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pre = nullptr, ev_push = nullptr, ev_gath = nullptr;
   std::string err;
   uint64_t launches = 0;
 
@@ -219,13 +221,24 @@ struct bs_engine {
   int64_t max_alloc[BS_MAX_LANES] = {}, max_requested[BS_MAX_LANES] = {}, max_req[BS_MAX_LANES] = {};
   int64_t max_pod_count = 0;
   int64_t neg_req[BS_MAX_LANES] = {};   // largest negative request per lane (0 when none)
+  // scaled-lane classification: OR of every residual (percent 1.0) / request value of a lane (its
+  // trailing zeros = the power of two every value is a multiple of) and max |residual|
+  uint64_t or_left[BS_MAX_LANES] = {}, or_req[BS_MAX_LANES] = {};
+  int64_t max_left[BS_MAX_LANES] = {};
+  bool no_scaled_lanes = false;         // BS_NO_SCALED_LANES=1: keep byte-valued lanes in int64 (experiments)
+  uint32_t score_pitch = 0;             // elements per score row: N rounded up to even
+  uint32_t bitmap_pitch = 0;            // words per fit-bitmap row: ceil(N/32) rounded up to 32 (whole 128-byte lines)
   // pod table
   DevBuf d_req, d_ppres, d_gid, d_prio, d_ts, d_pflags, d_pod_fit_class, d_pod_rep_class;
   // group table
   DevBuf d_min_member, d_scheduled, d_matched, d_gflags, d_min_res, d_mrpres, d_creation, d_name_rank,
       d_group_rep_class;
   // class tables
-  DevBuf d_fsel, d_ftol, d_fnz, d_rsel, d_rtol;
+  DevBuf d_fsel, d_ftol, d_fnz, d_faff, d_rsel, d_rtol, d_raff;
+  // affinity bit table (bs_upload_affinity): [n_aff][W] host-evaluated node predicates
+  DevBuf d_aff_bits;
+  uint32_t n_aff = 0;
+  std::vector<uint32_t> h_gaff;   // affinity class of each group's representative pod
   uint32_t n_fit_classes = 0, n_rep_classes = 0;
   // effective group state + round scratch
   DevBuf d_eflags, d_emin_res, d_emrpres, d_erep_class, d_first_pod, d_in_round, d_contrib, d_done, d_okA;
@@ -272,6 +285,8 @@ struct bs_engine {
   DevBuf d_gather, d_peer_err;
   uint32_t peer_rank = 0, peer_world = 0, peer_wpr = 0, peer_seq = 0;
   bool peer_attached = false;
+  bool peer_broken = false;          // a wait timed out: every later round fails fast until detach + re-attach
+  unsigned long long peer_timeout_ns = 2000000000ull;
   void* peer_ptr[PEER_MAX_WORLD] = {};
 
   // profiling
@@ -315,6 +330,28 @@ bool lane_maxima(const int64_t* a, uint32_t L, size_t n, int64_t* out) {
   return ok;
 }
 
+// Host restatement of singleNodeResource's per-lane residual at percent 1.0 (core.go:647-668) for the
+// lane statistics only: OR of the values (common power-of-two factor) and max |value| per lane.
+// (float)alloc is the RN convert, * 1.0f is exact, the cast back truncates — the device's scale_f32.
+void left_stats(const bs_node_table* t, uint32_t L, uint32_t n, uint64_t* or_out, int64_t* max_out) {
+  for (uint32_t d = 0; d < L; ++d) {
+    uint64_t o = 0;
+    int64_t mx = 0;
+    const int64_t* al = t->alloc + (size_t)d * n;
+    const int64_t* rq = t->requested + (size_t)d * n;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (d >= 4 && !((t->alloc_present[i] & t->req_present[i]) >> d & 1u)) continue;   // key absent: sentinel
+      int64_t used = rq[i];
+      if (d == (uint32_t)LANE_PODS && used == 0) used = t->pod_count[i];
+      const int64_t v = (int64_t)((float)al[i] * 1.0f) - used;
+      o |= (uint64_t)v;
+      mx = std::max(mx, v < 0 ? -v : v);
+    }
+    or_out[d] |= o;
+    max_out[d] = std::max(max_out[d], mx);
+  }
+}
+
 // Lane classification for the fit kernel (kernels.cuh "Narrow lanes"): lane d is narrow when every
 // residual |left[d]| and every request |req[d]| of the round is <= 2^27.  The narrow set must
 // contain a fixed lane (always a real value) and the (LW, LN) pair must be one the dispatch
@@ -351,6 +388,8 @@ NodeTab node_tab(const bs_engine* e) {
   t.label = e->d_label.as<uint64_t>();
   t.taint = e->d_taint.as<uint64_t>();
   t.flags = e->d_nflags.as<uint8_t>();
+  t.aff_bits = e->d_aff_bits.as<uint32_t>();
+  t.aff_W = e->W;
   t.N = e->N;
   t.Npad = e->Npad;
   t.L = e->L;
@@ -483,93 +522,68 @@ void launch_replay(uint32_t L, const ReplayArgs& a, cudaStream_t s) {
   }
 }
 
-template <int LW, int LN>
-cudaError_t launch_fit_t(const FitArgs& a, uint32_t grid, cudaStream_t s) {
-  const size_t smem = gang_fit_smem_bytes(LW, LN);
-  // per launch, not cached: the attribute is per device and one process may drive several GPUs
-  cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<LW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem);
-  if (er != cudaSuccess) return er;
-  gang_fit_kernel<LW, LN><<<grid, FIT_THREADS, smem, s>>>(a);
-  return cudaGetLastError();
-}
-
-constexpr int FIT_MAX_LW = 4, FIT_MAX_LN = 8;  // mixed wide/narrow instantiations: LW 0..4 x LN 1..8
-bool fit_variant_exists(uint32_t LW, uint32_t LN) {
-  if (LN == 0) return LW >= 4 && LW <= BS_MAX_LANES;
-  return LW <= FIT_MAX_LW && LN <= FIT_MAX_LN && LW + LN >= 4 && LW + LN <= BS_MAX_LANES;
-}
-
-template <int LW>
-cudaError_t launch_fit_ln(uint32_t LN, const FitArgs& a, uint32_t grid, cudaStream_t s) {
-  switch (LN) {
-#define BS_CASE(n) \
-  case n:          \
-    if constexpr (LW + n >= 4) return launch_fit_t<LW, n>(a, grid, s); else break;
-    BS_CASE(1) BS_CASE(2) BS_CASE(3) BS_CASE(4) BS_CASE(5) BS_CASE(6) BS_CASE(7) BS_CASE(8)
-#undef BS_CASE
-  }
-  return cudaErrorInvalidValue;
-}
-
 cudaError_t launch_fit(const FitArgs& a, uint32_t grid, cudaStream_t s) {
-  const uint32_t LW = a.lm.LW, LN = a.lm.LN;
-  if (LN == 0) {
-    switch (LW) {
-      case 4: return launch_fit_t<4, 0>(a, grid, s);
-      case 5: return launch_fit_t<5, 0>(a, grid, s);
-      case 6: return launch_fit_t<6, 0>(a, grid, s);
-      case 7: return launch_fit_t<7, 0>(a, grid, s);
-      case 8: return launch_fit_t<8, 0>(a, grid, s);
-      case 9: return launch_fit_t<9, 0>(a, grid, s);
-      case 10: return launch_fit_t<10, 0>(a, grid, s);
-      case 11: return launch_fit_t<11, 0>(a, grid, s);
-      case 12: return launch_fit_t<12, 0>(a, grid, s);
-      case 13: return launch_fit_t<13, 0>(a, grid, s);
-      case 14: return launch_fit_t<14, 0>(a, grid, s);
-      case 15: return launch_fit_t<15, 0>(a, grid, s);
-      case 16: return launch_fit_t<16, 0>(a, grid, s);
-    }
-    return cudaErrorInvalidValue;
-  }
-  switch (LW) {
-    case 0: return launch_fit_ln<0>(LN, a, grid, s);
-    case 1: return launch_fit_ln<1>(LN, a, grid, s);
-    case 2: return launch_fit_ln<2>(LN, a, grid, s);
-    case 3: return launch_fit_ln<3>(LN, a, grid, s);
-    case 4: return launch_fit_ln<4>(LN, a, grid, s);
-  }
-  return cudaErrorInvalidValue;
+  FitFn fn = fit_lookup(a.lm.LW, a.lm.LN, a.lm.LS, a.score != nullptr);
+  return fn ? fn(a, grid, s) : cudaErrorInvalidValue;
 }
+
+inline uint32_t ctz64(uint64_t v) { return v ? (uint32_t)__builtin_ctzll(v) : 63u; }
 
 LaneMap classify_lanes(const bs_engine* e) {
   LaneMap lm{};
   const uint32_t L = e->L;
-  bool narrow[BS_MAX_LANES];
+  enum { WIDE = 0, NARROW = 1, SCALED = 2 };
+  int kind[BS_MAX_LANES];
+  uint32_t unit[BS_MAX_LANES] = {};
   bool fixed_narrow = false;
-  uint32_t ln = 0;
+  uint32_t ln = 0, ls = 0;
   for (uint32_t d = 0; d < L; ++d) {
     // |left| <= |scale(alloc)| + |requested| (pods lane: + len(Pods())); float32 rounding of a
     // value <= 2^26 is exact, so the bound 2^26 + 2^26 = 2^27 holds.
     int64_t used = e->max_requested[d];
     if (d == LANE_PODS) used = std::max(used, e->max_pod_count);
-    narrow[d] = e->max_alloc[d] <= (NARROW_LIMIT >> 1) && used <= (NARROW_LIMIT >> 1) && e->max_req[d] <= NARROW_LIMIT;
-    if (narrow[d]) {
+    const bool narrow = e->max_alloc[d] <= (NARROW_LIMIT >> 1) && used <= (NARROW_LIMIT >> 1) && e->max_req[d] <= NARROW_LIMIT;
+    kind[d] = narrow ? NARROW : WIDE;
+    if (narrow) {
       ++ln;
       if (d < 4) fixed_narrow = true;
+      continue;
+    }
+    // scaled: every residual and every request of the lane is a multiple of 2^k (k from the OR of all
+    // values seen at upload) and fits 2^29 in those units; the smallest such k is taken
+    const uint32_t k_avail = std::min(ctz64(e->or_left[d]), ctz64(e->or_req[d]));
+    const int64_t mx = std::max(e->max_left[d], e->max_req[d]);
+    uint32_t k_need = 0;
+    while (k_need < 63 && (mx >> k_need) > SCALED_LIMIT) ++k_need;
+    if (k_need <= k_avail && !e->no_scaled_lanes) {
+      kind[d] = SCALED;
+      unit[d] = k_need;
+      ++ls;
     }
   }
-  // keep at most FIT_MAX_LN narrow lanes (prefer the fixed ones) and at most FIT_MAX_LW wide ones
+  // keep at most FIT_MAX_LN narrow lanes (prefer the fixed ones)
   if (fixed_narrow && ln > (uint32_t)FIT_MAX_LN)
     for (int d = (int)L - 1; d >= 4 && ln > (uint32_t)FIT_MAX_LN; --d)
-      if (narrow[d]) { narrow[d] = false; --ln; }
-  if (!fixed_narrow || !fit_variant_exists(L - ln, ln)) {
-    for (uint32_t d = 0; d < L; ++d) narrow[d] = false;
-    ln = 0;
+      if (kind[d] == NARROW) { kind[d] = WIDE; --ln; }
+  // scaled lanes back to wide (last first) until the shape is one the variant table holds
+  if (fixed_narrow) {
+    for (int d = (int)L - 1; d >= 0 && !fit_variant_exists(L - ln - ls, ln, ls) && ls > 0; --d)
+      if (kind[d] == SCALED) { kind[d] = WIDE; --ls; }
+  }
+  if (!fixed_narrow || !fit_variant_exists(L - ln - ls, ln, ls)) {
+    for (uint32_t d = 0; d < L; ++d) kind[d] = WIDE;
+    ln = ls = 0;
   }
   for (uint32_t d = 0; d < L; ++d) {
-    if (narrow[d]) lm.narrow[lm.LN++] = (uint8_t)d;
-    else lm.wide[lm.LW++] = (uint8_t)d;
+    if (kind[d] == NARROW) lm.narrow[lm.LN++] = (uint8_t)d;
+    else if (kind[d] == SCALED) {
+      const uint32_t k = unit[d];
+      lm.scaled[lm.LS] = (uint8_t)d;
+      lm.sunit[lm.LS] = (uint8_t)k;
+      lm.sshift[lm.LS] = (uint8_t)std::min(k, 28u);
+      lm.sclamp[lm.LS] = k <= 28 ? (1u << (28 - k)) : 1u;
+      ++lm.LS;
+    } else lm.wide[lm.LW++] = (uint8_t)d;
   }
   return lm;
 }
@@ -601,26 +615,39 @@ int rebuild_classes(bs_engine* e) {
     if (!e->h_grc.resize(G)) return fail(e, BS_E_NOMEM, "pinned host memory");
     const uint64_t* gs = e->h_gsel.data();
     const uint64_t* gt = e->h_gtol.data();
-    assign_classes(e->rep_index, G, [=](uint32_t g) { return ClassKey{gs[g], gt[g], 0u}; }, e->h_grc.data());
+    const uint32_t* ga = e->h_gaff.data();
+    assign_classes(e->rep_index, G, [=](uint32_t g) { return ClassKey{gs[g], gt[g], 0u, ga[g]}; }, e->h_grc.data());
     e->group_classes_dirty = false;
   }
-  if (e->fit_index.size() == 0) e->fit_index.get_or_add(ClassKey{0, 0, 0});
-  if (e->rep_index.size() == 0) e->rep_index.get_or_add(ClassKey{0, 0, 0});
+  if (e->fit_index.size() == 0) e->fit_index.get_or_add(ClassKey{0, 0, 0, BS_AFF_NONE});
+  if (e->rep_index.size() == 0) e->rep_index.get_or_add(ClassKey{0, 0, 0, BS_AFF_NONE});
   e->n_fit_classes = (uint32_t)e->fit_index.size();
   e->n_rep_classes = (uint32_t)e->rep_index.size();
   std::vector<uint64_t> fsel(e->n_fit_classes), ftol(e->n_fit_classes), rsel(e->n_rep_classes), rtol(e->n_rep_classes);
-  std::vector<uint32_t> fnz(e->n_fit_classes);
+  std::vector<uint32_t> fnz(e->n_fit_classes), faff(e->n_fit_classes), raff(e->n_rep_classes);
+  bool aff_bad = false;
   for (uint32_t c = 0; c < e->n_fit_classes; ++c) {
     fsel[c] = e->fit_index.keys[c].sel; ftol[c] = e->fit_index.keys[c].tol; fnz[c] = e->fit_index.keys[c].nz;
+    faff[c] = e->fit_index.keys[c].aff;
+    aff_bad = aff_bad || (faff[c] != BS_AFF_NONE && faff[c] >= e->n_aff);
   }
   for (uint32_t c = 0; c < e->n_rep_classes; ++c) {
-    rsel[c] = e->rep_index.keys[c].sel; rtol[c] = e->rep_index.keys[c].tol;
+    rsel[c] = e->rep_index.keys[c].sel; rtol[c] = e->rep_index.keys[c].tol; raff[c] = e->rep_index.keys[c].aff;
   }
+  // (stale representative classes may linger in the persistent index; only the classes in use are checked)
+  for (uint32_t p = 0; p < P && !aff_bad; ++p) {
+    const uint32_t a = e->rep_index.keys[e->h_prc[p]].aff;
+    aff_bad = a != BS_AFF_NONE && a >= e->n_aff;
+  }
+  for (uint32_t g = 0; g < G && !aff_bad; ++g) aff_bad = e->h_gaff[g] != BS_AFF_NONE && e->h_gaff[g] >= e->n_aff;
+  if (aff_bad) return fail(e, BS_E_INDEX, "affinity class outside the uploaded table (bs_upload_affinity after bs_upload_nodes)");
   int rc;
   // cudaMemcpyAsync from pageable memory returns once the data is staged, so the vectors may die.
   if ((rc = upload_vec(e, e->d_fsel, fsel.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
   if ((rc = upload_vec(e, e->d_ftol, ftol.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
   if ((rc = upload_vec(e, e->d_fnz, fnz.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
+  if ((rc = upload_vec(e, e->d_faff, faff.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
+  if ((rc = upload_vec(e, e->d_raff, raff.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
   if ((rc = upload_vec(e, e->d_rsel, rsel.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
   if ((rc = upload_vec(e, e->d_rtol, rtol.data(), e->n_rep_classes, e->n_rep_classes))) return rc;
   if (e->pod_classes_dirty) {   // a group-only change (bs_update_groups) leaves the pods' ids alone
@@ -657,8 +684,8 @@ int ensure_round_buffers(bs_engine* e) {
   CK(e->d_rank.ensure((size_t)P * 4));
   // rows padded to a whole CTA of pods: the fit kernel writes pods >= P without a guard
   const size_t Prows = (size_t)cdiv(std::max(e->P, 1u), PODS_PER_CTA) * PODS_PER_CTA;
-  if (e->out_flags & BS_OUT_FIT_BITMAP) CK(e->d_fit_bitmap.ensure(Prows * std::max(e->W, 1u) * 4));
-  if (e->out_flags & BS_OUT_SCORE) CK(e->d_score.ensure(Prows * N * 8));
+  if (e->out_flags & BS_OUT_FIT_BITMAP) CK(e->d_fit_bitmap.ensure(Prows * std::max(e->bitmap_pitch, 32u) * 4));
+  if (e->out_flags & BS_OUT_SCORE) CK(e->d_score.ensure(Prows * std::max(e->score_pitch, 2u) * 8));
   if (e->out_flags & BS_OUT_FILTER) {
     CK(e->d_filter_bitmap.ensure(Prows * std::max(e->W, 1u) * 4));
     CK(e->d_filter_code.ensure(P));
@@ -716,7 +743,7 @@ int prepare_nodes(bs_engine* e) {
   NodeTab t = node_tab(e);
   StageTimer tm(e, BS_K_NODE_LEFT, e->s);
   CK(e->d_left_w.ensure((size_t)std::max(e->lane_map.LW, 1u) * e->Npad * 8));
-  CK(e->d_left_n.ensure((size_t)std::max(e->lane_map.LN, 1u) * e->Npad * 4));
+  CK(e->d_left_n.ensure((size_t)std::max(e->lane_map.LN + e->lane_map.LS, 1u) * e->Npad * 4));
   CK(e->d_left_present.ensure((size_t)e->Npad * 4));
   if (e->out_flags & BS_OUT_FILTER) CK(e->d_left_plain.ensure((size_t)4 * e->Npad * 8));
   const uint32_t n_tiles = e->Npad / NODE_TILE;
@@ -730,7 +757,7 @@ int prepare_nodes(bs_engine* e) {
     for (uint32_t c0 = 0; c0 < e->n_fit_classes; c0 += 32768) {
       dim3 grid(cdiv(n_tiles * 32, 256), std::min(32768u, e->n_fit_classes - c0));
       class_fit_kernel<<<grid, 256, 0, e->s>>>(t, e->d_left_present.as<uint32_t>(), e->d_fsel.as<uint64_t>(),
-                                               e->d_ftol.as<uint64_t>(), e->d_fnz.as<uint32_t>(),
+                                               e->d_ftol.as<uint64_t>(), e->d_fnz.as<uint32_t>(), e->d_faff.as<uint32_t>(),
                                                e->n_fit_classes, n_tiles, e->d_classfit.as<ColBits>(), c0);
       tm.launched();
     }
@@ -743,6 +770,8 @@ int prepare_nodes(bs_engine* e) {
 int evaluate_async_locked(bs_engine* e) {
   if (!e->have_nodes || !e->have_pods || !e->have_groups)
     return fail(e, BS_E_STATE, "bs_evaluate: upload nodes, groups and pods first");
+  if (e->peer_broken)
+    return fail(e, BS_E_PEER, "peer exchange is broken (a rank did not arrive): bs_peer_detach on every rank, then init/attach again");
   BS_DEVICE_GUARD(e);
   int rc;
   bool reprepare = e->nodes_dirty;
@@ -851,7 +880,7 @@ int evaluate_async_locked(bs_engine* e) {
     StageTimer tm(e, BS_K_CLASS_PREFIX, e->s3);
     if (e->N && G && P) {
       PrefixScratch psc = prefix_scratch(e);
-      PrefixSel ps{e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), 0, 0, 0, 0, 0.f, st};
+      PrefixSel ps{e->d_rsel.as<uint64_t>(), e->d_rtol.as<uint64_t>(), e->d_raff.as<uint32_t>(), 0, 0, 0, 0, 0.f, st};
       for (uint32_t c0 = 0; c0 < e->n_rep_classes; c0 += e->prefix_slots) {
         const uint32_t nc = std::min(e->prefix_slots, e->n_rep_classes - c0);
         ps.c0 = c0;
@@ -894,23 +923,14 @@ int evaluate_async_locked(bs_engine* e) {
       a.req = e->d_req.as<int64_t>();
       a.req_present = e->d_ppres.as<uint32_t>();
       a.fit_class = e->d_pod_fit_class.as<uint32_t>();
-      a.gid = e->d_gid.as<int32_t>();
-      a.prefilter = e->d_prefilter.as<uint8_t>();
-      a.min_member = gt.min_member;
-      a.scheduled = gt.scheduled;
-      a.matched = gt.matched;
-      a.in_round = ge.in_round;
-      a.contrib = ge.contrib;
-      a.done = ge.done;
-      a.admit = e->d_admit.as<uint8_t>();
-      a.admit_bitmap = e->d_admit_bitmap.as<uint32_t>();
       a.feasible_count = e->d_feasible.as<uint32_t>();
       a.best_node = e->d_best_node.as<int32_t>();
       a.best_score = e->d_best_score.as<int64_t>();
       a.fit_bitmap = (e->out_flags & BS_OUT_FIT_BITMAP) ? e->d_fit_bitmap.as<uint32_t>() : nullptr;
       a.score = (e->out_flags & BS_OUT_SCORE) ? e->d_score.as<int64_t>() : nullptr;
-      a.P = P; a.N = e->N; a.Npad = e->Npad; a.W = e->W; a.G = G;
-      a.defer_admit = 1;
+      a.score_pitch = e->score_pitch;
+      a.bitmap_pitch = e->bitmap_pitch;
+      a.P = P; a.N = e->N; a.Npad = e->Npad; a.W = e->W;
       CK(launch_fit(a, cdiv(P, PODS_PER_CTA), e->s));
       tm.launched();
     }
@@ -951,19 +971,30 @@ int evaluate_async_locked(bs_engine* e) {
       tm.launched();
     }
   }
-  {
-    StageTimer tm(e, BS_K_PEER, e->s);
-    if (e->peer_attached) {
-      PeerArgs pa{};
-      for (uint32_t r = 0; r < e->peer_world; ++r) pa.peer_buf[r] = reinterpret_cast<uint32_t*>(e->peer_ptr[r]);
-      pa.local_bitmap = e->d_admit_bitmap.as<uint32_t>();
-      pa.rank = e->peer_rank; pa.world = e->peer_world; pa.words_per_rank = e->peer_wpr;
-      pa.n_words = std::min(e->peer_wpr, cdiv(std::max(G, 1u), 32));
-      pa.seq = ++e->peer_seq;
-      pa.err = e->d_peer_err.as<int>();
-      peer_exchange_kernel<<<1, 256, 0, e->s>>>(pa);
+  if (e->peer_attached) {
+    // admit-bitmap all-gather over peer memory (kernels.cuh K8): the push is the round's last kernel on
+    // the main stream, ordered behind the PREVIOUS round's wait (slot reuse rule); the wait for this
+    // round's slots spins on the side stream s4 while the next round may already be computing.
+    PeerArgs pa{};
+    for (uint32_t r = 0; r < e->peer_world; ++r) pa.peer_buf[r] = reinterpret_cast<uint32_t*>(e->peer_ptr[r]);
+    pa.local_bitmap = e->d_admit_bitmap.as<uint32_t>();
+    pa.rank = e->peer_rank; pa.world = e->peer_world; pa.words_per_rank = e->peer_wpr;
+    pa.n_words = std::min(e->peer_wpr, cdiv(std::max(G, 1u), 32));
+    pa.seq = ++e->peer_seq;
+    pa.err = e->d_peer_err.as<int>();
+    pa.timeout_ns = e->peer_timeout_ns;
+    if (pa.seq > 1) CK(cudaStreamWaitEvent(e->s, e->ev_gath, 0));
+    {
+      StageTimer tm(e, BS_K_PEER, e->s);
+      peer_push_kernel<<<e->peer_world, 256, 0, e->s>>>(pa);
       tm.launched();
     }
+    CK(cudaEventRecord(e->ev_push, e->s));
+    CK(cudaStreamWaitEvent(e->s4, e->ev_push, 0));
+    peer_wait_kernel<<<1, 32, 0, e->s4>>>(pa);
+    e->k_launches[BS_K_PEER] += 1;
+    e->launches += 1;
+    CK(cudaEventRecord(e->ev_gath, e->s4));
   }
   CK(cudaStreamWaitEvent(e->s, e->ev_join, 0));
   CK(cudaGetLastError());
@@ -1058,13 +1089,17 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
   e->device = cfg->device;
   e->L = cfg->n_lanes;
   e->out_flags = cfg->out_flags;
+  if (const char* ns = getenv("BS_NO_SCALED_LANES")) e->no_scaled_lanes = atoi(ns) != 0;
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the small kernels of the PreFilter chain must get the
                                                           // SM slots the fit kernel's retiring CTAs free
   bool ok = cudaStreamCreateWithFlags(&e->s, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithPriority(&e->s3, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&e->s4, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_pre, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_push, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_gath, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_classes, cudaEventDisableTiming) == cudaSuccess;
@@ -1090,6 +1125,7 @@ void bs_destroy(bs_engine* e) {
   DeviceGuard guard(e->device);
   if (e->s) cudaStreamSynchronize(e->s);
   if (e->s2) cudaStreamSynchronize(e->s2);
+  if (e->s4) cudaStreamSynchronize(e->s4);
   for (uint32_t r = 0; r < e->peer_world; ++r)
     if (r != e->peer_rank && e->peer_ptr[r]) cudaIpcCloseMemHandle(e->peer_ptr[r]);
   e->d_gather.release();
@@ -1099,7 +1135,7 @@ void bs_destroy(bs_engine* e) {
                     &e->d_ppres, &e->d_gid, &e->d_prio, &e->d_ts, &e->d_pflags, &e->d_pod_fit_class,
                     &e->d_pod_rep_class, &e->d_min_member, &e->d_scheduled, &e->d_matched, &e->d_gflags,
                     &e->d_min_res, &e->d_mrpres, &e->d_creation, &e->d_name_rank, &e->d_group_rep_class,
-                    &e->d_fsel, &e->d_ftol, &e->d_fnz, &e->d_rsel, &e->d_rtol, &e->d_eflags, &e->d_emin_res,
+                    &e->d_fsel, &e->d_ftol, &e->d_fnz, &e->d_faff, &e->d_rsel, &e->d_rtol, &e->d_raff, &e->d_aff_bits, &e->d_eflags, &e->d_emin_res,
                     &e->d_emrpres, &e->d_erep_class, &e->d_first_pod, &e->d_in_round, &e->d_contrib,
                     &e->d_done, &e->d_okA, &e->d_state, &e->d_pre, &e->d_pre_present, &e->d_pre_stats, &e->d_max_partial, &e->d_pre_part,
                     &e->d_pre_part_pres, &e->d_pre_cstats, &e->d_pre_done,
@@ -1121,7 +1157,10 @@ void bs_destroy(bs_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_pre) cudaEventDestroy(e->ev_pre);
+  if (e->ev_push) cudaEventDestroy(e->ev_push);
+  if (e->ev_gath) cudaEventDestroy(e->ev_gath);
   if (e->s3) cudaStreamDestroy(e->s3);
+  if (e->s4) cudaStreamDestroy(e->s4);
   if (e->ev_classes) cudaEventDestroy(e->ev_classes);
   e->h_pfc.release(); e->h_prc.release(); e->h_grc.release();
   if (e->s) cudaStreamDestroy(e->s);
@@ -1142,6 +1181,9 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
     return fail(e, BS_E_RANGE, "bs_upload_nodes: value outside +-2^56");
   int64_t mx_pc = 0;
   for (uint32_t i = 0; i < N; ++i) mx_pc = std::max<int64_t>(mx_pc, std::abs((int64_t)t->pod_count[i]));
+  uint64_t or_l[BS_MAX_LANES] = {};
+  int64_t mx_l[BS_MAX_LANES] = {};
+  left_stats(t, L, N, or_l, mx_l);
   BS_DEVICE_GUARD(e);
   const uint32_t Npad = std::max(1u, cdiv(N, NODE_TILE)) * NODE_TILE;
   int rc;
@@ -1157,8 +1199,13 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   e->h_nflags.assign(t->flags, t->flags + N);
   memcpy(e->max_alloc, mx_a, sizeof(mx_a));
   memcpy(e->max_requested, mx_r, sizeof(mx_r));
+  memcpy(e->or_left, or_l, sizeof(or_l));
+  memcpy(e->max_left, mx_l, sizeof(mx_l));
   e->max_pod_count = mx_pc;
   e->N = N;
+  e->score_pitch = (N + 1u) & ~1u;
+  e->bitmap_pitch = (cdiv(N, 32) + 31u) & ~31u;
+  e->n_aff = 0;            // the affinity table belongs to the node snapshot
   e->Npad = Npad;
   e->W = cdiv(N, 32);
   e->have_nodes = true;
@@ -1215,7 +1262,9 @@ int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t) {
   da.release(); dr.release(); dpc.release(); dap.release(); drp.release(); dl.release(); dt.release(); df.release();
   di.release();
   CK(er);
-  // lane maxima only ever grow here (a conservative bound keeps the wide/narrow split exact)
+  // lane maxima only ever grow here (a conservative bound keeps the wide/narrow split exact); the OR
+  // of the residuals only gains bits (fewer common trailing zeros: a smaller unit, still exact)
+  left_stats(t, L, n, e->or_left, e->max_left);
   for (uint32_t d = 0; d < L; ++d) {
     e->max_alloc[d] = std::max(e->max_alloc[d], mx_a[d]);
     e->max_requested[d] = std::max(e->max_requested[d], mx_r[d]);
@@ -1275,12 +1324,16 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   e->vary_name = G ? (o0 ^ a0) : 0;
   e->g_or1 = o1; e->g_and1 = a1; e->g_or0 = o0; e->g_and0 = a0;
   // representative (sel, tol) columns unchanged since the ids were assigned: nothing to look up again
-  const bool same_reps = e->h_gsel.size() == G && e->h_gtol.size() == G && e->h_grc.size() == G &&
-                         (G == 0 || (memcmp(e->h_gsel.data(), t->rep_sel, (size_t)G * 8) == 0 &&
-                                     memcmp(e->h_gtol.data(), t->rep_tol, (size_t)G * 8) == 0));
+  bool same_reps = e->h_gsel.size() == G && e->h_gtol.size() == G && e->h_grc.size() == G && e->h_gaff.size() == G &&
+                   (G == 0 || (memcmp(e->h_gsel.data(), t->rep_sel, (size_t)G * 8) == 0 &&
+                               memcmp(e->h_gtol.data(), t->rep_tol, (size_t)G * 8) == 0));
+  for (uint32_t g = 0; g < G && same_reps; ++g)
+    same_reps = e->h_gaff[g] == (t->rep_aff_class ? t->rep_aff_class[g] : BS_AFF_NONE);
   if (!same_reps) {
     e->h_gsel.assign(t->rep_sel, t->rep_sel + G);
     e->h_gtol.assign(t->rep_tol, t->rep_tol + G);
+    e->h_gaff.resize(G);
+    for (uint32_t g = 0; g < G; ++g) e->h_gaff[g] = t->rep_aff_class ? t->rep_aff_class[g] : BS_AFF_NONE;
     e->group_classes_dirty = true;
     e->classes_dirty = true;
   }
@@ -1345,6 +1398,7 @@ int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t)
     e->g_or1 |= c; e->g_and1 &= c; e->g_or0 |= nm; e->g_and0 &= nm;
     e->h_gsel[idx[k]] = t->rep_sel[k];
     e->h_gtol[idx[k]] = t->rep_tol[k];
+    e->h_gaff[idx[k]] = t->rep_aff_class ? t->rep_aff_class[k] : BS_AFF_NONE;
   }
   e->vary_creation = e->g_or1 ^ e->g_and1;
   e->vary_name = e->g_or0 ^ e->g_and0;
@@ -1369,6 +1423,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   const int T = P < 8192 ? 1 : host_threads();
   struct Part {
     int64_t lo[BS_MAX_LANES], hi[BS_MAX_LANES];
+    uint64_t orq[BS_MAX_LANES];
     uint64_t ot = 0, at = ~0ull;
     uint32_t op = 0, apr = ~0u;
     int miss = 0;
@@ -1392,19 +1447,21 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
+  // T fixed chunks handed out by an omp for: a team smaller than requested still covers every chunk
   const uint32_t chunk = (P + T - 1) / std::max(T, 1);
-#pragma omp parallel num_threads(T)
-  {
-    Part& pt = part[omp_get_thread_num()];
-    for (uint32_t d = 0; d < BS_MAX_LANES; ++d) { pt.lo[d] = 0; pt.hi[d] = 0; }
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+  for (int tk = 0; tk < T; ++tk) {
+    Part& pt = part[tk];
+    for (uint32_t d = 0; d < BS_MAX_LANES; ++d) { pt.lo[d] = 0; pt.hi[d] = 0; pt.orq[d] = 0; }
     pt.fit.clear();
     pt.rep.clear();
-    const uint32_t a0 = std::min(P, (uint32_t)omp_get_thread_num() * chunk), a1 = std::min(P, a0 + chunk);
+    const uint32_t a0 = std::min(P, (uint32_t)tk * chunk), a1 = std::min(P, a0 + chunk);
     for (uint32_t d = 0; d < L; ++d) {
       const int64_t* row = t->req + (size_t)d * P;
       int64_t lo = 0, hi = 0;
-      for (uint32_t p = a0; p < a1; ++p) { lo = std::min(lo, row[p]); hi = std::max(hi, row[p]); }
-      pt.lo[d] = lo; pt.hi[d] = hi;
+      uint64_t o = 0;
+      for (uint32_t p = a0; p < a1; ++p) { lo = std::min(lo, row[p]); hi = std::max(hi, row[p]); o |= (uint64_t)row[p]; }
+      pt.lo[d] = lo; pt.hi[d] = hi; pt.orq[d] = o;
     }
     for (uint32_t p = a0; p < a1; ++p) {
       const uint64_t ts = (uint64_t)t->ts_ns[p];
@@ -1419,11 +1476,13 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       const uint32_t rp = t->req_present[p];
       for (uint32_t d = 4; d < L; ++d)
         if (((rp >> d) & 1u) && t->req[(size_t)d * P + p] != 0) nz |= 1u << d;
-      e->h_pfc[p] = pt.fit.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], nz});
-      e->h_prc[p] = pt.rep.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], 0u});
+      const uint32_t af = t->aff_class ? t->aff_class[p] : BS_AFF_NONE;
+      e->h_pfc[p] = pt.fit.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], nz, af});
+      e->h_prc[p] = pt.rep.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], 0u, af});
     }
   }
   int64_t mx_q[BS_MAX_LANES] = {}, neg_q[BS_MAX_LANES] = {};
+  uint64_t or_q[BS_MAX_LANES] = {};
   {
     uint64_t ot = 0, at = ~0ull;
     uint32_t op = 0, apr = ~0u;
@@ -1436,6 +1495,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
         ok = ok && pt.lo[d] >= -BS_VALUE_LIMIT && pt.hi[d] <= BS_VALUE_LIMIT;
         mx_q[d] = std::max(mx_q[d], std::max(pt.hi[d], pt.lo[d] == INT64_MIN ? INT64_MAX : -pt.lo[d]));
         neg_q[d] = std::max(neg_q[d], pt.lo[d] == INT64_MIN ? INT64_MAX : -pt.lo[d]);
+        or_q[d] |= pt.orq[d];
       }
       ot |= pt.ot; at &= pt.at; op |= pt.op; apr &= pt.apr; miss |= pt.miss; mg = std::max(mg, pt.mg);
     }
@@ -1468,9 +1528,8 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       for (size_t j = 0; j < part[k].fit.size(); ++j) rf[k][j] = e->fit_index.get_or_add(part[k].fit.keys[j]);
       for (size_t j = 0; j < part[k].rep.size(); ++j) rr[k][j] = e->rep_index.get_or_add(part[k].rep.keys[j]);
     }
-#pragma omp parallel num_threads(T)
-    {
-      const int k = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int k = 0; k < T; ++k) {
       const uint32_t a0 = std::min(P, (uint32_t)k * chunk), a1 = std::min(P, a0 + chunk);
       for (uint32_t p = a0; p < a1; ++p) {
         e->h_pfc[p] = rf[k][e->h_pfc[p]];
@@ -1481,10 +1540,29 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   CK(cudaStreamSynchronize(e->s));
   memcpy(e->max_req, mx_q, sizeof(mx_q));
   memcpy(e->neg_req, neg_q, sizeof(neg_q));
+  memcpy(e->or_req, or_q, sizeof(or_q));
   e->P = P;
   e->have_pods = true;
   e->classes_dirty = true;
   e->pod_classes_dirty = true;
+  e->evaluated = false;
+  return BS_OK;
+}
+
+int bs_upload_affinity(bs_engine* e, uint32_t n_classes, const uint32_t* bits) {
+  if (!e || (n_classes && !bits)) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_nodes) return fail(e, BS_E_STATE, "bs_upload_affinity: upload nodes first");
+  BS_DEVICE_GUARD(e);
+  const size_t words = (size_t)n_classes * e->W;
+  if (words) {
+    CK(e->d_aff_bits.ensure(words * 4));
+    CK(cudaMemcpyAsync(e->d_aff_bits.p, bits, words * 4, cudaMemcpyHostToDevice, e->s));
+    CK(cudaStreamSynchronize(e->s));
+  }
+  e->n_aff = n_classes;
+  e->nodes_dirty = true;     // class-fit bits and cluster scans follow the table
+  e->classes_dirty = true;   // class ids are validated against it
   e->evaluated = false;
   return BS_OK;
 }
@@ -1503,17 +1581,25 @@ int bs_evaluate_async(bs_engine* e) {
   return evaluate_async_locked(e);
 }
 
+// checks the sticky error word of the peer exchange; on a timeout the exchange is marked broken
+static int peer_check_locked(bs_engine* e) {
+  if (!e->peer_attached) return BS_OK;
+  CK(cudaStreamSynchronize(e->s4));
+  int bad = 0;
+  CK(cudaMemcpy(&bad, e->d_peer_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (bad) {
+    e->peer_broken = true;
+    return fail(e, BS_E_PEER, "peer exchange timed out: a rank did not arrive (detach and re-attach every rank)");
+  }
+  return BS_OK;
+}
+
 int bs_sync(bs_engine* e) {
   if (!e) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);
   BS_DEVICE_GUARD(e);
   CK(cudaStreamSynchronize(e->s));
-  if (e->peer_attached) {
-    int bad = 0;
-    CK(cudaMemcpy(&bad, e->d_peer_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (bad) return fail(e, BS_E_PEER, "peer exchange timed out: a rank did not arrive");
-  }
-  return BS_OK;
+  return peer_check_locked(e);
 }
 
 int bs_fetch(bs_engine* e, bs_results* out) {
@@ -1693,7 +1779,7 @@ int bs_cluster_check(bs_engine* e, uint64_t sel, uint64_t tol, float percent, co
   if (er == cudaSuccess) {
     PrefixOut po{pre.as<int64_t>(), pp.as<uint32_t>(), stats.as<ClassStats>()};
     NodeTab t = node_tab(e);
-    PrefixSel ps{nullptr, nullptr, 0, 2, sel, tol, percent, nullptr};
+    PrefixSel ps{nullptr, nullptr, nullptr, 0, 2, sel, tol, percent, nullptr};
     PrefixScratch psc{spart.as<int64_t>(), spres.as<uint32_t>(), scst.as<ClassStats>(), sdone.as<uint32_t>()};
     launch_prefix(L, t, ps, psc, po, 1, e->s);
     const uint64_t threads = (uint64_t)n_needs * 32;
@@ -1777,6 +1863,7 @@ int bs_replay(bs_engine* e, const uint32_t* queue, uint32_t n_queue, bs_replay_r
     a.fitmask = e->n_rep_classes <= (uint32_t)REPLAY_MAX_CLASSES ? n_fit.as<uint32_t>() : nullptr;
     a.rsel = e->d_rsel.as<uint64_t>();
     a.rtol = e->d_rtol.as<uint64_t>();
+    a.raff = e->d_raff.as<uint32_t>();
     a.n_rep = e->n_rep_classes;
     {
       // block cache of the cluster scan (replay.cuh): every running sum must stay below 2^62.
@@ -1868,19 +1955,25 @@ int bs_device_buffer(bs_engine* e, int which, void** dev_ptr, size_t* bytes) {
   std::lock_guard<std::mutex> lk(e->mu);
   const uint32_t P = e->P, G = e->G;
   switch (which) {
-    case BS_BUF_FIT_BITMAP: *dev_ptr = e->d_fit_bitmap.p; *bytes = (size_t)P * e->W * 4; break;
-    case BS_BUF_SCORE: *dev_ptr = e->d_score.p; *bytes = (size_t)P * e->N * 8; break;
+    case BS_BUF_FIT_BITMAP: *dev_ptr = e->d_fit_bitmap.p; *bytes = (size_t)P * e->bitmap_pitch * 4; break;   // rows of bs_bitmap_pitch words
+    case BS_BUF_SCORE: *dev_ptr = e->d_score.p; *bytes = (size_t)P * e->score_pitch * 8; break;   // rows of bs_score_pitch elements
     case BS_BUF_ADMIT_BITMAP: *dev_ptr = e->d_admit_bitmap.p; *bytes = (size_t)cdiv(G, 32) * 4; break;
     case BS_BUF_PREFILTER: *dev_ptr = e->d_prefilter.p; *bytes = P; break;
     case BS_BUF_ADMIT: *dev_ptr = e->d_admit.p; *bytes = G; break;
     case BS_BUF_ORDER: *dev_ptr = e->d_order.p; *bytes = (size_t)P * 4; break;
-    case BS_BUF_GATHERED_ADMIT: *dev_ptr = e->d_gather.p; *bytes = (size_t)e->peer_world * e->peer_wpr * 4; break;
+    case BS_BUF_GATHERED_ADMIT:   // the slot set of the last round (they alternate with the parity of the round number)
+      *dev_ptr = e->d_gather.p ? e->d_gather.as<uint32_t>() + (size_t)(e->peer_seq & 1u) * e->peer_world * e->peer_wpr : nullptr;
+      *bytes = (size_t)e->peer_world * e->peer_wpr * 4;
+      break;
     default: return BS_E_INVAL;
   }
   return BS_OK;
 }
 
 void* bs_stream(bs_engine* e) { return e ? (void*)e->s : nullptr; }
+
+uint32_t bs_score_pitch(const bs_engine* e) { return e ? e->score_pitch : 0; }
+uint32_t bs_bitmap_pitch(const bs_engine* e) { return e ? e->bitmap_pitch : 0; }
 
 int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words) {
   if (!e || !words) return BS_E_INVAL;
@@ -1889,8 +1982,8 @@ int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words) 
   if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
   BS_DEVICE_GUARD(e);
   if (n && e->W)
-    CK(cudaMemcpyAsync(words, e->d_fit_bitmap.as<uint32_t>() + (size_t)pod0 * e->W, (size_t)n * e->W * 4,
-                       cudaMemcpyDeviceToHost, e->s));
+    CK(cudaMemcpy2DAsync(words, (size_t)e->W * 4, e->d_fit_bitmap.as<uint32_t>() + (size_t)pod0 * e->bitmap_pitch,
+                         (size_t)e->bitmap_pitch * 4, (size_t)e->W * 4, n, cudaMemcpyDeviceToHost, e->s));
   CK(cudaStreamSynchronize(e->s));
   return BS_OK;
 }
@@ -1940,8 +2033,8 @@ int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores
   if ((uint64_t)pod0 + n > e->P) return BS_E_INDEX;
   BS_DEVICE_GUARD(e);
   if (n && e->N)
-    CK(cudaMemcpyAsync(scores, e->d_score.as<int64_t>() + (size_t)pod0 * e->N, (size_t)n * e->N * 8,
-                       cudaMemcpyDeviceToHost, e->s));
+    CK(cudaMemcpy2DAsync(scores, (size_t)e->N * 8, e->d_score.as<int64_t>() + (size_t)pod0 * e->score_pitch,
+                         (size_t)e->score_pitch * 8, (size_t)e->N * 8, n, cudaMemcpyDeviceToHost, e->s));
   CK(cudaStreamSynchronize(e->s));
   return BS_OK;
 }
@@ -1951,7 +2044,7 @@ int bs_peer_init(bs_engine* e, uint32_t rank, uint32_t world, uint32_t words_per
   std::lock_guard<std::mutex> lk(e->mu);
   BS_DEVICE_GUARD(e);
   if (e->peer_attached) return fail(e, BS_E_STATE, "bs_peer_init: detach first");
-  const size_t bytes = ((size_t)world * words_per_rank + 2 * PEER_MAX_WORLD) * 4;
+  const size_t bytes = peer_buf_words(world, words_per_rank) * 4;
   e->d_gather.release();   // a fresh allocation: the IPC handle names this exact block
   CK(e->d_gather.ensure(bytes));
   CK(e->d_peer_err.ensure(sizeof(int)));
@@ -1959,6 +2052,8 @@ int bs_peer_init(bs_engine* e, uint32_t rank, uint32_t world, uint32_t words_per
   CK(cudaMemsetAsync(e->d_peer_err.p, 0, sizeof(int), e->s));
   CK(cudaStreamSynchronize(e->s));
   e->peer_rank = rank; e->peer_world = world; e->peer_wpr = words_per_rank; e->peer_seq = 0;
+  e->peer_broken = false;
+  if (const char* t = getenv("BS_PEER_TIMEOUT_MS")) e->peer_timeout_ns = (unsigned long long)std::max(1, atoi(t)) * 1000000ull;
   return BS_OK;
 }
 
@@ -2004,11 +2099,35 @@ int bs_peer_detach(bs_engine* e) {
   std::lock_guard<std::mutex> lk(e->mu);
   BS_DEVICE_GUARD(e);
   if (e->s) cudaStreamSynchronize(e->s);
+  if (e->s4) cudaStreamSynchronize(e->s4);
   for (uint32_t r = 0; r < e->peer_world; ++r) {
     if (r != e->peer_rank && e->peer_ptr[r]) cudaIpcCloseMemHandle(e->peer_ptr[r]);
     e->peer_ptr[r] = nullptr;
   }
   e->peer_attached = false;
+  e->peer_broken = false;
+  e->peer_seq = 0;
+  return BS_OK;
+}
+
+int bs_peer_join(bs_engine* e) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  BS_DEVICE_GUARD(e);
+  if (e->peer_attached && e->peer_seq) CK(cudaStreamWaitEvent(e->s, e->ev_gath, 0));
+  return BS_OK;
+}
+
+int bs_fetch_gathered_admit(bs_engine* e, uint32_t* words) {
+  if (!e || !words) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->peer_attached || !e->peer_seq) return fail(e, BS_E_STATE, "bs_fetch_gathered_admit: no exchanged round");
+  BS_DEVICE_GUARD(e);
+  int rc = peer_check_locked(e);   // waits for the round's slots to land (stream s4)
+  if (rc) return rc;
+  const size_t n = (size_t)e->peer_world * e->peer_wpr;
+  CK(cudaMemcpyAsync(words, e->d_gather.as<uint32_t>() + (size_t)(e->peer_seq & 1u) * n, n * 4, cudaMemcpyDeviceToHost, e->s4));
+  CK(cudaStreamSynchronize(e->s4));
   return BS_OK;
 }
 
@@ -2035,5 +2154,15 @@ int bs_kernel_ms(bs_engine* e, int k, float* ms, uint32_t* launches) {
 }
 
 uint64_t bs_launch_count(const bs_engine* e) { return e ? e->launches : 0; }
+
+int bs_fit_shape(bs_engine* e, uint32_t* wide, uint32_t* narrow, uint32_t* scaled) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->lane_map_valid) return fail(e, BS_E_STATE, "bs_fit_shape: evaluate first");
+  if (wide) *wide = e->lane_map.LW;
+  if (narrow) *narrow = e->lane_map.LN;
+  if (scaled) *scaled = e->lane_map.LS;
+  return BS_OK;
+}
 
 }  // extern "C"

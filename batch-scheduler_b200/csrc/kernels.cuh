@@ -7,58 +7,9 @@
 // padded to a multiple of NODE_TILE so tiles can be moved with 1-D TMA bulk
 // copies (cp.async.bulk, 16-byte granules).
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include <type_traits>
-
-#include "../../include/bsched.h"
+#include "common.cuh"
 
 namespace bsk {
-
-constexpr int LANE_CPU = 0, LANE_MEM = 1, LANE_EPH = 2, LANE_PODS = 3;
-// Sentinels for lanes without a map key.  With |table values| <= BS_VALUE_LIMIT = 2^56,
-// |left| <= 2^57 and every real left-req difference is below 2^58 in magnitude, while any
-// difference involving a sentinel is >= 2^61 - 2^57 and < 2^63: it never overflows, never
-// fails the >= 0 test, and never wins the min -> score = min over lanes present on BOTH sides.
-constexpr int64_t ABSENT_LEFT = (int64_t)1 << 61;      // left lane without a map key: never limits
-constexpr int64_t UNCHECKED_REQ = -((int64_t)1 << 61); // request lane without a map key: never checked
-// Narrow lanes: a lane whose every |left| and |req| is <= 2^27 (millicores, pod counts, GPUs ...)
-// is evaluated in int32: |real diff| <= 2^28 < any diff involving a 32-bit sentinel (>= 2^29-2^27),
-// and 2^29 - (-2^29) does not overflow.  The narrow set always contains a fixed lane (always a
-// real value), so the 32-bit min is always a real difference and widens by sign extension.
-constexpr int32_t ABSENT_LEFT32 = 1 << 29;
-constexpr int32_t UNCHECKED_REQ32 = -(1 << 29);
-constexpr int64_t NARROW_LIMIT = (int64_t)1 << 27;
-struct LaneMap {
-  uint8_t wide[BS_MAX_LANES];    // original lane index of wide slot k   (k < LW)
-  uint8_t narrow[BS_MAX_LANES];  // original lane index of narrow slot k (k < LN)
-  uint32_t LW, LN;
-};
-#ifndef BS_FIT_TILE
-#define BS_FIT_TILE 512
-#endif
-constexpr int NODE_TILE = BS_FIT_TILE;                  // nodes per shared-memory tile (512 / 1024 / 2048)
-#ifndef BS_FIT_WARPS
-#define BS_FIT_WARPS 8
-#endif
-#ifndef BS_FIT_PPW
-#define BS_FIT_PPW 4
-#endif
-constexpr int FIT_WARPS = BS_FIT_WARPS;                 // consumer warps (each sweeps PODS_PER_WARP pods)
-constexpr int FIT_THREADS = (FIT_WARPS + 1) * 32;       // + one producer warp that only drives the TMA ring
-constexpr int PODS_PER_WARP = BS_FIT_PPW;               // pods evaluated together per node (ILP)
-constexpr int PODS_PER_CTA = FIT_WARPS * PODS_PER_WARP; // 32
-constexpr int TILE_WORDS = NODE_TILE / 32;              // ballot words per tile and pod
-#ifndef BS_FIT_STAGES
-#define BS_FIT_STAGES 3
-#endif
-constexpr int FIT_STAGES = BS_FIT_STAGES;               // TMA ring depth (full/empty mbarrier pairs)
-// class bits of the TILE_WORDS nodes a lane owns in one tile
-using ColBits = std::conditional<(TILE_WORDS > 32), uint64_t, uint32_t>::type;
-#ifndef BS_FIT_MINB
-#define BS_FIT_MINB 2
-#endif
 
 // round-global scalars living in device memory (no host sync inside a round)
 struct RoundState {
@@ -108,19 +59,27 @@ struct NodeTab {
   const uint64_t* label;
   const uint64_t* taint;
   const uint8_t* flags;
-  uint32_t N, Npad, L;
+  const uint32_t* aff_bits;  // [n_aff][aff_W] host-evaluated node predicates (bs_upload_affinity), or null
+  uint32_t N, Npad, L, aff_W;
 };
 
-// singleNodeResource (core.go:634-670) for node i and class (sel,tol) at pct;
+// The part of PodMatchNodeSelector the 64-bit masks cannot carry (required nodeAffinity terms: In / NotIn /
+// Exists / DoesNotExist / Gt / Lt, ORed terms; core.go:741-759 -> predicates.PodMatchNodeSelector): the
+// caller evaluates each distinct affinity class against every node and uploads one bit per (class, node).
+__device__ __forceinline__ bool aff_ok(const NodeTab& t, uint32_t aff, uint32_t i) {
+  return aff == BS_AFF_NONE || ((t.aff_bits[(size_t)aff * t.aff_W + (i >> 5)] >> (i & 31)) & 1u);
+}
+
+// singleNodeResource (core.go:634-670) for node i and class (sel,tol,aff) at pct;
 // returns the scalar presence mask; v[] gets every lane (zeros when unfit).
 template <int MAXL>
 __device__ __forceinline__ uint32_t single_node_resource(const NodeTab& t, uint32_t i, uint64_t sel,
-                                                         uint64_t tol, float pct, int64_t* v) {
+                                                         uint64_t tol, uint32_t aff, float pct, int64_t* v) {
 #pragma unroll
   for (int d = 0; d < MAXL; ++d) v[d] = 0;
   const uint8_t f = t.flags[i];
   if (f & BS_NODE_TAINTS_ERR) return 0;                                  // :639-641
-  if (!check_fit(t.label[i], t.taint[i], sel, tol)) return 0;           // :642-645
+  if (!check_fit(t.label[i], t.taint[i], sel, tol) || !aff_ok(t, aff, i)) return 0;   // :642-645
   int64_t pc = t.requested[(size_t)LANE_PODS * t.Npad + i];              // :650-653
   if (pc == 0) pc = t.pod_count[i];
   v[LANE_PODS] = scale_f32(t.alloc[(size_t)LANE_PODS * t.Npad + i], pct) - pc;  // :656
@@ -160,7 +119,7 @@ __device__ __forceinline__ bool compare_res(const int64_t* left, uint32_t lpres,
 // wide (int64) and narrow (int32) lane tables of the round's LaneMap.
 // Restates singleNodeResource core.go:647-668.  Padding nodes (>= N) get zeros.
 __global__ void node_left_kernel(NodeTab t, LaneMap lm, int64_t* __restrict__ left_w /*[LW][Npad]*/,
-                                 int32_t* __restrict__ left_n /*[LN][Npad]*/,
+                                 int32_t* __restrict__ left_n /*[LN+LS][Npad]: narrow lanes, then scaled lanes*/,
                                  uint32_t* __restrict__ left_present /*[Npad]*/,
                                  int64_t* __restrict__ left_plain /*[4][Npad] getLeftResource, or null*/) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,7 +138,7 @@ __global__ void node_left_kernel(NodeTab t, LaneMap lm, int64_t* __restrict__ le
   }
   if (i >= t.N) {
     for (uint32_t k = 0; k < lm.LW; ++k) left_w[(size_t)k * t.Npad + i] = 0;
-    for (uint32_t k = 0; k < lm.LN; ++k) left_n[(size_t)k * t.Npad + i] = 0;
+    for (uint32_t k = 0; k < lm.LN + lm.LS; ++k) left_n[(size_t)k * t.Npad + i] = 0;
     left_present[i] = 0;
     return;
   }
@@ -203,6 +162,11 @@ __global__ void node_left_kernel(NodeTab t, LaneMap lm, int64_t* __restrict__ le
     bool pres;
     const int64_t v = lane_left(lm.narrow[k], pres);
     left_n[(size_t)k * t.Npad + i] = pres ? (int32_t)v : ABSENT_LEFT32;
+  }
+  for (uint32_t k = 0; k < lm.LS; ++k) {   // units of 2^sunit: exact, every value of the lane is a multiple
+    bool pres;
+    const int64_t v = lane_left(lm.scaled[k], pres);
+    left_n[(size_t)(lm.LN + k) * t.Npad + i] = pres ? (int32_t)(v >> lm.sunit[k]) : ABSENT_LEFTS;
   }
   left_present[i] = both;
 }
@@ -267,7 +231,7 @@ __global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, fl
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.N) return;
   int64_t v[BS_MAX_LANES];
-  const uint32_t pres = single_node_resource<BS_MAX_LANES>(t, i, sel, tol, pct, v);
+  const uint32_t pres = single_node_resource<BS_MAX_LANES>(t, i, sel, tol, BS_AFF_NONE, pct, v);
   for (uint32_t d = 0; d < t.L; ++d) left[(size_t)d * t.N + i] = v[d];
   present[i] = pres;
 }
@@ -281,14 +245,15 @@ __global__ void node_left_class_kernel(NodeTab t, uint64_t sel, uint64_t tol, fl
 // that tile, so the hot loop needs one coalesced 4-byte load per (pod, tile).
 __global__ void class_fit_kernel(NodeTab t, const uint32_t* __restrict__ left_present,
                                  const uint64_t* __restrict__ csel, const uint64_t* __restrict__ ctol,
-                                 const uint32_t* __restrict__ cnz, uint32_t n_classes, uint32_t n_tiles,
+                                 const uint32_t* __restrict__ cnz, const uint32_t* __restrict__ caff,
+                                 uint32_t n_classes, uint32_t n_tiles,
                                  ColBits* __restrict__ classfit, uint32_t class0) {
   const uint32_t c = class0 + blockIdx.y;   // gridDim.y is capped at 65535: classes go in chunks
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;  // tile * 32 + lane
   if (slot >= n_tiles * 32 || c >= n_classes) return;
   const uint32_t tile = slot >> 5, lane = slot & 31;
   const uint64_t sel = csel[c], tol = ctol[c];
-  const uint32_t nz = cnz[c];
+  const uint32_t nz = cnz[c], aff = caff[c];
   ColBits bits = 0;
 #pragma unroll
   for (int j = 0; j < TILE_WORDS; ++j) {
@@ -297,7 +262,7 @@ __global__ void class_fit_kernel(NodeTab t, const uint32_t* __restrict__ left_pr
     if (i < t.N) {
       const uint8_t f = t.flags[i];
       ok = !node_skipped(f) && !(f & BS_NODE_TAINTS_ERR) && check_fit(t.label[i], t.taint[i], sel, tol) &&
-           ((nz & ~left_present[i]) == 0);
+           aff_ok(t, aff, i) && ((nz & ~left_present[i]) == 0);
     }
     bits |= (ColBits)(ok ? 1u : 0u) << j;
   }
@@ -551,6 +516,7 @@ struct PrefixScratch {
 struct PrefixSel {
   const uint64_t* rsel;
   const uint64_t* rtol;
+  const uint32_t* raff;
   uint32_t c0;
   int mode;
   uint64_t xsel, xtol;
@@ -558,15 +524,15 @@ struct PrefixSel {
   const RoundState* st;
 };
 __device__ __forceinline__ bool prefix_select(const PrefixSel& ps, uint32_t slot, uint64_t& sel, uint64_t& tol,
-                                              float& pct) {
+                                              uint32_t& aff, float& pct) {
   if (ps.mode == 0) {
     if (!ps.st->case_a || ps.st->max_group < 0) return false;
-    sel = ps.rsel[ps.c0 + slot]; tol = ps.rtol[ps.c0 + slot]; pct = 1.0f;
+    sel = ps.rsel[ps.c0 + slot]; tol = ps.rtol[ps.c0 + slot]; aff = ps.raff[ps.c0 + slot]; pct = 1.0f;
   } else if (ps.mode == 1) {
     if (ps.st->case_a || ps.st->max_group < 0) return false;
-    sel = ps.rsel[ps.st->max_class]; tol = ps.rtol[ps.st->max_class]; pct = 0.7f;
+    sel = ps.rsel[ps.st->max_class]; tol = ps.rtol[ps.st->max_class]; aff = ps.raff[ps.st->max_class]; pct = 0.7f;
   } else {
-    sel = ps.xsel; tol = ps.xtol; pct = ps.xpct;
+    sel = ps.xsel; tol = ps.xtol; aff = BS_AFF_NONE; pct = ps.xpct;
   }
   return true;
 }
@@ -575,9 +541,10 @@ template <int MAXL>
 __global__ void __launch_bounds__(PREFIX_CHUNK)
 prefix_partial_kernel(NodeTab t, PrefixSel ps, PrefixScratch sc, uint32_t n_chunks) {
   uint64_t sel, tol;
+  uint32_t aff;
   float pct;
   const uint32_t slot = blockIdx.y, chunk = blockIdx.x;
-  if (!prefix_select(ps, slot, sel, tol, pct)) return;
+  if (!prefix_select(ps, slot, sel, tol, aff, pct)) return;
   __shared__ int64_t s_tot[PREFIX_CHUNK / 32][MAXL];
   __shared__ uint32_t s_pres[PREFIX_CHUNK / 32];
   const uint32_t i = chunk * PREFIX_CHUNK + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -585,7 +552,7 @@ prefix_partial_kernel(NodeTab t, PrefixSel ps, PrefixScratch sc, uint32_t n_chun
 #pragma unroll
   for (int d = 0; d < MAXL; ++d) v[d] = 0;
   uint32_t pres = 0;
-  if (i < t.N && !node_skipped(t.flags[i])) pres = single_node_resource<MAXL>(t, i, sel, tol, pct, v);
+  if (i < t.N && !node_skipped(t.flags[i])) pres = single_node_resource<MAXL>(t, i, sel, tol, aff, pct, v);
   for (int o = 16; o; o >>= 1) {
 #pragma unroll
     for (int d = 0; d < MAXL; ++d) v[d] += __shfl_xor_sync(0xffffffffu, v[d], o);
@@ -613,9 +580,10 @@ template <int MAXL>
 __global__ void __launch_bounds__(PREFIX_CHUNK)
 prefix_scan_kernel(NodeTab t, PrefixSel ps, PrefixScratch sc, uint32_t n_chunks, PrefixOut out) {
   uint64_t sel, tol;
+  uint32_t aff;
   float pct;
   const uint32_t slot = blockIdx.y, chunk = blockIdx.x;
-  if (!prefix_select(ps, slot, sel, tol, pct)) return;
+  if (!prefix_select(ps, slot, sel, tol, aff, pct)) return;
   const uint32_t N = t.N, L = t.L;
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NW = PREFIX_CHUNK / 32;
@@ -670,7 +638,7 @@ prefix_scan_kernel(NodeTab t, PrefixSel ps, PrefixScratch sc, uint32_t n_chunks,
 #pragma unroll
   for (int d = 0; d < MAXL; ++d) v[d] = 0;
   uint32_t pres = 0;
-  if (vis) pres = single_node_resource<MAXL>(t, i, sel, tol, pct, v);
+  if (vis) pres = single_node_resource<MAXL>(t, i, sel, tol, aff, pct, v);
   for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
     for (int d = 0; d < MAXL; ++d) {
@@ -970,421 +938,6 @@ __global__ void group_idle_admit_kernel(GroupTab g, GroupEff e, uint8_t* __restr
   if (ready) atomicOr(&admit_bitmap[i >> 5], 1u << (i & 31));
 }
 
-// ---------------------------------------------------------------------------
-// K6  gang_fit_kernel — THE hot kernel.  For every (pod, node) pair:
-//   fit   = classfit bit  AND  min_d(left_d - req_d) >= 0
-//           (compareResourceAndRequire(singleNodeResource(node,pod,1), require(pod)),
-//            core.go:634-699, as asserted by core_test.go:108-110)
-//   score = fit ? min_d(left_d - req_d) : INT64_MIN      (residual capacity)
-// then, in the same launch, per pod: feasible count + best node (warp shuffles),
-// and per group: the Permit readiness count (core.go:303) by a warp-segmented
-// reduction + one atomic per run, the last pod of a group (ticket) writing the
-// admit / Wait / Unschedulable verdict.
-//
-// Mapping: a CTA = FIT_WARPS consumer warps + one producer warp.  It owns PODS_PER_CTA
-// pods (each consumer warp PODS_PER_WARP of them, requests in registers) and sweeps the
-// whole node table in tiles of NODE_TILE nodes; the producer lane streams the tiles into a
-// FIT_STAGES-deep shared-memory ring with 1-D TMA bulk copies (one per lane row), guarded
-// by full/empty mbarrier pairs.  A lane owns nodes lane, lane+32, ... of the tile, keeps
-// their `left` in registers and evaluates PODS_PER_WARP pods against them at a time.  Score
-// rows are written with 8-byte streaming stores, 256 contiguous bytes per warp store.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                             uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-__device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
-// high word of an int64, opaque to the optimiser (it otherwise re-forms a 2-instruction 64-bit compare)
-__device__ __forceinline__ int32_t hi32(int64_t v) {
-  int32_t lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-  (void)lo;
-  return hi;
-}
-__device__ __forceinline__ uint32_t lo32(int64_t v) {
-  int32_t lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-  (void)hi;
-  return (uint32_t)lo;
-}
-__device__ __forceinline__ long long pack64(uint32_t lo, uint32_t hi) {
-  long long v;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
-  return v;
-}
-#ifndef BS_FIT_STORE
-#define BS_FIT_STORE 0
-#endif
-// score store: cache-policy variants for experiments (0 = .cs streaming / evict-first)
-__device__ __forceinline__ void score_store(int64_t* p, long long v) {
-#if BS_FIT_STORE == 0
-  __stcs(reinterpret_cast<long long*>(p), v);
-#elif BS_FIT_STORE == 1
-  *reinterpret_cast<long long*>(p) = v;
-#elif BS_FIT_STORE == 2
-  __stwt(reinterpret_cast<long long*>(p), v);
-#else
-  __stcg(reinterpret_cast<long long*>(p), v);
-#endif
-}
-__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-
-struct FitArgs {
-  const int64_t* left_w;     // [LW][Npad] wide lanes
-  const int32_t* left_n;     // [LN][Npad] narrow lanes
-  const ColBits* classfit;   // [classes][n_tiles][32] transposed class bits
-  const int64_t* req;        // [L][P]
-  const uint32_t* req_present;
-  const uint32_t* fit_class;
-  const int32_t* gid;
-  const uint8_t* prefilter;
-  LaneMap lm;
-  // group side
-  const uint32_t* min_member;
-  const uint32_t* scheduled;
-  const uint32_t* matched;
-  uint32_t* in_round;
-  uint32_t* contrib;
-  uint32_t* done;
-  uint8_t* admit;
-  uint32_t* admit_bitmap;
-  // outputs
-  uint32_t* feasible_count;
-  int32_t* best_node;
-  int64_t* best_score;
-  uint32_t* fit_bitmap;   // [Ppad][W] or null   (Ppad = P rounded up to PODS_PER_CTA: no pod guard)
-  int64_t* score;         // [Ppad][N] or null
-  // Row pitches in BYTES as 64-bit kernel parameters: ptxas 12.9 miscompiles the uniform-datapath
-  // form of `int32 base + (uint32 Npad << 2)` (a lone ULEA with the high word zeroed) when the
-  // TMA source address of a narrow row is derived from a 32-bit Npad; 64-bit pitches avoid it.
-  uint64_t left_w_pitch, left_n_pitch;
-  uint32_t P, N, Npad, W, G;
-  uint32_t defer_admit;   // 1: the group verdicts are left to gang_admit_kernel (the PreFilter chain runs beside this kernel)
-};
-
-// One node tile for the PODS_PER_WARP pods of a warp.  TAIL: the tile holds padding
-// nodes (>= N): score stores are guarded; full tiles carry no per-pair guard at all.
-// Wide lanes: 64-bit subtract + compare/select min.  Narrow lanes: one 32-bit VIADDMNMX
-// (fused subtract+min) each.  Ballot words go to a per-warp shared-memory slab (one STS per
-// pair, every lane writes the same word: no predicate, no ALU); after the tile lane
-// j < TILE_WORDS pops word j back for the fit-bitmap store (64 B per pod, coalesced) and the
-// feasible count (popcount, reduced across the warp once at the very end).
-// running best score of a lane: int32 on the narrow fast path (scores of fitting pairs are < 2^28,
-// "none" = -1), int64 otherwise ("none" = INT64_MIN)
-template <bool NARROW> struct BestT { using type = int64_t; };
-template <> struct BestT<true> { using type = int32_t; };
-
-template <int LW, int LN, bool TAIL>
-__device__ __forceinline__ void fit_tile(const FitArgs& a, const int64_t* __restrict__ tlw,
-                                         const int32_t* __restrict__ tln,
-                                         const int64_t (&rqw)[PODS_PER_WARP][LW > 0 ? LW : 1],
-                                         const int32_t (&rqn)[PODS_PER_WARP][LN > 0 ? LN : 1],
-                                         const ColBits (&colbits)[PODS_PER_WARP], int64_t* sp0,
-                                         size_t row_stride, uint32_t* s_words, uint32_t node_base,
-                                         uint32_t lane, bool want_score,
-                                         typename BestT<(LN > 0)>::type (&best_s)[PODS_PER_WARP],
-                                         int32_t (&best_n)[PODS_PER_WARP]) {
-  int64_t* sp[PODS_PER_WARP];
-#pragma unroll
-  for (int r = 0; r < PODS_PER_WARP; ++r) sp[r] = sp0 + r * row_stride;
-  const int64_t* tpw = tlw + lane;
-  const int32_t* tpn = tln + lane;
-  int32_t node = (int32_t)(node_base + lane);
-  uint32_t wp = smem_u32(s_words);
-#pragma unroll 1
-  for (int jb = 0; jb < TILE_WORDS; jb += 4) {
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      int64_t lfw[LW > 0 ? LW : 1];
-      int32_t lfn[LN > 0 ? LN : 1];
-#pragma unroll
-      for (int d = 0; d < LW; ++d) lfw[d] = tpw[d * NODE_TILE + jj * 32];
-#pragma unroll
-      for (int d = 0; d < LN; ++d) lfn[d] = tpn[d * NODE_TILE + jj * 32];
-      const bool in_range = !TAIL || ((uint32_t)node + jj * 32 < a.N);
-#pragma unroll
-      for (int r = 0; r < PODS_PER_WARP; ++r) {
-        if (LN > 0) {
-          // Narrow fast path.  t = min over the narrow lanes is a REAL difference (the narrow set
-          // holds a fixed lane) with |t| <= 2^28, and the pair's score m = min over all lanes <= t.
-          // So when the pair fits (every difference >= 0) m is a 32-bit value: wide differences
-          // only matter through (a) their sign and (b) their low word when the high word is 0.
-          int32_t t = lfn[0] - rqn[r][0];
-#ifndef BS_FIT_NOCOMPUTE   // (experiment switch: store pattern without the arithmetic)
-#pragma unroll
-          for (int d = 1; d < LN; ++d) t = min(t, lfn[d] - rqn[r][d]);
-#endif
-          uint32_t m32 = (uint32_t)t;
-          int32_t sgn = t;
-#ifndef BS_FIT_NOCOMPUTE
-#pragma unroll
-#endif
-          for (int d = 0; d < (LW
-#ifdef BS_FIT_NOCOMPUTE
-                                  * 0
-#endif
-                              ); ++d) {
-            const int64_t w = lfw[d] - rqw[r][d];
-            const int32_t whi = hi32(w);
-            sgn |= whi;                                               // any negative difference -> sign bit
-            m32 = min(m32, whi != 0 ? 0xffffffffu : lo32(w));         // unsigned: valid when all are >= 0
-          }
-          const bool fit = (sgn >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
-          sts_u32(wp + (r * TILE_WORDS + jj) * 4, __ballot_sync(0xffffffffu, fit));
-          if (fit && (int32_t)m32 > best_s[r]) { best_s[r] = (int32_t)m32; best_n[r] = node + jj * 32; }
-          if (want_score && in_range)
-            score_store(sp[r] + jj * 32, pack64(fit ? m32 : 0u, fit ? 0u : 0x80000000u));
-        } else {
-          int64_t m = lfw[0] - rqw[r][0];
-#pragma unroll
-          for (int d = 1; d < LW; ++d) m = min64(m, lfw[d] - rqw[r][d]);
-          const bool fit = (hi32(m) >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
-          sts_u32(wp + (r * TILE_WORDS + jj) * 4, __ballot_sync(0xffffffffu, fit));
-          if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
-          if (want_score && in_range)
-            score_store(sp[r] + jj * 32, fit ? (long long)m : (long long)INT64_MIN);
-        }
-      }
-    }
-    tpw += 128;
-    tpn += 128;
-    node += 128;
-    wp += 16;
-#pragma unroll
-    for (int r = 0; r < PODS_PER_WARP; ++r) sp[r] += 128;
-  }
-}
-
-__host__ __device__ constexpr size_t fit_tile_bytes(int LW, int LN) {
-  return (size_t)NODE_TILE * (8 * LW + 4 * LN);
-}
-__host__ __device__ constexpr int fit_min_blocks(int LW, int LN) {
-  return (2 * LW + LN) <= 10 ? BS_FIT_MINB : ((2 * LW + LN) <= 18 ? 2 : 1);
-}
-
-template <int LW, int LN>
-__global__ void __launch_bounds__(FIT_THREADS, fit_min_blocks(LW, LN)) gang_fit_kernel(FitArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [FIT_STAGES]{[LW][NODE_TILE] i64, [LN][NODE_TILE] i32} | req_w | req_n | mbarriers | ballot words
-  constexpr size_t STAGE_BYTES = fit_tile_bytes(LW, LN);
-  unsigned char* s_tile = smem_raw;
-  int64_t* s_req_w = reinterpret_cast<int64_t*>(smem_raw + FIT_STAGES * STAGE_BYTES);
-  int32_t* s_req_n = reinterpret_cast<int32_t*>(s_req_w + PODS_PER_CTA * LW);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(
-      (reinterpret_cast<uintptr_t>(s_req_n + PODS_PER_CTA * LN) + 7) & ~(uintptr_t)7);
-  uint64_t* s_full = s_bar;                 // [FIT_STAGES] TMA bytes landed
-  uint64_t* s_empty = s_bar + FIT_STAGES;   // [FIT_STAGES] every warp is done with the stage
-  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(s_bar + 2 * FIT_STAGES);
-
-  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  uint32_t* s_words = s_words_all + wid * PODS_PER_WARP * TILE_WORDS;
-  const uint32_t pod0 = blockIdx.x * PODS_PER_CTA;
-  const uint32_t wpod0 = pod0 + wid * PODS_PER_WARP;  // first pod of this warp
-  const uint32_t n_tiles = a.Npad / NODE_TILE;
-
-  if (tid == 0) {
-    for (int st = 0; st < FIT_STAGES; ++st) {
-      mbar_init(&s_full[st], 1);
-      mbar_init(&s_empty[st], FIT_WARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // stage the CTA's pod requests (sentinel for lanes without a map key)
-  for (uint32_t i = tid; i < PODS_PER_CTA * (LW + LN); i += FIT_THREADS) {
-    const uint32_t pl = i / (LW + LN), k = i % (LW + LN);
-    const uint32_t p = pod0 + pl;
-    const bool is_w = k < (uint32_t)LW;
-    const uint32_t d = is_w ? a.lm.wide[k] : a.lm.narrow[k - LW];
-    int64_t v = 0;
-    bool present = true;
-    if (p < a.P) {
-      present = d < 4 || ((a.req_present[p] >> d) & 1u);
-      v = present ? a.req[(size_t)d * a.P + p] : 0;
-    }
-    if (is_w) s_req_w[pl * LW + k] = present ? v : UNCHECKED_REQ;
-    else s_req_n[pl * LN + (k - LW)] = present ? (int32_t)v : UNCHECKED_REQ32;
-  }
-  __syncthreads();
-  auto issue = [&](uint32_t tile, uint32_t stage) {
-    mbar_expect_tx(&s_full[stage], (uint32_t)STAGE_BYTES);
-    unsigned char* dst = s_tile + stage * STAGE_BYTES;
-    const unsigned char* src_w = reinterpret_cast<const unsigned char*>(a.left_w) + (uint64_t)tile * (NODE_TILE * 8);
-    const unsigned char* src_n = reinterpret_cast<const unsigned char*>(a.left_n) + (uint64_t)tile * (NODE_TILE * 4);
-#pragma unroll
-    for (int d = 0; d < LW; ++d)
-      tma_bulk_g2s(dst + (size_t)d * NODE_TILE * 8, src_w + (uint64_t)d * a.left_w_pitch, NODE_TILE * 8,
-                   &s_full[stage]);
-#pragma unroll
-    for (int d = 0; d < LN; ++d)
-      tma_bulk_g2s(dst + (size_t)LW * NODE_TILE * 8 + (size_t)d * NODE_TILE * 4,
-                   src_n + (uint64_t)d * a.left_n_pitch, NODE_TILE * 4, &s_full[stage]);
-  };
-  // Warp specialisation: warp FIT_WARPS is the producer.  Its lane 0 walks the tiles, waits until
-  // every consumer warp has released the stage (`empty`), and issues the TMA bulk copies that
-  // complete on `full`.  Consumers never meet at a CTA-wide barrier during the sweep.
-  if (wid == FIT_WARPS) {
-    if (lane == 0) {
-      for (uint32_t tile = 0; tile < n_tiles; ++tile) {
-        const uint32_t st = tile % FIT_STAGES, use = tile / FIT_STAGES;
-        if (use > 0) mbar_wait(&s_empty[st], (use - 1) & 1);
-        issue(tile, st);
-      }
-    }
-    return;
-  }
-
-  // per-pod state of this warp (requests are warp-uniform, in registers for the whole sweep).
-  // The score / bitmap buffers hold PODS_PER_CTA-padded rows, so pods >= P need no guard.
-  const bool want_score = a.score != nullptr;
-  const bool want_bitmap = a.fit_bitmap != nullptr;
-  uint32_t cnt[PODS_PER_WARP];
-  typename BestT<(LN > 0)>::type best_s[PODS_PER_WARP];
-  int32_t best_n[PODS_PER_WARP];
-  int64_t rqw[PODS_PER_WARP][LW > 0 ? LW : 1];
-  int32_t rqn[PODS_PER_WARP][LN > 0 ? LN : 1];
-  uint32_t coff[PODS_PER_WARP];
-#pragma unroll
-  for (int r = 0; r < PODS_PER_WARP; ++r) {
-    cnt[r] = 0; best_n[r] = -1;
-    best_s[r] = LN > 0 ? (typename BestT<(LN > 0)>::type)(-1) : (typename BestT<(LN > 0)>::type)INT64_MIN;
-    const uint32_t p = wpod0 + r;
-    coff[r] = (p < a.P ? a.fit_class[p] : 0u) * n_tiles * 32 + lane;
-#pragma unroll
-    for (int d = 0; d < LW; ++d) rqw[r][d] = s_req_w[(wid * PODS_PER_WARP + r) * LW + d];
-#pragma unroll
-    for (int d = 0; d < LN; ++d) rqn[r][d] = s_req_n[(wid * PODS_PER_WARP + r) * LN + d];
-  }
-
-  // Consumers: a warp releases a stage by arriving on its `empty` mbarrier and may run up to
-  // FIT_STAGES-1 tiles ahead of the slowest warp.
-  uint32_t stage = 0, phase = 0;
-  for (uint32_t tile = 0; tile < n_tiles; ++tile) {
-    ColBits colbits[PODS_PER_WARP];
-#pragma unroll
-    for (int r = 0; r < PODS_PER_WARP; ++r) colbits[r] = __ldg(a.classfit + coff[r] + tile * 32);
-    mbar_wait(&s_full[stage], phase);
-    const int64_t* tlw = reinterpret_cast<const int64_t*>(s_tile + stage * STAGE_BYTES);
-    const int32_t* tln = reinterpret_cast<const int32_t*>(s_tile + stage * STAGE_BYTES + (size_t)LW * NODE_TILE * 8);
-    const uint32_t node_base = tile * NODE_TILE;
-    int64_t* sp0 = want_score ? a.score + (size_t)wpod0 * a.N + node_base + lane : nullptr;
-    if (node_base + NODE_TILE <= a.N)
-      fit_tile<LW, LN, false>(a, tlw, tln, rqw, rqn, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
-    else
-      fit_tile<LW, LN, true>(a, tlw, tln, rqw, rqn, colbits, sp0, a.N, s_words, node_base, lane, want_score, best_s, best_n);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the stage
-#pragma unroll
-    for (int w0 = 0; w0 < TILE_WORDS; w0 += 32) {
-      if (w0 + lane < TILE_WORDS) {
-        const uint32_t word = (node_base >> 5) + w0 + lane;
-#pragma unroll
-        for (int r = 0; r < PODS_PER_WARP; ++r) {
-          const uint32_t w = s_words[r * TILE_WORDS + w0 + lane];
-          cnt[r] += __popc(w);
-          if (want_bitmap && word < a.W) a.fit_bitmap[(size_t)(wpod0 + r) * a.W + word] = w;
-        }
-      }
-    }
-    __syncwarp();                                   // the ballot slab is rewritten by the next tile
-    if (++stage == FIT_STAGES) { stage = 0; phase ^= 1; }
-  }
-
-  // per-pod reductions across the warp: best = max score, lowest node on ties
-  uint32_t my_gid = 0xffffffffu, my_pass = 0;
-#pragma unroll
-  for (int k = 0; k < PODS_PER_WARP; ++k) {
-    int32_t n = best_n[k];
-    int64_t s = n < 0 ? INT64_MIN : (int64_t)best_s[k];
-    uint32_t c = cnt[k];
-    for (int o = 16; o; o >>= 1) {
-      const int64_t os = __shfl_xor_sync(0xffffffffu, s, o);
-      const int32_t on = __shfl_xor_sync(0xffffffffu, n, o);
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-      if (on >= 0 && (n < 0 || os > s || (os == s && on < n))) { s = os; n = on; }
-    }
-    const uint32_t p = wpod0 + k;
-    if (p < a.P) {
-      if (lane == 0) {
-        a.feasible_count[p] = c;
-        a.best_node[p] = n;
-        a.best_score[p] = s;
-      }
-      if (!a.defer_admit && lane == (uint32_t)k) {
-        const int32_t g = a.gid[p];
-        if (g >= 0 && (uint32_t)g < a.G) {
-          my_gid = (uint32_t)g;
-          my_pass = (a.prefilter[p] == BS_PF_PASS && c > 0) ? 1u : 0u;
-        }
-      }
-    }
-  }
-  // warp-segmented reduction over lanes 0..PODS_PER_WARP-1: runs of equal gid
-  if (!a.defer_admit) {
-    const uint32_t prev_gid = __shfl_up_sync(0xffffffffu, my_gid, 1);
-    const bool active = lane < PODS_PER_WARP && my_gid != 0xffffffffu;
-    const bool head = active && (lane == 0 || prev_gid != my_gid);
-    uint32_t run_pass = my_pass, run_len = active ? 1u : 0u;
-#pragma unroll
-    for (int o = 1; o < PODS_PER_WARP; ++o) {
-      const uint32_t og = __shfl_down_sync(0xffffffffu, my_gid, o);
-      const uint32_t op = __shfl_down_sync(0xffffffffu, my_pass, o);
-      // run_len == o  <=>  every lane in between carried the same gid (contiguous run)
-      if (head && run_len == (uint32_t)o && lane + o < PODS_PER_WARP && og == my_gid) {
-        run_pass += op;
-        run_len += 1;
-      }
-    }
-    if (head) {
-      if (run_pass) atomicAdd(&a.contrib[my_gid], run_pass);
-      __threadfence();
-      const uint32_t ticket = atomicAdd(&a.done[my_gid], run_len) + run_len;
-      if (ticket == a.in_round[my_gid]) {
-        // last pod of the group: Permit readiness (core.go:303) on the full count
-        __threadfence();
-        const uint32_t c = atomicAdd(&a.contrib[my_gid], 0u);
-        const uint32_t total = a.matched[my_gid] + c;
-        uint8_t verdict;
-        if (c == 0) verdict = BS_UNSCHEDULABLE;
-        else verdict = (total >= (uint32_t)(a.min_member[my_gid] - a.scheduled[my_gid])) ? BS_ADMIT : BS_WAIT;
-        a.admit[my_gid] = verdict;
-        if (verdict == BS_ADMIT) atomicOr(&a.admit_bitmap[my_gid >> 5], 1u << (my_gid & 31));
-      }
-    }
-  }
-}
-
 // K6b  gang_admit_kernel — the per-group half of Permit (core.go:303) as its own launch: one pod per
 // thread, runs of equal gid merged inside the warp, one atomic per run, the run that completes the
 // group's pod count writes the verdict.  Used when the PreFilter chain runs on a side stream beside
@@ -1551,14 +1104,23 @@ __global__ void __launch_bounds__(256) filter_kernel(FilterArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// K8  peer_exchange_kernel — all-gather of the admit bitmap over NVLink peer memory, fused into
-// the round as its last kernel (one CTA).  Protocol per evaluation `seq` (1, 2, ...):
-//   1. wait until every peer has acknowledged seq-1 (their buffers may be overwritten);
-//   2. store this rank's words into slot[rank] of every peer's gather buffer (plain coalesced
-//      stores to mapped peer addresses), __threadfence_system(), publish flag[rank] = seq there;
-//   3. wait until flag[r] == seq for every r in the local buffer (all slots have landed);
-//   4. write ack[rank] = seq to every peer.
-// All spins are bounded (clock64); on a timeout *err is set and the kernel leaves.
+// K8  peer exchange — all-gather of the admit bitmap over NVLink peer memory (CUDA IPC), as two
+// small kernels so that no rank ever spins on its critical path:
+//   peer_push_kernel  (main stream, last kernel of round `seq`; one CTA per destination rank):
+//       stores this rank's words into slot[seq & 1][rank] of every peer's gather buffer (plain
+//       coalesced stores to mapped peer addresses), __threadfence_system(), then publishes
+//       flag[seq & 1][rank] = seq at the peer.
+//   peer_wait_kernel  (side stream, one warp): waits until flag[seq & 1][r] >= seq for every r,
+//       i.e. until every rank's slot of round `seq` has landed here.  Consumers of the gathered
+//       bitmap (bs_fetch_gathered_admit, bs_sync, bs_peer_join) order themselves behind it.
+// The gather buffer holds TWO slot sets, indexed by the parity of seq.  Slot set seq & 1 last held
+// round seq-2; a rank pushes round seq only after its own wait for round seq-1 has finished (the
+// engine orders the push behind that event), and a peer publishes its flag for seq-1 only after it
+// has consumed round seq-2 (same rule on its side, stream order) — so the overwrite is safe without
+// acknowledgements, and the next round's fit kernel runs while the previous round's wait is
+// still spinning: a late rank delays its peers only once it is more than one round behind.
+// The spin is bounded (globaltimer); on a timeout *err is set, the engine marks the exchange
+// broken and every later call fails fast with BS_E_PEER until the ranks detach and re-attach.
 constexpr int PEER_MAX_WORLD = 16;
 struct PeerArgs {
   uint32_t* peer_buf[PEER_MAX_WORLD];  // mapped base of every rank's gather buffer (own = local)
@@ -1566,58 +1128,47 @@ struct PeerArgs {
   uint32_t rank, world, words_per_rank, n_words;  // n_words <= words_per_rank valid words
   uint32_t seq;
   int* err;
+  unsigned long long timeout_ns;
 };
-// buffer layout: [world][words_per_rank] data | [PEER_MAX_WORLD] flags | [PEER_MAX_WORLD] acks
-__device__ __forceinline__ uint32_t* peer_flags(uint32_t* base, uint32_t world, uint32_t wpr) { return base + (size_t)world * wpr; }
-__device__ __forceinline__ bool peer_spin(volatile uint32_t* p, uint32_t want) {
-  const long long t0 = clock64();
-  while (*p < want) {
-    __nanosleep(128);
-    if (clock64() - t0 > 6000000000ll) return false;   // ~3 s
-  }
-  return true;
+// buffer layout: [2][world][words_per_rank] data | [2][PEER_MAX_WORLD] flags
+__host__ __device__ inline size_t peer_buf_words(uint32_t world, uint32_t wpr) {
+  return (size_t)2 * world * wpr + 2 * PEER_MAX_WORLD;
 }
-__global__ void __launch_bounds__(256) peer_exchange_kernel(PeerArgs a) {
-  __shared__ int s_bad;
-  uint32_t* mine = a.peer_buf[a.rank];
-  volatile uint32_t* my_flags = peer_flags(mine, a.world, a.words_per_rank);
-  volatile uint32_t* my_acks = my_flags + PEER_MAX_WORLD;
-  if (threadIdx.x == 0) s_bad = 0;
+__device__ __forceinline__ uint32_t* peer_slot(uint32_t* base, uint32_t world, uint32_t wpr, uint32_t parity, uint32_t r) {
+  return base + ((size_t)parity * world + r) * wpr;
+}
+__device__ __forceinline__ uint32_t* peer_flags(uint32_t* base, uint32_t world, uint32_t wpr, uint32_t parity) {
+  return base + (size_t)2 * world * wpr + (size_t)parity * PEER_MAX_WORLD;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(256) peer_push_kernel(PeerArgs a) {
+  const uint32_t r = blockIdx.x, par = a.seq & 1u;
+  uint32_t* dst = peer_slot(a.peer_buf[r], a.world, a.words_per_rank, par, a.rank);
+  for (uint32_t w = threadIdx.x; w < a.words_per_rank; w += blockDim.x) dst[w] = w < a.n_words ? a.local_bitmap[w] : 0u;
+  __threadfence_system();
   __syncthreads();
-  // 1. peers are done reading the previous round out of their buffers
-  if (threadIdx.x < a.world && a.seq > 1 && !peer_spin(&my_acks[threadIdx.x], a.seq - 1)) s_bad = 1;
-  __syncthreads();
-  if (!s_bad) {
-    // 2. push
-    for (uint32_t r = 0; r < a.world; ++r) {
-      uint32_t* dst = a.peer_buf[r] + (size_t)a.rank * a.words_per_rank;
-      for (uint32_t w = threadIdx.x; w < a.words_per_rank; w += blockDim.x) dst[w] = w < a.n_words ? a.local_bitmap[w] : 0u;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < a.world) {
-      volatile uint32_t* f = peer_flags(a.peer_buf[threadIdx.x], a.world, a.words_per_rank);
-      f[a.rank] = a.seq;
-    }
-    __threadfence_system();
-    // 3. everybody's slot has landed here
-    if (threadIdx.x < a.world && !peer_spin(&my_flags[threadIdx.x], a.seq)) s_bad = 1;
-    __syncthreads();
-    // 4. acknowledge
-    if (threadIdx.x < a.world) {
-      volatile uint32_t* ack = peer_flags(a.peer_buf[threadIdx.x], a.world, a.words_per_rank) + PEER_MAX_WORLD;
-      ack[a.rank] = a.seq;
-    }
+  if (threadIdx.x == 0) {
+    volatile uint32_t* f = peer_flags(a.peer_buf[r], a.world, a.words_per_rank, par);
+    f[a.rank] = a.seq;
     __threadfence_system();
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && s_bad) *a.err = 1;
 }
-
-inline size_t gang_fit_smem_bytes(int LW, int LN) {
-  size_t b = FIT_STAGES * fit_tile_bytes(LW, LN) + (size_t)PODS_PER_CTA * (8 * LW + 4 * LN);
-  b = (b + 7) & ~(size_t)7;
-  return b + 2 * FIT_STAGES * sizeof(uint64_t) + (size_t)PODS_PER_CTA * TILE_WORDS * sizeof(uint32_t);
+__global__ void __launch_bounds__(32) peer_wait_kernel(PeerArgs a) {
+  volatile uint32_t* f = peer_flags(a.peer_buf[a.rank], a.world, a.words_per_rank, a.seq & 1u);
+  bool ok = true;
+  if (threadIdx.x < a.world) {
+    const unsigned long long t0 = global_ns();
+    while (f[threadIdx.x] < a.seq) {
+      __nanosleep(64);
+      if (global_ns() - t0 > a.timeout_ns) { ok = false; break; }
+    }
+  }
+  __threadfence_system();
+  if (!ok) *a.err = 1;
 }
 
 }  // namespace bsk

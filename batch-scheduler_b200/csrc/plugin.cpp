@@ -126,6 +126,67 @@ bool IsScalarResourceName(const std::string& name) {
   return false;
 }
 
+namespace {
+// labels.Requirement.Matches / NodeSelectorRequirementsAsSelector (k8s v1.17.5 apimachinery labels/selector.go,
+// api/core/v1/helper, restated): valid = false when the requirement itself is malformed (the term then fails)
+bool requirement_matches(const NodeSelectorRequirement& r, const std::map<std::string, std::string>& labels, bool* valid) {
+  *valid = true;
+  auto it = labels.find(r.key);
+  const bool has = it != labels.end();
+  auto in_values = [&]() {
+    for (auto& v : r.values) if (v == it->second) return true;
+    return false;
+  };
+  if (r.op == "In") {
+    if (r.values.empty()) { *valid = false; return false; }
+    return has && in_values();
+  }
+  if (r.op == "NotIn") {
+    if (r.values.empty()) { *valid = false; return false; }
+    return !has || !in_values();
+  }
+  if (r.op == "Exists") { if (!r.values.empty()) { *valid = false; return false; } return has; }
+  if (r.op == "DoesNotExist") { if (!r.values.empty()) { *valid = false; return false; } return !has; }
+  if (r.op == "Gt" || r.op == "Lt") {
+    if (r.values.size() != 1) { *valid = false; return false; }
+    char* end = nullptr;
+    const long long rv = strtoll(r.values[0].c_str(), &end, 10);
+    if (r.values[0].empty() || *end) { *valid = false; return false; }
+    if (!has) return false;
+    const long long lv = strtoll(it->second.c_str(), &end, 10);
+    if (it->second.empty() || *end) return false;       // label value is not an integer: no match
+    return r.op == "Gt" ? lv > rv : lv < rv;
+  }
+  *valid = false;
+  return false;
+}
+// NodeSelectorRequirementsAsFieldSelector: only metadata.name with In / NotIn and exactly one value
+bool field_requirement_matches(const NodeSelectorRequirement& r, const std::string& node_name, bool* valid) {
+  *valid = r.key == "metadata.name" && r.values.size() == 1 && (r.op == "In" || r.op == "NotIn");
+  if (!*valid) return false;
+  return r.op == "In" ? node_name == r.values[0] : node_name != r.values[0];
+}
+}  // namespace
+
+bool MatchNodeSelectorTerms(const std::vector<NodeSelectorTerm>& terms, const std::map<std::string, std::string>& labels,
+                            const std::string& node_name) {
+  for (auto& t : terms) {
+    if (t.match_expressions.empty() && t.match_fields.empty()) continue;   // matches no objects
+    bool ok = true, valid = true;
+    for (auto& r : t.match_expressions) {
+      ok = requirement_matches(r, labels, &valid) && valid;
+      if (!ok) break;
+    }
+    if (!ok) continue;
+    for (auto& r : t.match_fields) {
+      ok = field_requirement_matches(r, node_name, &valid) && valid;
+      if (!ok) break;
+    }
+    if (ok) return true;
+  }
+  return false;
+}
+
 bs_node_table PackedSnapshot::node_table() const {
   bs_node_table t{};
   t.n_nodes = n_nodes; t.n_lanes = lanes;
@@ -140,6 +201,7 @@ bs_pod_table PackedSnapshot::pod_table() const {
   t.req = req.data(); t.req_present = pod_req_present.data(); t.gid = gid.data();
   t.sel_mask = sel_mask.data(); t.tol_mask = tol_mask.data(); t.priority = priority.data();
   t.ts_ns = ts_ns.data(); t.flags = pod_flags.data();
+  t.aff_class = aff_class.size() == n_pods && n_pods ? aff_class.data() : nullptr;
   return t;
 }
 bs_group_table PackedSnapshot::group_table() const {
@@ -149,6 +211,7 @@ bs_group_table PackedSnapshot::group_table() const {
   t.flags = group_flags.data(); t.min_res = min_res.data(); t.min_res_present = min_res_present.data();
   t.rep_sel = rep_sel.data(); t.rep_tol = rep_tol.data(); t.creation_ns = creation_ns.data();
   t.name_rank = name_rank.data();
+  t.rep_aff_class = rep_aff.size() == n_groups && n_groups ? rep_aff.data() : nullptr;
   return t;
 }
 
@@ -215,6 +278,39 @@ std::string joined_sorted(std::vector<std::string> v) {
   std::string s;
   for (size_t i = 0; i < v.size(); ++i) { if (i) s += ","; s += v[i]; }
   return s;
+}
+
+// canonical text of a pod's node predicate beyond the selector bits ("" = none)
+std::string aff_signature(const Pod& p, bool sel_in_table) {
+  const bool sel = sel_in_table && !p.node_selector.empty();
+  if (!p.has_required_affinity && !sel) return std::string();
+  std::string s;
+  if (sel)
+    for (auto& kv : p.node_selector) { s += 'S'; s += kv.first; s += '\x1f'; s += kv.second; s += '\x1e'; }
+  if (p.has_required_affinity) {
+    s += 'A';
+    for (auto& t : p.required_affinity) {
+      s += 'T';
+      auto put = [&](char tag, const std::vector<NodeSelectorRequirement>& rs) {
+        for (auto& r : rs) {
+          s += tag; s += r.key; s += '\x1f'; s += r.op; s += '\x1f';
+          for (auto& v : r.values) { s += v; s += '\x1d'; }
+          s += '\x1e';
+        }
+      };
+      put('E', t.match_expressions);
+      put('F', t.match_fields);
+    }
+  }
+  return s;
+}
+
+bool aff_class_matches(const PackedSnapshot::AffClassDef& c, const Node& nd) {
+  for (auto& kv : c.node_selector) {
+    auto it = nd.labels.find(kv.first);
+    if (it == nd.labels.end() || it->second != kv.second) return false;
+  }
+  return !c.has_required_affinity || MatchNodeSelectorTerms(c.terms, nd.labels, nd.name);
 }
 
 struct PackGroupIn {
@@ -295,8 +391,39 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   auto scan_sel = [&](const Pod* p) { for (auto& kv : p->node_selector) sel_bit.emplace(kv, 0); };
   for (auto* p : pending) scan_sel(p);
   for (auto& g : groups) if (g.rep_pod) scan_sel(g.rep_pod);
-  if (sel_bit.size() > 64) { bad.message = "more than 64 distinct nodeSelector pairs in one round"; return bad; }
+  // more than 64 distinct pairs: every nodeSelector moves into the affinity table (one class per distinct
+  // selector map), the 64-bit masks stay zero
+  ps.sel_in_table = sel_bit.size() > 64;
+  if (ps.sel_in_table) sel_bit.clear();
   { int b = 0; for (auto& kv : sel_bit) kv.second = b++; }
+  // ---- affinity classes: first-seen order over the pending pods, then the groups' representatives
+  {
+    std::unordered_map<std::string, uint32_t> cls;
+    auto class_of = [&](const Pod& p) -> uint32_t {
+      const std::string sig = aff_signature(p, ps.sel_in_table);
+      if (sig.empty()) return BS_AFF_NONE;
+      auto it = cls.find(sig);
+      if (it != cls.end()) return it->second;
+      const uint32_t id = (uint32_t)ps.aff_classes.size();
+      PackedSnapshot::AffClassDef d;
+      if (ps.sel_in_table) d.node_selector = p.node_selector;
+      d.has_required_affinity = p.has_required_affinity;
+      d.terms = p.required_affinity;
+      ps.aff_classes.push_back(std::move(d));
+      ps.aff_signatures.push_back(sig);
+      cls.emplace(sig, id);
+      return id;
+    };
+    ps.aff_class.assign(P, BS_AFF_NONE);
+    ps.rep_aff.assign(G, BS_AFF_NONE);
+    bool any = ps.sel_in_table;
+    for (uint32_t i = 0; i < P && !any; ++i) any = pending[i]->has_required_affinity;
+    for (uint32_t g = 0; g < G && !any; ++g) any = groups[g].rep_pod && groups[g].rep_pod->has_required_affinity;
+    if (any) {
+      for (uint32_t i = 0; i < P; ++i) ps.aff_class[i] = class_of(*pending[i]);
+      for (uint32_t g = 0; g < G; ++g) if (groups[g].rep_pod) ps.rep_aff[g] = class_of(*groups[g].rep_pod);
+    }
+  }
   std::vector<Taint> taints;
   auto taint_bit = [&](const Taint& t) -> int {
     for (size_t i = 0; i < taints.size(); ++i)
@@ -356,9 +483,26 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   }
   if (err) { bad.message = err == 1 ? "bad quantity in requested" : "bad quantity in allocatable"; return bad; }
   phase("nodes");
+  // ---- (affinity class, node) verdicts, evaluated on the host once per class and node
+  {
+    const uint32_t A = ps.n_aff(), W = (N + 31) / 32;
+    ps.aff_bits.assign((size_t)A * W, 0);
+#pragma omp parallel for num_threads(T) schedule(static) collapse(2)
+    for (uint32_t c = 0; c < A; ++c)
+      for (uint32_t w = 0; w < W; ++w) {
+        uint32_t word = 0;
+        for (uint32_t b = 0; b < 32 && w * 32 + b < N; ++b) {
+          const NodeInfo* ni = snapshot[w * 32 + b];
+          if (ni && ni->node && aff_class_matches(ps.aff_classes[c], *ni->node)) word |= 1u << b;
+        }
+        ps.aff_bits[(size_t)c * W + w] = word;
+      }
+  }
+  phase("affinity");
   auto pod_masks = [&](const Pod& p, uint64_t* sel, uint64_t* tol) {
     *sel = 0; *tol = 0;
-    for (auto& kv : p.node_selector) *sel |= 1ull << sel_bit.at(kv);
+    if (!ps.sel_in_table)
+      for (auto& kv : p.node_selector) *sel |= 1ull << sel_bit.at(kv);
     for (size_t b = 0; b < taints.size(); ++b)
       for (auto& t : p.tolerations)
         if (tolerates(t, taints[b])) { *tol |= 1ull << b; break; }
@@ -563,6 +707,7 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   bs_pod_table pt = packed_.pod_table();
   int rc;
   if ((rc = bs_upload_nodes(eng_, &nt))) return fail(rc);
+  if (packed_.n_aff() && (rc = bs_upload_affinity(eng_, packed_.n_aff(), packed_.aff_bits.data()))) return fail(rc);
   if ((rc = bs_upload_groups(eng_, &gt))) return fail(rc);
   if ((rc = bs_upload_pods(eng_, &pt))) return fail(rc);
   if ((rc = bs_set_wait_time(eng_, max_schedule_time_ns_, packed_.wait_ns.data(), packed_.n_groups))) return fail(rc);
@@ -608,6 +753,15 @@ Status BatchSchedulingPlugin::PackNodeRows(const PackedSnapshot& ctx, const std:
   const uint32_t n = (uint32_t)rows.size(), L = ctx.lanes;
   ps.lanes = L; ps.scalar_names = ctx.scalar_names; ps.sel_pairs = ctx.sel_pairs; ps.taint_list = ctx.taint_list;
   ps.n_nodes = n;
+  // affinity verdicts of the changed rows: aff_bits[c * n + k] = 0 / 1 (one word per (class, row); the
+  // caller patches the round's bit table with them)
+  ps.sel_in_table = ctx.sel_in_table;
+  ps.aff_classes = ctx.aff_classes;
+  ps.aff_signatures = ctx.aff_signatures;
+  ps.aff_bits.assign((size_t)ctx.n_aff() * n, 0);
+  for (uint32_t c = 0; c < ctx.n_aff(); ++c)
+    for (uint32_t k = 0; k < n; ++k)
+      if (rows[k] && rows[k]->node && aff_class_matches(ctx.aff_classes[c], *rows[k]->node)) ps.aff_bits[(size_t)c * n + k] = 1;
   LaneTable lt;   // the lanes of the full pack, nothing may be added
   for (auto& nm : ctx.scalar_names) lt.lane(nm, true);
   auto known = [&](const ResourceList& rl) {
@@ -675,8 +829,19 @@ Status BatchSchedulingPlugin::UpdateNodes(const std::vector<std::pair<uint32_t, 
   if (!st.ok()) return st;
   if (needs_full) return Status{BS_CODE_ERROR, "full repack needed"};
   bs_node_table t = delta.node_table();
-  const int rc = bs_update_nodes(eng_, idx.data(), &t);
+  int rc = bs_update_nodes(eng_, idx.data(), &t);
   if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
+  if (packed_.n_aff()) {   // the changed nodes' labels may have moved their affinity verdicts
+    const uint32_t W = (packed_.n_nodes + 31) / 32, nrow = delta.n_nodes;
+    for (uint32_t c = 0; c < packed_.n_aff(); ++c)
+      for (uint32_t k = 0; k < nrow; ++k) {
+        uint32_t& word = packed_.aff_bits[(size_t)c * W + (idx[k] >> 5)];
+        const uint32_t bit = 1u << (idx[k] & 31);
+        word = delta.aff_bits[(size_t)c * nrow + k] ? (word | bit) : (word & ~bit);
+      }
+    rc = bs_upload_affinity(eng_, packed_.n_aff(), packed_.aff_bits.data());
+    if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
+  }
   // keep the host copy of the round in step with the device table
   const uint32_t N = packed_.n_nodes, n = delta.n_nodes, L = packed_.lanes;
   for (uint32_t k = 0; k < n; ++k) {
@@ -714,6 +879,7 @@ Status BatchSchedulingPlugin::PackGroupRows(const PackedSnapshot& ctx, const std
   ps.min_member.assign(n, 0); ps.scheduled.assign(n, 0); ps.matched.assign(n, 0); ps.group_flags.assign(n, 0);
   ps.min_res.assign((size_t)L * n, 0); ps.min_res_present.assign(n, 0); ps.rep_sel.assign(n, 0);
   ps.rep_tol.assign(n, 0); ps.creation_ns.assign(n, 0); ps.name_rank.assign(n, 0); ps.wait_ns.assign(n, 0);
+  ps.rep_aff.assign(n, BS_AFF_NONE);
   for (uint32_t k = 0; k < n; ++k) {
     const GroupDelta& gd = rows[k];
     if (!gd.pg || gd.index >= ctx.n_groups) return Status{BS_CODE_ERROR, "PackGroupRows: bad row"};
@@ -740,7 +906,16 @@ Status BatchSchedulingPlugin::PackGroupRows(const PackedSnapshot& ctx, const std
     }
     if (gd.rep_pod) {
       ps.group_flags[k] |= BS_GROUP_HAS_POD;
+      const std::string sig = aff_signature(*gd.rep_pod, ctx.sel_in_table);
+      if (!sig.empty()) {
+        uint32_t cid = BS_AFF_NONE;
+        for (uint32_t c = 0; c < ctx.n_aff(); ++c)
+          if (ctx.aff_signatures[c] == sig) { cid = c; break; }
+        if (cid == BS_AFF_NONE) { *needs_full = true; return Status{}; }   // a predicate the round's table has no row for
+        ps.rep_aff[k] = cid;
+      }
       for (auto& kv : gd.rep_pod->node_selector) {
+        if (ctx.sel_in_table) break;
         bool found = false;
         for (size_t b = 0; b < ctx.sel_pairs.size() && !found; ++b)
           if (ctx.sel_pairs[b] == std::pair<std::string, std::string>(kv.first, kv.second)) {
@@ -796,6 +971,7 @@ Status BatchSchedulingPlugin::UpdateGroups(const std::vector<std::string>& ns_na
     for (uint32_t d = 0; d < L; ++d) packed_.min_res[(size_t)d * G + g] = delta.min_res[(size_t)d * n + k];
     packed_.min_res_present[g] = delta.min_res_present[k]; packed_.rep_sel[g] = delta.rep_sel[k];
     packed_.rep_tol[g] = delta.rep_tol[k]; packed_.creation_ns[g] = delta.creation_ns[k];
+    if (packed_.rep_aff.size() == G) packed_.rep_aff[g] = delta.rep_aff[k];
     packed_.wait_ns[g] = delta.wait_ns[k];
   }
   if ((rc = bs_set_wait_time(eng_, max_schedule_time_ns_, packed_.wait_ns.data(), G)))

@@ -40,10 +40,23 @@ struct Toleration {
 struct Taint {
   std::string key, value, effect;  // effect: NoSchedule | PreferNoSchedule | NoExecute
 };
+// v1.NodeSelectorRequirement / v1.NodeSelectorTerm: the REQUIRED node affinity of a pod
+// (Spec.Affinity.NodeAffinity.RequiredDuringSchedulingIgnoredDuringExecution.NodeSelectorTerms), which
+// predicates.PodMatchNodeSelector evaluates next to Spec.NodeSelector (checkFit, core.go:741-746).
+struct NodeSelectorRequirement {
+  std::string key, op /* In | NotIn | Exists | DoesNotExist | Gt | Lt */;
+  std::vector<std::string> values;
+};
+struct NodeSelectorTerm {
+  std::vector<NodeSelectorRequirement> match_expressions;  // against node labels
+  std::vector<NodeSelectorRequirement> match_fields;       // against node fields (metadata.name)
+};
 struct Pod {
   std::string ns, name, uid;
   std::map<std::string, std::string> labels;
   std::map<std::string, std::string> node_selector;
+  bool has_required_affinity = false;                 // the required node-affinity field is non-nil
+  std::vector<NodeSelectorTerm> required_affinity;    // its terms, ORed; an empty term matches nothing
   std::vector<Toleration> tolerations;
   std::vector<Container> containers;
   std::vector<std::string> owner_uids;  // OwnerReferences[].UID (core.go:483-485)
@@ -86,6 +99,10 @@ bool ParseQuantityMilli(const std::string& s, __int128* milli);
 bool QuantityValue(const std::string& s, int64_t* out);       // Quantity.Value()
 bool QuantityMilliValue(const std::string& s, int64_t* out);  // Quantity.MilliValue()
 bool IsScalarResourceName(const std::string& name);           // v1helper.IsScalarResourceName
+// v1helper.MatchNodeSelectorTerms (k8s v1.17.5, restated): terms are ORed, the requirements of a term ANDed;
+// a term without requirements matches nothing; an invalid requirement fails its term.
+bool MatchNodeSelectorTerms(const std::vector<NodeSelectorTerm>& terms, const std::map<std::string, std::string>& labels,
+                            const std::string& node_name);
 
 // The packed tables of one round (owning storage + the C-ABI views over it).
 struct PackedSnapshot {
@@ -114,6 +131,21 @@ struct PackedSnapshot {
   // masks (needed to pack changed rows later with the same encoding, PackNodeRows)
   std::vector<std::pair<std::string, std::string>> sel_pairs;
   std::vector<Taint> taint_list;
+  // affinity classes (bs_upload_affinity): pods whose node predicate does not fit the 64 selector bits —
+  // required nodeAffinity terms, or every nodeSelector when the round holds more than 64 distinct pairs
+  // (sel_in_table: the masks stay zero then) — share one class per distinct predicate; aff_bits holds the
+  // host-evaluated verdict of every class on every node
+  struct AffClassDef {
+    std::map<std::string, std::string> node_selector;   // only when sel_in_table
+    bool has_required_affinity = false;
+    std::vector<NodeSelectorTerm> terms;
+  };
+  bool sel_in_table = false;
+  std::vector<AffClassDef> aff_classes;
+  std::vector<std::string> aff_signatures;              // canonical text of each class (lookup key)
+  std::vector<uint32_t> aff_class, rep_aff;             // per pod / per group, BS_AFF_NONE = none
+  std::vector<uint32_t> aff_bits;                       // [n_aff][ceil(n_nodes / 32)]
+  uint32_t n_aff() const { return (uint32_t)aff_classes.size(); }
 
   bs_node_table node_table() const;
   bs_pod_table pod_table() const;

@@ -66,6 +66,7 @@ struct ReplayArgs {
   PodTab pt;
   const uint64_t* rsel;       // representative-class tables (every pod's (sel, tol) is one of them)
   const uint64_t* rtol;
+  const uint32_t* raff;       // affinity class of each representative class (BS_AFF_NONE: none)
   uint32_t n_rep;
   uint32_t cache_ok;          // block summaries usable: sums stay below 2^62 and the scratch exists (host)
   int64_t* blk_sum;           // [2*n_rep][n_blocks][MAXL] block totals
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
       if (use_mask) {
         const uint64_t lb = a.nt.label[i], tn = a.nt.taint[i];
         for (uint32_t c = 0; c < C; ++c)
-          if (check_fit(lb, tn, a.rsel[c], a.rtol[c])) fm |= 1u << c;
+          if (check_fit(lb, tn, a.rsel[c], a.rtol[c]) && aff_ok(a.nt, a.raff[c], i)) fm |= 1u << c;
       }
     } else {
       for (uint32_t d = 0; d < L; ++d) { a.left[0][(size_t)d * Npad + i] = 0; a.left[1][(size_t)d * Npad + i] = 0; }
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 1) replay_kernel(ReplayArgs a)
       } else {
 #pragma unroll
         for (int k = 0; k < REPLAY_NPT; ++k)
-          if (i0 + k < N && check_fit(a.nt.label[i0 + k], a.nt.taint[i0 + k], sel, tol)) fit |= 1u << k;
+          if (i0 + k < N && check_fit(a.nt.label[i0 + k], a.nt.taint[i0 + k], sel, tol) && aff_ok(a.nt, a.raff[rc], i0 + k))
+            fit |= 1u << k;
       }
 #pragma unroll
       for (int k = 0; k < REPLAY_NPT; ++k) {

@@ -80,7 +80,7 @@ class Engine:
         t = capi.GroupTableC(gt.n, gt.lanes, capi.ptr(gt.min_member), capi.ptr(gt.scheduled), capi.ptr(gt.matched),
                              capi.ptr(gt.flags), capi.ptr(gt.min_res), capi.ptr(gt.min_res_present),
                              capi.ptr(gt.rep_sel), capi.ptr(gt.rep_tol), capi.ptr(gt.creation_ns),
-                             capi.ptr(gt.name_rank))
+                             capi.ptr(gt.name_rank), capi.ptr(gt.rep_aff))
         self._check(self.lib.bs_upload_groups(self.h, C.byref(t)))
         self.G = gt.n
 
@@ -97,12 +97,23 @@ class Engine:
     def upload_pods(self, pt: PodTable):
         t = capi.PodTableC(pt.n, pt.lanes, capi.ptr(pt.req), capi.ptr(pt.req_present), capi.ptr(pt.gid),
                            capi.ptr(pt.sel_mask), capi.ptr(pt.tol_mask), capi.ptr(pt.priority),
-                           capi.ptr(pt.ts_ns), capi.ptr(pt.flags))
+                           capi.ptr(pt.ts_ns), capi.ptr(pt.flags), capi.ptr(pt.aff_class))
         self._check(self.lib.bs_upload_pods(self.h, C.byref(t)))
         self.P = pt.n
 
+    def upload_affinity(self, bits):
+        """[n_classes, ceil(N/32)] uint32 host-evaluated (affinity class, node) predicate bits, or None to clear."""
+        if bits is None:
+            self._check(self.lib.bs_upload_affinity(self.h, 0, None))
+            return
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        assert bits.ndim == 2 and bits.shape[1] == (self.N + 31) // 32
+        self._check(self.lib.bs_upload_affinity(self.h, bits.shape[0], capi.ptr(bits)))
+
     def upload(self, snap: Snapshot):
         self.upload_nodes(snap.nodes)
+        if getattr(snap, "aff_bits", None) is not None:
+            self.upload_affinity(snap.aff_bits)
         self.upload_groups(snap.groups)
         self.upload_pods(snap.pods)
 
@@ -257,19 +268,15 @@ class Engine:
     def peer_detach(self):
         self._check(self.lib.bs_peer_detach(self.h))
 
+    def peer_join(self):
+        """Orders work enqueued on the engine stream after this call behind the last round's gathered words."""
+        self._check(self.lib.bs_peer_join(self.h))
+
     def gathered_admit(self) -> np.ndarray:
         """[world, words_per_rank] uint32: every rank's admit bitmap after the last evaluation."""
-        ptr, nbytes = self.device_buffer(capi.BUF_GATHERED_ADMIT)
-        out = np.zeros(nbytes // 4, np.uint32)
-        import torch
-
-        class _H:
-            pass
-        h = _H()
-        h.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-        t = torch.as_tensor(h, device=torch.device("cuda", torch.cuda.current_device()))
-        out[:] = t.cpu().numpy().view(np.uint32)
-        return out.reshape(self.peer_world, self.peer_wpr)
+        out = np.zeros((self.peer_world, self.peer_wpr), np.uint32)
+        self._check(self.lib.bs_fetch_gathered_admit(self.h, capi.ptr(out)))
+        return out
 
     # -- device access / measurement ---------------------------------------------------------
     def device_buffer(self, which: int):
@@ -290,6 +297,15 @@ class Engine:
             self._check(self.lib.bs_kernel_ms(self.h, k, C.byref(ms), C.byref(n)))
             out[name] = (float(ms.value), int(n.value))
         return out
+
+    def fit_shape(self) -> dict:
+        """Lane classes of the last evaluation's fit kernel: LW int64, LN int32, LS int32 in 2^k units."""
+        w, n, sc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self.lib.bs_fit_shape(self.h, C.byref(w), C.byref(n), C.byref(sc)))
+        return {"LW": int(w.value), "LN": int(n.value), "LS": int(sc.value)}
+
+    def score_pitch(self) -> int:
+        return int(self.lib.bs_score_pitch(self.h))
 
     def launch_count(self) -> int:
         return int(self.lib.bs_launch_count(self.h))

@@ -22,6 +22,7 @@ NODE_NIL, NODE_NO_NODE, NODE_UNSCHEDULABLE, NODE_TAINTS_ERR = 0x01, 0x02, 0x04, 
 POD_PERMITTED_RECENTLY, POD_OCC_NOREFS, POD_OCC_MISMATCH, POD_LISTER_MISS = 0x01, 0x02, 0x04, 0x08
 GROUP_SCHEDULED, GROUP_HAS_POD, GROUP_HAS_MINRES, GROUP_DENIED = 0x01, 0x02, 0x04, 0x08
 GID_NONE, GID_MISSING = -1, -2
+AFF_NONE = 0xFFFFFFFF
 
 PF_PASS, PF_NOT_FOUND, PF_DENIED, PF_OCC_NOREFS, PF_OCCUPIED, PF_NOT_ENOUGH = range(6)
 ADMIT, WAIT, UNSCHEDULABLE = 0, 1, 2
@@ -84,8 +85,11 @@ class PodTable:
     priority: np.ndarray     # int32 [P]
     ts_ns: np.ndarray        # int64 [P]
     flags: np.ndarray        # uint8 [P]
+    aff_class: np.ndarray = None   # uint32 [P] row of Snapshot.aff_bits, AFF_NONE = no affinity constraint; None = all NONE
 
     def __post_init__(self):
+        if self.aff_class is not None:
+            self.aff_class = _c(self.aff_class, np.uint32)
         self.req = _c(self.req, np.int64)
         self.req_present = _c(self.req_present, np.uint32)
         self.gid = _c(self.gid, np.int32)
@@ -111,12 +115,13 @@ class PodTable:
                         z(np.uint64), z(np.uint64), z(np.int32), z(np.int64), z(np.uint8))
 
     def copy(self):
-        return PodTable(*(getattr(self, f).copy() for f in self.__dataclass_fields__))
+        return PodTable(*(None if getattr(self, f) is None else getattr(self, f).copy() for f in self.__dataclass_fields__))
 
     def take(self, idx):
         idx = np.asarray(idx)
         return PodTable(self.req[:, idx], self.req_present[idx], self.gid[idx], self.sel_mask[idx],
-                        self.tol_mask[idx], self.priority[idx], self.ts_ns[idx], self.flags[idx])
+                        self.tol_mask[idx], self.priority[idx], self.ts_ns[idx], self.flags[idx],
+                        None if self.aff_class is None else self.aff_class[idx])
 
 
 @dataclass
@@ -131,8 +136,11 @@ class GroupTable:
     rep_tol: np.ndarray          # uint64 [G]
     creation_ns: np.ndarray      # int64 [G]
     name_rank: np.ndarray        # uint32 [G]
+    rep_aff: np.ndarray = None   # uint32 [G] affinity class of pgs.Pod (AFF_NONE = none); None = all NONE
 
     def __post_init__(self):
+        if self.rep_aff is not None:
+            self.rep_aff = _c(self.rep_aff, np.uint32)
         self.min_member = _c(self.min_member, np.uint32)
         self.scheduled = _c(self.scheduled, np.uint32)
         self.matched = _c(self.matched, np.uint32)
@@ -161,7 +169,7 @@ class GroupTable:
                           z(np.int64), z(np.uint32))
 
     def copy(self):
-        return GroupTable(*(getattr(self, f).copy() for f in self.__dataclass_fields__))
+        return GroupTable(*(None if getattr(self, f) is None else getattr(self, f).copy() for f in self.__dataclass_fields__))
 
 
 @dataclass
@@ -171,6 +179,7 @@ class Snapshot:
     groups: GroupTable
     name: str = ""
     meta: dict = field(default_factory=dict)
+    aff_bits: np.ndarray = None   # uint32 [n_aff, ceil(N/32)]: (affinity class, node) predicate bits, or None
 
     @property
     def lanes(self):
@@ -182,7 +191,7 @@ class Snapshot:
 
     def copy(self):
         return Snapshot(self.nodes.copy(), self.pods.copy(), self.groups.copy(), self.name,
-                        dict(self.meta))
+                        dict(self.meta), None if self.aff_bits is None else self.aff_bits.copy())
 
     def resolve_groups(self) -> "Snapshot":
         """Applies fillOccupiedObj's first-pod capture (core.go:486-493) on the host, over the WHOLE
@@ -207,6 +216,9 @@ class Snapshot:
         take_res = has & ((gt.flags & GROUP_HAS_MINRES) == 0)
         gt.rep_sel = np.where(take_pod, pt.sel_mask[fp], gt.rep_sel)
         gt.rep_tol = np.where(take_pod, pt.tol_mask[fp], gt.rep_tol)
+        if pt.aff_class is not None:
+            base = gt.rep_aff if gt.rep_aff is not None else np.full(G, AFF_NONE, np.uint32)
+            gt.rep_aff = np.where(take_pod, pt.aff_class[fp], base).astype(np.uint32)
         pres = pt.req_present[fp] & ~np.uint32(0xF)
         for d in range(gt.lanes):
             lane_present = np.ones(G, bool) if d < 4 else ((pres >> np.uint32(d)) & 1).astype(bool)
@@ -233,7 +245,7 @@ class Snapshot:
         keep = ((gid >= g0) & (gid < g1)) | ((gid < 0) & (np.arange(P) % world == rank))
         idx = np.nonzero(keep)[0]
         s = Snapshot(self.nodes, self.pods.take(idx), self.groups, f"{self.name}[{rank}/{world}]",
-                     dict(self.meta))
+                     dict(self.meta), self.aff_bits)
         s.meta.update(group_range=(g0, g1), pod_index=idx)
         return s
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 4
+#define BS_ABI_VERSION 5
 #define BS_FIXED_LANES 4
 #define BS_MAX_LANES 16
 /* |value| bound accepted for every int64 table entry (validated at upload):
@@ -114,6 +114,9 @@ typedef enum {
 #define BS_GROUP_HAS_MINRES 0x04u  /* Spec.MinResources != nil     types.go:97 */
 #define BS_GROUP_DENIED 0x08u      /* ns/name in lastDeniedPG      core.go:105 */
 
+/* affinity class of a pod / a group's representative pod: BS_AFF_NONE = no constraint beyond the masks */
+#define BS_AFF_NONE 0xffffffffu
+
 /* gid values for pods that carry no usable group */
 #define BS_GID_NONE (-1)    /* no group label: VerifyPodLabelSatisfied false (k8s.go:62) */
 #define BS_GID_MISSING (-2) /* labelled, but podGroupStatusCache.Get == nil (core.go:100) */
@@ -144,6 +147,8 @@ typedef struct {
   const int32_t* priority;     /* [n_pods] podutil.GetPodPriority         core.go:372    */
   const int64_t* ts_ns;        /* [n_pods] PodInfo.Timestamp              core.go:385    */
   const uint8_t* flags;        /* [n_pods] BS_POD_*                                      */
+  const uint32_t* aff_class;   /* [n_pods] row of the affinity bit table (bs_upload_affinity) the pod must
+                                  match besides sel_mask, or BS_AFF_NONE; the column may be NULL (all NONE)  */
 } bs_pod_table;
 
 /* Group table: PGStatusCache.PGStatusMap flattened (cache.go:45-67); canonical
@@ -161,6 +166,7 @@ typedef struct {
   const uint64_t* rep_tol;         /* toleration mask of pgs.Pod                   */
   const int64_t* creation_ns;      /* PodGroup CreationTimestamp      core.go:400  */
   const uint32_t* name_rank;       /* rank of the bare pgName, byte-wise ascending; equal names share a rank (core.go:404) */
+  const uint32_t* rep_aff_class;   /* affinity class of pgs.Pod, or BS_AFF_NONE; the column may be NULL     */
 } bs_group_table;
 
 /* What one evaluation materialises in HBM besides the decision vectors. */
@@ -233,6 +239,17 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t);
  * size and order stay. */
 int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t);
 int bs_upload_pods(bs_engine* e, const bs_pod_table* t);
+/* checkFit beyond bit masks (core.go:741-759 -> predicates.PodMatchNodeSelector).  sel_mask / label_mask
+ * carry nodeSelector pairs exactly (<= 64 distinct pairs per round); REQUIRED node-affinity terms
+ * (matchExpressions with In / NotIn / Exists / DoesNotExist / Gt / Lt, matchFields, ORed terms) and any
+ * overflow of the 64 pairs travel as an explicit table: the caller groups pods into affinity classes,
+ * evaluates each class against every node of the uploaded snapshot and uploads
+ *     bits[n_classes][ceil(n_nodes / 32)]   bit n%32 of word n/32 of row c = class c matches node n.
+ * A pod fits a node iff the mask test AND its class's bit hold (bs_pod_table.aff_class, BS_AFF_NONE =
+ * mask test only); the group's representative pod likewise (bs_group_table.rep_aff_class).  The table
+ * belongs to the node snapshot: bs_upload_nodes drops it (upload nodes, then the table), n_classes = 0
+ * clears it.  A class id >= n_classes at evaluation time is BS_E_INDEX. */
+int bs_upload_affinity(bs_engine* e, uint32_t n_classes, const uint32_t* bits);
 /* max_schedule_time: plugin arg (batchscheduler.go:71-75, util.GetWaitTimeDuration
  * k8s.go:82-91).  per_group_ns may be NULL; entries < 0 mean "unset". */
 int bs_set_wait_time(bs_engine* e, int64_t default_ns, const int64_t* per_group_ns,
@@ -318,6 +335,14 @@ void* bs_stream(bs_engine* e); /* the cudaStream_t a round is ordered on: upload
                                   verdicts run on it, and the two side streams of a round (PreFilter chain,
                                   queue sort) join it before the round ends, so work enqueued on it after
                                   bs_evaluate_async sees every result */
+/* elements per row of the score matrix in HBM (BS_BUF_SCORE): n_nodes rounded up to even, so that every
+ * row starts on a 16-byte boundary (the kernel writes row segments with TMA bulk stores); the pad
+ * element of an odd-sized table holds no score.  bs_fetch_score_rows returns dense [n][n_nodes] rows. */
+uint32_t bs_score_pitch(const bs_engine* e);
+/* words per row of the fit bitmap in HBM (BS_BUF_FIT_BITMAP): ceil(n_nodes / 32) rounded up to 32, so that every
+ * row is a whole number of 128-byte lines (the kernel writes one aligned line per pod and 1024 nodes);
+ * bs_fetch_fit_rows returns dense [n][ceil(n_nodes / 32)] rows. */
+uint32_t bs_bitmap_pitch(const bs_engine* e);
 /* copy rows [pod0, pod0+n) of the fit bitmap / score matrix to the host */
 int bs_fetch_fit_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* words);
 int bs_fetch_score_rows(bs_engine* e, uint32_t pod0, uint32_t n, int64_t* scores);
@@ -325,17 +350,30 @@ int bs_fetch_filter_rows(bs_engine* e, uint32_t pod0, uint32_t n, uint32_t* word
 
 /* ---- multi-GPU exchange of the admit bitmap over peer memory (NVLink / NVSwitch) ----
  * The path shards over groups (one process per GPU); the only exchange is the all-gather of the
- * per-rank admit bitmaps.  Instead of a separate NCCL launch, bs_evaluate_async ends with ONE small
+ * per-rank admit bitmaps.  Instead of a separate NCCL launch, bs_evaluate_async ends with a push
  * kernel that writes this rank's bitmap words straight into every peer's gather buffer (CUDA IPC
- * mapped peer memory), publishes a sequence number, and waits (bounded spins) for the peers'.
- *   bs_peer_init    allocate the gather buffer [world][words_per_rank] (+ flags) on this GPU
+ * mapped peer memory) and publishes the round number there; a one-warp wait kernel on a side stream
+ * waits (bounded) for the peers' words of the same round.  The buffer holds two slot sets (round
+ * parity), so the NEXT round's kernels run while the wait is still pending: a late rank stalls its
+ * peers only once it is more than one round behind.  No rank ever spins on its main stream.
+ *   bs_peer_init    allocate the gather buffer [2][world][words_per_rank] (+ flags) on this GPU
  *   bs_peer_handle  64-byte cudaIpcMemHandle of it, to be exchanged out of band (e.g. torch.distributed)
  *   bs_peer_attach  map every peer's buffer (handles[world][64], own slot ignored)
- * BS_BUF_GATHERED_ADMIT then holds, after each evaluation, rank r's bitmap at word r*words_per_rank. */
+ *   bs_peer_join    make the engine stream wait for the last round's gathered words (for work the
+ *                   caller enqueues on bs_stream; bs_sync and bs_fetch_gathered_admit wait themselves)
+ *   bs_fetch_gathered_admit  copy [world][words_per_rank] words of the last round to the host
+ * BS_BUF_GATHERED_ADMIT is the device address of the last round's slot set (rank r at word
+ * r*words_per_rank); it alternates between two addresses from round to round.
+ * Failure: a rank that does not arrive within BS_PEER_TIMEOUT_MS (env, default 2000) makes bs_sync /
+ * bs_fetch_gathered_admit return BS_E_PEER; from then on bs_evaluate* fails fast with BS_E_PEER (no
+ * further spinning) until every rank has called bs_peer_detach and attached again (a new epoch:
+ * buffers zeroed, round numbers restart at 1). */
 int bs_peer_init(bs_engine* e, uint32_t rank, uint32_t world, uint32_t words_per_rank);
 int bs_peer_handle(bs_engine* e, unsigned char handle[64]);
 int bs_peer_attach(bs_engine* e, const unsigned char* handles /* [world][64] */);
 int bs_peer_detach(bs_engine* e);
+int bs_peer_join(bs_engine* e);
+int bs_fetch_gathered_admit(bs_engine* e, uint32_t* words /* [world][words_per_rank] */);
 
 /* ---- measurement hooks ---- */
 typedef enum {
@@ -354,6 +392,10 @@ int bs_set_profiling(bs_engine* e, int on); /* record CUDA events around each st
 /* milliseconds of stage k in the last evaluation, and launches it took */
 int bs_kernel_ms(bs_engine* e, int k, float* ms, uint32_t* launches);
 uint64_t bs_launch_count(const bs_engine* e); /* kernels launched since bs_create */
+/* how the last evaluation's fit kernel carried the resource lanes: int64 (wide), int32 (narrow: every
+ * |value| <= 2^27) and int32 in exact power-of-two units (scaled: every value of the lane a multiple of
+ * 2^k, |value| >> k <= 2^29); wide + narrow + scaled == n_lanes */
+int bs_fit_shape(bs_engine* e, uint32_t* wide, uint32_t* narrow, uint32_t* scaled);
 
 #ifdef __cplusplus
 }

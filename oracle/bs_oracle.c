@@ -22,6 +22,9 @@
 #define LANE_EPH 2
 #define LANE_PODS 3
 
+#define POD_AFF(pd, p) ((pd)->aff_class ? (pd)->aff_class[p] : BSO_AFF_NONE)
+#define GROUP_AFF(gr, g) ((gr)->rep_aff ? (gr)->rep_aff[g] : BSO_AFF_NONE)
+
 static inline int64_t wrap_add(int64_t a, int64_t b) { return (int64_t)((uint64_t)a + (uint64_t)b); }
 static inline int64_t wrap_sub(int64_t a, int64_t b) { return (int64_t)((uint64_t)a - (uint64_t)b); }
 static inline int64_t wrap_mul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
@@ -45,19 +48,26 @@ int64_t bso_scale(int64_t alloc, float percent) {
 /* core.go:741-759 checkFit: PodMatchNodeSelector && PodToleratesNodeTaints, with
  * both predicates pre-encoded by the packer: every required label bit is on the
  * node, and every NoSchedule/NoExecute taint bit of the node is tolerated. */
-int bso_check_fit(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol) {
+int bso_check_fit(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol, uint32_t aff) {
   if ((nd->label_mask[i] & sel) != sel) return 0;
   if ((nd->taint_mask[i] & ~tol) != 0) return 0;
+  /* the part of PodMatchNodeSelector bit masks cannot carry (required nodeAffinity terms): one
+   * host-evaluated bit per (affinity class, node), see include/bsched.h bs_upload_affinity */
+  if (aff != BSO_AFF_NONE) {
+    if (!nd->aff_bits || aff >= nd->n_aff) return 0;
+    const uint32_t W = (nd->n + 31) / 32;
+    if (!((nd->aff_bits[(size_t)aff * W + (i >> 5)] >> (i & 31)) & 1u)) return 0;
+  }
   return 1;
 }
 
 /* core.go:634-670 singleNodeResource */
-void bso_single_node_resource(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol,
+void bso_single_node_resource(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol, uint32_t aff,
                               float percent, bso_resource* out) {
   const uint32_t n = nd->n, L = nd->lanes;
   memset(out, 0, sizeof(*out)); /* :635-637 empty resource, empty scalar map */
   if (nd->flags[i] & BSO_NODE_TAINTS_ERR) return; /* :639-641 */
-  if (!bso_check_fit(nd, i, sel, tol)) return;    /* :642-645 */
+  if (!bso_check_fit(nd, i, sel, tol, aff)) return; /* :642-645 */
   /* :650-653 podCount = requested.AllowedPodNumber, or len(info.Pods()) when 0 */
   int64_t pod_count = nd->requested[(size_t)LANE_PODS * n + i];
   if (pod_count == 0) pod_count = nd->pod_count[i];
@@ -118,13 +128,13 @@ static inline int node_skipped(const bso_nodes* nd, uint32_t i) {
 }
 
 /* core.go:595-632 compareClusterResourceAndRequire */
-int bso_compare_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, const bso_resource* need,
+int bso_compare_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, uint32_t aff, const bso_resource* need,
                         float percent) {
   bso_resource running, left;
   memset(&running, 0, sizeof(running)); /* :602 */
   for (uint32_t i = 0; i < nd->n; ++i) { /* :604 snapshot list order */
     if (node_skipped(nd, i)) continue;   /* :606-617 */
-    bso_single_node_resource(nd, i, sel, tol, percent, &left); /* :619 */
+    bso_single_node_resource(nd, i, sel, tol, aff, percent, &left); /* :619 */
     bso_resource_add(&running, &left, nd->lanes);              /* :621 */
     if (bso_compare_resource_and_require(&running, need, nd->lanes)) return 1; /* :623-627 */
   }
@@ -132,12 +142,12 @@ int bso_compare_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, const b
 }
 
 /* core.go:566-593 computeClusterResource (no early exit; log argument only) */
-void bso_compute_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, bso_resource* out) {
+void bso_compute_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, uint32_t aff, bso_resource* out) {
   bso_resource left;
   memset(out, 0, sizeof(*out));
   for (uint32_t i = 0; i < nd->n; ++i) {
     if (node_skipped(nd, i)) continue;
-    bso_single_node_resource(nd, i, sel, tol, 1.0f, &left);
+    bso_single_node_resource(nd, i, sel, tol, aff, 1.0f, &left);
     bso_resource_add(out, &left, nd->lanes);
   }
 }
@@ -294,9 +304,9 @@ int bso_fit_eval(const bso_nodes* nd, const bso_pods* pd, uint32_t p, uint32_t n
   if (score) *score = INT64_MIN;
   if (node_skipped(nd, n)) return 0;
   if (nd->flags[n] & BSO_NODE_TAINTS_ERR) return 0;
-  if (!bso_check_fit(nd, n, pd->sel_mask[p], pd->tol_mask[p])) return 0;
+  if (!bso_check_fit(nd, n, pd->sel_mask[p], pd->tol_mask[p], POD_AFF(pd, p))) return 0;
   bso_resource left, req;
-  bso_single_node_resource(nd, n, pd->sel_mask[p], pd->tol_mask[p], 1.0f, &left);
+  bso_single_node_resource(nd, n, pd->sel_mask[p], pd->tol_mask[p], POD_AFF(pd, p), 1.0f, &left);
   bso_pod_require(pd, p, &req);
   if (!bso_compare_resource_and_require(&left, &req, nd->lanes)) return 0;
   if (score) {
@@ -354,6 +364,7 @@ typedef struct {
   uint8_t* flags;
   uint64_t* rep_sel;
   uint64_t* rep_tol;
+  uint32_t* rep_aff;
   int64_t* min_res; /* [lanes][G] */
   uint32_t* min_res_present;
 } eff_groups;
@@ -372,6 +383,7 @@ static void fill_from_pod(const bso_pods* pd, const bso_groups* gr, eff_groups* 
     eg->flags[g] |= BSO_GROUP_HAS_POD;
     eg->rep_sel[g] = pd->sel_mask[p];
     eg->rep_tol[g] = pd->tol_mask[p];
+    eg->rep_aff[g] = POD_AFF(pd, p);
   }
   if (!(eg->flags[g] & BSO_GROUP_HAS_MINRES)) { /* :489-493 */
     eg->flags[g] |= BSO_GROUP_HAS_MINRES;
@@ -388,19 +400,21 @@ static int eff_alloc(const bso_groups* gr, eff_groups* eg) {
   eg->flags = (uint8_t*)malloc(G);
   eg->rep_sel = (uint64_t*)malloc(G * 8);
   eg->rep_tol = (uint64_t*)malloc(G * 8);
+  eg->rep_aff = (uint32_t*)malloc(G * 4);
   eg->min_res = (int64_t*)malloc(G * 8 * gr->lanes);
   eg->min_res_present = (uint32_t*)malloc(G * 4);
-  if (!eg->flags || !eg->rep_sel || !eg->rep_tol || !eg->min_res || !eg->min_res_present) return -1;
+  if (!eg->flags || !eg->rep_sel || !eg->rep_tol || !eg->rep_aff || !eg->min_res || !eg->min_res_present) return -1;
   memcpy(eg->flags, gr->flags, gr->n);
   memcpy(eg->rep_sel, gr->rep_sel, (size_t)gr->n * 8);
   memcpy(eg->rep_tol, gr->rep_tol, (size_t)gr->n * 8);
+  for (uint32_t g = 0; g < gr->n; ++g) eg->rep_aff[g] = gr->rep_aff ? gr->rep_aff[g] : BSO_AFF_NONE;
   memcpy(eg->min_res, gr->min_res, (size_t)gr->n * 8 * gr->lanes);
   memcpy(eg->min_res_present, gr->min_res_present, (size_t)gr->n * 4);
   return 0;
 }
 
 static void eff_free(eff_groups* eg) {
-  free(eg->flags); free(eg->rep_sel); free(eg->rep_tol); free(eg->min_res);
+  free(eg->flags); free(eg->rep_sel); free(eg->rep_tol); free(eg->rep_aff); free(eg->min_res);
   free(eg->min_res_present);
 }
 
@@ -430,7 +444,7 @@ static uint8_t prefilter_one(const bso_nodes* nd, const bso_pods* pd, const bso_
   bso_resource need, req;
   if (matched == 0) {                                                 /* :136 */
     eff_pre_allocated(gr, eg, (uint32_t)g, 0, &need);                 /* :137-139 own group */
-    if (!bso_compare_cluster(nd, eg->rep_sel[g], eg->rep_tol[g], &need, 1.0f)) { /* :140 */
+    if (!bso_compare_cluster(nd, eg->rep_sel[g], eg->rep_tol[g], eg->rep_aff[g], &need, 1.0f)) { /* :140 */
       *deny = 1;                                                      /* :142 */
       return BSO_PF_NOT_ENOUGH;                                       /* :143 */
     }
@@ -440,7 +454,7 @@ static uint8_t prefilter_one(const bso_nodes* nd, const bso_pods* pd, const bso_
   eff_pre_allocated(gr, eg, (uint32_t)m, (int64_t)matched, &need);    /* :157 */
   bso_pod_require(pd, p, &req);                                       /* :158 */
   bso_resource_add(&need, &req, nd->lanes);                           /* :159 */
-  if (!bso_compare_cluster(nd, eg->rep_sel[m], eg->rep_tol[m], &need, 0.7f)) { /* :161 */
+  if (!bso_compare_cluster(nd, eg->rep_sel[m], eg->rep_tol[m], eg->rep_aff[m], &need, 0.7f)) { /* :161 */
     *deny = 1;                                                        /* :163 */
     return BSO_PF_NOT_ENOUGH;                                         /* :164 */
   }
@@ -652,6 +666,7 @@ int bso_replay(bso_nodes* nd, const bso_pods* pd, bso_groups* gr, const uint32_t
         gr->flags[g] |= BSO_GROUP_HAS_POD;
         gr->rep_sel[g] = pd->sel_mask[p];
         gr->rep_tol[g] = pd->tol_mask[p];
+        if (gr->rep_aff) gr->rep_aff[g] = POD_AFF(pd, p);
       }
       if (!(gr->flags[g] & BSO_GROUP_HAS_MINRES)) {
         gr->flags[g] |= BSO_GROUP_HAS_MINRES;
@@ -671,7 +686,7 @@ int bso_replay(bso_nodes* nd, const bso_pods* pd, bso_groups* gr, const uint32_t
       bso_resource need, req;
       if (matched == 0) {
         bso_pre_allocated(gr, (uint32_t)g, 0, &need);
-        if (!bso_compare_cluster(nd, gr->rep_sel[g], gr->rep_tol[g], &need, 1.0f)) {
+        if (!bso_compare_cluster(nd, gr->rep_sel[g], gr->rep_tol[g], GROUP_AFF(gr, g), &need, 1.0f)) {
           gr->flags[g] |= BSO_GROUP_DENIED;
           code = BSO_PF_NOT_ENOUGH;
         }
@@ -681,7 +696,7 @@ int bso_replay(bso_nodes* nd, const bso_pods* pd, bso_groups* gr, const uint32_t
       bso_pre_allocated(gr, (uint32_t)m, (int64_t)matched, &need);
       bso_pod_require(pd, p, &req);
       bso_resource_add(&need, &req, L);
-      if (!bso_compare_cluster(nd, gr->rep_sel[m], gr->rep_tol[m], &need, 0.7f)) {
+      if (!bso_compare_cluster(nd, gr->rep_sel[m], gr->rep_tol[m], GROUP_AFF(gr, m), &need, 0.7f)) {
         gr->flags[g] |= BSO_GROUP_DENIED;
         code = BSO_PF_NOT_ENOUGH;
       }

@@ -40,6 +40,7 @@
 #define BSO_GROUP_HAS_POD 0x02u
 #define BSO_GROUP_HAS_MINRES 0x04u
 #define BSO_GROUP_DENIED 0x08u
+#define BSO_AFF_NONE 0xffffffffu
 #define BSO_GID_NONE (-1)
 #define BSO_GID_MISSING (-2)
 
@@ -66,6 +67,8 @@ typedef struct {
   uint64_t* label_mask;
   uint64_t* taint_mask;
   uint8_t* flags;
+  uint32_t n_aff;      /* affinity classes in aff_bits (0: none) */
+  uint32_t* aff_bits;  /* [n_aff][ceil(n/32)] host-evaluated (affinity class, node) predicate bits, or NULL */
 } bso_nodes;
 
 typedef struct {
@@ -78,6 +81,7 @@ typedef struct {
   int32_t* priority;
   int64_t* ts_ns;
   uint8_t* flags;
+  uint32_t* aff_class; /* [n] row of aff_bits the pod must match, BSO_AFF_NONE = none; NULL = all NONE */
 } bso_pods;
 
 typedef struct {
@@ -92,6 +96,7 @@ typedef struct {
   uint64_t* rep_tol;
   int64_t* creation_ns;
   uint32_t* name_rank;
+  uint32_t* rep_aff;   /* affinity class of pgs.Pod, or NULL */
 } bso_groups;
 
 typedef struct {
@@ -115,15 +120,15 @@ typedef struct {
 
 /* ---- line-by-line helpers ---- */
 int64_t bso_scale(int64_t alloc, float percent);                              /* core.go:656-659,667 */
-int bso_check_fit(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol); /* core.go:741-759 */
-void bso_single_node_resource(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol,
+int bso_check_fit(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol, uint32_t aff); /* core.go:741-759 */
+void bso_single_node_resource(const bso_nodes* nd, uint32_t i, uint64_t sel, uint64_t tol, uint32_t aff,
                               float percent, bso_resource* out);              /* core.go:634-670 */
 int bso_compare_resource_and_require(const bso_resource* left, const bso_resource* req,
                                      uint32_t lanes);                         /* core.go:672-699 */
 void bso_resource_add(bso_resource* acc, const bso_resource* x, uint32_t lanes); /* Resource.Add(x.ResourceList()) */
-int bso_compare_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, const bso_resource* need,
+int bso_compare_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, uint32_t aff, const bso_resource* need,
                         float percent);                                       /* core.go:595-632 */
-void bso_compute_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, bso_resource* out); /* core.go:566-593 */
+void bso_compute_cluster(const bso_nodes* nd, uint64_t sel, uint64_t tol, uint32_t aff, bso_resource* out); /* core.go:566-593 */
 int bso_find_max_pg(const bso_groups* gr, uint32_t* max_finished, int* panic); /* core.go:701-739 */
 void bso_pre_allocated(const bso_groups* gr, uint32_t g, int64_t matched, bso_resource* out); /* core.go:774-793 */
 void bso_pod_require(const bso_pods* pd, uint32_t p, bso_resource* out);      /* core.go:761-772 (packed) */

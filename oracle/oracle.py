@@ -38,14 +38,15 @@ class _Nodes(C.Structure):
     _fields_ = [("n", C.c_uint32), ("lanes", C.c_uint32), ("alloc", _p(C.c_int64)),
                 ("requested", _p(C.c_int64)), ("pod_count", _p(C.c_int32)),
                 ("alloc_present", _p(C.c_uint32)), ("req_present", _p(C.c_uint32)),
-                ("label_mask", _p(C.c_uint64)), ("taint_mask", _p(C.c_uint64)), ("flags", _p(C.c_uint8))]
+                ("label_mask", _p(C.c_uint64)), ("taint_mask", _p(C.c_uint64)), ("flags", _p(C.c_uint8)),
+                ("n_aff", C.c_uint32), ("aff_bits", _p(C.c_uint32))]
 
 
 class _Pods(C.Structure):
     _fields_ = [("n", C.c_uint32), ("lanes", C.c_uint32), ("req", _p(C.c_int64)),
                 ("req_present", _p(C.c_uint32)), ("gid", _p(C.c_int32)), ("sel_mask", _p(C.c_uint64)),
                 ("tol_mask", _p(C.c_uint64)), ("priority", _p(C.c_int32)), ("ts_ns", _p(C.c_int64)),
-                ("flags", _p(C.c_uint8))]
+                ("flags", _p(C.c_uint8)), ("aff_class", _p(C.c_uint32))]
 
 
 class _Groups(C.Structure):
@@ -53,7 +54,7 @@ class _Groups(C.Structure):
                 ("scheduled", _p(C.c_uint32)), ("matched", _p(C.c_uint32)), ("flags", _p(C.c_uint8)),
                 ("min_res", _p(C.c_int64)), ("min_res_present", _p(C.c_uint32)),
                 ("rep_sel", _p(C.c_uint64)), ("rep_tol", _p(C.c_uint64)), ("creation_ns", _p(C.c_int64)),
-                ("name_rank", _p(C.c_uint32))]
+                ("name_rank", _p(C.c_uint32)), ("rep_aff", _p(C.c_uint32))]
 
 
 class _Results(C.Structure):
@@ -76,10 +77,10 @@ def lib():
         _lib.bso_scale.restype = C.c_int64
         _lib.bso_scale.argtypes = [C.c_int64, C.c_float]
         _lib.bso_permit_ready.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
-        _lib.bso_compare_cluster.argtypes = [_p(_Nodes), C.c_uint64, C.c_uint64, _p(_Resource), C.c_float]
-        _lib.bso_single_node_resource.argtypes = [_p(_Nodes), C.c_uint32, C.c_uint64, C.c_uint64,
+        _lib.bso_compare_cluster.argtypes = [_p(_Nodes), C.c_uint64, C.c_uint64, C.c_uint32, _p(_Resource), C.c_float]
+        _lib.bso_single_node_resource.argtypes = [_p(_Nodes), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
                                                   C.c_float, _p(_Resource)]
-        _lib.bso_compute_cluster.argtypes = [_p(_Nodes), C.c_uint64, C.c_uint64, _p(_Resource)]
+        _lib.bso_compute_cluster.argtypes = [_p(_Nodes), C.c_uint64, C.c_uint64, C.c_uint32, _p(_Resource)]
         _lib.bso_pre_allocated.argtypes = [_p(_Groups), C.c_uint32, C.c_int64, _p(_Resource)]
         _lib.bso_fit_eval.argtypes = [_p(_Nodes), _p(_Pods), C.c_uint32, C.c_uint32, _p(C.c_int64)]
         _lib.bso_compare.argtypes = [_p(_Pods), _p(_Groups), C.c_uint32, C.c_uint32]
@@ -92,17 +93,26 @@ def _ptr(a, t):
     return a.ctypes.data_as(_p(t))
 
 
-def _nodes(nt):
+AFF_NONE = 0xFFFFFFFF
+
+
+def _nodes(nt, aff_bits=None):
+    """aff_bits: Snapshot.aff_bits ([n_aff, ceil(N/32)] uint32) or None."""
+    if aff_bits is not None:
+        assert aff_bits.dtype == np.uint32 and aff_bits.flags["C_CONTIGUOUS"] and aff_bits.shape[1] == (nt.n + 31) // 32
     return _Nodes(nt.n, nt.lanes, _ptr(nt.alloc, C.c_int64), _ptr(nt.requested, C.c_int64),
                   _ptr(nt.pod_count, C.c_int32), _ptr(nt.alloc_present, C.c_uint32),
                   _ptr(nt.req_present, C.c_uint32), _ptr(nt.label_mask, C.c_uint64),
-                  _ptr(nt.taint_mask, C.c_uint64), _ptr(nt.flags, C.c_uint8))
+                  _ptr(nt.taint_mask, C.c_uint64), _ptr(nt.flags, C.c_uint8),
+                  0 if aff_bits is None else aff_bits.shape[0], None if aff_bits is None else _ptr(aff_bits, C.c_uint32))
 
 
 def _pods(pt):
+    aff = getattr(pt, "aff_class", None)
     return _Pods(pt.n, pt.lanes, _ptr(pt.req, C.c_int64), _ptr(pt.req_present, C.c_uint32),
                  _ptr(pt.gid, C.c_int32), _ptr(pt.sel_mask, C.c_uint64), _ptr(pt.tol_mask, C.c_uint64),
-                 _ptr(pt.priority, C.c_int32), _ptr(pt.ts_ns, C.c_int64), _ptr(pt.flags, C.c_uint8))
+                 _ptr(pt.priority, C.c_int32), _ptr(pt.ts_ns, C.c_int64), _ptr(pt.flags, C.c_uint8),
+                 None if aff is None else _ptr(aff, C.c_uint32))
 
 
 def _groups(gt):
@@ -110,7 +120,8 @@ def _groups(gt):
                    _ptr(gt.matched, C.c_uint32), _ptr(gt.flags, C.c_uint8), _ptr(gt.min_res, C.c_int64),
                    _ptr(gt.min_res_present, C.c_uint32), _ptr(gt.rep_sel, C.c_uint64),
                    _ptr(gt.rep_tol, C.c_uint64), _ptr(gt.creation_ns, C.c_int64),
-                   _ptr(gt.name_rank, C.c_uint32))
+                   _ptr(gt.name_rank, C.c_uint32),
+                   None if getattr(gt, "rep_aff", None) is None else _ptr(gt.rep_aff, C.c_uint32))
 
 
 def _res_from(vals, present, lanes):
@@ -129,10 +140,10 @@ def permit_ready(matched: int, min_member: int, scheduled: int) -> bool:
     return bool(lib().bso_permit_ready(matched, min_member, scheduled))
 
 
-def single_node_resource(nt, i, sel, tol, percent):
+def single_node_resource(nt, i, sel, tol, percent, aff=AFF_NONE, aff_bits=None):
     r = _Resource()
-    nd = _nodes(nt)
-    lib().bso_single_node_resource(C.byref(nd), i, int(sel), int(tol), C.c_float(percent), C.byref(r))
+    nd = _nodes(nt, aff_bits)
+    lib().bso_single_node_resource(C.byref(nd), i, int(sel), int(tol), int(aff), C.c_float(percent), C.byref(r))
     return np.array(r.v[:nt.lanes], dtype=np.int64), int(r.present)
 
 
@@ -144,22 +155,22 @@ def node_left(nt, sel, tol, percent):
     r = _Resource()
     f = lib().bso_single_node_resource
     for i in range(nt.n):
-        f(C.byref(nd), i, int(sel), int(tol), C.c_float(percent), C.byref(r))
+        f(C.byref(nd), i, int(sel), int(tol), AFF_NONE, C.c_float(percent), C.byref(r))
         left[:, i] = r.v[:nt.lanes]
         pres[i] = r.present
     return left, pres
 
 
-def compare_cluster(nt, sel, tol, need, need_present, percent) -> bool:
-    nd = _nodes(nt)
+def compare_cluster(nt, sel, tol, need, need_present, percent, aff=AFF_NONE, aff_bits=None) -> bool:
+    nd = _nodes(nt, aff_bits)
     r = _res_from(need, need_present, nt.lanes)
-    return bool(lib().bso_compare_cluster(C.byref(nd), int(sel), int(tol), C.byref(r), C.c_float(percent)))
+    return bool(lib().bso_compare_cluster(C.byref(nd), int(sel), int(tol), int(aff), C.byref(r), C.c_float(percent)))
 
 
 def compute_cluster(nt, sel, tol):
     nd = _nodes(nt)
     r = _Resource()
-    lib().bso_compute_cluster(C.byref(nd), int(sel), int(tol), C.byref(r))
+    lib().bso_compute_cluster(C.byref(nd), int(sel), int(tol), AFF_NONE, C.byref(r))
     return np.array(r.v[:nt.lanes], dtype=np.int64), int(r.present)
 
 
@@ -231,7 +242,7 @@ def round(snap, want_bitmap=True, want_score=False, faithful=False, threads=0, w
                    _ptr(r.filter_code, C.c_uint8) if want_filter else None,
                    _ptr(r.fit_bitmap, C.c_uint32) if want_bitmap else None,
                    _ptr(r.score, C.c_int64) if want_score else None, -1, 0, 0)
-    nd, pd, gr = _nodes(nt), _pods(pt), _groups(gt)
+    nd, pd, gr = _nodes(nt, getattr(snap, "aff_bits", None)), _pods(pt), _groups(gt)
     rc = lib().bso_round(C.byref(nd), C.byref(pd), C.byref(gr), C.byref(res), int(faithful), int(threads))
     if rc < 0:
         raise MemoryError("oracle round failed")
@@ -247,7 +258,9 @@ def replay(snap, queue=None):
     pf = np.zeros(len(q), np.uint8)
     node = np.zeros(len(q), np.int32)
     ready = np.zeros(len(q), np.uint8)
-    nd, pd, gr = _nodes(nt), _pods(pt), _groups(gt)
+    if pt.aff_class is not None and gt.rep_aff is None:
+        gt.rep_aff = np.full(gt.n, AFF_NONE, np.uint32)   # the walk records the first pod's class here
+    nd, pd, gr = _nodes(nt, getattr(s, "aff_bits", None)), _pods(pt), _groups(gt)
     f = lib().bso_replay
     f.argtypes = [_p(_Nodes), _p(_Pods), _p(_Groups), _p(C.c_uint32), C.c_uint32, _p(C.c_uint8),
                   _p(C.c_int32), _p(C.c_uint8)]

@@ -4,6 +4,7 @@
 //   pack_core_test    : core_test.go:27-115 objects -> packed tables             (CPU)
 //   readme            : README.md:76-188 resource race, pod by pod, on the GPU
 //   readme_replay     : the same race in one call (all pods pending, the device walks the queue)
+//   pack_affinity [k] : required nodeAffinity terms -> affinity classes + verdict bits; k > 64 extra selector pairs (CPU)
 //   bench_pack N P G  : packer throughput on synthetic objects                   (CPU)
 #include <chrono>
 #include <cstdio>
@@ -437,6 +438,76 @@ static int cmd_readme_replay() {
   return 0;
 }
 
+// Required node affinity (checkFit -> PodMatchNodeSelector, core.go:741-746) through the packer: pods with
+// matchExpressions / matchFields terms get affinity classes, the (class, node) verdicts come out as bits;
+// `many` > 64 distinct nodeSelector pairs move every selector into the table as well.
+static int cmd_pack_affinity(int many) {
+  const int N = 40;
+  std::vector<Node> nodes(N);
+  std::vector<NodeInfo> infos(N);
+  for (int i = 0; i < N; ++i) {
+    nodes[i].name = "node-" + std::to_string(i);
+    nodes[i].allocatable = {{"cpu", "16"}, {"memory", "64Gi"}, {"pods", "110"}};
+    nodes[i].labels = {{"zone", "z" + std::to_string(i % 4)}, {"cores", std::to_string(8 << (i % 3))}};
+    if (i % 2) nodes[i].labels["disk"] = "ssd";
+    if (i % 5 == 0) nodes[i].labels["gpu"] = "a100";
+    if (i % 7 == 0) nodes[i].labels["cores"] = "many";            // not an integer: Gt / Lt never match
+    for (int k = 0; k < many; ++k) if ((i + k) % 3 == 0) nodes[i].labels["k" + std::to_string(k)] = "v";
+    infos[i].node = &nodes[i];
+  }
+  infos[9].node = nullptr;   // info.Node() == nil: no verdict bit
+  auto req = [](const char* key, const char* op, std::vector<std::string> vals) {
+    NodeSelectorRequirement r; r.key = key; r.op = op; r.values = std::move(vals); return r;
+  };
+  std::vector<Pod> pods;
+  auto add = [&](std::vector<NodeSelectorTerm> terms, std::map<std::string, std::string> sel = {}) {
+    Pod p;
+    p.ns = "default"; p.name = "pod-" + std::to_string(pods.size()); p.uid = "uid-" + std::to_string(pods.size());
+    Container c; c.has_limits = true; c.limits = {{"cpu", "1"}};
+    p.containers = {c};
+    p.has_required_affinity = true;
+    p.required_affinity = std::move(terms);
+    p.node_selector = std::move(sel);
+    pods.push_back(p);
+  };
+  NodeSelectorTerm t;
+  t = {}; t.match_expressions = {req("zone", "In", {"z1", "z3"})}; add({t});                                  // 0
+  t = {}; t.match_expressions = {req("zone", "NotIn", {"z0"}), req("disk", "Exists", {})}; add({t});          // 1
+  t = {}; t.match_expressions = {req("gpu", "DoesNotExist", {})}; add({t});                                   // 2
+  t = {}; t.match_expressions = {req("cores", "Gt", {"8"})}; add({t});                                        // 3
+  t = {}; t.match_expressions = {req("cores", "Lt", {"32"})}; add({t}, {{"disk", "ssd"}});                    // 4  + nodeSelector
+  { NodeSelectorTerm a, b; a.match_expressions = {req("zone", "In", {"z0"})}; b.match_expressions = {req("gpu", "In", {"a100"})};
+    add({a, b}); }                                                                                            // 5  ORed terms
+  t = {}; t.match_fields = {req("metadata.name", "In", {"node-7"})}; add({t});                                // 6
+  t = {}; t.match_fields = {req("metadata.name", "NotIn", {"node-7"})}; t.match_expressions = {req("zone", "In", {"z3"})}; add({t});  // 7
+  add({NodeSelectorTerm{}});                                                                                  // 8  empty term: matches nothing
+  add({});                                                                                                    // 9  no terms: matches nothing
+  t = {}; t.match_expressions = {req("zone", "In", {})}; add({t});                                            // 10 invalid requirement
+  t = {}; t.match_expressions = {req("cores", "Gt", {"1", "2"})}; add({t});                                   // 11 invalid: Gt needs one value
+  t = {}; t.match_expressions = {req("zone", "In", {"z1", "z3"})}; add({t});                                  // 12 same class as 0
+  { Pod p; p.ns = "default"; p.name = "plain"; p.uid = "uid-plain"; Container c; c.has_limits = true; c.limits = {{"cpu", "1"}};
+    p.containers = {c}; p.node_selector = {{"disk", "ssd"}}; pods.push_back(p); }                             // 13 selector only
+  for (int k = 0; k < many; ++k) {                                                                            // 14.. distinct pairs
+    Pod p; p.ns = "default"; p.name = "sel-" + std::to_string(k); p.uid = "uid-sel-" + std::to_string(k);
+    Container c; c.has_limits = true; c.limits = {{"cpu", "1"}};
+    p.containers = {c}; p.node_selector = {{"k" + std::to_string(k), "v"}};
+    pods.push_back(p);
+  }
+  std::vector<const NodeInfo*> snap(N);
+  std::vector<const Pod*> pend(pods.size());
+  for (int i = 0; i < N; ++i) snap[i] = &infos[i];
+  for (size_t i = 0; i < pods.size(); ++i) pend[i] = &pods[i];
+  PackedSnapshot ps;
+  Status st = BatchSchedulingPlugin::Pack(snap, pend, {}, {}, {}, {}, 0, &ps);
+  if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+  printf("{\"n_nodes\": %d, \"n_aff\": %u, \"sel_in_table\": %d, \"n_sel_pairs\": %zu,\n", N, ps.n_aff(), ps.sel_in_table ? 1 : 0,
+         ps.sel_pairs.size());
+  print_arr("aff_class", ps.aff_class); print_arr("sel_mask", ps.sel_mask); print_arr("label_mask", ps.label_mask);
+  print_arr("aff_bits", ps.aff_bits, true);
+  printf("}\n");
+  return 0;
+}
+
 static int cmd_bench_pack(int N, int P, int G) {
   std::vector<Node> nodes(N);
   std::vector<NodeInfo> infos(N);
@@ -496,6 +567,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "pack_group_delta")) return cmd_pack_group_delta();
   if (!strcmp(argv[1], "readme")) return cmd_readme();
   if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
+  if (!strcmp(argv[1], "pack_affinity")) return cmd_pack_affinity(argc >= 3 ? atoi(argv[2]) : 0);
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
   return 2;
 }

@@ -33,7 +33,8 @@ def dump(name, snap, queue):
     d = {"queue": queue, "out__prefilter": pf, "out__node": node, "out__ready": ready}
     for tname, t in (("nodes", snap.nodes), ("pods", snap.pods), ("groups", snap.groups)):
         for f in t.__dataclass_fields__:
-            d[f"{tname}__{f}"] = getattr(t, f)
+            if getattr(t, f) is not None:
+                d[f"{tname}__{f}"] = getattr(t, f)
     np.savez_compressed(os.path.join(HERE, f"replay_{name}.npz"), **d)
     print(name, np.bincount(pf, minlength=6).tolist(), int((node >= 0).sum()), int(ready.sum()))
 

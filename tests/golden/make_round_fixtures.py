@@ -28,7 +28,8 @@ def dump(name, snap):
     d = {}
     for tname, t in (("nodes", snap.nodes), ("pods", snap.pods), ("groups", snap.groups)):
         for f in t.__dataclass_fields__:
-            d[f"{tname}__{f}"] = getattr(t, f)
+            if getattr(t, f) is not None:
+                d[f"{tname}__{f}"] = getattr(t, f)
     for f in ("prefilter", "feasible_count", "best_node", "best_score", "admit", "admit_bitmap", "new_denied", "order",
               "rank", "fit_bitmap", "score", "filter_bitmap", "filter_code"):
         d[f"out__{f}"] = getattr(r, f)

@@ -16,7 +16,7 @@ def load(path):
     S = importlib.import_module("batch-scheduler_b200.snapshot")
     z = np.load(path)
     def table(cls, prefix):
-        return cls(**{f: z[f"{prefix}__{f}"] for f in cls.__dataclass_fields__})
+        return cls(**{f: z[f"{prefix}__{f}"] for f in cls.__dataclass_fields__ if f"{prefix}__{f}" in z.files})
     snap = S.Snapshot(table(S.NodeTable, "nodes"), table(S.PodTable, "pods"), table(S.GroupTable, "groups"),
                       os.path.basename(path))
     out = {k[5:]: z[k] for k in z.files if k.startswith("out__")}

@@ -8,7 +8,9 @@ import numpy as np
 S = importlib.import_module("batch-scheduler_b200.snapshot")
 
 
-def random_snapshot(seed, P=200, N=70, G=30, L=6, case="mixed", value_scale="normal"):
+def random_snapshot(seed, P=200, N=70, G=30, L=6, case="mixed", value_scale="normal", aff=0):
+    """aff > 0: that many affinity classes (required nodeAffinity terms the bit masks cannot carry) with a
+    random (class, node) bit table; pods and group representatives draw a class or AFF_NONE."""
     rng = np.random.default_rng(seed)
     nt = S.NodeTable.empty(N, L)
     big = value_scale == "big"
@@ -85,4 +87,16 @@ def random_snapshot(seed, P=200, N=70, G=30, L=6, case="mixed", value_scale="nor
     pf |= np.where(rng.random(P) < 0.03, S.POD_OCC_NOREFS, 0).astype(np.uint8)
     pf |= np.where(rng.random(P) < 0.03, S.POD_OCC_MISMATCH, 0).astype(np.uint8)
     pt.flags = pf
-    return S.Snapshot(nt, pt, gt, f"rand{seed}")
+    snap = S.Snapshot(nt, pt, gt, f"rand{seed}")
+    if aff:
+        W = (N + 31) // 32
+        dens = rng.choice([0.0, 0.2, 0.6, 0.95, 1.0], aff)
+        bits = np.zeros((aff, W), np.uint32)
+        for c in range(aff):
+            on = rng.random(N) < dens[c]
+            by = np.packbits(np.concatenate([on, np.zeros(W * 32 - N, bool)]), bitorder="little")
+            bits[c] = by.view(np.uint32)
+        snap.aff_bits = bits
+        pt.aff_class = np.where(rng.random(P) < 0.5, S.AFF_NONE, rng.integers(0, aff, P)).astype(np.uint32)
+        gt.rep_aff = np.where(rng.random(G) < 0.5, S.AFF_NONE, rng.integers(0, aff, G)).astype(np.uint32)
+    return snap

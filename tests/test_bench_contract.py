@@ -12,7 +12,7 @@ REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
 
 def test_reference_arm_json_line():
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
-                                   "--warmup", "1"], text=True, timeout=600)
+                                   "--warmup", "1", "--scale", "0.05"], text=True, timeout=600)
     lines = [ln for ln in out.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
@@ -21,6 +21,12 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0 and "workload" in d["config"]
+    # both arms print the SAME config object (the driver compares them): built by one function
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(0.05)
+    assert d["cpu_baseline_1thread"]["cores"] == 1 and d["cpu_baseline"]["cores"] == bench.usable_threads()
+    assert d["sample_pods_per_step"] == d["config"]["pods_per_gpu"]   # the whole snapshot per step
 
 
 def test_reference_arm_other_ranks_are_silent():

