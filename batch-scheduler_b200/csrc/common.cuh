@@ -17,19 +17,22 @@ constexpr int LANE_CPU = 0, LANE_MEM = 1, LANE_EPH = 2, LANE_PODS = 3;
 constexpr int64_t ABSENT_LEFT = (int64_t)1 << 61;      // left lane without a map key: never limits
 constexpr int64_t UNCHECKED_REQ = -((int64_t)1 << 61); // request lane without a map key: never checked
 // Narrow lanes: a lane whose every |left| and |req| is <= 2^27 (millicores, pod counts, GPUs ...)
-// is evaluated in int32: |real diff| <= 2^28 < any diff involving a 32-bit sentinel (>= 2^29-2^27),
+// is evaluated in int32: |real diff| < 2^27 < any diff involving a 32-bit sentinel (>= 2^29-2^26),
 // and 2^29 - (-2^29) does not overflow.  The narrow set always contains a fixed lane (always a
 // real value), so the 32-bit min is always a real difference and widens by sign extension.
 constexpr int32_t ABSENT_LEFT32 = 1 << 29;
 constexpr int32_t UNCHECKED_REQ32 = -(1 << 29);
-constexpr int64_t NARROW_LIMIT = (int64_t)1 << 27;
+// |v| <= 2^26 - 1 on both sides: every real narrow difference is < 2^27, so a fitting pair's score fits 27 bits
+// and (score << KEY_BITS) + j stays below 2^31 (the best-node key of the fit kernel)
+constexpr int FIT_CAP_LOG2 = 27;
+constexpr int64_t NARROW_LIMIT = ((int64_t)1 << (FIT_CAP_LOG2 - 1)) - 1;
 // Scaled lanes (round 2): a byte-valued lane whose every `left` and `req` is a multiple of 2^k
 // (k = the lane's common trailing zeros, found at upload) and fits |v| >> k <= 2^29 is carried in
 // units of 2^k as int32 — EXACT: (left - req) >= 0  <=>  (left>>k) - (req>>k) >= 0, and the
 // difference in original units is (left>>k - req>>k) << k.  A fitting pair's score is <= the
-// narrow-lane minimum t <= 2^28, so a scaled difference only matters below 2^28: the kernel clamps
-// it to C = 2^(28-k) (k <= 28; else 1) before shifting back by min(k, 28), i.e. it contributes either its
-// exact value or 2^28 ("not the minimum").  Sentinels +-(2^30 - 1): no int32 overflow against 2^29.
+// narrow-lane minimum t < 2^27, so a scaled difference only matters below 2^27: the kernel clamps
+// it to C = 2^(27-k) (k <= 27; else 1) before shifting back by min(k, 27), i.e. it contributes either its
+// exact value or 2^27 ("not the minimum").  Sentinels +-(2^30 - 1): no int32 overflow against 2^29.
 constexpr int32_t ABSENT_LEFTS = (1 << 30) - 1;
 constexpr int32_t UNCHECKED_REQS = -((1 << 30) - 1);
 constexpr int64_t SCALED_LIMIT = (int64_t)1 << 29;
@@ -43,7 +46,7 @@ struct LaneMap {
   uint32_t LW, LN, LS;
 };
 #ifndef BS_FIT_TILE
-#define BS_FIT_TILE 256
+#define BS_FIT_TILE 512
 #endif
 constexpr int NODE_TILE = BS_FIT_TILE;                  // nodes per shared-memory tile (128 / 256 / 512 / 1024)
 #ifndef BS_FIT_WARPS
@@ -59,8 +62,10 @@ constexpr int PODS_PER_CTA = FIT_WARPS * PODS_PER_WARP; // 32
 constexpr int TILE_WORDS = NODE_TILE / 32;              // ballot words per tile and pod
 static_assert(TILE_WORDS <= 32 && 32 % TILE_WORDS == 0, "a 32-word bitmap line is a whole number of tiles");
 constexpr int TILES_PER_LINE = 32 / TILE_WORDS;         // tiles whose ballot words fill one 128-byte bitmap line
+constexpr int KEY_BITS = TILE_WORDS <= 2 ? 1 : TILE_WORDS <= 4 ? 2 : TILE_WORDS <= 8 ? 3 : 4;   // log2(TILE_WORDS)
+static_assert(TILE_WORDS <= 16, "best-node key: score (27 bits) + word index (4 bits) must fit 31 bits");
 #ifndef BS_FIT_STAGES
-#define BS_FIT_STAGES 3
+#define BS_FIT_STAGES 2
 #endif
 constexpr int FIT_STAGES = BS_FIT_STAGES;               // TMA ring depth (full/empty mbarrier pairs)
 #ifndef BS_FIT_SEG

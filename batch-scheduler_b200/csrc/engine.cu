@@ -33,9 +33,12 @@ namespace {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;    // false: a view into an arena (alias), never freed here
+  void alias(void* ptr, size_t bytes) { p = ptr; cap = bytes; owned = false; }
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
+    owned = true;
     p = nullptr;
     cap = 0;
     const size_t want = std::max<size_t>(bytes, 256);
@@ -44,9 +47,10 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p); }
@@ -55,9 +59,12 @@ struct DevBuf {
 struct PinBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;
+  void alias(void* ptr, size_t bytes) { p = ptr; cap = bytes; owned = false; }
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
+    if (p && owned) cudaFreeHost(p);
+    owned = true;
     p = nullptr;
     cap = 0;
     const size_t want = std::max<size_t>(bytes, 256);
@@ -66,9 +73,10 @@ struct PinBuf {
     return e;
   }
   void release() {
-    if (p) cudaFreeHost(p);
+    if (p && owned) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p); }
@@ -245,6 +253,8 @@ struct bs_engine {
   DevBuf d_state, d_pre, d_pre_present, d_pre_stats, d_max_partial, d_pre_part, d_pre_part_pres, d_pre_cstats, d_pre_done;
   uint32_t prefix_slots = 0;
   // outputs
+  DevBuf u_buf[9];        // bs_update_nodes / bs_update_groups: device scratch of the changed rows
+  DevBuf d_best_packed;   // gang_fit tail pieces: max((score + 1) << 32 | ~node) per pod
   DevBuf d_prefilter, d_feasible, d_best_node, d_best_score, d_admit, d_admit_bitmap, d_new_denied,
       d_fit_bitmap, d_score, d_order, d_rank;
   // sort scratch
@@ -276,6 +286,11 @@ struct bs_engine {
   PinBuf h_prefilter, h_feasible, h_best_node, h_best_score, h_admit, h_admit_bitmap, h_new_denied,
       h_order, h_rank, h_state, h_filter_code;
   bool fetched = false;
+  // decision arena: every per-round decision vector lives in ONE device block and ONE pinned block with the
+  // same layout (the d_* / h_* buffers above are views into them), so bs_fetch is a single D2H copy
+  DevBuf d_arena;
+  PinBuf h_arena;
+  size_t arena_bytes = 0;
 
   // bs_replay scratch (kept between calls: cudaMalloc/cudaFree per call would dominate small queues)
   DevBuf r_req, r_pc, r_rp, r_matched, r_gflags, r_grc, r_minres, r_mrp, r_queue, r_pf, r_node, r_ready, r_status,
@@ -522,9 +537,10 @@ void launch_replay(uint32_t L, const ReplayArgs& a, cudaStream_t s) {
   }
 }
 
-cudaError_t launch_fit(const FitArgs& a, uint32_t grid, cudaStream_t s) {
-  FitFn fn = fit_lookup(a.lm.LW, a.lm.LN, a.lm.LS, a.score != nullptr);
-  return fn ? fn(a, grid, s) : cudaErrorInvalidValue;
+cudaError_t launch_fit(const FitArgs& a, uint32_t units, cudaStream_t s, uint32_t* launches) {
+  const int out = a.score ? FIT_OUT_SCORE : (a.fit_bitmap ? FIT_OUT_BITMAP : FIT_OUT_NONE);
+  FitFn fn = fit_lookup(a.lm.LW, a.lm.LN, a.lm.LS, out);
+  return fn ? fn(a, units, s, launches) : cudaErrorInvalidValue;
 }
 
 inline uint32_t ctz64(uint64_t v) { return v ? (uint32_t)__builtin_ctzll(v) : 63u; }
@@ -580,8 +596,8 @@ LaneMap classify_lanes(const bs_engine* e) {
       const uint32_t k = unit[d];
       lm.scaled[lm.LS] = (uint8_t)d;
       lm.sunit[lm.LS] = (uint8_t)k;
-      lm.sshift[lm.LS] = (uint8_t)std::min(k, 28u);
-      lm.sclamp[lm.LS] = k <= 28 ? (1u << (28 - k)) : 1u;
+      lm.sshift[lm.LS] = (uint8_t)std::min(k, (uint32_t)FIT_CAP_LOG2);
+      lm.sclamp[lm.LS] = k <= (uint32_t)FIT_CAP_LOG2 ? (1u << (FIT_CAP_LOG2 - k)) : 1u;
       ++lm.LS;
     } else lm.wide[lm.LW++] = (uint8_t)d;
   }
@@ -640,7 +656,10 @@ int rebuild_classes(bs_engine* e) {
     aff_bad = a != BS_AFF_NONE && a >= e->n_aff;
   }
   for (uint32_t g = 0; g < G && !aff_bad; ++g) aff_bad = e->h_gaff[g] != BS_AFF_NONE && e->h_gaff[g] >= e->n_aff;
-  if (aff_bad) return fail(e, BS_E_INDEX, "affinity class outside the uploaded table (bs_upload_affinity after bs_upload_nodes)");
+  if (aff_bad) {
+    if (groups_assigned) e->group_classes_dirty = true;   // their ids were not uploaded: assign again next time
+    return fail(e, BS_E_INDEX, "affinity class outside the uploaded table (bs_upload_affinity after bs_upload_nodes)");
+  }
   int rc;
   // cudaMemcpyAsync from pageable memory returns once the data is staged, so the vectors may die.
   if ((rc = upload_vec(e, e->d_fsel, fsel.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
@@ -672,24 +691,39 @@ int ensure_round_buffers(bs_engine* e) {
   CK(e->d_contrib.ensure((size_t)G * 4));
   CK(e->d_done.ensure((size_t)G * 4));
   CK(e->d_okA.ensure(G));
-  CK(e->d_state.ensure(sizeof(RoundState)));
-  CK(e->d_prefilter.ensure(P));
-  CK(e->d_feasible.ensure((size_t)P * 4));
-  CK(e->d_best_node.ensure((size_t)P * 4));
-  CK(e->d_best_score.ensure((size_t)P * 8));
-  CK(e->d_admit.ensure(G));
-  CK(e->d_admit_bitmap.ensure((size_t)cdiv(G, 32) * 4));
-  CK(e->d_new_denied.ensure(G));
-  CK(e->d_order.ensure((size_t)P * 4));
-  CK(e->d_rank.ensure((size_t)P * 4));
+  {
+    // decision arena layout (256-byte aligned fields)
+    struct F { DevBuf* d; PinBuf* h; size_t bytes; };
+    F fields[] = {{&e->d_state, &e->h_state, sizeof(RoundState)},
+                  {&e->d_prefilter, &e->h_prefilter, P},
+                  {&e->d_feasible, &e->h_feasible, (size_t)P * 4},
+                  {&e->d_best_node, &e->h_best_node, (size_t)P * 4},
+                  {&e->d_best_score, &e->h_best_score, (size_t)P * 8},
+                  {&e->d_admit, &e->h_admit, G},
+                  {&e->d_admit_bitmap, &e->h_admit_bitmap, (size_t)cdiv(G, 32) * 4},
+                  {&e->d_new_denied, &e->h_new_denied, G},
+                  {&e->d_order, &e->h_order, (size_t)P * 4},
+                  {&e->d_rank, &e->h_rank, (size_t)P * 4},
+                  {&e->d_filter_code, &e->h_filter_code, (e->out_flags & BS_OUT_FILTER) ? (size_t)P : 0}};
+    size_t total = 0;
+    for (auto& f : fields) total += (f.bytes + 255) & ~(size_t)255;
+    CK(e->d_arena.ensure(total));
+    CK(e->h_arena.ensure(total));
+    size_t off = 0;
+    for (auto& f : fields) {
+      f.d->alias(static_cast<char*>(e->d_arena.p) + off, f.bytes);
+      f.h->alias(static_cast<char*>(e->h_arena.p) + off, f.bytes);
+      off += (f.bytes + 255) & ~(size_t)255;
+    }
+    e->arena_bytes = total;
+  }
+  CK(e->d_best_packed.ensure((size_t)P * 8));
   // rows padded to a whole CTA of pods: the fit kernel writes pods >= P without a guard
   const size_t Prows = (size_t)cdiv(std::max(e->P, 1u), PODS_PER_CTA) * PODS_PER_CTA;
   if (e->out_flags & BS_OUT_FIT_BITMAP) CK(e->d_fit_bitmap.ensure(Prows * std::max(e->bitmap_pitch, 32u) * 4));
   if (e->out_flags & BS_OUT_SCORE) CK(e->d_score.ensure(Prows * std::max(e->score_pitch, 2u) * 8));
   if (e->out_flags & BS_OUT_FILTER) {
     CK(e->d_filter_bitmap.ensure(Prows * std::max(e->W, 1u) * 4));
-    CK(e->d_filter_code.ensure(P));
-    CK(e->h_filter_code.ensure(P));
   }
   // prefix scratch: as many rep-class slots as fit a 1 GiB budget
   const size_t per_class = (size_t)N * (8 * L + 4);
@@ -724,17 +758,6 @@ int ensure_round_buffers(bs_engine* e) {
   CK(e->d_tilecnt.ensure((size_t)cdiv(M, SORT_TILE) * 4));
   CK(e->d_sort_barrier.ensure(sizeof(unsigned int)));
   CK(e->d_group_rank.ensure((size_t)G * 4));
-  // pinned result cache
-  CK(e->h_prefilter.ensure(P));
-  CK(e->h_feasible.ensure((size_t)P * 4));
-  CK(e->h_best_node.ensure((size_t)P * 4));
-  CK(e->h_best_score.ensure((size_t)P * 8));
-  CK(e->h_admit.ensure(G));
-  CK(e->h_admit_bitmap.ensure((size_t)cdiv(G, 32) * 4));
-  CK(e->h_new_denied.ensure(G));
-  CK(e->h_order.ensure((size_t)P * 4));
-  CK(e->h_rank.ensure((size_t)P * 4));
-  CK(e->h_state.ensure(sizeof(RoundState)));
   return BS_OK;
 }
 
@@ -931,8 +954,10 @@ int evaluate_async_locked(bs_engine* e) {
       a.score_pitch = e->score_pitch;
       a.bitmap_pitch = e->bitmap_pitch;
       a.P = P; a.N = e->N; a.Npad = e->Npad; a.W = e->W;
-      CK(launch_fit(a, cdiv(P, PODS_PER_CTA), e->s));
-      tm.launched();
+      a.best_packed = e->d_best_packed.as<unsigned long long>();
+      uint32_t nl = 1;
+      CK(launch_fit(a, cdiv(P, PODS_PER_CTA), e->s, &nl));
+      tm.launched(nl);
     }
   }
   CK(cudaStreamWaitEvent(e->s, e->ev_pre, 0));   // PreFilter verdicts, effective group state, RoundState
@@ -1007,20 +1032,8 @@ int fetch_locked(bs_engine* e, bs_results* out) {
   if (!e->evaluated) return fail(e, BS_E_STATE, "bs_fetch: nothing evaluated");
   const uint32_t P = e->P, G = e->G;
   if (!e->fetched) {
-    auto d2h = [&](PinBuf& h, const DevBuf& d, size_t bytes) -> cudaError_t {
-      return bytes ? cudaMemcpyAsync(h.p, d.p, bytes, cudaMemcpyDeviceToHost, e->s) : cudaSuccess;
-    };
-    CK(d2h(e->h_prefilter, e->d_prefilter, P));
-    CK(d2h(e->h_feasible, e->d_feasible, (size_t)P * 4));
-    CK(d2h(e->h_best_node, e->d_best_node, (size_t)P * 4));
-    CK(d2h(e->h_best_score, e->d_best_score, (size_t)P * 8));
-    CK(d2h(e->h_admit, e->d_admit, G));
-    CK(d2h(e->h_admit_bitmap, e->d_admit_bitmap, (size_t)cdiv(G, 32) * 4));
-    CK(d2h(e->h_new_denied, e->d_new_denied, G));
-    CK(d2h(e->h_order, e->d_order, (size_t)P * 4));
-    CK(d2h(e->h_rank, e->d_rank, (size_t)P * 4));
-    CK(d2h(e->h_state, e->d_state, sizeof(RoundState)));
-    if (e->out_flags & BS_OUT_FILTER) CK(d2h(e->h_filter_code, e->d_filter_code, P));
+    if (e->arena_bytes)   // every decision vector in one DMA (the arena layout is the same on both sides)
+      CK(cudaMemcpyAsync(e->h_arena.p, e->d_arena.p, e->arena_bytes, cudaMemcpyDeviceToHost, e->s));
     CK(cudaStreamSynchronize(e->s));
     e->fetched = true;
   }
@@ -1111,6 +1124,7 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess;
     // the sort shares the GPU with the fit kernel on the other stream: one CTA per SM is plenty
     e->sort_max_grid = (uint32_t)std::max(1, std::min(per_sm * sms, sms));
+    if (const char* sg = getenv("BS_SORT_GRID")) e->sort_max_grid = (uint32_t)std::max(1, std::min(atoi(sg), per_sm * sms));
   }
   if (!ok) {
     bs_destroy(e);
@@ -1139,7 +1153,7 @@ void bs_destroy(bs_engine* e) {
                     &e->d_emrpres, &e->d_erep_class, &e->d_first_pod, &e->d_in_round, &e->d_contrib,
                     &e->d_done, &e->d_okA, &e->d_state, &e->d_pre, &e->d_pre_present, &e->d_pre_stats, &e->d_max_partial, &e->d_pre_part,
                     &e->d_pre_part_pres, &e->d_pre_cstats, &e->d_pre_done,
-                    &e->d_prefilter, &e->d_feasible, &e->d_best_node, &e->d_best_score, &e->d_admit,
+                    &e->d_best_packed, &e->d_prefilter, &e->d_feasible, &e->d_best_node, &e->d_best_score, &e->d_admit,
                     &e->d_admit_bitmap, &e->d_new_denied, &e->d_fit_bitmap, &e->d_score, &e->d_order,
                     &e->d_rank, &e->d_gk0, &e->d_gk1, &e->d_pk0, &e->d_pk1, &e->d_idx_a, &e->d_idx_b,
                     &e->d_ghist, &e->d_skip, &e->d_group_rank, &e->d_gorder, &e->d_tilecnt, &e->d_sort_barrier,
@@ -1147,6 +1161,9 @@ void bs_destroy(bs_engine* e) {
                     &e->r_queue, &e->r_pf, &e->r_node, &e->r_ready, &e->r_status, &e->r_sum, &e->r_max, &e->r_keys,
                     &e->r_left0, &e->r_left1, &e->r_both, &e->r_fit, &e->r_stat};
   for (DevBuf* b : bufs) b->release();
+  e->d_arena.release();
+  e->h_arena.release();
+  for (DevBuf& b : e->u_buf) b.release();
   PinBuf* pins[] = {&e->h_prefilter, &e->h_feasible, &e->h_best_node, &e->h_best_score, &e->h_admit,
                     &e->h_admit_bitmap, &e->h_new_denied, &e->h_order, &e->h_rank, &e->h_state, &e->h_filter_code};
   for (PinBuf* b : pins) b->release();
@@ -1205,7 +1222,8 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   e->N = N;
   e->score_pitch = (N + 1u) & ~1u;
   e->bitmap_pitch = (cdiv(N, 32) + 31u) & ~31u;
-  e->n_aff = 0;            // the affinity table belongs to the node snapshot
+  if (e->n_aff) e->classes_dirty = true;   // class ids are validated again: the affinity table belongs to the
+  e->n_aff = 0;                            // node snapshot and goes with it
   e->Npad = Npad;
   e->W = cdiv(N, 32);
   e->have_nodes = true;
@@ -1230,7 +1248,9 @@ int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t) {
   if (!lane_maxima(t->alloc, L, n, mx_a) || !lane_maxima(t->requested, L, n, mx_r))
     return fail(e, BS_E_RANGE, "bs_update_nodes: value outside +-2^56");
   BS_DEVICE_GUARD(e);
-  DevBuf da, dr, dpc, dap, drp, dl, dt, df, di;
+  // scratch of the changed rows: kept in the engine (cudaMalloc / cudaFree per call would cost more than the scatter)
+  DevBuf &da = e->u_buf[0], &dr = e->u_buf[1], &dpc = e->u_buf[2], &dap = e->u_buf[3], &drp = e->u_buf[4], &dl = e->u_buf[5],
+         &dt = e->u_buf[6], &df = e->u_buf[7], &di = e->u_buf[8];
   cudaError_t er = da.ensure((size_t)L * n * 8);
   if (er == cudaSuccess) er = dr.ensure((size_t)L * n * 8);
   if (er == cudaSuccess) er = dpc.ensure((size_t)n * 4);
@@ -1259,8 +1279,6 @@ int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t) {
     e->launches++;
     er = cudaStreamSynchronize(e->s);
   }
-  da.release(); dr.release(); dpc.release(); dap.release(); drp.release(); dl.release(); dt.release(); df.release();
-  di.release();
   CK(er);
   // lane maxima only ever grow here (a conservative bound keeps the wide/narrow split exact); the OR
   // of the residuals only gains bits (fewer common trailing zeros: a smaller unit, still exact)
@@ -1364,7 +1382,8 @@ int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t)
   for (uint32_t k = 0; k < n; ++k)
     if (t->creation_ns[k] == INT64_MAX) return fail(e, BS_E_RANGE, "bs_update_groups: creation_ns == INT64_MAX");
   BS_DEVICE_GUARD(e);
-  DevBuf dmm, dsc, dma, dfl, dmr, dmp, dcr, dnr, di;
+  DevBuf &dmm = e->u_buf[0], &dsc = e->u_buf[1], &dma = e->u_buf[2], &dfl = e->u_buf[3], &dmr = e->u_buf[4], &dmp = e->u_buf[5],
+         &dcr = e->u_buf[6], &dnr = e->u_buf[7], &di = e->u_buf[8];
   cudaError_t er = dmm.ensure((size_t)n * 4);
   if (er == cudaSuccess) er = dsc.ensure((size_t)n * 4);
   if (er == cudaSuccess) er = dma.ensure((size_t)n * 4);
@@ -1390,7 +1409,6 @@ int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t)
     e->launches++;
     er = cudaStreamSynchronize(e->s);
   }
-  for (DevBuf* b : {&dmm, &dsc, &dma, &dfl, &dmr, &dmp, &dcr, &dnr, &di}) b->release();
   CK(er);
   // sort-key digits that vary: the accumulated OR / AND only widen (a superset costs a pass, never an error)
   for (uint32_t k = 0; k < n; ++k) {

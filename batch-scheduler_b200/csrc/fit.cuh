@@ -73,6 +73,16 @@ __device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, uint32_t src_smem, 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_bulk_s2g_hint(void* dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(src_smem),
+               "r"(bytes), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -127,9 +137,15 @@ struct FitArgs {
   uint64_t score_pitch;   // elements per score row: N rounded up to even (16-byte row starts for the bulk stores)
   uint32_t bitmap_pitch;  // words per fit-bitmap row: ceil(N/32) rounded up to 32 (rows are whole 128-byte lines)
   uint32_t P, N, Npad, W;
+  // Tail balance: CTA units (PODS_PER_CTA pods x the whole node range) [0, n_full) fill whole waves of the
+  // resident CTA slots; each of the remaining units is cut into tail_split node-range pieces (whole bitmap
+  // lines), one CTA each, so that the last partial wave spreads over every SM instead of leaving most idle.
+  // Pieces combine their per-pod results with atomics (count add, packed (score+1, ~node) max).
+  uint32_t n_full, tail_split;
+  unsigned long long* best_packed;   // [P] or null (tail_split == 1)
 };
 
-// running best score of a lane: int32 on the narrow fast path (scores of fitting pairs are <= 2^28,
+// running best score of a lane: int32 on the narrow fast path (scores of fitting pairs are < 2^27,
 // "none" = -1), int64 otherwise ("none" = INT64_MIN)
 template <bool NARROW> struct BestT { using type = int64_t; };
 template <> struct BestT<true> { using type = int32_t; };
@@ -137,11 +153,14 @@ template <> struct BestT<true> { using type = int32_t; };
 // One node tile for the PODS_PER_WARP pods of a warp.
 //   narrow lanes: one 32-bit VIADDMNMX (fused subtract+min) each;
 //   scaled lanes: x = min(left' - req', C) (one VIADDMNMX: the clamp keeps x << k below 2^31), its sign
-//     joins the fit test, x << k (exact original units, or 2^28 = "cannot be the minimum") joins the min;
+//     joins the fit test, x << k (exact original units, or 2^27 = "cannot be the minimum") joins the min;
 //   wide lanes: 64-bit subtract, sign through the high word, low word when the high word is 0.
 // Ballot words go to a per-warp shared-memory slab (one STS per pair, every lane writes the same word);
 // scores go to the warp's staging slab (SCORE) as int64: fit ? m : INT64_MIN.
-template <int LW, int LN, int LS, bool SCORE>
+// OUT: what leaves the SMs besides the per-pod results — 0 nothing (decisions only: feasible counts come from a
+// predicated add, no ballot), 1 the fit bitmap, 2 the score matrix (+ the bitmap when its pointer is set).
+enum { FIT_OUT_NONE = 0, FIT_OUT_BITMAP = 1, FIT_OUT_SCORE = 2 };
+template <int LW, int LN, int LS, int OUT>
 __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restrict__ tlw,
                                          const int32_t* __restrict__ tln,
                                          const int64_t (&rqw)[PODS_PER_WARP][LW > 0 ? LW : 1],
@@ -150,12 +169,16 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
                                          uint32_t* s_words, uint32_t wbase /*tile's first word in the line*/, uint32_t node_base, uint32_t lane,
                                          int j0 /*first word of the segment*/,
                                          typename BestT<(LN > 0)>::type (&best_s)[PODS_PER_WARP],
-                                         int32_t (&best_n)[PODS_PER_WARP]) {
+                                         int32_t (&best_n)[PODS_PER_WARP], int32_t (&kb)[PODS_PER_WARP],
+                                         uint32_t (&cnt)[PODS_PER_WARP]) {
+  constexpr bool SCORE = OUT == FIT_OUT_SCORE;
+  constexpr bool WORDS = OUT != FIT_OUT_NONE;
   const int64_t* tpw = tlw + lane + j0 * 32;
   const int32_t* tpn = tln + lane + j0 * 32;
   int32_t node = (int32_t)(node_base + lane) + j0 * 32;
   uint32_t wp = smem_u32(s_words) + (wbase + j0) * 4;   // word (wbase + j) of the 32-word line being assembled
   uint32_t sp = slab + lane * 8;
+  int32_t jrem = TILE_WORDS - 1 - j0;   // best-node key: low KEY_BITS bits = TILE_WORDS-1-j (earlier node wins a tie)
 #pragma unroll 1
   for (int jb = j0; jb < j0 + SEG_WORDS; jb += 4) {
 #pragma unroll
@@ -175,9 +198,9 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
 #endif
         if (LN > 0) {
           // Narrow fast path.  t = min over the narrow lanes is a REAL difference (the narrow set
-          // holds a fixed lane) with |t| <= 2^28, and the pair's score m = min over all lanes <= t.
+          // holds a fixed lane) with |t| < 2^27, and the pair's score m = min over all lanes <= t.
           // So when the pair fits (every difference >= 0) m is a 32-bit value: the other lanes
-          // only matter through (a) their sign and (b) their value when it is below 2^28.
+          // only matter through (a) their sign and (b) their value when it is below 2^27.
           int32_t t = lfn[0] - rqn[r][0];
 #pragma unroll
           for (int d = 1; d < LN; ++d) t = min(t, lfn[d] - rqn[r][d]);
@@ -197,8 +220,12 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
             m32 = min(m32, whi != 0 ? 0xffffffffu : lo32(w));
           }
           const bool fit = (sgn >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
-          sts_u32(wp + (r * 32 + jj) * 4, __ballot_sync(0xffffffffu, fit));
-          if (fit && (int32_t)m32 > best_s[r]) { best_s[r] = (int32_t)m32; best_n[r] = node + jj * 32; }
+          if (WORDS) sts_u32(wp + (r * 32 + jj) * 4, __ballot_sync(0xffffffffu, fit));
+          else if (fit) ++cnt[r];
+          // best node of the tile as ONE running max: key = score * 2^KEY_BITS + (TILE_WORDS-1-j) < 2^31
+          // (scores of fitting pairs are < 2^27), -1 = none; decoded once per tile
+          const int32_t key = (int32_t)(m32 << KEY_BITS) + (jrem - jj);
+          if (fit) kb[r] = max(kb[r], key);
 #if BS_FIT_EXP != 2   // (experiment 2: bulk stores without the staging stores)
           if (SCORE) sts_v2u32(sp + (r * FIT_SEG + jj * 32) * 8, fit ? m32 : 0u, fit ? 0u : 0x80000000u);
 #endif
@@ -207,7 +234,8 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
 #pragma unroll
           for (int d = 1; d < LW; ++d) m = min64(m, lfw[d] - rqw[r][d]);
           const bool fit = (hi32(m) >= 0) && ((colbits[r] >> (jb + jj)) & 1u);
-          sts_u32(wp + (r * 32 + jj) * 4, __ballot_sync(0xffffffffu, fit));
+          if (WORDS) sts_u32(wp + (r * 32 + jj) * 4, __ballot_sync(0xffffffffu, fit));
+          else if (fit) ++cnt[r];
           if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
           if (SCORE) sts_u64(sp + (r * FIT_SEG + jj * 32) * 8, fit ? (long long)m : (long long)INT64_MIN);
         }
@@ -216,6 +244,7 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
     tpw += 128;
     tpn += 128;
     node += 128;
+    jrem -= 4;
     wp += 16;
     sp += 128 * 8;
   }
@@ -245,8 +274,10 @@ inline size_t gang_fit_smem_bytes(int LW, int LN, int LS, bool score) {
   return fit_smem_total(LW, LN, LS, score, fit_stages(LW, LN, LS, score));
 }
 
-template <int LW, int LN, int LS, bool SCORE>
-__global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB_NOSCORE) gang_fit_kernel(FitArgs a) {
+template <int LW, int LN, int LS, int OUT>
+__global__ void __launch_bounds__(FIT_THREADS, OUT == FIT_OUT_SCORE ? BS_FIT_MINB : BS_FIT_MINB_NOSCORE) gang_fit_kernel(FitArgs a) {
+  constexpr bool SCORE = OUT == FIT_OUT_SCORE;
+  constexpr bool WORDS = OUT != FIT_OUT_NONE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr size_t STAGE_BYTES = fit_tile_bytes(LW, LN, LS);
   constexpr int LNS = LN + LS;
@@ -262,9 +293,20 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   uint32_t* s_words = s_words_all + wid * PODS_PER_WARP * 32;   // per pod: the 32-word (1024-node) bitmap line being assembled
-  const uint32_t pod0 = blockIdx.x * PODS_PER_CTA;
+  uint32_t unit = blockIdx.x, piece = 0, npieces = 1;
+  if (blockIdx.x >= a.n_full) {
+    const uint32_t tl = blockIdx.x - a.n_full;
+    unit = a.n_full + tl / a.tail_split;
+    piece = tl % a.tail_split;
+    npieces = a.tail_split;
+  }
+  const uint32_t pod0 = unit * PODS_PER_CTA;
   const uint32_t wpod0 = pod0 + wid * PODS_PER_WARP;  // first pod of this warp
   const uint32_t n_tiles = a.Npad / NODE_TILE;
+  // this CTA's tile range: whole bitmap lines (TILES_PER_LINE tiles), split as evenly as lines allow
+  const uint32_t n_lines = (n_tiles + TILES_PER_LINE - 1) / TILES_PER_LINE;
+  const uint32_t tile_lo = min(n_tiles, (n_lines * piece / npieces) * TILES_PER_LINE);
+  const uint32_t tile_hi = min(n_tiles, (n_lines * (piece + 1) / npieces) * TILES_PER_LINE);
 
   if (tid == 0) {
     for (int st = 0; st < STAGES; ++st) {
@@ -313,8 +355,8 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
     return;
 #endif
     if (lane == 0) {
-      for (uint32_t tile = 0; tile < n_tiles; ++tile) {
-        const uint32_t st = tile % STAGES, use = tile / STAGES;
+      for (uint32_t tile = tile_lo; tile < tile_hi; ++tile) {
+        const uint32_t st = (tile - tile_lo) % STAGES, use = (tile - tile_lo) / STAGES;
         if (use > 0) mbar_wait(&s_empty[st], (use - 1) & 1);
         issue(tile, st);
       }
@@ -328,12 +370,13 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
   uint32_t cnt[PODS_PER_WARP];
   typename BestT<(LN > 0)>::type best_s[PODS_PER_WARP];
   int32_t best_n[PODS_PER_WARP];
+  int32_t kb[PODS_PER_WARP], kthr[PODS_PER_WARP];   // tile-local best key; smallest key that beats best_s
   int64_t rqw[PODS_PER_WARP][LW > 0 ? LW : 1];
   int32_t rqn[PODS_PER_WARP][LNS > 0 ? LNS : 1];
   uint32_t coff[PODS_PER_WARP];
 #pragma unroll
   for (int r = 0; r < PODS_PER_WARP; ++r) {
-    cnt[r] = 0; best_n[r] = -1;
+    cnt[r] = 0; best_n[r] = -1; kb[r] = -1; kthr[r] = 0;
     best_s[r] = LN > 0 ? (typename BestT<(LN > 0)>::type)(-1) : (typename BestT<(LN > 0)>::type)INT64_MIN;
     const uint32_t p = wpod0 + r;
     coff[r] = (p < a.P ? a.fit_class[p] : 0u) * n_tiles * 32 + lane;
@@ -344,16 +387,19 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
   }
   const uint32_t slab0 = smem_u32(smem_raw + fit_smem_front(LW, LN, LS, STAGES)) + wid * (uint32_t)(FIT_NB * fit_slab_bytes());
   int64_t* srow = SCORE ? a.score + (size_t)wpod0 * a.score_pitch : nullptr;
+#ifdef BS_FIT_L2HINT
+  const uint64_t l2pol = l2_evict_first_policy();
+#endif
 
   // Consumers: a warp releases a stage by arriving on its `empty` mbarrier and may run up to
   // STAGES-1 tiles ahead of the slowest warp.
   uint32_t stage = 0, phase = 0, sb = 0, nseg = 0;
   ColBits colnext[PODS_PER_WARP];   // class bits are fetched one tile ahead (their L2 latency stays off the tile's critical path)
 #pragma unroll
-  for (int r = 0; r < PODS_PER_WARP; ++r) colnext[r] = __ldg(a.classfit + coff[r]);
-  for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+  for (int r = 0; r < PODS_PER_WARP; ++r) colnext[r] = __ldg(a.classfit + coff[r] + min(tile_lo, n_tiles - 1) * 32);
+  for (uint32_t tile = tile_lo; tile < tile_hi; ++tile) {
     ColBits colbits[PODS_PER_WARP];
-    const uint32_t tnext = tile + 1 < n_tiles ? tile + 1 : tile;
+    const uint32_t tnext = tile + 1 < tile_hi ? tile + 1 : tile;
 #pragma unroll
     for (int r = 0; r < PODS_PER_WARP; ++r) {
       colbits[r] = colnext[r];
@@ -375,7 +421,7 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
         if (lane == 0) bulk_wait_read<FIT_NB - 1>();   // the bulk stores that last read this slab are done with it
         __syncwarp();
       }
-      fit_seg<LW, LN, LS, SCORE>(a, tlw, tln, rqw, rqn, colbits, slab, s_words, wbase, node_base, lane, sg * SEG_WORDS, best_s, best_n);
+      fit_seg<LW, LN, LS, OUT>(a, tlw, tln, rqw, rqn, colbits, slab, s_words, wbase, node_base, lane, sg * SEG_WORDS, best_s, best_n, kb, cnt);
       if (SCORE) {
         fence_async_smem();
         __syncwarp();
@@ -390,7 +436,11 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
             const uint32_t cols = min((uint32_t)FIT_SEG, (uint32_t)a.score_pitch - col0);
 #pragma unroll
             for (int r = 0; r < PODS_PER_WARP; ++r)
+#ifdef BS_FIT_L2HINT
+              tma_bulk_s2g_hint(srow + (size_t)r * a.score_pitch + col0, slab + r * (FIT_SEG * 8), cols * 8, l2pol);
+#else
               tma_bulk_s2g(srow + (size_t)r * a.score_pitch + col0, slab + r * (FIT_SEG * 8), cols * 8);
+#endif
           }
           bulk_commit();
         }
@@ -398,12 +448,25 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
         if (++sb == FIT_NB) sb = 0;
       }
     }
+    if (LN > 0) {
+      // a tile's best key beats the running best iff key >= (best_s + 1) << KEY_BITS: strictly greater score
+      // (an equal score in a later tile loses to the earlier node)
+#pragma unroll
+      for (int r = 0; r < PODS_PER_WARP; ++r) {
+        if (kb[r] >= kthr[r]) {
+          best_s[r] = kb[r] >> KEY_BITS;
+          best_n[r] = (int32_t)(node_base + lane) + (TILE_WORDS - 1 - (kb[r] & (TILE_WORDS - 1))) * 32;
+          kthr[r] = (best_s[r] + 1) << KEY_BITS;
+        }
+        kb[r] = -1;
+      }
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the stage
     // Fit bitmap: the ballot words of TILES_PER_LINE tiles make one 128-byte line per pod (the bitmap's row
     // pitch is a multiple of 32 words), written with one fully coalesced store — 4-byte pieces of unaligned rows
     // cost 0.15 ms on the bench workload (partial sectors), a full aligned line costs nothing measurable.
-    if ((tile + 1) % TILES_PER_LINE == 0 || tile + 1 == n_tiles) {
+    if (WORDS && ((tile + 1) % TILES_PER_LINE == 0 || tile + 1 == tile_hi)) {
       const uint32_t line = tile / TILES_PER_LINE;
       const uint32_t valid = (tile % TILES_PER_LINE + 1) * TILE_WORDS;   // words assembled in this line
       if (lane < valid) {
@@ -436,12 +499,33 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
     }
     const uint32_t p = wpod0 + k;
     if (p < a.P && lane == 0) {
-      a.feasible_count[p] = c;
-      a.best_node[p] = n;
-      a.best_score[p] = s;
+      if (npieces == 1) {
+        a.feasible_count[p] = c;
+        a.best_node[p] = n;
+        a.best_score[p] = s;
+      } else {
+        // a piece of a split unit: max of (score + 1) << 32 | ~node picks the highest score, then the lowest
+        // node; 0 = none (fit_unpack_kernel turns it back into best_node / best_score)
+        if (c) atomicAdd(&a.feasible_count[p], c);
+        if (n >= 0) atomicMax(&a.best_packed[p], ((unsigned long long)(uint32_t)(s + 1) << 32) | (uint32_t)(~(uint32_t)n));
+      }
     }
   }
 }
+
+// per-pod results of the split tail units: max((score + 1) << 32 | ~node) -> best_node / best_score
+static __global__ void fit_unpack_kernel(const unsigned long long* __restrict__ packed, uint32_t p0, uint32_t P,
+                                         int32_t* __restrict__ best_node, int64_t* __restrict__ best_score) {
+  const uint32_t p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const unsigned long long v = packed[p];
+  if (v == 0) { best_node[p] = -1; best_score[p] = INT64_MIN; return; }
+  best_node[p] = (int32_t)(~(uint32_t)v);
+  best_score[p] = (int64_t)(v >> 32) - 1;
+}
+#ifndef BS_FIT_TAIL_SPLIT
+#define BS_FIT_TAIL_SPLIT 8   // pieces a tail unit is cut into at most (1 = off)
+#endif
 
 }  // namespace bsk
 
@@ -451,7 +535,9 @@ __global__ void __launch_bounds__(FIT_THREADS, SCORE ? BS_FIT_MINB : BS_FIT_MINB
 //   LN 1..8 : (LW, LS) in FIT_WS_COMBOS.
 // fit_inst.cu compiles slice n (BS_FIT_SLICE): 0 = the all-wide kernels, n = 1..8 the kernels with LN = n.
 namespace bsk {
-using FitFn = cudaError_t (*)(const FitArgs&, uint32_t grid, cudaStream_t);
+// launches gang_fit_kernel over `units` CTA units (tail units split, see FitArgs); *launches gets the number of
+// kernels launched (1, or 2 with the unpack kernel)
+using FitFn = cudaError_t (*)(const FitArgs&, uint32_t units, cudaStream_t, uint32_t* launches);   // one per (shape, FIT_OUT_*)
 constexpr int FIT_MAX_LN = 8;
 constexpr int FIT_N_SLICES = FIT_MAX_LN + 1;
 struct FitWS { int lw, ls; };
@@ -465,26 +551,26 @@ inline bool fit_variant_exists(uint32_t LW, uint32_t LN, uint32_t LS) {
   return false;
 }
 // defined in fit_inst.cu (one definition per slice); nullptr when the slice does not hold the shape
-FitFn fit_lookup_slice0(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice1(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice2(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice3(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice4(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice5(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice6(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice7(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-FitFn fit_lookup_slice8(uint32_t LW, uint32_t LN, uint32_t LS, bool score);
-inline FitFn fit_lookup(uint32_t LW, uint32_t LN, uint32_t LS, bool score) {
+FitFn fit_lookup_slice0(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice1(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice2(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice3(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice4(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice5(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice6(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice7(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+FitFn fit_lookup_slice8(uint32_t LW, uint32_t LN, uint32_t LS, int out);
+inline FitFn fit_lookup(uint32_t LW, uint32_t LN, uint32_t LS, int out) {
   switch (LN) {
-    case 0: return fit_lookup_slice0(LW, LN, LS, score);
-    case 1: return fit_lookup_slice1(LW, LN, LS, score);
-    case 2: return fit_lookup_slice2(LW, LN, LS, score);
-    case 3: return fit_lookup_slice3(LW, LN, LS, score);
-    case 4: return fit_lookup_slice4(LW, LN, LS, score);
-    case 5: return fit_lookup_slice5(LW, LN, LS, score);
-    case 6: return fit_lookup_slice6(LW, LN, LS, score);
-    case 7: return fit_lookup_slice7(LW, LN, LS, score);
-    case 8: return fit_lookup_slice8(LW, LN, LS, score);
+    case 0: return fit_lookup_slice0(LW, LN, LS, out);
+    case 1: return fit_lookup_slice1(LW, LN, LS, out);
+    case 2: return fit_lookup_slice2(LW, LN, LS, out);
+    case 3: return fit_lookup_slice3(LW, LN, LS, out);
+    case 4: return fit_lookup_slice4(LW, LN, LS, out);
+    case 5: return fit_lookup_slice5(LW, LN, LS, out);
+    case 6: return fit_lookup_slice6(LW, LN, LS, out);
+    case 7: return fit_lookup_slice7(LW, LN, LS, out);
+    case 8: return fit_lookup_slice8(LW, LN, LS, out);
   }
   return nullptr;
 }

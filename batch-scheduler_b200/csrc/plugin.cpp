@@ -652,9 +652,8 @@ void BatchSchedulingPlugin::AddPermitted(const std::string& uid, int64_t now_ns)
 }
 
 int BatchSchedulingPlugin::group_index(const std::string& ns_name) const {
-  for (size_t i = 0; i < group_names_.size(); ++i)
-    if (group_names_[i] == ns_name) return (int)i;
-  return -1;
+  auto it = group_row_.find(ns_name);
+  return it == group_row_.end() ? -1 : (int)it->second;
 }
 
 Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& snapshot,
@@ -666,6 +665,7 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   for (auto it = permitted_expiry_.begin(); it != permitted_expiry_.end();) it = it->second <= now_ns ? permitted_expiry_.erase(it) : std::next(it);
   std::vector<PackGroupIn> gin;
   group_names_.clear();
+  group_row_.clear();
   for (auto& kv : groups_) {
     GroupState& gs = kv.second;
     for (auto it = gs.matched_uid_expiry.begin(); it != gs.matched_uid_expiry.end();)
@@ -674,6 +674,7 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
     if (gs.scheduled_flag) fl |= BS_GROUP_SCHEDULED;
     if (deny_expiry_.count(kv.first)) fl |= BS_GROUP_DENIED;
     gin.push_back(PackGroupIn{&gs.pg, (uint32_t)gs.matched_uid_expiry.size(), fl, gs.has_pod ? &gs.rep_pod : nullptr});
+    group_row_[kv.first] = (uint32_t)group_names_.size();
     group_names_.push_back(kv.first);
   }
   std::vector<uint8_t> pflags(pending.size(), 0);
@@ -813,7 +814,29 @@ Status BatchSchedulingPlugin::PackNodeRows(const PackedSnapshot& ctx, const std:
   return Status{};
 }
 
-Status BatchSchedulingPlugin::UpdateNodes(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed) {
+Status BatchSchedulingPlugin::Reevaluate() {
+  bs_results r{};
+  r.prefilter = prefilter_.data(); r.feasible_count = feasible_.data(); r.best_node = best_node_.data();
+  r.admit = admit_.data(); r.new_denied = new_denied_.data(); r.order = order_.data(); r.rank = rank_.data();
+  const int rc = bs_evaluate(eng_, &r);
+  if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
+  for (uint32_t g = 0; g < packed_.n_groups; ++g)
+    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns_);   // core.go:142,163
+  return Status{};
+}
+
+Status BatchSchedulingPlugin::UpdateRound(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed_nodes,
+                                          const std::vector<std::string>& changed_groups, int64_t now_ns) {
+  if (!eng_) return Status{BS_CODE_ERROR, "UpdateRound: no round has been started"};
+  now_ns_ = now_ns;
+  Status st = UpdateNodes(changed_nodes, false);
+  if (!st.ok()) return st;
+  st = UpdateGroups(changed_groups, now_ns, false);
+  if (!st.ok()) return st;
+  return Reevaluate();
+}
+
+Status BatchSchedulingPlugin::UpdateNodes(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed, bool evaluate) {
   if (!eng_) return Status{BS_CODE_ERROR, "UpdateNodes: no round has been started"};
   if (changed.empty()) return Status{};
   std::vector<const NodeInfo*> rows(changed.size());
@@ -855,14 +878,7 @@ Status BatchSchedulingPlugin::UpdateNodes(const std::vector<std::pair<uint32_t, 
     packed_.taint_mask[i] = delta.taint_mask[k]; packed_.node_flags[i] = delta.node_flags[k];
   }
   // the round's decisions follow the new snapshot: same pods, same groups, same result vectors
-  bs_results r{};
-  r.prefilter = prefilter_.data(); r.feasible_count = feasible_.data(); r.best_node = best_node_.data();
-  r.admit = admit_.data(); r.new_denied = new_denied_.data(); r.order = order_.data(); r.rank = rank_.data();
-  const int rc2 = bs_evaluate(eng_, &r);
-  if (rc2) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc2) + " (" + bs_last_error(eng_) + ")"};
-  for (uint32_t g = 0; g < packed_.n_groups; ++g)
-    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns_);   // core.go:142,163
-  return Status{};
+  return evaluate ? Reevaluate() : Status{};
 }
 
 Status BatchSchedulingPlugin::PackGroupRows(const PackedSnapshot& ctx, const std::vector<GroupDelta>& rows,
@@ -932,7 +948,7 @@ Status BatchSchedulingPlugin::PackGroupRows(const PackedSnapshot& ctx, const std
   return Status{};
 }
 
-Status BatchSchedulingPlugin::UpdateGroups(const std::vector<std::string>& ns_names, int64_t now_ns) {
+Status BatchSchedulingPlugin::UpdateGroups(const std::vector<std::string>& ns_names, int64_t now_ns, bool evaluate) {
   if (!eng_) return Status{BS_CODE_ERROR, "UpdateGroups: no round has been started"};
   if (ns_names.empty()) return Status{};
   now_ns_ = now_ns;
@@ -976,14 +992,7 @@ Status BatchSchedulingPlugin::UpdateGroups(const std::vector<std::string>& ns_na
   }
   if ((rc = bs_set_wait_time(eng_, max_schedule_time_ns_, packed_.wait_ns.data(), G)))
     return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
-  bs_results r{};
-  r.prefilter = prefilter_.data(); r.feasible_count = feasible_.data(); r.best_node = best_node_.data();
-  r.admit = admit_.data(); r.new_denied = new_denied_.data(); r.order = order_.data(); r.rank = rank_.data();
-  if ((rc = bs_evaluate(eng_, &r)))
-    return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
-  for (uint32_t g = 0; g < G; ++g)
-    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns_);   // core.go:142,163
-  return Status{};
+  return evaluate ? Reevaluate() : Status{};
 }
 
 Status BatchSchedulingPlugin::ReplayQueue(std::vector<ReplayDecision>* out) {

@@ -217,7 +217,11 @@ class BatchSchedulingPlugin {
   // table (bs_update_nodes); `changed` pairs the snapshot index with the new NodeInfo.
   static Status PackNodeRows(const PackedSnapshot& ctx, const std::vector<const NodeInfo*>& rows, PackedSnapshot* out,
                              bool* needs_full);
-  Status UpdateNodes(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed);
+  Status UpdateNodes(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed, bool evaluate = true);
+  // one delta round: the informer's changed NodeInfos and PodGroups scattered into the resident tables, then
+  // ONE re-evaluation (UpdateNodes / UpdateGroups with evaluate = false, then the round)
+  Status UpdateRound(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed_nodes,
+                     const std::vector<std::string>& changed_groups, int64_t now_ns);
   // The same for PodGroup state (cache.go:52-67): one changed group = its table index, the object, the
   // unexpired matched count, the SCHEDULED / HAS_POD / DENIED flags and the representative pod (or null).
   // Names are immutable, so the bare-name rank is taken over from `ctx`.  needs_full: MinResources or the
@@ -233,7 +237,7 @@ class BatchSchedulingPlugin {
                               PackedSnapshot* out, bool* needs_full);
   // re-derives the named groups ("namespace/name") from the plugin's caches and scatters their rows
   // into the resident device table (bs_update_groups), then re-evaluates the round
-  Status UpdateGroups(const std::vector<std::string>& ns_names, int64_t now_ns);
+  Status UpdateGroups(const std::vector<std::string>& ns_names, int64_t now_ns, bool evaluate = true);
 
   // the packer alone (no GPU): objects -> tables
   static Status Pack(const std::vector<const NodeInfo*>& snapshot, const std::vector<const Pod*>& pending,
@@ -264,11 +268,13 @@ class BatchSchedulingPlugin {
   std::unordered_map<std::string, uint32_t> pod_row_;               // uid -> pending index
   std::unordered_map<std::string, uint32_t> node_row_;              // node name -> snapshot index
   std::vector<std::string> group_names_;                            // table index -> "ns/name"
+  std::unordered_map<std::string, uint32_t> group_row_;             // "ns/name" -> table index
   std::vector<uint8_t> prefilter_, admit_, new_denied_;
   std::vector<uint32_t> order_, rank_, feasible_;
   std::vector<int32_t> best_node_;
   int64_t now_ns_ = 0;
   double last_pack_ms_ = 0, last_device_ms_ = 0;
+  Status Reevaluate();   // bs_evaluate into the round's result vectors + the deny side effect (core.go:142,163)
 };
 
 }  // namespace bsched

@@ -99,17 +99,16 @@ int main(int argc, char** argv) {
       names.push_back(groups[g].ns + "/" + groups[g].name);
     }
     const double t0 = now_ms();
-    Status s1 = plugin.UpdateNodes(changed);
-    Status s2 = plugin.UpdateGroups(names, now);
+    Status s1 = plugin.UpdateRound(changed, names, now);
     const double t1 = now_ms();
-    if (!s1.ok() || !s2.ok()) { fprintf(stderr, "delta: %s %s\n", s1.message.c_str(), s2.message.c_str()); return 1; }
+    if (!s1.ok()) { fprintf(stderr, "delta: %s\n", s1.message.c_str()); return 1; }
     if (it >= 2) delta += t1 - t0;
     now += 100000000ll;
   }
   printf("{\"nodes\": %d, \"pods\": %d, \"groups\": %d, \"lanes\": %u, \"full_round_ms\": %.3f, \"pack_ms\": %.3f, "
          "\"upload_evaluate_fetch_ms\": %.3f, \"delta_round_ms\": %.3f, \"delta_nodes\": %d, \"delta_groups\": %d, "
          "\"iters\": %d, \"what\": \"BatchSchedulingPlugin::BeginRound from NodeInfo/Pod/PodGroup objects (packer included); "
-         "delta = UpdateNodes + UpdateGroups for 1%% changed rows, each followed by a re-evaluation and fetch\"}\n",
+         "delta = UpdateRound: 1%% changed NodeInfos and PodGroups re-packed and scattered into the resident tables, one re-evaluation, fetch\"}\n",
          N, P, G, plugin.packed().lanes, full / iters, pack / iters, dev / iters, delta / iters, dn, dg, iters);
   return 0;
 }
