@@ -96,6 +96,20 @@ SYMBOLS = {
     "bs_permit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(PermitResultC)]),
     "bs_less": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "bs_filter": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(StatusC)]),
+    "bs_state_reset": (C.c_int, [C.c_void_p]),
+    "bs_state_remap": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "bs_state_view": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "bs_permitted_view": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "bs_state_move": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bs_set_pod_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bs_begin_cycle": (C.c_int, [C.c_void_p, C.c_int64]),
+    "bs_permit_at": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int64, _p(PermitResultC)]),
+    "bs_expire": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, _p(C.c_uint32), C.c_void_p, C.c_uint32,
+                            _p(C.c_uint32)]),
+    "bs_allow_list": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, _p(C.c_uint32)]),
+    "bs_deny": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int64]),
+    "bs_mark_permitted": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64]),
+    "bs_group_state": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int64, _p(C.c_uint32), _p(C.c_int32), _p(C.c_int32)]),
     "bs_format_message": (C.c_int, [_p(StatusC), C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "bs_node_left": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
     "bs_replay": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, _p(ReplayResultC)]),

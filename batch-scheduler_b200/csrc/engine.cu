@@ -23,6 +23,7 @@
 
 #include "kernels.cuh"
 #include "fit.cuh"
+#include "gang_state.hpp"
 #include "sort.cuh"
 #include "replay.cuh"
 
@@ -247,6 +248,13 @@ struct bs_engine {
   DevBuf d_aff_bits;
   uint32_t n_aff = 0;
   std::vector<uint32_t> h_gaff;   // affinity class of each group's representative pod
+  // gang state: the reference's TTL tables around Permit, see gang_state.hpp
+  GangState gang;
+  std::vector<uint32_t> h_min_member, h_scheduled, h_matched_up;   // group columns as uploaded
+  std::vector<uint8_t> h_gflags_up;
+  std::vector<uint64_t> h_pod_uid, h_pod_name;                     // bs_set_pod_ids
+  int64_t cycle_now_ns = 0;
+  bool gang_applied = false;     // the round's new_denied have been added to the deny table
   uint32_t n_fit_classes = 0, n_rep_classes = 0;
   // effective group state + round scratch
   DevBuf d_eflags, d_emin_res, d_emrpres, d_erep_class, d_first_pod, d_in_round, d_contrib, d_done, d_okA;
@@ -1025,6 +1033,7 @@ int evaluate_async_locked(bs_engine* e) {
   CK(cudaGetLastError());
   e->evaluated = true;
   e->fetched = false;
+  e->gang_applied = false;
   return BS_OK;
 }
 
@@ -1038,6 +1047,13 @@ int fetch_locked(bs_engine* e, bs_results* out) {
     e->fetched = true;
   }
   const RoundState* st = e->h_state.as<RoundState>();
+  if (e->gang.active && e->gang.groups.size() == G && !e->gang_applied) {
+    // AddToDenyCache for every group a pod of the round hit "cluster resource not enough" in (core.go:142,163)
+    const uint8_t* nd = e->h_new_denied.as<uint8_t>();
+    for (uint32_t g = 0; g < G; ++g)
+      if (nd[g]) e->gang.deny(g, e->cycle_now_ns);
+    e->gang_applied = true;
+  }
   if (out) {
     auto cp = [](void* dst, const PinBuf& src, size_t bytes) {
       if (dst && bytes) memcpy(dst, src.p, bytes);
@@ -1357,6 +1373,10 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   }
   if (e->h_wait_ns.size() != G) e->h_wait_ns.assign(G, -1);
   CK(cudaStreamSynchronize(e->s));   // the caller's arrays are free again once we return
+  e->h_min_member.assign(t->min_member, t->min_member + G);
+  e->h_scheduled.assign(t->scheduled, t->scheduled + G);
+  e->h_matched_up.assign(t->matched, t->matched + G);
+  e->h_gflags_up.assign(t->flags, t->flags + G);
   e->G = G;
   e->have_groups = true;
   e->evaluated = false;
@@ -1417,6 +1437,10 @@ int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t)
     e->h_gsel[idx[k]] = t->rep_sel[k];
     e->h_gtol[idx[k]] = t->rep_tol[k];
     e->h_gaff[idx[k]] = t->rep_aff_class ? t->rep_aff_class[k] : BS_AFF_NONE;
+    e->h_min_member[idx[k]] = t->min_member[k];
+    e->h_scheduled[idx[k]] = t->scheduled[k];
+    e->h_matched_up[idx[k]] = t->matched[k];
+    e->h_gflags_up[idx[k]] = t->flags[k];
   }
   e->vary_creation = e->g_or1 ^ e->g_and1;
   e->vary_name = e->g_or0 ^ e->g_and0;
@@ -1582,6 +1606,187 @@ int bs_upload_affinity(bs_engine* e, uint32_t n_classes, const uint32_t* bits) {
   e->nodes_dirty = true;     // class-fit bits and cluster scans follow the table
   e->classes_dirty = true;   // class ids are validated against it
   e->evaluated = false;
+  return BS_OK;
+}
+
+// ---- gang state: the TTL tables around Permit as engine state (gang_state.hpp) ----
+int bs_state_reset(bs_engine* e) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_groups) return fail(e, BS_E_STATE, "bs_state_reset: upload groups first");
+  e->gang.reset(e->G);
+  return BS_OK;
+}
+
+int bs_state_remap(bs_engine* e, uint32_t n_groups, const int32_t* old_index) {
+  if (!e || (n_groups && !old_index)) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->gang.remap(n_groups, old_index);
+  return BS_OK;
+}
+
+int bs_state_view(bs_engine* e, int64_t now_ns, uint32_t n_groups, uint32_t* matched, uint8_t* flags) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->gang.active || e->gang.groups.size() != n_groups) return fail(e, BS_E_STATE, "bs_state_view: tables of another shape");
+  for (uint32_t g = 0; g < n_groups; ++g) {
+    if (matched) matched[g] = e->gang.matched_count(g, now_ns);
+    if (flags) flags[g] = (uint8_t)((e->gang.groups[g].scheduled ? BS_GROUP_SCHEDULED : 0u) | (e->gang.denied(g, now_ns) ? BS_GROUP_DENIED : 0u));
+  }
+  return BS_OK;
+}
+
+int bs_permitted_view(bs_engine* e, int64_t now_ns, const uint64_t* uids, uint32_t n, uint8_t* out) {
+  if (!e || (n && (!uids || !out))) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  for (uint32_t i = 0; i < n; ++i) out[i] = e->gang.active && e->gang.permitted_recently(uids[i], now_ns) ? 1 : 0;
+  return BS_OK;
+}
+
+int bs_state_move(bs_engine* dst, bs_engine* src) {
+  if (!dst || !src || dst == src) return BS_E_INVAL;
+  std::lock_guard<std::mutex> l1(src->mu);
+  std::lock_guard<std::mutex> l2(dst->mu);
+  dst->gang = std::move(src->gang);
+  src->gang = GangState();
+  return BS_OK;
+}
+
+int bs_set_pod_ids(bs_engine* e, const uint64_t* uid, const uint64_t* name_id) {
+  if (!e || !uid || !name_id) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_pods) return fail(e, BS_E_STATE, "bs_set_pod_ids: upload pods first");
+  e->h_pod_uid.assign(uid, uid + e->P);
+  e->h_pod_name.assign(name_id, name_id + e->P);
+  return BS_OK;
+}
+
+int bs_begin_cycle(bs_engine* e, int64_t now_ns) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_groups || !e->have_pods) return fail(e, BS_E_STATE, "bs_begin_cycle: upload groups and pods first");
+  if (!e->gang.active || e->gang.groups.size() != e->G) return fail(e, BS_E_STATE, "bs_begin_cycle: bs_state_reset after the group table changed size");
+  BS_DEVICE_GUARD(e);
+  const uint32_t G = e->G, P = e->P;
+  e->cycle_now_ns = now_ns;
+  // the go-cache views at `now` become the columns the round reads: len(MatchedPodNodes.Items()), pgs.Scheduled,
+  // lastDeniedPG and lastPermittedPod membership (core.go:95-110,706,711)
+  std::vector<uint32_t> matched(G);
+  std::vector<uint8_t> gfl(G), pfl(P);
+  for (uint32_t g = 0; g < G; ++g) {
+    matched[g] = e->gang.matched_count(g, now_ns);
+    uint8_t f = e->h_gflags_up[g] & ~(uint8_t)(BS_GROUP_SCHEDULED | BS_GROUP_DENIED);
+    if (e->gang.groups[g].scheduled) f |= BS_GROUP_SCHEDULED;
+    if (e->gang.denied(g, now_ns)) f |= BS_GROUP_DENIED;
+    gfl[g] = f;
+  }
+  const bool ids = e->h_pod_uid.size() == P;
+  for (uint32_t p = 0; p < P; ++p) {
+    uint8_t f = e->h_pflags[p] & ~(uint8_t)BS_POD_PERMITTED_RECENTLY;
+    if (ids && e->gang.permitted_recently(e->h_pod_uid[p], now_ns)) f |= BS_POD_PERMITTED_RECENTLY;
+    pfl[p] = f;
+  }
+  if (G) {
+    CK(cudaMemcpyAsync(e->d_matched.p, matched.data(), (size_t)G * 4, cudaMemcpyHostToDevice, e->s));
+    CK(cudaMemcpyAsync(e->d_gflags.p, gfl.data(), G, cudaMemcpyHostToDevice, e->s));
+  }
+  if (P) CK(cudaMemcpyAsync(e->d_pflags.p, pfl.data(), P, cudaMemcpyHostToDevice, e->s));
+  CK(cudaStreamSynchronize(e->s));
+  e->evaluated = false;
+  return BS_OK;
+}
+
+int bs_permit_at(bs_engine* e, uint32_t pod, uint32_t node, int64_t now_ns, bs_permit_result* r) {
+  if (!e || !r) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->have_pods || !e->have_groups) return fail(e, BS_E_STATE, "bs_permit_at: upload groups and pods first");
+  if (pod >= e->P || (e->have_nodes && node >= e->N)) return BS_E_INDEX;
+  const int64_t kSecond = 1000000000ll, kDefaultWait = 60 * kSecond;  // util.DefaultWaitTime k8s.go:31
+  const int32_t g = e->h_gid[pod];
+  memset(r, 0, sizeof(*r));
+  r->group = -1;
+  if (g == BS_GID_NONE) {  // core.go:270-272 + batchscheduler.go:190-193
+    r->ready = 1; r->code = BS_CODE_SUCCESS; r->wait_ns = 0;
+    return BS_OK;
+  }
+  if (g < 0 || (uint32_t)g >= e->G) {  // core.go:275-277 + batchscheduler.go:194-195
+    r->ready = 0; r->code = BS_CODE_UNSCHEDULABLE; r->wait_ns = kDefaultWait;
+    return BS_OK;
+  }
+  if (!e->gang.active || e->gang.groups.size() != e->G || e->h_pod_uid.size() != e->P)
+    return fail(e, BS_E_STATE, "bs_permit_at: bs_state_reset and bs_set_pod_ids first");
+  r->group = g;
+  int64_t wait = e->default_wait_ns;   // util.GetWaitTimeDuration (k8s.go:82-91)
+  if ((size_t)g < e->h_wait_ns.size() && e->h_wait_ns[g] >= 0) wait = e->h_wait_ns[g];
+  const bool ready = e->gang.permit((uint32_t)g, e->h_pod_uid[pod], e->h_pod_name[pod], node, now_ns, wait,
+                                    e->h_min_member[g], e->h_scheduled[g]);   // core.go:283-307
+  r->wait_ns = wait + kSecond;           // batchscheduler.go:180-182
+  r->ready = ready ? 1 : 0;
+  r->start_signal = r->ready;            // :197-199
+  r->code = BS_CODE_WAIT;                // :184-187 and :201
+  return BS_OK;
+}
+
+int bs_expire(bs_engine* e, int64_t now_ns, uint32_t* rej_group, uint64_t* rej_uid, uint32_t rej_cap, uint32_t* n_rejected,
+              uint32_t* evicted_group, uint32_t evict_cap, uint32_t* n_evicted) {
+  if (!e || !n_rejected || !n_evicted) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->gang.active) return fail(e, BS_E_STATE, "bs_expire: bs_state_reset first");
+  std::vector<uint32_t> rg, ev;
+  std::vector<uint64_t> ru;
+  e->gang.expire(now_ns, &rg, &ru, &ev);
+  *n_rejected = (uint32_t)rg.size();
+  *n_evicted = (uint32_t)ev.size();
+  for (uint32_t i = 0; i < rg.size() && i < rej_cap; ++i) {
+    if (rej_group) rej_group[i] = rg[i];
+    if (rej_uid) rej_uid[i] = ru[i];
+  }
+  for (uint32_t i = 0; i < ev.size() && i < evict_cap; ++i)
+    if (evicted_group) evicted_group[i] = ev[i];
+  return BS_OK;
+}
+
+int bs_allow_list(bs_engine* e, uint32_t group, int64_t now_ns, uint64_t* uids, uint32_t* nodes, uint32_t cap, uint32_t* n) {
+  if (!e || !n) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->gang.active || e->gang.groups.size() != e->G) return fail(e, BS_E_STATE, "bs_allow_list: bs_state_reset first");
+  if (group >= e->G) return BS_E_INDEX;
+  std::vector<uint64_t> u;
+  std::vector<uint32_t> nd;
+  e->gang.allow_list(group, now_ns, e->h_min_member[group], e->h_scheduled[group], &u, &nd);
+  *n = (uint32_t)u.size();
+  for (uint32_t i = 0; i < u.size() && i < cap; ++i) {
+    if (uids) uids[i] = u[i];
+    if (nodes) nodes[i] = nd[i];
+  }
+  return BS_OK;
+}
+
+int bs_deny(bs_engine* e, uint32_t group, int64_t now_ns) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->gang.active || e->gang.groups.size() != e->G) return fail(e, BS_E_STATE, "bs_deny: bs_state_reset first");
+  if (group >= e->G) return BS_E_INDEX;
+  e->gang.deny(group, now_ns);
+  return BS_OK;
+}
+
+int bs_mark_permitted(bs_engine* e, uint64_t uid, int64_t now_ns) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->gang.active) return fail(e, BS_E_STATE, "bs_mark_permitted: bs_state_reset first");
+  e->gang.mark_permitted(uid, now_ns);
+  return BS_OK;
+}
+
+int bs_group_state(bs_engine* e, uint32_t group, int64_t now_ns, uint32_t* matched, int32_t* scheduled_flag, int32_t* denied) {
+  if (!e) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->gang.active || e->gang.groups.size() != e->G) return fail(e, BS_E_STATE, "bs_group_state: bs_state_reset first");
+  if (group >= e->G) return BS_E_INDEX;
+  if (matched) *matched = e->gang.matched_count(group, now_ns);
+  if (scheduled_flag) *scheduled_flag = e->gang.groups[group].scheduled ? 1 : 0;
+  if (denied) *denied = e->gang.denied(group, now_ns) ? 1 : 0;
   return BS_OK;
 }
 

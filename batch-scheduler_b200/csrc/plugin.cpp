@@ -633,22 +633,69 @@ BatchSchedulingPlugin::~BatchSchedulingPlugin() {
 }
 
 void BatchSchedulingPlugin::SetPodGroup(const PodGroup& pg) {
+  std::lock_guard<std::mutex> lk(mu_);
   GroupState& gs = groups_[pg.ns + "/" + pg.name];
   gs.pg = pg;
 }
 
-void BatchSchedulingPlugin::DeletePodGroup(const std::string& ns_name) { groups_.erase(ns_name); }
+void BatchSchedulingPlugin::DeletePodGroup(const std::string& ns_name) {
+  std::lock_guard<std::mutex> lk(mu_);
+  groups_.erase(ns_name);
+}
+
+uint64_t BatchSchedulingPlugin::IdOf(const std::string& s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
 
 void BatchSchedulingPlugin::AddToDenyCache(const std::string& ns_name, int64_t now_ns) {
-  auto it = deny_expiry_.find(ns_name);
-  if (it != deny_expiry_.end() && it->second > now_ns) return;  // go-cache Add: no-op while present (Q11)
-  deny_expiry_[ns_name] = now_ns + 20 * kSecond;                 // core.go:424
+  const int g = group_index(ns_name);
+  if (eng_ && g >= 0) bs_deny(eng_, (uint32_t)g, now_ns);          // lastDeniedPG.Add(.., 20 s)  core.go:424 (Add: Q11)
+  else pending_deny_.push_back({ns_name, now_ns});
 }
 
 void BatchSchedulingPlugin::AddPermitted(const std::string& uid, int64_t now_ns) {
-  auto it = permitted_expiry_.find(uid);
-  if (it != permitted_expiry_.end() && it->second > now_ns) return;
-  permitted_expiry_[uid] = now_ns + 2 * kSecond;                 // core.go:188
+  if (eng_) bs_mark_permitted(eng_, IdOf(uid), now_ns);           // core.go:188
+  else pending_permitted_.push_back({uid, now_ns});
+}
+
+Status BatchSchedulingPlugin::Tick(int64_t now_ns, std::vector<std::string>* rejected_uids,
+                                   std::vector<std::string>* evicted_groups) {
+  if (!eng_) return Status{};
+  std::lock_guard<std::mutex> lk(mu_);
+  const uint32_t cap = (uint32_t)uid_of_id_.size() + 1, G = (uint32_t)group_names_.size();
+  std::vector<uint32_t> rg(cap), ev(G + 1);
+  std::vector<uint64_t> ru(cap);
+  uint32_t nr = 0, ne = 0;
+  const int rc = bs_expire(eng_, now_ns, rg.data(), ru.data(), cap, &nr, ev.data(), G + 1, &ne);
+  if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+  for (uint32_t i = 0; i < nr && i < cap; ++i) {
+    auto it = uid_of_id_.find(ru[i]);
+    if (rejected_uids && it != uid_of_id_.end()) rejected_uids->push_back(it->second);
+  }
+  for (uint32_t i = 0; i < ne && i < G + 1; ++i)
+    if (evicted_groups && ev[i] < G) evicted_groups->push_back(group_names_[ev[i]]);
+  return Status{};
+}
+
+Status BatchSchedulingPlugin::AllowList(const std::string& ns_name, int64_t now_ns,
+                                        std::vector<std::pair<std::string, std::string>>* allow) {
+  if (!eng_ || !allow) return Status{BS_CODE_ERROR, "AllowList: no round has been started"};
+  std::lock_guard<std::mutex> lk(mu_);
+  const int g = group_index(ns_name);
+  if (g < 0) return Status{BS_CODE_ERROR, "AllowList: unknown group"};
+  const uint32_t cap = (uint32_t)uid_of_id_.size() + 1;
+  std::vector<uint64_t> u(cap);
+  std::vector<uint32_t> nd(cap);
+  uint32_t n = 0;
+  const int rc = bs_allow_list(eng_, (uint32_t)g, now_ns, u.data(), nd.data(), cap, &n);
+  if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+  for (uint32_t i = 0; i < n && i < cap; ++i) {
+    auto it = uid_of_id_.find(u[i]);
+    allow->push_back({it != uid_of_id_.end() ? it->second : std::string(), nd[i] < node_names_.size() ? node_names_[nd[i]] : std::string()});
+  }
+  return Status{};
 }
 
 int BatchSchedulingPlugin::group_index(const std::string& ns_name) const {
@@ -659,33 +706,63 @@ int BatchSchedulingPlugin::group_index(const std::string& ns_name) const {
 Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& snapshot,
                                          const std::vector<const Pod*>& pending, int64_t now_ns) {
   const double t0 = now_ms();
+  std::lock_guard<std::mutex> lk(mu_);
   now_ns_ = now_ns;
-  // TTL expiry (go-cache semantics: an entry is gone once now >= expiry)
-  for (auto it = deny_expiry_.begin(); it != deny_expiry_.end();) it = it->second <= now_ns ? deny_expiry_.erase(it) : std::next(it);
-  for (auto it = permitted_expiry_.begin(); it != permitted_expiry_.end();) it = it->second <= now_ns ? permitted_expiry_.erase(it) : std::next(it);
-  std::vector<PackGroupIn> gin;
-  group_names_.clear();
-  group_row_.clear();
+  // the group table of this round (canonical order = the map's) and how it continues the last one's rows
+  std::vector<std::string> names;
+  std::vector<int32_t> old_index;
+  names.reserve(groups_.size());
+  bool same = group_names_.size() == groups_.size();
   for (auto& kv : groups_) {
-    GroupState& gs = kv.second;
-    for (auto it = gs.matched_uid_expiry.begin(); it != gs.matched_uid_expiry.end();)
-      it = it->second <= now_ns ? gs.matched_uid_expiry.erase(it) : std::next(it);
-    uint8_t fl = 0;
-    if (gs.scheduled_flag) fl |= BS_GROUP_SCHEDULED;
-    if (deny_expiry_.count(kv.first)) fl |= BS_GROUP_DENIED;
-    gin.push_back(PackGroupIn{&gs.pg, (uint32_t)gs.matched_uid_expiry.size(), fl, gs.has_pod ? &gs.rep_pod : nullptr});
-    group_row_[kv.first] = (uint32_t)group_names_.size();
-    group_names_.push_back(kv.first);
+    auto it = group_row_.find(kv.first);
+    old_index.push_back(it == group_row_.end() ? -1 : (int32_t)it->second);
+    same = same && old_index.back() == (int32_t)names.size();
+    names.push_back(kv.first);
+  }
+  const uint32_t Gn = (uint32_t)names.size();
+  if (eng_ && state_ready_ && !same) {
+    const int rc = bs_state_remap(eng_, Gn, old_index.data());
+    if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+  }
+  // the engine's TTL tables as of now: matched counts, pgs.Scheduled, deny list, recently permitted uids
+  std::vector<uint32_t> st_matched(Gn, 0);
+  std::vector<uint8_t> st_flags(Gn, 0);
+  if (eng_ && state_ready_ && Gn) {
+    const int rc = bs_state_view(eng_, now_ns, Gn, st_matched.data(), st_flags.data());
+    if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+  }
+  std::vector<PackGroupIn> gin;
+  group_names_ = names;
+  group_row_.clear();
+  {
+    uint32_t g = 0;
+    for (auto& kv : groups_) {
+      GroupState& gs = kv.second;
+      gin.push_back(PackGroupIn{&gs.pg, st_matched[g], st_flags[g], gs.has_pod ? &gs.rep_pod : nullptr});
+      group_row_[kv.first] = g++;
+    }
   }
   std::vector<uint8_t> pflags(pending.size(), 0);
+  std::vector<uint64_t> uid_ids(pending.size()), name_ids(pending.size());
   pod_row_.clear();
   for (size_t i = 0; i < pending.size(); ++i) {
     pod_row_[pending[i]->uid] = (uint32_t)i;
-    if (permitted_expiry_.count(pending[i]->uid)) pflags[i] |= BS_POD_PERMITTED_RECENTLY;
+    uid_ids[i] = IdOf(pending[i]->uid);
+    name_ids[i] = IdOf(pending[i]->ns + "/" + pending[i]->name);
+  }
+  if (eng_ && state_ready_ && !pending.empty()) {
+    std::vector<uint8_t> perm(pending.size());
+    bs_permitted_view(eng_, now_ns, uid_ids.data(), (uint32_t)pending.size(), perm.data());
+    for (size_t i = 0; i < pending.size(); ++i)
+      if (perm[i]) pflags[i] |= BS_POD_PERMITTED_RECENTLY;
   }
   node_row_.clear();
+  node_names_.assign(snapshot.size(), std::string());
   for (size_t i = 0; i < snapshot.size(); ++i)
-    if (snapshot[i] && snapshot[i]->node) node_row_[snapshot[i]->node->name] = (uint32_t)i;
+    if (snapshot[i] && snapshot[i]->node) {
+      node_row_[snapshot[i]->node->name] = (uint32_t)i;
+      node_names_[i] = snapshot[i]->node->name;
+    }
   Status st = pack_impl(snapshot, pending, gin, pflags, max_schedule_time_ns_, &packed_);
   if (!st.ok()) return st;
   last_pack_ms_ = now_ms() - t0;
@@ -696,11 +773,14 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
     if (eng_) s.message += std::string(" (") + bs_last_error(eng_) + ")";
     return s;
   };
-  if (eng_ && eng_lanes_ != packed_.lanes) { bs_destroy(eng_); eng_ = nullptr; }
-  if (!eng_) {
+  if (!eng_ || eng_lanes_ != packed_.lanes) {
+    // a new scalar resource changed the lane count: a fresh engine takes over the gang state of the old one
+    bs_engine* fresh = nullptr;
     bs_config cfg{device_, packed_.lanes, out_flags_, 0};
-    int rc = bs_create(&cfg, &eng_);
-    if (rc) { eng_ = nullptr; return fail(rc); }
+    int rc = bs_create(&cfg, &fresh);
+    if (rc) return fail(rc);
+    if (eng_) { bs_state_move(fresh, eng_); bs_destroy(eng_); }
+    eng_ = fresh;
     eng_lanes_ = packed_.lanes;
   }
   bs_node_table nt = packed_.node_table();
@@ -712,6 +792,16 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   if ((rc = bs_upload_groups(eng_, &gt))) return fail(rc);
   if ((rc = bs_upload_pods(eng_, &pt))) return fail(rc);
   if ((rc = bs_set_wait_time(eng_, max_schedule_time_ns_, packed_.wait_ns.data(), packed_.n_groups))) return fail(rc);
+  if (!state_ready_) {
+    if ((rc = bs_state_reset(eng_))) return fail(rc);
+    state_ready_ = true;
+  }
+  for (auto& d : pending_deny_) { const int g = group_index(d.first); if (g >= 0) bs_deny(eng_, (uint32_t)g, d.second); }
+  for (auto& d : pending_permitted_) bs_mark_permitted(eng_, IdOf(d.first), d.second);
+  pending_deny_.clear();
+  pending_permitted_.clear();
+  if ((rc = bs_set_pod_ids(eng_, uid_ids.data(), name_ids.data()))) return fail(rc);
+  if ((rc = bs_begin_cycle(eng_, now_ns))) return fail(rc);   // the round reads the engine's own tables
   const uint32_t P = packed_.n_pods, G = packed_.n_groups;
   prefilter_.assign(P, 0); feasible_.assign(P, 0); best_node_.assign(P, -1); order_.assign(P, 0); rank_.assign(P, 0);
   admit_.assign(G, 0); new_denied_.assign(G, 0);
@@ -724,8 +814,8 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   // side effects the reference performs while it walks the pods:
   //  * AddToDenyCache for every group refused with "cluster resource not enough" (core.go:142,163)
   //  * fillOccupiedObj: first reaching pod becomes pgs.Pod, supplies MinResources / OccupiedBy
-  for (uint32_t g = 0; g < G; ++g)
-    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns);
+  // (AddToDenyCache for the groups refused with "cluster resource not enough", core.go:142,163, happened inside
+  //  the engine when the round was fetched)
   for (uint32_t i = 0; i < P; ++i) {
     const int32_t g = packed_.gid[i];
     if (g < 0) continue;
@@ -818,11 +908,10 @@ Status BatchSchedulingPlugin::Reevaluate() {
   bs_results r{};
   r.prefilter = prefilter_.data(); r.feasible_count = feasible_.data(); r.best_node = best_node_.data();
   r.admit = admit_.data(); r.new_denied = new_denied_.data(); r.order = order_.data(); r.rank = rank_.data();
-  const int rc = bs_evaluate(eng_, &r);
+  int rc = bs_begin_cycle(eng_, now_ns_);   // matched / flags columns follow the engine's tables at now
+  if (!rc) rc = bs_evaluate(eng_, &r);
   if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc) + " (" + bs_last_error(eng_) + ")"};
-  for (uint32_t g = 0; g < packed_.n_groups; ++g)
-    if (new_denied_[g]) AddToDenyCache(group_names_[g], now_ns_);   // core.go:142,163
-  return Status{};
+  return Status{};   // (new_denied groups were deny-listed by the engine's fetch, core.go:142,163)
 }
 
 Status BatchSchedulingPlugin::UpdateRound(const std::vector<std::pair<uint32_t, const NodeInfo*>>& changed_nodes,
@@ -959,14 +1048,14 @@ Status BatchSchedulingPlugin::UpdateGroups(const std::vector<std::string>& ns_na
     auto it = groups_.find(name);
     if (gi < 0 || it == groups_.end()) return Status{BS_CODE_ERROR, "UpdateGroups: " + name + " is not part of the round (full repack needed)"};
     GroupState& gs = it->second;
-    for (auto m = gs.matched_uid_expiry.begin(); m != gs.matched_uid_expiry.end();)
-      m = m->second <= now_ns ? gs.matched_uid_expiry.erase(m) : std::next(m);
-    auto de = deny_expiry_.find(name);
+    uint32_t matched = 0;
+    int32_t sched = 0, den = 0;
+    bs_group_state(eng_, (uint32_t)gi, now_ns, &matched, &sched, &den);
     uint8_t fl = 0;
-    if (gs.scheduled_flag) fl |= BS_GROUP_SCHEDULED;
-    if (de != deny_expiry_.end() && de->second > now_ns) fl |= BS_GROUP_DENIED;
+    if (sched) fl |= BS_GROUP_SCHEDULED;
+    if (den) fl |= BS_GROUP_DENIED;
     GroupDelta gd;
-    gd.index = (uint32_t)gi; gd.pg = &gs.pg; gd.matched = (uint32_t)gs.matched_uid_expiry.size(); gd.flags = fl;
+    gd.index = (uint32_t)gi; gd.pg = &gs.pg; gd.matched = matched; gd.flags = fl;
     gd.rep_pod = gs.has_pod ? &gs.rep_pod : nullptr;
     rows.push_back(gd);
     idx.push_back((uint32_t)gi);
@@ -1029,12 +1118,18 @@ Status BatchSchedulingPlugin::PreFilter(const Pod& pod) {
 std::pair<Status, int64_t> BatchSchedulingPlugin::Permit(const Pod& pod, const std::string& node_name,
                                                          bool* start_signal) {
   if (start_signal) *start_signal = false;
-  auto it = pod_row_.find(pod.uid);
-  auto nt = node_row_.find(node_name);
-  if (it == pod_row_.end() || nt == node_row_.end())
-    return {Status{BS_CODE_ERROR, "pod or node is not part of the current round"}, 0};
+  std::unordered_map<std::string, uint32_t>::const_iterator it, nt;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    it = pod_row_.find(pod.uid);
+    nt = node_row_.find(node_name);
+    if (it == pod_row_.end() || nt == node_row_.end())
+      return {Status{BS_CODE_ERROR, "pod or node is not part of the current round"}, 0};
+  }
   bs_permit_result r{};
-  int rc = bs_permit(eng_, it->second, nt->second, &r);
+  // core.Permit with its bookkeeping (MatchedPodNodes.Set, the name -> uid de-dup of core.go:286-296, PodNameUIDs.Set,
+  // ready on the live count, pgs.Scheduled) against the engine's TTL tables
+  int rc = bs_permit_at(eng_, it->second, nt->second, now_ns_, &r);
   if (rc) return {Status{BS_CODE_ERROR, bs_strerror(rc)}, 0};
   if (r.code == BS_CODE_UNSCHEDULABLE) {
     auto lab = pod.labels.find(kPodGroupLabel);
@@ -1042,15 +1137,8 @@ std::pair<Status, int64_t> BatchSchedulingPlugin::Permit(const Pod& pod, const s
             r.wait_ns};                                                          // core.go:276, batchscheduler.go:194-195
   }
   if (r.group >= 0) {
-    // bookkeeping of core.go:284-300 for the NEXT round's carried-in matched count
-    GroupState& gs = groups_[group_names_[r.group]];
-    const std::string pod_name = pod.ns + "/" + pod.name;
-    const int64_t ttl = r.wait_ns - kSecond;                                     // waitTime (without the +1 s)
-    gs.matched_uid_expiry[pod.uid] = now_ns_ + (ttl > 0 ? ttl : 60 * kSecond);   // go-cache default 1 min (Q12, controller.go:317)
-    auto old = gs.pod_name_uid.find(pod_name);
-    if (old != gs.pod_name_uid.end()) gs.matched_uid_expiry.erase(old->second);  // core.go:293-296 (quirk Q7)
-    gs.pod_name_uid[pod_name] = pod.uid;                                         // core.go:300
-    if (r.ready) gs.scheduled_flag = true;                                       // core.go:305
+    std::lock_guard<std::mutex> lk(mu_);
+    uid_of_id_[IdOf(pod.uid)] = pod.uid;
   }
   if (start_signal) *start_signal = r.start_signal != 0;                         // batchscheduler.go:197-199
   return {Status{r.code, ""}, r.wait_ns};
@@ -1083,10 +1171,28 @@ Status BatchSchedulingPlugin::Filter(const Pod& pod, const std::string& node_nam
   }
 }
 
+// ScheduleOperation.Compare (core.go:368-411), from the two pods and the PodGroup cache alone — the scheduling
+// queue calls Less at any time on any two pods, also ones no round has seen yet.
 bool BatchSchedulingPlugin::Less(const Pod& a, const Pod& b) {
-  auto ia = pod_row_.find(a.uid), ib = pod_row_.find(b.uid);
-  if (ia == pod_row_.end() || ib == pod_row_.end()) return false;
-  return bs_less(eng_, ia->second, ib->second) == 1;
+  std::lock_guard<std::mutex> lk(mu_);
+  auto pg_name = [](const Pod& p) {                            // util.VerifyPodLabelSatisfied k8s.go:62-70
+    auto it = p.labels.find(kPodGroupLabel);
+    return it == p.labels.end() ? std::string() : it->second;
+  };
+  const std::string n1 = pg_name(a), n2 = pg_name(b);
+  if (a.priority > b.priority) return true;                    // :380-382
+  if (a.priority == b.priority) {
+    if (n1.empty() && n2.empty()) return a.queue_ts_ns < b.queue_ts_ns;   // :385-387
+    if (n1.empty()) return true;                               // :389-391
+    if (n2.empty()) return false;                              // :392-394
+  }
+  auto g1 = groups_.find(a.ns + "/" + n1), g2 = groups_.find(b.ns + "/" + n2);   // pgLister.PodGroups(ns).Get(name) :395-396
+  if (g1 == groups_.end() || g2 == groups_.end()) return false;                  // :397-399
+  if (a.priority != b.priority) return false;
+  const int64_t c1 = g1->second.pg.creation_ns, c2 = g2->second.pg.creation_ns;
+  if (c1 < c2) return true;                                    // :400-402
+  if (c1 == c2 && n1 > n2) return true;                        // :404-406
+  return c1 == c2 && n1 == n2 && a.queue_ts_ns < b.queue_ts_ns;   // :407-408
 }
 
 }  // namespace bsched

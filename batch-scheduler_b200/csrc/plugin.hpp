@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -184,6 +185,14 @@ class BatchSchedulingPlugin {
   void AddToDenyCache(const std::string& ns_name, int64_t now_ns);
   // lastPermittedPod.Add(uid, 2s) (core.go:188)
   void AddPermitted(const std::string& uid, int64_t now_ns);
+  // One janitor tick of the gangs' TTL tables (controller.go:322-333 via bs_expire): a gang whose wait time ran
+  // out rejects every pod it still holds at Permit ("Group failed", batchscheduler.go:347-354) and is deny-listed
+  // for 20 s.  rejected: uids to Reject; evicted: the groups ("namespace/name").
+  Status Tick(int64_t now_ns, std::vector<std::string>* rejected_uids, std::vector<std::string>* evicted_groups);
+  // StartBatchSchedule's Allow loop (batchscheduler.go:292-344) for a group whose Permit fired the start signal:
+  // (uid, node name) of every waiting pod to Allow; empty while the gang is incomplete.
+  Status AllowList(const std::string& ns_name, int64_t now_ns, std::vector<std::pair<std::string, std::string>>* allow);
+  static uint64_t IdOf(const std::string& s);   // FNV-1a 64: uids and "ns/name"s cross the C ABI as ids
 
   // The whole pending queue of the last BeginRound walked through the reference's pod-at-a-time cycle
   // (PreFilter against live state -> first fitting node -> assume -> Permit, core.go:88-167,268-309)
@@ -246,23 +255,26 @@ class BatchSchedulingPlugin {
                      int64_t default_wait_ns, PackedSnapshot* out);
 
  private:
+  // MatchedPodNodes / PodNameUIDs / pgs.Scheduled and the deny / permitted caches live in the ENGINE (bs_state_*,
+  // bs_permit_at, bs_expire, bs_allow_list: include/bsched.h "gang state"); here only what packing needs
   struct GroupState {
     PodGroup pg;
-    std::unordered_map<std::string, int64_t> matched_uid_expiry;   // MatchedPodNodes (TTL)
-    std::unordered_map<std::string, std::string> pod_name_uid;     // PodNameUIDs (name -> uid)
-    bool scheduled_flag = false;                                    // pgs.Scheduled (cache.go:66)
     bool has_pod = false;                                           // pgs.Pod != nil
     uint64_t rep_sel_pairs_hash = 0;
     Pod rep_pod;                                                    // pgs.Pod
   };
   bs_engine* eng_ = nullptr;
+  bool state_ready_ = false;   // bs_state_reset has run for this plugin's engine lineage
   int device_ = 0;
   uint32_t out_flags_ = 0, eng_lanes_ = 0;
   std::string init_error_;
   int64_t max_schedule_time_ns_;
   std::map<std::string, GroupState> groups_;                        // ordered: canonical table order
-  std::unordered_map<std::string, int64_t> deny_expiry_;            // lastDeniedPG
-  std::unordered_map<std::string, int64_t> permitted_expiry_;       // lastPermittedPod
+  std::vector<std::pair<std::string, int64_t>> pending_deny_;       // AddToDenyCache before the first round
+  std::vector<std::pair<std::string, int64_t>> pending_permitted_;  // AddPermitted before the first round
+  std::unordered_map<uint64_t, std::string> uid_of_id_;             // 64-bit id -> uid of every pod that reached Permit
+  std::vector<std::string> node_names_;                             // snapshot index -> node name
+  std::mutex mu_;                                                   // guards the maps against concurrent Less / Permit
   // last round
   PackedSnapshot packed_;
   std::unordered_map<std::string, uint32_t> pod_row_;               // uid -> pending index

@@ -241,6 +241,51 @@ class Engine:
         return dict(ready=bool(r.ready), code=r.code, wait_ns=r.wait_ns, start_signal=bool(r.start_signal),
                     group=r.group)
 
+    # -- gang state: the reference's TTL tables around Permit, kept in the engine --------------------
+    def state_reset(self):
+        self._check(self.lib.bs_state_reset(self.h))
+
+    def set_pod_ids(self, uid, name_id):
+        uid = np.ascontiguousarray(uid, dtype=np.uint64)
+        name_id = np.ascontiguousarray(name_id, dtype=np.uint64)
+        assert len(uid) == self.P and len(name_id) == self.P
+        self._check(self.lib.bs_set_pod_ids(self.h, capi.ptr(uid), capi.ptr(name_id)))
+
+    def begin_cycle(self, now_ns: int):
+        self._check(self.lib.bs_begin_cycle(self.h, int(now_ns)))
+
+    def permit_at(self, pod: int, node: int, now_ns: int):
+        r = capi.PermitResultC()
+        self._check(self.lib.bs_permit_at(self.h, pod, node, int(now_ns), C.byref(r)))
+        return dict(ready=bool(r.ready), code=r.code, wait_ns=r.wait_ns, start_signal=bool(r.start_signal), group=r.group)
+
+    def expire(self, now_ns: int, cap: int = None):
+        cap = cap or max(self.P, 1)
+        rg, ru = np.zeros(cap, np.uint32), np.zeros(cap, np.uint64)
+        ev = np.zeros(max(self.G, 1), np.uint32)
+        nr, ne = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.bs_expire(self.h, int(now_ns), capi.ptr(rg), capi.ptr(ru), cap, C.byref(nr), capi.ptr(ev), len(ev),
+                                       C.byref(ne)))
+        return list(zip(rg[:nr.value].tolist(), ru[:nr.value].tolist())), ev[:ne.value].tolist()
+
+    def allow_list(self, group: int, now_ns: int, cap: int = None):
+        cap = cap or max(self.P, 1)
+        u, nd = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        n = C.c_uint32()
+        self._check(self.lib.bs_allow_list(self.h, group, int(now_ns), capi.ptr(u), capi.ptr(nd), cap, C.byref(n)))
+        return u[:n.value].tolist(), nd[:n.value].tolist()
+
+    def deny(self, group: int, now_ns: int):
+        self._check(self.lib.bs_deny(self.h, group, int(now_ns)))
+
+    def mark_permitted(self, uid: int, now_ns: int):
+        self._check(self.lib.bs_mark_permitted(self.h, int(uid), int(now_ns)))
+
+    def group_state(self, group: int, now_ns: int):
+        m, s, d = C.c_uint32(), C.c_int32(), C.c_int32()
+        self._check(self.lib.bs_group_state(self.h, group, int(now_ns), C.byref(m), C.byref(s), C.byref(d)))
+        return dict(matched=int(m.value), scheduled=bool(s.value), denied=bool(d.value))
+
     def less(self, a: int, b: int) -> bool:
         rc = self.lib.bs_less(self.h, a, b)
         if rc < 0:

@@ -281,6 +281,51 @@ int bs_filter(bs_engine* e, uint32_t pod, uint32_t node, bs_status* st);
 int bs_format_message(const bs_status* st, const char* ns_name, const char* occupied_by,
                       char* buf, size_t buf_len);
 
+/* ---- gang state: the TTL tables around Permit as ENGINE state ----
+ * The reference keeps, per PodGroup, MatchedPodNodes (uid -> pod/node pair) and PodNameUIDs ("ns/name" -> uid),
+ * both go-cache maps with a per-entry TTL of the group's wait time (controller.go:314-335, core.go:283-300), plus
+ * the scheduler-wide lastDeniedPG (20 s) and lastPermittedPod (2 s) caches (core.go:71-72,188,423-425).  These
+ * calls keep them inside the engine, driven by the caller's clock (now_ns); uids and pod names cross the ABI as
+ * 64-bit ids (the Go shim hashes the strings).
+ *   bs_state_reset    empty tables for the uploaded group table
+ *   bs_state_remap    carry the tables over to a group table of another shape
+ *   bs_set_pod_ids    uid and "ns/name" id of every pod of the uploaded pod table
+ *   bs_begin_cycle    writes the tables' view at now_ns into the round's inputs — matched[g] =
+ *                     len(MatchedPodNodes.Items()), the SCHEDULED (pgs.Scheduled) and DENIED flags, the pods'
+ *                     PERMITTED_RECENTLY flag — replacing those columns of the uploaded tables; after the round,
+ *                     every group with new_denied set is added to the deny table (core.go:142,163)
+ *   bs_permit_at      ScheduleOperation.Permit with its bookkeeping (core.go:268-309): Set / Delete-old-uid / Set,
+ *                     ready = uint32(len(Items())) >= MinMember - Status.Scheduled, pgs.Scheduled on ready; the
+ *                     adapter mapping of bs_permit (batchscheduler.go:165-202)
+ *   bs_expire         one janitor tick: a group whose PodNameUIDs holds an expired entry rejects every matched
+ *                     pod ("Group failed", batchscheduler.go:347-354), forgets them, flushes its names and is
+ *                     deny-listed for 20 s (controller.go:322-333); returns the (group, uid) pairs to reject
+ *                     and the evicted groups (counts may exceed the capacities: call again with larger buffers
+ *                     is NOT possible, size them for the worst case = pods in flight)
+ *   bs_allow_list     StartBatchSchedule's Allow loop (batchscheduler.go:292-344): the uids (and the nodes they
+ *                     were permitted on) to Allow when the group has enough waiting pods, removed from the table
+ *   bs_deny / bs_mark_permitted   AddToDenyCache (core.go:423) / lastPermittedPod.Add (core.go:188)
+ *   bs_group_state    read-back for tests and metrics */
+int bs_state_reset(bs_engine* e);
+/* the group table is about to change shape (PodGroups created / deleted): row g of the NEXT table continues
+ * row old_index[g] of the current one (-1: a new group, empty tables); call before bs_begin_cycle */
+int bs_state_remap(bs_engine* e, uint32_t n_groups, const int32_t* old_index);
+/* bulk read-backs for a packer that needs the flags before it builds the round's tables: per group
+ * len(MatchedPodNodes.Items()) and BS_GROUP_SCHEDULED | BS_GROUP_DENIED; per uid lastPermittedPod membership */
+int bs_state_view(bs_engine* e, int64_t now_ns, uint32_t n_groups, uint32_t* matched, uint8_t* flags);
+int bs_permitted_view(bs_engine* e, int64_t now_ns, const uint64_t* uids, uint32_t n, uint8_t* out);
+/* hands the tables of `src` over to `dst` (an engine re-created with another lane count keeps its history) */
+int bs_state_move(bs_engine* dst, bs_engine* src);
+int bs_set_pod_ids(bs_engine* e, const uint64_t* uid /* [n_pods] */, const uint64_t* name_id /* [n_pods] */);
+int bs_begin_cycle(bs_engine* e, int64_t now_ns);
+int bs_permit_at(bs_engine* e, uint32_t pod, uint32_t node, int64_t now_ns, bs_permit_result* r);
+int bs_expire(bs_engine* e, int64_t now_ns, uint32_t* rej_group, uint64_t* rej_uid, uint32_t rej_cap, uint32_t* n_rejected,
+              uint32_t* evicted_group, uint32_t evict_cap, uint32_t* n_evicted);
+int bs_allow_list(bs_engine* e, uint32_t group, int64_t now_ns, uint64_t* uids, uint32_t* nodes, uint32_t cap, uint32_t* n);
+int bs_deny(bs_engine* e, uint32_t group, int64_t now_ns);
+int bs_mark_permitted(bs_engine* e, uint64_t uid, int64_t now_ns);
+int bs_group_state(bs_engine* e, uint32_t group, int64_t now_ns, uint32_t* matched, int32_t* scheduled_flag, int32_t* denied);
+
 /* ---- standalone table kernels (unit-level parity with the reference helpers) ---- */
 /* singleNodeResource over every node for one (sel,tol) pod class and percent
  * (core.go:634-670).  left: [n_lanes][n_nodes], present: [n_nodes]. */

@@ -160,5 +160,22 @@ int bso_round(const bso_nodes* nd, const bso_pods* pd, const bso_groups* gr, bso
 int bso_replay(bso_nodes* nd, const bso_pods* pd, bso_groups* gr, const uint32_t* queue,
                uint32_t n_queue, uint8_t* prefilter_out, int32_t* node_out, uint8_t* ready_out);
 
+/* ---- state around Permit (bs_gang.c): the reference's go-cache TTL tables, restated from their call sites ---- */
+typedef struct bso_gang bso_gang;
+bso_gang* bso_gang_new(uint32_t n_groups);
+void bso_gang_free(bso_gang* s);
+int bso_permit_step(bso_gang* s, uint32_t g, uint64_t uid, uint64_t name, uint32_t node, int64_t now, int64_t wait_ns,
+                    uint32_t min_member, uint32_t scheduled);                        /* core.go:283-307 */
+uint32_t bso_expire(bso_gang* s, int64_t now, uint32_t* rej_group, uint64_t* rej_uid, uint32_t cap, uint32_t* evicted,
+                    uint32_t ecap, uint32_t* n_evicted);                             /* controller.go:322-333 */
+uint32_t bso_allow_list(bso_gang* s, uint32_t g, int64_t now, uint32_t min_member, uint32_t scheduled, uint64_t* uids,
+                        uint32_t* nodes, uint32_t cap);                              /* batchscheduler.go:292-344 */
+uint32_t bso_gang_matched(const bso_gang* s, uint32_t g, int64_t now);
+int bso_gang_scheduled(const bso_gang* s, uint32_t g);
+int bso_gang_denied(bso_gang* s, uint32_t g, int64_t now);
+void bso_gang_deny(bso_gang* s, uint32_t g, int64_t now);                            /* core.go:423-425 */
+int bso_gang_permitted(bso_gang* s, uint64_t uid, int64_t now);
+void bso_gang_mark_permitted(bso_gang* s, uint64_t uid, int64_t now);                /* core.go:188 */
+
 int bso_max_threads(void);
 #endif

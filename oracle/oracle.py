@@ -19,7 +19,7 @@ MAX_LANES = 16
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("bs_oracle.c", "bs_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("bs_oracle.c", "bs_gang.c", "bs_oracle.h")]
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "libbs_oracle.so"])
@@ -271,3 +271,69 @@ def replay(snap, queue=None):
 
 def max_threads() -> int:
     return int(lib().bso_max_threads())
+
+
+class Gang:
+    """CPU model of the state around Permit (oracle/bs_gang.c): MatchedPodNodes / PodNameUIDs with TTLs, the
+    deny and permitted caches, the eviction callback and the Allow loop."""
+
+    def __init__(self, n_groups: int):
+        L = lib()
+        L.bso_gang_new.restype = C.c_void_p
+        L.bso_gang_new.argtypes = [C.c_uint32]
+        L.bso_gang_free.argtypes = [C.c_void_p]
+        L.bso_permit_step.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64,
+                                      C.c_uint32, C.c_uint32]
+        L.bso_expire.restype = C.c_uint32
+        L.bso_expire.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                 _p(C.c_uint32)]
+        L.bso_allow_list.restype = C.c_uint32
+        L.bso_allow_list.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_uint32]
+        L.bso_gang_matched.restype = C.c_uint32
+        L.bso_gang_matched.argtypes = [C.c_void_p, C.c_uint32, C.c_int64]
+        L.bso_gang_scheduled.argtypes = [C.c_void_p, C.c_uint32]
+        L.bso_gang_denied.argtypes = [C.c_void_p, C.c_uint32, C.c_int64]
+        L.bso_gang_deny.argtypes = [C.c_void_p, C.c_uint32, C.c_int64]
+        L.bso_gang_permitted.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+        L.bso_gang_mark_permitted.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+        self.L, self.n = L, n_groups
+        self.h = L.bso_gang_new(n_groups)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.bso_gang_free(self.h)
+            self.h = None
+
+    def permit(self, g, uid, name, node, now, wait_ns, min_member, scheduled) -> bool:
+        return bool(self.L.bso_permit_step(self.h, g, uid, name, node, now, wait_ns, min_member, scheduled))
+
+    def expire(self, now, cap=4096):
+        rg, ru = np.zeros(cap, np.uint32), np.zeros(cap, np.uint64)
+        ev = np.zeros(max(self.n, 1), np.uint32)
+        ne = C.c_uint32()
+        n = self.L.bso_expire(self.h, now, rg.ctypes.data, ru.ctypes.data, cap, ev.ctypes.data, len(ev), C.byref(ne))
+        return list(zip(rg[:n].tolist(), ru[:n].tolist())), ev[:ne.value].tolist()
+
+    def allow_list(self, g, now, min_member, scheduled, cap=4096):
+        u, nd = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        n = self.L.bso_allow_list(self.h, g, now, min_member, scheduled, u.ctypes.data, nd.ctypes.data, cap)
+        return u[:n].tolist(), nd[:n].tolist()
+
+    def matched(self, g, now):
+        return int(self.L.bso_gang_matched(self.h, g, now))
+
+    def scheduled(self, g):
+        return bool(self.L.bso_gang_scheduled(self.h, g))
+
+    def denied(self, g, now):
+        return bool(self.L.bso_gang_denied(self.h, g, now))
+
+    def deny(self, g, now):
+        self.L.bso_gang_deny(self.h, g, now)
+
+    def permitted(self, uid, now):
+        return bool(self.L.bso_gang_permitted(self.h, uid, now))
+
+    def mark_permitted(self, uid, now):
+        self.L.bso_gang_mark_permitted(self.h, uid, now)

@@ -3,6 +3,7 @@
 //   quantity <s>...   : Quantity.Value / MilliValue of each argument             (CPU)
 //   pack_core_test    : core_test.go:27-115 objects -> packed tables             (CPU)
 //   readme            : README.md:76-188 resource race, pod by pod, on the GPU
+//   gang_timeout      : TTL eviction => reject-all + flush + deny 20 s, and the Allow list of a complete gang (GPU)
 //   readme_replay     : the same race in one call (all pods pending, the device walks the queue)
 //   pack_affinity [k] : required nodeAffinity terms -> affinity classes + verdict bits; k > 64 extra selector pairs (CPU)
 //   bench_pack N P G  : packer throughput on synthetic objects                   (CPU)
@@ -141,6 +142,71 @@ static int cmd_readme() {
            "\"wait_ns\": 0, \"start_signal\": 0}\n", p.name.c_str(), pf.code, pf.message.c_str());
   }
   printf("]\n");
+  return 0;
+}
+
+// SURVEY 8(f) row 3 through the plugin: the gang-timeout path (controller.go:314-335: TTL eviction => reject every
+// matched pod => flush => deny 20 s) and the Allow loop (batchscheduler.go:292-344), on the engine's gang state.
+static int cmd_gang_timeout() {
+  Node node; node.name = "node1";
+  node.allocatable = {{"cpu", "8"}, {"memory", "16Gi"}, {"ephemeral-storage", "100Gi"}, {"pods", "110"}};
+  NodeInfo info; info.node = &node; info.num_pods = 0;
+  info.requested = {{"cpu", "0"}};
+  const int64_t S = 1000000000ll;
+  BatchSchedulingPlugin plugin(0, 60 * S);
+  PodGroup a; a.ns = "default"; a.name = "gang-a"; a.min_member = 3; a.max_schedule_time_ns = 10 * S; a.creation_ns = 1;
+  PodGroup b; b.ns = "default"; b.name = "gang-b"; b.min_member = 2; b.max_schedule_time_ns = 30 * S; b.creation_ns = 2;
+  plugin.SetPodGroup(a); plugin.SetPodGroup(b);
+  auto mk = [](const char* grp, int i) {
+    Pod p; p.ns = "default"; p.name = std::string(grp) + "-" + std::to_string(i); p.uid = "uid-" + p.name;
+    p.labels[kPodGroupLabel] = grp;
+    Container c; c.has_limits = true; c.limits = {{"cpu", "1"}}; c.requests = c.limits;
+    p.containers = {c};
+    return p;
+  };
+  int64_t t0 = 1000 * S;
+  printf("{\n");
+  auto cycle = [&](const char* tag, const Pod& p, int64_t now, bool last = false) {
+    Status st = plugin.BeginRound({&info}, {&p}, now);
+    if (!st.ok()) { fprintf(stderr, "round failed: %s\n", st.message.c_str()); exit(1); }
+    Status pf = plugin.PreFilter(p);
+    int permit_code = -1; bool start = false; long long wait = 0;
+    if (pf.ok()) {
+      auto r = plugin.Permit(p, node.name, &start);
+      permit_code = r.first.code; wait = r.second;
+    }
+    printf("\"%s\": {\"prefilter_code\": %d, \"message\": \"%s\", \"permit_code\": %d, \"wait_ns\": %lld, \"start_signal\": %d}%s\n",
+           tag, pf.code, pf.message.c_str(), permit_code, wait, start ? 1 : 0, last ? "" : ",");
+  };
+  auto tick = [&](const char* tag, int64_t now) {
+    std::vector<std::string> rej, ev;
+    plugin.Tick(now, &rej, &ev);
+    printf("\"%s\": {\"rejected\": [", tag);
+    for (size_t i = 0; i < rej.size(); ++i) printf("%s\"%s\"", i ? ", " : "", rej[i].c_str());
+    printf("], \"evicted\": [");
+    for (size_t i = 0; i < ev.size(); ++i) printf("%s\"%s\"", i ? ", " : "", ev[i].c_str());
+    printf("]},\n");
+  };
+  auto allow = [&](const char* tag, const char* grp, int64_t now) {
+    std::vector<std::pair<std::string, std::string>> al;
+    plugin.AllowList(std::string("default/") + grp, now, &al);
+    printf("\"%s\": [", tag);
+    for (size_t i = 0; i < al.size(); ++i) printf("%s[\"%s\", \"%s\"]", i ? ", " : "", al[i].first.c_str(), al[i].second.c_str());
+    printf("],\n");
+  };
+  Pod a0 = mk("gang-a", 0), a1 = mk("gang-a", 1), a2 = mk("gang-a", 2), b0 = mk("gang-b", 0), b1 = mk("gang-b", 1);
+  cycle("a0@0", a0, t0);                    // waits (1 of 3), TTL 10 s
+  cycle("a1@4", a1, t0 + 4 * S);            // waits (2 of 3), TTL until 14 s
+  cycle("b0@5", b0, t0 + 5 * S);            // gang-b 1 of 2
+  allow("allow_b@5", "gang-b", t0 + 5 * S); // incomplete: nothing to Allow
+  cycle("b1@6", b1, t0 + 6 * S);            // gang-b complete: start signal
+  allow("allow_b@6", "gang-b", t0 + 6 * S); // both pods, with their node
+  allow("allow_b_again", "gang-b", t0 + 6 * S);
+  tick("tick@9", t0 + 9 * S);               // nothing has expired
+  tick("tick@11", t0 + 11 * S);             // a0's name entry ran out: gang-a evicted, a1 (still waiting) rejected
+  cycle("a2@12", a2, t0 + 12 * S);          // frozen: "last failed in 20s, deny"
+  cycle("a2@32", a2, t0 + 32 * S, true);    // the deny entry has expired: passes, waits as 1 of 3 again
+  printf("}\n");
   return 0;
 }
 
@@ -566,6 +632,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "pack_delta")) return cmd_pack_delta();
   if (!strcmp(argv[1], "pack_group_delta")) return cmd_pack_group_delta();
   if (!strcmp(argv[1], "readme")) return cmd_readme();
+  if (!strcmp(argv[1], "gang_timeout")) return cmd_gang_timeout();
   if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
   if (!strcmp(argv[1], "pack_affinity")) return cmd_pack_affinity(argc >= 3 ? atoi(argv[2]) : 0);
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));

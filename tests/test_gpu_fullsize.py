@@ -70,20 +70,32 @@ def test_full_size_decisions_and_properties(pkg, oracle, snapshot_mod, cfg):
     eng.close()
 
 
-def test_cfg5_shard_properties(pkg, oracle, snapshot_mod):
-    # config #5 is 1M pods / 50k nodes over 8 GPUs: one rank's shard (125k pods, 9 lanes) on one GPU
+def test_cfg5_one_rank_shard_full_size(pkg, oracle, snapshot_mod):
+    """BASELINE configs[4] (1M pods / 50k nodes / 62.5k groups / 9 lanes) as rank 0 of the 8-way group sharding sees
+    it: 125k pods x ALL 50k nodes, a 50 GB int64 score shard + fit bitmap on one GPU.  Every decision vector against
+    the multi-threaded oracle round on the same shard, 300 rows of both matrices, and the size-independent properties."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 70e9:
+        pytest.skip("needs ~55 GB of free HBM")
     S = snapshot_mod
-    snap = S.config(5, 0.125)
-    snap.nodes = S.config(5, 0.25).nodes      # 12.5k nodes keep the score matrix at 12.5 GB
+    full = S.config(5).resolve_groups()
+    snap = full.shard_groups(0, 8)
+    assert 124900 <= snap.pods.n <= 125100 and snap.nodes.n == 50000 and snap.lanes == 9   # ranges follow group borders
     eng = pkg.Engine(snap.lanes, 0, fit_bitmap=True, score=True)
     eng.upload(snap)
     res = eng.evaluate()
-    _properties(snap, res, eng, S, sample_rows=24)
-    sub = S.Snapshot(snap.nodes, snap.pods.take(np.arange(500, 700)), snap.groups)
-    o2 = oracle.round(sub, want_bitmap=True, want_score=True, want_sort=False)
-    np.testing.assert_array_equal(eng.fit_rows(500, 200), o2.fit_bitmap)
-    np.testing.assert_array_equal(eng.score_rows(500, 200), o2.score)
-    np.testing.assert_array_equal(res.feasible_count[500:700], o2.feasible_count)
+    assert eng.fit_shape()["LW"] + eng.fit_shape()["LN"] + eng.fit_shape()["LS"] == 9
+    _properties(snap, res, eng, S, sample_rows=16)
+    orc = oracle.round(snap, want_bitmap=False, want_score=False, threads=0)
+    for f in ("prefilter", "feasible_count", "best_node", "best_score", "admit", "admit_bitmap", "new_denied",
+              "order", "rank"):
+        np.testing.assert_array_equal(getattr(res, f), getattr(orc, f), err_msg=f)
+    assert res.max_group == orc.max_group and res.max_finished == orc.max_finished
+    for p0 in (0, 62000, 124900):
+        sub = S.Snapshot(snap.nodes, snap.pods.take(np.arange(p0, p0 + 100)), snap.groups)
+        o2 = oracle.round(sub, want_bitmap=True, want_score=True, want_sort=False)
+        np.testing.assert_array_equal(eng.fit_rows(p0, 100), o2.fit_bitmap)
+        np.testing.assert_array_equal(eng.score_rows(p0, 100), o2.score)
     eng.close()
 
 

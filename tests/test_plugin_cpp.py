@@ -140,6 +140,29 @@ def test_readme_race_through_cpp_plugin(plugin_bin, snapshot_mod):
 
 
 @pytest.mark.gpu
+def test_gang_timeout_and_allow_list(plugin_bin):
+    """SURVEY 8(f) row 3 on the engine's gang state: a gang that does not complete within its wait time is
+    evicted — every pod it still holds at Permit is rejected, its tables are flushed and it is deny-listed for 20 s
+    (controller.go:314-335, batchscheduler.go:347-354); a gang that completes hands out its Allow list once
+    (batchscheduler.go:292-344)."""
+    out = _run(plugin_bin, "gang_timeout")
+    WAIT, UNSCHED = 4, 2
+    assert out["a0@0"]["prefilter_code"] == 0 and out["a0@0"]["permit_code"] == WAIT and out["a0@0"]["start_signal"] == 0
+    assert out["a0@0"]["wait_ns"] == 11 * 10**9                      # MaxScheduleTime 10 s + 1 s (batchscheduler.go:180-182)
+    assert out["a1@4"]["permit_code"] == WAIT and out["a1@4"]["start_signal"] == 0
+    assert out["b0@5"]["start_signal"] == 0 and out["allow_b@5"] == []
+    assert out["b1@6"]["start_signal"] == 1                          # 2 >= MinMember 2: ready on the second pod, not the first
+    assert sorted(out["allow_b@6"]) == [["uid-gang-b-0", "node1"], ["uid-gang-b-1", "node1"]]
+    assert out["allow_b_again"] == []                                # allowed pods left MatchedPodNodes
+    assert out["tick@9"] == {"rejected": [], "evicted": []}
+    # at 11 s a0's entries (TTL 10 s) are gone: the name cache's eviction fires; a1 (TTL until 14 s) is still waiting
+    assert out["tick@11"] == {"rejected": ["uid-gang-a-1"], "evicted": ["default/gang-a"]}
+    assert out["a2@12"]["prefilter_code"] == UNSCHED
+    assert out["a2@12"]["message"] == "pod with pgName: default/gang-a last failed in 20s, deny"
+    assert out["a2@32"]["prefilter_code"] == 0 and out["a2@32"]["permit_code"] == WAIT and out["a2@32"]["start_signal"] == 0
+
+
+@pytest.mark.gpu
 def test_readme_race_in_one_call(plugin_bin, snapshot_mod):
     # all ten pods pending at once; ReplayQueue walks them in Less order on the device: equal priority
     # and creation time -> the group with the greater name goes first (core.go:404) and wins the race
