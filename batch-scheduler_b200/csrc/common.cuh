@@ -68,8 +68,19 @@ static_assert(TILE_WORDS <= 16, "best-node key: score (27 bits) + word index (4 
 #define BS_FIT_STAGES 2
 #endif
 constexpr int FIT_STAGES = BS_FIT_STAGES;               // TMA ring depth (full/empty mbarrier pairs)
+// Score rows leave the SMs with 8-byte streaming stores (BS_FIT_STG, default).  -DBS_FIT_TMA_STORE stages them in
+// shared memory and hands FIT_SEG-node row segments to the TMA engine instead (cp.async.bulk shared -> global):
+// built, parity-tested and measured in round 2 — 3 % slower in the kernel (the per-segment proxy fence and
+// issue cost more than the cleaner HBM burst pattern returns), see profiles/README.md.
+#if !defined(BS_FIT_TMA_STORE) && !defined(BS_FIT_STG)
+#define BS_FIT_STG 1
+#endif
 #ifndef BS_FIT_SEG
+#ifdef BS_FIT_STG
+#define BS_FIT_SEG BS_FIT_TILE
+#else
 #define BS_FIT_SEG 128
+#endif
 #endif
 constexpr int FIT_SEG = BS_FIT_SEG;                     // nodes per score store segment (one bulk store per pod row)
 constexpr int SEG_WORDS = FIT_SEG / 32;

@@ -170,7 +170,7 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
                                          int j0 /*first word of the segment*/,
                                          typename BestT<(LN > 0)>::type (&best_s)[PODS_PER_WARP],
                                          int32_t (&best_n)[PODS_PER_WARP], int32_t (&kb)[PODS_PER_WARP],
-                                         uint32_t (&cnt)[PODS_PER_WARP]) {
+                                         uint32_t (&cnt)[PODS_PER_WARP], uint32_t stg_row0 = 0) {
   constexpr bool SCORE = OUT == FIT_OUT_SCORE;
   constexpr bool WORDS = OUT != FIT_OUT_NONE;
   const int64_t* tpw = tlw + lane + j0 * 32;
@@ -226,7 +226,11 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
           // (scores of fitting pairs are < 2^27), -1 = none; decoded once per tile
           const int32_t key = (int32_t)(m32 << KEY_BITS) + (jrem - jj);
           if (fit) kb[r] = max(kb[r], key);
-#if BS_FIT_EXP != 2   // (experiment 2: bulk stores without the staging stores)
+#ifdef BS_FIT_STG     // (experiment: scores straight to HBM with 8-byte streaming stores, no staging / TMA)
+          if (SCORE && (uint32_t)(node + jj * 32) < a.N)
+            __stcs(reinterpret_cast<unsigned long long*>(a.score) + (size_t)(stg_row0 + r) * a.score_pitch + (node + jj * 32),
+                   (unsigned long long)(fit ? m32 : 0u) | ((unsigned long long)(fit ? 0u : 0x80000000u) << 32));
+#elif BS_FIT_EXP != 2   // (experiment 2: bulk stores without the staging stores)
           if (SCORE) sts_v2u32(sp + (r * FIT_SEG + jj * 32) * 8, fit ? m32 : 0u, fit ? 0u : 0x80000000u);
 #endif
         } else {
@@ -237,7 +241,13 @@ __device__ __forceinline__ void fit_seg(const FitArgs& a, const int64_t* __restr
           if (WORDS) sts_u32(wp + (r * 32 + jj) * 4, __ballot_sync(0xffffffffu, fit));
           else if (fit) ++cnt[r];
           if (fit && m > best_s[r]) { best_s[r] = m; best_n[r] = node + jj * 32; }
+#ifdef BS_FIT_STG
+          if (SCORE && (uint32_t)(node + jj * 32) < a.N)
+            __stcs(reinterpret_cast<long long*>(a.score) + (size_t)(stg_row0 + r) * a.score_pitch + (node + jj * 32),
+                   fit ? (long long)m : (long long)INT64_MIN);
+#else
           if (SCORE) sts_u64(sp + (r * FIT_SEG + jj * 32) * 8, fit ? (long long)m : (long long)INT64_MIN);
+#endif
         }
       }
     }
@@ -271,6 +281,9 @@ __host__ __device__ constexpr int fit_stages(int LW, int LN, int LS, bool score)
   return fit_smem_total(LW, LN, LS, score, FIT_STAGES) <= FIT_SMEM_MAX ? FIT_STAGES : 2;
 }
 inline size_t gang_fit_smem_bytes(int LW, int LN, int LS, bool score) {
+#ifdef BS_FIT_STG
+  score = false;   // no staging slabs
+#endif
   return fit_smem_total(LW, LN, LS, score, fit_stages(LW, LN, LS, score));
 }
 
@@ -417,12 +430,17 @@ __global__ void __launch_bounds__(FIT_THREADS, OUT == FIT_OUT_SCORE ? BS_FIT_MIN
 #pragma unroll 1
     for (int sg = 0; sg < NODE_TILE / FIT_SEG; ++sg) {
       const uint32_t slab = slab0 + sb * (uint32_t)fit_slab_bytes();
-      if (SCORE && nseg >= (uint32_t)FIT_NB) {
+#ifdef BS_FIT_STG
+      constexpr bool STAGE = false;
+#else
+      constexpr bool STAGE = SCORE;
+#endif
+      if (STAGE && nseg >= (uint32_t)FIT_NB) {
         if (lane == 0) bulk_wait_read<FIT_NB - 1>();   // the bulk stores that last read this slab are done with it
         __syncwarp();
       }
-      fit_seg<LW, LN, LS, OUT>(a, tlw, tln, rqw, rqn, colbits, slab, s_words, wbase, node_base, lane, sg * SEG_WORDS, best_s, best_n, kb, cnt);
-      if (SCORE) {
+      fit_seg<LW, LN, LS, OUT>(a, tlw, tln, rqw, rqn, colbits, slab, s_words, wbase, node_base, lane, sg * SEG_WORDS, best_s, best_n, kb, cnt, wpod0);
+      if (STAGE) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -483,7 +501,9 @@ __global__ void __launch_bounds__(FIT_THREADS, OUT == FIT_OUT_SCORE ? BS_FIT_MIN
     __syncwarp();                                   // the ballot slab is rewritten by the next tile
     if (++stage == STAGES) { stage = 0; phase ^= 1; }
   }
+#ifndef BS_FIT_STG
   if (SCORE && lane == 0) bulk_wait_read<0>();      // the slabs must outlive their bulk reads
+#endif
 
   // per-pod reductions across the warp: best = max score, lowest node on ties
 #pragma unroll
