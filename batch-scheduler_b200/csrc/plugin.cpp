@@ -587,7 +587,21 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   }
   if (err) { bad.message = "bad quantity in a pod's containers"; return bad; }
   phase("pods par");
-  for (uint32_t i = 0; i < P; ++i) {
+  // fillOccupiedObj runs when a pod is popped, i.e. in QUEUE order (Less = Compare, core.go:368-411), not in
+  // arrival order: with an empty OccupiedBy and pods of one group carrying different ownerRefs, the first pod
+  // in queue order decides who occupies the group.  Stable sort of the grouped pods by Compare's key.
+  std::vector<uint32_t> qorder;
+  qorder.reserve(P);
+  for (uint32_t i = 0; i < P; ++i) if (ps.gid[i] >= 0) qorder.push_back(i);
+  std::stable_sort(qorder.begin(), qorder.end(), [&](uint32_t a, uint32_t b) {
+    if (ps.priority[a] != ps.priority[b]) return ps.priority[a] > ps.priority[b];
+    const PodGroup& ga = *groups[ps.gid[a]].pg;
+    const PodGroup& gb = *groups[ps.gid[b]].pg;
+    if (ga.creation_ns != gb.creation_ns) return ga.creation_ns < gb.creation_ns;
+    if (ga.name != gb.name) return ga.name > gb.name;            // core.go:404: the greater bare name first
+    return ps.ts_ns[a] < ps.ts_ns[b];
+  });
+  for (uint32_t i : qorder) {
     const int32_t gidx = ps.gid[i];
     if (gidx < 0) continue;
     const uint32_t g = (uint32_t)gidx;

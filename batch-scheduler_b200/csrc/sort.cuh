@@ -27,6 +27,8 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_MAX_PASSES = 16;
+// register budget: 65536 / (256 * 6) -> 40 per thread, what two 288-thread, 96-register gang_fit CTAs leave free
+constexpr int SORT_MIN_CTAS = 6;
 
 struct SortPass {
   uint8_t word;   // 0: k0, 1: k1
@@ -108,6 +110,7 @@ __device__ void sort_init_tiles(const uint64_t* k0, const uint64_t* k1, const So
     s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = t * SORT_TILE;
+#pragma unroll 4
     for (int k = 0; k < SORT_ITEMS; ++k) {
       const uint32_t i = base + k * SORT_THREADS + threadIdx.x;
       if (i < n) {
@@ -135,28 +138,40 @@ __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, b
     __syncthreads();
     const uint32_t wbase = t * SORT_TILE + wid * (SORT_TILE / SORT_WARPS);
     constexpr int ITER = SORT_TILE / SORT_WARPS / 32;
-    uint32_t my_idx[ITER];
-    uint32_t my_dig[ITER];
+    // Digits are parked four to a word in shared memory and the indices are re-read in (c): the CTA
+    // has to fit into the registers two gang_fit CTAs leave free on an SM (SORT_MIN_CTAS), or every
+    // SM that hosts a sort CTA runs no fit CTA while the sort lasts.
+    __shared__ uint32_t s_dpack[ITER / 4][SORT_THREADS];
     // (a) warp digit counts
+#pragma unroll 1
+    for (int q = 0; q < ITER / 4; ++q) {
+      uint32_t ix[4], pk = 0;
 #pragma unroll
-    for (int k = 0; k < ITER; ++k) {
-      const uint32_t i = wbase + k * 32 + lane;
-      const bool act = i < n;
-      my_idx[k] = act ? in[i] : 0u;
-      my_dig[k] = act ? digit_of(k0, k1, ps, my_idx[k]) : 0x100u;
-    }
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        ix[u] = i < n ? in[i] : 0u;
+      }
 #pragma unroll
-    for (int k = 0; k < ITER; ++k) {
-      const bool act = wbase + k * 32 + lane < n;
-      const uint32_t mask = warp_peers(my_dig[k], act);
-      if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][my_dig[k]] += __popc(mask);
-      __syncwarp();
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        pk |= (i < n ? digit_of(k0, k1, ps, ix[u]) : 0u) << (8 * u);
+      }
+      s_dpack[q][threadIdx.x] = pk;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool act = wbase + (q * 4 + u) * 32 + lane < n;
+        const uint32_t dig = (pk >> (8 * u)) & 0xffu;
+        const uint32_t mask = warp_peers(dig, act);
+        if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][dig] += __popc(mask);
+        __syncwarp();
+      }
     }
     // (b) thread d: tiles before this one with digit d, and the digit total
     {
       const uint32_t d = threadIdx.x;
       const uint32_t* row = cur + d * ntiles;
       uint32_t before = 0, total = 0;
+#pragma unroll 4
       for (uint32_t tt = 0; tt < ntiles; ++tt) {
         const uint32_t c = row[tt];
         total += c;
@@ -183,19 +198,30 @@ __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, b
     }
     __syncthreads();
     // (c) ranks in original order, scatter, next-digit histogram at the destination tile
+#pragma unroll 1
+    for (int q = 0; q < ITER / 4; ++q) {
+      uint32_t ix[4];
+      const uint32_t pk = s_dpack[q][threadIdx.x];
 #pragma unroll
-    for (int k = 0; k < ITER; ++k) {
-      const uint32_t i = wbase + k * 32 + lane;
-      const bool act = i < n;
-      const uint32_t mask = warp_peers(my_dig[k], act);
-      uint32_t pos = 0;
-      if (act) pos = wcount[wid][my_dig[k]] + __popc(mask & ((1u << lane) - 1u));
-      __syncwarp();
-      if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][my_dig[k]] += __popc(mask);
-      __syncwarp();
-      if (act) {
-        out[pos] = my_idx[k];
-        if (has_next) atomicAdd(&nxt[digit_of(k0, k1, ps_next, my_idx[k]) * ntiles + pos / SORT_TILE], 1u);
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        ix[u] = i < n ? in[i] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        const bool act = i < n;
+        const uint32_t dig = (pk >> (8 * u)) & 0xffu;
+        const uint32_t mask = warp_peers(dig, act);
+        uint32_t pos = 0;
+        if (act) pos = wcount[wid][dig] + __popc(mask & ((1u << lane) - 1u));
+        __syncwarp();
+        if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][dig] += __popc(mask);
+        __syncwarp();
+        if (act) {
+          out[pos] = ix[u];
+          if (has_next) atomicAdd(&nxt[digit_of(k0, k1, ps_next, ix[u]) * ntiles + pos / SORT_TILE], 1u);
+        }
       }
     }
     __syncthreads();
@@ -227,6 +253,7 @@ __device__ void rank_count_tiles(const uint32_t* order, const uint64_t* k0, cons
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
     uint32_t c = 0;
+#pragma unroll 4
     for (int k = 0; k < SORT_ITEMS; ++k)
       if (base + k < n) c += rank_flag(order, k0, k1, base + k);
     c = block_sum(c, s_w);
@@ -244,6 +271,7 @@ __device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, cons
     off = block_sum(off, s_w);
     const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
     uint32_t c = 0;
+#pragma unroll 4
     for (int k = 0; k < SORT_ITEMS; ++k)
       if (base + k < n) c += rank_flag(order, k0, k1, base + k);
     uint32_t inc = c;
@@ -256,6 +284,7 @@ __device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, cons
     __syncthreads();
     uint32_t run = off + inc - c;
     for (uint32_t w = 0; w < wid; ++w) run += s_w[w];
+#pragma unroll 2
     for (int k = 0; k < SORT_ITEMS; ++k) {
       const uint32_t i = base + k;
       if (i < n) {
@@ -291,7 +320,7 @@ __device__ uint32_t* sort_table(const uint64_t* k0, const uint64_t* k1, const So
   return cur;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) queue_sort_kernel(SortArgs a) {
+__global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_CTAS) queue_sort_kernel(SortArgs a) {
   __shared__ uint32_t wcount[SORT_WARPS][256];
   __shared__ uint32_t s_misc[256];
   unsigned int epoch = 0;

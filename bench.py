@@ -723,6 +723,36 @@ def main():
     h2d = table_bytes(snap)
     d2h = sum(getattr(res, f).nbytes for f in ("prefilter", "feasible_count", "best_node", "best_score", "admit",
                                                "admit_bitmap", "new_denied", "order", "rank"))
+    # ---- delta e2e: what a scheduling cycle looks like once the tables are resident — 1 % of the node rows and
+    # 1 % of the group rows changed on the host (bs_update_nodes / bs_update_groups: H2D of the changed rows +
+    # device scatter), evaluate, one D2H of every decision vector
+    e2e_delta = None
+    if world == 1:
+        rng = np.random.default_rng(7)
+        nn, ng = max(1, N // 100), max(1, G // 100)
+        ni = np.sort(rng.choice(N, nn, replace=False)).astype(np.uint32)
+        gi = np.sort(rng.choice(G, ng, replace=False)).astype(np.uint32)
+        nrows = S.NodeTable(snap.nodes.alloc[:, ni], snap.nodes.requested[:, ni], snap.nodes.pod_count[ni],
+                            snap.nodes.alloc_present[ni], snap.nodes.req_present[ni], snap.nodes.label_mask[ni],
+                            snap.nodes.taint_mask[ni], snap.nodes.flags[ni])
+        grows = S.GroupTable(snap.groups.min_member[gi], snap.groups.scheduled[gi], snap.groups.matched[gi],
+                             snap.groups.flags[gi], snap.groups.min_res[:, gi], snap.groups.min_res_present[gi],
+                             snap.groups.rep_sel[gi], snap.groups.rep_tol[gi], snap.groups.creation_ns[gi],
+                             snap.groups.name_rank[gi])
+        for _ in range(3):
+            eng.update_nodes(ni, nrows); eng.update_groups(gi, grows); res = eng.evaluate(out=res)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.update_nodes(ni, nrows); eng.update_groups(gi, grows); res = eng.evaluate(out=res)
+        dd = time.perf_counter() - t0
+        e2e_delta = {"ms_per_step": dd / e2e_steps * 1e3, "value": float(P) * N * e2e_steps / dd, "unit": UNIT,
+                     "steps": e2e_steps, "changed_nodes": int(nn), "changed_groups": int(ng),
+                     "h2d_bytes_per_step": int(sum(getattr(nrows, f).nbytes for f in nrows.__dataclass_fields__) + ni.nbytes +
+                                               sum(getattr(grows, f).nbytes for f in grows.__dataclass_fields__
+                                                   if getattr(grows, f) is not None) + gi.nbytes),
+                     "d2h_bytes_per_step": int(d2h),
+                     "what": "bs_update_nodes + bs_update_groups (1 % of the rows each) + bs_evaluate with the fetch of "
+                             "every decision vector, wall clock"}
     if use_p2p:
         dist.barrier()
         eng.peer_detach()
@@ -794,6 +824,7 @@ def main():
                     "breakdown_ms": {k: v / e2e_steps * 1e3 for k, v in br.items()},
                     "what": "bs_upload_nodes/groups/pods from pinned host tables + bs_evaluate (D2H of all decision "
                             "vectors) per step, wall clock"},
+            "e2e_delta": e2e_delta,
             "e2e_objects": objects,
             "gpu_launches": int(round(launches_per_step * head["steps"])),
             "gpu_launches_per_step": launches_per_step,

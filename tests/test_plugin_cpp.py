@@ -82,9 +82,10 @@ def test_packer_semantics(plugin_bin, snapshot_mod):
     assert o["sel_mask"] == [1, 0, 0, 0, 0, 0, 0]
     assert o["tol_mask"][:2] == [1, 3]                            # Equal key/value/effect; bare Exists tolerates all
     assert o["priority"][1] == 7 and o["ts_ns"][1] == 42
-    # fillOccupiedObj order: p1 is the first pod with owner refs -> OccupiedBy "u1,u2" (sorted); p6 matches it;
-    # pgB is occupied by "u1,u2": other owners -> mismatch, no owners -> the "no refs" message
-    assert o["pod_flags"] == [0, 0, S.POD_LISTER_MISS, 0, S.POD_OCC_MISMATCH, S.POD_OCC_NOREFS, 0]
+    # fillOccupiedObj runs in QUEUE order (Less, core.go:368-411): p1 (priority 7) is popped first and, having owner
+    # refs, occupies pgA with "u1,u2" (sorted); p0 (no owner refs) then meets an occupied group -> the "no refs"
+    # message; p6 matches the owners; pgB is occupied by "u1,u2": other owners -> mismatch, no owners -> "no refs"
+    assert o["pod_flags"] == [S.POD_OCC_NOREFS, 0, S.POD_LISTER_MISS, 0, S.POD_OCC_MISMATCH, S.POD_OCC_NOREFS, 0]
     assert o["min_member"] == [2, 3, 1, 4] and o["scheduled"] == [0, 1, 0, 0] and o["matched"] == [1, 0, 0, 0]
     assert o["group_flags"] == [0, S.GROUP_HAS_MINRES, 0, S.GROUP_SCHEDULED]
     min_res = np.array(o["min_res"]).reshape(L, G)
