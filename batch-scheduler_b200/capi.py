@@ -92,6 +92,8 @@ SYMBOLS = {
     "bs_evaluate_async": (C.c_int, [C.c_void_p]),
     "bs_sync": (C.c_int, [C.c_void_p]),
     "bs_fetch": (C.c_int, [C.c_void_p, _p(ResultsC)]),
+    "bs_fetch_view": (C.c_int, [C.c_void_p, _p(ResultsC)]),
+    "bs_evaluate_view": (C.c_int, [C.c_void_p, _p(ResultsC)]),
     "bs_prefilter": (C.c_int, [C.c_void_p, C.c_uint32, _p(StatusC)]),
     "bs_permit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(PermitResultC)]),
     "bs_less": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),

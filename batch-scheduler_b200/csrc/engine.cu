@@ -281,7 +281,8 @@ struct bs_engine {
   ClassIndex fit_index, rep_index;
   PinVec<uint32_t> h_pfc, h_prc, h_grc;   // pinned: DMA'd whenever the classes change
   cudaEvent_t ev_classes = nullptr;       // the last class-table DMA out of them
-  bool group_classes_dirty = true;
+  bool group_classes_dirty = true;   // every group's representative id has to be looked up again
+  bool group_ids_dirty = false;      // some ids in h_grc changed in place (bs_update_groups): DMA them again
   std::vector<int64_t> h_wait_ns;
   int64_t default_wait_ns = 0;
   // bits that differ between rows of each sort key word (a constant byte needs no radix pass)
@@ -291,6 +292,10 @@ struct bs_engine {
   uint64_t g_or1 = 0, g_and1 = ~0ull, g_or0 = 0, g_and0 = ~0ull;   // OR / AND of the group key words seen so far
   bool pod_classes_dirty = true;
   double last_classes_us = 0;
+  // BS_HOST_PROFILE: host-side segment times (label, us) since the last bs_evaluate, printed there
+  bool host_prof = false;
+  std::vector<std::pair<const char*, double>> hp_log;
+  std::chrono::steady_clock::time_point hp_t;
   // pinned result cache
   PinBuf h_prefilter, h_feasible, h_best_node, h_best_score, h_admit, h_admit_bitmap, h_new_denied,
       h_order, h_rank, h_state, h_filter_code;
@@ -374,6 +379,65 @@ void left_stats(const bs_node_table* t, uint32_t L, uint32_t n, uint64_t* or_out
     or_out[d] |= o;
     max_out[d] = std::max(max_out[d], mx);
   }
+}
+
+// Everything bs_upload_nodes needs from the host columns in ONE chunked pass (an omp team for big tables):
+// |value| maxima of alloc / requested (range check + lane classification), max |pod_count| and the
+// residual statistics of left_stats.
+struct NodeHostStats {
+  int64_t mx_a[BS_MAX_LANES] = {}, mx_r[BS_MAX_LANES] = {}, mx_l[BS_MAX_LANES] = {};
+  uint64_t or_l[BS_MAX_LANES] = {};
+  int64_t mx_pc = 0;
+  bool ok = true;
+};
+NodeHostStats node_host_pass(const bs_node_table* t, uint32_t L, uint32_t N) {
+  const int T = N < 4096 ? 1 : host_threads();
+  std::vector<NodeHostStats> part(T);
+  const uint32_t chunk = (N + T - 1) / std::max(T, 1);
+#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
+  for (int tk = 0; tk < T; ++tk) {
+    NodeHostStats st;
+    const uint32_t a0 = std::min(N, (uint32_t)tk * chunk), a1 = std::min(N, a0 + chunk);
+    for (uint32_t d = 0; d < L; ++d) {
+      const int64_t* al = t->alloc + (size_t)d * N;
+      const int64_t* rq = t->requested + (size_t)d * N;
+      int64_t alo = 0, ahi = 0, rlo = 0, rhi = 0, mx = 0;
+      uint64_t o = 0;
+      for (uint32_t i = a0; i < a1; ++i) {
+        alo = std::min(alo, al[i]); ahi = std::max(ahi, al[i]);
+        rlo = std::min(rlo, rq[i]); rhi = std::max(rhi, rq[i]);
+      }
+      for (uint32_t i = a0; i < a1; ++i) {   // left_stats' body
+        if (d >= 4 && !((t->alloc_present[i] & t->req_present[i]) >> d & 1u)) continue;
+        int64_t used = rq[i];
+        if (d == (uint32_t)LANE_PODS && used == 0) used = t->pod_count[i];
+        const int64_t v = (int64_t)((float)al[i] * 1.0f) - used;
+        o |= (uint64_t)v;
+        mx = std::max(mx, v < 0 ? -v : v);
+      }
+      st.ok = st.ok && alo >= -BS_VALUE_LIMIT && ahi <= BS_VALUE_LIMIT && rlo >= -BS_VALUE_LIMIT && rhi <= BS_VALUE_LIMIT;
+      st.mx_a[d] = std::max(ahi, alo == INT64_MIN ? INT64_MAX : -alo);
+      st.mx_r[d] = std::max(rhi, rlo == INT64_MIN ? INT64_MAX : -rlo);
+      st.or_l[d] = o;
+      st.mx_l[d] = mx;
+    }
+    int64_t pc = 0;
+    for (uint32_t i = a0; i < a1; ++i) pc = std::max<int64_t>(pc, std::abs((int64_t)t->pod_count[i]));
+    st.mx_pc = pc;
+    part[tk] = st;
+  }
+  NodeHostStats r;
+  for (int tk = 0; tk < T; ++tk) {
+    r.ok = r.ok && part[tk].ok;
+    r.mx_pc = std::max(r.mx_pc, part[tk].mx_pc);
+    for (uint32_t d = 0; d < L; ++d) {
+      r.mx_a[d] = std::max(r.mx_a[d], part[tk].mx_a[d]);
+      r.mx_r[d] = std::max(r.mx_r[d], part[tk].mx_r[d]);
+      r.mx_l[d] = std::max(r.mx_l[d], part[tk].mx_l[d]);
+      r.or_l[d] |= part[tk].or_l[d];
+    }
+  }
+  return r;
 }
 
 // Lane classification for the fit kernel (kernels.cuh "Narrow lanes"): lane d is narrow when every
@@ -491,16 +555,22 @@ struct DeviceGuard {
   DeviceGuard _guard((e)->device); \
   CK(_guard.err)
 
+// host-side segment timer (BS_HOST_PROFILE): HP_BEGIN at the top of an entry point, HP("what") after a segment
+#define HP_BEGIN(e) do { if ((e)->host_prof) (e)->hp_t = std::chrono::steady_clock::now(); } while (0)
+#define HP(e, label) do { if ((e)->host_prof) { const auto _n = std::chrono::steady_clock::now(); \
+    if ((e)->hp_log.size() > 4096) (e)->hp_log.clear(); (e)->hp_log.emplace_back(label, std::chrono::duration<double, std::micro>(_n - (e)->hp_t).count()); (e)->hp_t = _n; } } while (0)
+
 struct StageTimer {
   bs_engine* e;
   int k;
   cudaStream_t st;
-  StageTimer(bs_engine* e_, int k_, cudaStream_t st_) : e(e_), k(k_), st(st_) {
+  bool manual;   // the launcher records the two events itself (gang_fit: around the one kernel)
+  StageTimer(bs_engine* e_, int k_, cudaStream_t st_, bool manual_ = false) : e(e_), k(k_), st(st_), manual(manual_) {
     e->k_launches[k] = 0;
-    if (e->profiling) cudaEventRecord(e->ev_a[k], st);
+    if (e->profiling && !manual) cudaEventRecord(e->ev_a[k], st);
   }
   ~StageTimer() {
-    if (e->profiling) {
+    if (e->profiling && !manual) {
       cudaEventRecord(e->ev_b[k], st);
       e->k_valid[k] = true;
     }
@@ -546,10 +616,10 @@ void launch_replay(uint32_t L, const ReplayArgs& a, cudaStream_t s) {
   }
 }
 
-cudaError_t launch_fit(const FitArgs& a, uint32_t units, cudaStream_t s, uint32_t* launches) {
+cudaError_t launch_fit(const FitArgs& a, uint32_t units, cudaStream_t s, uint32_t* launches, cudaEvent_t ev_a, cudaEvent_t ev_b) {
   const int out = a.score ? FIT_OUT_SCORE : (a.fit_bitmap ? FIT_OUT_BITMAP : FIT_OUT_NONE);
   FitFn fn = fit_lookup(a.lm.LW, a.lm.LN, a.lm.LS, out);
-  return fn ? fn(a, units, s, launches) : cudaErrorInvalidValue;
+  return fn ? fn(a, units, s, launches, ev_a, ev_b) : cudaErrorInvalidValue;
 }
 
 inline uint32_t ctz64(uint64_t v) { return v ? (uint32_t)__builtin_ctzll(v) : 63u; }
@@ -634,7 +704,9 @@ int rebuild_classes(bs_engine* e) {
   // looked up here (the representative index must already hold the pods' (sel, tol) pairs so that
   // the ids agree).  Then the class tables go to the device.
   const uint32_t P = e->P, G = e->G;
+  HP_BEGIN(e);
   CK(cudaEventSynchronize(e->ev_classes));   // a previous DMA out of h_grc has finished
+  HP(e, "classes:event-wait");
   const bool groups_assigned = e->group_classes_dirty;
   if (e->group_classes_dirty) {
     if (!e->h_grc.resize(G)) return fail(e, BS_E_NOMEM, "pinned host memory");
@@ -644,13 +716,14 @@ int rebuild_classes(bs_engine* e) {
     assign_classes(e->rep_index, G, [=](uint32_t g) { return ClassKey{gs[g], gt[g], 0u, ga[g]}; }, e->h_grc.data());
     e->group_classes_dirty = false;
   }
+  HP(e, "classes:assign-groups");
   if (e->fit_index.size() == 0) e->fit_index.get_or_add(ClassKey{0, 0, 0, BS_AFF_NONE});
   if (e->rep_index.size() == 0) e->rep_index.get_or_add(ClassKey{0, 0, 0, BS_AFF_NONE});
   e->n_fit_classes = (uint32_t)e->fit_index.size();
   e->n_rep_classes = (uint32_t)e->rep_index.size();
   std::vector<uint64_t> fsel(e->n_fit_classes), ftol(e->n_fit_classes), rsel(e->n_rep_classes), rtol(e->n_rep_classes);
   std::vector<uint32_t> fnz(e->n_fit_classes), faff(e->n_fit_classes), raff(e->n_rep_classes);
-  bool aff_bad = false;
+  bool aff_bad = false, any_aff = false;
   for (uint32_t c = 0; c < e->n_fit_classes; ++c) {
     fsel[c] = e->fit_index.keys[c].sel; ftol[c] = e->fit_index.keys[c].tol; fnz[c] = e->fit_index.keys[c].nz;
     faff[c] = e->fit_index.keys[c].aff;
@@ -658,17 +731,23 @@ int rebuild_classes(bs_engine* e) {
   }
   for (uint32_t c = 0; c < e->n_rep_classes; ++c) {
     rsel[c] = e->rep_index.keys[c].sel; rtol[c] = e->rep_index.keys[c].tol; raff[c] = e->rep_index.keys[c].aff;
+    any_aff = any_aff || raff[c] != BS_AFF_NONE;
   }
-  // (stale representative classes may linger in the persistent index; only the classes in use are checked)
-  for (uint32_t p = 0; p < P && !aff_bad; ++p) {
-    const uint32_t a = e->rep_index.keys[e->h_prc[p]].aff;
-    aff_bad = a != BS_AFF_NONE && a >= e->n_aff;
+  // (stale representative classes may linger in the persistent index; only the classes in use are checked, and
+  // every pod / group has its representative class in that index: no affinity id there, nothing to check)
+  if (any_aff) {
+    for (uint32_t p = 0; p < P && !aff_bad; ++p) {
+      const uint32_t a = e->rep_index.keys[e->h_prc[p]].aff;
+      aff_bad = a != BS_AFF_NONE && a >= e->n_aff;
+    }
+    for (uint32_t g = 0; g < G && !aff_bad; ++g) aff_bad = e->h_gaff[g] != BS_AFF_NONE && e->h_gaff[g] >= e->n_aff;
   }
-  for (uint32_t g = 0; g < G && !aff_bad; ++g) aff_bad = e->h_gaff[g] != BS_AFF_NONE && e->h_gaff[g] >= e->n_aff;
   if (aff_bad) {
     if (groups_assigned) e->group_classes_dirty = true;   // their ids were not uploaded: assign again next time
+    // (group_ids_dirty stays set: an in-place change is uploaded by the next successful rebuild)
     return fail(e, BS_E_INDEX, "affinity class outside the uploaded table (bs_upload_affinity after bs_upload_nodes)");
   }
+  HP(e, "classes:tables+checks");
   int rc;
   // cudaMemcpyAsync from pageable memory returns once the data is staged, so the vectors may die.
   if ((rc = upload_vec(e, e->d_fsel, fsel.data(), e->n_fit_classes, e->n_fit_classes))) return rc;
@@ -682,8 +761,11 @@ int rebuild_classes(bs_engine* e) {
     if ((rc = upload_vec(e, e->d_pod_fit_class, e->h_pfc.data(), P, std::max(P, 1u)))) return rc;
     if ((rc = upload_vec(e, e->d_pod_rep_class, e->h_prc.data(), P, std::max(P, 1u)))) return rc;
   }
-  if (groups_assigned && (rc = upload_vec(e, e->d_group_rep_class, e->h_grc.data(), G, std::max(G, 1u)))) return rc;
+  if ((groups_assigned || e->group_ids_dirty) &&
+      (rc = upload_vec(e, e->d_group_rep_class, e->h_grc.data(), G, std::max(G, 1u)))) return rc;
+  e->group_ids_dirty = false;
   CK(cudaEventRecord(e->ev_classes, e->s));   // the pinned id arrays are read asynchronously from here on
+  HP(e, "classes:uploads");
   e->classes_dirty = false;
   e->pod_classes_dirty = false;
   return BS_OK;
@@ -945,7 +1027,7 @@ int evaluate_async_locked(bs_engine* e) {
   if (e->exp_mode == 2) { CK(cudaStreamWaitEvent(e->s, e->ev_join, 0)); CK(cudaStreamWaitEvent(e->s, e->ev_pre, 0)); }
   if (e->exp_mode == 3) CK(cudaStreamWaitEvent(e->s, e->ev_pre, 0));
   {
-    StageTimer tm(e, BS_K_GANG_FIT, e->s);
+    StageTimer tm(e, BS_K_GANG_FIT, e->s, true);
     if (P) {
       FitArgs a;
       a.left_w = e->d_left_w.as<int64_t>();
@@ -967,7 +1049,9 @@ int evaluate_async_locked(bs_engine* e) {
       a.P = P; a.N = e->N; a.Npad = e->Npad; a.W = e->W;
       a.best_packed = e->d_best_packed.as<unsigned long long>();
       uint32_t nl = 1;
-      CK(launch_fit(a, cdiv(P, PODS_PER_CTA), e->s, &nl));
+      CK(launch_fit(a, cdiv(P, PODS_PER_CTA), e->s, &nl, e->profiling ? e->ev_a[BS_K_GANG_FIT] : nullptr,
+                    e->profiling ? e->ev_b[BS_K_GANG_FIT] : nullptr));
+      if (e->profiling) e->k_valid[BS_K_GANG_FIT] = true;
       tm.launched(nl);
     }
   }
@@ -1040,15 +1124,17 @@ int evaluate_async_locked(bs_engine* e) {
   return BS_OK;
 }
 
-int fetch_locked(bs_engine* e, bs_results* out) {
+int fetch_locked(bs_engine* e, bs_results* out, bool view = false) {
   if (!e->evaluated) return fail(e, BS_E_STATE, "bs_fetch: nothing evaluated");
   const uint32_t P = e->P, G = e->G;
+  HP_BEGIN(e);
   if (!e->fetched) {
     if (e->arena_bytes)   // every decision vector in one DMA (the arena layout is the same on both sides)
       CK(cudaMemcpyAsync(e->h_arena.p, e->d_arena.p, e->arena_bytes, cudaMemcpyDeviceToHost, e->s));
     CK(cudaStreamSynchronize(e->s));
     e->fetched = true;
   }
+  HP(e, "fetch:d2h+wait");
   const RoundState* st = e->h_state.as<RoundState>();
   if (e->gang.active && e->gang.groups.size() == G && !e->gang_applied) {
     // AddToDenyCache for every group a pod of the round hit "cluster resource not enough" in (core.go:142,163)
@@ -1057,7 +1143,20 @@ int fetch_locked(bs_engine* e, bs_results* out) {
       if (nd[g]) e->gang.deny(g, e->cycle_now_ns);
     e->gang_applied = true;
   }
-  if (out) {
+  if (out && view) {
+    out->prefilter = e->h_prefilter.as<uint8_t>();
+    out->feasible_count = e->h_feasible.as<uint32_t>();
+    out->best_node = e->h_best_node.as<int32_t>();
+    out->best_score = e->h_best_score.as<int64_t>();
+    out->admit = e->h_admit.as<uint8_t>();
+    out->admit_bitmap = e->h_admit_bitmap.as<uint32_t>();
+    out->new_denied = e->h_new_denied.as<uint8_t>();
+    out->order = e->h_order.as<uint32_t>();
+    out->rank = e->h_rank.as<uint32_t>();
+    out->filter_code = (e->out_flags & BS_OUT_FILTER) ? e->h_filter_code.as<uint8_t>() : nullptr;
+    out->max_group = st->max_group;
+    out->max_finished = st->max_finished;
+  } else if (out) {
     auto cp = [](void* dst, const PinBuf& src, size_t bytes) {
       if (dst && bytes) memcpy(dst, src.p, bytes);
     };
@@ -1074,6 +1173,7 @@ int fetch_locked(bs_engine* e, bs_results* out) {
     out->max_finished = st->max_finished;
     if (e->out_flags & BS_OUT_FILTER) cp(out->filter_code, e->h_filter_code, P);
   }
+  HP(e, "fetch:copy-out");
   if (st->ref_panic)
     return fail(e, BS_E_REF_PANIC, "findMaxPG: MinMember == 0 with Status.Scheduled != 0 (core.go:716-717 divides by zero)");
   return BS_OK;
@@ -1123,6 +1223,7 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
   e->out_flags = cfg->out_flags;
   if (const char* ns = getenv("BS_NO_SCALED_LANES")) e->no_scaled_lanes = atoi(ns) != 0;
   if (const char* xm = getenv("BS_EXP_MODE")) e->exp_mode = atoi(xm);
+  e->host_prof = getenv("BS_HOST_PROFILE") != nullptr;
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the small kernels of the PreFilter chain must get the
                                                           // SM slots the fit kernel's retiring CTAs free
@@ -1213,14 +1314,10 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   if (N && (!t->alloc || !t->requested || !t->pod_count || !t->alloc_present || !t->req_present ||
             !t->label_mask || !t->taint_mask || !t->flags))
     return fail(e, BS_E_INVAL, "bs_upload_nodes: null column");
-  int64_t mx_a[BS_MAX_LANES] = {}, mx_r[BS_MAX_LANES] = {};
-  if (!lane_maxima(t->alloc, L, N, mx_a) || !lane_maxima(t->requested, L, N, mx_r))
-    return fail(e, BS_E_RANGE, "bs_upload_nodes: value outside +-2^56");
-  int64_t mx_pc = 0;
-  for (uint32_t i = 0; i < N; ++i) mx_pc = std::max<int64_t>(mx_pc, std::abs((int64_t)t->pod_count[i]));
-  uint64_t or_l[BS_MAX_LANES] = {};
-  int64_t mx_l[BS_MAX_LANES] = {};
-  left_stats(t, L, N, or_l, mx_l);
+  HP_BEGIN(e);
+  const NodeHostStats hs = node_host_pass(t, L, N);
+  if (!hs.ok) return fail(e, BS_E_RANGE, "bs_upload_nodes: value outside +-2^56");
+  HP(e, "nodes:host-pass");
   BS_DEVICE_GUARD(e);
   const uint32_t Npad = std::max(1u, cdiv(N, NODE_TILE)) * NODE_TILE;
   int rc;
@@ -1232,13 +1329,15 @@ int bs_upload_nodes(bs_engine* e, const bs_node_table* t) {
   if ((rc = upload_vec(e, e->d_label, t->label_mask, N, Npad))) return rc;
   if ((rc = upload_vec(e, e->d_taint, t->taint_mask, N, Npad))) return rc;
   if ((rc = upload_vec(e, e->d_nflags, t->flags, N, Npad))) return rc;
+  HP(e, "nodes:dma-enqueue");
   CK(cudaStreamSynchronize(e->s));
+  HP(e, "nodes:dma-wait");
   e->h_nflags.assign(t->flags, t->flags + N);
-  memcpy(e->max_alloc, mx_a, sizeof(mx_a));
-  memcpy(e->max_requested, mx_r, sizeof(mx_r));
-  memcpy(e->or_left, or_l, sizeof(or_l));
-  memcpy(e->max_left, mx_l, sizeof(mx_l));
-  e->max_pod_count = mx_pc;
+  memcpy(e->max_alloc, hs.mx_a, sizeof(hs.mx_a));
+  memcpy(e->max_requested, hs.mx_r, sizeof(hs.mx_r));
+  memcpy(e->or_left, hs.or_l, sizeof(hs.or_l));
+  memcpy(e->max_left, hs.mx_l, sizeof(hs.mx_l));
+  e->max_pod_count = hs.mx_pc;
   e->N = N;
   e->score_pitch = (N + 1u) & ~1u;
   e->bitmap_pitch = (cdiv(N, 32) + 31u) & ~31u;
@@ -1268,6 +1367,7 @@ int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t) {
   if (!lane_maxima(t->alloc, L, n, mx_a) || !lane_maxima(t->requested, L, n, mx_r))
     return fail(e, BS_E_RANGE, "bs_update_nodes: value outside +-2^56");
   BS_DEVICE_GUARD(e);
+  HP_BEGIN(e);
   // scratch of the changed rows: kept in the engine (cudaMalloc / cudaFree per call would cost more than the scatter)
   DevBuf &da = e->u_buf[0], &dr = e->u_buf[1], &dpc = e->u_buf[2], &dap = e->u_buf[3], &drp = e->u_buf[4], &dl = e->u_buf[5],
          &dt = e->u_buf[6], &df = e->u_buf[7], &di = e->u_buf[8];
@@ -1297,9 +1397,11 @@ int bs_update_nodes(bs_engine* e, const uint32_t* idx, const bs_node_table* t) {
     src.taint = dt.as<uint64_t>(); src.flags = df.as<uint8_t>();
     node_scatter_kernel<<<cdiv(n, 256), 256, 0, e->s>>>(dst, e->Npad, L, src, di.as<uint32_t>(), n);
     e->launches++;
+    HP(e, "upd-nodes:enqueue");
     er = cudaStreamSynchronize(e->s);
   }
   CK(er);
+  HP(e, "upd-nodes:wait");
   // lane maxima only ever grow here (a conservative bound keeps the wide/narrow split exact); the OR
   // of the residuals only gains bits (fewer common trailing zeros: a smaller unit, still exact)
   left_stats(t, L, n, e->or_left, e->max_left);
@@ -1327,6 +1429,7 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   // the DMAs go first (asynchronous from pinned tables) and run under the host checks below; a table
   // that then fails validation is dropped (have_groups = false)
   BS_DEVICE_GUARD(e);
+  HP_BEGIN(e);
   e->have_groups = false;
   e->evaluated = false;
   const uint32_t Gp = std::max(G, 1u);
@@ -1339,20 +1442,48 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   if ((rc = upload_vec(e, e->d_mrpres, t->min_res_present, G, Gp))) return rc;
   if ((rc = upload_vec(e, e->d_creation, t->creation_ns, G, Gp))) return rc;
   if ((rc = upload_vec(e, e->d_name_rank, t->name_rank, G, Gp))) return rc;
+  HP(e, "groups:dma-enqueue");
+  // one chunked pass over the host columns (an omp team for big tables): |min_res| range, the varying bits of the
+  // sort-key words, creation sentinel, and whether the representative columns moved since their ids were assigned
+  uint64_t o1 = 0, a1 = ~0ull, o0 = 0, a0 = ~0ull;
+  int bad_creation = 0, bad_range = 0, reps_differ = 0;
   {
-    int64_t mx[BS_MAX_LANES] = {};
-    if (!lane_maxima(t->min_res, L, G, mx)) {
-      cudaStreamSynchronize(e->s);
-      return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
+    const bool cmp_reps = e->h_gsel.size() == G && e->h_gtol.size() == G && e->h_grc.size() == G && e->h_gaff.size() == G;
+    if (!cmp_reps) reps_differ = 1;
+    const int T = G < 8192 ? 1 : host_threads();
+    const uint32_t chunk = (G + T - 1) / std::max(T, 1);
+    const uint64_t* hs = e->h_gsel.data();
+    const uint64_t* ht = e->h_gtol.data();
+    const uint32_t* ha = e->h_gaff.data();
+#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1) reduction(| : o1, o0, bad_creation, bad_range, reps_differ) reduction(& : a1, a0)
+    for (int tk = 0; tk < T; ++tk) {
+      const uint32_t g0 = std::min(G, (uint32_t)tk * chunk), g1 = std::min(G, g0 + chunk);
+      for (uint32_t d = 0; d < L; ++d) {
+        const int64_t* row = t->min_res + (size_t)d * G;
+        int64_t lo = 0, hi = 0;
+        for (uint32_t g = g0; g < g1; ++g) { lo = std::min(lo, row[g]); hi = std::max(hi, row[g]); }
+        bad_range |= (lo < -BS_VALUE_LIMIT || hi > BS_VALUE_LIMIT) ? 1 : 0;
+      }
+      uint64_t lo1 = 0, la1 = ~0ull, lo0 = 0, la0 = ~0ull;
+      int bc = 0;
+      for (uint32_t g = g0; g < g1; ++g) {
+        const uint64_t c = (uint64_t)t->creation_ns[g], nm = (uint64_t)(~t->name_rank[g]);
+        lo1 |= c; la1 &= c; lo0 |= nm; la0 &= nm;
+        bc |= t->creation_ns[g] == INT64_MAX ? 1 : 0;
+      }
+      o1 |= lo1; a1 &= la1; o0 |= lo0; a0 &= la0; bad_creation |= bc;
+      if (cmp_reps && g1 > g0) {
+        int df = memcmp(hs + g0, t->rep_sel + g0, (size_t)(g1 - g0) * 8) != 0 || memcmp(ht + g0, t->rep_tol + g0, (size_t)(g1 - g0) * 8) != 0;
+        if (t->rep_aff_class) df = df || memcmp(ha + g0, t->rep_aff_class + g0, (size_t)(g1 - g0) * 4) != 0;
+        else
+          for (uint32_t g = g0; g < g1 && !df; ++g) df = ha[g] != BS_AFF_NONE;
+        reps_differ |= df;
+      }
     }
   }
-  uint64_t o1 = 0, a1 = ~0ull, o0 = 0, a0 = ~0ull;
-  int bad_creation = 0;
-#pragma omp parallel for reduction(| : o1, o0, bad_creation) reduction(& : a1, a0) if (G > 65536) num_threads(host_threads())
-  for (uint32_t g = 0; g < G; ++g) {
-    const uint64_t c = (uint64_t)t->creation_ns[g], nm = (uint64_t)(~t->name_rank[g]);
-    o1 |= c; a1 &= c; o0 |= nm; a0 &= nm;
-    bad_creation |= t->creation_ns[g] == INT64_MAX ? 1 : 0;
+  if (bad_range) {
+    cudaStreamSynchronize(e->s);
+    return fail(e, BS_E_RANGE, "bs_upload_groups: value outside +-2^56");
   }
   if (bad_creation) {
     cudaStreamSynchronize(e->s);
@@ -1361,12 +1492,8 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
   e->vary_creation = G ? (o1 ^ a1) : 0;
   e->vary_name = G ? (o0 ^ a0) : 0;
   e->g_or1 = o1; e->g_and1 = a1; e->g_or0 = o0; e->g_and0 = a0;
-  // representative (sel, tol) columns unchanged since the ids were assigned: nothing to look up again
-  bool same_reps = e->h_gsel.size() == G && e->h_gtol.size() == G && e->h_grc.size() == G && e->h_gaff.size() == G &&
-                   (G == 0 || (memcmp(e->h_gsel.data(), t->rep_sel, (size_t)G * 8) == 0 &&
-                               memcmp(e->h_gtol.data(), t->rep_tol, (size_t)G * 8) == 0));
-  for (uint32_t g = 0; g < G && same_reps; ++g)
-    same_reps = e->h_gaff[g] == (t->rep_aff_class ? t->rep_aff_class[g] : BS_AFF_NONE);
+  // representative (sel, tol, affinity) columns unchanged since the ids were assigned: nothing to look up again
+  const bool same_reps = !reps_differ;
   if (!same_reps) {
     e->h_gsel.assign(t->rep_sel, t->rep_sel + G);
     e->h_gtol.assign(t->rep_tol, t->rep_tol + G);
@@ -1376,11 +1503,14 @@ int bs_upload_groups(bs_engine* e, const bs_group_table* t) {
     e->classes_dirty = true;
   }
   if (e->h_wait_ns.size() != G) e->h_wait_ns.assign(G, -1);
+  HP(e, "groups:host-pass");
   CK(cudaStreamSynchronize(e->s));   // the caller's arrays are free again once we return
+  HP(e, "groups:dma-wait");
   e->h_min_member.assign(t->min_member, t->min_member + G);
   e->h_scheduled.assign(t->scheduled, t->scheduled + G);
   e->h_matched_up.assign(t->matched, t->matched + G);
   e->h_gflags_up.assign(t->flags, t->flags + G);
+  HP(e, "groups:host-copies");
   e->G = G;
   e->have_groups = true;
   e->evaluated = false;
@@ -1406,6 +1536,7 @@ int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t)
   for (uint32_t k = 0; k < n; ++k)
     if (t->creation_ns[k] == INT64_MAX) return fail(e, BS_E_RANGE, "bs_update_groups: creation_ns == INT64_MAX");
   BS_DEVICE_GUARD(e);
+  HP_BEGIN(e);
   DevBuf &dmm = e->u_buf[0], &dsc = e->u_buf[1], &dma = e->u_buf[2], &dfl = e->u_buf[3], &dmr = e->u_buf[4], &dmp = e->u_buf[5],
          &dcr = e->u_buf[6], &dnr = e->u_buf[7], &di = e->u_buf[8];
   cudaError_t er = dmm.ensure((size_t)n * 4);
@@ -1431,9 +1562,11 @@ int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t)
                   dmp.as<uint32_t>(), dcr.as<int64_t>(), dnr.as<uint32_t>()};
     group_scatter_kernel<<<cdiv(n, 256), 256, 0, e->s>>>(dst, std::max(G, 1u), L, src, di.as<uint32_t>(), n);
     e->launches++;
+    HP(e, "upd-groups:enqueue");
     er = cudaStreamSynchronize(e->s);
   }
   CK(er);
+  HP(e, "upd-groups:wait");
   // sort-key digits that vary: the accumulated OR / AND only widen (a superset costs a pass, never an error)
   for (uint32_t k = 0; k < n; ++k) {
     const uint64_t c = (uint64_t)t->creation_ns[k], nm = (uint64_t)(~t->name_rank[k]);
@@ -1448,8 +1581,16 @@ int bs_update_groups(bs_engine* e, const uint32_t* idx, const bs_group_table* t)
   }
   e->vary_creation = e->g_or1 ^ e->g_and1;
   e->vary_name = e->g_or0 ^ e->g_and0;
-  e->classes_dirty = true;         // representative classes are looked up again; the pods' ids stay
-  e->group_classes_dirty = true;
+  e->classes_dirty = true;         // the class tables go to the device again (new classes may have appeared); the pods' ids stay
+  if (!e->group_classes_dirty && e->h_grc.size() == G) {
+    // the other groups' ids are current: look up only the changed rows (the index keeps ids stable)
+    CK(cudaEventSynchronize(e->ev_classes));   // no DMA is reading h_grc
+    for (uint32_t k = 0; k < n; ++k)
+      e->h_grc[idx[k]] = e->rep_index.get_or_add(ClassKey{e->h_gsel[idx[k]], e->h_gtol[idx[k]], 0u, e->h_gaff[idx[k]]});
+    e->group_ids_dirty = true;
+  } else {
+    e->group_classes_dirty = true;
+  }
   e->evaluated = false;
   return BS_OK;
 }
@@ -1477,6 +1618,7 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
     ClassIndex fit, rep;
   };
   std::vector<Part> part(T);
+  HP_BEGIN(e);
   e->h_gid.resize(P); e->h_prio.resize(P); e->h_pflags.resize(P);
   BS_DEVICE_GUARD(e);
   CK(cudaEventSynchronize(e->ev_classes));   // the class ids of the previous table are no longer being read
@@ -1493,14 +1635,13 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
   if ((rc = upload_vec(e, e->d_prio, t->priority, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_ts, t->ts_ns, P, Pp))) return rc;
   if ((rc = upload_vec(e, e->d_pflags, t->flags, P, Pp))) return rc;
+  HP(e, "pods:dma-enqueue");
   // T fixed chunks handed out by an omp for: a team smaller than requested still covers every chunk
   const uint32_t chunk = (P + T - 1) / std::max(T, 1);
 #pragma omp parallel for schedule(static, 1) num_threads(T)
   for (int tk = 0; tk < T; ++tk) {
     Part& pt = part[tk];
     for (uint32_t d = 0; d < BS_MAX_LANES; ++d) { pt.lo[d] = 0; pt.hi[d] = 0; pt.orq[d] = 0; }
-    pt.fit.clear();
-    pt.rep.clear();
     const uint32_t a0 = std::min(P, (uint32_t)tk * chunk), a1 = std::min(P, a0 + chunk);
     for (uint32_t d = 0; d < L; ++d) {
       const int64_t* row = t->req + (size_t)d * P;
@@ -1509,24 +1650,52 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       for (uint32_t p = a0; p < a1; ++p) { lo = std::min(lo, row[p]); hi = std::max(hi, row[p]); o |= (uint64_t)row[p]; }
       pt.lo[d] = lo; pt.hi[d] = hi; pt.orq[d] = o;
     }
-    for (uint32_t p = a0; p < a1; ++p) {
-      const uint64_t ts = (uint64_t)t->ts_ns[p];
-      const uint32_t pr = (uint32_t)t->priority[p];
-      const int32_t g = t->gid[p];
-      const uint8_t fl = t->flags[p];
-      pt.ot |= ts; pt.at &= ts; pt.op |= pr; pt.apr &= pr;
-      pt.miss |= ((g < BS_GID_NONE) || (fl & BS_POD_LISTER_MISS)) ? 1 : 0;
-      pt.mg = std::max(pt.mg, g);
-      e->h_gid[p] = g; e->h_prio[p] = (int32_t)pr; e->h_pflags[p] = fl;
-      uint32_t nz = 0;
-      const uint32_t rp = t->req_present[p];
-      for (uint32_t d = 4; d < L; ++d)
-        if (((rp >> d) & 1u) && t->req[(size_t)d * P + p] != 0) nz |= 1u << d;
-      const uint32_t af = t->aff_class ? t->aff_class[p] : BS_AFF_NONE;
-      e->h_pfc[p] = pt.fit.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], nz, af});
-      e->h_prc[p] = pt.rep.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], 0u, af});
+    {
+      // reductions in locals and the plain column copies as memcpy: a byte store inside the loop would make the
+      // compiler spill every accumulator (char stores alias everything)
+      uint64_t ot = 0, at = ~0ull;
+      uint32_t op = 0, apr = ~0u;
+      int miss = 0;
+      int32_t mg = -1;
+      for (uint32_t p = a0; p < a1; ++p) {
+        const uint64_t ts = (uint64_t)t->ts_ns[p];
+        const uint32_t pr = (uint32_t)t->priority[p];
+        const int32_t g = t->gid[p];
+        ot |= ts; at &= ts; op |= pr; apr &= pr;
+        miss |= ((g < BS_GID_NONE) || (t->flags[p] & BS_POD_LISTER_MISS)) ? 1 : 0;
+        mg = std::max(mg, g);
+      }
+      pt.ot = ot; pt.at = at; pt.op = op; pt.apr = apr; pt.miss = miss; pt.mg = mg;
+      if (a1 > a0) {
+        memcpy(e->h_gid.data() + a0, t->gid + a0, (size_t)(a1 - a0) * 4);
+        memcpy(e->h_prio.data() + a0, t->priority + a0, (size_t)(a1 - a0) * 4);
+        memcpy(e->h_pflags.data() + a0, t->flags + a0, (size_t)(a1 - a0));
+      }
+    }
+    {
+      // one index lookup per pod: the representative class of a fit class is looked up once per class
+      ClassIndex fit, rep;
+      fit.clear();
+      rep.clear();
+      std::vector<uint32_t> rep_of_fit;
+      uint32_t* pfc = e->h_pfc.data();
+      uint32_t* prc = e->h_prc.data();
+      for (uint32_t p = a0; p < a1; ++p) {
+        uint32_t nz = 0;
+        const uint32_t rp = t->req_present[p];
+        for (uint32_t d = 4; d < L; ++d)
+          if (((rp >> d) & 1u) && t->req[(size_t)d * P + p] != 0) nz |= 1u << d;
+        const uint32_t af = t->aff_class ? t->aff_class[p] : BS_AFF_NONE;
+        const uint32_t fc = fit.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], nz, af});
+        if (fc >= rep_of_fit.size()) rep_of_fit.push_back(rep.get_or_add(ClassKey{t->sel_mask[p], t->tol_mask[p], 0u, af}));
+        pfc[p] = fc;
+        prc[p] = rep_of_fit[fc];
+      }
+      pt.fit = std::move(fit);
+      pt.rep = std::move(rep);
     }
   }
+  HP(e, "pods:host-pass");
   int64_t mx_q[BS_MAX_LANES] = {}, neg_q[BS_MAX_LANES] = {};
   uint64_t or_q[BS_MAX_LANES] = {};
   {
@@ -1583,7 +1752,9 @@ int bs_upload_pods(bs_engine* e, const bs_pod_table* t) {
       }
     }
   }
+  HP(e, "pods:class-merge");
   CK(cudaStreamSynchronize(e->s));
+  HP(e, "pods:dma-wait");
   memcpy(e->max_req, mx_q, sizeof(mx_q));
   memcpy(e->neg_req, neg_q, sizeof(neg_q));
   memcpy(e->or_req, or_q, sizeof(or_q));
@@ -1836,6 +2007,22 @@ int bs_fetch(bs_engine* e, bs_results* out) {
   return fetch_locked(e, out);
 }
 
+int bs_fetch_view(bs_engine* e, bs_results* out) {
+  if (!e || !out) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  BS_DEVICE_GUARD(e);
+  return fetch_locked(e, out, true);
+}
+
+int bs_evaluate_view(bs_engine* e, bs_results* out) {
+  if (!e || !out) return BS_E_INVAL;
+  std::lock_guard<std::mutex> lk(e->mu);
+  int rc = evaluate_async_locked(e);
+  if (rc) return rc;
+  BS_DEVICE_GUARD(e);
+  return fetch_locked(e, out, true);
+}
+
 int bs_evaluate(bs_engine* e, bs_results* out) {
   if (!e) return BS_E_INVAL;
   std::lock_guard<std::mutex> lk(e->mu);
@@ -1855,8 +2042,11 @@ int bs_evaluate(bs_engine* e, bs_results* out) {
   auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double, std::micro>(b - a).count();
   };
-  fprintf(stderr, "[bs_evaluate] enqueue %.0f us (classes %.0f us)  device wait %.0f us  fetch %.0f us\n", us(t0, t1),
+  fprintf(stderr, "[bs_evaluate] enqueue %.0f us (classes %.0f us)  device wait %.0f us  fetch %.0f us |", us(t0, t1),
           e->last_classes_us, us(t1, t2), us(t2, t3));
+  for (auto& kv : e->hp_log) fprintf(stderr, " %s %.0f", kv.first, kv.second);
+  fprintf(stderr, "\n");
+  e->hp_log.clear();
   return rc;
 }
 

@@ -557,7 +557,9 @@ static __global__ void fit_unpack_kernel(const unsigned long long* __restrict__ 
 namespace bsk {
 // launches gang_fit_kernel over `units` CTA units (tail units split, see FitArgs); *launches gets the number of
 // kernels launched (1, or 2 with the unpack kernel)
-using FitFn = cudaError_t (*)(const FitArgs&, uint32_t units, cudaStream_t, uint32_t* launches);   // one per (shape, FIT_OUT_*)
+// ev_a / ev_b (null = none) are recorded right around the gang_fit_kernel launch itself, inside the tail's memsets
+// and unpack kernel: the stage time the roofline uses is that one kernel's duration
+using FitFn = cudaError_t (*)(const FitArgs&, uint32_t units, cudaStream_t, uint32_t* launches, cudaEvent_t ev_a, cudaEvent_t ev_b);   // one per (shape, FIT_OUT_*)
 constexpr int FIT_MAX_LN = 8;
 constexpr int FIT_N_SLICES = FIT_MAX_LN + 1;
 struct FitWS { int lw, ls; };

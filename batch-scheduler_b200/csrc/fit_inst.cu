@@ -13,7 +13,7 @@ namespace bsk {
 namespace {
 
 template <int LW, int LN, int LS, int OUT>
-cudaError_t launch_fit_t(const FitArgs& a0, uint32_t units, cudaStream_t s, uint32_t* launches) {
+cudaError_t launch_fit_t(const FitArgs& a0, uint32_t units, cudaStream_t s, uint32_t* launches, cudaEvent_t ev_a, cudaEvent_t ev_b) {
   const size_t smem = gang_fit_smem_bytes(LW, LN, LS, OUT == FIT_OUT_SCORE);
   // per launch, not cached: the attribute is per device and one process may drive several GPUs
   cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<LW, LN, LS, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -49,7 +49,9 @@ cudaError_t launch_fit_t(const FitArgs& a0, uint32_t units, cudaStream_t s, uint
       if (er != cudaSuccess) return er;
     }
   }
+  if (ev_a) cudaEventRecord(ev_a, s);
   gang_fit_kernel<LW, LN, LS, OUT><<<a.n_full + tail_units * a.tail_split, FIT_THREADS, smem, s>>>(a);
+  if (ev_b) cudaEventRecord(ev_b, s);
   if (launches) *launches = 1;
   if (a.tail_split > 1) {
     const uint32_t p0 = a.n_full * PODS_PER_CTA;

@@ -27,8 +27,8 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_MAX_PASSES = 16;
-// register budget: 65536 / (256 * 6) -> 40 per thread, what two 288-thread, 96-register gang_fit CTAs leave free
-constexpr int SORT_MIN_CTAS = 6;
+// register budget: 65536 / (256 * 8) = 32 per thread; two 288-thread, 96-register gang_fit CTAs leave 10240 free
+constexpr int SORT_MIN_CTAS = 8;
 
 struct SortPass {
   uint8_t word;   // 0: k0, 1: k1

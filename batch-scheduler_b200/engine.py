@@ -149,7 +149,36 @@ class Engine:
                         np.zeros(P, np.uint8) if (self.out_flags & capi.OUT_FILTER) else None)
         return r
 
-    def evaluate(self, out=None) -> RoundResult:
+    def _view_results(self, c) -> RoundResult:
+        """RoundResult whose arrays ARE the engine's pinned decision arena (bs_fetch_view): read-only, valid until
+        the next evaluate / upload / update on this engine.  The numpy wrappers are cached per arena layout."""
+        P, G = self.P, self.G
+        key = (c.prefilter, c.feasible_count, c.best_node, c.best_score, c.admit, c.admit_bitmap, c.new_denied,
+               c.order, c.rank, c.filter_code, P, G)
+        if getattr(self, "_view_key", None) != key:
+            def arr(addr, n, dt):
+                dt = np.dtype(dt)
+                if not addr or n == 0:
+                    return np.zeros(0, dt)
+                a = np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(addr), dtype=dt)
+                a.flags.writeable = False
+                return a
+            self._view = RoundResult(arr(c.prefilter, P, np.uint8), arr(c.feasible_count, P, np.uint32),
+                                     arr(c.best_node, P, np.int32), arr(c.best_score, P, np.int64),
+                                     arr(c.admit, G, np.uint8), arr(c.admit_bitmap, (G + 31) // 32, np.uint32),
+                                     arr(c.new_denied, G, np.uint8), arr(c.order, P, np.uint32), arr(c.rank, P, np.uint32),
+                                     -1, 0, arr(c.filter_code, P, np.uint8) if c.filter_code else None)
+            self._view_key = key
+        self._view.max_group, self._view.max_finished = int(c.max_group), int(c.max_finished)
+        return self._view
+
+    def evaluate(self, out=None, view=False) -> RoundResult:
+        """One round.  view=True returns the decision vectors in place (zero-copy views of the engine's pinned arena,
+        read-only, overwritten by the next round) instead of copies."""
+        if view:
+            c = capi.ResultsC()
+            self._check(self.lib.bs_evaluate_view(self.h, C.byref(c)))
+            return self._view_results(c)
         r, c = self._alloc_results(out)
         self._check(self.lib.bs_evaluate(self.h, C.byref(c)))
         r.max_group, r.max_finished = int(c.max_group), int(c.max_finished)
@@ -161,7 +190,11 @@ class Engine:
     def sync(self):
         self._check(self.lib.bs_sync(self.h))
 
-    def fetch(self, out=None) -> RoundResult:
+    def fetch(self, out=None, view=False) -> RoundResult:
+        if view:
+            c = capi.ResultsC()
+            self._check(self.lib.bs_fetch_view(self.h, C.byref(c)))
+            return self._view_results(c)
         r, c = self._alloc_results(out)
         self._check(self.lib.bs_fetch(self.h, C.byref(c)))
         r.max_group, r.max_finished = int(c.max_group), int(c.max_finished)

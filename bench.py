@@ -701,7 +701,7 @@ def main():
     res = None
     for _ in range(2):
         eng.upload(snap)
-        res = eng.evaluate()
+        res = eng.evaluate(view=True)
     H.full_sync(eng)
     t0 = time.perf_counter()
     e2e_steps = max(3, min(steps_req, 30))   # wall clock with host passes in it: enough steps to ride out jitter
@@ -710,7 +710,7 @@ def main():
         ta = time.perf_counter(); eng.upload_nodes(snap.nodes)
         tb = time.perf_counter(); eng.upload_groups(snap.groups)
         tc = time.perf_counter(); eng.upload_pods(snap.pods)
-        td = time.perf_counter(); res = eng.evaluate(out=res)
+        td = time.perf_counter(); res = eng.evaluate(view=True)   # bs_evaluate_view: one D2H into the pinned arena, read in place
         te_ = time.perf_counter()
         br["upload_nodes"] += tb - ta; br["upload_groups"] += tc - tb; br["upload_pods"] += td - tc
         br["evaluate_fetch"] += te_ - td
@@ -740,10 +740,10 @@ def main():
                              snap.groups.rep_sel[gi], snap.groups.rep_tol[gi], snap.groups.creation_ns[gi],
                              snap.groups.name_rank[gi])
         for _ in range(3):
-            eng.update_nodes(ni, nrows); eng.update_groups(gi, grows); res = eng.evaluate(out=res)
+            eng.update_nodes(ni, nrows); eng.update_groups(gi, grows); res = eng.evaluate(view=True)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            eng.update_nodes(ni, nrows); eng.update_groups(gi, grows); res = eng.evaluate(out=res)
+            eng.update_nodes(ni, nrows); eng.update_groups(gi, grows); res = eng.evaluate(view=True)
         dd = time.perf_counter() - t0
         e2e_delta = {"ms_per_step": dd / e2e_steps * 1e3, "value": float(P) * N * e2e_steps / dd, "unit": UNIT,
                      "steps": e2e_steps, "changed_nodes": int(nn), "changed_groups": int(ng),
@@ -751,8 +751,8 @@ def main():
                                                sum(getattr(grows, f).nbytes for f in grows.__dataclass_fields__
                                                    if getattr(grows, f) is not None) + gi.nbytes),
                      "d2h_bytes_per_step": int(d2h),
-                     "what": "bs_update_nodes + bs_update_groups (1 % of the rows each) + bs_evaluate with the fetch of "
-                             "every decision vector, wall clock"}
+                     "what": "bs_update_nodes + bs_update_groups (1 % of the rows each) + bs_evaluate_view (one D2H of every "
+                             "decision vector into the engine's pinned arena, read in place), wall clock"}
     if use_p2p:
         dist.barrier()
         eng.peer_detach()
@@ -822,8 +822,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
                     "breakdown_ms": {k: v / e2e_steps * 1e3 for k, v in br.items()},
-                    "what": "bs_upload_nodes/groups/pods from pinned host tables + bs_evaluate (D2H of all decision "
-                            "vectors) per step, wall clock"},
+                    "what": "bs_upload_nodes/groups/pods from pinned host tables + bs_evaluate_view (one D2H of all decision "
+                            "vectors into the engine's pinned arena, read in place) per step, wall clock"},
             "e2e_delta": e2e_delta,
             "e2e_objects": objects,
             "gpu_launches": int(round(launches_per_step * head["steps"])),

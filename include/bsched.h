@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 5
+#define BS_ABI_VERSION 6
 #define BS_FIXED_LANES 4
 #define BS_MAX_LANES 16
 /* |value| bound accepted for every int64 table entry (validated at upload):
@@ -265,6 +265,13 @@ int bs_evaluate(bs_engine* e, bs_results* out);
 int bs_evaluate_async(bs_engine* e);       /* enqueue the kernels, no host sync */
 int bs_sync(bs_engine* e);                 /* wait for the engine stream        */
 int bs_fetch(bs_engine* e, bs_results* out);
+/* bs_fetch without the copy: waits for the round, brings every decision vector to the host in one DMA and POINTS the
+ * array fields of *out into the engine's pinned decision arena (filter_code: null without BS_OUT_FILTER).  The
+ * pointers and their contents stay valid until the next bs_evaluate* / bs_upload_* / bs_update_* / bs_destroy on
+ * this engine; the caller must not write through them.  (A scheduler reads the verdicts once per cycle: copying
+ * 2.6 MB out of the arena costs as much as the DMA that filled it.) */
+int bs_evaluate_view(bs_engine* e, bs_results* out);
+int bs_fetch_view(bs_engine* e, bs_results* out);
 
 /* ---- per-call mirrors answering from the last evaluation ---- */
 /* batchSchedulingPlugin.PreFilter  (batchscheduler.go:102-108) */
@@ -426,7 +433,8 @@ typedef enum {
   BS_K_FIND_MAX = 1,
   BS_K_CLASS_PREFIX = 2,
   BS_K_PREFILTER = 3,
-  BS_K_GANG_FIT = 4,   /* the dominant kernel: fit predicate + score + gang admit */
+  BS_K_GANG_FIT = 4,   /* the dominant kernel: gang_fit_kernel alone (events right around its launch; the tail's memsets and
+                          unpack kernel and gang_admit are counted in its launches, not in its time) */
   BS_K_SORT = 5,
   BS_K_FILTER = 6,     /* optional Filter matrix (BS_OUT_FILTER) */
   BS_K_PEER = 7,       /* admit-bitmap exchange over peer memory */

@@ -565,3 +565,24 @@ def test_affinity_semantics(pkg, oracle):
             eng.evaluate()
     finally:
         eng.close()
+
+
+def test_view_results_match_copies(pkg, oracle, snapshot_mod):
+    """bs_evaluate_view / bs_fetch_view: the zero-copy decision vectors (pointers into the engine's pinned arena)
+    hold exactly what bs_evaluate copies out, round after round, also after the tables change shape."""
+    fields = ("prefilter", "feasible_count", "best_node", "best_score", "admit", "admit_bitmap", "new_denied", "order", "rank")
+    eng = pkg.Engine(5, 0, fit_bitmap=True, score=True)
+    for seed, (P, N, G) in enumerate([(300, 700, 25), (300, 700, 25), (90, 130, 7)]):
+        snap = random_snapshot(8800 + seed, P=P, N=N, G=G, L=5)
+        eng.upload(snap)
+        v = eng.evaluate(view=True)
+        orc = oracle.round(snap, want_bitmap=True, want_score=True)
+        assert_round_equal(v, eng.fit_rows(), eng.score_rows(), orc)
+        assert not v.prefilter.flags.writeable
+        c = eng.fetch()            # the copying call answers from the same round
+        v2 = eng.fetch(view=True)
+        for f in fields:
+            assert np.array_equal(getattr(v, f), getattr(c, f)), f
+            assert np.array_equal(getattr(v2, f), getattr(c, f)), f
+        assert (v.max_group, v.max_finished) == (c.max_group, c.max_finished)
+    eng.close()
