@@ -1855,7 +1855,7 @@ int bs_begin_cycle(bs_engine* e, int64_t now_ns) {
     if (e->gang.denied(g, now_ns)) f |= BS_GROUP_DENIED;
     gfl[g] = f;
   }
-  const bool ids = e->h_pod_uid.size() == P;
+  const bool ids = e->h_pod_uid.size() == P && !e->gang.permitted.empty();   // an empty lastPermittedPod: no lookups
   for (uint32_t p = 0; p < P; ++p) {
     uint8_t f = e->h_pflags[p] & ~(uint8_t)BS_POD_PERMITTED_RECENTLY;
     if (ids && e->gang.permitted_recently(e->h_pod_uid[p], now_ns)) f |= BS_POD_PERMITTED_RECENTLY;
