@@ -90,6 +90,32 @@ func (e *Engine) BeginCycle(now time.Time) error { return e.rc(C.bs_begin_cycle(
 // decisions and the queue order, in one call.
 func (e *Engine) Evaluate() error { return e.rc(C.bs_evaluate(e.h, nil)) }
 
+// Round is the whole round read in place: slices over the engine's pinned decision arena (bs_evaluate_view), valid
+// until the next Evaluate* / Upload* / Update* on this engine.  Nothing is copied; do not write through them.
+type Round struct {
+	PreFilter []uint8  // BS_PF_* per pending pod
+	Feasible  []uint32 // nodes each pod fits on
+	BestNode  []int32  // highest-score node, -1 = none
+	Admit     []uint8  // per PodGroup: the gang reaches minMember this round
+	Order     []uint32 // queue order (Compare, core.go:368-411)
+	Rank      []uint32 // dense rank of each pod in that order
+}
+
+func (e *Engine) EvaluateView(nPods, nGroups int) (Round, error) {
+	var r C.bs_results
+	if err := e.rc(C.bs_evaluate_view(e.h, &r)); err != nil {
+		return Round{}, err
+	}
+	return Round{
+		PreFilter: unsafe.Slice((*uint8)(unsafe.Pointer(r.prefilter)), nPods),
+		Feasible:  unsafe.Slice((*uint32)(unsafe.Pointer(r.feasible_count)), nPods),
+		BestNode:  unsafe.Slice((*int32)(unsafe.Pointer(r.best_node)), nPods),
+		Admit:     unsafe.Slice((*uint8)(unsafe.Pointer(r.admit)), nGroups),
+		Order:     unsafe.Slice((*uint32)(unsafe.Pointer(r.order)), nPods),
+		Rank:      unsafe.Slice((*uint32)(unsafe.Pointer(r.rank)), nPods),
+	}, nil
+}
+
 // PreFilter mirrors ScheduleOperation.PreFilter(pod) error (core.go:88): nil == pass.
 func (e *Engine) PreFilter(pod uint32, nsName, occupiedBy string) error {
 	var st C.bs_status
