@@ -270,6 +270,9 @@ struct bs_engine {
   DevBuf d_gk0, d_gk1, d_pk0, d_pk1, d_idx_a, d_idx_b, d_ghist, d_skip, d_group_rank, d_gorder, d_tilecnt,
       d_sort_barrier;
   uint32_t sort_max_grid = 1;
+  DevBuf d_sort_arena;            // the sort scratch buffers above are views into it
+  size_t sort_arena_bytes = 0;
+  size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside for the sort scratch (0 = off)
 
   // host copies for the per-call mirrors and class building
   std::vector<int32_t> h_gid, h_prio;
@@ -837,18 +840,38 @@ int ensure_round_buffers(bs_engine* e) {
     if (fresh) CK(cudaMemsetAsync(e->d_pre_done.p, 0, e->d_pre_done.cap, e->s));
     CK(e->d_max_partial.ensure((size_t)cdiv(G, FINDMAX_THREADS * FINDMAX_PER_THREAD) * sizeof(MaxState)));
   }
-  // sort scratch
-  const uint32_t M = std::max(P, G);
-  CK(e->d_gk0.ensure((size_t)G * 8));
-  CK(e->d_gk1.ensure((size_t)G * 8));
-  CK(e->d_pk0.ensure((size_t)P * 8));
-  CK(e->d_pk1.ensure((size_t)P * 8));
-  CK(e->d_idx_a.ensure((size_t)M * 4));
-  CK(e->d_idx_b.ensure((size_t)M * 4));
-  CK(e->d_ghist.ensure((size_t)3 * 256 * cdiv(M, SORT_TILE) * 4));
-  CK(e->d_tilecnt.ensure((size_t)cdiv(M, SORT_TILE) * 4));
-  CK(e->d_sort_barrier.ensure(sizeof(unsigned int)));
-  CK(e->d_group_rank.ensure((size_t)G * 4));
+  // sort scratch: ONE arena, so that one L2 access-policy window on the sort stream covers it.  The queue sort
+  // gathers its key words at random while gang_fit streams 8 GB of scores through the same L2: marked persisting,
+  // the sort's few megabytes stay resident instead of turning into DRAM reads in the middle of a write stream.
+  {
+    const uint32_t M = std::max(P, G);
+    struct F { DevBuf* d; size_t bytes; };
+    F fields[] = {{&e->d_gk0, (size_t)G * 8}, {&e->d_gk1, (size_t)G * 8}, {&e->d_pk0, (size_t)P * 8}, {&e->d_pk1, (size_t)P * 8},
+                  {&e->d_idx_a, (size_t)M * 4}, {&e->d_idx_b, (size_t)M * 4},
+                  {&e->d_ghist, (size_t)3 * 256 * cdiv(M, SORT_TILE) * 4}, {&e->d_tilecnt, (size_t)cdiv(M, SORT_TILE) * 4},
+                  {&e->d_sort_barrier, sizeof(unsigned int)}, {&e->d_group_rank, (size_t)G * 4}};
+    size_t total = 0;
+    for (auto& f : fields) total += (f.bytes + 255) & ~(size_t)255;
+    const void* old_base = e->d_sort_arena.p;
+    CK(e->d_sort_arena.ensure(total));
+    size_t off = 0;
+    for (auto& f : fields) {
+      f.d->alias(static_cast<char*>(e->d_sort_arena.p) + off, f.bytes);
+      off += (f.bytes + 255) & ~(size_t)255;
+    }
+    if (e->d_sort_arena.p != old_base || total != e->sort_arena_bytes) {
+      e->sort_arena_bytes = total;
+      if (e->l2_persist_bytes) {
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow.base_ptr = e->d_sort_arena.p;
+        v.accessPolicyWindow.num_bytes = std::min(total, e->l2_window_max);
+        v.accessPolicyWindow.hitRatio = total <= e->l2_persist_bytes ? 1.0f : (float)((double)e->l2_persist_bytes / (double)total);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(e->s2, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();   // a hint only
+      }
+    }
+  }
   return BS_OK;
 }
 
@@ -1245,6 +1268,21 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess;
     // the sort shares the GPU with the fit kernel on the other stream: one CTA per SM is plenty
     e->sort_max_grid = (uint32_t)std::max(1, std::min(per_sm * sms, sms));
+    // persisting-L2 set-aside for the sort scratch (BS_SORT_L2_PERSIST_MB, default 16, 0 = off); a hint: failures are ignored
+    int max_persist = 0, max_window = 0;
+    size_t want_mb = 16;
+    if (const char* lp = getenv("BS_SORT_L2_PERSIST_MB")) want_mb = (size_t)std::max(0, atoi(lp));
+    if (want_mb && cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device) == cudaSuccess &&
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device) == cudaSuccess &&
+        max_persist > 0 && max_window > 0) {
+      const size_t want = std::min<size_t>(want_mb << 20, (size_t)max_persist);
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        e->l2_persist_bytes = want;
+        e->l2_window_max = (size_t)max_window;
+      } else {
+        cudaGetLastError();
+      }
+    }
     if (const char* sg = getenv("BS_SORT_GRID")) e->sort_max_grid = (uint32_t)std::max(1, std::min(atoi(sg), per_sm * sms));
   }
   if (!ok) {
@@ -1282,6 +1320,7 @@ void bs_destroy(bs_engine* e) {
                     &e->r_queue, &e->r_pf, &e->r_node, &e->r_ready, &e->r_status, &e->r_sum, &e->r_max, &e->r_keys,
                     &e->r_left0, &e->r_left1, &e->r_both, &e->r_fit, &e->r_stat};
   for (DevBuf* b : bufs) b->release();
+  e->d_sort_arena.release();
   e->d_arena.release();
   e->h_arena.release();
   for (DevBuf& b : e->u_buf) b.release();
