@@ -32,10 +32,11 @@ for score in (True, False):
     for _ in range(3): eng.evaluate_async()
     eng.sync()
     eng.set_profiling(True)
-    ms = []; st = []
+    ms = []; st = []; so = []
     for _ in range(20):
         t0 = time.perf_counter(); eng.evaluate_async(); eng.sync(); st.append((time.perf_counter() - t0) * 1e3)
-        ms.append(eng.kernel_ms()["gang_fit"][0])
+        km = eng.kernel_ms()
+        ms.append(km["gang_fit"][0]); so.append(km["sort"][0])
     eng.set_profiling(False)
     import torch
     ext = torch.cuda.ExternalStream(eng.stream())
@@ -44,6 +45,6 @@ for score in (True, False):
     for _ in range(50): eng.evaluate_async()
     e1.record(ext); eng.sync(); torch.cuda.synchronize()
     out["score" if score else "decisions"] = {"gang_fit_ms": float(np.mean(ms)), "gang_fit_min": float(np.min(ms)),
-                                               "step_ms": e0.elapsed_time(e1) / 50}
+                                               "step_ms": e0.elapsed_time(e1) / 50, "sort_ms": float(np.mean(so))}
     eng.close()
 print(json.dumps(out), flush=True)
