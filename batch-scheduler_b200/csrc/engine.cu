@@ -984,7 +984,7 @@ int evaluate_async_locked(bs_engine* e) {
         CK(cudaMemsetAsync(sa.barrier, 0, sizeof(unsigned int), e->s2));
         const uint32_t grid = std::max(1u, std::min(sa.ntiles_max, e->sort_max_grid));
         void* params[] = {&sa};
-        CK(cudaLaunchCooperativeKernel((const void*)queue_sort_kernel, dim3(grid), dim3(SORT_THREADS), params, sort_smem_bytes(), e->s2));
+        CK(cudaLaunchCooperativeKernel((const void*)queue_sort_kernel, dim3(grid), dim3(SORT_THREADS), params, 0, e->s2));
       }
       tm.launched();
     }
@@ -1264,11 +1264,7 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
     ok = cudaEventCreate(&e->ev_a[k]) == cudaSuccess && cudaEventCreate(&e->ev_b[k]) == cudaSuccess;
   if (ok) {
     int per_sm = 0, sms = 0;
-    // The sort CTAs (130 KB of staging) share their SMs with two gang_fit CTAs: both kernels ask for the largest
-    // shared-memory carveout, or an SM configured for one of them cannot take the other's CTAs until it drains.
-    ok = cudaFuncSetAttribute(queue_sort_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
-         cudaFuncSetAttribute(queue_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes()) == cudaSuccess &&
-         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, queue_sort_kernel, SORT_THREADS, sort_smem_bytes()) == cudaSuccess &&
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, queue_sort_kernel, SORT_THREADS, 0) == cudaSuccess &&
          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess;
     // the sort shares the GPU with the fit kernel on the other stream: one CTA per SM is plenty
     e->sort_max_grid = (uint32_t)std::max(1, std::min(per_sm * sms, sms));

@@ -19,10 +19,6 @@ cudaError_t launch_fit_t(const FitArgs& a0, uint32_t units, cudaStream_t s, uint
   cudaError_t er = cudaFuncSetAttribute(gang_fit_kernel<LW, LN, LS, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem);
   if (er != cudaSuccess) return er;
-  // largest shared-memory carveout: the queue sort's CTAs (130 KB of staging) run on the same SMs, and an SM whose
-  // carveout was sized for this kernel alone could not take them until it drained
-  er = cudaFuncSetAttribute(gang_fit_kernel<LW, LN, LS, OUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (er != cudaSuccess) return er;
   FitArgs a = a0;
   a.n_full = units;
   a.tail_split = 1;

@@ -28,7 +28,6 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_MAX_PASSES = 16;
 // register budget: 65536 / (256 * 8) = 32 per thread; two 288-thread, 96-register gang_fit CTAs leave 10240 free
-// (a sort CTA that does not fit beside them keeps its SM free of fit CTAs for as long as the sort lasts)
 constexpr int SORT_MIN_CTAS = 8;
 
 struct SortPass {
@@ -69,33 +68,18 @@ struct SortArgs {
 
 __device__ __forceinline__ uint64_t bias64(int64_t v) { return (uint64_t)v ^ 0x8000000000000000ull; }
 
-#ifdef BS_SORT_PROFILE   // (development: where a phase of the sort spends its time, printed by CTA 0)
-__device__ unsigned long long sp_acc[8];
-__device__ __forceinline__ unsigned long long sp_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define SP_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long _n = sp_now(); sp_acc[k] += _n - sp_t; sp_t = _n; } } while (0)
-#define SP_DECL unsigned long long sp_t = sp_now()
-#else
-#define SP_T(k) do { } while (0)
-#define SP_DECL do { } while (0)
-#endif
-
 // software grid barrier: every CTA of a co-resident grid arrives once per call
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
-  SP_DECL;
   __syncthreads();
-  SP_T(5);
   if (threadIdx.x == 0) {
     __threadfence();
-    SP_T(6);
     const unsigned int target = (epoch + 1) * gridDim.x;
     atomicAdd(counter, 1u);
     while (*((volatile unsigned int*)counter) < target) __nanosleep(64);
-    SP_T(7);
     __threadfence();
   }
   epoch += 1;
   __syncthreads();
-  SP_T(6);
 }
 
 // lanes of the warp holding the same 8-bit digit (inactive lanes match nobody): eight ballots —
@@ -117,59 +101,25 @@ __device__ __forceinline__ uint32_t digit_of(const uint64_t* __restrict__ k0, co
   return (uint32_t)(k[idx] >> ps.shift) & 0xffu;
 }
 
-// ---- shared-memory staging -------------------------------------------------------------------------
-// The sort runs beside gang_fit, which saturates HBM and the L2: a phase costs the number of DEPENDENT
-// global round trips in it, not its instructions.  Every gather therefore goes global -> shared with
-// cp.async (no destination registers: a thread keeps all 16 of its copies in flight at once) in two
-// stages per tile — the indices, then the key words they point at — and the tile histograms of the
-// current digit are staged once per pass while stage 1 is in flight.
-constexpr int SORT_HIST_TILES = 32;                        // histograms of up to this many tiles are staged
-constexpr int SORT_HIST_PITCH = SORT_HIST_TILES + 1;       // odd row pitch: thread d reads row d without bank conflicts
-constexpr int SORT_SLOTS = SORT_TILE + 1 + (SORT_TILE + 1) / 16 + 1;   // rank phases: tile + predecessor, one pad per 16
-
-struct SortSmem {
-  uint64_t key[SORT_SLOTS];     // word of the current digit (radix pass) / k0 (rank)
-  uint64_t key2[SORT_SLOTS];    // word of the next digit when it differs / k1 (rank)
-  uint32_t idx[SORT_SLOTS];
-  uint32_t hist[256 * SORT_HIST_PITCH];
-  uint32_t wcount[SORT_WARPS][256];
-  uint32_t misc[256];
-  uint32_t wtot[SORT_WARPS];
-};
-inline size_t sort_smem_bytes() { return sizeof(SortSmem); }
-
-__device__ __forceinline__ uint32_t sort_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sort_smem_u32(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sort_smem_u32(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Keys of the tiles this CTA owns (built here: no separate pass, no barrier), identity order, the tile
-// histograms of the first digit, and zeroing of the other two histogram buffers.
-template <class KeyFn>
-__device__ void sort_init_tiles(KeyFn build_key, uint64_t* k0, uint64_t* k1, const SortPass* passes, uint32_t npass,
-                                uint32_t n, uint32_t* idx, uint32_t* hist, uint32_t ntiles, uint32_t hstride, SortSmem& sm) {
+// first-pass tile histograms for identity order, and zeroing of the other two buffers,
+// restricted to the tiles this CTA owns (no cross-CTA write races)
+__device__ void sort_init_tiles(const uint64_t* k0, const uint64_t* k1, const SortPass* passes, uint32_t npass,
+                                uint32_t n, uint32_t* idx, uint32_t* hist, uint32_t ntiles, uint32_t hstride,
+                                uint32_t* s_hist) {
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    sm.misc[threadIdx.x] = 0;
+    s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = t * SORT_TILE;
 #pragma unroll 4
     for (int k = 0; k < SORT_ITEMS; ++k) {
       const uint32_t i = base + k * SORT_THREADS + threadIdx.x;
       if (i < n) {
-        uint64_t a0, a1;
-        build_key(i, a0, a1);
-        k0[i] = a0;
-        k1[i] = a1;
         idx[i] = i;
-        if (npass) atomicAdd(&sm.misc[(uint32_t)((passes[0].word ? a1 : a0) >> passes[0].shift) & 0xffu], 1u);
+        if (npass) atomicAdd(&s_hist[digit_of(k0, k1, passes[0], i)], 1u);
       }
     }
     __syncthreads();
-    hist[0 * hstride + threadIdx.x * ntiles + t] = sm.misc[threadIdx.x];
+    hist[0 * hstride + threadIdx.x * ntiles + t] = s_hist[threadIdx.x];
     hist[1 * hstride + threadIdx.x * ntiles + t] = 0;
     hist[2 * hstride + threadIdx.x * ntiles + t] = 0;
     __syncthreads();
@@ -179,69 +129,53 @@ __device__ void sort_init_tiles(KeyFn build_key, uint64_t* k0, uint64_t* k1, con
 // One radix pass (one phase).  cur: histograms of this digit; nxt: accumulates the next digit's
 // tile histograms at the scatter destinations; clr: cleared for the pass after next.
 __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, bool has_next, SortPass ps_next,
-                          uint32_t n, const uint32_t* in, uint32_t* out, const uint32_t* cur, uint32_t* nxt,
-                          uint32_t* clr, uint32_t ntiles, SortSmem& sm) {
+                          uint32_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                          const uint32_t* cur, uint32_t* nxt, uint32_t* clr, uint32_t ntiles,
+                          uint32_t (*wcount)[256], uint32_t* s_base) {
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  constexpr int ITER = SORT_TILE / SORT_WARPS / 32;
-  const uint64_t* kw = ps.word ? k1 : k0;
-  const bool two_words = has_next && ps_next.word != ps.word;
-  const uint64_t* kw2 = ps_next.word ? k1 : k0;
-  const bool cached = ntiles <= (uint32_t)SORT_HIST_TILES;
-  bool hist_staged = false;
-  SP_DECL;
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    if (cached && !hist_staged) {   // [digit][tile] -> rows of SORT_HIST_PITCH words, once per pass
-      for (uint32_t j = threadIdx.x; j < 256u * ntiles; j += SORT_THREADS)
-        cp_async4(&sm.hist[(j / ntiles) * SORT_HIST_PITCH + j % ntiles], &cur[j]);
-      hist_staged = true;
-    }
-    for (int w = 0; w < SORT_WARPS; ++w) sm.wcount[w][threadIdx.x] = 0;
-    const uint32_t slot0 = wid * (SORT_TILE / SORT_WARPS) + lane;   // a warp owns a contiguous slice: equal digits keep their order
-    const uint32_t wbase = t * SORT_TILE + slot0;
-    // stage 1: the indices of the slice;  stage 2: the key words they point at
-#pragma unroll
-    for (int k = 0; k < ITER; ++k)
-      if (wbase + k * 32 < n) cp_async4(&sm.idx[slot0 + k * 32], &in[wbase + k * 32]);
-    cp_async_wait_all();
-#pragma unroll
-    for (int k = 0; k < ITER; ++k)
-      if (wbase + k * 32 < n) {
-        const uint32_t ix = sm.idx[slot0 + k * 32];
-        cp_async8(&sm.key[slot0 + k * 32], &kw[ix]);
-        if (two_words) cp_async8(&sm.key2[slot0 + k * 32], &kw2[ix]);
-      }
-    cp_async_wait_all();
-    __syncthreads();   // counters zeroed, staged histograms visible to every thread
-    SP_T(0);
+    for (int w = 0; w < SORT_WARPS; ++w) wcount[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t wbase = t * SORT_TILE + wid * (SORT_TILE / SORT_WARPS);
+    constexpr int ITER = SORT_TILE / SORT_WARPS / 32;
+    // Digits are parked four to a word in shared memory and the indices are re-read in (c): the CTA
+    // has to fit into the registers two gang_fit CTAs leave free on an SM (SORT_MIN_CTAS), or every
+    // SM that hosts a sort CTA runs no fit CTA while the sort lasts.
+    __shared__ uint32_t s_dpack[ITER / 4][SORT_THREADS];
     // (a) warp digit counts
-#pragma unroll 4
-    for (int k = 0; k < ITER; ++k) {
-      const bool act = wbase + k * 32 < n;
-      const uint32_t dig = act ? (uint32_t)(sm.key[slot0 + k * 32] >> ps.shift) & 0xffu : 0u;
-      const uint32_t mask = warp_peers(dig, act);
-      if (act && lane == (uint32_t)(__ffs(mask) - 1)) sm.wcount[wid][dig] += __popc(mask);
-      __syncwarp();
+#pragma unroll 1
+    for (int q = 0; q < ITER / 4; ++q) {
+      uint32_t ix[4], pk = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        ix[u] = i < n ? in[i] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        pk |= (i < n ? digit_of(k0, k1, ps, ix[u]) : 0u) << (8 * u);
+      }
+      s_dpack[q][threadIdx.x] = pk;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool act = wbase + (q * 4 + u) * 32 + lane < n;
+        const uint32_t dig = (pk >> (8 * u)) & 0xffu;
+        const uint32_t mask = warp_peers(dig, act);
+        if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][dig] += __popc(mask);
+        __syncwarp();
+      }
     }
-    SP_T(1);
     // (b) thread d: tiles before this one with digit d, and the digit total
     {
       const uint32_t d = threadIdx.x;
+      const uint32_t* row = cur + d * ntiles;
       uint32_t before = 0, total = 0;
-      if (cached) {
-        const uint32_t* row = sm.hist + d * SORT_HIST_PITCH;
-        for (uint32_t tt = 0; tt < ntiles; ++tt) {
-          const uint32_t c = row[tt];
-          total += c;
-          if (tt < t) before += c;
-        }
-      } else {
-        const uint32_t* row = cur + d * ntiles;
 #pragma unroll 4
-        for (uint32_t tt = 0; tt < ntiles; ++tt) {
-          const uint32_t c = row[tt];
-          total += c;
-          if (tt < t) before += c;
-        }
+      for (uint32_t tt = 0; tt < ntiles; ++tt) {
+        const uint32_t c = row[tt];
+        total += c;
+        if (tt < t) before += c;
       }
       // exclusive scan of the 256 digit totals (warp scans + warp offsets)
       uint32_t inc = total;
@@ -249,76 +183,58 @@ __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, b
         const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
         if ((int)lane >= o) inc += v;
       }
-      if (lane == 31) sm.wtot[wid] = inc;
-      __syncthreads();   // (a)'s counters complete as well
+      __shared__ uint32_t s_wtot[SORT_WARPS];
+      if (lane == 31) s_wtot[wid] = inc;
+      __syncthreads();
       uint32_t digit_base = inc - total;
-      for (uint32_t w = 0; w < wid; ++w) digit_base += sm.wtot[w];
+      for (uint32_t w = 0; w < wid; ++w) digit_base += s_wtot[w];
       uint32_t run = digit_base + before;
       for (int w = 0; w < SORT_WARPS; ++w) {
-        const uint32_t c = sm.wcount[w][d];
-        sm.wcount[w][d] = run;
+        const uint32_t c = wcount[w][d];
+        wcount[w][d] = run;
         run += c;
       }
       clr[d * ntiles + t] = 0;
     }
     __syncthreads();
-    SP_T(2);
     // (c) ranks in original order, scatter, next-digit histogram at the destination tile
-#pragma unroll 4
-    for (int k = 0; k < ITER; ++k) {
-      const bool act = wbase + k * 32 < n;
-      const uint32_t slot = slot0 + k * 32;
-      const uint32_t dig = act ? (uint32_t)(sm.key[slot] >> ps.shift) & 0xffu : 0u;
-      const uint32_t mask = warp_peers(dig, act);
-      uint32_t pos = 0;
-      if (act) pos = sm.wcount[wid][dig] + __popc(mask & ((1u << lane) - 1u));
-      __syncwarp();
-      if (act && lane == (uint32_t)(__ffs(mask) - 1)) sm.wcount[wid][dig] += __popc(mask);
-      __syncwarp();
-      if (act) {
-        out[pos] = sm.idx[slot];
-        if (has_next) {
-          const uint64_t kn = two_words ? sm.key2[slot] : sm.key[slot];
-          atomicAdd(&nxt[((uint32_t)(kn >> ps_next.shift) & 0xffu) * ntiles + pos / SORT_TILE], 1u);
+#pragma unroll 1
+    for (int q = 0; q < ITER / 4; ++q) {
+      uint32_t ix[4];
+      const uint32_t pk = s_dpack[q][threadIdx.x];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        ix[u] = i < n ? in[i] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+        const bool act = i < n;
+        const uint32_t dig = (pk >> (8 * u)) & 0xffu;
+        const uint32_t mask = warp_peers(dig, act);
+        uint32_t pos = 0;
+        if (act) pos = wcount[wid][dig] + __popc(mask & ((1u << lane) - 1u));
+        __syncwarp();
+        if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][dig] += __popc(mask);
+        __syncwarp();
+        if (act) {
+          out[pos] = ix[u];
+          if (has_next) atomicAdd(&nxt[digit_of(k0, k1, ps_next, ix[u]) * ntiles + pos / SORT_TILE], 1u);
         }
       }
     }
     __syncthreads();
-    SP_T(3);
   }
+  (void)s_base;
 }
 
-// ---- dense rank over a sorted order (two phases): rank[order[i]] = number of key changes before i ----
-// A tile of the order and its predecessor are staged with both key words; slot j holds position
-// base - 1 + j, padded by one per 16 so that a thread's 16 consecutive positions spread over the banks.
-__device__ __forceinline__ uint32_t rank_pad(uint32_t j) { return j + (j >> 4); }
-
-__device__ void rank_stage_tile(const uint32_t* order, const uint64_t* k0, const uint64_t* k1, uint32_t n, uint32_t t,
-                                SortSmem& sm) {
-  const uint32_t base = t * SORT_TILE;
-  __syncthreads();   // the previous user of the staging arrays is done
-  for (uint32_t j = threadIdx.x; j <= (uint32_t)SORT_TILE; j += SORT_THREADS) {
-    const uint32_t pos = base + j - 1;   // j == 0 at base == 0 wraps: excluded by the range test
-    if (base + j >= 1 && pos < n) cp_async4(&sm.idx[rank_pad(j)], &order[pos]);
-  }
-  cp_async_wait_all();
-  for (uint32_t j = threadIdx.x; j <= (uint32_t)SORT_TILE; j += SORT_THREADS) {
-    const uint32_t pos = base + j - 1;
-    if (base + j >= 1 && pos < n) {
-      const uint32_t x = sm.idx[rank_pad(j)];
-      cp_async8(&sm.key[rank_pad(j)], &k0[x]);
-      cp_async8(&sm.key2[rank_pad(j)], &k1[x]);
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-}
-
-// key change between position base + q and its predecessor (q = position within the staged tile)
-__device__ __forceinline__ uint32_t rank_flag(const SortSmem& sm, uint32_t base, uint32_t q) {
-  if (base + q == 0) return 0u;
-  const uint32_t a = rank_pad(q + 1), b = rank_pad(q);
-  return (sm.key[a] != sm.key[b] || sm.key2[a] != sm.key2[b]) ? 1u : 0u;
+// dense rank over a sorted order (two phases): rank[order[i]] = number of key changes before i
+__device__ __forceinline__ uint32_t rank_flag(const uint32_t* order, const uint64_t* k0, const uint64_t* k1,
+                                              uint32_t i) {
+  if (i == 0) return 0u;
+  const uint32_t x = order[i], y = order[i - 1];
+  return (k0[x] != k0[y] || k1[x] != k1[y]) ? 1u : 0u;
 }
 
 __device__ uint32_t block_sum(uint32_t v, uint32_t* s_w) {
@@ -333,75 +249,71 @@ __device__ uint32_t block_sum(uint32_t v, uint32_t* s_w) {
 }
 
 __device__ void rank_count_tiles(const uint32_t* order, const uint64_t* k0, const uint64_t* k1, uint32_t n,
-                                 uint32_t ntiles, uint32_t* tilecnt, SortSmem& sm, uint32_t& staged) {
+                                 uint32_t ntiles, uint32_t* tilecnt, uint32_t* s_w) {
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    rank_stage_tile(order, k0, k1, n, t, sm);
-    staged = t;
-    const uint32_t base = t * SORT_TILE, q0 = threadIdx.x * SORT_ITEMS;
+    const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
     uint32_t c = 0;
 #pragma unroll 4
     for (int k = 0; k < SORT_ITEMS; ++k)
-      if (base + q0 + k < n) c += rank_flag(sm, base, q0 + k);
-    c = block_sum(c, sm.misc);
+      if (base + k < n) c += rank_flag(order, k0, k1, base + k);
+    c = block_sum(c, s_w);
     if (threadIdx.x == 0) tilecnt[t] = c;
   }
 }
 
 __device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, const uint64_t* k1, uint32_t n,
                                  uint32_t ntiles, const uint32_t* tilecnt, uint32_t* rank, uint32_t* order_out,
-                                 SortSmem& sm, uint32_t staged) {
+                                 uint32_t* s_w) {
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    if (t != staged) {   // one tile per CTA (the usual case): still staged from the counting phase
-      rank_stage_tile(order, k0, k1, n, t, sm);
-      staged = t;
-    }
     uint32_t off = 0;
     for (uint32_t tt = threadIdx.x; tt < t; tt += SORT_THREADS) off += tilecnt[tt];
-    off = block_sum(off, sm.misc);
-    const uint32_t base = t * SORT_TILE, q0 = threadIdx.x * SORT_ITEMS;
+    off = block_sum(off, s_w);
+    const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
     uint32_t c = 0;
 #pragma unroll 4
     for (int k = 0; k < SORT_ITEMS; ++k)
-      if (base + q0 + k < n) c += rank_flag(sm, base, q0 + k);
+      if (base + k < n) c += rank_flag(order, k0, k1, base + k);
     uint32_t inc = c;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
       if ((int)lane >= o) inc += v;
     }
     __syncthreads();
-    if (lane == 31) sm.wtot[wid] = inc;
+    if (lane == 31) s_w[wid] = inc;
     __syncthreads();
     uint32_t run = off + inc - c;
-    for (uint32_t w = 0; w < wid; ++w) run += sm.wtot[w];
+    for (uint32_t w = 0; w < wid; ++w) run += s_w[w];
 #pragma unroll 2
     for (int k = 0; k < SORT_ITEMS; ++k) {
-      const uint32_t i = base + q0 + k;
+      const uint32_t i = base + k;
       if (i < n) {
-        run += rank_flag(sm, base, q0 + k);
-        const uint32_t o = sm.idx[rank_pad(q0 + k + 1)];
+        run += rank_flag(order, k0, k1, i);
+        const uint32_t o = order[i];
         rank[o] = run;
         if (order_out) order_out[i] = o;
       }
     }
+    __syncthreads();
   }
 }
 
 // sorts 0..n-1 by the pass list; returns the buffer holding the final order (uniform over the grid)
-template <class KeyFn>
-__device__ uint32_t* sort_table(KeyFn build_key, uint64_t* k0, uint64_t* k1, const SortPass* passes, uint32_t npass,
+__device__ uint32_t* sort_table(const uint64_t* k0, const uint64_t* k1, const SortPass* passes, uint32_t npass,
                                 uint32_t n, uint32_t* a, uint32_t* b, uint32_t* hist, uint32_t ntiles_max,
-                                unsigned int* barrier, unsigned int& epoch, SortSmem& sm) {
+                                unsigned int* barrier, unsigned int& epoch, uint32_t (*wcount)[256],
+                                uint32_t* s_misc) {
   const uint32_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
   const uint32_t hstride = 256 * ntiles_max;
-  sort_init_tiles(build_key, k0, k1, passes, npass, n, a, hist, ntiles, hstride, sm);
+  sort_init_tiles(k0, k1, passes, npass, n, a, hist, ntiles, hstride, s_misc);
   grid_barrier(barrier, epoch);
   uint32_t* cur = a;
   uint32_t* nxt = b;
   for (uint32_t k = 0; k < npass; ++k) {
     const bool has_next = k + 1 < npass;
     sort_pass(k0, k1, passes[k], has_next, passes[has_next ? k + 1 : k], n, cur, nxt,
-              hist + (k % 3) * hstride, hist + ((k + 1) % 3) * hstride, hist + ((k + 2) % 3) * hstride, ntiles, sm);
+              hist + (k % 3) * hstride, hist + ((k + 1) % 3) * hstride, hist + ((k + 2) % 3) * hstride, ntiles,
+              wcount, s_misc);
     grid_barrier(barrier, epoch);
     uint32_t* tmp = cur; cur = nxt; nxt = tmp;
   }
@@ -409,28 +321,29 @@ __device__ uint32_t* sort_table(KeyFn build_key, uint64_t* k0, uint64_t* k1, con
 }
 
 __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_CTAS) queue_sort_kernel(SortArgs a) {
-  extern __shared__ __align__(16) unsigned char sort_smem_raw[];
-  SortSmem& sm = *reinterpret_cast<SortSmem*>(sort_smem_raw);
+  __shared__ uint32_t wcount[SORT_WARPS][256];
+  __shared__ uint32_t s_misc[256];
   unsigned int epoch = 0;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
 
   // ---- groups: keys -> sort -> dense rank
   if (a.G) {
-    auto gkey = [&](uint32_t i, uint64_t& w0, uint64_t& w1) {
-      w0 = (uint64_t)(~a.name_rank[i]);   // descending name
-      w1 = bias64(a.creation[i]);         // ascending creation
-    };
-    uint32_t* gord = sort_table(gkey, a.gk0, a.gk1, a.gpass, a.n_gpass, a.G, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
-                                a.barrier, epoch, sm);
-    const uint32_t gt = (a.G + SORT_TILE - 1) / SORT_TILE;
-    uint32_t staged = 0xffffffffu;
-    rank_count_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, sm, staged);
+    for (uint32_t i = gtid; i < a.G; i += gsz) {
+      a.gk0[i] = (uint64_t)(~a.name_rank[i]);   // descending name
+      a.gk1[i] = bias64(a.creation[i]);         // ascending creation
+    }
     grid_barrier(a.barrier, epoch);
-    rank_write_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, a.group_rank, nullptr, sm, staged);
+    uint32_t* gord = sort_table(a.gk0, a.gk1, a.gpass, a.n_gpass, a.G, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
+                                a.barrier, epoch, wcount, s_misc);
+    const uint32_t gt = (a.G + SORT_TILE - 1) / SORT_TILE;
+    rank_count_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, s_misc);
+    grid_barrier(a.barrier, epoch);
+    rank_write_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, a.group_rank, nullptr, s_misc);
     grid_barrier(a.barrier, epoch);
   }
   // ---- pods
   if (a.P) {
-    auto pkey = [&](uint32_t i, uint64_t& w0, uint64_t& w1) {
+    for (uint32_t i = gtid; i < a.P; i += gsz) {
       const int32_t g = a.gid[i];
       const uint32_t pbits = ~((uint32_t)a.prio[i] ^ 0x80000000u);  // higher priority first
       uint32_t low;
@@ -439,24 +352,17 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_CTAS) queue_sort_kernel
         const bool miss = g < 0 || (uint32_t)g >= a.G || (a.pflags[i] & BS_POD_LISTER_MISS);
         low = 0x80000000u | (miss ? 0x7fffffffu : a.group_rank[g]);
       }
-      w1 = ((uint64_t)pbits << 32) | low;
-      w0 = bias64(a.ts[i]);
-    };
-    uint32_t* pord = sort_table(pkey, a.pk0, a.pk1, a.ppass, a.n_ppass, a.P, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
-                                a.barrier, epoch, sm);
-    const uint32_t pt = (a.P + SORT_TILE - 1) / SORT_TILE;
-    uint32_t staged = 0xffffffffu;
-    rank_count_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, sm, staged);
+      a.pk1[i] = ((uint64_t)pbits << 32) | low;
+      a.pk0[i] = bias64(a.ts[i]);
+    }
     grid_barrier(a.barrier, epoch);
-    rank_write_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, a.rank, a.order, sm, staged);
+    uint32_t* pord = sort_table(a.pk0, a.pk1, a.ppass, a.n_ppass, a.P, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
+                                a.barrier, epoch, wcount, s_misc);
+    const uint32_t pt = (a.P + SORT_TILE - 1) / SORT_TILE;
+    rank_count_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, s_misc);
+    grid_barrier(a.barrier, epoch);
+    rank_write_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, a.rank, a.order, s_misc);
   }
-#ifdef BS_SORT_PROFILE
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    printf("[sort us] stage %.1f  a %.1f  b %.1f  c %.1f | barrier: entry-sync %.1f  fences+exit %.1f  arrive+poll %.1f  (%u barriers)\n",
-           sp_acc[0] * 1e-3, sp_acc[1] * 1e-3, sp_acc[2] * 1e-3, sp_acc[3] * 1e-3, sp_acc[5] * 1e-3, sp_acc[6] * 1e-3, sp_acc[7] * 1e-3, epoch);
-    for (int k = 0; k < 8; ++k) sp_acc[k] = 0;
-  }
-#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -562,13 +468,6 @@ __device__ uint32_t* small_radix(const uint64_t* k0, const uint64_t* k1, const S
     uint32_t* t = in; in = out; out = t;
   }
   return in;
-}
-
-__device__ __forceinline__ uint32_t rank_flag(const uint32_t* order, const uint64_t* k0, const uint64_t* k1,
-                                              uint32_t i) {
-  if (i == 0) return 0u;
-  const uint32_t x = order[i], y = order[i - 1];
-  return (k0[x] != k0[y] || k1[x] != k1[y]) ? 1u : 0u;
 }
 
 // dense rank over the sorted order: rank_out[ord[i]] = number of key changes before position i (inclusive)
