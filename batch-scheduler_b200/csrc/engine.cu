@@ -270,6 +270,7 @@ struct bs_engine {
   DevBuf d_gk0, d_gk1, d_pk0, d_pk1, d_idx_a, d_idx_b, d_ghist, d_skip, d_group_rank, d_gorder, d_tilecnt,
       d_sort_barrier;
   uint32_t sort_max_grid = 1;
+  int sort_variant = 0;           // 0: by the estimated fit time; 1 / 2: force the lean / wide sort kernel
   DevBuf d_sort_arena;            // the sort scratch buffers above are views into it
   size_t sort_arena_bytes = 0;
   size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside for the sort scratch (0 = off)
@@ -984,7 +985,14 @@ int evaluate_async_locked(bs_engine* e) {
         CK(cudaMemsetAsync(sa.barrier, 0, sizeof(unsigned int), e->s2));
         const uint32_t grid = std::max(1u, std::min(sa.ntiles_max, e->sort_max_grid));
         void* params[] = {&sa};
-        CK(cudaLaunchCooperativeKernel((const void*)queue_sort_kernel, dim3(grid), dim3(SORT_THREADS), params, 0, e->s2));
+        // Two builds of the same kernel.  Beside a long fit kernel the sort is hidden anyway and must stay out of its
+        // way (32 registers: its CTAs share their SMs with the fit CTAs); when the fit kernel is the shorter of the two
+        // (a small shard, few nodes) the round waits for the sort, and the build with 16 gathers in flight per thread
+        // is the faster one.  Estimate: pairs x the measured per-pair time of the output mode.
+        const double est_fit_ms = (double)P * (double)e->N * ((e->out_flags & BS_OUT_SCORE) ? 1.4e-9 : 0.8e-9);
+        const bool lean = e->sort_variant == 1 || (e->sort_variant == 0 && est_fit_ms > 0.6);
+        const void* fn = lean ? (const void*)queue_sort_kernel<SORT_LEAN_GROUP> : (const void*)queue_sort_kernel<SORT_WIDE_GROUP>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SORT_THREADS), params, 0, e->s2));
       }
       tm.launched();
     }
@@ -1264,10 +1272,14 @@ int bs_create(const bs_config* cfg, bs_engine** out) {
     ok = cudaEventCreate(&e->ev_a[k]) == cudaSuccess && cudaEventCreate(&e->ev_b[k]) == cudaSuccess;
   if (ok) {
     int per_sm = 0, sms = 0;
-    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, queue_sort_kernel, SORT_THREADS, 0) == cudaSuccess &&
+    int per_sm_wide = 0;
+    ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, queue_sort_kernel<SORT_LEAN_GROUP>, SORT_THREADS, 0) == cudaSuccess &&
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, queue_sort_kernel<SORT_WIDE_GROUP>, SORT_THREADS, 0) == cudaSuccess &&
          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess;
     // the sort shares the GPU with the fit kernel on the other stream: one CTA per SM is plenty
+    per_sm = std::min(per_sm, per_sm_wide);
     e->sort_max_grid = (uint32_t)std::max(1, std::min(per_sm * sms, sms));
+    if (const char* sv = getenv("BS_SORT_VARIANT")) e->sort_variant = atoi(sv);   // 0 auto, 1 lean, 2 wide (measurement)
     // persisting-L2 set-aside for the sort scratch (BS_SORT_L2_PERSIST_MB, default 16, 0 = off); a hint: failures are ignored
     int max_persist = 0, max_window = 0;
     size_t want_mb = 16;

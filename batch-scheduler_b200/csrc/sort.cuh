@@ -29,6 +29,7 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_MAX_PASSES = 16;
 // register budget: 65536 / (256 * 8) = 32 per thread; two 288-thread, 96-register gang_fit CTAs leave 10240 free
 constexpr int SORT_MIN_CTAS = 8;
+constexpr int SORT_LEAN_GROUP = 4, SORT_WIDE_GROUP = 16;   // keys a thread keeps in flight (sort_pass)
 
 struct SortPass {
   uint8_t word;   // 0: k0, 1: k1
@@ -103,6 +104,7 @@ __device__ __forceinline__ uint32_t digit_of(const uint64_t* __restrict__ k0, co
 
 // first-pass tile histograms for identity order, and zeroing of the other two buffers,
 // restricted to the tiles this CTA owns (no cross-CTA write races)
+template <int GROUP>
 __device__ void sort_init_tiles(const uint64_t* k0, const uint64_t* k1, const SortPass* passes, uint32_t npass,
                                 uint32_t n, uint32_t* idx, uint32_t* hist, uint32_t ntiles, uint32_t hstride,
                                 uint32_t* s_hist) {
@@ -110,7 +112,7 @@ __device__ void sort_init_tiles(const uint64_t* k0, const uint64_t* k1, const So
     s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = t * SORT_TILE;
-#pragma unroll 4
+#pragma unroll GROUP
     for (int k = 0; k < SORT_ITEMS; ++k) {
       const uint32_t i = base + k * SORT_THREADS + threadIdx.x;
       if (i < n) {
@@ -128,39 +130,49 @@ __device__ void sort_init_tiles(const uint64_t* k0, const uint64_t* k1, const So
 
 // One radix pass (one phase).  cur: histograms of this digit; nxt: accumulates the next digit's
 // tile histograms at the scatter destinations; clr: cleared for the pass after next.
+// GROUP = keys a thread has in flight at once (4 or 16).  Digits are parked four to a word in shared
+// memory and the indices are re-read in (c), so the live state is GROUP registers, not 2 x 16:
+//   GROUP 4  (the "lean" kernel, 32 registers): the CTA fits into the registers two gang_fit CTAs leave
+//            free on an SM — a sort CTA that does not keeps its SM free of fit CTAs while the sort lasts;
+//   GROUP 16 (the "wide" kernel): all 16 gathers of a thread in flight, for rounds whose fit kernel is
+//            shorter than the sort, where the sort's own latency is what the round waits for.
+template <int GROUP>
 __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, bool has_next, SortPass ps_next,
                           uint32_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                           const uint32_t* cur, uint32_t* nxt, uint32_t* clr, uint32_t ntiles,
-                          uint32_t (*wcount)[256], uint32_t* s_base) {
+                          uint32_t (*wcount)[256]) {
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int ITER = SORT_TILE / SORT_WARPS / 32;
+  constexpr int WORDS = GROUP / 4;
+  static_assert(GROUP % 4 == 0 && ITER % GROUP == 0, "GROUP: a multiple of 4 dividing the keys per lane");
+  __shared__ uint32_t s_dpack[ITER / 4][SORT_THREADS];
+  __shared__ uint32_t s_wtot[SORT_WARPS];
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     for (int w = 0; w < SORT_WARPS; ++w) wcount[w][threadIdx.x] = 0;
     __syncthreads();
     const uint32_t wbase = t * SORT_TILE + wid * (SORT_TILE / SORT_WARPS);
-    constexpr int ITER = SORT_TILE / SORT_WARPS / 32;
-    // Digits are parked four to a word in shared memory and the indices are re-read in (c): the CTA
-    // has to fit into the registers two gang_fit CTAs leave free on an SM (SORT_MIN_CTAS), or every
-    // SM that hosts a sort CTA runs no fit CTA while the sort lasts.
-    __shared__ uint32_t s_dpack[ITER / 4][SORT_THREADS];
     // (a) warp digit counts
 #pragma unroll 1
-    for (int q = 0; q < ITER / 4; ++q) {
-      uint32_t ix[4], pk = 0;
+    for (int q = 0; q < ITER / GROUP; ++q) {
+      uint32_t ix[GROUP], pk[WORDS];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+      for (int u = 0; u < GROUP; ++u) {
+        const uint32_t i = wbase + (q * GROUP + u) * 32 + lane;
         ix[u] = i < n ? in[i] : 0u;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
-        pk |= (i < n ? digit_of(k0, k1, ps, ix[u]) : 0u) << (8 * u);
-      }
-      s_dpack[q][threadIdx.x] = pk;
+      for (int w = 0; w < WORDS; ++w) pk[w] = 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool act = wbase + (q * 4 + u) * 32 + lane < n;
-        const uint32_t dig = (pk >> (8 * u)) & 0xffu;
+      for (int u = 0; u < GROUP; ++u) {
+        const uint32_t i = wbase + (q * GROUP + u) * 32 + lane;
+        pk[u / 4] |= (i < n ? digit_of(k0, k1, ps, ix[u]) : 0u) << (8 * (u % 4));
+      }
+#pragma unroll
+      for (int w = 0; w < WORDS; ++w) s_dpack[q * WORDS + w][threadIdx.x] = pk[w];
+#pragma unroll
+      for (int u = 0; u < GROUP; ++u) {
+        const bool act = wbase + (q * GROUP + u) * 32 + lane < n;
+        const uint32_t dig = (pk[u / 4] >> (8 * (u % 4))) & 0xffu;
         const uint32_t mask = warp_peers(dig, act);
         if (act && lane == (uint32_t)(__ffs(mask) - 1)) wcount[wid][dig] += __popc(mask);
         __syncwarp();
@@ -171,7 +183,7 @@ __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, b
       const uint32_t d = threadIdx.x;
       const uint32_t* row = cur + d * ntiles;
       uint32_t before = 0, total = 0;
-#pragma unroll 4
+#pragma unroll GROUP
       for (uint32_t tt = 0; tt < ntiles; ++tt) {
         const uint32_t c = row[tt];
         total += c;
@@ -183,7 +195,6 @@ __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, b
         const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
         if ((int)lane >= o) inc += v;
       }
-      __shared__ uint32_t s_wtot[SORT_WARPS];
       if (lane == 31) s_wtot[wid] = inc;
       __syncthreads();
       uint32_t digit_base = inc - total;
@@ -199,19 +210,20 @@ __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, b
     __syncthreads();
     // (c) ranks in original order, scatter, next-digit histogram at the destination tile
 #pragma unroll 1
-    for (int q = 0; q < ITER / 4; ++q) {
-      uint32_t ix[4];
-      const uint32_t pk = s_dpack[q][threadIdx.x];
+    for (int q = 0; q < ITER / GROUP; ++q) {
+      uint32_t ix[GROUP], pk[WORDS];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+      for (int w = 0; w < WORDS; ++w) pk[w] = s_dpack[q * WORDS + w][threadIdx.x];
+#pragma unroll
+      for (int u = 0; u < GROUP; ++u) {
+        const uint32_t i = wbase + (q * GROUP + u) * 32 + lane;
         ix[u] = i < n ? in[i] : 0u;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = wbase + (q * 4 + u) * 32 + lane;
+      for (int u = 0; u < GROUP; ++u) {
+        const uint32_t i = wbase + (q * GROUP + u) * 32 + lane;
         const bool act = i < n;
-        const uint32_t dig = (pk >> (8 * u)) & 0xffu;
+        const uint32_t dig = (pk[u / 4] >> (8 * (u % 4))) & 0xffu;
         const uint32_t mask = warp_peers(dig, act);
         uint32_t pos = 0;
         if (act) pos = wcount[wid][dig] + __popc(mask & ((1u << lane) - 1u));
@@ -226,7 +238,6 @@ __device__ void sort_pass(const uint64_t* k0, const uint64_t* k1, SortPass ps, b
     }
     __syncthreads();
   }
-  (void)s_base;
 }
 
 // dense rank over a sorted order (two phases): rank[order[i]] = number of key changes before i
@@ -248,12 +259,13 @@ __device__ uint32_t block_sum(uint32_t v, uint32_t* s_w) {
   return t;
 }
 
+template <int GROUP>
 __device__ void rank_count_tiles(const uint32_t* order, const uint64_t* k0, const uint64_t* k1, uint32_t n,
                                  uint32_t ntiles, uint32_t* tilecnt, uint32_t* s_w) {
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
     uint32_t c = 0;
-#pragma unroll 4
+#pragma unroll GROUP
     for (int k = 0; k < SORT_ITEMS; ++k)
       if (base + k < n) c += rank_flag(order, k0, k1, base + k);
     c = block_sum(c, s_w);
@@ -261,6 +273,7 @@ __device__ void rank_count_tiles(const uint32_t* order, const uint64_t* k0, cons
   }
 }
 
+template <int GROUP>
 __device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, const uint64_t* k1, uint32_t n,
                                  uint32_t ntiles, const uint32_t* tilecnt, uint32_t* rank, uint32_t* order_out,
                                  uint32_t* s_w) {
@@ -271,7 +284,7 @@ __device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, cons
     off = block_sum(off, s_w);
     const uint32_t base = t * SORT_TILE + threadIdx.x * SORT_ITEMS;
     uint32_t c = 0;
-#pragma unroll 4
+#pragma unroll GROUP
     for (int k = 0; k < SORT_ITEMS; ++k)
       if (base + k < n) c += rank_flag(order, k0, k1, base + k);
     uint32_t inc = c;
@@ -284,7 +297,7 @@ __device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, cons
     __syncthreads();
     uint32_t run = off + inc - c;
     for (uint32_t w = 0; w < wid; ++w) run += s_w[w];
-#pragma unroll 2
+#pragma unroll (GROUP / 2)
     for (int k = 0; k < SORT_ITEMS; ++k) {
       const uint32_t i = base + k;
       if (i < n) {
@@ -299,28 +312,29 @@ __device__ void rank_write_tiles(const uint32_t* order, const uint64_t* k0, cons
 }
 
 // sorts 0..n-1 by the pass list; returns the buffer holding the final order (uniform over the grid)
+template <int GROUP>
 __device__ uint32_t* sort_table(const uint64_t* k0, const uint64_t* k1, const SortPass* passes, uint32_t npass,
                                 uint32_t n, uint32_t* a, uint32_t* b, uint32_t* hist, uint32_t ntiles_max,
                                 unsigned int* barrier, unsigned int& epoch, uint32_t (*wcount)[256],
                                 uint32_t* s_misc) {
   const uint32_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
   const uint32_t hstride = 256 * ntiles_max;
-  sort_init_tiles(k0, k1, passes, npass, n, a, hist, ntiles, hstride, s_misc);
+  sort_init_tiles<GROUP>(k0, k1, passes, npass, n, a, hist, ntiles, hstride, s_misc);
   grid_barrier(barrier, epoch);
   uint32_t* cur = a;
   uint32_t* nxt = b;
   for (uint32_t k = 0; k < npass; ++k) {
     const bool has_next = k + 1 < npass;
-    sort_pass(k0, k1, passes[k], has_next, passes[has_next ? k + 1 : k], n, cur, nxt,
-              hist + (k % 3) * hstride, hist + ((k + 1) % 3) * hstride, hist + ((k + 2) % 3) * hstride, ntiles,
-              wcount, s_misc);
+    sort_pass<GROUP>(k0, k1, passes[k], has_next, passes[has_next ? k + 1 : k], n, cur, nxt,
+                     hist + (k % 3) * hstride, hist + ((k + 1) % 3) * hstride, hist + ((k + 2) % 3) * hstride, ntiles, wcount);
     grid_barrier(barrier, epoch);
     uint32_t* tmp = cur; cur = nxt; nxt = tmp;
   }
   return cur;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_CTAS) queue_sort_kernel(SortArgs a) {
+template <int GROUP>
+__global__ void __launch_bounds__(SORT_THREADS, GROUP == SORT_LEAN_GROUP ? SORT_MIN_CTAS : 2) queue_sort_kernel(SortArgs a) {
   __shared__ uint32_t wcount[SORT_WARPS][256];
   __shared__ uint32_t s_misc[256];
   unsigned int epoch = 0;
@@ -333,12 +347,12 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_CTAS) queue_sort_kernel
       a.gk1[i] = bias64(a.creation[i]);         // ascending creation
     }
     grid_barrier(a.barrier, epoch);
-    uint32_t* gord = sort_table(a.gk0, a.gk1, a.gpass, a.n_gpass, a.G, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
+    uint32_t* gord = sort_table<GROUP>(a.gk0, a.gk1, a.gpass, a.n_gpass, a.G, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
                                 a.barrier, epoch, wcount, s_misc);
     const uint32_t gt = (a.G + SORT_TILE - 1) / SORT_TILE;
-    rank_count_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, s_misc);
+    rank_count_tiles<GROUP>(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, s_misc);
     grid_barrier(a.barrier, epoch);
-    rank_write_tiles(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, a.group_rank, nullptr, s_misc);
+    rank_write_tiles<GROUP>(gord, a.gk0, a.gk1, a.G, gt, a.tilecnt, a.group_rank, nullptr, s_misc);
     grid_barrier(a.barrier, epoch);
   }
   // ---- pods
@@ -356,12 +370,12 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_CTAS) queue_sort_kernel
       a.pk0[i] = bias64(a.ts[i]);
     }
     grid_barrier(a.barrier, epoch);
-    uint32_t* pord = sort_table(a.pk0, a.pk1, a.ppass, a.n_ppass, a.P, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
+    uint32_t* pord = sort_table<GROUP>(a.pk0, a.pk1, a.ppass, a.n_ppass, a.P, a.idx_a, a.idx_b, a.hist, a.ntiles_max,
                                 a.barrier, epoch, wcount, s_misc);
     const uint32_t pt = (a.P + SORT_TILE - 1) / SORT_TILE;
-    rank_count_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, s_misc);
+    rank_count_tiles<GROUP>(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, s_misc);
     grid_barrier(a.barrier, epoch);
-    rank_write_tiles(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, a.rank, a.order, s_misc);
+    rank_write_tiles<GROUP>(pord, a.pk0, a.pk1, a.P, pt, a.tilecnt, a.rank, a.order, s_misc);
   }
 }
 
