@@ -85,7 +85,8 @@ def usable_threads() -> int:
 
 
 class ClockSampler:
-    """SM clock + throttle reasons of one GPU, sampled in-process through NVML every 10 ms (a thread);
+    """SM clock + throttle reasons of one GPU, sampled in-process through NVML every 50 ms (a thread: about 20 samples
+    inside the >= 1 s timed region; NVML queries take driver locks, so no more often than that);
     `window(t0, t1)` summarises the samples taken inside a perf_counter interval.  Falls back to one
     nvidia-smi -lms subprocess (started long before the timed region) when NVML is unavailable."""
 
@@ -142,7 +143,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), mhz, rs, pw))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.05)
 
     def _loop_smi(self):
         names = [0x8, 0x40, 0x20, 0x4]
