@@ -513,15 +513,28 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
     return true;
   };
   // ---- groups
-  std::unordered_map<std::string, uint32_t> gindex;
   ps.min_member.assign(G, 0); ps.scheduled.assign(G, 0); ps.matched.assign(G, 0); ps.group_flags.assign(G, 0);
   ps.min_res.assign((size_t)L * G, 0); ps.min_res_present.assign(G, 0); ps.rep_sel.assign(G, 0);
   ps.rep_tol.assign(G, 0); ps.creation_ns.assign(G, 0); ps.name_rank.assign(G, 0); ps.wait_ns.assign(G, 0);
   // bare-name ranks, byte-wise ascending (Go string compare); equal names share a rank (core.go:404)
+  // (sorted on the big-endian first 8 bytes as an integer; the strings are compared only where those tie)
   std::vector<uint32_t> by_name(G);
-  for (uint32_t g = 0; g < G; ++g) by_name[g] = g;
-  std::sort(by_name.begin(), by_name.end(),
-            [&](uint32_t a, uint32_t b) { return groups[a].pg->name < groups[b].pg->name; });
+  {
+    struct NameKey { uint64_t pre; uint32_t g; };
+    std::vector<NameKey> nk(G);
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (uint32_t g = 0; g < G; ++g) {
+      const std::string& nm = groups[g].pg->name;
+      uint64_t pre = 0;
+      for (size_t b = 0; b < 8; ++b) pre = (pre << 8) | (b < nm.size() ? (unsigned char)nm[b] : 0u);
+      nk[g] = NameKey{pre, g};
+    }
+    std::sort(nk.begin(), nk.end(), [&](const NameKey& a, const NameKey& b) {
+      if (a.pre != b.pre) return a.pre < b.pre;
+      return groups[a.g].pg->name < groups[b.g].pg->name;   // equal prefixes (incl. a short name vs one with NUL bytes)
+    });
+    for (uint32_t k = 0; k < G; ++k) by_name[k] = nk[k].g;
+  }
   std::vector<uint32_t> rank_of_group(G);
   {
     uint32_t r = 0;
@@ -530,8 +543,44 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
       rank_of_group[by_name[k]] = r;
     }
   }
-  gindex.reserve((size_t)G * 2);
-  for (uint32_t g = 0; g < G; ++g) gindex.emplace(groups[g].pg->ns + "/" + groups[g].pg->name, g);
+  // "ns/name" -> group row (the lister's key, util.GetPodGroupFullName): a flat open-addressing table over a
+  // 64-bit hash of the two strings — no key is concatenated or allocated, neither here nor in the pods' lookups.
+  // The first row with a given full name wins, as a map insert would.
+  auto full_hash = [](const std::string& ns, const std::string& name) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : ns) h = (h ^ c) * 1099511628211ull;
+    h = (h ^ (unsigned char)'/') * 1099511628211ull;
+    for (unsigned char c : name) h = (h ^ c) * 1099511628211ull;
+    return h ^ (h >> 32);
+  };
+  uint32_t gmask = 1;
+  while (gmask < 2 * std::max(G, 1u)) gmask <<= 1;
+  gmask -= 1;
+  std::vector<uint32_t> gslot((size_t)gmask + 1, 0xffffffffu);
+  {
+    std::vector<uint64_t> gh(G);
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (uint32_t g = 0; g < G; ++g) gh[g] = full_hash(groups[g].pg->ns, groups[g].pg->name);
+    for (uint32_t g = 0; g < G; ++g) {
+      uint32_t sl = (uint32_t)gh[g] & gmask;
+      bool dup = false;
+      while (gslot[sl] != 0xffffffffu) {
+        const PodGroup& o = *groups[gslot[sl]].pg;
+        if (o.name == groups[g].pg->name && o.ns == groups[g].pg->ns) { dup = true; break; }
+        sl = (sl + 1) & gmask;
+      }
+      if (!dup) gslot[sl] = g;
+    }
+  }
+  auto find_group = [&](const std::string& ns, const std::string& name) -> int32_t {
+    uint32_t sl = (uint32_t)full_hash(ns, name) & gmask;
+    while (gslot[sl] != 0xffffffffu) {
+      const PodGroup& o = *groups[gslot[sl]].pg;
+      if (o.name == name && o.ns == ns) return (int32_t)gslot[sl];
+      sl = (sl + 1) & gmask;
+    }
+    return -1;
+  };
 #pragma omp parallel for num_threads(T) schedule(static)
   for (uint32_t g = 0; g < G; ++g) {
     const PodGroup& pg = *groups[g].pg;
@@ -563,8 +612,6 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   ps.req.assign((size_t)L * P, 0); ps.pod_req_present.assign(P, 0); ps.gid.assign(P, BS_GID_NONE);
   ps.sel_mask.assign(P, 0); ps.tol_mask.assign(P, 0); ps.priority.assign(P, 0); ps.ts_ns.assign(P, 0);
   ps.pod_flags.assign(P, 0);
-  std::vector<std::string> occupied(G);
-  for (uint32_t g = 0; g < G; ++g) occupied[g] = groups[g].pg->occupied_by;
 #pragma omp parallel for num_threads(T) schedule(static)
   for (uint32_t i = 0; i < P; ++i) {
     const Pod& p = *pending[i];
@@ -579,9 +626,9 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
     uint8_t fl = i < pod_flags_in.size() ? pod_flags_in[i] : 0;
     auto lab = p.labels.find(kPodGroupLabel);                          // util.VerifyPodLabelSatisfied k8s.go:62-70
     if (lab != p.labels.end() && !lab->second.empty()) {
-      auto gi = gindex.find(p.ns + "/" + lab->second);
-      if (gi == gindex.end()) { ps.gid[i] = BS_GID_MISSING; fl |= BS_POD_LISTER_MISS; }
-      else ps.gid[i] = (int32_t)gi->second;
+      const int32_t gi = find_group(p.ns, lab->second);
+      if (gi < 0) { ps.gid[i] = BS_GID_MISSING; fl |= BS_POD_LISTER_MISS; }
+      else ps.gid[i] = gi;
     }
     ps.pod_flags[i] = fl;
   }
@@ -590,31 +637,42 @@ Status pack_impl(const std::vector<const NodeInfo*>& snapshot, const std::vector
   // fillOccupiedObj runs when a pod is popped, i.e. in QUEUE order (Less = Compare, core.go:368-411), not in
   // arrival order: with an empty OccupiedBy and pods of one group carrying different ownerRefs, the first pod
   // in queue order decides who occupies the group.  Stable sort of the grouped pods by Compare's key.
-  std::vector<uint32_t> qorder;
-  qorder.reserve(P);
-  for (uint32_t i = 0; i < P; ++i) if (ps.gid[i] >= 0) qorder.push_back(i);
-  std::stable_sort(qorder.begin(), qorder.end(), [&](uint32_t a, uint32_t b) {
-    if (ps.priority[a] != ps.priority[b]) return ps.priority[a] > ps.priority[b];
-    const PodGroup& ga = *groups[ps.gid[a]].pg;
-    const PodGroup& gb = *groups[ps.gid[b]].pg;
-    if (ga.creation_ns != gb.creation_ns) return ga.creation_ns < gb.creation_ns;
-    if (ga.name != gb.name) return ga.name > gb.name;            // core.go:404: the greater bare name first
-    return ps.ts_ns[a] < ps.ts_ns[b];
-  });
-  for (uint32_t i : qorder) {
-    const int32_t gidx = ps.gid[i];
-    if (gidx < 0) continue;
-    const uint32_t g = (uint32_t)gidx;
-    const Pod& p = *pending[i];
-    uint8_t fl = ps.pod_flags[i];
-    const bool reaches = !(fl & BS_POD_PERMITTED_RECENTLY) && !(ps.group_flags[g] & BS_GROUP_DENIED);
-    if (reaches) {
-      if (occupied[g].empty()) {
-        if (!p.owner_uids.empty()) occupied[g] = joined_sorted(p.owner_uids);   // core.go:496-500
-      } else if (p.owner_uids.empty()) fl |= BS_POD_OCC_NOREFS;                 // core.go:504-506
-      else if (joined_sorted(p.owner_uids) != occupied[g]) fl |= BS_POD_OCC_MISMATCH;  // core.go:507-510
+  // Only pods of one group interact, and within a group Compare's key reduces to (priority desc, timestamp asc)
+  // with arrival order on ties — so the pods are bucketed by group (counting sort, arrival order kept) and every
+  // group replays its own few pods in queue order, groups in parallel.
+  {
+    std::vector<uint32_t> start((size_t)G + 1, 0);
+    for (uint32_t i = 0; i < P; ++i)
+      if (ps.gid[i] >= 0) ++start[(size_t)ps.gid[i] + 1];
+    for (uint32_t g = 0; g < G; ++g) start[g + 1] += start[g];
+    std::vector<uint32_t> bucket(start[G]);
+    {
+      std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+      for (uint32_t i = 0; i < P; ++i)
+        if (ps.gid[i] >= 0) bucket[fill[ps.gid[i]]++] = i;
     }
-    ps.pod_flags[i] = fl;
+#pragma omp parallel for num_threads(T) schedule(dynamic, 2048)
+    for (uint32_t g = 0; g < G; ++g) {
+      uint32_t* b0 = bucket.data() + start[g];
+      uint32_t* b1 = bucket.data() + start[g + 1];
+      if (b0 == b1 || (ps.group_flags[g] & BS_GROUP_DENIED)) continue;   // a frozen group: no pod reaches fillOccupiedObj
+      std::stable_sort(b0, b1, [&](uint32_t x, uint32_t y) {
+        if (ps.priority[x] != ps.priority[y]) return ps.priority[x] > ps.priority[y];
+        return ps.ts_ns[x] < ps.ts_ns[y];
+      });
+      std::string occ = groups[g].pg->occupied_by;
+      for (uint32_t* q = b0; q != b1; ++q) {
+        const uint32_t i = *q;
+        uint8_t fl = ps.pod_flags[i];
+        if (fl & BS_POD_PERMITTED_RECENTLY) continue;
+        const Pod& p = *pending[i];
+        if (occ.empty()) {
+          if (!p.owner_uids.empty()) occ = joined_sorted(p.owner_uids);             // core.go:496-500
+        } else if (p.owner_uids.empty()) fl |= BS_POD_OCC_NOREFS;                   // core.go:504-506
+        else if (joined_sorted(p.owner_uids) != occ) fl |= BS_POD_OCC_MISMATCH;    // core.go:507-510
+        ps.pod_flags[i] = fl;
+      }
+    }
   }
   phase("occupancy");
   return Status{};

@@ -7,10 +7,13 @@
 //   readme_replay     : the same race in one call (all pods pending, the device walks the queue)
 //   pack_affinity [k] : required nodeAffinity terms -> affinity classes + verdict bits; k > 64 extra selector pairs (CPU)
 //   bench_pack N P G  : packer throughput on synthetic objects                   (CPU)
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
+#include <random>
 #include <vector>
 
 #include "../../batch-scheduler_b200/csrc/plugin.hpp"
@@ -574,6 +577,101 @@ static int cmd_pack_affinity(int many) {
   return 0;
 }
 
+// Randomised check of the packer's three order-dependent parts against a direct restatement written here:
+// group lookup by "ns/name" (first row with a name wins), bare-name ranks (byte-wise ascending, equal names share
+// a rank), and fillOccupiedObj's OccupiedBy rule replayed in QUEUE order over the whole pod list (global stable sort
+// by Compare's key, core.go:368-411, then the sequential rule of core.go:494-511).
+static int cmd_pack_occupancy_random(int seeds) {
+  int bad = 0, flagged = 0, total = 0;
+  for (int seed = 0; seed < seeds; ++seed) {
+    std::mt19937_64 rng(1234 + seed);
+    auto rnd = [&](uint64_t n) { return (uint32_t)(rng() % n); };
+    const uint32_t G = 5 + rnd(60), P = 50 + rnd(900);
+    Node n0; n0.name = "n0"; n0.allocatable = {{"cpu", "64"}, {"memory", "64Gi"}, {"pods", "110"}};
+    NodeInfo i0; i0.node = &n0;
+    std::vector<const NodeInfo*> snap = {&i0};
+    static const char* kNames[] = {"a", "ab", "abcdefgh", "abcdefghi", "abcdefghj", "abcdefgh\x01", "zz", "Z", "pg-1", "pg-10", "pg-2"};
+    std::vector<PodGroup> groups(G);
+    for (uint32_t g = 0; g < G; ++g) {
+      groups[g].ns = rnd(3) ? "default" : "other";
+      groups[g].name = rnd(3) ? std::string(kNames[rnd(11)]) : "grp-" + std::to_string(rnd(G));   // duplicates on purpose
+      groups[g].min_member = 1 + rnd(4);
+      groups[g].creation_ns = 1000 + rnd(4);            // many ties: the name decides
+      if (rnd(5) == 0) groups[g].occupied_by = rnd(2) ? "u1,u2" : "u3";
+    }
+    std::vector<uint8_t> gflags(G, 0), pflags(P, 0);
+    for (uint32_t g = 0; g < G; ++g) if (rnd(7) == 0) gflags[g] = BS_GROUP_DENIED;
+    std::vector<Pod> pods(P);
+    for (uint32_t i = 0; i < P; ++i) {
+      Pod& p = pods[i];
+      p.ns = rnd(4) ? "default" : "other"; p.name = "pod-" + std::to_string(i); p.uid = "uid-" + std::to_string(i);
+      const uint32_t pick = rnd(G + 2);
+      if (pick < G) p.labels[kPodGroupLabel] = groups[pick].name;     // may resolve to another row of the same full name
+      else if (pick == G) p.labels[kPodGroupLabel] = "no-such-group";
+      switch (rnd(4)) {
+        case 0: break;
+        case 1: p.owner_uids = {"u2", "u1"}; break;
+        case 2: p.owner_uids = {"u3"}; break;
+        default: p.owner_uids = {"u1", "u2"}; break;
+      }
+      p.priority = (int32_t)rnd(3) - 1; p.queue_ts_ns = rnd(6);
+      if (rnd(9) == 0) pflags[i] = BS_POD_PERMITTED_RECENTLY;
+      Container c; c.requests = {{"cpu", "100m"}}; p.containers = {c};
+    }
+    std::vector<const Pod*> pending(P);
+    for (uint32_t i = 0; i < P; ++i) pending[i] = &pods[i];
+    PackedSnapshot ps;
+    Status st = BatchSchedulingPlugin::Pack(snap, pending, groups, {}, gflags, pflags, 0, &ps);
+    if (!st.ok()) { fprintf(stderr, "pack failed: %s\n", st.message.c_str()); return 1; }
+    // ---- restatement
+    std::map<std::string, uint32_t> index;
+    for (uint32_t g = 0; g < G; ++g) index.emplace(groups[g].ns + "/" + groups[g].name, g);
+    std::vector<int32_t> gid(P, BS_GID_NONE);
+    for (uint32_t i = 0; i < P; ++i) {
+      auto lab = pods[i].labels.find(kPodGroupLabel);
+      if (lab == pods[i].labels.end()) continue;
+      auto it = index.find(pods[i].ns + "/" + lab->second);
+      gid[i] = it == index.end() ? BS_GID_MISSING : (int32_t)it->second;
+    }
+    std::vector<std::string> names;
+    for (auto& g : groups) names.push_back(g.name);
+    std::sort(names.begin(), names.end());
+    names.erase(std::unique(names.begin(), names.end()), names.end());
+    std::vector<uint32_t> order;
+    for (uint32_t i = 0; i < P; ++i) if (gid[i] >= 0) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      if (pods[a].priority != pods[b].priority) return pods[a].priority > pods[b].priority;
+      const PodGroup& ga = groups[gid[a]]; const PodGroup& gb = groups[gid[b]];
+      if (ga.creation_ns != gb.creation_ns) return ga.creation_ns < gb.creation_ns;
+      if (ga.name != gb.name) return ga.name > gb.name;
+      return pods[a].queue_ts_ns < pods[b].queue_ts_ns;
+    });
+    std::vector<std::string> occ(G);
+    for (uint32_t g = 0; g < G; ++g) occ[g] = groups[g].occupied_by;
+    std::vector<uint8_t> want(P);
+    for (uint32_t i = 0; i < P; ++i) want[i] = pflags[i] | (gid[i] == BS_GID_MISSING ? BS_POD_LISTER_MISS : 0);
+    auto joined = [](std::vector<std::string> v) { std::sort(v.begin(), v.end()); std::string r; for (size_t k = 0; k < v.size(); ++k) { if (k) r += ","; r += v[k]; } return r; };
+    for (uint32_t i : order) {
+      const uint32_t g = (uint32_t)gid[i];
+      if ((pflags[i] & BS_POD_PERMITTED_RECENTLY) || (gflags[g] & BS_GROUP_DENIED)) continue;
+      if (occ[g].empty()) { if (!pods[i].owner_uids.empty()) occ[g] = joined(pods[i].owner_uids); }
+      else if (pods[i].owner_uids.empty()) want[i] |= BS_POD_OCC_NOREFS;
+      else if (joined(pods[i].owner_uids) != occ[g]) want[i] |= BS_POD_OCC_MISMATCH;
+    }
+    for (uint32_t i = 0; i < P; ++i) {
+      ++total;
+      if (want[i] & (BS_POD_OCC_NOREFS | BS_POD_OCC_MISMATCH)) ++flagged;
+      if (ps.gid[i] != gid[i] || ps.pod_flags[i] != want[i]) ++bad;
+    }
+    for (uint32_t g = 0; g < G; ++g) {
+      const uint32_t r = (uint32_t)(std::lower_bound(names.begin(), names.end(), groups[g].name) - names.begin());
+      if (ps.name_rank[g] != r) ++bad;
+    }
+  }
+  printf("{\"seeds\": %d, \"pods\": %d, \"flagged\": %d, \"mismatches\": %d}\n", seeds, total, flagged, bad);
+  return 0;
+}
+
 static int cmd_bench_pack(int N, int P, int G) {
   std::vector<Node> nodes(N);
   std::vector<NodeInfo> infos(N);
@@ -635,6 +733,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "gang_timeout")) return cmd_gang_timeout();
   if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
   if (!strcmp(argv[1], "pack_affinity")) return cmd_pack_affinity(argc >= 3 ? atoi(argv[2]) : 0);
+  if (!strcmp(argv[1], "pack_occupancy_random")) return cmd_pack_occupancy_random(argc >= 3 ? atoi(argv[2]) : 20);
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
   return 2;
 }

@@ -114,6 +114,14 @@ def test_packer_group_delta_rows(plugin_bin):
     assert o["rep_ok"] == 1 and o["full_on_new_selector"] == 1 and o["full_on_new_scalar"] == 1
 
 
+def test_packer_occupancy_lookup_ranks_randomised(plugin_bin):
+    """The packer's order-dependent parts on 40 random object sets (duplicate and prefix-sharing group names, ties in
+    every key field, frozen groups, recently permitted pods): group lookup, bare-name ranks and the OccupiedBy rule of
+    fillOccupiedObj (core.go:494-511) replayed in queue order, against a direct restatement over the whole pod list."""
+    o = _run(plugin_bin, "pack_occupancy_random", "40")
+    assert o["mismatches"] == 0 and o["flagged"] > 500 and o["pods"] > 10000
+
+
 def test_packer_throughput_smoke(plugin_bin):
     out = _run(plugin_bin, "bench_pack", "500", "4000", "500")
     assert out["lanes"] == 5 and out["pack_ms"] > 0
