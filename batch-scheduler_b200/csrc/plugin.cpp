@@ -806,6 +806,8 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   std::vector<PackGroupIn> gin;
   group_names_ = names;
   group_row_.clear();
+  group_row_.reserve(Gn);
+  gin.reserve(Gn);
   {
     uint32_t g = 0;
     for (auto& kv : groups_) {
@@ -817,10 +819,20 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   std::vector<uint8_t> pflags(pending.size(), 0);
   std::vector<uint64_t> uid_ids(pending.size()), name_ids(pending.size());
   pod_row_.clear();
-  for (size_t i = 0; i < pending.size(); ++i) {
-    pod_row_[pending[i]->uid] = (uint32_t)i;
-    uid_ids[i] = IdOf(pending[i]->uid);
-    name_ids[i] = IdOf(pending[i]->ns + "/" + pending[i]->name);
+  pod_row_.reserve(pending.size());
+  for (size_t i = 0; i < pending.size(); ++i) pod_row_[pending[i]->uid] = (uint32_t)i;
+  {
+    // ids of the uids and of "ns/name" (FNV-1a streams: hashing ns, '/', name in turn equals hashing the joined string)
+    const int T = pack_threads(pending.size());
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (size_t i = 0; i < pending.size(); ++i) {
+      uid_ids[i] = IdOf(pending[i]->uid);
+      uint64_t h = 1469598103934665603ull;
+      for (unsigned char c : pending[i]->ns) { h ^= c; h *= 1099511628211ull; }
+      h ^= (unsigned char)'/'; h *= 1099511628211ull;
+      for (unsigned char c : pending[i]->name) { h ^= c; h *= 1099511628211ull; }
+      name_ids[i] = h;
+    }
   }
   if (eng_ && state_ready_ && !pending.empty()) {
     std::vector<uint8_t> perm(pending.size());
@@ -829,6 +841,7 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
       if (perm[i]) pflags[i] |= BS_POD_PERMITTED_RECENTLY;
   }
   node_row_.clear();
+  node_row_.reserve(snapshot.size());
   node_names_.assign(snapshot.size(), std::string());
   for (size_t i = 0; i < snapshot.size(); ++i)
     if (snapshot[i] && snapshot[i]->node) {
