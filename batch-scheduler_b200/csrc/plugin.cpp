@@ -780,22 +780,43 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
   const double t0 = now_ms();
   std::lock_guard<std::mutex> lk(mu_);
   now_ns_ = now_ns;
+  const bool prof = getenv("BS_PACK_PROFILE") != nullptr;
+  double tp = t0;
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    const double t = now_ms();
+    fprintf(stderr, "[begin] %-12s %.2f ms\n", what, t - tp);
+    tp = t;
+  };
   // the group table of this round (canonical order = the map's) and how it continues the last one's rows
-  std::vector<std::string> names;
-  std::vector<int32_t> old_index;
-  names.reserve(groups_.size());
+  // (the usual cycle has the same PodGroups as the last one: one pass of string compares, nothing rebuilt)
   bool same = group_names_.size() == groups_.size();
-  for (auto& kv : groups_) {
-    auto it = group_row_.find(kv.first);
-    old_index.push_back(it == group_row_.end() ? -1 : (int32_t)it->second);
-    same = same && old_index.back() == (int32_t)names.size();
-    names.push_back(kv.first);
+  if (same) {
+    size_t i = 0;
+    for (auto& kv : groups_)
+      if (kv.first != group_names_[i++]) { same = false; break; }
   }
-  const uint32_t Gn = (uint32_t)names.size();
-  if (eng_ && state_ready_ && !same) {
-    const int rc = bs_state_remap(eng_, Gn, old_index.data());
-    if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+  const uint32_t Gn = (uint32_t)groups_.size();
+  if (!same) {
+    std::vector<std::string> names;
+    std::vector<int32_t> old_index;
+    names.reserve(Gn);
+    old_index.reserve(Gn);
+    for (auto& kv : groups_) {
+      auto it = group_row_.find(kv.first);
+      old_index.push_back(it == group_row_.end() ? -1 : (int32_t)it->second);
+      names.push_back(kv.first);
+    }
+    if (eng_ && state_ready_) {
+      const int rc = bs_state_remap(eng_, Gn, old_index.data());
+      if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
+    }
+    group_names_.swap(names);
+    group_row_.clear();
+    group_row_.reserve(Gn);
+    for (uint32_t g = 0; g < Gn; ++g) group_row_[group_names_[g]] = g;
   }
+  lap("group names");
   // the engine's TTL tables as of now: matched counts, pgs.Scheduled, deny list, recently permitted uids
   std::vector<uint32_t> st_matched(Gn, 0);
   std::vector<uint8_t> st_flags(Gn, 0);
@@ -804,26 +825,22 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
     if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
   }
   std::vector<PackGroupIn> gin;
-  group_names_ = names;
-  group_row_.clear();
-  group_row_.reserve(Gn);
   gin.reserve(Gn);
   {
     uint32_t g = 0;
     for (auto& kv : groups_) {
       GroupState& gs = kv.second;
       gin.push_back(PackGroupIn{&gs.pg, st_matched[g], st_flags[g], gs.has_pod ? &gs.rep_pod : nullptr});
-      group_row_[kv.first] = g++;
+      ++g;
     }
   }
+  lap("group rows");
   std::vector<uint8_t> pflags(pending.size(), 0);
   std::vector<uint64_t> uid_ids(pending.size()), name_ids(pending.size());
-  pod_row_.clear();
-  pod_row_.reserve(pending.size());
-  for (size_t i = 0; i < pending.size(); ++i) pod_row_[pending[i]->uid] = (uint32_t)i;
+  const int T = pack_threads(pending.size());
+  pod_row_.build(pending.size(), [&](size_t i) { return &pending[i]->uid; }, T);
   {
     // ids of the uids and of "ns/name" (FNV-1a streams: hashing ns, '/', name in turn equals hashing the joined string)
-    const int T = pack_threads(pending.size());
 #pragma omp parallel for num_threads(T) schedule(static)
     for (size_t i = 0; i < pending.size(); ++i) {
       uid_ids[i] = IdOf(pending[i]->uid);
@@ -834,22 +851,22 @@ Status BatchSchedulingPlugin::BeginRound(const std::vector<const NodeInfo*>& sna
       name_ids[i] = h;
     }
   }
+  lap("pod rows+ids");
   if (eng_ && state_ready_ && !pending.empty()) {
     std::vector<uint8_t> perm(pending.size());
     bs_permitted_view(eng_, now_ns, uid_ids.data(), (uint32_t)pending.size(), perm.data());
     for (size_t i = 0; i < pending.size(); ++i)
       if (perm[i]) pflags[i] |= BS_POD_PERMITTED_RECENTLY;
   }
-  node_row_.clear();
-  node_row_.reserve(snapshot.size());
+  node_row_.build(snapshot.size(), [&](size_t i) { return snapshot[i] && snapshot[i]->node ? &snapshot[i]->node->name : nullptr; },
+                  pack_threads(snapshot.size()));
   node_names_.assign(snapshot.size(), std::string());
   for (size_t i = 0; i < snapshot.size(); ++i)
-    if (snapshot[i] && snapshot[i]->node) {
-      node_row_[snapshot[i]->node->name] = (uint32_t)i;
-      node_names_[i] = snapshot[i]->node->name;
-    }
+    if (snapshot[i] && snapshot[i]->node) node_names_[i] = snapshot[i]->node->name;
+  lap("node rows");
   Status st = pack_impl(snapshot, pending, gin, pflags, max_schedule_time_ns_, &packed_);
   if (!st.ok()) return st;
+  lap("pack_impl");
   last_pack_ms_ = now_ms() - t0;
 
   const double t1 = now_ms();
@@ -1185,10 +1202,10 @@ Status BatchSchedulingPlugin::ReplayQueue(std::vector<ReplayDecision>* out) {
 }
 
 Status BatchSchedulingPlugin::PreFilter(const Pod& pod) {
-  auto it = pod_row_.find(pod.uid);
-  if (it == pod_row_.end()) return Status{BS_CODE_ERROR, "pod is not part of the current round"};
+  const int32_t row = pod_row_.find(pod.uid);
+  if (row < 0) return Status{BS_CODE_ERROR, "pod is not part of the current round"};
   bs_status st{};
-  int rc = bs_prefilter(eng_, it->second, &st);
+  int rc = bs_prefilter(eng_, (uint32_t)row, &st);
   if (rc) return Status{BS_CODE_ERROR, bs_strerror(rc)};
   if (st.reason == BS_PF_PASS) return Status{};                                 // batchscheduler.go:107
   std::string ns_name, occ;
@@ -1203,18 +1220,18 @@ Status BatchSchedulingPlugin::PreFilter(const Pod& pod) {
 std::pair<Status, int64_t> BatchSchedulingPlugin::Permit(const Pod& pod, const std::string& node_name,
                                                          bool* start_signal) {
   if (start_signal) *start_signal = false;
-  std::unordered_map<std::string, uint32_t>::const_iterator it, nt;
+  int32_t row, nrow;
   {
     std::lock_guard<std::mutex> lk(mu_);
-    it = pod_row_.find(pod.uid);
-    nt = node_row_.find(node_name);
-    if (it == pod_row_.end() || nt == node_row_.end())
+    row = pod_row_.find(pod.uid);
+    nrow = node_row_.find(node_name);
+    if (row < 0 || nrow < 0)
       return {Status{BS_CODE_ERROR, "pod or node is not part of the current round"}, 0};
   }
   bs_permit_result r{};
   // core.Permit with its bookkeeping (MatchedPodNodes.Set, the name -> uid de-dup of core.go:286-296, PodNameUIDs.Set,
   // ready on the live count, pgs.Scheduled) against the engine's TTL tables
-  int rc = bs_permit_at(eng_, it->second, nt->second, now_ns_, &r);
+  int rc = bs_permit_at(eng_, (uint32_t)row, (uint32_t)nrow, now_ns_, &r);
   if (rc) return {Status{BS_CODE_ERROR, bs_strerror(rc)}, 0};
   if (r.code == BS_CODE_UNSCHEDULABLE) {
     auto lab = pod.labels.find(kPodGroupLabel);
@@ -1230,12 +1247,11 @@ std::pair<Status, int64_t> BatchSchedulingPlugin::Permit(const Pod& pod, const s
 }
 
 Status BatchSchedulingPlugin::Filter(const Pod& pod, const std::string& node_name) {
-  auto it = pod_row_.find(pod.uid);
-  auto nt = node_row_.find(node_name);
-  if (it == pod_row_.end() || nt == node_row_.end())
+  const int32_t row = pod_row_.find(pod.uid), nrow = node_row_.find(node_name);
+  if (row < 0 || nrow < 0)
     return Status{BS_CODE_ERROR, "pod or node is not part of the current round"};
   bs_status st{};
-  int rc = bs_filter(eng_, it->second, nt->second, &st);
+  int rc = bs_filter(eng_, (uint32_t)row, (uint32_t)nrow, &st);
   if (rc) return Status{BS_CODE_ERROR, std::string("bsched: ") + bs_strerror(rc)};
   auto lab = pod.labels.find(kPodGroupLabel);
   const std::string pg_name = lab != pod.labels.end() ? lab->second : std::string();

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <map>
 #include <mutex>
+#include <cstring>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -153,6 +154,68 @@ struct PackedSnapshot {
   bs_group_table group_table() const;
 };
 
+// string -> row index of one round, built in one go: the keys are copied into ONE arena (no allocation per key),
+// hashed in parallel, and a later duplicate overwrites an earlier one, as `map[key] = row` in a loop would.
+// Lookups are exact (the arena bytes are compared), not by hash alone.
+class StrIndex {
+ public:
+  // key_at(i) -> const std::string* (nullptr: row i has no key)
+  template <class KeyAt>
+  void build(size_t n, KeyAt key_at, int threads) {
+    off_.assign(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) {
+      const std::string* k = key_at(i);
+      off_[i + 1] = off_[i] + (k ? k->size() + 1 : 0);   // +1: a present key owns at least one byte (empty != absent)
+    }
+    chars_.resize(off_[n]);
+    std::vector<uint64_t> h(n);
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+      const std::string* k = key_at(i);
+      if (!k) continue;
+      char* dst = chars_.data() + off_[i];
+      std::memcpy(dst, k->data(), k->size());
+      dst[k->size()] = 0;
+      h[i] = hash(k->data(), k->size());
+    }
+    size_t cap = 16;
+    while (cap < 2 * n) cap <<= 1;
+    slot_.assign(cap, kNone);
+    mask_ = (uint32_t)(cap - 1);
+    for (size_t i = 0; i < n; ++i) {
+      if (off_[i + 1] == off_[i]) continue;
+      uint32_t s = (uint32_t)h[i] & mask_;
+      while (slot_[s] != kNone && !equal(slot_[s], chars_.data() + off_[i], off_[i + 1] - off_[i] - 1)) s = (s + 1) & mask_;
+      slot_[s] = (uint32_t)i;   // empty slot, or the same key again: the later row wins
+    }
+  }
+  int32_t find(const std::string& k) const {
+    if (slot_.empty()) return -1;
+    uint32_t s = (uint32_t)hash(k.data(), k.size()) & mask_;
+    while (slot_[s] != kNone) {
+      if (equal(slot_[s], k.data(), k.size())) return (int32_t)slot_[s];
+      s = (s + 1) & mask_;
+    }
+    return -1;
+  }
+  void clear() { off_.clear(); chars_.clear(); slot_.clear(); mask_ = 0; }
+
+ private:
+  static constexpr uint32_t kNone = 0xffffffffu;
+  static uint64_t hash(const char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+    return h ^ (h >> 32);
+  }
+  bool equal(uint32_t row, const char* p, size_t n) const {
+    return off_[row + 1] - off_[row] - 1 == n && std::memcmp(chars_.data() + off_[row], p, n) == 0;
+  }
+  std::vector<size_t> off_;
+  std::vector<char> chars_;
+  std::vector<uint32_t> slot_;
+  uint32_t mask_ = 0;
+};
+
 class BatchSchedulingPlugin {
  public:
   // batch.New (batchscheduler.go:377): max_schedule_time from the plugin args (Configuration, :71-75)
@@ -277,8 +340,8 @@ class BatchSchedulingPlugin {
   std::mutex mu_;                                                   // guards the maps against concurrent Less / Permit
   // last round
   PackedSnapshot packed_;
-  std::unordered_map<std::string, uint32_t> pod_row_;               // uid -> pending index
-  std::unordered_map<std::string, uint32_t> node_row_;              // node name -> snapshot index
+  StrIndex pod_row_;                                                // uid -> pending index
+  StrIndex node_row_;                                               // node name -> snapshot index
   std::vector<std::string> group_names_;                            // table index -> "ns/name"
   std::unordered_map<std::string, uint32_t> group_row_;             // "ns/name" -> table index
   std::vector<uint8_t> prefilter_, admit_, new_denied_;

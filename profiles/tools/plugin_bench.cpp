@@ -6,7 +6,7 @@
 //   delta round: 1 % of the NodeInfos and 1 % of the PodGroups changed since the last cycle ->
 //                UpdateNodes + UpdateGroups (row re-pack, device scatter, re-evaluation, fetch).
 // Objects have the shape of BASELINE.json configs[3] (100k pods / 10k nodes / 50k groups, scaled by argv[1]).
-//   usage: plugin_bench [scale] [device]
+//   usage: plugin_bench [scale] [device] [pack]     ("pack": host part of BeginRound only — runs without a GPU)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +24,7 @@ static double now_ms() {
 int main(int argc, char** argv) {
   const double scale = argc > 1 ? atof(argv[1]) : 1.0;
   const int device = argc > 2 ? atoi(argv[2]) : 0;
+  const bool pack_only = argc > 3 && std::string(argv[3]) == "pack";
   const int N = std::max(1, (int)(10000 * scale)), P = std::max(1, (int)(100000 * scale)), G = std::max(1, (int)(50000 * scale));
   std::vector<Node> nodes(N);
   std::vector<NodeInfo> infos(N);
@@ -76,9 +77,13 @@ int main(int argc, char** argv) {
     const double t0 = now_ms();
     Status st = plugin.BeginRound(snap, pend, now);
     const double t1 = now_ms();
-    if (!st.ok()) { fprintf(stderr, "BeginRound: %s\n", st.message.c_str()); return 1; }
+    if (!st.ok() && !pack_only) { fprintf(stderr, "BeginRound: %s\n", st.message.c_str()); return 1; }
     if (it >= 2) { full += t1 - t0; pack += plugin.last_pack_ms(); dev += plugin.last_device_ms(); }
     now += 100000000ll;
+  }
+  if (pack_only) {   // everything BeginRound does on the host before it needs the device
+    printf("{\"nodes\": %d, \"pods\": %d, \"groups\": %d, \"pack_ms\": %.3f, \"iters\": %d}\n", N, P, G, pack / iters, iters);
+    return 0;
   }
   // delta rounds: 1 % of the nodes (a pod was bound: requested grows) and 1 % of the groups (Status.Scheduled moved)
   const int dn = std::max(1, N / 100), dg = std::max(1, G / 100);

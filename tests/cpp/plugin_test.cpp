@@ -14,6 +14,7 @@
 #include <string>
 #include <map>
 #include <random>
+#include <unordered_map>
 #include <vector>
 
 #include "../../batch-scheduler_b200/csrc/plugin.hpp"
@@ -672,6 +673,42 @@ static int cmd_pack_occupancy_random(int seeds) {
   return 0;
 }
 
+// StrIndex (plugin.hpp: uid -> pod row, node name -> snapshot row of a round) against std::unordered_map filled
+// with `m[key] = row` in row order: duplicates (the later row wins), empty keys, rows without a key, keys that are
+// prefixes of one another, lookups of absent keys.
+static int cmd_strindex(int seeds) {
+  int bad = 0, checked = 0;
+  for (int seed = 0; seed < seeds; ++seed) {
+    std::mt19937_64 rng(99 + seed);
+    const size_t n = seed == 0 ? 0 : 1 + rng() % 5000;
+    std::vector<std::string> keys(n);
+    std::vector<char> present(n, 1);
+    for (size_t i = 0; i < n; ++i) {
+      const uint32_t kind = rng() % 10;
+      if (kind == 0) present[i] = 0;
+      else if (kind == 1) keys[i] = "";
+      else if (kind < 5) keys[i] = "uid-" + std::to_string(rng() % (n / 2 + 1));       // duplicates
+      else if (kind < 7) keys[i] = std::string(1 + rng() % 40, (char)('a' + rng() % 3));  // prefixes of one another
+      else { keys[i].resize(1 + rng() % 24); for (auto& c : keys[i]) c = (char)(rng() % 256); }  // arbitrary bytes, NULs too
+    }
+    StrIndex ix;
+    ix.build(n, [&](size_t i) { return present[i] ? &keys[i] : nullptr; }, 1 + seed % 4);
+    std::unordered_map<std::string, uint32_t> ref;
+    for (size_t i = 0; i < n; ++i) if (present[i]) ref[keys[i]] = (uint32_t)i;
+    for (auto& kv : ref) { ++checked; if (ix.find(kv.first) != (int32_t)kv.second) ++bad; }
+    for (int q = 0; q < 200; ++q) {
+      std::string probe = q % 2 ? "uid-" + std::to_string(rng() % (2 * n + 3)) : std::string(1 + rng() % 45, (char)('a' + rng() % 4));
+      auto it = ref.find(probe);
+      ++checked;
+      if (ix.find(probe) != (it == ref.end() ? -1 : (int32_t)it->second)) ++bad;
+    }
+    ix.clear();
+    if (ix.find("x") != -1) ++bad;
+  }
+  printf("{\"seeds\": %d, \"checked\": %d, \"mismatches\": %d}\n", seeds, checked, bad);
+  return 0;
+}
+
 static int cmd_bench_pack(int N, int P, int G) {
   std::vector<Node> nodes(N);
   std::vector<NodeInfo> infos(N);
@@ -733,6 +770,7 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "gang_timeout")) return cmd_gang_timeout();
   if (!strcmp(argv[1], "readme_replay")) return cmd_readme_replay();
   if (!strcmp(argv[1], "pack_affinity")) return cmd_pack_affinity(argc >= 3 ? atoi(argv[2]) : 0);
+  if (!strcmp(argv[1], "strindex")) return cmd_strindex(argc >= 3 ? atoi(argv[2]) : 30);
   if (!strcmp(argv[1], "pack_occupancy_random")) return cmd_pack_occupancy_random(argc >= 3 ? atoi(argv[2]) : 20);
   if (!strcmp(argv[1], "bench_pack") && argc >= 5) return cmd_bench_pack(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
   return 2;

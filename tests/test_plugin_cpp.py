@@ -122,6 +122,13 @@ def test_packer_occupancy_lookup_ranks_randomised(plugin_bin):
     assert o["mismatches"] == 0 and o["flagged"] > 500 and o["pods"] > 10000
 
 
+def test_round_row_index(plugin_bin):
+    """StrIndex, the uid -> pod row / node name -> snapshot row lookup PreFilter, Filter and Permit go through, against a
+    std::unordered_map filled in row order: duplicates (later row wins), empty and absent keys, arbitrary bytes."""
+    o = _run(plugin_bin, "strindex", "60")
+    assert o["mismatches"] == 0 and o["checked"] > 50000
+
+
 def test_packer_throughput_smoke(plugin_bin):
     out = _run(plugin_bin, "bench_pack", "500", "4000", "500")
     assert out["lanes"] == 5 and out["pack_ms"] > 0
